@@ -1,0 +1,171 @@
+/* stark_verifier_b200.h -- C ABI of the B200-native batch FRI query-phase verifier.
+ *
+ * The reference (DoHoonKim8/stark-verifier, crate `semaphore_aggregation`) has NO FFI today; this
+ * header is the extern "C" seam a maintainer would bind from Rust.  Each entry
+ * point names the reference interface it replaces (paths relative to src/plonky2_verifier/).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; the caller owns every input/output buffer; the library owns
+ *    only `sv_ctx` (CUDA stream, staging buffers, constant tables);
+ *  - return value: 0 = ok, < 0 = error (bad shape / CUDA failure); `sv_last_error` gives text;
+ *  - an INVALID PROOF IS DATA, NOT AN ERROR: bit i of the accept bitmap says whether proof i was
+ *    accepted (reference: panic / failed MockProver, verifier_api.rs:50-51);
+ *  - every field element is a canonical little-endian u64 < p = 2^64 - 2^32 + 1; a non-canonical
+ *    word anywhere in a proof rejects that proof (reference: range check in assign_value,
+ *    native_chip/arithmetic_chip.rs:256-268);
+ *  - `mem` says where the data buffers live: SV_MEM_HOST (the call copies H2D in chunks overlapped
+ *    with the kernels, copies the result back and returns when it is in host memory) or
+ *    SV_MEM_DEVICE (pointers are device pointers on the ctx device; the work is enqueued on the
+ *    ctx stream and the call returns without synchronising);
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef STARK_VERIFIER_B200_H
+#define STARK_VERIFIER_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SV_MEM_HOST 0
+#define SV_MEM_DEVICE 1
+
+#define SV_HASH_POSEIDON_GOLDILOCKS 0 /* plonky2 PoseidonHash; constants chip/plonk/gates/poseidon.rs:26-322 */
+#define SV_HASH_POSEIDON_BN254 1      /* bn245_poseidon/*; not implemented yet */
+
+#define SV_MAX_STEPS 32
+
+/* == FriParams + FriConfig (types/common_data.rs:10-54) and the part of FriInstanceInfo
+ *    (types/fri.rs:50-72, types/common_data.rs:153-221) the FRI verifier reads. == */
+typedef struct sv_fri_shape {
+    uint32_t degree_bits;         /* FriParams.degree_bits */
+    uint32_t rate_bits;           /* FriConfig.rate_bits */
+    uint32_t cap_height;          /* FriConfig.cap_height */
+    uint32_t num_query_rounds;    /* FriConfig.num_query_rounds */
+    uint32_t proof_of_work_bits;  /* FriConfig.proof_of_work_bits */
+    uint32_t num_steps;           /* FriParams.reduction_arity_bits.len(); every entry must be 1
+                                     (the reference supports arity 2 only: chip/fri_chip.rs:211) */
+    uint32_t final_poly_len;      /* number of Fp2 coefficients in FriProofValues.final_poly */
+    uint32_t hiding;              /* FriParams.hiding */
+    uint32_t oracle_num_polys[4]; /* FriOracleInfo.num_polys: constants_sigmas, wires, zs_partial_products, quotient */
+    uint32_t oracle_blinding[4];  /* FriOracleInfo.blinding (salted leaf = +4 limbs when hiding) */
+    uint32_t num_zs;              /* batch 1 (opened at g*zeta) = polynomials [0, num_zs) of oracle 2 */
+    uint32_t hash_kind;           /* SV_HASH_* */
+} sv_fri_shape;
+
+/* Flat per-proof record: word (u64) offsets.  Every segment starts on a 4-word (32-byte) boundary
+ * so that digests can be fetched with aligned 128/256-bit loads.
+ *
+ *   header (shared by all query rounds of the proof):
+ *     init_caps    4 x ncap x 4     MerkleCapValues of the 4 initial oracles, in FriInstanceInfo order
+ *                                   (plonk_verifier_chip.rs:212-217)
+ *     step_caps    num_steps x ncap x 4   FriProofValues.commit_phase_merkle_cap_values
+ *     open0        n0 x 2           FriOpenings.batches[0] (order: types/assigned.rs:26-37)
+ *     open1        n1 x 2           FriOpenings.batches[1] (plonk_zs_next)
+ *     final_poly   final_poly_len x 2
+ *     pow_witness  1
+ *     alpha 2, betas num_steps x 2, pow_response 1, indices num_query_rounds   FriChallenges
+ *     zeta 2, zeta_next 2           FriBatchInfo.point of the two batches
+ *   then num_query_rounds x query block (FriQueryRoundValues, types/proof.rs:217):
+ *     for k in 0..4: evals[leaf_len[k]], siblings[init_depth x 4]    (FriInitialTreeProofValues)
+ *     for i in steps: evals[2 x 2], siblings[step_depth[i] x 4]      (FriQueryStepValues)
+ */
+typedef struct sv_fri_layout {
+    uint32_t ncap, lde_bits, n0, n1;
+    uint32_t off_init_caps, off_step_caps, off_open0, off_open1, off_final_poly, off_pow_witness;
+    uint32_t off_alpha, off_betas, off_pow_response, off_indices, off_zeta, off_zeta_next;
+    uint32_t header_words;
+    uint32_t leaf_len[4];
+    uint32_t q_off_init_evals[4], q_off_init_sibs[4], init_depth;
+    uint32_t q_off_step_evals[SV_MAX_STEPS], q_off_step_sibs[SV_MAX_STEPS], step_depth[SV_MAX_STEPS];
+    uint32_t query_words, record_words;
+    /* algorithmic HBM read bytes: unpadded per-query and per-proof-shared payload */
+    uint32_t algo_bytes_per_query, algo_bytes_shared;
+    uint32_t perms_per_query; /* Poseidon permutations per (proof x query) */
+} sv_fri_layout;
+
+/* first-failure codes, ordered like the checks of check_consistency (chip/fri_chip.rs:228-327) */
+enum {
+    SV_OK = 0,
+    SV_FAIL_POW = 1,          /* fri_verify_proof_of_work, fri_chip.rs:364-376 */
+    SV_FAIL_NONCANONICAL = 2, /* a word >= p */
+    SV_FAIL_INIT_MERKLE = 3,  /* verify_initial_merkle_proof, fri_chip.rs:85-110 */
+    SV_FAIL_ZERO_DENOM = 4,   /* div_extension on zero, goldilocks_extension_chip.rs:72-101 */
+    SV_FAIL_STEP_EVAL = 5,    /* evals[x_index_within_coset] != prev_eval, fri_chip.rs:285-292 */
+    SV_FAIL_STEP_MERKLE = 6,  /* step Merkle proof, fri_chip.rs:303-311 */
+    SV_FAIL_FINAL = 7         /* final_poly(x) != prev_eval, fri_chip.rs:317-325 */
+};
+/* first_fail[i] = 0 if proof i is accepted, else (query_round << 8) | code of the FIRST check that
+ * fails in the reference's order (query rounds in order; inside a round: non-canonical word, the 4
+ * initial Merkle proofs, DEEP-quotient division, then per step: eval consistency, fold division,
+ * step Merkle proof; finally the final polynomial).  Per-proof failures (PoW, header word >= p) use
+ * query_round = 0. */
+
+typedef struct sv_ctx sv_ctx;
+
+/* --- context --------------------------------------------------------------------------------- */
+int sv_ctx_create(int device, sv_ctx** out);
+void sv_ctx_destroy(sv_ctx* ctx);
+const char* sv_last_error(const sv_ctx* ctx); /* ctx may be NULL: last error of a failed create */
+/* Use an existing CUDA stream (cudaStream_t cast to void*) for SV_MEM_DEVICE work; NULL restores
+ * the context's own stream. */
+int sv_ctx_set_stream(sv_ctx* ctx, void* cuda_stream);
+int sv_ctx_synchronize(sv_ctx* ctx);
+/* number of kernel launches issued through this context so far */
+uint64_t sv_ctx_launch_count(const sv_ctx* ctx);
+/* pinned host memory for the SV_MEM_HOST path (pageable memory works too, slower) */
+int sv_host_alloc(size_t bytes, void** out);
+int sv_host_free(void* p);
+
+/* --- layout ---------------------------------------------------------------------------------- */
+int sv_fri_layout_make(const sv_fri_shape* shape, sv_fri_layout* out);
+
+/* --- hot path -------------------------------------------------------------------------------- */
+/* n independent width-12 permutations, in[12n] -> out[12n] (in == out allowed).
+ * Replaces: PlonkyPermutation::permute / HasherChip::permutation (chip/hasher_chip.rs:101-105). */
+int sv_poseidon_permute_batch(sv_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, int hash_kind, int mem);
+
+/* n independent Merkle paths against one cap.  paths: n records of (leaf_len + 4*depth) words
+ * (leaf, then siblings bottom-up); indices[n] leaf indices (bit l of the index selects the side at
+ * level l; the bits above `depth` select the cap entry); caps: 2^cap_height x 4 words; ok[n] bytes.
+ * Replaces: MerkleProofChip::verify_merkle_proof_to_cap_with_cap_index (chip/merkle_proof_chip.rs:39-87). */
+int sv_merkle_verify_batch(sv_ctx* ctx, uint32_t leaf_len, uint32_t depth, uint32_t cap_height, int hash_kind,
+                           const uint64_t* paths, const uint64_t* indices, const uint64_t* caps, uint8_t* ok,
+                           size_t n, int mem);
+
+/* Batch FRI query-phase verification: n_proofs flat records (sv_fri_layout.record_words each).
+ * accept_bitmap: ceil(n_proofs/32) u32 words, bit (i & 31) of word i/32 = proof i accepted.
+ * first_fail: optional (NULL to skip), n_proofs u32 (see above).
+ * Replaces: FriVerifierChip::verify_fri_proof (chip/fri_chip.rs:329-362) called once per proof from
+ * PlonkVerifierChip::verify_proof_with_challenges (chip/plonk/plonk_verifier_chip.rs:212-240). */
+int sv_fri_verify_batch(sv_ctx* ctx, const sv_fri_shape* shape, size_t n_proofs, const uint64_t* records,
+                        uint32_t* accept_bitmap, uint32_t* first_fail, int mem);
+
+/* Gather the per-rank accept bitmaps of a sharded batch: ncclAllGather(local -> full) on the ctx
+ * stream.  nccl_comm is an ncclComm_t; libnccl.so.2 is resolved at run time (dlopen).  New -- the
+ * reference is single-process. */
+int sv_allgather_bitmap(sv_ctx* ctx, void* nccl_comm, const uint32_t* local_words, uint32_t* all_words,
+                        size_t words_per_rank);
+
+/* --- host side (CPU): transcript and synthetic proofs ----------------------------------------- */
+/* Fiat-Shamir challenges of one proof, written into the record header (zeta, zeta_next, alpha,
+ * betas, pow_response, indices).  Replaces: PlonkVerifierChip::get_challenges
+ * (chip/plonk/plonk_verifier_chip.rs:55-154) + TranscriptChip + HasherChip::{update,squeeze}. */
+int sv_fri_challenges(const sv_fri_shape* shape, uint64_t* record, const uint64_t circuit_digest[4],
+                      const uint64_t public_inputs_hash[4], uint32_t num_challenges);
+
+/* Synthetic plonky2-shaped proofs (valid by construction), `n_proofs` records written to
+ * records_out.  `n_circuits` distinct committed oracle sets are built from `seed`; proof i uses
+ * circuit i % n_circuits and its own public-input hash, so every proof has its own challenges,
+ * query indices, openings and FRI commit phase.  Stand-in for plonky2's prover
+ * (plonky2_semaphore/*, not on the hot path) -- test/bench data only. */
+int sv_synth_proofs(const sv_fri_shape* shape, uint64_t seed, uint32_t n_circuits, size_t n_proofs,
+                    uint32_t num_challenges, uint64_t* records_out, int nthreads);
+
+/* library / build info */
+const char* sv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

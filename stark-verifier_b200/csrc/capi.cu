@@ -1,0 +1,298 @@
+// C ABI (include/stark_verifier_b200.h): context, launches, host<->device pipeline.
+// No CPU fallback: every compute entry point needs a CUDA device and fails loudly otherwise.
+#include "../../include/stark_verifier_b200.h"
+#include "fri_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace svb;
+
+struct sv_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;   // compute
+    cudaStream_t copy_stream = nullptr;  // H2D of the next chunk
+    cudaStream_t stream = nullptr;       // stream used for SV_MEM_DEVICE work (own or caller's)
+    // device scratch, grown on demand, reused across calls (no hidden allocation after warm-up)
+    u64* d_scratch = nullptr; size_t scratch_words = 0;          // reduced openings
+    u64* d_stage[2] = {nullptr, nullptr}; size_t stage_words[2] = {0, 0}; // H2D chunks (double buffered)
+    u32* d_bitmap = nullptr; size_t bitmap_words = 0;
+    u32* d_fail = nullptr; size_t fail_words = 0;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    uint64_t launches = 0;
+    std::string err;
+    int sm_count = 0;
+    // dlopen'ed NCCL
+    void* nccl_lib = nullptr;
+    int (*ncclAllGather_fn)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+};
+
+static std::string g_create_err;
+
+static int fail(sv_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_err = buf;
+    return code;
+}
+#define CK(c, call)                                                                              \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) return fail((c), -100 - (int)e_, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char* sv_version(void) { return "stark-verifier_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* sv_last_error(const sv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int sv_ctx_create(int device, sv_ctx** out) {
+    if (!out) return -1;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, -2, "no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, -3, "device %d out of range (%d devices)", device, n);
+    CK(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(nullptr, -4, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    sv_ctx* c = new sv_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CK(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CK(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CK(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        CK(nullptr, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return 0;
+}
+
+extern "C" void sv_ctx_destroy(sv_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->d_scratch);
+    cudaFree(c->d_stage[0]);
+    cudaFree(c->d_stage[1]);
+    cudaFree(c->d_bitmap);
+    cudaFree(c->d_fail);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_done[i]); }
+    cudaStreamDestroy(c->own_stream);
+    cudaStreamDestroy(c->copy_stream);
+    if (c->nccl_lib) dlclose(c->nccl_lib);
+    delete c;
+}
+
+extern "C" int sv_ctx_set_stream(sv_ctx* c, void* s) {
+    if (!c) return -1;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+extern "C" int sv_ctx_synchronize(sv_ctx* c) {
+    if (!c) return -1;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaStreamSynchronize(c->own_stream));
+    CK(c, cudaStreamSynchronize(c->copy_stream));
+    return 0;
+}
+extern "C" uint64_t sv_ctx_launch_count(const sv_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int sv_host_alloc(size_t bytes, void** out) {
+    if (!out) return -1;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    return e == cudaSuccess ? 0 : fail(nullptr, -100 - (int)e, "cudaHostAlloc: %s", cudaGetErrorString(e));
+}
+extern "C" int sv_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? 0 : -1; }
+
+template <typename T>
+static int grow(sv_ctx* c, T*& ptr, size_t& have, size_t need) {
+    if (need <= have) return 0;
+    if (ptr) CK(c, cudaFree(ptr));
+    ptr = nullptr; have = 0;
+    CK(c, cudaMalloc((void**)&ptr, need * sizeof(T)));
+    have = need;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int sv_poseidon_permute_batch(sv_ctx* c, const uint64_t* in, uint64_t* out, size_t n, int hash_kind, int mem) {
+    if (!c || !in || !out) return -1;
+    if (hash_kind != SV_HASH_POSEIDON_GOLDILOCKS) return fail(c, -5, "hash_kind %d not implemented", hash_kind);
+    if (n == 0) return 0;
+    CK(c, cudaSetDevice(c->device));
+    const int B = 128;
+    if (mem == SV_MEM_DEVICE) {
+        poseidon_permute_kernel<<<(unsigned)((n + B - 1) / B), B, 0, c->stream>>>(in, out, n);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        return 0;
+    }
+    size_t words = 12 * n;
+    if (grow(c, c->d_stage[0], c->stage_words[0], words)) return -6;
+    cudaStream_t s = c->own_stream;
+    CK(c, cudaMemcpyAsync(c->d_stage[0], in, words * 8, cudaMemcpyHostToDevice, s));
+    poseidon_permute_kernel<<<(unsigned)((n + B - 1) / B), B, 0, s>>>(c->d_stage[0], c->d_stage[0], n);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out, c->d_stage[0], words * 8, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int sv_merkle_verify_batch(sv_ctx* c, uint32_t leaf_len, uint32_t depth, uint32_t cap_height, int hash_kind,
+                                      const uint64_t* paths, const uint64_t* indices, const uint64_t* caps, uint8_t* ok,
+                                      size_t n, int mem) {
+    if (!c || !paths || !indices || !caps || !ok) return -1;
+    if (hash_kind != SV_HASH_POSEIDON_GOLDILOCKS) return fail(c, -5, "hash_kind %d not implemented", hash_kind);
+    if (leaf_len == 0 || depth > 63 || cap_height > 16 || depth + cap_height > 63) return fail(c, -7, "bad merkle shape");
+    if (n == 0) return 0;
+    CK(c, cudaSetDevice(c->device));
+    const int B = 128;
+    size_t rec_words = up4(leaf_len) + 4 * (size_t)depth;
+    if (mem == SV_MEM_DEVICE) {
+        merkle_verify_kernel<<<(unsigned)((n + B - 1) / B), B, 0, c->stream>>>(paths, indices, caps, ok, n, leaf_len, depth, cap_height);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        return 0;
+    }
+    // host buffers: one shot (this entry point is the micro-benchmark path; the FRI entry point pipelines)
+    size_t cap_words = 4ull << cap_height;
+    size_t total = rec_words * n + n + cap_words + (n + 7) / 8 + 4;
+    if (grow(c, c->d_stage[0], c->stage_words[0], total)) return -6;
+    u64* d_paths = c->d_stage[0];
+    u64* d_idx = d_paths + rec_words * n;
+    u64* d_caps = d_idx + n;
+    unsigned char* d_ok = reinterpret_cast<unsigned char*>(d_caps + cap_words);
+    cudaStream_t s = c->own_stream;
+    CK(c, cudaMemcpyAsync(d_paths, paths, rec_words * n * 8, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(d_idx, indices, n * 8, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(d_caps, caps, cap_words * 8, cudaMemcpyHostToDevice, s));
+    merkle_verify_kernel<<<(unsigned)((n + B - 1) / B), B, 0, s>>>(d_paths, d_idx, d_caps, d_ok, n, leaf_len, depth, cap_height);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(ok, d_ok, n, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int make_params(sv_ctx* c, const sv_fri_shape& s, FriKernelParams& P) {
+    memset(&P, 0, sizeof P);
+    if (make_layout(s, P.L)) return fail(c, -8, "bad FRI shape");
+    if (s.hash_kind != SV_HASH_POSEIDON_GOLDILOCKS) return fail(c, -5, "hash_kind %u not implemented", s.hash_kind);
+    if (s.proof_of_work_bits > 63) return fail(c, -8, "proof_of_work_bits > 63");
+    if (s.num_query_rounds >= (1u << 12)) return fail(c, -8, "num_query_rounds too large");
+    P.num_queries = s.num_query_rounds;
+    P.num_steps = s.num_steps;
+    P.final_poly_len = s.final_poly_len;
+    P.pow_bits = s.proof_of_work_bits;
+    for (int k = 0; k < 4; k++) P.oracle_num_polys[k] = s.oracle_num_polys[k];
+    P.num_zs = s.num_zs;
+    P.n_classes = 4 + s.num_steps + 1;
+    // class cost in permutations (algebra ~ 2), heaviest first
+    std::vector<std::pair<u32, u32>> cost;
+    for (u32 k = 0; k < 4; k++) cost.push_back({(P.L.leaf_len[k] > 4 ? (P.L.leaf_len[k] + 7) / 8 : 0) + P.L.init_depth, k});
+    for (u32 i = 0; i < s.num_steps; i++) cost.push_back({P.L.step_depth[i], 4 + i});
+    cost.push_back({2, 4 + s.num_steps});
+    std::stable_sort(cost.begin(), cost.end(), [](const std::pair<u32, u32>& a, const std::pair<u32, u32>& b) { return a.first > b.first; });
+    for (u32 i = 0; i < P.n_classes; i++) P.class_order[i] = cost[i].second;
+    u64 omega = svb::pow(7, (GL_P - 1) >> P.L.lde_bits);
+    for (u32 i = 0; i < P.L.lde_bits; i++) { P.omega_pow2[i] = omega; omega = mulc(omega, omega); }
+    return 0;
+}
+
+// enqueue prepare + query (+ finalize) for `n` proofs whose records are at d_records
+static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_records, u64* d_scratch, u32* d_bitmap,
+                       u32* d_fail, cudaStream_t s) {
+    const int B = 128;
+    P.n_proofs = (u32)n;
+    P.n_units = (u32)(n * P.num_queries);
+    P.blocks_per_class = (P.n_units + B - 1) / B;
+    fri_prepare_kernel<<<(unsigned)((n + B - 1) / B), B, 0, s>>>(d_records, P, d_scratch, d_bitmap, d_fail);
+    fri_query_kernel<<<P.blocks_per_class * P.n_classes, B, 0, s>>>(d_records, P, d_scratch, d_bitmap, d_fail);
+    c->launches += 2;
+    if (d_fail) {
+        fri_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_fail, (u32)n);
+        c->launches++;
+    }
+    CK(c, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sv_fri_verify_batch(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs, const uint64_t* records,
+                                   uint32_t* accept_bitmap, uint32_t* first_fail, int mem) {
+    if (!c || !shape || !records || !accept_bitmap) return -1;
+    FriKernelParams P;
+    int rc = make_params(c, *shape, P);
+    if (rc) return rc;
+    if (n_proofs == 0) return 0;
+    if (n_proofs * (size_t)P.num_queries >= (1ull << 31)) return fail(c, -8, "batch too large for one call");
+    CK(c, cudaSetDevice(c->device));
+    size_t rw = P.L.record_words;
+    if (grow(c, c->d_scratch, c->scratch_words, 4 * n_proofs)) return -6;
+
+    if (mem == SV_MEM_DEVICE) return enqueue_fri(c, P, n_proofs, records, c->d_scratch, accept_bitmap, first_fail, c->stream);
+
+    // Host buffers: chunks of whole 32-proof bitmap words, H2D of chunk i+1 on the copy stream
+    // overlapped with the kernels of chunk i on the compute stream.
+    size_t n_words = (n_proofs + 31) / 32;
+    if (grow(c, c->d_bitmap, c->bitmap_words, n_words)) return -6;
+    if (first_fail && grow(c, c->d_fail, c->fail_words, n_proofs)) return -6;
+    size_t chunk = ((64ull << 20) / (rw * 8)) & ~(size_t)31;   // ~64 MiB per chunk
+    if (chunk < 32) chunk = 32;
+    if (chunk > n_proofs) chunk = (n_proofs + 31) & ~(size_t)31;
+    for (int b = 0; b < 2; b++)
+        if (grow(c, c->d_stage[b], c->stage_words[b], chunk * rw)) return -6;
+    cudaStream_t cs = c->copy_stream, ks = c->own_stream;
+    size_t n_chunks = (n_proofs + chunk - 1) / chunk;
+    for (size_t i = 0; i < n_chunks; i++) {
+        int b = (int)(i & 1);
+        size_t first = i * chunk, cnt = std::min(chunk, n_proofs - first);
+        if (i >= 2) CK(c, cudaStreamWaitEvent(cs, c->ev_done[b], 0));   // buffer b free again
+        CK(c, cudaMemcpyAsync(c->d_stage[b], records + first * rw, cnt * rw * 8, cudaMemcpyHostToDevice, cs));
+        CK(c, cudaEventRecord(c->ev_copied[b], cs));
+        CK(c, cudaStreamWaitEvent(ks, c->ev_copied[b], 0));
+        rc = enqueue_fri(c, P, cnt, c->d_stage[b], c->d_scratch + 4 * first, c->d_bitmap + first / 32,
+                         first_fail ? c->d_fail + first : nullptr, ks);
+        if (rc) return rc;
+        CK(c, cudaEventRecord(c->ev_done[b], ks));
+    }
+    CK(c, cudaMemcpyAsync(accept_bitmap, c->d_bitmap, n_words * 4, cudaMemcpyDeviceToHost, ks));
+    if (first_fail) CK(c, cudaMemcpyAsync(first_fail, c->d_fail, n_proofs * 4, cudaMemcpyDeviceToHost, ks));
+    CK(c, cudaStreamSynchronize(ks));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int sv_allgather_bitmap(sv_ctx* c, void* nccl_comm, const uint32_t* local_words, uint32_t* all_words,
+                                   size_t words_per_rank) {
+    if (!c || !nccl_comm || !local_words || !all_words) return -1;
+    if (!c->ncclAllGather_fn) {
+        c->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!c->nccl_lib) return fail(c, -9, "dlopen libnccl.so.2: %s", dlerror());
+        c->ncclAllGather_fn = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(c->nccl_lib, "ncclAllGather");
+        if (!c->ncclAllGather_fn) return fail(c, -9, "dlsym ncclAllGather failed");
+    }
+    CK(c, cudaSetDevice(c->device));
+    const int ncclUint32 = 3;  // ncclDataType_t: ncclInt8=0, ncclUint8=1, ncclInt32=2, ncclUint32=3
+    int r = c->ncclAllGather_fn(local_words, all_words, words_per_rank, ncclUint32, nccl_comm, c->stream);
+    if (r != 0) return fail(c, -10, "ncclAllGather failed with %d", r);
+    return 0;
+}

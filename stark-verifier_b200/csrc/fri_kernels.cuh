@@ -1,0 +1,301 @@
+// sm_100a kernels of the FRI query-phase verifier.
+//
+// Work decomposition.  A (proof x query) unit of check_consistency (chip/fri_chip.rs:228-327) is
+// 4 + num_steps INDEPENDENT Merkle chains (each: optional leaf sponge, then one two-to-one
+// permutation per level, then a cap compare -- chip/merkle_proof_chip.rs:39-87) plus one short
+// algebra chain (DEEP quotient, folds, final polynomial).  Only the algebra chain is sequential
+// across steps, and it never needs a hash output: the step evals it consumes are proof data, and
+// their authenticity is exactly what the step chains check.  So every chain is its own work item:
+//
+//      work item = (class, unit)      class in { init oracle 0..3, step 0..S-1, algebra }
+//
+// One thread per work item, 32 consecutive units of the SAME class per warp, so a warp runs one
+// instruction stream with no divergence (all lanes hash the same number of levels).  Blocks are
+// ordered heaviest class first so the tail of the grid is made of the short chains.  A failing item
+// clears its proof's accept bit with one atomicAnd (the rare path).
+//
+// Memory.  Records are read straight from global memory with 128-bit read-only loads: a lane reads
+// the 32 B digest of its own query block, i.e. each request touches 32 distinct sectors, all fully
+// used (no over-fetch).  The path is integer-issue bound (~2.5e4 instructions per 32 B sibling), so
+// nothing is staged through shared memory: there is no reuse to exploit and no latency left exposed
+// at >= 8 warps per scheduler.
+#pragma once
+#include "layout.hpp"
+#include "poseidon_g.cuh"
+
+namespace svb {
+
+struct FriKernelParams {
+    sv_fri_layout L;
+    u32 num_queries, num_steps, final_poly_len, pow_bits;
+    u32 oracle_num_polys[4];
+    u32 num_zs;
+    u32 n_proofs;
+    u32 n_units;          // n_proofs * num_queries
+    u32 blocks_per_class; // ceil(n_units / block)
+    u32 n_classes;        // 4 + num_steps + 1
+    u32 class_order[SV_MAX_STEPS + 5];  // heaviest first
+    u64 omega_pow2[40];   // omega^(2^i), omega = 7^((p-1)/2^lde_bits)
+};
+
+SVB_D void ldg4(const u64* p, u64 out[4]) {
+    const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p);
+    ulonglong2 a = __ldg(q), b = __ldg(q + 1);
+    out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+}
+
+SVB_D void report_fail(u32* accept_bitmap, u32* first_fail, u32 proof, u32 query, u32 order_key, u32 code) {
+    atomicAnd(&accept_bitmap[proof >> 5], ~(1u << (proof & 31)));
+    // order key: query-major, then the reference's check order inside the round, code in the low byte
+    if (first_fail) atomicMin(&first_fail[proof], (query << 20) | (order_key << 8) | code);
+}
+
+// One Merkle chain: hash_or_noop(leaf) then `depth` two-to-one levels, compare with cap[cap_index].
+// Returns 0 ok, SV_FAIL_NONCANONICAL, or `merkle_code`.
+// Written as ONE loop over "absorb a block, permute" so the kernel holds a single inlined copy of
+// the permutation: iterations [0, n_sponge) overwrite the rate lanes with the next leaf chunk
+// (overwrite-mode sponge, rate 8: hasher_chip.rs:122-148), iterations [n_sponge, n_sponge+depth)
+// compress with the sibling of that level on a fresh capacity (merkle_proof_chip.rs:58-71).
+SVB_D u32 merkle_chain(const u64* __restrict__ leaf, u32 leaf_len, const u64* __restrict__ sibs, u32 depth,
+                       u64 index, const u64* __restrict__ cap_entry, u32 merkle_code) {
+    u64 s[12];
+    bool canon_ok = true;
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    u32 n_sponge = 0;
+    if (leaf_len <= 4) {
+        // hash_or_noop: the leaf IS the digest (merkle_proof_chip.rs:52-53); segments are 4-word padded
+        u64 w[4];
+        ldg4(leaf, w);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            s[i] = (u32)i < leaf_len ? w[i] : 0;
+            canon_ok &= is_canonical(s[i]);
+        }
+    } else {
+        n_sponge = (leaf_len + 7) >> 3;
+    }
+    const u32 n_iter = n_sponge + depth;
+#pragma unroll 1
+    for (u32 it = 0; it < n_iter; it++) {
+        if (it < n_sponge) {
+            u32 off = it * 8, rem = leaf_len - off;
+            u64 w[8];
+            ldg4(leaf + off, w);
+            if (rem > 4) ldg4(leaf + off + 4, w + 4);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if ((u32)i < rem) {
+                    s[i] = w[i];
+                    canon_ok &= is_canonical(w[i]);
+                }
+        } else {
+            u32 lvl = it - n_sponge;
+            u64 sib[4];
+            ldg4(sibs + 4 * lvl, sib);
+            bool bit = (index >> lvl) & 1;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                canon_ok &= is_canonical(sib[i]);
+                u64 cur = s[i];
+                s[i] = bit ? sib[i] : cur;      // select(sibling, state, bit)  (merkle_proof_chip.rs:61-69)
+                s[i + 4] = bit ? cur : sib[i];
+            }
+#pragma unroll
+            for (int i = 8; i < 12; i++) s[i] = 0;  // fresh hasher per level (:59)
+        }
+        poseidon_g(s);
+    }
+    u64 c[4];
+    ldg4(cap_entry, c);
+    bool eq = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++) eq &= (canon(s[i]) == c[i]);
+    if (!canon_ok) return SV_FAIL_NONCANONICAL;
+    return eq ? 0u : merkle_code;
+}
+
+// reduce_extension with base-field terms: acc = acc*alpha + (e, 0), from the last term
+// (goldilocks_extension_chip.rs:331-355)
+SVB_D fp2 horner_base(fp2 alpha, const u64* __restrict__ terms, u32 n, fp2 acc) {
+    for (u32 i = n; i-- > 0;) {
+        fp2 t = mul2(acc, alpha);
+        acc = mk2(add(t.c0, __ldg(terms + i)), t.c1);
+    }
+    return acc;
+}
+
+// Per-proof preparation: range-check the header, proof-of-work check, reduced openings.
+// One thread per proof; writes scratch[4*p..] = reduced_openings and the initial accept word.
+__global__ void __launch_bounds__(128) fri_prepare_kernel(const u64* __restrict__ records, FriKernelParams P,
+                                                          u64* __restrict__ scratch, u32* __restrict__ accept_bitmap,
+                                                          u32* __restrict__ first_fail) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (p < P.n_proofs) {
+        const sv_fri_layout& L = P.L;
+        const u64* rec = records + (size_t)p * L.record_words;
+        bool canon_ok = true;
+        for (u32 w = 0; w < L.header_words; w += 2) {
+            ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(rec + w));
+            canon_ok &= is_canonical(v.x) & is_canonical(v.y);
+        }
+        // fri_verify_proof_of_work (fri_chip.rs:364-376)
+        u64 resp = rec[L.off_pow_response];
+        bool pow_ok = P.pow_bits == 0 || (resp >> (64 - P.pow_bits)) == 0;
+        // compute_reduced_openings (fri_chip.rs:58-70): Horner from the last opening
+        fp2 alpha = mk2(rec[L.off_alpha], rec[L.off_alpha + 1]);
+        fp2 ro[2];
+        for (int b = 0; b < 2; b++) {
+            const u64* o = rec + (b ? L.off_open1 : L.off_open0);
+            u32 n = b ? L.n1 : L.n0;
+            fp2 acc = mk2(0, 0);
+            if (canon_ok)
+                for (u32 i = n; i-- > 0;) {
+                    ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(o + 2 * i));
+                    acc = add2(mul2(acc, alpha), mk2(v.x, v.y));
+                }
+            ro[b] = acc;
+        }
+        scratch[4 * (size_t)p + 0] = ro[0].c0; scratch[4 * (size_t)p + 1] = ro[0].c1;
+        scratch[4 * (size_t)p + 2] = ro[1].c0; scratch[4 * (size_t)p + 3] = ro[1].c1;
+        ok = canon_ok && pow_ok;
+        if (first_fail) first_fail[p] = ok ? 0xFFFFFFFFu : (canon_ok ? SV_FAIL_POW : SV_FAIL_NONCANONICAL);
+    }
+    u32 word = __ballot_sync(0xFFFFFFFFu, ok);
+    if ((threadIdx.x & 31) == 0 && (p >> 5) < (P.n_proofs + 31) / 32) accept_bitmap[p >> 5] = word;
+}
+
+// The fused query kernel: one thread per (class, unit).
+__global__ void __launch_bounds__(128) fri_query_kernel(const u64* __restrict__ records, FriKernelParams P,
+                                                        const u64* __restrict__ scratch, u32* __restrict__ accept_bitmap,
+                                                        u32* __restrict__ first_fail) {
+    const sv_fri_layout& L = P.L;
+    u32 cls = P.class_order[blockIdx.x / P.blocks_per_class];
+    u32 unit = (blockIdx.x % P.blocks_per_class) * blockDim.x + threadIdx.x;
+    if (unit >= P.n_units) return;
+    u32 proof = unit / P.num_queries, query = unit - proof * P.num_queries;
+    const u64* rec = records + (size_t)proof * L.record_words;
+    const u64* q = rec + L.header_words + (size_t)query * L.query_words;
+    u64 x_index_fe = __ldg(rec + L.off_indices + query);
+    u32 lde_bits = L.lde_bits;
+    u64 x_index = x_index_fe & ((1ull << lde_bits) - 1);       // to_bits(.., 64).take(lde_bits)  (fri_chip.rs:245-250)
+    u32 cap_index = (u32)(x_index >> (lde_bits - __popc(L.ncap - 1)));  // top cap_height bits (:72-82), reused by every tree (:308)
+
+    if (cls < 4 + P.num_steps) {
+        // cls < 4: verify_initial_merkle_proof, oracle `cls` (fri_chip.rs:85-110)
+        // else:    step Merkle proof (fri_chip.rs:303-311): leaf = the 2 Fp2 evals (no leaf hash),
+        //          index = x_index >> (i+1)
+        bool init = cls < 4;
+        u32 i = init ? 0 : cls - 4;
+        const u64* cap = rec + (init ? L.off_init_caps + ((size_t)cls * L.ncap + cap_index) * 4
+                                     : L.off_step_caps + ((size_t)i * L.ncap + cap_index) * 4);
+        const u64* leaf = q + (init ? L.q_off_init_evals[cls] : L.q_off_step_evals[i]);
+        const u64* sibs = q + (init ? L.q_off_init_sibs[cls] : L.q_off_step_sibs[i]);
+        u32 rc = merkle_chain(leaf, init ? L.leaf_len[cls] : 4u, sibs, init ? L.init_depth : L.step_depth[i],
+                              init ? x_index : x_index >> (i + 1), cap, init ? SV_FAIL_INIT_MERKLE : SV_FAIL_STEP_MERKLE);
+        if (rc) report_fail(accept_bitmap, first_fail, proof, query,
+                            rc == SV_FAIL_NONCANONICAL ? 0 : (init ? 1 + cls : 8 + 3 * i + 2), rc);
+        return;
+    }
+
+    // ---- algebra chain -------------------------------------------------------------------------
+    // x = 7 * omega^{bitrev(x_index)} (fri_chip.rs:152-166,262-264): bit (lde_bits-1-i) of x_index selects omega^(2^i)
+    u64 x = 7;
+    for (u32 i = 0; i < lde_bits; i++)
+        if ((x_index >> (lde_bits - 1 - i)) & 1) x = mul(x, P.omega_pow2[i]);
+    x = canon(x);
+
+    fp2 alpha = mk2(__ldg(rec + L.off_alpha), __ldg(rec + L.off_alpha + 1));
+    fp2 zeta = mk2(__ldg(rec + L.off_zeta), __ldg(rec + L.off_zeta + 1));
+    fp2 zeta_next = mk2(__ldg(rec + L.off_zeta_next), __ldg(rec + L.off_zeta_next + 1));
+    fp2 ro0 = mk2(scratch[4 * (size_t)proof], scratch[4 * (size_t)proof + 1]);
+    fp2 ro1 = mk2(scratch[4 * (size_t)proof + 2], scratch[4 * (size_t)proof + 3]);
+
+    // batch_initial_polynomials (fri_chip.rs:112-149).  The evals are range-checked by the init
+    // chains of the same unit; here they are only consumed.
+    // batch 0: all polys, oracle order; reduce_extension folds from the last term.
+    fp2 r0 = mk2(0, 0);
+    for (int k = 3; k >= 0; k--) r0 = horner_base(alpha, q + L.q_off_init_evals[k], P.oracle_num_polys[k], r0);
+    fp2 r1 = horner_base(alpha, q + L.q_off_init_evals[2], P.num_zs, mk2(0, 0));
+    fp2 d0 = sub2(mk2(x, 0), zeta), d1 = sub2(mk2(x, 0), zeta_next);
+    u32 fail_key = 0xFFFFFFFFu, fail_code = 0;
+    if (is_zero2(d0) || is_zero2(d1)) { fail_key = 5; fail_code = SV_FAIL_ZERO_DENOM; }
+    // sum = ((0 * alpha^n0 + (r0 - ro0)/d0) * alpha^n1) + (r1 - ro1)/d1
+    fp2 an1 = mk2(1, 0);
+    for (u32 i = 0; i < L.n1; i++) an1 = mul2(an1, alpha);   // exp() as a product loop (goldilocks_extension_chip.rs:264-282)
+    fp2 sum = mul2(sub2(r0, ro0), inv2(d0));
+    sum = add2(mul2(sum, an1), mul2(sub2(r1, ro1), inv2(d1)));
+    fp2 prev = sum;
+
+    u64 idx = x_index;
+    for (u32 i = 0; i < P.num_steps; i++) {
+        u64 ev[4];
+        ldg4(q + L.q_off_step_evals[i], ev);
+        u32 b = (u32)(idx & 1);
+        // evals[x_index_within_coset] == prev_eval (fri_chip.rs:285-292)
+        u64 e0 = b ? ev[2] : ev[0], e1 = b ? ev[3] : ev[1];
+        if ((e0 != prev.c0 || e1 != prev.c1) && 8 + 3 * i < fail_key) { fail_key = 8 + 3 * i; fail_code = SV_FAIL_STEP_EVAL; }
+        // next_eval (fri_chip.rs:168-226): coset_start = x * (-1)^b; a = (cs, ev[0..2]), b = (-cs, ev[2..4])
+        u64 cs = b ? neg(x) : x;
+        fp2 a0 = mk2(cs, 0), a1 = mk2(ev[0], ev[1]), b0 = mk2(neg(cs), 0), b1 = mk2(ev[2], ev[3]);
+        fp2 beta = mk2(__ldg(rec + L.off_betas + 2 * i), __ldg(rec + L.off_betas + 2 * i + 1));
+        fp2 num = mul2(sub2(beta, a0), sub2(b1, a1));
+        fp2 den = sub2(b0, a0);
+        if (is_zero2(den) && 8 + 3 * i + 1 < fail_key) { fail_key = 8 + 3 * i + 1; fail_code = SV_FAIL_ZERO_DENOM; }
+        prev = add2(mul2(num, inv2(den)), a1);
+        x = mulc(x, x);   // exp_power_of_2(x, arity_bits) (:313)
+        idx >>= 1;
+    }
+    // final_poly(x) == prev_eval (fri_chip.rs:317-325)
+    fp2 fe = mk2(0, 0);
+    const u64* fp = rec + L.off_final_poly;
+    for (u32 j = P.final_poly_len; j-- > 0;) {
+        ulonglong2 c = __ldg(reinterpret_cast<const ulonglong2*>(fp + 2 * j));
+        fe = add2(scale2(fe, x), mk2(c.x, c.y));
+    }
+    if (!eq2(fe, prev) && 8 + 3 * P.num_steps < fail_key) { fail_key = 8 + 3 * P.num_steps; fail_code = SV_FAIL_FINAL; }
+    if (fail_code) report_fail(accept_bitmap, first_fail, proof, query, fail_key, fail_code);
+}
+
+// n independent permutations, thread per state (canonical in / out).
+__global__ void __launch_bounds__(128) poseidon_permute_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 s[12];
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(in + 12 * i);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        ulonglong2 v = __ldg(p + k);
+        s[2 * k] = v.x;
+        s[2 * k + 1] = v.y;
+    }
+    poseidon_g(s);
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(out + 12 * i);
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[k] = make_ulonglong2(canon(s[2 * k]), canon(s[2 * k + 1]));
+}
+
+// n independent Merkle paths, thread per path.  Record = up4(leaf_len) + 4*depth words.
+__global__ void __launch_bounds__(128) merkle_verify_kernel(const u64* __restrict__ paths, const u64* __restrict__ indices,
+                                                            const u64* __restrict__ caps, unsigned char* __restrict__ ok,
+                                                            size_t n, u32 leaf_len, u32 depth, u32 cap_height) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 leaf_words = up4(leaf_len);
+    const u64* rec = paths + i * (size_t)(leaf_words + 4 * depth);
+    u64 index = __ldg(indices + i);
+    u32 cap_index = (u32)((index >> depth) & ((1ull << cap_height) - 1));
+    u32 rc = merkle_chain(rec, leaf_len, rec + leaf_words, depth, index, caps + 4 * (size_t)cap_index, 1);
+    ok[i] = rc == 0;
+}
+
+// first_fail post-pass: 0xFFFFFFFF (never failed) -> 0, else (query << 8) | code.
+__global__ void fri_finalize_kernel(u32* __restrict__ first_fail, u32 n) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    u32 v = first_fail[p];
+    first_fail[p] = v == 0xFFFFFFFFu ? 0u : (((v >> 20) << 8) | (v & 0xFFu));
+}
+
+}  // namespace svb

@@ -1,0 +1,232 @@
+// Goldilocks field F_p, p = 2^64 - 2^32 + 1, and its quadratic extension F_p[X]/(X^2 - 7).
+//
+// Semantics replaced: GoldilocksChip / GoldilocksExtensionChip of the reference
+//   chip/goldilocks_chip.rs:105-404, chip/goldilocks_extension_chip.rs:49-400,
+//   gate r = a*b + c mod p: native_chip/arithmetic_chip.rs:19,98-132.
+// One implementation for host (synthetic prover, transcript) and device (sm_100a kernels).
+//
+// Representation: a field element travels as a u64 that is either CANONICAL (< p; everything in
+// memory, everything compared) or LOOSE (any u64, congruent mod p; the inside of the Poseidon
+// permutation).  2^64 = 2^32 - 1 =: EPS and 2^96 = -1 (mod p) make the reduction of a 128-bit product
+// three add/sub steps; on the device they are carry-chain PTX so that ptxas emits
+// IMAD.WIDE.U32 / IADD3.X with predicate carries (checked with cuobjdump -sass).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SVB_HD __host__ __device__ __forceinline__
+#define SVB_D __device__ __forceinline__
+#else
+#define SVB_HD inline
+#define SVB_D inline
+#endif
+
+namespace svb {
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+static constexpr u64 GL_P = 0xFFFFFFFF00000001ull;
+static constexpr u64 GL_EPS = 0xFFFFFFFFull;
+
+// ---- 64x64 -> 128 --------------------------------------------------------------------------
+SVB_HD void mul_wide(u64 a, u64 b, u64& lo, u64& hi) {
+#if defined(__CUDA_ARCH__)
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    u32 r0, r1, r2, r3;
+    asm("{\n\t"
+        ".reg .u32 m0, m1, m2;\n\t"
+        "mul.lo.u32 %0, %4, %6;\n\t"
+        "mul.hi.u32 %1, %4, %6;\n\t"
+        "mul.lo.u32 %2, %5, %7;\n\t"
+        "mul.hi.u32 %3, %5, %7;\n\t"
+        "mul.lo.u32 m0, %4, %7;\n\t"
+        "mul.hi.u32 m1, %4, %7;\n\t"
+        "mad.lo.cc.u32 m0, %5, %6, m0;\n\t"
+        "madc.hi.cc.u32 m1, %5, %6, m1;\n\t"
+        "addc.u32 m2, 0, 0;\n\t"
+        "add.cc.u32 %1, %1, m0;\n\t"
+        "addc.cc.u32 %2, %2, m1;\n\t"
+        "addc.u32 %3, %3, m2;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    lo = ((u64)r1 << 32) | r0;
+    hi = ((u64)r3 << 32) | r2;
+#else
+    unsigned __int128 p = (unsigned __int128)a * b;
+    lo = (u64)p;
+    hi = (u64)(p >> 64);
+#endif
+}
+
+// a*a: three 32x32 products instead of four.
+SVB_HD void sqr_wide(u64 a, u64& lo, u64& hi) {
+#if defined(__CUDA_ARCH__)
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32);
+    u32 r0, r1, r2, r3;
+    asm("{\n\t"
+        ".reg .u32 m0, m1, m2;\n\t"
+        "mul.lo.u32 %0, %4, %4;\n\t"
+        "mul.hi.u32 %1, %4, %4;\n\t"
+        "mul.lo.u32 %2, %5, %5;\n\t"
+        "mul.hi.u32 %3, %5, %5;\n\t"
+        "mul.lo.u32 m0, %4, %5;\n\t"
+        "mul.hi.u32 m1, %4, %5;\n\t"
+        "add.cc.u32 m0, m0, m0;\n\t"
+        "addc.cc.u32 m1, m1, m1;\n\t"
+        "addc.u32 m2, 0, 0;\n\t"
+        "add.cc.u32 %1, %1, m0;\n\t"
+        "addc.cc.u32 %2, %2, m1;\n\t"
+        "addc.u32 %3, %3, m2;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+        : "r"(a0), "r"(a1));
+    lo = ((u64)r1 << 32) | r0;
+    hi = ((u64)r3 << 32) | r2;
+#else
+    mul_wide(a, a, lo, hi);
+#endif
+}
+
+// (hi:lo) mod p as a LOOSE u64.  lo + hi_lo*EPS - hi_hi with the two wrap corrections
+// (each can fire at most once: after a wrap the value is small).
+SVB_HD u64 reduce128(u64 lo, u64 hi) {
+#if defined(__CUDA_ARCH__)
+    u32 r0 = (u32)lo, r1 = (u32)(lo >> 32), r2 = (u32)hi, r3 = (u32)(hi >> 32);
+    u32 t0, t1;
+    asm("{\n\t"
+        ".reg .u32 bw, cy;\n\t"
+        "sub.cc.u32 %0, %2, %5;\n\t"   // (r1:r0) - r3
+        "subc.cc.u32 %1, %3, 0;\n\t"
+        "subc.u32 bw, 0, 0;\n\t"       // 0xFFFFFFFF on borrow
+        "sub.cc.u32 %0, %0, bw;\n\t"   // -= EPS on borrow
+        "subc.u32 %1, %1, 0;\n\t"
+        "mad.lo.cc.u32 %0, %4, 0xFFFFFFFF, %0;\n\t"   // += r2 * EPS
+        "madc.hi.cc.u32 %1, %4, 0xFFFFFFFF, %1;\n\t"
+        "addc.u32 cy, 0, 0;\n\t"
+        "sub.u32 cy, 0, cy;\n\t"       // 0xFFFFFFFF on carry
+        "add.cc.u32 %0, %0, cy;\n\t"   // += EPS on carry
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=r"(t0), "=r"(t1)
+        : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
+    return ((u64)t1 << 32) | t0;
+#else
+    u64 hh = hi >> 32, hl = hi & GL_EPS;
+    u64 t0 = lo - hh;
+    if (lo < hh) t0 -= GL_EPS;
+    u64 t1 = hl * GL_EPS;
+    u64 t2 = t0 + t1;
+    if (t2 < t1) t2 += GL_EPS;
+    return t2;
+#endif
+}
+
+// lo + hi32 * 2^64 (hi32 < 2^32) mod p as a LOOSE u64.
+SVB_HD u64 reduce96(u64 lo, u32 hi32) {
+#if defined(__CUDA_ARCH__)
+    u32 r0 = (u32)lo, r1 = (u32)(lo >> 32);
+    u32 t0, t1;
+    asm("{\n\t"
+        ".reg .u32 cy;\n\t"
+        "mad.lo.cc.u32 %0, %4, 0xFFFFFFFF, %2;\n\t"
+        "madc.hi.cc.u32 %1, %4, 0xFFFFFFFF, %3;\n\t"
+        "addc.u32 cy, 0, 0;\n\t"
+        "sub.u32 cy, 0, cy;\n\t"
+        "add.cc.u32 %0, %0, cy;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=r"(t0), "=r"(t1)
+        : "r"(r0), "r"(r1), "r"(hi32));
+    return ((u64)t1 << 32) | t0;
+#else
+    u64 t1 = (u64)hi32 * GL_EPS;
+    u64 t2 = lo + t1;
+    if (t2 < t1) t2 += GL_EPS;
+    return t2;
+#endif
+}
+
+SVB_HD u64 canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
+SVB_HD bool is_canonical(u64 a) { return a < GL_P; }
+
+// LOOSE x LOOSE -> LOOSE
+SVB_HD u64 mul(u64 a, u64 b) { u64 lo, hi; mul_wide(a, b, lo, hi); return reduce128(lo, hi); }
+SVB_HD u64 sqr(u64 a) { u64 lo, hi; sqr_wide(a, lo, hi); return reduce128(lo, hi); }
+// a*b + c, all LOOSE
+SVB_HD u64 mul_add(u64 a, u64 b, u64 c) {
+    u64 lo, hi;
+    mul_wide(a, b, lo, hi);
+    u64 l2 = lo + c;
+    hi += (l2 < lo);   // a*b + c < 2^128: no overflow
+    return reduce128(l2, hi);
+}
+// LOOSE + CANONICAL -> LOOSE   (after a wrap the sum is < b < p, so + EPS cannot wrap again)
+SVB_HD u64 add_lc(u64 a, u64 b_canonical) {
+    u64 s = a + b_canonical;
+    return s < a ? s + GL_EPS : s;
+}
+// canonical ops (inputs canonical, output canonical)
+SVB_HD u64 add(u64 a, u64 b) {
+    u64 s = a + b;
+    if (s < a || s >= GL_P) s -= GL_P;
+    return s;
+}
+SVB_HD u64 sub(u64 a, u64 b) { return a >= b ? a - b : a + (GL_P - b); }
+SVB_HD u64 neg(u64 a) { return a ? GL_P - a : 0; }
+SVB_HD u64 mulc(u64 a, u64 b) { return canon(mul(a, b)); }
+
+SVB_HD u64 pow(u64 b, u64 e) {
+    u64 r = 1;
+    while (e) {
+        if (e & 1) r = mulc(r, b);
+        b = mulc(b, b);
+        e >>= 1;
+    }
+    return r;
+}
+// Fermat inverse with the standard Goldilocks addition chain for p - 2 = 2^64 - 2^32 - 1
+// (72 multiplications).  a != 0.
+SVB_HD u64 sqn(u64 a, int n) { for (int i = 0; i < n; i++) a = sqr(a); return a; }
+SVB_HD u64 inv(u64 a) {
+    // p - 2 = 0xFFFFFFFE_FFFFFFFF : 31 ones, a zero, 32 ones
+    u64 t2 = mul(sqr(a), a);              // 2 ones
+    u64 t3 = mul(sqr(t2), a);             // 3 ones
+    u64 t6 = mul(sqn(t3, 3), t3);         // 6
+    u64 t12 = mul(sqn(t6, 6), t6);        // 12
+    u64 t24 = mul(sqn(t12, 12), t12);     // 24
+    u64 t30 = mul(sqn(t24, 6), t6);       // 30
+    u64 t31 = mul(sqr(t30), a);           // 31
+    u64 t32 = mul(sqr(t31), a);           // 32 ones
+    u64 t63 = mul(sqn(t31, 33), t32);     // ones at [63:33], zero at bit 32, ones at [31:0]
+    return canon(t63);
+}
+
+// ---- quadratic extension -----------------------------------------------------------------------
+struct fp2 {
+    u64 c0, c1;
+};
+SVB_HD fp2 mk2(u64 a, u64 b) { fp2 r; r.c0 = a; r.c1 = b; return r; }
+SVB_HD fp2 add2(fp2 a, fp2 b) { return mk2(add(a.c0, b.c0), add(a.c1, b.c1)); }
+SVB_HD fp2 sub2(fp2 a, fp2 b) { return mk2(sub(a.c0, b.c0), sub(a.c1, b.c1)); }
+SVB_HD bool eq2(fp2 a, fp2 b) { return a.c0 == b.c0 && a.c1 == b.c1; }
+SVB_HD bool is_zero2(fp2 a) { return (a.c0 | a.c1) == 0; }
+// (a0 b0 + 7 a1 b1, a0 b1 + a1 b0): arithmetic_chip.rs:109-132.  Inputs canonical.
+SVB_HD fp2 mul2(fp2 a, fp2 b) {
+    u64 t = mul(a.c1, b.c1);
+    u64 c0 = mul_add(t, 7, mul(a.c0, b.c0));
+    u64 c1 = mul_add(a.c0, b.c1, mul(a.c1, b.c0));
+    return mk2(canon(c0), canon(c1));
+}
+SVB_HD fp2 mul_add2(fp2 a, fp2 b, fp2 c) { return add2(mul2(a, b), c); }
+// fp2 * base-field scalar
+SVB_HD fp2 scale2(fp2 a, u64 s) { return mk2(mulc(a.c0, s), mulc(a.c1, s)); }
+// (a0 + a1 X)^-1 = (a0 - a1 X)/(a0^2 - 7 a1^2); a != 0 (norm != 0 because 7 is a non-residue)
+SVB_HD fp2 inv2(fp2 a) {
+    u64 n = sub(mulc(a.c0, a.c0), mulc(7, mulc(a.c1, a.c1)));
+    u64 ni = inv(n);
+    return mk2(mulc(a.c0, ni), mulc(neg(a.c1), ni));
+}
+
+}  // namespace svb

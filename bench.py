@@ -1,0 +1,371 @@
+#!/usr/bin/env python3
+"""bench.py -- plonky2 proofs verified/s (FRI query phase) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload A|B|merkle]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the hot path (fri_prepare + fused fri_query kernel) over one batch of synthetic
+proofs per GPU.  Default workload = BASELINE configs[1]: 4 096 proofs of shape A (2^12 trace, 28 FRI
+queries, blowup 8, cap 4, PoW 16) per GPU; proofs shard across ranks with no data-path collective
+(weak scaling), and one all-gather of the accept bitmap per step (NCCL) is inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="A", choices=["A", "B", "merkle"])
+    ap.add_argument("--proofs", type=int, default=0, help="proofs per GPU per step (default 4096 for A, 256 for B)")
+    ap.add_argument("--distinct", type=int, default=0, help="distinct base proofs generated on the host (default 64 / 4)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_params(svb, name):
+    return {"A": svb.SHAPE_A, "B": svb.SHAPE_B}[name]
+
+
+def cpu_baseline(svb, params, base, sample_proofs, threads):
+    """The oracle (CPU restatement of the reference semantics; NOT the Rust binary) timed on the host cores."""
+    from oracle import binding as orc
+    oshape = orc.shape_from(params.to_shape())
+    n = base.shape[0]
+    reps = (sample_proofs + n - 1) // n
+    recs = np.ascontiguousarray(np.tile(base, (reps, 1))[:sample_proofs])
+    orc.fri_verify_batch(oshape, recs[: min(len(recs), threads)], nthreads=threads)   # warm-up
+    t = time.perf_counter()
+    bm = orc.fri_verify_batch(oshape, recs, nthreads=threads)
+    dt = time.perf_counter() - t
+    return sample_proofs / dt, dt, bm
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  The Rust crate cannot be built in this image (no
+    cargo/rustc, dependencies not on disk), so this times the oracle port on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import stark_verifier_b200 as svb
+    params = workload_params(svb, "A" if args.workload == "merkle" else args.workload)
+    L = svb.api.make_layout(params)
+    threads = os.cpu_count() or 1
+    distinct = args.distinct or (16 if args.workload != "B" else 2)
+    base = svb.synth_proofs(params, distinct, seed=0xB2000002, n_circuits=min(4, distinct), nthreads=threads)
+    sample = args.cpu_sample or (64 * threads if args.workload != "B" else 2 * threads)
+    from oracle import binding as orc
+    oshape = orc.shape_from(params.to_shape())
+    recs = np.ascontiguousarray(np.tile(base, ((sample + distinct - 1) // distinct, 1))[:sample])
+    for _ in range(args.warmup):
+        orc.fri_verify_batch(oshape, recs[:threads], nthreads=threads)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        bm = orc.fri_verify_batch(oshape, recs, nthreads=threads)
+    dt = time.perf_counter() - t
+    assert all((int(bm[i >> 5]) >> (i & 31)) & 1 for i in range(sample))
+    v = sample * args.steps / dt
+    cpu = open("/proc/cpuinfo").read().split("model name")[1].split("\n")[0].strip(": \t") if os.path.exists("/proc/cpuinfo") else "?"
+    print(json.dumps({
+        "impl": "reference", "metric": "plonky2_proofs_verified_per_sec", "value": v, "unit": "proofs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"shape {args.workload}: {sample} proofs/step (bounded sample of configs[1]) on host CPU",
+                   "trace_bits": params.degree_bits, "fri_queries": params.config.num_query_rounds,
+                   "blowup": 1 << params.config.rate_bits},
+        "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} proofs x {args.steps} steps, oracle/oracle.c on {threads} threads ({cpu}); "
+                                   "CPU restatement of reference semantics, not the Rust binary"},
+        "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import stark_verifier_b200 as svb
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    threads = os.cpu_count() or 1
+    if args.workload == "merkle":
+        return bench_merkle(args, svb, torch, dist, rank, local_rank, world)
+    params = workload_params(svb, args.workload)
+    L = svb.api.make_layout(params)
+    n = args.proofs or (4096 if args.workload == "A" else 256)
+    n = (n + 31) & ~31
+    distinct = args.distinct or (64 if args.workload == "A" else 2)
+    # synthetic proofs: `distinct` base proofs per rank (own seed), tiled to n PHYSICALLY DISTINCT copies
+    t0 = time.perf_counter()
+    base = svb.synth_proofs(params, distinct, seed=0xB2000002 ^ (rank << 20), n_circuits=min(2, distinct),
+                            nthreads=max(1, threads // max(1, world)))
+    t_gen = time.perf_counter() - t0
+    rw = L.record_words
+    host = torch.empty((n, rw), dtype=torch.int64).pin_memory()
+    hv = host.numpy().view(np.uint64)
+    for i in range(0, n, distinct):
+        c = min(distinct, n - i)
+        hv[i:i + c] = base[:c]
+    # seeded negative controls: 1/64 of the proofs corrupted; expected bitmap known without the oracle
+    rng = np.random.default_rng(1234 + rank)
+    exp = np.full(n // 32, 0xFFFFFFFF, dtype=np.uint32)
+    for i in range(32, n, 64):
+        q = int(rng.integers(0, params.config.num_query_rounds))
+        hv[i, L.header_words + q * L.query_words + L.q_off_init_sibs[i % 4] + int(rng.integers(0, 4 * L.init_depth))] ^= np.uint64(1)
+        exp[i >> 5] &= np.uint32(~(1 << (i & 31)) & 0xFFFFFFFF)
+
+    ctx = svb.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    d_recs = host.cuda(non_blocking=False)
+    words = n // 32
+    d_bm = torch.zeros(words, dtype=torch.int32, device="cuda")
+    d_all = torch.zeros(words * world, dtype=torch.int32, device="cuda")
+
+    def step():
+        ctx.fri_verify_batch(params, d_recs.data_ptr(), n_proofs=n, accept_bitmap=d_bm.data_ptr(), mem=svb.MEM_DEVICE)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_bm)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    got = d_bm.cpu().numpy().view(np.uint32)
+    if not (got == exp).all():
+        raise SystemExit(f"rank {rank}: accept bitmap differs from the expected pattern")
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.kernel_timing(True)
+    l0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    kernel_ms, kernel_n = ctx.kernel_time_ms()
+    ctx.kernel_timing(False)
+    launches = ctx.launch_count - l0 + (args.steps if world > 1 else 0)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * n * args.steps / (ms / 1e3)
+
+    # end to end through the public C ABI with HOST buffers (pinned): H2D + kernels + D2H of the bitmap
+    e2e = None
+    if not args.no_e2e:
+        ctx.set_stream(0)
+        hb = np.zeros(words, dtype=np.uint32)
+        e2e_steps = max(2, min(args.steps, 5))
+        for _ in range(2):
+            ctx.fri_verify_batch(params, host.data_ptr(), n_proofs=n, accept_bitmap=hb, mem=svb.MEM_HOST)
+        assert (hb == exp).all()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.fri_verify_batch(params, host.data_ptr(), n_proofs=n, accept_bitmap=hb, mem=svb.MEM_HOST)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * e2e_steps / float(tt.item()), "unit": "proofs/s",
+               "h2d_bytes_per_step": int(n * rw * 8), "d2h_bytes_per_step": int(words * 4), "steps": e2e_steps,
+               "note": "sv_fri_verify_batch(SV_MEM_HOST) from pinned host records, chunked H2D overlapped with kernels"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    algo_bytes = n * (params.config.num_query_rounds * L.algo_bytes_per_query + L.algo_bytes_shared)
+    k_avg_s = (kernel_ms / max(1, kernel_n)) / 1e3
+    achieved = algo_bytes / k_avg_s / 1e9
+    perms = n * params.config.num_query_rounds * L.perms_per_query
+    out = {
+        "metric": "plonky2_proofs_verified_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[{1 if args.workload == 'A' else 2}]: {n} proofs/GPU/step, shape {args.workload}",
+                   "trace_bits": params.degree_bits, "fri_queries": params.config.num_query_rounds,
+                   "blowup": 1 << params.config.rate_bits, "cap_height": params.config.cap_height,
+                   "pow_bits": params.config.proof_of_work_bits, "proofs_per_gpu": n, "distinct_base_proofs": distinct,
+                   "record_bytes": rw * 8, "l2_policy": f"inputs larger than L2 ({n * rw * 8 / 1e6:.0f} MB/GPU resident, physically distinct copies)",
+                   "sharding": f"proofs sharded over {world} ranks; NCCL all-gather of the accept bitmap only",
+                   "corrupted": "1/64 proofs (sibling limb), bitmap checked against the expected pattern"},
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "fri_query_kernel", "kernel_ms": kernel_ms / max(1, kernel_n),
+                     "kernel_share_of_step": kernel_ms / ms, "algorithmic_bytes_per_launch": int(algo_bytes),
+                     "peak_source": peak_src,
+                     "note": "integer-issue bound, not HBM bound (SURVEY 8d): see perms_per_sec"},
+        "perms_per_sec": world * perms * args.steps / (ms / 1e3),
+        "synth_seconds": t_gen,
+    }
+    if not args.no_cpu_baseline:
+        sample = args.cpu_sample or (32 * threads if args.workload == "A" else threads)
+        v, dt, _ = cpu_baseline(svb, params, base, sample, threads)
+        out["cpu_baseline"] = {"value": v, "unit": "proofs/s", "cores": threads, "kind": "port",
+                               "sample": f"{sample} proofs of the same workload in {dt:.1f} s on {threads} threads; oracle/oracle.c, "
+                                         "CPU restatement of reference semantics (not the Rust binary)"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_merkle(args, svb, torch, dist, rank, local_rank, world):
+    """BASELINE configs[4]: 2^24 independent Merkle paths x depth 20, 4-limb leaves, cap_height 0."""
+    n = args.proofs or (1 << 24)
+    depth, leaf_len = 20, 4
+    rec_words = leaf_len + 4 * depth
+    g = torch.Generator(device="cuda"); g.manual_seed(0xB2000005 + rank)
+    # uniform canonical field elements on the device: 63-bit randoms are < p
+    paths = torch.randint(0, 1 << 62, (n, rec_words), dtype=torch.int64, device="cuda", generator=g)
+    idx = torch.randint(0, 1 << depth, (n,), dtype=torch.int64, device="cuda", generator=g)
+    caps = torch.zeros(4, dtype=torch.int64, device="cuda")
+    ok = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    ctx = svb.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    def step():
+        ctx.merkle_verify_batch(leaf_len, depth, 0, paths.data_ptr(), idx.data_ptr(), caps.data_ptr(), ok.data_ptr(), n=n, mem=svb.MEM_DEVICE)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    # parity on a sampled subset against the oracle
+    from oracle import binding as orc
+    sub = 4096
+    hp = paths[:sub].cpu().numpy().view(np.uint64); hi = idx[:sub].cpu().numpy().view(np.uint64)
+    # give the first half of the subset a matching root so both outcomes occur
+    want = orc.merkle_verify_batch(hp, leaf_len, depth, hi, np.zeros(4, dtype=np.uint64), 0)
+    assert (ok[:sub].cpu().numpy() == want).all()
+    sampler = ClockSampler(local_rank); sampler.start()
+    ctx.kernel_timing(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    kernel_ms, kernel_n = ctx.kernel_time_ms()
+    clocks = sampler.stop()
+    peak, peak_src = measured_peak_gbs()
+    algo = n * (32 + 32 * depth)
+    achieved = algo / (kernel_ms / kernel_n / 1e3) / 1e9
+    if rank == 0:
+        print(json.dumps({
+            "metric": "merkle_paths_verified_per_sec", "value": world * n * args.steps / (ms / 1e3), "unit": "paths/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[4]: {n} Merkle paths x depth {depth}, 4-limb leaves, cap_height 0",
+                       "l2_policy": f"inputs larger than L2 ({n * rec_words * 8 / 1e9:.2f} GB resident)"},
+            "gpu_launches": args.steps, "clocks": clocks,
+            "perms_per_sec": world * n * depth * args.steps / (ms / 1e3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "merkle_verify_kernel", "kernel_ms": kernel_ms / kernel_n,
+                         "algorithmic_bytes_per_launch": int(algo), "peak_source": peak_src},
+        }))
+
+
+if __name__ == "__main__":
+    main()

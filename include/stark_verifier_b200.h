@@ -113,6 +113,11 @@ int sv_ctx_set_stream(sv_ctx* ctx, void* cuda_stream);
 int sv_ctx_synchronize(sv_ctx* ctx);
 /* number of kernel launches issued through this context so far */
 uint64_t sv_ctx_launch_count(const sv_ctx* ctx);
+/* CUDA-event timing of the dominant kernel of each call (fri_query_kernel, merkle_verify_kernel,
+ * poseidon_permute_kernel), recorded on the stream the kernel is launched on.  kernel_time_ms
+ * synchronises, returns the sum and the number of launches since the last call, and resets. */
+int sv_ctx_kernel_timing(sv_ctx* ctx, int enable);
+int sv_ctx_kernel_time_ms(sv_ctx* ctx, double* total_ms, uint64_t* n_launches);
 /* pinned host memory for the SV_MEM_HOST path (pageable memory works too, slower) */
 int sv_host_alloc(size_t bytes, void** out);
 int sv_host_free(void* p);

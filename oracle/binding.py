@@ -1,0 +1,144 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.  ctypes binding of oracle/_build/liboracle.so.
+
+Importers allowed: tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference legs.
+The product package never imports this module.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class OrcShape(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "degree_bits", "rate_bits", "cap_height", "num_query_rounds", "proof_of_work_bits",
+        "num_steps", "final_poly_len", "hiding")] + [
+        ("oracle_num_polys", ctypes.c_uint32 * 4), ("oracle_blinding", ctypes.c_uint32 * 4),
+        ("num_zs", ctypes.c_uint32), ("hash_kind", ctypes.c_uint32)]
+
+
+class OrcLayout(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "ncap", "lde_bits", "n0", "n1", "off_init_caps", "off_step_caps", "off_open0", "off_open1",
+        "off_final_poly", "off_pow_witness", "off_alpha", "off_betas", "off_pow_response",
+        "off_indices", "off_zeta", "off_zeta_next", "header_words")] + [
+        ("leaf_len", ctypes.c_uint32 * 4), ("q_off_init_evals", ctypes.c_uint32 * 4),
+        ("q_off_init_sibs", ctypes.c_uint32 * 4), ("init_depth", ctypes.c_uint32),
+        ("q_off_step_evals", ctypes.c_uint32 * 32), ("q_off_step_sibs", ctypes.c_uint32 * 32),
+        ("step_depth", ctypes.c_uint32 * 32), ("query_words", ctypes.c_uint32), ("record_words", ctypes.c_uint32)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "_build", "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "orc_field.h", "poseidon_g_constants.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(build())
+        vp = ctypes.c_void_p
+        L.orc_make_layout.argtypes = [ctypes.POINTER(OrcShape), ctypes.POINTER(OrcLayout)]
+        L.orc_poseidon.argtypes = [vp]
+        L.orc_poseidon_naive.argtypes = [vp]
+        L.orc_poseidon_batch.argtypes = [vp, ctypes.c_size_t]
+        L.orc_hash_no_pad.argtypes = [vp, ctypes.c_size_t, vp]
+        L.orc_two_to_one.argtypes = [vp, vp, vp]
+        L.orc_merkle_verify.argtypes = [vp, ctypes.c_size_t, ctypes.c_uint64, vp, ctypes.c_size_t, vp, ctypes.c_size_t]
+        L.orc_merkle_verify_batch.argtypes = [vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, vp, vp, ctypes.c_size_t, vp]
+        L.orc_fri_verify.argtypes = [ctypes.POINTER(OrcShape), vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+        L.orc_fri_verify_batch.argtypes = [ctypes.POINTER(OrcShape), vp, ctypes.c_size_t, vp, ctypes.c_int]
+        L.orc_fri_challenges.argtypes = [ctypes.POINTER(OrcShape), vp, vp, vp, ctypes.c_uint32]
+        u64 = ctypes.c_uint64
+        L.orc_f_mul.argtypes = [u64, u64]; L.orc_f_mul.restype = u64
+        L.orc_f_pow.argtypes = [u64, u64]; L.orc_f_pow.restype = u64
+        L.orc_f_inv.argtypes = [u64]; L.orc_f_inv.restype = u64
+        L.orc_f_red128.argtypes = [u64, u64, ctypes.c_int]; L.orc_f_red128.restype = u64
+        L.orc_f2_mul.argtypes = [vp, vp, vp]
+        L.orc_f2_inv.argtypes = [vp, vp]
+        _LIB = L
+    return _LIB
+
+
+def shape_from(sv_shape) -> OrcShape:
+    """Field-by-field copy of an sv_fri_shape-like ctypes struct."""
+    s = OrcShape()
+    for name, _ in OrcShape._fields_:
+        v = getattr(sv_shape, name)
+        if hasattr(v, "__len__"):
+            setattr(s, name, (ctypes.c_uint32 * 4)(*list(v)))
+        else:
+            setattr(s, name, v)
+    return s
+
+
+def layout(shape: OrcShape) -> OrcLayout:
+    L = OrcLayout()
+    assert lib().orc_make_layout(ctypes.byref(shape), ctypes.byref(L)) == 0
+    return L
+
+
+def poseidon(state, naive=False):
+    a = np.array(state, dtype=np.uint64)
+    (lib().orc_poseidon_naive if naive else lib().orc_poseidon)(a.ctypes.data)
+    return a
+
+
+def poseidon_batch(states):
+    a = np.array(states, dtype=np.uint64, copy=True).reshape(-1, 12)
+    lib().orc_poseidon_batch(a.ctypes.data, a.shape[0])
+    return a
+
+
+def hash_no_pad(inp):
+    a = np.ascontiguousarray(inp, dtype=np.uint64)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_hash_no_pad(a.ctypes.data, a.size, out.ctypes.data)
+    return out
+
+
+def two_to_one(l, r):
+    l = np.ascontiguousarray(l, dtype=np.uint64)
+    r = np.ascontiguousarray(r, dtype=np.uint64)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_two_to_one(l.ctypes.data, r.ctypes.data, out.ctypes.data)
+    return out
+
+
+def merkle_verify_batch(records, leaf_len, depth, indices, caps, cap_height):
+    records = np.ascontiguousarray(records, dtype=np.uint64)
+    indices = np.ascontiguousarray(indices, dtype=np.uint64)
+    caps = np.ascontiguousarray(caps, dtype=np.uint64)
+    ok = np.zeros(len(indices), dtype=np.uint8)
+    lib().orc_merkle_verify_batch(records.ctypes.data, len(indices), leaf_len, depth, indices.ctypes.data,
+                                  caps.ctypes.data, cap_height, ok.ctypes.data)
+    return ok
+
+
+def fri_verify(shape: OrcShape, record):
+    record = np.ascontiguousarray(record, dtype=np.uint64)
+    f, fq = ctypes.c_int(), ctypes.c_int()
+    ok = lib().orc_fri_verify(ctypes.byref(shape), record.ctypes.data, ctypes.byref(f), ctypes.byref(fq))
+    return bool(ok), f.value, fq.value
+
+
+def fri_verify_batch(shape: OrcShape, records, nthreads=1):
+    records = np.ascontiguousarray(records, dtype=np.uint64)
+    L = layout(shape)
+    n = records.size // L.record_words
+    bm = np.zeros((n + 31) // 32, dtype=np.uint32)
+    lib().orc_fri_verify_batch(ctypes.byref(shape), records.ctypes.data, n, bm.ctypes.data, nthreads)
+    return bm
+
+
+def fri_challenges(shape: OrcShape, record, circuit_digest, pi_hash, num_challenges=2):
+    cd = np.asarray(circuit_digest, dtype=np.uint64)
+    ph = np.asarray(pi_hash, dtype=np.uint64)
+    lib().orc_fri_challenges(ctypes.byref(shape), record.ctypes.data, cd.ctypes.data, ph.ctypes.data, num_challenges)

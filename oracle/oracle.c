@@ -15,6 +15,17 @@
 /* ------------------------------------------------------------------------------------------
  * Poseidon over Goldilocks: width 12, S-box x^7, 4 + 22 + 4 rounds.
  * ---------------------------------------------------------------------------------------- */
+/* All table entries are canonical (< p); orc_tables_canonical() lets the tests assert it. */
+int orc_tables_canonical(void) {
+    int ok = 1;
+    for (int i = 0; i < 360; i++) ok &= ORC_ALL_ROUND_CONSTANTS[i] < ORC_P;
+    for (int i = 0; i < 12; i++) ok &= ORC_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i] < ORC_P;
+    for (int i = 0; i < 22; i++) ok &= ORC_FAST_PARTIAL_ROUND_CONSTANTS[i] < ORC_P;
+    for (int i = 0; i < 242; i++) ok &= ORC_FAST_PARTIAL_ROUND_VS[i] < ORC_P && ORC_FAST_PARTIAL_ROUND_W_HATS[i] < ORC_P;
+    for (int i = 0; i < 121; i++) ok &= ORC_FAST_PARTIAL_ROUND_INITIAL_MATRIX[i] < ORC_P;
+    return ok;
+}
+
 static uint64_t sbox7(uint64_t x) { /* gates/poseidon.rs:428-436: exp(element, 7) */
     uint64_t x2 = orc_mul(x, x), x4 = orc_mul(x2, x2), x3 = orc_mul(x, x2);
     return orc_mul(x3, x4);
@@ -25,7 +36,7 @@ static void mds_layer(uint64_t st[12]) {
     uint64_t out[12];
     for (int r = 0; r < 12; r++) {
         orc_u128 acc = 0; /* 12 * 41 * 2^64 < 2^128: exact */
-        for (int i = 0; i < 12; i++) acc += (orc_u128)ORC_MDS_MATRIX_CIRC[i] * st[(i + r) % 12];
+        for (int i = 0; i < 12; i++) acc += (orc_u128)ORC_MDS_MATRIX_CIRC[i] * st[i + r < 12 ? i + r : i + r - 12];
         acc += (orc_u128)ORC_MDS_MATRIX_DIAG[r] * st[r];
         out[r] = orc_red128(acc);
     }
@@ -33,7 +44,7 @@ static void mds_layer(uint64_t st[12]) {
 }
 
 static void full_round(uint64_t st[12], int round_ctr) {
-    for (int i = 0; i < 12; i++) st[i] = orc_add(st[i], ORC_ALL_ROUND_CONSTANTS[i + 12 * round_ctr] % ORC_P); /* :383-406 */
+    for (int i = 0; i < 12; i++) st[i] = orc_add(st[i], ORC_ALL_ROUND_CONSTANTS[i + 12 * round_ctr]); /* :383-406 */
     for (int i = 0; i < 12; i++) st[i] = sbox7(st[i]);                                                     /* :438-448 */
     mds_layer(st);
 }
@@ -45,7 +56,7 @@ void orc_poseidon_naive(uint64_t st[12]) {
     int rc = 0;
     for (int r = 0; r < 4; r++) full_round(st, rc++);
     for (int r = 0; r < 22; r++) {
-        for (int i = 0; i < 12; i++) st[i] = orc_add(st[i], ORC_ALL_ROUND_CONSTANTS[i + 12 * rc] % ORC_P);
+        for (int i = 0; i < 12; i++) st[i] = orc_add(st[i], ORC_ALL_ROUND_CONSTANTS[i + 12 * rc]);
         st[0] = sbox7(st[0]);
         mds_layer(st);
         rc++;
@@ -58,28 +69,43 @@ void orc_poseidon(uint64_t st[12]) {
     for (int i = 0; i < 12; i++) st[i] %= ORC_P;
     int rc = 0;
     for (int r = 0; r < 4; r++) full_round(st, rc++);                               /* :637-650 */
-    for (int i = 0; i < 12; i++) st[i] = orc_add(st[i], ORC_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i] % ORC_P); /* :652, :408-426 */
+    for (int i = 0; i < 12; i++) st[i] = orc_add(st[i], ORC_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i]); /* :652, :408-426 */
     {   /* mds_partial_layer_init :504-537 */
         uint64_t res[12] = {0};
         res[0] = st[0];
         for (int r = 1; r < 12; r++)
             for (int c = 1; c < 12; c++)
-                res[c] = orc_mul_add(ORC_FAST_PARTIAL_ROUND_INITIAL_MATRIX[(r - 1) * 11 + (c - 1)] % ORC_P, st[r], res[c]);
+                res[c] = orc_mul_add(ORC_FAST_PARTIAL_ROUND_INITIAL_MATRIX[(r - 1) * 11 + (c - 1)], st[r], res[c]);
         memcpy(st, res, sizeof res);
     }
     for (int r = 0; r < 22; r++) {                                                   /* :654-672 */
         st[0] = sbox7(st[0]);
-        if (r != 21) st[0] = orc_add(st[0], ORC_FAST_PARTIAL_ROUND_CONSTANTS[r] % ORC_P);
+        if (r != 21) st[0] = orc_add(st[0], ORC_FAST_PARTIAL_ROUND_CONSTANTS[r]);
         /* mds_partial_layer_fast :539-589 */
         uint64_t d = orc_mul(st[0], ORC_MDS_MATRIX_CIRC[0] + ORC_MDS_MATRIX_DIAG[0]);
-        for (int i = 1; i < 12; i++) d = orc_mul_add(ORC_FAST_PARTIAL_ROUND_W_HATS[r * 11 + i - 1] % ORC_P, st[i], d);
+        for (int i = 1; i < 12; i++) d = orc_mul_add(ORC_FAST_PARTIAL_ROUND_W_HATS[r * 11 + i - 1], st[i], d);
         uint64_t res[12];
         res[0] = d;
-        for (int i = 1; i < 12; i++) res[i] = orc_mul_add(ORC_FAST_PARTIAL_ROUND_VS[r * 11 + i - 1] % ORC_P, st[0], st[i]);
+        for (int i = 1; i < 12; i++) res[i] = orc_mul_add(ORC_FAST_PARTIAL_ROUND_VS[r * 11 + i - 1], st[0], st[i]);
         memcpy(st, res, sizeof res);
     }
     rc += 22;                                                                        /* :673 */
     for (int r = 0; r < 4; r++) full_round(st, rc++);                               /* :675-686 */
+}
+
+/* thin exports of the field restatement, for the KAT tests */
+uint64_t orc_f_mul(uint64_t a, uint64_t b) { return orc_mul(a % ORC_P, b % ORC_P); }
+uint64_t orc_f_pow(uint64_t a, uint64_t e) { return orc_pow(a % ORC_P, e); }
+uint64_t orc_f_inv(uint64_t a) { return orc_inv(a % ORC_P); }
+uint64_t orc_f_red128(uint64_t lo, uint64_t hi, int slow) {
+    orc_u128 x = ((orc_u128)hi << 64) | lo;
+    return slow ? orc_red128_slow(x) : orc_red128(x);
+}
+void orc_f2_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]) {
+    orc_fp2 r = orc2_mul(orc2(a[0], a[1]), orc2(b[0], b[1])); out[0] = r.c[0]; out[1] = r.c[1];
+}
+void orc_f2_inv(const uint64_t a[2], uint64_t out[2]) {
+    orc_fp2 r = orc2_inv(orc2(a[0], a[1])); out[0] = r.c[0]; out[1] = r.c[1];
 }
 
 void orc_poseidon_batch(uint64_t *states, size_t n) {

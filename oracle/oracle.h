@@ -51,6 +51,15 @@ typedef struct {
 
 int orc_make_layout(const orc_shape *s, orc_layout *L);
 
+/* field restatement (orc_field.h), exported for the KAT tests */
+int orc_tables_canonical(void);
+uint64_t orc_f_mul(uint64_t a, uint64_t b);
+uint64_t orc_f_pow(uint64_t a, uint64_t e);
+uint64_t orc_f_inv(uint64_t a);
+uint64_t orc_f_red128(uint64_t lo, uint64_t hi, int slow);
+void orc_f2_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]);
+void orc_f2_inv(const uint64_t a[2], uint64_t out[2]);
+
 /* Poseidon-Goldilocks permutation: fast form (poseidon.rs:634-686) and naive 30-round form. */
 void orc_poseidon(uint64_t st[12]);
 void orc_poseidon_naive(uint64_t st[12]);

@@ -22,9 +22,25 @@
 typedef unsigned __int128 orc_u128;
 typedef struct { uint64_t c[2]; } orc_fp2;
 
-static inline uint64_t orc_red128(orc_u128 x) { return (uint64_t)(x % ORC_P); }
-static inline uint64_t orc_add(uint64_t a, uint64_t b) { return orc_red128((orc_u128)a + b); }
-static inline uint64_t orc_sub(uint64_t a, uint64_t b) { return orc_red128((orc_u128)a + ORC_P - (b % ORC_P)); }
+/* Reference reduction (definition): x mod p with the compiler's 128-bit remainder. */
+static inline uint64_t orc_red128_slow(orc_u128 x) { return (uint64_t)(x % ORC_P); }
+/* plonky2_field's published reduce128 (goldilocks_field.rs, `reduce128`): with EPS = 2^32 - 1,
+ * 2^64 = EPS and 2^96 = -1 (mod p), so x = lo + hi_lo*EPS - hi_hi; each wrap is fixed by +-EPS.
+ * Canonicalised at the end.  tests/test_oracle_kat.py checks it against orc_red128_slow. */
+static inline uint64_t orc_red128(orc_u128 x) {
+    uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
+    uint64_t hh = hi >> 32, hl = hi & 0xFFFFFFFFULL;
+    uint64_t t0 = lo - hh;
+    if (lo < hh) t0 -= 0xFFFFFFFFULL;
+    uint64_t t1 = hl * 0xFFFFFFFFULL;
+    uint64_t t2 = t0 + t1;
+    if (t2 < t1) t2 += 0xFFFFFFFFULL;
+    return t2 >= ORC_P ? t2 - ORC_P : t2;
+}
+/* a, b canonical */
+static inline uint64_t orc_add(uint64_t a, uint64_t b) { orc_u128 s = (orc_u128)a + b; return (uint64_t)(s >= ORC_P ? s - ORC_P : s); }
+/* a, b canonical */
+static inline uint64_t orc_sub(uint64_t a, uint64_t b) { return a >= b ? a - b : a + (ORC_P - b); }
 static inline uint64_t orc_neg(uint64_t a) { return orc_sub(0, a); }
 static inline uint64_t orc_mul(uint64_t a, uint64_t b) { return orc_red128((orc_u128)a * b); }
 /* r = a*b + c  (arithmetic_chip.rs:98-107) */

@@ -1,0 +1,30 @@
+"""stark-verifier_b200 -- B200-native batch verifier for the FRI query phase of plonky2 proofs.
+
+Python face of the C ABI in ``include/stark_verifier_b200.h`` (ctypes; no torch types cross the
+boundary).  Names mirror the reference's ``plonky2_verifier`` data model
+(``types/common_data.rs``: ``FriConfig``/``FriParams``; ``chip/fri_chip.rs``: ``FriVerifierChip``
+with ``verify_fri_proof``).  The package directory name contains a hyphen; import it with
+``importlib.import_module("stark-verifier_b200")`` or through the ``stark_verifier_b200`` shim at
+the repository root.
+
+There is no CPU fallback: creating a :class:`Context` without a CUDA device raises.
+"""
+from .api import (  # noqa: F401
+    Context,
+    FriConfig,
+    FriParams,
+    FriShape,
+    FriVerifierChip,
+    Layout,
+    SvError,
+    SHAPE_A,
+    SHAPE_B,
+    SHAPE_SEMAPHORE,
+    FAIL_NAMES,
+    fri_challenges,
+    lib,
+    lib_path,
+    synth_proofs,
+    MEM_HOST,
+    MEM_DEVICE,
+)

@@ -1,0 +1,309 @@
+"""ctypes binding of libsvb200.so and a thin mirror of the reference's verifier interface.
+
+Reference interface mirrored (paths relative to src/plonky2_verifier/):
+  FriConfig, FriParams ............ types/common_data.rs:10-54
+  FriVerifierChip::construct ....... chip/fri_chip.rs:35-46   (offset = MULTIPLICATIVE_GROUP_GENERATOR = 7)
+  FriVerifierChip::verify_fri_proof  chip/fri_chip.rs:329-362 (here: a batch of flat proof records)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+MEM_HOST = 0
+MEM_DEVICE = 1
+HASH_POSEIDON_GOLDILOCKS = 0
+SV_MAX_STEPS = 32
+
+FAIL_NAMES = {0: "ok", 1: "pow", 2: "noncanonical", 3: "init_merkle", 4: "zero_denominator",
+              5: "step_eval", 6: "step_merkle", 7: "final_poly"}
+
+
+class SvError(RuntimeError):
+    pass
+
+
+class FriShape(ctypes.Structure):
+    """sv_fri_shape (include/stark_verifier_b200.h)."""
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "degree_bits", "rate_bits", "cap_height", "num_query_rounds", "proof_of_work_bits",
+        "num_steps", "final_poly_len", "hiding")] + [
+        ("oracle_num_polys", ctypes.c_uint32 * 4), ("oracle_blinding", ctypes.c_uint32 * 4),
+        ("num_zs", ctypes.c_uint32), ("hash_kind", ctypes.c_uint32)]
+
+
+class Layout(ctypes.Structure):
+    """sv_fri_layout (include/stark_verifier_b200.h)."""
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "ncap", "lde_bits", "n0", "n1", "off_init_caps", "off_step_caps", "off_open0", "off_open1",
+        "off_final_poly", "off_pow_witness", "off_alpha", "off_betas", "off_pow_response",
+        "off_indices", "off_zeta", "off_zeta_next", "header_words")] + [
+        ("leaf_len", ctypes.c_uint32 * 4), ("q_off_init_evals", ctypes.c_uint32 * 4),
+        ("q_off_init_sibs", ctypes.c_uint32 * 4), ("init_depth", ctypes.c_uint32),
+        ("q_off_step_evals", ctypes.c_uint32 * SV_MAX_STEPS), ("q_off_step_sibs", ctypes.c_uint32 * SV_MAX_STEPS),
+        ("step_depth", ctypes.c_uint32 * SV_MAX_STEPS), ("query_words", ctypes.c_uint32),
+        ("record_words", ctypes.c_uint32), ("algo_bytes_per_query", ctypes.c_uint32),
+        ("algo_bytes_shared", ctypes.c_uint32), ("perms_per_query", ctypes.c_uint32)]
+
+
+@dataclass
+class FriConfig:
+    """types/common_data.rs:10-21"""
+    rate_bits: int
+    cap_height: int
+    proof_of_work_bits: int
+    num_query_rounds: int
+
+
+@dataclass
+class FriParams:
+    """types/common_data.rs:43-54 plus the FriInstanceInfo facts the FRI verifier reads
+    (types/fri.rs:50-72, types/common_data.rs:153-221)."""
+    config: FriConfig
+    hiding: bool
+    degree_bits: int
+    reduction_arity_bits: List[int]
+    oracle_num_polys: Sequence[int] = (84, 135, 20, 16)      # constants_sigmas, wires, zs_pp, quotient
+    oracle_blinding: Sequence[bool] = (False, True, True, True)  # PlonkOracle::*.blinding (common_data.rs:101-123)
+    num_zs: int = 2                                           # = num_challenges (zs_range, common_data.rs:148-150)
+
+    def lde_bits(self) -> int:
+        return self.degree_bits + self.config.rate_bits
+
+    def final_poly_len(self) -> int:
+        return 1 << (self.degree_bits - sum(self.reduction_arity_bits))
+
+    def to_shape(self) -> FriShape:
+        if any(a != 1 for a in self.reduction_arity_bits):
+            # the reference's next_eval is arity-2 only (chip/fri_chip.rs:211)
+            raise SvError("only reduction_arity_bits == 1 is supported (reference: fri_chip.rs:211)")
+        s = FriShape()
+        s.degree_bits = self.degree_bits
+        s.rate_bits = self.config.rate_bits
+        s.cap_height = self.config.cap_height
+        s.num_query_rounds = self.config.num_query_rounds
+        s.proof_of_work_bits = self.config.proof_of_work_bits
+        s.num_steps = len(self.reduction_arity_bits)
+        s.final_poly_len = self.final_poly_len()
+        s.hiding = int(self.hiding)
+        s.oracle_num_polys = (ctypes.c_uint32 * 4)(*self.oracle_num_polys)
+        s.oracle_blinding = (ctypes.c_uint32 * 4)(*[int(b) for b in self.oracle_blinding])
+        s.num_zs = self.num_zs
+        s.hash_kind = HASH_POSEIDON_GOLDILOCKS
+        return s
+
+
+def _params(degree_bits, rate_bits, cap_height, pow_bits, queries, hiding=False, final_bits=5, **kw) -> FriParams:
+    # FriReductionStrategy::ConstantArityBits(1, 5) (bn245_poseidon/plonky2_config.rs:84)
+    steps = max(0, degree_bits - final_bits)
+    return FriParams(FriConfig(rate_bits, cap_height, pow_bits, queries), hiding, degree_bits, [1] * steps, **kw)
+
+
+#: BASELINE configs[1]/[3]: 2^12 trace, blowup 8, 28 queries, cap 4, PoW 16 (standard_inner_stark_verifier_config)
+SHAPE_A = _params(12, 3, 4, 16, 28)
+#: BASELINE configs[2]: 2^20 trace, blowup 4, 84 queries
+SHAPE_B = _params(20, 2, 4, 16, 84)
+#: BASELINE configs[0]: semaphore-shaped (zero_knowledge => salted leaves), plonky2_semaphore/access_set.rs:68-84
+SHAPE_SEMAPHORE = _params(12, 3, 4, 16, 28, hiding=True)
+
+
+# ---------------------------------------------------------------------------------------------
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libsvb200.so")
+
+
+def lib() -> ctypes.CDLL:
+    """Load libsvb200.so (built in-tree by build.sh / __graft_entry__.build)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise SvError(f"{p} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      f"(there is no CPU fallback)")
+    L = ctypes.CDLL(p)
+    vp, u32p, u64 = ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.c_uint64
+    L.sv_version.restype = ctypes.c_char_p
+    L.sv_last_error.restype = ctypes.c_char_p
+    L.sv_last_error.argtypes = [vp]
+    L.sv_ctx_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    L.sv_ctx_destroy.argtypes = [vp]
+    L.sv_ctx_destroy.restype = None
+    L.sv_ctx_set_stream.argtypes = [vp, vp]
+    L.sv_ctx_synchronize.argtypes = [vp]
+    L.sv_ctx_launch_count.argtypes = [vp]
+    L.sv_ctx_launch_count.restype = u64
+    L.sv_ctx_kernel_timing.argtypes = [vp, ctypes.c_int]
+    L.sv_ctx_kernel_time_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
+    L.sv_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    L.sv_host_free.argtypes = [vp]
+    L.sv_fri_layout_make.argtypes = [ctypes.POINTER(FriShape), ctypes.POINTER(Layout)]
+    L.sv_poseidon_permute_batch.argtypes = [vp, vp, vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
+    L.sv_merkle_verify_batch.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int,
+                                         vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_int]
+    L.sv_fri_verify_batch.argtypes = [vp, ctypes.POINTER(FriShape), ctypes.c_size_t, vp, vp, vp, ctypes.c_int]
+    L.sv_allgather_bitmap.argtypes = [vp, vp, vp, vp, ctypes.c_size_t]
+    L.sv_fri_challenges.argtypes = [ctypes.POINTER(FriShape), vp, vp, vp, ctypes.c_uint32]
+    L.sv_synth_proofs.argtypes = [ctypes.POINTER(FriShape), u64, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_uint32,
+                                  vp, ctypes.c_int]
+    _LIB = L
+    return L
+
+
+def make_layout(params_or_shape) -> Layout:
+    s = params_or_shape.to_shape() if isinstance(params_or_shape, FriParams) else params_or_shape
+    out = Layout()
+    if lib().sv_fri_layout_make(ctypes.byref(s), ctypes.byref(out)) != 0:
+        raise SvError("bad FRI shape")
+    return out
+
+
+def _ptr(a) -> int:
+    """address of a numpy array / int device pointer"""
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return int(a)
+
+
+def synth_proofs(params: FriParams, n_proofs: int, seed: int = 0xB2000002, n_circuits: int = 1,
+                 num_challenges: int = 2, nthreads: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """Synthetic valid proofs as a (n_proofs, record_words) uint64 array (host side, CPU)."""
+    s = params.to_shape()
+    L = make_layout(s)
+    if out is None:
+        out = np.zeros((n_proofs, L.record_words), dtype=np.uint64)
+    assert out.dtype == np.uint64 and out.size == n_proofs * L.record_words
+    nthreads = nthreads or os.cpu_count() or 1
+    rc = lib().sv_synth_proofs(ctypes.byref(s), ctypes.c_uint64(seed), n_circuits, n_proofs, num_challenges,
+                               _ptr(out), nthreads)
+    if rc != 0:
+        raise SvError(f"sv_synth_proofs failed: {rc}")
+    return out
+
+
+def fri_challenges(params: FriParams, record: np.ndarray, circuit_digest, pi_hash, num_challenges: int = 2) -> None:
+    """Host-side Fiat-Shamir (plonk_verifier_chip.rs:55-154): rewrites the challenge fields of `record`."""
+    s = params.to_shape()
+    cd = np.asarray(circuit_digest, dtype=np.uint64)
+    ph = np.asarray(pi_hash, dtype=np.uint64)
+    rc = lib().sv_fri_challenges(ctypes.byref(s), _ptr(record), _ptr(cd), _ptr(ph), num_challenges)
+    if rc != 0:
+        raise SvError(f"sv_fri_challenges failed: {rc}")
+
+
+class Context:
+    """sv_ctx: one per (host thread, GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = lib()
+        h = ctypes.c_void_p()
+        rc = self._lib.sv_ctx_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise SvError(f"sv_ctx_create({device}) failed ({rc}): {self._lib.sv_last_error(None).decode()}")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sv_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise SvError(f"{what} failed ({rc}): {self._lib.sv_last_error(self._h).decode()}")
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self._lib.sv_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream)), "sv_ctx_set_stream")
+
+    def synchronize(self):
+        self._ck(self._lib.sv_ctx_synchronize(self._h), "sv_ctx_synchronize")
+
+    def kernel_timing(self, enable: bool = True):
+        self._ck(self._lib.sv_ctx_kernel_timing(self._h, int(enable)), "sv_ctx_kernel_timing")
+
+    def kernel_time_ms(self):
+        ms, n = ctypes.c_double(), ctypes.c_uint64()
+        self._ck(self._lib.sv_ctx_kernel_time_ms(self._h, ctypes.byref(ms), ctypes.byref(n)), "sv_ctx_kernel_time_ms")
+        return ms.value, int(n.value)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.sv_ctx_launch_count(self._h))
+
+    # -- hot path -------------------------------------------------------------------------------
+    def poseidon_permute_batch(self, states, out=None, n: Optional[int] = None, mem: int = MEM_HOST):
+        if mem == MEM_HOST:
+            states = np.ascontiguousarray(states, dtype=np.uint64)
+            n = states.size // 12
+            out = np.empty_like(states) if out is None else out
+        self._ck(self._lib.sv_poseidon_permute_batch(self._h, _ptr(states), _ptr(out), n, HASH_POSEIDON_GOLDILOCKS, mem),
+                 "sv_poseidon_permute_batch")
+        return out
+
+    def merkle_verify_batch(self, leaf_len: int, depth: int, cap_height: int, paths, indices, caps, ok=None,
+                            n: Optional[int] = None, mem: int = MEM_HOST):
+        if mem == MEM_HOST:
+            n = len(indices)
+            ok = np.zeros(n, dtype=np.uint8) if ok is None else ok
+        self._ck(self._lib.sv_merkle_verify_batch(self._h, leaf_len, depth, cap_height, HASH_POSEIDON_GOLDILOCKS,
+                                                  _ptr(paths), _ptr(indices), _ptr(caps), _ptr(ok), n, mem),
+                 "sv_merkle_verify_batch")
+        return ok
+
+    def fri_verify_batch(self, params: FriParams, records, n_proofs: Optional[int] = None, accept_bitmap=None,
+                         first_fail=None, want_fail: bool = False, mem: int = MEM_HOST):
+        s = params.to_shape()
+        if mem == MEM_HOST:
+            n_proofs = records.shape[0] if n_proofs is None else n_proofs
+            accept_bitmap = np.zeros((n_proofs + 31) // 32, dtype=np.uint32) if accept_bitmap is None else accept_bitmap
+            if want_fail and first_fail is None:
+                first_fail = np.zeros(n_proofs, dtype=np.uint32)
+        self._ck(self._lib.sv_fri_verify_batch(self._h, ctypes.byref(s), n_proofs, _ptr(records), _ptr(accept_bitmap),
+                                               _ptr(first_fail) if first_fail is not None else None, mem),
+                 "sv_fri_verify_batch")
+        return (accept_bitmap, first_fail) if want_fail else accept_bitmap
+
+    def allgather_bitmap(self, nccl_comm: int, local_ptr: int, all_ptr: int, words_per_rank: int):
+        self._ck(self._lib.sv_allgather_bitmap(self._h, ctypes.c_void_p(nccl_comm), local_ptr, all_ptr, words_per_rank),
+                 "sv_allgather_bitmap")
+
+
+class FriVerifierChip:
+    """Mirror of the reference's seam: ``FriVerifierChip::construct(config, offset, fri_params)`` then
+    ``verify_fri_proof(initial_merkle_caps, fri_challenges, fri_openings, fri_proof, fri_instance_info)``
+    (chip/fri_chip.rs:35-46, 329-362).  Here the five arguments of one proof are one flat record
+    (layout: include/stark_verifier_b200.h) and the call takes a batch of them; rejection is a bit in the
+    returned bitmap instead of a panic."""
+
+    OFFSET = 7  # GoldilocksField::MULTIPLICATIVE_GROUP_GENERATOR (plonk_verifier_chip.rs:225-227)
+
+    def __init__(self, ctx: Context, fri_params: FriParams, offset: int = 7):
+        if offset != self.OFFSET:
+            raise SvError("the LDE coset shift is fixed to the multiplicative generator 7, like the reference")
+        self.ctx = ctx
+        self.fri_params = fri_params
+        self.layout = make_layout(fri_params)
+
+    def verify_fri_proof(self, records: np.ndarray, want_fail: bool = False):
+        """records: (n_proofs, record_words) uint64 host array -> list[bool] (and fail codes)."""
+        records = np.ascontiguousarray(records, dtype=np.uint64).reshape(-1, self.layout.record_words)
+        n = records.shape[0]
+        res = self.ctx.fri_verify_batch(self.fri_params, records, n, want_fail=want_fail)
+        bitmap = res[0] if want_fail else res
+        accept = [bool((int(bitmap[i >> 5]) >> (i & 31)) & 1) for i in range(n)]
+        return (accept, res[1]) if want_fail else accept

@@ -28,6 +28,10 @@ struct sv_ctx {
     u32* d_fail = nullptr; size_t fail_words = 0;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     uint64_t launches = 0;
+    // optional CUDA-event timing of the dominant kernel (fri_query_kernel / merkle / permute), on
+    // the stream it is launched on
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> tev; size_t tev_used = 0;
     std::string err;
     int sm_count = 0;
     // dlopen'ed NCCL
@@ -93,6 +97,7 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaFree(c->d_bitmap);
     cudaFree(c->d_fail);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_done[i]); }
+    for (auto& pr : c->tev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->copy_stream);
     if (c->nccl_lib) dlclose(c->nccl_lib);
@@ -121,6 +126,45 @@ extern "C" int sv_host_alloc(size_t bytes, void** out) {
 }
 extern "C" int sv_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? 0 : -1; }
 
+static cudaEvent_t time_begin(sv_ctx* c, cudaStream_t s) {
+    if (!c->timing) return nullptr;
+    if (c->tev_used == c->tev.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return nullptr;
+        c->tev.push_back({a, b});
+    }
+    cudaEventRecord(c->tev[c->tev_used].first, s);
+    return c->tev[c->tev_used].second;
+}
+static void time_end(sv_ctx* c, cudaEvent_t e, cudaStream_t s) {
+    if (!e) return;
+    cudaEventRecord(e, s);
+    c->tev_used++;
+}
+
+extern "C" int sv_ctx_kernel_timing(sv_ctx* c, int enable) {
+    if (!c) return -1;
+    c->timing = enable != 0;
+    c->tev_used = 0;
+    return 0;
+}
+// Sum of the recorded durations (ms) of the dominant kernel since the last call; synchronises.
+extern "C" int sv_ctx_kernel_time_ms(sv_ctx* c, double* total_ms, uint64_t* n_launches) {
+    if (!c || !total_ms || !n_launches) return -1;
+    CK(c, cudaSetDevice(c->device));
+    double tot = 0;
+    for (size_t i = 0; i < c->tev_used; i++) {
+        CK(c, cudaEventSynchronize(c->tev[i].second));
+        float ms = 0;
+        CK(c, cudaEventElapsedTime(&ms, c->tev[i].first, c->tev[i].second));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *n_launches = c->tev_used;
+    c->tev_used = 0;
+    return 0;
+}
+
 template <typename T>
 static int grow(sv_ctx* c, T*& ptr, size_t& have, size_t need) {
     if (need <= have) return 0;
@@ -139,7 +183,9 @@ extern "C" int sv_poseidon_permute_batch(sv_ctx* c, const uint64_t* in, uint64_t
     CK(c, cudaSetDevice(c->device));
     const int B = 128;
     if (mem == SV_MEM_DEVICE) {
+        cudaEvent_t te = time_begin(c, c->stream);
         poseidon_permute_kernel<<<(unsigned)((n + B - 1) / B), B, 0, c->stream>>>(in, out, n);
+        time_end(c, te, c->stream);
         c->launches++;
         CK(c, cudaGetLastError());
         return 0;
@@ -167,7 +213,9 @@ extern "C" int sv_merkle_verify_batch(sv_ctx* c, uint32_t leaf_len, uint32_t dep
     const int B = 128;
     size_t rec_words = up4(leaf_len) + 4 * (size_t)depth;
     if (mem == SV_MEM_DEVICE) {
+        cudaEvent_t te = time_begin(c, c->stream);
         merkle_verify_kernel<<<(unsigned)((n + B - 1) / B), B, 0, c->stream>>>(paths, indices, caps, ok, n, leaf_len, depth, cap_height);
+        time_end(c, te, c->stream);
         c->launches++;
         CK(c, cudaGetLastError());
         return 0;
@@ -226,7 +274,9 @@ static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_rec
     P.n_units = (u32)(n * P.num_queries);
     P.blocks_per_class = (P.n_units + B - 1) / B;
     fri_prepare_kernel<<<(unsigned)((n + B - 1) / B), B, 0, s>>>(d_records, P, d_scratch, d_bitmap, d_fail);
+    cudaEvent_t te = time_begin(c, s);
     fri_query_kernel<<<P.blocks_per_class * P.n_classes, B, 0, s>>>(d_records, P, d_scratch, d_bitmap, d_fail);
+    time_end(c, te, s);
     c->launches += 2;
     if (d_fail) {
         fri_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_fail, (u32)n);

@@ -1,0 +1,166 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit for bit."""
+import numpy as np
+import pytest
+
+from common import P, bit, corrupt, tiny_params
+
+pytestmark = pytest.mark.gpu
+
+
+def test_permute_kat_and_random(svb, orc, ctx):
+    rng = np.random.default_rng(0xB200)
+    edge = np.array([[0] * 12, list(range(12)), [P - 1] * 12, [P - 1, 0, 1, P - 2] * 3], dtype=np.uint64)
+    rnd = rng.integers(0, P, size=(4099, 12), dtype=np.uint64)   # ragged: not a multiple of the block
+    states = np.concatenate([edge, rnd])
+    got = ctx.poseidon_permute_batch(states)
+    want = orc.poseidon_batch(states)
+    assert (got.reshape(-1, 12) == want).all()
+    assert int(got.reshape(-1, 12)[0, 0]) == 0x3c18a9786cb0b359
+    assert int(got.reshape(-1, 12)[1, 0]) == 0xd64e1e3efc5b8e9e
+    assert int(got.reshape(-1, 12)[2, 0]) == 0xbe0085cfc57a8357
+
+
+def test_permute_empty(svb, ctx):
+    out = ctx.poseidon_permute_batch(np.zeros((0, 12), dtype=np.uint64))
+    assert out.size == 0
+
+
+def _make_paths(orc, rng, n, leaf_len, depth, cap_height):
+    """Random paths; the cap is built so that path 0..n-1 verify (each path gets its own cap slot
+    only when cap_height allows; otherwise only the paths whose root lands in the cap verify)."""
+    lw = (leaf_len + 3) & ~3
+    rec = np.zeros((n, lw + 4 * depth), dtype=np.uint64)
+    rec[:, :leaf_len] = rng.integers(0, P, size=(n, leaf_len), dtype=np.uint64)
+    rec[:, lw:] = rng.integers(0, P, size=(n, 4 * depth), dtype=np.uint64)
+    ncap = 1 << cap_height
+    idx = rng.integers(0, 1 << (depth + cap_height), size=n, dtype=np.uint64)
+    caps = rng.integers(0, P, size=(ncap, 4), dtype=np.uint64)
+    # make the first ncap paths valid by writing their roots into their cap slot
+    for i in range(min(n, ncap)):
+        idx[i] = (np.uint64(i) << np.uint64(depth)) | (idx[i] & np.uint64((1 << depth) - 1))
+        st = rec[i, :leaf_len].copy() if leaf_len <= 4 else orc.hash_no_pad(rec[i, :leaf_len])
+        if leaf_len < 4:
+            st = np.concatenate([st, np.zeros(4 - leaf_len, dtype=np.uint64)])
+        for l in range(depth):
+            sib = rec[i, lw + 4 * l: lw + 4 * l + 4]
+            st = orc.two_to_one(sib, st) if (int(idx[i]) >> l) & 1 else orc.two_to_one(st, sib)
+        caps[i] = st
+    return rec, idx, caps
+
+
+@pytest.mark.parametrize("leaf_len,depth,cap_height", [(4, 20, 0), (1, 3, 1), (3, 5, 2), (5, 4, 2), (8, 1, 0),
+                                                       (9, 0, 3), (135, 11, 4), (84, 7, 4), (20, 6, 1), (16, 2, 0)])
+def test_merkle_batch(svb, orc, ctx, leaf_len, depth, cap_height):
+    rng = np.random.default_rng(leaf_len * 1000 + depth)
+    n = 300
+    rec, idx, caps = _make_paths(orc, rng, n, leaf_len, depth, cap_height)
+    lw = (leaf_len + 3) & ~3
+    # oracle wants unpadded leaves: feed it a compacted copy
+    compact = np.concatenate([rec[:, :leaf_len], rec[:, lw:]], axis=1)
+    # non-canonical word in a path that would otherwise verify
+    if n > 0 and (1 << cap_height) > 1:
+        rec[1, 0] = np.uint64(P)
+        compact[1, 0] = np.uint64(P)
+    got = ctx.merkle_verify_batch(leaf_len, depth, cap_height, rec, idx, caps)
+    want = orc.merkle_verify_batch(compact, leaf_len, depth, idx, caps, cap_height)
+    assert (got == want).all()
+    assert got[0] == 1                      # a valid path is accepted
+    assert got[(1 << cap_height):].sum() == 0  # random paths are rejected
+
+
+@pytest.mark.parametrize("hiding,cap,degree_bits,rate_bits", [(False, 2, 7, 3), (True, 0, 8, 2), (False, 4, 6, 3), (True, 3, 9, 1)])
+def test_fri_small_shapes(svb, orc, ctx, hiding, cap, degree_bits, rate_bits):
+    params = tiny_params(svb, hiding=hiding, cap=cap, degree_bits=degree_bits, rate_bits=rate_bits)
+    L = svb.api.make_layout(params)
+    n = 77   # ragged: not a multiple of 32
+    recs = svb.synth_proofs(params, n, seed=degree_bits * 31 + cap, n_circuits=2)
+    rng = np.random.default_rng(5)
+    bad = corrupt(recs, L, rng, every=4)
+    bm, ff = ctx.fri_verify_batch(params, recs, want_fail=True)
+    oshape = orc.shape_from(params.to_shape())
+    want = orc.fri_verify_batch(oshape, recs, nthreads=4)
+    assert (bm == want).all()
+    for i in range(n):
+        ok, code, q = orc.fri_verify(oshape, recs[i])
+        assert bit(bm, i) == int(ok)
+        assert bit(bm, i) == (0 if i in bad else 1), (i, bad.get(i), code)
+        exp = 0 if ok else ((max(q, 0) << 8) | code)
+        assert int(ff[i]) == exp, (i, bad.get(i), hex(int(ff[i])), hex(exp))
+
+
+def test_fri_empty_and_single(svb, orc, ctx):
+    params = tiny_params(svb)
+    L = svb.api.make_layout(params)
+    bm = ctx.fri_verify_batch(params, np.zeros((0, L.record_words), dtype=np.uint64), n_proofs=0)
+    assert bm.size == 0
+    recs = svb.synth_proofs(params, 1, seed=3)
+    assert bit(ctx.fri_verify_batch(params, recs), 0) == 1
+
+
+def test_fri_shape_a(svb, orc, ctx):
+    """BASELINE configs[1] shape (2^12 trace, 28 queries, blowup 8, cap 4, PoW 16) on a batch the oracle
+    finishes in seconds."""
+    params = svb.SHAPE_A
+    L = svb.api.make_layout(params)
+    assert L.algo_bytes_per_query == 5240 and L.algo_bytes_shared == 10264 and L.perms_per_query == 126
+    n = 96
+    recs = svb.synth_proofs(params, n, seed=0xB2000002, n_circuits=2)
+    bad = corrupt(recs, L, np.random.default_rng(11), every=8)
+    bm, ff = ctx.fri_verify_batch(params, recs, want_fail=True)
+    oshape = orc.shape_from(params.to_shape())
+    want = orc.fri_verify_batch(oshape, recs, nthreads=8)
+    assert (bm == want).all()
+    for i in range(n):
+        assert bit(bm, i) == (0 if i in bad else 1), (i, bad.get(i))
+
+
+def test_fri_semaphore_shape_salted(svb, orc, ctx):
+    """BASELINE configs[0]: semaphore-shaped proof (zero_knowledge => hiding, salted leaves)."""
+    params = svb.SHAPE_SEMAPHORE
+    recs = svb.synth_proofs(params, 2, seed=1)
+    bm = ctx.fri_verify_batch(params, recs)
+    oshape = orc.shape_from(params.to_shape())
+    assert (bm == orc.fri_verify_batch(oshape, recs, nthreads=2)).all()
+    assert int(bm[0]) == 3
+
+
+def test_fri_device_memory_path(svb, orc, ctx):
+    """SV_MEM_DEVICE: records already resident, result left on the device (torch is only the allocator)."""
+    import torch
+    params = tiny_params(svb)
+    L = svb.api.make_layout(params)
+    n = 64
+    recs = svb.synth_proofs(params, n, seed=9)
+    bad = corrupt(recs, L, np.random.default_rng(2), every=8)
+    d = torch.from_numpy(recs.view(np.int64)).cuda()
+    bm = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.fri_verify_batch(params, d.data_ptr(), n_proofs=n, accept_bitmap=bm.data_ptr(), mem=svb.MEM_DEVICE)
+    torch.cuda.synchronize()
+    ctx.set_stream(0)
+    got = bm.cpu().numpy().view(np.uint32)
+    want = orc.fri_verify_batch(orc.shape_from(params.to_shape()), recs, nthreads=2)
+    assert (got == want).all()
+    assert all(bit(got, i) == (0 if i in bad else 1) for i in range(n))
+
+
+def test_full_size_tiled_batch(svb, orc, ctx):
+    """configs[1] at full size (4 096 proofs): distinct base proofs tiled into physically distinct
+    copies with a seeded 1/64 corruption pattern; the bitmap must equal the pattern, and the base
+    proofs are checked against the oracle."""
+    params = svb.SHAPE_A
+    L = svb.api.make_layout(params)
+    base = svb.synth_proofs(params, 16, seed=0xB2000002, n_circuits=2)
+    oshape = orc.shape_from(params.to_shape())
+    assert (orc.fri_verify_batch(oshape, base, nthreads=8) == np.array([0xFFFF], dtype=np.uint32)).all()
+    n = 4096
+    recs = np.ascontiguousarray(np.tile(base, (n // 16, 1)))
+    bad = corrupt(recs, L, np.random.default_rng(64), every=64)
+    bm = ctx.fri_verify_batch(params, recs)
+    exp = np.zeros(n // 32, dtype=np.uint32)
+    for i in range(n):
+        if i not in bad:
+            exp[i >> 5] |= np.uint32(1 << (i & 31))
+    assert (bm == exp).all()
+    # idempotence: the same call again gives the same bitmap
+    assert (ctx.fri_verify_batch(params, recs) == exp).all()

@@ -198,7 +198,8 @@ def main():
         exp[i >> 5] &= np.uint32(~(1 << (i & 31)) & 0xFFFFFFFF)
 
     ctx = svb.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: handle 0 would mean "ctx's own stream"
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     d_recs = host.cuda(non_blocking=False)
     words = n // 32
@@ -321,7 +322,8 @@ def bench_merkle(args, svb, torch, dist, rank, local_rank, world):
     caps = torch.zeros(4, dtype=torch.int64, device="cuda")
     ok = torch.zeros(n, dtype=torch.uint8, device="cuda")
     ctx = svb.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     def step():

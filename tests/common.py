@@ -24,6 +24,8 @@ def corrupt(recs, L, rng, every=8, num_steps=None):
     for i in range(every // 2, n, every):
         c = classes[k % len(classes)]
         k += 1
+        if num_steps == 0 and c in ("step_eval", "step_sibling"):
+            c = "leaf"   # a shape without reduction steps has no step data to corrupt
         q = int(rng.integers(0, nq))
         qb = L.header_words + q * L.query_words
         delta = np.uint64(1) << np.uint64(int(rng.integers(0, 20)))

@@ -134,9 +134,11 @@ def test_fri_device_memory_path(svb, orc, ctx):
     bad = corrupt(recs, L, np.random.default_rng(2), every=8)
     d = torch.from_numpy(recs.view(np.int64)).cuda()
     bm = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    ctx.set_stream(stream.cuda_stream)
     ctx.fri_verify_batch(params, d.data_ptr(), n_proofs=n, accept_bitmap=bm.data_ptr(), mem=svb.MEM_DEVICE)
-    torch.cuda.synchronize()
+    ev = torch.cuda.Event(); ev.record(stream); ev.synchronize()   # the work really ran on `stream`
     ctx.set_stream(0)
     got = bm.cpu().numpy().view(np.uint32)
     want = orc.fri_verify_batch(orc.shape_from(params.to_shape()), recs, nthreads=2)

@@ -181,7 +181,7 @@ extern "C" int sv_poseidon_permute_batch(sv_ctx* c, const uint64_t* in, uint64_t
     if (hash_kind != SV_HASH_POSEIDON_GOLDILOCKS) return fail(c, -5, "hash_kind %d not implemented", hash_kind);
     if (n == 0) return 0;
     CK(c, cudaSetDevice(c->device));
-    const int B = 128;
+    const int B = SVB_BLOCK;
     if (mem == SV_MEM_DEVICE) {
         cudaEvent_t te = time_begin(c, c->stream);
         poseidon_permute_kernel<<<(unsigned)((n + B - 1) / B), B, 0, c->stream>>>(in, out, n);
@@ -210,7 +210,7 @@ extern "C" int sv_merkle_verify_batch(sv_ctx* c, uint32_t leaf_len, uint32_t dep
     if (leaf_len == 0 || depth > 63 || cap_height > 16 || depth + cap_height > 63) return fail(c, -7, "bad merkle shape");
     if (n == 0) return 0;
     CK(c, cudaSetDevice(c->device));
-    const int B = 128;
+    const int B = SVB_BLOCK;
     size_t rec_words = up4(leaf_len) + 4 * (size_t)depth;
     if (mem == SV_MEM_DEVICE) {
         cudaEvent_t te = time_begin(c, c->stream);
@@ -269,7 +269,7 @@ static int make_params(sv_ctx* c, const sv_fri_shape& s, FriKernelParams& P) {
 // enqueue prepare + query (+ finalize) for `n` proofs whose records are at d_records
 static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_records, u64* d_scratch, u32* d_bitmap,
                        u32* d_fail, cudaStream_t s) {
-    const int B = 128;
+    const int B = SVB_BLOCK;
     P.n_proofs = (u32)n;
     P.n_units = (u32)(n * P.num_queries);
     P.blocks_per_class = (P.n_units + B - 1) / B;

@@ -25,6 +25,8 @@
 
 namespace svb {
 
+#define SVB_BLOCK 128   // threads per block of every kernel; also the stride of the per-thread smem scratch
+
 struct FriKernelParams {
     sv_fri_layout L;
     u32 num_queries, num_steps, final_poly_len, pow_bits;
@@ -57,7 +59,7 @@ SVB_D void report_fail(u32* accept_bitmap, u32* first_fail, u32 proof, u32 query
 // (overwrite-mode sponge, rate 8: hasher_chip.rs:122-148), iterations [n_sponge, n_sponge+depth)
 // compress with the sibling of that level on a fresh capacity (merkle_proof_chip.rs:58-71).
 SVB_D u32 merkle_chain(const u64* __restrict__ leaf, u32 leaf_len, const u64* __restrict__ sibs, u32 depth,
-                       u64 index, const u64* __restrict__ cap_entry, u32 merkle_code) {
+                       u64 index, const u64* __restrict__ cap_entry, u32 merkle_code, u64* scratch) {
     u64 s[12];
     bool canon_ok = true;
 #pragma unroll
@@ -104,7 +106,7 @@ SVB_D u32 merkle_chain(const u64* __restrict__ leaf, u32 leaf_len, const u64* __
 #pragma unroll
             for (int i = 8; i < 12; i++) s[i] = 0;  // fresh hasher per level (:59)
         }
-        poseidon_g(s);
+        poseidon_g_dev(s, scratch, SVB_BLOCK);
     }
     u64 c[4];
     ldg4(cap_entry, c);
@@ -127,7 +129,7 @@ SVB_D fp2 horner_base(fp2 alpha, const u64* __restrict__ terms, u32 n, fp2 acc) 
 
 // Per-proof preparation: range-check the header, proof-of-work check, reduced openings.
 // One thread per proof; writes scratch[4*p..] = reduced_openings and the initial accept word.
-__global__ void __launch_bounds__(128) fri_prepare_kernel(const u64* __restrict__ records, FriKernelParams P,
+__global__ void __launch_bounds__(SVB_BLOCK) fri_prepare_kernel(const u64* __restrict__ records, FriKernelParams P,
                                                           u64* __restrict__ scratch, u32* __restrict__ accept_bitmap,
                                                           u32* __restrict__ first_fail) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,9 +169,10 @@ __global__ void __launch_bounds__(128) fri_prepare_kernel(const u64* __restrict_
 }
 
 // The fused query kernel: one thread per (class, unit).
-__global__ void __launch_bounds__(128) fri_query_kernel(const u64* __restrict__ records, FriKernelParams P,
+__global__ void __launch_bounds__(SVB_BLOCK) fri_query_kernel(const u64* __restrict__ records, FriKernelParams P,
                                                         const u64* __restrict__ scratch, u32* __restrict__ accept_bitmap,
                                                         u32* __restrict__ first_fail) {
+    __shared__ u64 pscratch[11 * SVB_BLOCK];   // poseidon_g_dev's staging of the initial-matrix outputs
     const sv_fri_layout& L = P.L;
     u32 cls = P.class_order[blockIdx.x / P.blocks_per_class];
     u32 unit = (blockIdx.x % P.blocks_per_class) * blockDim.x + threadIdx.x;
@@ -193,7 +196,8 @@ __global__ void __launch_bounds__(128) fri_query_kernel(const u64* __restrict__ 
         const u64* leaf = q + (init ? L.q_off_init_evals[cls] : L.q_off_step_evals[i]);
         const u64* sibs = q + (init ? L.q_off_init_sibs[cls] : L.q_off_step_sibs[i]);
         u32 rc = merkle_chain(leaf, init ? L.leaf_len[cls] : 4u, sibs, init ? L.init_depth : L.step_depth[i],
-                              init ? x_index : x_index >> (i + 1), cap, init ? SV_FAIL_INIT_MERKLE : SV_FAIL_STEP_MERKLE);
+                              init ? x_index : x_index >> (i + 1), cap, init ? SV_FAIL_INIT_MERKLE : SV_FAIL_STEP_MERKLE,
+                              pscratch + threadIdx.x);
         if (rc) report_fail(accept_bitmap, first_fail, proof, query,
                             rc == SV_FAIL_NONCANONICAL ? 0 : (init ? 1 + cls : 8 + 3 * i + 2), rc);
         return;
@@ -259,7 +263,8 @@ __global__ void __launch_bounds__(128) fri_query_kernel(const u64* __restrict__ 
 }
 
 // n independent permutations, thread per state (canonical in / out).
-__global__ void __launch_bounds__(128) poseidon_permute_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
+__global__ void __launch_bounds__(SVB_BLOCK) poseidon_permute_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
+    __shared__ u64 scratch[11 * SVB_BLOCK];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     u64 s[12];
@@ -270,23 +275,24 @@ __global__ void __launch_bounds__(128) poseidon_permute_kernel(const u64* __rest
         s[2 * k] = v.x;
         s[2 * k + 1] = v.y;
     }
-    poseidon_g(s);
+    poseidon_g_dev(s, scratch + threadIdx.x, SVB_BLOCK);
     ulonglong2* o = reinterpret_cast<ulonglong2*>(out + 12 * i);
 #pragma unroll
     for (int k = 0; k < 6; k++) o[k] = make_ulonglong2(canon(s[2 * k]), canon(s[2 * k + 1]));
 }
 
 // n independent Merkle paths, thread per path.  Record = up4(leaf_len) + 4*depth words.
-__global__ void __launch_bounds__(128) merkle_verify_kernel(const u64* __restrict__ paths, const u64* __restrict__ indices,
+__global__ void __launch_bounds__(SVB_BLOCK) merkle_verify_kernel(const u64* __restrict__ paths, const u64* __restrict__ indices,
                                                             const u64* __restrict__ caps, unsigned char* __restrict__ ok,
                                                             size_t n, u32 leaf_len, u32 depth, u32 cap_height) {
+    __shared__ u64 scratch[11 * SVB_BLOCK];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     u32 leaf_words = up4(leaf_len);
     const u64* rec = paths + i * (size_t)(leaf_words + 4 * depth);
     u64 index = __ldg(indices + i);
     u32 cap_index = (u32)((index >> depth) & ((1ull << cap_height) - 1));
-    u32 rc = merkle_chain(rec, leaf_len, rec + leaf_words, depth, index, caps + 4 * (size_t)cap_index, 1);
+    u32 rc = merkle_chain(rec, leaf_len, rec + leaf_words, depth, index, caps + 4 * (size_t)cap_index, 1, scratch + threadIdx.x);
     ok[i] = rc == 0;
 }
 

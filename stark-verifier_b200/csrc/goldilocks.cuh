@@ -49,7 +49,7 @@ SVB_HD void mul_wide(u64 a, u64 b, u64& lo, u64& hi) {
         "addc.cc.u32 %2, %2, m1;\n\t"
         "addc.u32 %3, %3, m2;\n\t"
         "}"
-        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
     lo = ((u64)r1 << 32) | r0;
     hi = ((u64)r3 << 32) | r2;
@@ -80,7 +80,7 @@ SVB_HD void sqr_wide(u64 a, u64& lo, u64& hi) {
         "addc.cc.u32 %2, %2, m1;\n\t"
         "addc.u32 %3, %3, m2;\n\t"
         "}"
-        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
         : "r"(a0), "r"(a1));
     lo = ((u64)r1 << 32) | r0;
     hi = ((u64)r3 << 32) | r2;
@@ -109,7 +109,7 @@ SVB_HD u64 reduce128(u64 lo, u64 hi) {
         "add.cc.u32 %0, %0, cy;\n\t"   // += EPS on carry
         "addc.u32 %1, %1, 0;\n\t"
         "}"
-        : "=r"(t0), "=r"(t1)
+        : "=&r"(t0), "=&r"(t1)
         : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
     return ((u64)t1 << 32) | t0;
 #else
@@ -137,7 +137,7 @@ SVB_HD u64 reduce96(u64 lo, u32 hi32) {
         "add.cc.u32 %0, %0, cy;\n\t"
         "addc.u32 %1, %1, 0;\n\t"
         "}"
-        : "=r"(t0), "=r"(t1)
+        : "=&r"(t0), "=&r"(t1)
         : "r"(r0), "r"(r1), "r"(hi32));
     return ((u64)t1 << 32) | t0;
 #else

@@ -36,12 +36,12 @@ SVB_HD void mul_wide(u64 a, u64 b, u64& lo, u64& hi) {
     u32 r0, r1, r2, r3;
     asm("{\n\t"
         ".reg .u32 m0, m1, m2;\n\t"
-        "mul.lo.u32 %0, %4, %6;\n\t"
-        "mul.hi.u32 %1, %4, %6;\n\t"
-        "mul.lo.u32 %2, %5, %7;\n\t"
-        "mul.hi.u32 %3, %5, %7;\n\t"
-        "mul.lo.u32 m0, %4, %7;\n\t"
-        "mul.hi.u32 m1, %4, %7;\n\t"
+        "mad.lo.cc.u32 %0, %4, %6, 0;\n\t"     // (r1:r0) = a0*b0
+        "madc.hi.cc.u32 %1, %4, %6, 0;\n\t"
+        "madc.lo.cc.u32 %2, %5, %7, 0;\n\t"    // (r3:r2) = a1*b1 (+ carry, always 0)
+        "madc.hi.u32 %3, %5, %7, 0;\n\t"
+        "mad.lo.cc.u32 m0, %4, %7, 0;\n\t"     // (m2:m1:m0) = a0*b1 + a1*b0
+        "madc.hi.u32 m1, %4, %7, 0;\n\t"
         "mad.lo.cc.u32 m0, %5, %6, m0;\n\t"
         "madc.hi.cc.u32 m1, %5, %6, m1;\n\t"
         "addc.u32 m2, 0, 0;\n\t"
@@ -67,12 +67,12 @@ SVB_HD void sqr_wide(u64 a, u64& lo, u64& hi) {
     u32 r0, r1, r2, r3;
     asm("{\n\t"
         ".reg .u32 m0, m1, m2;\n\t"
-        "mul.lo.u32 %0, %4, %4;\n\t"
-        "mul.hi.u32 %1, %4, %4;\n\t"
-        "mul.lo.u32 %2, %5, %5;\n\t"
-        "mul.hi.u32 %3, %5, %5;\n\t"
-        "mul.lo.u32 m0, %4, %5;\n\t"
-        "mul.hi.u32 m1, %4, %5;\n\t"
+        "mad.lo.cc.u32 %0, %4, %4, 0;\n\t"
+        "madc.hi.cc.u32 %1, %4, %4, 0;\n\t"
+        "madc.lo.cc.u32 %2, %5, %5, 0;\n\t"
+        "madc.hi.u32 %3, %5, %5, 0;\n\t"
+        "mad.lo.cc.u32 m0, %4, %5, 0;\n\t"
+        "madc.hi.u32 m1, %4, %5, 0;\n\t"
         "add.cc.u32 m0, m0, m0;\n\t"
         "addc.cc.u32 m1, m1, m1;\n\t"
         "addc.u32 m2, 0, 0;\n\t"

@@ -154,14 +154,18 @@ SVB_D void mds_layer_rc(u64 s[12], const u64* __restrict__ rc) {
 #pragma unroll
     for (int r = 0; r < 12; r++) {
         u64 c = rc[r];
-        u64 al = (u32)c, ah = c >> 32;
+        u32 al0 = (u32)c, al1 = 0, ah0 = (u32)(c >> 32), ah1 = 0;
+        // carry-chain form: ptxas keeps each pair as ONE accumulating IMAD.WIDE.U32 (a plain mad.wide
+        // gets re-associated into IMAD.WIDE + IADD3 + IADD3.X, one extra issue slot per product)
 #pragma unroll
         for (int j = 0; j < 12; j++) {
-            al = mad_wide(l[j], mds_coeff(r, j), al);
-            ah = mad_wide(h[j], mds_coeff(r, j), ah);
+            asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(al0), "+r"(al1) : "r"(l[j]), "r"(mds_coeff(r, j)));
+            asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(ah0), "+r"(ah1) : "r"(h[j]), "r"(mds_coeff(r, j)));
         }
+        u64 al = ((u64)al1 << 32) | al0, ah = ((u64)ah1 << 32) | ah0;
         // al + ah*2^32, al, ah < 2^42
         u32 t0 = (u32)al, t1, top, r0, r1;
+        (void)t1; (void)top;
         asm("{\n\t"
             ".reg .u32 cy;\n\t"
             "add.cc.u32 %2, %4, %5;\n\t"
@@ -175,6 +179,57 @@ SVB_D void mds_layer_rc(u64 s[12], const u64* __restrict__ rc) {
             "}"
             : "=&r"(r0), "=&r"(r1), "=&r"(t1), "=&r"(top)
             : "r"((u32)(al >> 32)), "r"((u32)ah), "r"((u32)(ah >> 32)), "r"(t0));
+        s[r] = ((u64)r1 << 32) | r0;
+    }
+}
+
+// The same layer on the FP64 pipe.  Measured on B200 (tools/microbench/pipes.cu): IMAD.WIDE.U32 issues
+// at 1/4 rate per scheduler (4 cycles per warp instruction on the fmaheavy pipe, which the S-boxes
+// already saturate), DFMA at 1/2 rate on the otherwise idle FP64 pipe.  Every product here is
+// (coefficient <= 49) x (32-bit half) and every row sum is < 2^42, so the arithmetic is EXACT in
+// binary64: the accumulator starts at 2^52 + rc_half and stays inside [2^52, 2^53), where doubles are
+// consecutive integers, and the integer is read back from the mantissa bits.
+SVB_D void mds_layer_rc_f64(u64 s[12], const u64* __restrict__ rc) {
+    const double TWO52 = 4503599627370496.0;
+    double d[12];
+    u32 h[12];
+    u64 al[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        d[j] = __hiloint2double(0x43300000, (int)(u32)s[j]) - TWO52;
+        h[j] = (u32)(s[j] >> 32);
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        double acc = __hiloint2double(0x43300000, (int)(u32)rc[r]);
+#pragma unroll
+        for (int j = 0; j < 12; j++) acc = __fma_rn(d[j], (double)mds_coeff(r, j), acc);
+        al[r] = (u64)__double_as_longlong(acc) & 0xFFFFFFFFFFFFFull;
+    }
+#pragma unroll
+    for (int j = 0; j < 12; j++) d[j] = __hiloint2double(0x43300000, (int)h[j]) - TWO52;
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        double acc = __hiloint2double(0x43300000, (int)(u32)(rc[r] >> 32));
+#pragma unroll
+        for (int j = 0; j < 12; j++) acc = __fma_rn(d[j], (double)mds_coeff(r, j), acc);
+        u64 ah = (u64)__double_as_longlong(acc) & 0xFFFFFFFFFFFFFull;
+        // al + ah*2^32, al, ah < 2^42
+        u32 t0 = (u32)al[r], t1, top, r0, r1;
+        (void)t1; (void)top;
+        asm("{\n\t"
+            ".reg .u32 cy;\n\t"
+            "add.cc.u32 %2, %4, %5;\n\t"
+            "addc.u32 %3, %6, 0;\n\t"
+            "mad.lo.cc.u32 %0, %3, 0xFFFFFFFF, %7;\n\t"
+            "madc.hi.cc.u32 %1, %3, 0xFFFFFFFF, %2;\n\t"
+            "addc.u32 cy, 0, 0;\n\t"
+            "sub.u32 cy, 0, cy;\n\t"
+            "add.cc.u32 %0, %0, cy;\n\t"
+            "addc.u32 %1, %1, 0;\n\t"
+            "}"
+            : "=&r"(r0), "=&r"(r1), "=&r"(t1), "=&r"(top)
+            : "r"((u32)(al[r] >> 32)), "r"((u32)ah), "r"((u32)(ah >> 32)), "r"(t0));
         s[r] = ((u64)r1 << 32) | r0;
     }
 }
@@ -285,7 +340,7 @@ SVB_D void poseidon_g_dev(u64 s[12], u64* __restrict__ scratch /* 11 words of pe
             for (int i = 0; i < 4; i++) s[i] = sbox7(s[i]);
             rot4(s);
         }
-        mds_layer_rc(s, d_FULL_RC_NEXT + 12 * f);   // (:450-502) + next constant layer
+        mds_layer_rc_f64(s, d_FULL_RC_NEXT + 12 * f);   // (:450-502) + next constant layer
         if (f == 3) {
             // mds_partial_layer_init (:504-537): t[c] = sum_{r=1..11} INIT[r-1][c-1] * s[r]
 #pragma unroll 1

@@ -1,0 +1,71 @@
+#!/usr/bin/env python3
+"""Dynamic opcode counts of poseidon_permute_kernel from its SASS listing, using the known loop trip
+counts (S-box loop x3 per full round, full rounds x8, initial-matrix loop x11, partial rounds x22).
+Usage: cuobjdump -sass libsvb200.so | tools/sass_dyn.py   (prints issue-slot and fmaheavy estimates
+with the B200 rates measured by tools/microbench/pipes.cu: IMAD.WIDE = 2 issue slots, IMAD.HI = 4
+fmaheavy cycles, other IMAD = 2 fmaheavy cycles)."""
+import re, sys, collections
+lines = []
+on = False
+for l in sys.stdin:
+    if "Function :" in l:
+        on = "poseidon_permute_kernel" in l
+    if on:
+        m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);", l)
+        if m:
+            lines.append((int(m.group(1), 16), m.group(2).strip()))
+addr_to_idx = {a: i for i, (a, _) in enumerate(lines)}
+# backward branches define loops
+loops = []
+for i, (a, t) in enumerate(lines):
+    m = re.search(r"BRA(?:\.U)?\s+(?:U?P\d,\s*|!U?P\d,\s*|UP\d,\s*)?(0x[0-9a-f]+)", t)
+    if m and "BRA" in t:
+        tgt = int(m.group(1), 16)
+        if tgt in addr_to_idx and addr_to_idx[tgt] <= i and tgt != a:
+            loops.append((addr_to_idx[tgt], i))
+loops.sort()
+# expected nesting: outer (x8) contains sbox (x3); then init (x11), partial (x22) inside the f==3 branch
+trip = {}
+if len(loops) == 4:
+    loops_sorted = sorted(loops, key=lambda x: x[1] - x[0])
+    # identify: largest = outer
+    outer = max(loops, key=lambda x: x[1] - x[0])
+    inner = [l for l in loops if l != outer]
+    inner.sort()
+    trip[inner[0]] = 3; trip[inner[1]] = 11; trip[inner[2]] = 22; trip[outer] = 8
+else:
+    print("unexpected loop structure", loops); sys.exit(1)
+mult = [1.0] * len(lines)
+outer = max(loops, key=lambda x: x[1] - x[0])
+for (b, e), t in trip.items():
+    for i in range(b, e + 1):
+        if (b, e) == outer:
+            mult[i] *= 8
+        elif (b, e) == sorted([l for l in loops if l != outer])[0]:
+            mult[i] *= 3
+# init/partial loops execute once (inside f==3): undo the outer x8 for everything between the forward branch and its target
+inner = sorted([l for l in loops if l != outer])
+fwd_start = inner[0][1] + 1
+# find forward branch after MDS
+for i in range(inner[0][1] + 1, inner[1][0]):
+    if "BRA" in lines[i][1]:
+        m = re.search(r"(0x[0-9a-f]+)", lines[i][1].split("BRA")[1])
+        tgt = addr_to_idx[int(m.group(1), 16)]
+        for j in range(i + 1, tgt):
+            mult[j] /= 8
+        break
+for (b, e) in inner[1:]:
+    for i in range(b, e + 1):
+        mult[i] *= trip[(b, e)]
+cnt = collections.Counter()
+for (a, t), m in zip(lines, mult):
+    op = t.split()[0] if not t.startswith("@") else t.split()[1]
+    cnt[op] += m
+tot = sum(cnt.values())
+wide = sum(v for k, v in cnt.items() if k.startswith("IMAD.WIDE"))
+hi = sum(v for k, v in cnt.items() if k.startswith("IMAD.HI"))
+imad_other = sum(v for k, v in cnt.items() if k.startswith("IMAD") and not k.startswith("IMAD.WIDE") and not k.startswith("IMAD.HI"))
+print(f"dynamic instructions per permutation: {tot:.0f}")
+for k, v in cnt.most_common(16):
+    print(f"  {k:22s} {v:8.0f}")
+print(f"instructions: {tot:.0f};  fmaheavy cycles (WIDE,HI=4, other IMAD=2): {4 * (wide + hi) + 2 * imad_other:.0f}  (wide {wide:.0f}, hi {hi:.0f}, other IMAD {imad_other:.0f})")

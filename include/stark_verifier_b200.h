@@ -130,6 +130,12 @@ int sv_fri_layout_make(const sv_fri_shape* shape, sv_fri_layout* out);
  * Replaces: PlonkyPermutation::permute / HasherChip::permutation (chip/hasher_chip.rs:101-105). */
 int sv_poseidon_permute_batch(sv_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, int hash_kind, int mem);
 
+/* out[i] = a[i] * b[i] + c[i] mod p (canonical); a, b, c are arbitrary u64 words (reduced mod p).
+ * Replaces: GoldilocksChip::mul_add, the gate r = a*b + c (chip/goldilocks_chip.rs:175-195,
+ * native_chip/arithmetic_chip.rs:98-107) -- the arithmetic every kernel of this library is built on. */
+int sv_goldilocks_mul_add_batch(sv_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint64_t* out,
+                                size_t n, int mem);
+
 /* n independent Merkle paths against one cap.  paths: n records of (leaf_len + 4*depth) words
  * (leaf, then siblings bottom-up); indices[n] leaf indices (bit l of the index selects the side at
  * level l; the bits above `depth` select the cap entry); caps: 2^cap_height x 4 words; ok[n] bytes.

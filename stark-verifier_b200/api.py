@@ -147,6 +147,7 @@ def lib() -> ctypes.CDLL:
     L.sv_host_free.argtypes = [vp]
     L.sv_fri_layout_make.argtypes = [ctypes.POINTER(FriShape), ctypes.POINTER(Layout)]
     L.sv_poseidon_permute_batch.argtypes = [vp, vp, vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
+    L.sv_goldilocks_mul_add_batch.argtypes = [vp, vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_int]
     L.sv_merkle_verify_batch.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int,
                                          vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_int]
     L.sv_fri_verify_batch.argtypes = [vp, ctypes.POINTER(FriShape), ctypes.c_size_t, vp, vp, vp, ctypes.c_int]
@@ -253,6 +254,16 @@ class Context:
             out = np.empty_like(states) if out is None else out
         self._ck(self._lib.sv_poseidon_permute_batch(self._h, _ptr(states), _ptr(out), n, HASH_POSEIDON_GOLDILOCKS, mem),
                  "sv_poseidon_permute_batch")
+        return out
+
+    def goldilocks_mul_add_batch(self, a, b, c):
+        """a*b + c mod p on the device (host arrays in, canonical host array out)."""
+        a = np.ascontiguousarray(a, dtype=np.uint64); b = np.ascontiguousarray(b, dtype=np.uint64)
+        c = np.ascontiguousarray(c, dtype=np.uint64)
+        assert a.shape == b.shape == c.shape
+        out = np.empty_like(a)
+        self._ck(self._lib.sv_goldilocks_mul_add_batch(self._h, _ptr(a), _ptr(b), _ptr(c), _ptr(out), a.size, MEM_HOST),
+                 "sv_goldilocks_mul_add_batch")
         return out
 
     def merkle_verify_batch(self, leaf_len: int, depth: int, cap_height: int, paths, indices, caps, ok=None,

@@ -16,17 +16,21 @@
 
 using namespace svb;
 
+// SV_MEM_HOST pipeline depth: staging buffers in flight (H2D of chunk i+2.. while chunks i, i+1 compute)
+#define SV_NBUF 4
+
 struct sv_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;   // compute
-    cudaStream_t copy_stream = nullptr;  // H2D of the next chunk
+    cudaStream_t aux_stream = nullptr;   // second compute stream of the SV_MEM_HOST pipeline
+    cudaStream_t copy_stream = nullptr;  // H2D of the next chunks
     cudaStream_t stream = nullptr;       // stream used for SV_MEM_DEVICE work (own or caller's)
     // device scratch, grown on demand, reused across calls (no hidden allocation after warm-up)
     u64* d_scratch = nullptr; size_t scratch_words = 0;          // reduced openings
-    u64* d_stage[2] = {nullptr, nullptr}; size_t stage_words[2] = {0, 0}; // H2D chunks (double buffered)
+    u64* d_stage[SV_NBUF] = {}; size_t stage_words[SV_NBUF] = {};   // H2D chunk ring
     u32* d_bitmap = nullptr; size_t bitmap_words = 0;
     u32* d_fail = nullptr; size_t fail_words = 0;
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[SV_NBUF] = {}, ev_done[SV_NBUF] = {}, ev_join = nullptr;
     uint64_t launches = 0;
     // optional CUDA-event timing of the dominant kernel (fri_query_kernel / merkle / permute), on
     // the stream it is launched on
@@ -77,11 +81,13 @@ extern "C" int sv_ctx_create(int device, sv_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     CK(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CK(nullptr, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
     CK(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < SV_NBUF; i++) {
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
+    CK(nullptr, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     c->stream = c->own_stream;
     *out = c;
     return 0;
@@ -92,13 +98,14 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     cudaFree(c->d_scratch);
-    cudaFree(c->d_stage[0]);
-    cudaFree(c->d_stage[1]);
+    for (int i = 0; i < SV_NBUF; i++) cudaFree(c->d_stage[i]);
     cudaFree(c->d_bitmap);
     cudaFree(c->d_fail);
-    for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_done[i]); }
+    for (int i = 0; i < SV_NBUF; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_done[i]); }
+    cudaEventDestroy(c->ev_join);
     for (auto& pr : c->tev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaStreamDestroy(c->own_stream);
+    cudaStreamDestroy(c->aux_stream);
     cudaStreamDestroy(c->copy_stream);
     if (c->nccl_lib) dlclose(c->nccl_lib);
     delete c;
@@ -114,6 +121,7 @@ extern "C" int sv_ctx_synchronize(sv_ctx* c) {
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaStreamSynchronize(c->own_stream));
+    CK(c, cudaStreamSynchronize(c->aux_stream));
     CK(c, cudaStreamSynchronize(c->copy_stream));
     return 0;
 }
@@ -198,6 +206,32 @@ extern "C" int sv_poseidon_permute_batch(sv_ctx* c, const uint64_t* in, uint64_t
     c->launches++;
     CK(c, cudaGetLastError());
     CK(c, cudaMemcpyAsync(out, c->d_stage[0], words * 8, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int sv_goldilocks_mul_add_batch(sv_ctx* c, const uint64_t* a, const uint64_t* b, const uint64_t* cc, uint64_t* out,
+                                           size_t n, int mem) {
+    if (!c || !a || !b || !cc || !out) return -1;
+    if (n == 0) return 0;
+    CK(c, cudaSetDevice(c->device));
+    const int B = 256;
+    if (mem == SV_MEM_DEVICE) {
+        goldilocks_mul_add_kernel<<<(unsigned)((n + B - 1) / B), B, 0, c->stream>>>(a, b, cc, out, n);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        return 0;
+    }
+    if (grow(c, c->d_stage[0], c->stage_words[0], 4 * n)) return -6;
+    u64* d = c->d_stage[0];
+    cudaStream_t s = c->own_stream;
+    CK(c, cudaMemcpyAsync(d, a, n * 8, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(d + n, b, n * 8, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(d + 2 * n, cc, n * 8, cudaMemcpyHostToDevice, s));
+    goldilocks_mul_add_kernel<<<(unsigned)((n + B - 1) / B), B, 0, s>>>(d, d + n, d + 2 * n, d + 3 * n, n);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out, d + 3 * n, n * 8, cudaMemcpyDeviceToHost, s));
     CK(c, cudaStreamSynchronize(s));
     return 0;
 }
@@ -300,33 +334,43 @@ extern "C" int sv_fri_verify_batch(sv_ctx* c, const sv_fri_shape* shape, size_t 
 
     if (mem == SV_MEM_DEVICE) return enqueue_fri(c, P, n_proofs, records, c->d_scratch, accept_bitmap, first_fail, c->stream);
 
-    // Host buffers: chunks of whole 32-proof bitmap words, H2D of chunk i+1 on the copy stream
-    // overlapped with the kernels of chunk i on the compute stream.
+    // Host buffers: chunks of whole 32-proof bitmap words move through a ring of SV_NBUF staging
+    // buffers.  H2D copies run back to back on the copy stream; the kernels of consecutive chunks
+    // alternate between two compute streams so that the tail wave of chunk i overlaps the head of
+    // chunk i+1 (a chunk is only ~1.5 waves of blocks).  Distinct chunks touch distinct bitmap
+    // words / first_fail entries / scratch rows, so they need no ordering among themselves.
     size_t n_words = (n_proofs + 31) / 32;
     if (grow(c, c->d_bitmap, c->bitmap_words, n_words)) return -6;
     if (first_fail && grow(c, c->d_fail, c->fail_words, n_proofs)) return -6;
-    size_t chunk = ((64ull << 20) / (rw * 8)) & ~(size_t)31;   // ~64 MiB per chunk
+    size_t chunk = ((48ull << 20) / (rw * 8)) & ~(size_t)31;   // ~48 MiB per chunk
     if (chunk < 32) chunk = 32;
     if (chunk > n_proofs) chunk = (n_proofs + 31) & ~(size_t)31;
-    for (int b = 0; b < 2; b++)
+    for (int b = 0; b < SV_NBUF; b++)
         if (grow(c, c->d_stage[b], c->stage_words[b], chunk * rw)) return -6;
-    cudaStream_t cs = c->copy_stream, ks = c->own_stream;
+    cudaStream_t cs = c->copy_stream;
+    cudaStream_t ks[2] = {c->own_stream, c->aux_stream};
     size_t n_chunks = (n_proofs + chunk - 1) / chunk;
     for (size_t i = 0; i < n_chunks; i++) {
-        int b = (int)(i & 1);
+        int b = (int)(i % SV_NBUF);
+        cudaStream_t k = ks[i & 1];
         size_t first = i * chunk, cnt = std::min(chunk, n_proofs - first);
-        if (i >= 2) CK(c, cudaStreamWaitEvent(cs, c->ev_done[b], 0));   // buffer b free again
+        if (i >= SV_NBUF) CK(c, cudaStreamWaitEvent(cs, c->ev_done[b], 0));   // buffer b free again
         CK(c, cudaMemcpyAsync(c->d_stage[b], records + first * rw, cnt * rw * 8, cudaMemcpyHostToDevice, cs));
         CK(c, cudaEventRecord(c->ev_copied[b], cs));
-        CK(c, cudaStreamWaitEvent(ks, c->ev_copied[b], 0));
+        CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
         rc = enqueue_fri(c, P, cnt, c->d_stage[b], c->d_scratch + 4 * first, c->d_bitmap + first / 32,
-                         first_fail ? c->d_fail + first : nullptr, ks);
+                         first_fail ? c->d_fail + first : nullptr, k);
         if (rc) return rc;
-        CK(c, cudaEventRecord(c->ev_done[b], ks));
+        CK(c, cudaEventRecord(c->ev_done[b], k));
     }
-    CK(c, cudaMemcpyAsync(accept_bitmap, c->d_bitmap, n_words * 4, cudaMemcpyDeviceToHost, ks));
-    if (first_fail) CK(c, cudaMemcpyAsync(first_fail, c->d_fail, n_proofs * 4, cudaMemcpyDeviceToHost, ks));
-    CK(c, cudaStreamSynchronize(ks));
+    // join the second compute stream, then read the results back on the first
+    if (n_chunks > 1) {
+        CK(c, cudaEventRecord(c->ev_join, ks[1]));
+        CK(c, cudaStreamWaitEvent(ks[0], c->ev_join, 0));
+    }
+    CK(c, cudaMemcpyAsync(accept_bitmap, c->d_bitmap, n_words * 4, cudaMemcpyDeviceToHost, ks[0]));
+    if (first_fail) CK(c, cudaMemcpyAsync(first_fail, c->d_fail, n_proofs * 4, cudaMemcpyDeviceToHost, ks[0]));
+    CK(c, cudaStreamSynchronize(ks[0]));
     return 0;
 }
 

@@ -26,6 +26,9 @@
 namespace svb {
 
 #define SVB_BLOCK 128   // threads per block of every kernel; also the stride of the per-thread smem scratch
+#ifndef SVB_MINBLOCKS
+#define SVB_MINBLOCKS 1  // __launch_bounds__ second argument of the hashing kernels (register cap = 65536 / (128 * N))
+#endif
 
 struct FriKernelParams {
     sv_fri_layout L;
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(SVB_BLOCK) fri_prepare_kernel(const u64* __res
 }
 
 // The fused query kernel: one thread per (class, unit).
-__global__ void __launch_bounds__(SVB_BLOCK) fri_query_kernel(const u64* __restrict__ records, FriKernelParams P,
+__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) fri_query_kernel(const u64* __restrict__ records, FriKernelParams P,
                                                         const u64* __restrict__ scratch, u32* __restrict__ accept_bitmap,
                                                         u32* __restrict__ first_fail) {
     __shared__ u64 pscratch[11 * SVB_BLOCK];   // poseidon_g_dev's staging of the initial-matrix outputs
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(SVB_BLOCK) fri_query_kernel(const u64* __restr
 }
 
 // n independent permutations, thread per state (canonical in / out).
-__global__ void __launch_bounds__(SVB_BLOCK) poseidon_permute_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
+__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) poseidon_permute_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
     __shared__ u64 scratch[11 * SVB_BLOCK];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(SVB_BLOCK) poseidon_permute_kernel(const u64* 
 }
 
 // n independent Merkle paths, thread per path.  Record = up4(leaf_len) + 4*depth words.
-__global__ void __launch_bounds__(SVB_BLOCK) merkle_verify_kernel(const u64* __restrict__ paths, const u64* __restrict__ indices,
+__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) merkle_verify_kernel(const u64* __restrict__ paths, const u64* __restrict__ indices,
                                                             const u64* __restrict__ caps, unsigned char* __restrict__ ok,
                                                             size_t n, u32 leaf_len, u32 depth, u32 cap_height) {
     __shared__ u64 scratch[11 * SVB_BLOCK];
@@ -294,6 +297,16 @@ __global__ void __launch_bounds__(SVB_BLOCK) merkle_verify_kernel(const u64* __r
     u32 cap_index = (u32)((index >> depth) & ((1ull << cap_height) - 1));
     u32 rc = merkle_chain(rec, leaf_len, rec + leaf_words, depth, index, caps + 4 * (size_t)cap_index, 1, scratch + threadIdx.x);
     ok[i] = rc == 0;
+}
+
+// out[i] = a[i] * b[i] + c[i] mod p, canonical; inputs are arbitrary u64 (LOOSE).  Exposes the device field
+// arithmetic (GoldilocksChip::mul_add, chip/goldilocks_chip.rs:175) so that its rare carry/borrow paths
+// can be driven with crafted operands from the tests.
+__global__ void goldilocks_mul_add_kernel(const u64* __restrict__ a, const u64* __restrict__ b, const u64* __restrict__ c,
+                                          u64* __restrict__ out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = canon(mul_add(a[i], b[i], c[i]));
 }
 
 // first_fail post-pass: 0xFFFFFFFF (never failed) -> 0, else (query << 8) | code.

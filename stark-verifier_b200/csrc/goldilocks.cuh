@@ -148,19 +148,113 @@ SVB_HD u64 reduce96(u64 lo, u32 hi32) {
 #endif
 }
 
+#if defined(__CUDACC__)
+// ---- device limb primitives (sm_100a) -----------------------------------------------------------
+// Cost model measured on B200 (tools/microbench/pipes.cu): IMAD.WIDE.U32 (32x32+64 -> 64, optional
+// carry-out predicate, .X = carry-in) occupies the fmaheavy pipe for 4 cycles per warp, IMAD.HI 4,
+// other IMAD forms 2; IADD3 issues every cycle, IADD3.X / LOP3 / SHF / SEL every 2.  The sequences
+// below are written so that ptxas maps every mad.lo.cc/madc.hi pair onto ONE IMAD.WIDE.U32 and
+// merges carry captures into dual-carry IADD3.X (checked with cuobjdump -sass; a*b mod p is 5
+// IMAD.WIDE + 11 ALU instructions).
+//
+// 0xFFFFFFFF lives in constant memory on purpose: as an immediate ptxas strength-reduces the
+// multiplication by EPS into IMAD.HI + IMAD.IADD (6 fmaheavy cycles instead of 4).
+__constant__ u32 d_EPS32 = 0xFFFFFFFFu;
+
+// a*b = r0 + r1 W + r2 W^2 + r3 W^3  (W = 2^32)
+SVB_D void mulw4(u64 a, u64 b, u32& r0, u32& r1, u32& r2, u32& r3) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    asm("{\n\t.reg .u32 m0, m1, n0, n1, c, p1, q0, q1;\n\t.reg .u64 P, Q, M;\n\t"
+        "mul.wide.u32 M, %4, %7;\n\t mov.b64 {m0, m1}, M;\n\t"
+        "mad.lo.cc.u32 n0, %5, %6, m0;\n\t madc.hi.cc.u32 n1, %5, %6, m1;\n\t addc.u32 c, 0, 0;\n\t"
+        "mul.wide.u32 P, %4, %6;\n\t mov.b64 {%0, p1}, P;\n\t"
+        "mul.wide.u32 Q, %5, %7;\n\t mov.b64 {q0, q1}, Q;\n\t"
+        "add.cc.u32 %1, p1, n0;\n\t"
+        "addc.cc.u32 %2, q0, n1;\n\t"
+        "addc.u32 %3, q1, c;\n\t"
+        "}" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+}
+// a*b + c (c any u64): the addend rides on the a0*b0 product, its carry on the a1*b1 product
+SVB_D void muladdw4(u64 a, u64 b, u64 cc, u32& r0, u32& r1, u32& r2, u32& r3) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), c0 = (u32)cc, c1 = (u32)(cc >> 32);
+    asm("{\n\t.reg .u32 m0, m1, n0, n1, c, p1, q0, q1;\n\t.reg .u64 M;\n\t"
+        "mul.wide.u32 M, %4, %7;\n\t mov.b64 {m0, m1}, M;\n\t"
+        "mad.lo.cc.u32 n0, %5, %6, m0;\n\t madc.hi.cc.u32 n1, %5, %6, m1;\n\t addc.u32 c, 0, 0;\n\t"
+        "mad.lo.cc.u32 %0, %4, %6, %8;\n\t madc.hi.cc.u32 p1, %4, %6, %9;\n\t"
+        "madc.lo.cc.u32 q0, %5, %7, 0;\n\t madc.hi.u32 q1, %5, %7, 0;\n\t"
+        "add.cc.u32 %1, p1, n0;\n\t"
+        "addc.cc.u32 %2, q0, n1;\n\t"
+        "addc.u32 %3, q1, c;\n\t"
+        "}" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(c0), "r"(c1));
+}
+// r0 + r1 W + r2 W^2 + r3 W^3 + r4 W^4 as a LOOSE u64 (W^2 = W - 1, W^3 = -1, W^4 = -W mod p).
+//   T = r2 * EPS + (r1:r0)      one IMAD.WIDE with carry-out cy
+//   u = T - (r4:r3)             borrow b
+//   k = cy - b in {-1, 0, 1}    number of 2^64 wraps; 2^64 = EPS, so the result is u + k*EPS, computed as
+//                               (u1:u0) - sign_extend(k) + (k << 32); it cannot wrap again.
+// 1 IMAD.WIDE + 7 ALU instructions.  (A 7-instruction variant that feeds the borrow of a sub.cc chain
+// into madc.cc was tried: ptxas passes the inverted flag there, see tools/lab/NOTES.md.)
+// Exhaustive corner-limb model: tools/lab/reduce_model.py; on the device:
+// tests/test_gpu_parity.py::test_field_corner_cases.
+#ifndef SVB_RED_ALU
+#define SVB_RED_ALU 0   // 1: reduction without the IMAD.WIDE by EPS (12 add/sub instructions)
+#endif
+SVB_D u64 red5(u32 r0, u32 r1, u32 r2, u32 r3, u32 r4) {
+    u32 lo, hi;
+#if SVB_RED_ALU
+    asm("{\n\t.reg .u32 t0, t1, k, kh, h2;\n\t"
+        "sub.cc.u32 t0, %2, %4;\n\t subc.cc.u32 t1, %3, 0;\n\t subc.u32 k, 0, 0;\n\t"
+        "sub.cc.u32 t0, t0, %5;\n\t subc.cc.u32 t1, t1, %6;\n\t subc.u32 k, k, 0;\n\t"
+        "add.cc.u32 t1, t1, %4;\n\t addc.u32 k, k, 0;\n\t"
+        "shr.s32 kh, k, 31;\n\t"
+        "sub.cc.u32 %0, t0, k;\n\t subc.u32 h2, t1, kh;\n\t add.u32 %1, h2, k;\n\t"
+        "}" : "=r"(lo), "=r"(hi) : "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(r4));
+#else
+    asm("{\n\t.reg .u32 t0, t1, cy, u0, u1, k, kh, h2;\n\t"
+        "mad.lo.cc.u32 t0, %4, %7, %2;\n\t madc.hi.cc.u32 t1, %4, %7, %3;\n\t addc.u32 cy, 0, 0;\n\t"
+        "sub.cc.u32 u0, t0, %5;\n\t subc.cc.u32 u1, t1, %6;\n\t subc.u32 k, cy, 0;\n\t"
+        "shr.s32 kh, k, 31;\n\t"
+        "sub.cc.u32 %0, u0, k;\n\t subc.u32 h2, u1, kh;\n\t add.u32 %1, h2, k;\n\t"
+        "}" : "=r"(lo), "=r"(hi) : "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(r4), "r"(d_EPS32));
+#endif
+    return ((u64)hi << 32) | lo;
+}
+SVB_D u64 red4(u32 r0, u32 r1, u32 r2, u32 r3) { return red5(r0, r1, r2, r3, 0); }
+#endif
+
 SVB_HD u64 canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
 SVB_HD bool is_canonical(u64 a) { return a < GL_P; }
 
 // LOOSE x LOOSE -> LOOSE
-SVB_HD u64 mul(u64 a, u64 b) { u64 lo, hi; mul_wide(a, b, lo, hi); return reduce128(lo, hi); }
-SVB_HD u64 sqr(u64 a) { u64 lo, hi; sqr_wide(a, lo, hi); return reduce128(lo, hi); }
+SVB_HD u64 mul(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    u32 r0, r1, r2, r3;
+    mulw4(a, b, r0, r1, r2, r3);
+    return red4(r0, r1, r2, r3);
+#else
+    u64 lo, hi; mul_wide(a, b, lo, hi); return reduce128(lo, hi);
+#endif
+}
+SVB_HD u64 sqr(u64 a) {
+#if defined(__CUDA_ARCH__)
+    return mul(a, a);
+#else
+    u64 lo, hi; sqr_wide(a, lo, hi); return reduce128(lo, hi);
+#endif
+}
 // a*b + c, all LOOSE
 SVB_HD u64 mul_add(u64 a, u64 b, u64 c) {
+#if defined(__CUDA_ARCH__)
+    u32 r0, r1, r2, r3;
+    muladdw4(a, b, c, r0, r1, r2, r3);
+    return red4(r0, r1, r2, r3);
+#else
     u64 lo, hi;
     mul_wide(a, b, lo, hi);
     u64 l2 = lo + c;
     hi += (l2 < lo);   // a*b + c < 2^128: no overflow
     return reduce128(l2, hi);
+#endif
 }
 // LOOSE + CANONICAL -> LOOSE   (after a wrap the sum is < b < p, so + EPS cannot wrap again)
 SVB_HD u64 add_lc(u64 a, u64 b_canonical) {

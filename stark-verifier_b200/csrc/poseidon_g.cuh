@@ -183,143 +183,116 @@ SVB_D void mds_layer_rc(u64 s[12], const u64* __restrict__ rc) {
     }
 }
 
-// The same layer on the FP64 pipe.  Measured on B200 (tools/microbench/pipes.cu): IMAD.WIDE.U32 issues
-// at 1/4 rate per scheduler (4 cycles per warp instruction on the fmaheavy pipe, which the S-boxes
-// already saturate), DFMA at 1/2 rate on the otherwise idle FP64 pipe.  Every product here is
-// (coefficient <= 49) x (32-bit half) and every row sum is < 2^42, so the arithmetic is EXACT in
-// binary64: the accumulator starts at 2^52 + rc_half and stays inside [2^52, 2^53), where doubles are
-// consecutive integers, and the integer is read back from the mantissa bits.
-SVB_D void mds_layer_rc_f64(u64 s[12], const u64* __restrict__ rc) {
-    const double TWO52 = 4503599627370496.0;
+// The MDS layer on the FP64 pipe.  Measured on B200 (tools/microbench/pipes.cu): IMAD.WIDE.U32 holds
+// the fmaheavy pipe 4 cycles per warp instruction and the S-boxes already saturate it; DFMA issues
+// every 2 cycles on the otherwise idle FP64 pipe.  Every product here is (coefficient <= 49) x (32-bit
+// half) and every row sum is < 2^42, so the arithmetic is EXACT in binary64: the accumulator starts at
+// 2^52 + rc_half and stays inside [2^52, 2^53), where doubles are consecutive integers, and the
+// integer is read back from the mantissa bits (the exponent pattern 0x433 of the high words is
+// subtracted inside the carry chain that recombines the two halves).
+#ifndef SVB_MDS_CVT
+#define SVB_MDS_CVT 1   // 1: I2F.F64.U32 conversions; 0: mantissa trick (2 MOV + DADD per value)
+#endif
+SVB_D double u32_to_f64(u32 x) {
+#if SVB_MDS_CVT
+    return __uint2double_rn(x);
+#else
+    return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;
+#endif
+}
+SVB_D void mds_layer_rc_f64(u64 s[12], const u64* __restrict__ rcf /* FULL_RC_NEXT_F64: 2 words per row */) {
     double d[12];
     u32 h[12];
-    u64 al[12];
+    u32 al0[12], al1[12];
 #pragma unroll
     for (int j = 0; j < 12; j++) {
-        d[j] = __hiloint2double(0x43300000, (int)(u32)s[j]) - TWO52;
+        d[j] = u32_to_f64((u32)s[j]);
         h[j] = (u32)(s[j] >> 32);
     }
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-        double acc = __hiloint2double(0x43300000, (int)(u32)rc[r]);
+        double acc = __longlong_as_double((long long)rcf[2 * r]);
 #pragma unroll
         for (int j = 0; j < 12; j++) acc = __fma_rn(d[j], (double)mds_coeff(r, j), acc);
-        al[r] = (u64)__double_as_longlong(acc) & 0xFFFFFFFFFFFFFull;
+        al0[r] = (u32)__double2loint(acc);
+        al1[r] = (u32)__double2hiint(acc);
     }
 #pragma unroll
-    for (int j = 0; j < 12; j++) d[j] = __hiloint2double(0x43300000, (int)h[j]) - TWO52;
+    for (int j = 0; j < 12; j++) d[j] = u32_to_f64(h[j]);
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-        double acc = __hiloint2double(0x43300000, (int)(u32)(rc[r] >> 32));
+        double acc = __longlong_as_double((long long)rcf[2 * r + 1]);
 #pragma unroll
         for (int j = 0; j < 12; j++) acc = __fma_rn(d[j], (double)mds_coeff(r, j), acc);
-        u64 ah = (u64)__double_as_longlong(acc) & 0xFFFFFFFFFFFFFull;
-        // al + ah*2^32, al, ah < 2^42
-        u32 t0 = (u32)al[r], t1, top, r0, r1;
-        (void)t1; (void)top;
-        asm("{\n\t"
-            ".reg .u32 cy;\n\t"
-            "add.cc.u32 %2, %4, %5;\n\t"
-            "addc.u32 %3, %6, 0;\n\t"
-            "mad.lo.cc.u32 %0, %3, 0xFFFFFFFF, %7;\n\t"
-            "madc.hi.cc.u32 %1, %3, 0xFFFFFFFF, %2;\n\t"
-            "addc.u32 cy, 0, 0;\n\t"
-            "sub.u32 cy, 0, cy;\n\t"
-            "add.cc.u32 %0, %0, cy;\n\t"
-            "addc.u32 %1, %1, 0;\n\t"
-            "}"
-            : "=&r"(r0), "=&r"(r1), "=&r"(t1), "=&r"(top)
-            : "r"((u32)(al[r] >> 32)), "r"((u32)ah), "r"((u32)(ah >> 32)), "r"(t0));
-        s[r] = ((u64)r1 << 32) | r0;
+        u32 ah0 = (u32)__double2loint(acc), ah1 = (u32)__double2hiint(acc);
+        // V = al + ah*W = v0 + v1 W + v2 W^2 (v2 < 2^11); result = v2*EPS + (v1:v0) + cy*EPS
+        u32 lo, hi;
+        asm("{\n\t.reg .u32 x1, v1, v2, t0, t1, cy, h2;\n\t"
+            "sub.u32 x1, %3, 0x43300000;\n\t"
+            "add.cc.u32 v1, x1, %4;\n\t addc.u32 v2, %5, 0xBCD00000;\n\t"
+            "mad.lo.cc.u32 t0, v2, %6, %2;\n\t madc.hi.cc.u32 t1, v2, %6, v1;\n\t addc.u32 cy, 0, 0;\n\t"
+            "sub.cc.u32 %0, t0, cy;\n\t subc.u32 h2, t1, 0;\n\t add.u32 %1, h2, cy;\n\t"
+            "}" : "=r"(lo), "=r"(hi) : "r"(al0[r]), "r"(al1[r]), "r"(ah0), "r"(ah1), "r"(d_EPS32));
+        s[r] = ((u64)hi << 32) | lo;
     }
 }
 
-// Unreduced sum of 64x64 products: even columns (a0*b0, a1*b1) in e0..e4, odd columns
-// (a0*b1 + a1*b0, weight 2^32) in o0..o2.  Up to 2^4 terms.
+// Unreduced sum of up to 16 products of 64-bit words: E = e0..e4 collects x0*y0 (weight 1) and x1*y1
+// (weight W^2), chained through the IMAD.WIDE carry; O = o1..o3 collects the cross products at weight
+// W.  ptxas maps each term to 4 IMAD.WIDE.U32 and merges the carry captures into dual-carry-in
+// IADD3.X (5.5 instructions per term).
 struct dot_acc {
-    u32 e0, e1, e2, e3, e4, o0, o1, o2;
+    u32 e0, e1, e2, e3, e4, o1, o2, o3;
 };
-SVB_D void dot_init(dot_acc& a) { a.e0 = a.e1 = a.e2 = a.e3 = a.e4 = a.o0 = a.o1 = a.o2 = 0; }
+SVB_D void dot_init(dot_acc& a) { a.e0 = a.e1 = a.e2 = a.e3 = a.e4 = a.o1 = a.o2 = a.o3 = 0; }
 SVB_D void dot_mac(dot_acc& a, u64 x, u64 y) {
     u32 x0 = (u32)x, x1 = (u32)(x >> 32), y0 = (u32)y, y1 = (u32)(y >> 32);
-    asm("mad.lo.cc.u32 %0, %8, %10, %0;\n\t"
-        "madc.hi.cc.u32 %1, %8, %10, %1;\n\t"
-        "madc.lo.cc.u32 %2, %9, %11, %2;\n\t"
-        "madc.hi.cc.u32 %3, %9, %11, %3;\n\t"
-        "addc.u32 %4, %4, 0;\n\t"
-        "mad.lo.cc.u32 %5, %8, %11, %5;\n\t"
-        "madc.hi.cc.u32 %6, %8, %11, %6;\n\t"
-        "addc.u32 %7, %7, 0;\n\t"
-        "mad.lo.cc.u32 %5, %9, %10, %5;\n\t"
-        "madc.hi.cc.u32 %6, %9, %10, %6;\n\t"
-        "addc.u32 %7, %7, 0;"
-        : "+r"(a.e0), "+r"(a.e1), "+r"(a.e2), "+r"(a.e3), "+r"(a.e4), "+r"(a.o0), "+r"(a.o1), "+r"(a.o2)
+    asm("mad.lo.cc.u32 %0, %8, %10, %0;\n\t madc.hi.cc.u32 %1, %8, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %11, %2;\n\t madc.hi.cc.u32 %3, %9, %11, %3;\n\t addc.u32 %4, %4, 0;\n\t"
+        "mad.lo.cc.u32 %5, %8, %11, %5;\n\t madc.hi.cc.u32 %6, %8, %11, %6;\n\t addc.u32 %7, %7, 0;\n\t"
+        "mad.lo.cc.u32 %5, %9, %10, %5;\n\t madc.hi.cc.u32 %6, %9, %10, %6;\n\t addc.u32 %7, %7, 0;"
+        : "+r"(a.e0), "+r"(a.e1), "+r"(a.e2), "+r"(a.e3), "+r"(a.e4), "+r"(a.o1), "+r"(a.o2), "+r"(a.o3)
         : "r"(x0), "r"(x1), "r"(y0), "r"(y1));
 }
 // small constant k (< 2^32) times y
 SVB_D void dot_mac_small(dot_acc& a, u32 k, u64 y) {
     u32 y0 = (u32)y, y1 = (u32)(y >> 32);
-    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t"
-        "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
-        "addc.cc.u32 %2, %2, 0;\n\t"
-        "addc.cc.u32 %3, %3, 0;\n\t"
-        "addc.u32 %4, %4, 0;\n\t"
+    asm("mad.lo.cc.u32 %0, %5, %6, %0;\n\t madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t addc.cc.u32 %3, %3, 0;\n\t addc.u32 %4, %4, 0;"
         : "+r"(a.e0), "+r"(a.e1), "+r"(a.e2), "+r"(a.e3), "+r"(a.e4)
         : "r"(k), "r"(y0));
-    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
-        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
-        "addc.u32 %2, %2, 0;"
-        : "+r"(a.o0), "+r"(a.o1), "+r"(a.o2)
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t madc.hi.cc.u32 %1, %3, %4, %1;\n\t addc.u32 %2, %2, 0;"
+        : "+r"(a.o1), "+r"(a.o2), "+r"(a.o3)
         : "r"(k), "r"(y1));
 }
 SVB_D u64 dot_reduce(dot_acc a) {
-    // T = E + (O << 32), then lo + hi*2^64 + top*2^128 with 2^128 = -2^32
-    asm("add.cc.u32 %0, %0, %4;\n\t"
-        "addc.cc.u32 %1, %1, %5;\n\t"
-        "addc.cc.u32 %2, %2, %6;\n\t"
-        "addc.u32 %3, %3, 0;"
+    // T = E + O*W (5 limbs), then red5 folds W^4 = -W
+    asm("add.cc.u32 %0, %0, %4;\n\t addc.cc.u32 %1, %1, %5;\n\t addc.cc.u32 %2, %2, %6;\n\t addc.u32 %3, %3, 0;"
         : "+r"(a.e1), "+r"(a.e2), "+r"(a.e3), "+r"(a.e4)
-        : "r"(a.o0), "r"(a.o1), "r"(a.o2));
-    u64 r = reduce128(((u64)a.e1 << 32) | a.e0, ((u64)a.e3 << 32) | a.e2);
-    u64 sub = (u64)a.e4 << 32;
-    u64 d = r - sub;
-    return r < sub ? d - GL_EPS : d;
+        : "r"(a.o1), "r"(a.o2), "r"(a.o3));
+    return red5(a.e0, a.e1, a.e2, a.e3, a.e4);
 }
 
-// v*x + c -> LOOSE, one carry chain for the product and the addend
-SVB_D u64 mul_add_dev(u64 v, u64 x, u64 c) {
-    u32 v0 = (u32)v, v1 = (u32)(v >> 32), x0 = (u32)x, x1 = (u32)(x >> 32);
-    u32 c0 = (u32)c, c1 = (u32)(c >> 32);
-    u32 r0, r1, r2, r3;
-    asm("{\n\t"
-        ".reg .u32 m0, m1, m2;\n\t"
-        "mad.lo.cc.u32 %0, %4, %6, %8;\n\t"
-        "madc.hi.cc.u32 %1, %4, %6, %9;\n\t"
-        "madc.lo.cc.u32 %2, %5, %7, 0;\n\t"
-        "madc.hi.u32 %3, %5, %7, 0;\n\t"
-        "mul.lo.u32 m0, %4, %7;\n\t"
-        "mul.hi.u32 m1, %4, %7;\n\t"
-        "mad.lo.cc.u32 m0, %5, %6, m0;\n\t"
-        "madc.hi.cc.u32 m1, %5, %6, m1;\n\t"
-        "addc.u32 m2, 0, 0;\n\t"
-        "add.cc.u32 %1, %1, m0;\n\t"
-        "addc.cc.u32 %2, %2, m1;\n\t"
-        "addc.u32 %3, %3, m2;\n\t"
-        "}"
-        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
-        : "r"(v0), "r"(v1), "r"(x0), "r"(x1), "r"(c0), "r"(c1));
-    return reduce128(((u64)r1 << 32) | r0, ((u64)r3 << 32) | r2);
+// x^7 + c: the additive constant rides on the last product
+SVB_D u64 sbox7_add(u64 x, u64 c) {
+    u64 x2 = mul(x, x);
+    u64 x4 = mul(x2, x2);
+    u64 x3 = mul(x, x2);
+    return mul_add(x3, x4, c);
 }
 
-// Rotate the 12-word state left by 4 words (register moves).
-SVB_D void rot4(u64 s[12]) {
+// S-box lanes per loop iteration of the full-round S-box layer: 12 = fully unrolled (no register
+// rotation, largest code), 6 or 4 = looped with the state rotated between iterations.
+#ifndef SVB_SBOX_LANES
+#define SVB_SBOX_LANES 4
+#endif
+// Rotate the 12-word state left by SVB_SBOX_LANES words (register moves).
+SVB_D void rot_lanes(u64 s[12]) {
+    u64 t[12];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        u64 t = s[i];
-        s[i] = s[i + 4];
-        s[i + 4] = s[i + 8];
-        s[i + 8] = t;
-    }
+    for (int i = 0; i < 12; i++) t[i] = s[(i + SVB_SBOX_LANES) % 12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = t[i];
 }
 
 // d_FULL_RC_NEXT (derived table, poseidon_g_constants.inc): constants folded into the MDS layer that
@@ -334,13 +307,18 @@ SVB_D void poseidon_g_dev(u64 s[12], u64* __restrict__ scratch /* 11 words of pe
 #pragma unroll 1
     for (int f = 0; f < 8; f++) {
         // S-box layer: 4 lanes per iteration, state rotated by 4 between iterations (:438-448)
-#pragma unroll 1
-        for (int g = 0; g < 3; g++) {
+#if SVB_SBOX_LANES == 12
 #pragma unroll
-            for (int i = 0; i < 4; i++) s[i] = sbox7(s[i]);
-            rot4(s);
+        for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+#else
+#pragma unroll 1
+        for (int g = 0; g < 12 / SVB_SBOX_LANES; g++) {
+#pragma unroll
+            for (int i = 0; i < SVB_SBOX_LANES; i++) s[i] = sbox7(s[i]);
+            rot_lanes(s);
         }
-        mds_layer_rc_f64(s, d_FULL_RC_NEXT + 12 * f);   // (:450-502) + next constant layer
+#endif
+        mds_layer_rc_f64(s, d_FULL_RC_NEXT_F64 + 24 * f);   // (:450-502) + next constant layer
         if (f == 3) {
             // mds_partial_layer_init (:504-537): t[c] = sum_{r=1..11} INIT[r-1][c-1] * s[r]
 #pragma unroll 1
@@ -348,7 +326,7 @@ SVB_D void poseidon_g_dev(u64 s[12], u64* __restrict__ scratch /* 11 words of pe
                 dot_acc a;
                 dot_init(a);
 #pragma unroll
-                for (int r = 1; r < 12; r++) dot_mac(a, d_FAST_PARTIAL_ROUND_INITIAL_MATRIX[(r - 1) * 11 + c], s[r]);
+                for (int r = 1; r < 12; r++) dot_mac(a, s[r], d_FAST_PARTIAL_ROUND_INITIAL_MATRIX[(r - 1) * 11 + c]);
                 scratch[c * scratch_stride] = dot_reduce(a);
             }
 #pragma unroll
@@ -356,16 +334,15 @@ SVB_D void poseidon_g_dev(u64 s[12], u64* __restrict__ scratch /* 11 words of pe
             // 22 partial rounds (:654-672)
 #pragma unroll 1
             for (int r = 0; r < 22; r++) {
-                u64 s0 = sbox7(s[0]);
-                s0 = add_lc(s0, d_FAST_PARTIAL_ROUND_CONSTANTS[r]);   // entry 21 is 0 (:140)
+                u64 s0 = sbox7_add(s[0], d_FAST_PARTIAL_ROUND_CONSTANTS[r]);   // entry 21 is 0 (:140)
                 // mds_partial_layer_fast (:539-589)
                 dot_acc a;
                 dot_init(a);
                 dot_mac_small(a, 25, s0);   // MDS_MATRIX_CIRC[0] + MDS_MATRIX_DIAG[0]
 #pragma unroll
-                for (int i = 1; i < 12; i++) dot_mac(a, d_FAST_PARTIAL_ROUND_W_HATS[r * 11 + i - 1], s[i]);
+                for (int i = 1; i < 12; i++) dot_mac(a, s[i], d_FAST_PARTIAL_ROUND_W_HATS[r * 11 + i - 1]);
 #pragma unroll
-                for (int i = 1; i < 12; i++) s[i] = mul_add_dev(d_FAST_PARTIAL_ROUND_VS[r * 11 + i - 1], s0, s[i]);
+                for (int i = 1; i < 12; i++) s[i] = mul_add(d_FAST_PARTIAL_ROUND_VS[r * 11 + i - 1], s0, s[i]);
                 s[0] = dot_reduce(a);
             }
             // constant layer of full round 26 (:675-678)

@@ -20,6 +20,33 @@ def test_permute_kat_and_random(svb, orc, ctx):
     assert int(got.reshape(-1, 12)[2, 0]) == 0xbe0085cfc57a8357
 
 
+def test_field_corner_cases(svb, ctx):
+    """a*b + c mod p on the device against Python big integers, on operands whose 128-bit products hit
+    the rare limb patterns of the reduction (borrow with a zero middle limb, carry out of the
+    EPS multiply-add, both at once) -- random operands reach those with probability ~2^-32."""
+    sp = [0, 1, 2, 0xFFFFFFFF, 0x100000000, 0x100000001, 0xFFFFFFFF00000000, P - 1, P, P + 1, 2**64 - 1,
+          0xFFFFFFFEFFFFFFFF, 1 << 48, 5 << 48, 1 << 63, 0x00000001FFFFFFFF, 0x0000FFFF0000FFFF, 3 << 62,
+          0x7FFFFFFF80000001, 0xFFFFFFFF, 0xFFFFFFFE00000001, 0x8000000000000001]
+    a, b, c = [], [], []
+    for x in sp:
+        for y in sp:
+            for z in sp[::3]:
+                a.append(x); b.append(y); c.append(z)
+    rng = np.random.default_rng(7)
+    # products with chosen low / high limbs: a = 2^k, b = pattern
+    for k in (16, 31, 32, 33, 47, 48, 63):
+        for pat in (0xFFFFFFFF, 0xFFFFFFFF00000000, 0x00000001FFFFFFFF, 0x8000000080000000, 2**64 - 1):
+            a.append(1 << k); b.append(pat); c.append(int(rng.integers(0, 2**63)))
+    ra = rng.integers(0, 2**64, size=20000, dtype=np.uint64); rb = rng.integers(0, 2**64, size=20000, dtype=np.uint64)
+    rc = rng.integers(0, 2**64, size=20000, dtype=np.uint64)
+    A = np.concatenate([np.array(a, dtype=np.uint64), ra]); B = np.concatenate([np.array(b, dtype=np.uint64), rb])
+    C = np.concatenate([np.array(c, dtype=np.uint64), rc])
+    got = ctx.goldilocks_mul_add_batch(A, B, C)
+    want = np.array([(int(x) * int(y) + int(z)) % P for x, y, z in zip(A, B, C)], dtype=np.uint64)
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, [(hex(int(A[i])), hex(int(B[i])), hex(int(C[i])), hex(int(got[i])), hex(int(want[i]))) for i in bad[:5]]
+
+
 def test_permute_empty(svb, ctx):
     out = ctx.poseidon_permute_batch(np.zeros((0, 12), dtype=np.uint64))
     assert out.size == 0

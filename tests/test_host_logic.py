@@ -87,7 +87,7 @@ def test_abi_exports_every_declared_symbol(svb):
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     names = set(re.findall(r"\b(sv_[a-z0-9_]+)\s*\(", hdr))
     assert {"sv_ctx_create", "sv_fri_verify_batch", "sv_merkle_verify_batch", "sv_poseidon_permute_batch",
-            "sv_allgather_bitmap", "sv_fri_challenges", "sv_synth_proofs"} <= names
+            "sv_allgather_bitmap", "sv_fri_challenges", "sv_synth_proofs", "sv_goldilocks_mul_add_batch"} <= names
     L = ctypes.CDLL(svb.lib_path())
     for n in sorted(names):
         assert hasattr(L, n), f"{n} declared in include/stark_verifier_b200.h but not exported"

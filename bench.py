@@ -27,13 +27,13 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="A", choices=["A", "B", "merkle"])
     ap.add_argument("--proofs", type=int, default=0, help="proofs per GPU per step (default 4096 for A, 256 for B)")
     ap.add_argument("--distinct", type=int, default=0, help="distinct base proofs generated on the host (default 64 / 4)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the cpu_baseline sample (default: sized for ~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -250,7 +250,7 @@ def main():
     if not args.no_e2e:
         ctx.set_stream(0)
         hb = np.zeros(words, dtype=np.uint32)
-        e2e_steps = max(2, min(args.steps, 5))
+        e2e_steps = max(2, min(args.steps, 10))
         for _ in range(2):
             ctx.fri_verify_batch(params, host.data_ptr(), n_proofs=n, accept_bitmap=hb, mem=svb.MEM_HOST)
         assert (hb == exp).all()
@@ -297,10 +297,22 @@ def main():
                      "peak_source": peak_src,
                      "note": "integer-issue bound, not HBM bound (SURVEY 8d): see perms_per_sec"},
         "perms_per_sec": world * perms * args.steps / (ms / 1e3),
+        # what actually binds: the 32x32->64 integer multiplier.  IMAD.WIDE issues every
+        # 4.24 cycles per SM sub-partition (profiles/pipes2_b200_r1.txt); a permutation needs 4 308
+        # of them algorithmically (1 077 modular multiplications x 4 limb products).
+        "int_mul_roofline": {"achieved_gmul_s": perms * 4308 / k_avg_s / 1e9,
+                             "peak_gmul_s": 148 * 4 * 32 / 4.24 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
+                             "frac": (perms * 4308 / k_avg_s) / (148 * 4 * 32 / 4.24 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
+                             "unit": "1e9 32x32->64 multiplies/s", "kernel": "fri_query_kernel"},
         "synth_seconds": t_gen,
     }
     if not args.no_cpu_baseline:
-        sample = args.cpu_sample or (32 * threads if args.workload == "A" else threads)
+        sample = args.cpu_sample
+        if not sample:
+            # probe on a small batch, then size the sample for ~12 s of CPU work on all host threads
+            probe = 8 * threads if args.workload == "A" else threads
+            v0, _, _ = cpu_baseline(svb, params, base, probe, threads)
+            sample = max(probe, int(v0 * 12.0) // threads * threads)
         v, dt, _ = cpu_baseline(svb, params, base, sample, threads)
         out["cpu_baseline"] = {"value": v, "unit": "proofs/s", "cores": threads, "kind": "port",
                                "sample": f"{sample} proofs of the same workload in {dt:.1f} s on {threads} threads; oracle/oracle.c, "

@@ -152,6 +152,23 @@ int sv_merkle_verify_batch(sv_ctx* ctx, uint32_t leaf_len, uint32_t depth, uint3
 int sv_fri_verify_batch(sv_ctx* ctx, const sv_fri_shape* shape, size_t n_proofs, const uint64_t* records,
                         uint32_t* accept_bitmap, uint32_t* first_fail, int mem);
 
+/* Device-side Fiat-Shamir: the transcript of sv_fri_challenges for n_proofs records at once,
+ * one GPU thread per proof; rewrites zeta, zeta_next, alpha, betas, pow_response and indices of every
+ * record header in place.  circuit_digest is ALWAYS a host pointer (4 words, one circuit per batch);
+ * public_inputs_hashes (n_proofs x 4 words) lives where `mem` says, like the records.
+ * Replaces: PlonkVerifierChip::get_challenges (chip/plonk/plonk_verifier_chip.rs:55-154). */
+int sv_fri_challenges_batch(sv_ctx* ctx, const sv_fri_shape* shape, size_t n_proofs, uint64_t* records,
+                            const uint64_t circuit_digest[4], const uint64_t* public_inputs_hashes,
+                            uint32_t num_challenges, int mem);
+
+/* get_challenges + verify_fri_proof in one call: the challenge fields of the records are ignored on
+ * input and derived on the device before the query phase.  SV_MEM_DEVICE: the device records get their
+ * challenge fields overwritten; SV_MEM_HOST: the host records are not modified.
+ * Replaces: plonk_verifier_chip.rs:55-154 followed by chip/fri_chip.rs:329-362. */
+int sv_fri_verify_batch_fs(sv_ctx* ctx, const sv_fri_shape* shape, size_t n_proofs, uint64_t* records,
+                           const uint64_t circuit_digest[4], const uint64_t* public_inputs_hashes,
+                           uint32_t num_challenges, uint32_t* accept_bitmap, uint32_t* first_fail, int mem);
+
 /* Gather the per-rank accept bitmaps of a sharded batch: ncclAllGather(local -> full) on the ctx
  * stream.  nccl_comm is an ncclComm_t; libnccl.so.2 is resolved at run time (dlopen).  New -- the
  * reference is single-process. */
@@ -172,6 +189,12 @@ int sv_fri_challenges(const sv_fri_shape* shape, uint64_t* record, const uint64_
  * (plonky2_semaphore/*, not on the hot path) -- test/bench data only. */
 int sv_synth_proofs(const sv_fri_shape* shape, uint64_t seed, uint32_t n_circuits, size_t n_proofs,
                     uint32_t num_challenges, uint64_t* records_out, int nthreads);
+
+/* The transcript inputs sv_synth_proofs used for the same (shape, seed, n_circuits, n_proofs):
+ * circuit_digests_out: n_circuits x 4 words (proof i belongs to circuit i % n_circuits),
+ * pi_hashes_out: n_proofs x 4 words.  Either pointer may be NULL. */
+int sv_synth_public_inputs(const sv_fri_shape* shape, uint64_t seed, uint32_t n_circuits, size_t n_proofs,
+                           uint64_t* circuit_digests_out, uint64_t* pi_hashes_out);
 
 /* library / build info */
 const char* sv_version(void);

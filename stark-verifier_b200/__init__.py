@@ -25,6 +25,7 @@ from .api import (  # noqa: F401
     lib,
     lib_path,
     synth_proofs,
+    synth_public_inputs,
     MEM_HOST,
     MEM_DEVICE,
 )

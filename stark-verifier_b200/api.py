@@ -155,6 +155,10 @@ def lib() -> ctypes.CDLL:
     L.sv_fri_challenges.argtypes = [ctypes.POINTER(FriShape), vp, vp, vp, ctypes.c_uint32]
     L.sv_synth_proofs.argtypes = [ctypes.POINTER(FriShape), u64, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_uint32,
                                   vp, ctypes.c_int]
+    L.sv_synth_public_inputs.argtypes = [ctypes.POINTER(FriShape), u64, ctypes.c_uint32, ctypes.c_size_t, vp, vp]
+    L.sv_fri_challenges_batch.argtypes = [vp, ctypes.POINTER(FriShape), ctypes.c_size_t, vp, vp, vp, ctypes.c_uint32, ctypes.c_int]
+    L.sv_fri_verify_batch_fs.argtypes = [vp, ctypes.POINTER(FriShape), ctypes.c_size_t, vp, vp, vp, ctypes.c_uint32, vp, vp,
+                                         ctypes.c_int]
     _LIB = L
     return L
 
@@ -189,6 +193,18 @@ def synth_proofs(params: FriParams, n_proofs: int, seed: int = 0xB2000002, n_cir
     if rc != 0:
         raise SvError(f"sv_synth_proofs failed: {rc}")
     return out
+
+
+def synth_public_inputs(params: FriParams, n_proofs: int, seed: int = 0xB2000002, n_circuits: int = 1):
+    """(circuit_digests[n_circuits,4], pi_hashes[n_proofs,4]) that synth_proofs used with the same arguments."""
+    s = params.to_shape()
+    nc = max(1, min(n_circuits, n_proofs))
+    cd = np.zeros((nc, 4), dtype=np.uint64)
+    ph = np.zeros((n_proofs, 4), dtype=np.uint64)
+    rc = lib().sv_synth_public_inputs(ctypes.byref(s), ctypes.c_uint64(seed), n_circuits, n_proofs, _ptr(cd), _ptr(ph))
+    if rc != 0:
+        raise SvError(f"sv_synth_public_inputs failed: {rc}")
+    return cd, ph
 
 
 def fri_challenges(params: FriParams, record: np.ndarray, circuit_digest, pi_hash, num_challenges: int = 2) -> None:
@@ -287,6 +303,36 @@ class Context:
         self._ck(self._lib.sv_fri_verify_batch(self._h, ctypes.byref(s), n_proofs, _ptr(records), _ptr(accept_bitmap),
                                                _ptr(first_fail) if first_fail is not None else None, mem),
                  "sv_fri_verify_batch")
+        return (accept_bitmap, first_fail) if want_fail else accept_bitmap
+
+    def fri_challenges_batch(self, params: FriParams, records, circuit_digest, pi_hashes, num_challenges: int = 2,
+                             n_proofs: Optional[int] = None, mem: int = MEM_HOST):
+        """Device-side Fiat-Shamir: rewrites the challenge fields of every record (in place)."""
+        s = params.to_shape()
+        cd = np.ascontiguousarray(circuit_digest, dtype=np.uint64)
+        if mem == MEM_HOST:
+            n_proofs = records.shape[0]
+            pi_hashes = np.ascontiguousarray(pi_hashes, dtype=np.uint64)
+        self._ck(self._lib.sv_fri_challenges_batch(self._h, ctypes.byref(s), n_proofs, _ptr(records), _ptr(cd), _ptr(pi_hashes),
+                                                   num_challenges, mem), "sv_fri_challenges_batch")
+        return records
+
+    def fri_verify_batch_fs(self, params: FriParams, records, circuit_digest, pi_hashes, num_challenges: int = 2,
+                            n_proofs: Optional[int] = None, accept_bitmap=None, first_fail=None, want_fail: bool = False,
+                            mem: int = MEM_HOST):
+        """get_challenges + verify_fri_proof: the challenge fields of `records` are derived on the device."""
+        s = params.to_shape()
+        cd = np.ascontiguousarray(circuit_digest, dtype=np.uint64)
+        if mem == MEM_HOST:
+            n_proofs = records.shape[0] if n_proofs is None else n_proofs
+            pi_hashes = np.ascontiguousarray(pi_hashes, dtype=np.uint64)
+            accept_bitmap = np.zeros((n_proofs + 31) // 32, dtype=np.uint32) if accept_bitmap is None else accept_bitmap
+            if want_fail and first_fail is None:
+                first_fail = np.zeros(n_proofs, dtype=np.uint32)
+        self._ck(self._lib.sv_fri_verify_batch_fs(self._h, ctypes.byref(s), n_proofs, _ptr(records), _ptr(cd), _ptr(pi_hashes),
+                                                  num_challenges, _ptr(accept_bitmap),
+                                                  _ptr(first_fail) if first_fail is not None else None, mem),
+                 "sv_fri_verify_batch_fs")
         return (accept_bitmap, first_fail) if want_fail else accept_bitmap
 
     def allgather_bitmap(self, nccl_comm: int, local_ptr: int, all_ptr: int, words_per_rank: int):

@@ -30,6 +30,7 @@ struct sv_ctx {
     u64* d_stage[SV_NBUF] = {}; size_t stage_words[SV_NBUF] = {};   // H2D chunk ring
     u32* d_bitmap = nullptr; size_t bitmap_words = 0;
     u32* d_fail = nullptr; size_t fail_words = 0;
+    u64* d_pi = nullptr; size_t pi_words = 0;                          // public-input hashes (device-side transcript)
     cudaEvent_t ev_copied[SV_NBUF] = {}, ev_done[SV_NBUF] = {}, ev_join = nullptr;
     uint64_t launches = 0;
     // optional CUDA-event timing of the dominant kernel (fri_query_kernel / merkle / permute), on
@@ -101,6 +102,7 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     for (int i = 0; i < SV_NBUF; i++) cudaFree(c->d_stage[i]);
     cudaFree(c->d_bitmap);
     cudaFree(c->d_fail);
+    cudaFree(c->d_pi);
     for (int i = 0; i < SV_NBUF; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_done[i]); }
     cudaEventDestroy(c->ev_join);
     for (auto& pr : c->tev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -301,6 +303,15 @@ static int make_params(sv_ctx* c, const sv_fri_shape& s, FriKernelParams& P) {
 }
 
 // enqueue prepare + query (+ finalize) for `n` proofs whose records are at d_records
+static int enqueue_challenges(sv_ctx* c, FriKernelParams& P, const FsParams& F, size_t n, u64* d_records, const u64* d_pi,
+                              cudaStream_t s) {
+    P.n_proofs = (u32)n;
+    fri_challenges_kernel<<<(unsigned)((n + SVB_FS_BLOCK - 1) / SVB_FS_BLOCK), SVB_FS_BLOCK, 0, s>>>(d_records, P, F, d_pi);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return 0;
+}
+
 static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_records, u64* d_scratch, u32* d_bitmap,
                        u32* d_fail, cudaStream_t s) {
     const int B = SVB_BLOCK;
@@ -320,8 +331,10 @@ static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_rec
     return 0;
 }
 
-extern "C" int sv_fri_verify_batch(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs, const uint64_t* records,
-                                   uint32_t* accept_bitmap, uint32_t* first_fail, int mem) {
+// fs == nullptr: the records carry their challenges.  Otherwise the transcript runs on the device first
+// (pi_hashes: n_proofs x 4 words, same memory space as the records).
+static int fri_verify_impl(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs, const uint64_t* records,
+                           uint32_t* accept_bitmap, uint32_t* first_fail, int mem, const FsParams* fs, const uint64_t* pi_hashes) {
     if (!c || !shape || !records || !accept_bitmap) return -1;
     FriKernelParams P;
     int rc = make_params(c, *shape, P);
@@ -332,7 +345,11 @@ extern "C" int sv_fri_verify_batch(sv_ctx* c, const sv_fri_shape* shape, size_t 
     size_t rw = P.L.record_words;
     if (grow(c, c->d_scratch, c->scratch_words, 4 * n_proofs)) return -6;
 
-    if (mem == SV_MEM_DEVICE) return enqueue_fri(c, P, n_proofs, records, c->d_scratch, accept_bitmap, first_fail, c->stream);
+    if (mem == SV_MEM_DEVICE) {
+        if (fs && (rc = enqueue_challenges(c, P, *fs, n_proofs, const_cast<u64*>(records), pi_hashes, c->stream))) return rc;
+        return enqueue_fri(c, P, n_proofs, records, c->d_scratch, accept_bitmap, first_fail, c->stream);
+    }
+    if (fs && grow(c, c->d_pi, c->pi_words, 4 * n_proofs)) return -6;
 
     // Host buffers: chunks of whole 32-proof bitmap words move through a ring of SV_NBUF staging
     // buffers.  H2D copies run back to back on the copy stream; the kernels of consecutive chunks
@@ -356,8 +373,10 @@ extern "C" int sv_fri_verify_batch(sv_ctx* c, const sv_fri_shape* shape, size_t 
         size_t first = i * chunk, cnt = std::min(chunk, n_proofs - first);
         if (i >= SV_NBUF) CK(c, cudaStreamWaitEvent(cs, c->ev_done[b], 0));   // buffer b free again
         CK(c, cudaMemcpyAsync(c->d_stage[b], records + first * rw, cnt * rw * 8, cudaMemcpyHostToDevice, cs));
+        if (fs) CK(c, cudaMemcpyAsync(c->d_pi + 4 * first, pi_hashes + 4 * first, cnt * 32, cudaMemcpyHostToDevice, cs));
         CK(c, cudaEventRecord(c->ev_copied[b], cs));
         CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
+        if (fs && (rc = enqueue_challenges(c, P, *fs, cnt, c->d_stage[b], c->d_pi + 4 * first, k))) return rc;
         rc = enqueue_fri(c, P, cnt, c->d_stage[b], c->d_scratch + 4 * first, c->d_bitmap + first / 32,
                          first_fail ? c->d_fail + first : nullptr, k);
         if (rc) return rc;
@@ -371,6 +390,58 @@ extern "C" int sv_fri_verify_batch(sv_ctx* c, const sv_fri_shape* shape, size_t 
     CK(c, cudaMemcpyAsync(accept_bitmap, c->d_bitmap, n_words * 4, cudaMemcpyDeviceToHost, ks[0]));
     if (first_fail) CK(c, cudaMemcpyAsync(first_fail, c->d_fail, n_proofs * 4, cudaMemcpyDeviceToHost, ks[0]));
     CK(c, cudaStreamSynchronize(ks[0]));
+    return 0;
+}
+
+extern "C" int sv_fri_verify_batch(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs, const uint64_t* records,
+                                   uint32_t* accept_bitmap, uint32_t* first_fail, int mem) {
+    return fri_verify_impl(c, shape, n_proofs, records, accept_bitmap, first_fail, mem, nullptr, nullptr);
+}
+
+static int make_fs(sv_ctx* c, const sv_fri_shape* shape, const uint64_t circuit_digest[4], uint32_t num_challenges, FsParams& F) {
+    if (!shape || !circuit_digest) return -1;
+    if (num_challenges == 0 || num_challenges > 16) return fail(c, -8, "num_challenges out of range");
+    for (int i = 0; i < 4; i++) {
+        if (!is_canonical(circuit_digest[i])) return fail(c, -8, "circuit_digest word >= p");
+        F.circuit_digest[i] = circuit_digest[i];
+    }
+    F.g = svb::pow(7, (GL_P - 1) >> shape->degree_bits);
+    F.num_challenges = num_challenges;
+    return 0;
+}
+
+extern "C" int sv_fri_verify_batch_fs(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs, uint64_t* records,
+                                      const uint64_t circuit_digest[4], const uint64_t* public_inputs_hashes,
+                                      uint32_t num_challenges, uint32_t* accept_bitmap, uint32_t* first_fail, int mem) {
+    if (!c || !public_inputs_hashes) return -1;
+    FsParams F;
+    int rc = make_fs(c, shape, circuit_digest, num_challenges, F);
+    if (rc) return rc;
+    return fri_verify_impl(c, shape, n_proofs, records, accept_bitmap, first_fail, mem, &F, public_inputs_hashes);
+}
+
+extern "C" int sv_fri_challenges_batch(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs, uint64_t* records,
+                                       const uint64_t circuit_digest[4], const uint64_t* public_inputs_hashes,
+                                       uint32_t num_challenges, int mem) {
+    if (!c || !records || !public_inputs_hashes) return -1;
+    FsParams F;
+    int rc = make_fs(c, shape, circuit_digest, num_challenges, F);
+    if (rc) return rc;
+    FriKernelParams P;
+    if ((rc = make_params(c, *shape, P))) return rc;
+    if (n_proofs == 0) return 0;
+    CK(c, cudaSetDevice(c->device));
+    if (mem == SV_MEM_DEVICE) return enqueue_challenges(c, P, F, n_proofs, records, public_inputs_hashes, c->stream);
+    // host records: only the header (caps, openings, final poly, pow witness) travels, in both directions
+    size_t rw = P.L.record_words, hw = P.L.header_words;
+    if (grow(c, c->d_stage[0], c->stage_words[0], n_proofs * rw)) return -6;
+    if (grow(c, c->d_pi, c->pi_words, 4 * n_proofs)) return -6;
+    cudaStream_t s = c->own_stream;
+    CK(c, cudaMemcpy2DAsync(c->d_stage[0], rw * 8, records, rw * 8, hw * 8, n_proofs, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(c->d_pi, public_inputs_hashes, n_proofs * 32, cudaMemcpyHostToDevice, s));
+    if ((rc = enqueue_challenges(c, P, F, n_proofs, c->d_stage[0], c->d_pi, s))) return rc;
+    CK(c, cudaMemcpy2DAsync(records, rw * 8, c->d_stage[0], rw * 8, hw * 8, n_proofs, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
     return 0;
 }
 

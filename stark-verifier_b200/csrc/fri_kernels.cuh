@@ -309,6 +309,93 @@ __global__ void goldilocks_mul_add_kernel(const u64* __restrict__ a, const u64* 
     out[i] = canon(mul_add(a[i], b[i], c[i]));
 }
 
+// ---- device-side Fiat-Shamir -------------------------------------------------------
+// One thread per proof replays PlonkVerifierChip::get_challenges (chip/plonk/plonk_verifier_chip.rs:
+// 55-154) over the duplex sponge of HasherChip (chip/hasher_chip.rs:51-120: rate 8, overwrite mode,
+// squeeze pops from the END of state[0..8]) and writes zeta, zeta_next = g*zeta, fri_alpha, fri_betas,
+// fri_pow_response and the query indices into the record header -- the same fields, in the same
+// order, as the host-side sv_fri_challenges.  ~85 dependent permutations per proof: latency-bound, so
+// it runs on its own small blocks beside the query kernel of the neighbouring chunk.
+#define SVB_FS_BLOCK 32
+struct FsParams {
+    u64 circuit_digest[4];
+    u64 g;                 // generator of the trace subgroup, 7^((p-1)/2^degree_bits)
+    u32 num_challenges;
+};
+struct DevChallenger {
+    u64 st[12];
+    u64 in[8], out[8];     // dynamically indexed: local memory, negligible beside the permutations
+    int n_in, n_out;
+    u64* scratch;
+    // one out-of-line copy of the permutation for the ~10 call sites of the transcript
+    __device__ __noinline__ void permute() {
+        poseidon_g_dev(st, scratch, SVB_FS_BLOCK);
+#pragma unroll
+        for (int i = 0; i < 12; i++) st[i] = canon(st[i]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) out[i] = st[i];
+        n_out = 8;
+    }
+    SVB_D void duplex(int len) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < len) st[i] = in[i];
+        permute();
+        n_in = 0;
+    }
+    SVB_D void observe(u64 v) {
+        n_out = 0;                 // update() clears the output buffer (hasher_chip.rs:56)
+        in[n_in++] = v;
+        if (n_in == 8) duplex(8);
+    }
+    SVB_D void observe_n(const u64* __restrict__ p, u32 n) {
+        for (u32 i = 0; i < n; i++) observe(p[i]);
+    }
+    SVB_D u64 squeeze() {
+        if (n_in) duplex(n_in);
+        if (n_out == 0) permute();
+        return out[--n_out];
+    }
+};
+
+__global__ void __launch_bounds__(SVB_FS_BLOCK) fri_challenges_kernel(u64* __restrict__ records, FriKernelParams P, FsParams F,
+                                                                      const u64* __restrict__ pi_hashes) {
+    __shared__ u64 pscratch[11 * SVB_FS_BLOCK];
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.n_proofs) return;
+    const sv_fri_layout& L = P.L;
+    u64* rec = records + (size_t)p * L.record_words;
+    DevChallenger ch;
+#pragma unroll
+    for (int i = 0; i < 12; i++) ch.st[i] = 0;
+    ch.n_in = ch.n_out = 0;
+    ch.scratch = pscratch + threadIdx.x;
+    const u32 cap_words = L.ncap * 4;
+    for (int i = 0; i < 4; i++) ch.observe(F.circuit_digest[i]);                      // :65-68
+    ch.observe_n(pi_hashes + 4 * (size_t)p, 4);                                       // :69-71
+    ch.observe_n(rec + L.off_init_caps + 1 * cap_words, cap_words);                   // wires_cap
+    for (u32 i = 0; i < 2 * F.num_challenges; i++) (void)ch.squeeze();                // plonk betas, gammas
+    ch.observe_n(rec + L.off_init_caps + 2 * cap_words, cap_words);                   // zs_partial_products_cap
+    for (u32 i = 0; i < F.num_challenges; i++) (void)ch.squeeze();                    // plonk alphas
+    ch.observe_n(rec + L.off_init_caps + 3 * cap_words, cap_words);                   // quotient_polys_cap
+    u64 z0 = ch.squeeze(), z1 = ch.squeeze();                                         // plonk_zeta
+    rec[L.off_zeta] = z0; rec[L.off_zeta + 1] = z1;
+    rec[L.off_zeta_next] = mulc(z0, F.g); rec[L.off_zeta_next + 1] = mulc(z1, F.g);
+    ch.observe_n(rec + L.off_open0, 2 * L.n0);                                        // openings, batch order
+    ch.observe_n(rec + L.off_open1, 2 * L.n1);
+    u64 a0 = ch.squeeze(), a1 = ch.squeeze();                                         // fri_alpha
+    rec[L.off_alpha] = a0; rec[L.off_alpha + 1] = a1;
+    for (u32 st = 0; st < P.num_steps; st++) {
+        ch.observe_n(rec + L.off_step_caps + (size_t)st * cap_words, cap_words);
+        u64 b0 = ch.squeeze(), b1 = ch.squeeze();
+        rec[L.off_betas + 2 * st] = b0; rec[L.off_betas + 2 * st + 1] = b1;
+    }
+    ch.observe_n(rec + L.off_final_poly, 2 * P.final_poly_len);
+    ch.observe(rec[L.off_pow_witness]);
+    rec[L.off_pow_response] = ch.squeeze();
+    for (u32 q = 0; q < P.num_queries; q++) rec[L.off_indices + q] = ch.squeeze();
+}
+
 // first_fail post-pass: 0xFFFFFFFF (never failed) -> 0, else (query << 8) | code.
 __global__ void fri_finalize_kernel(u32* __restrict__ first_fail, u32 n) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -175,7 +175,8 @@ struct Circuit {
             for (u32 j = np; j < L.leaf_len[k]; j++) out[j] = r.fe();
         }
     }
-    void build(const sv_fri_shape& s, u64 seed, int nthreads) {
+    // everything drawn from the seed (degrees, coefficients, salt key, circuit digest); no trees yet
+    void init_params(const sv_fri_shape& s, u64 seed) {
         shape = s;
         make_layout(s, L);
         N = 1u << L.lde_bits;
@@ -192,6 +193,9 @@ struct Circuit {
         }
         salt_key = rng.next();
         for (int i = 0; i < 4; i++) circuit_digest[i] = rng.fe();
+    }
+    void build(const sv_fri_shape& s, u64 seed, int nthreads) {
+        init_params(s, seed);
         u64 omega = pow(7, (GL_P - 1) >> L.lde_bits);
         wtab.resize(N);
         wtab[0] = 1;
@@ -447,6 +451,30 @@ extern "C" int sv_fri_challenges(const sv_fri_shape* shape, uint64_t* rec, const
     return 0;
 }
 
+static inline u64 synth_circuit_seed(u64 seed, uint32_t c) { return seed ^ (0x5EED0000ull + c); }
+static inline void synth_pi_hash(u64 seed, size_t i, u64 pi[4]) {
+    Rng r(seed ^ (0xB2000000ull + i * 0x9E3779B97F4A7C15ull));
+    for (int k = 0; k < 4; k++) pi[k] = r.fe();
+}
+
+// The transcript inputs sv_synth_proofs used: circuit digest of circuit c, public-input hash of proof i.
+extern "C" int sv_synth_public_inputs(const sv_fri_shape* shape, uint64_t seed, uint32_t n_circuits, size_t n_proofs,
+                                      uint64_t* circuit_digests_out, uint64_t* pi_hashes_out) {
+    sv_fri_layout L;
+    if (!shape || make_layout(*shape, L)) return -1;
+    if (n_circuits == 0) n_circuits = 1;
+    if (n_circuits > n_proofs) n_circuits = (uint32_t)(n_proofs ? n_proofs : 1);
+    if (circuit_digests_out)
+        for (uint32_t c = 0; c < n_circuits; c++) {
+            Circuit C;
+            C.init_params(*shape, synth_circuit_seed(seed, c));
+            memcpy(circuit_digests_out + 4 * c, C.circuit_digest, 32);
+        }
+    if (pi_hashes_out)
+        for (size_t i = 0; i < n_proofs; i++) synth_pi_hash(seed, i, pi_hashes_out + 4 * i);
+    return 0;
+}
+
 extern "C" int sv_synth_proofs(const sv_fri_shape* shape, uint64_t seed, uint32_t n_circuits, size_t n_proofs,
                                uint32_t num_challenges, uint64_t* records_out, int nthreads) {
     sv_fri_layout L;
@@ -457,7 +485,7 @@ extern "C" int sv_synth_proofs(const sv_fri_shape* shape, uint64_t seed, uint32_
     if (nthreads < 1) nthreads = 1;
     if (n_circuits > n_proofs) n_circuits = (uint32_t)(n_proofs ? n_proofs : 1);
     std::vector<Circuit> circuits(n_circuits);
-    for (uint32_t c = 0; c < n_circuits; c++) circuits[c].build(*shape, seed ^ (0x5EED0000ull + c), nthreads);
+    for (uint32_t c = 0; c < n_circuits; c++) circuits[c].build(*shape, synth_circuit_seed(seed, c), nthreads);
     // proofs are independent: parallelise across proofs when there are many, inside a proof otherwise
     std::atomic<int> err(0);
     bool outer = n_proofs >= (size_t)nthreads;
@@ -466,8 +494,8 @@ extern "C" int sv_synth_proofs(const sv_fri_shape* shape, uint64_t seed, uint32_
         for (;;) {
             size_t i = next.fetch_add(1);
             if (i >= n_proofs) break;
-            Rng r(seed ^ (0xB2000000ull + i * 0x9E3779B97F4A7C15ull));
-            u64 pi[4] = {r.fe(), r.fe(), r.fe(), r.fe()};
+            u64 pi[4];
+            synth_pi_hash(seed, i, pi);
             int rc = prove(circuits[i % n_circuits], pi, num_challenges, records_out + i * (size_t)L.record_words,
                            outer ? 1 : nthreads);
             if (rc) err = rc;

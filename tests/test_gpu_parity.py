@@ -193,3 +193,90 @@ def test_full_size_tiled_batch(svb, orc, ctx):
     assert (bm == exp).all()
     # idempotence: the same call again gives the same bitmap
     assert (ctx.fri_verify_batch(params, recs) == exp).all()
+
+
+def _clear_challenges(recs, L, params):
+    """zero every field the transcript derives"""
+    r = recs.copy()
+    ns = len(params.reduction_arity_bits)
+    for off, n in ((L.off_alpha, 2), (L.off_betas, 2 * ns), (L.off_pow_response, 1),
+                   (L.off_indices, params.config.num_query_rounds), (L.off_zeta, 2), (L.off_zeta_next, 2)):
+        r[:, off:off + n] = 0
+    return r
+
+
+@pytest.mark.parametrize("hiding,cap,degree_bits", [(False, 2, 7), (True, 0, 8), (False, 4, 6)])
+def test_device_transcript_matches_host_and_oracle(svb, orc, ctx, hiding, cap, degree_bits):
+    """sv_fri_challenges_batch (one GPU thread per proof) == host sv_fri_challenges == oracle transcript."""
+    params = tiny_params(svb, hiding=hiding, cap=cap, degree_bits=degree_bits)
+    L = svb.api.make_layout(params)
+    n = 45
+    recs = svb.synth_proofs(params, n, seed=21 + cap, n_circuits=1)
+    rng = np.random.default_rng(99)
+    cd = rng.integers(0, P, size=4, dtype=np.uint64)
+    ph = rng.integers(0, P, size=(n, 4), dtype=np.uint64)
+    dev = _clear_challenges(recs, L, params)
+    ctx.fri_challenges_batch(params, dev, cd, ph)
+    oshape = orc.shape_from(params.to_shape())
+    for i in range(n):
+        h = _clear_challenges(recs[i:i + 1], L, params)[0]
+        svb.fri_challenges(params, h, cd, ph[i])
+        o = _clear_challenges(recs[i:i + 1], L, params)[0]
+        orc.fri_challenges(oshape, o, cd, ph[i])
+        assert (h == o).all()
+        assert (dev[i] == h).all(), i
+    # and with the inputs the prover used, the transcript reproduces the proofs' own challenges
+    cd0, ph0 = svb.synth_public_inputs(params, n, seed=21 + cap, n_circuits=1)
+    dev = _clear_challenges(recs, L, params)
+    ctx.fri_challenges_batch(params, dev, cd0[0], ph0)
+    assert (dev == recs).all()
+
+
+def test_verify_with_device_transcript(svb, orc, ctx):
+    """sv_fri_verify_batch_fs: challenge fields are ignored on input and derived on the device; the accept
+    bitmap equals the oracle's on the fully specified records (host and device memory paths)."""
+    import torch
+    params = tiny_params(svb, cap=3, degree_bits=8)
+    L = svb.api.make_layout(params)
+    n = 96
+    recs = svb.synth_proofs(params, n, seed=5, n_circuits=1)
+    cd, ph = svb.synth_public_inputs(params, n, seed=5, n_circuits=1)
+    # corrupt data the transcript does not observe (siblings / leaf evals / step evals), so that the
+    # derived challenges stay those of the original proof and the oracle can check the same records
+    rng = np.random.default_rng(17)
+    bad = {}
+    for i in range(3, n, 7):
+        q = int(rng.integers(0, params.config.num_query_rounds))
+        qb = L.header_words + q * L.query_words
+        which = i % 3
+        if which == 0:
+            recs[i, qb + L.q_off_init_sibs[1] + 3] ^= np.uint64(2)
+        elif which == 1:
+            recs[i, qb + L.q_off_init_evals[0] + 1] ^= np.uint64(1)
+        else:
+            recs[i, qb + L.q_off_step_evals[0] + 2] ^= np.uint64(4)
+        bad[i] = which
+    ph[10, 0] ^= np.uint64(1)            # wrong public-input hash: different challenges => reject
+    bad[10] = "pi"
+    want = orc.fri_verify_batch(orc.shape_from(params.to_shape()), recs, nthreads=4)
+    stripped = _clear_challenges(recs, L, params)
+    keep = stripped.copy()
+    bm, ff = ctx.fri_verify_batch_fs(params, stripped, cd[0], ph, want_fail=True)
+    assert (stripped == keep).all()                       # SV_MEM_HOST: host records untouched
+    for i in range(n):
+        exp = 0 if i in bad else 1
+        assert bit(bm, i) == exp, (i, bad.get(i))
+        if i != 10:
+            assert bit(bm, i) == bit(want, i)
+    # device-resident records
+    d = torch.from_numpy(stripped.view(np.int64)).cuda()
+    dph = torch.from_numpy(ph.view(np.int64)).cuda()
+    dbm = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.fri_verify_batch_fs(params, d.data_ptr(), cd[0], dph.data_ptr(), n_proofs=n, accept_bitmap=dbm.data_ptr(), mem=svb.MEM_DEVICE)
+    ctx.synchronize()
+    assert (dbm.cpu().numpy().view(np.uint32) == bm).all()
+    # in device mode the challenge fields were written in place
+    back = d.cpu().numpy().view(np.uint64)
+    good = [i for i in range(n) if i != 10]
+    assert (back[good] == recs[good]).all()

@@ -17,12 +17,13 @@
 using namespace svb;
 
 // SV_MEM_HOST pipeline depth: staging buffers in flight (H2D of chunk i+2.. while chunks i, i+1 compute)
-#define SV_NBUF 4
+#define SV_NBUF 6
+#define SV_NKS 4    // compute streams the chunk kernels rotate over
 
 struct sv_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;   // compute
-    cudaStream_t aux_stream = nullptr;   // second compute stream of the SV_MEM_HOST pipeline
+    cudaStream_t aux_stream[SV_NKS - 1] = {};   // further compute streams of the SV_MEM_HOST pipeline
     cudaStream_t copy_stream = nullptr;  // H2D of the next chunks
     cudaStream_t stream = nullptr;       // stream used for SV_MEM_DEVICE work (own or caller's)
     // device scratch, grown on demand, reused across calls (no hidden allocation after warm-up)
@@ -31,7 +32,7 @@ struct sv_ctx {
     u32* d_bitmap = nullptr; size_t bitmap_words = 0;
     u32* d_fail = nullptr; size_t fail_words = 0;
     u64* d_pi = nullptr; size_t pi_words = 0;                          // public-input hashes (device-side transcript)
-    cudaEvent_t ev_copied[SV_NBUF] = {}, ev_done[SV_NBUF] = {}, ev_join = nullptr;
+    cudaEvent_t ev_copied[SV_NBUF] = {}, ev_done[SV_NBUF] = {}, ev_join[SV_NKS] = {};
     uint64_t launches = 0;
     // optional CUDA-event timing of the dominant kernel (fri_query_kernel / merkle / permute), on
     // the stream it is launched on
@@ -82,13 +83,13 @@ extern "C" int sv_ctx_create(int device, sv_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     CK(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    CK(nullptr, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < SV_NKS - 1; i++) CK(nullptr, cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));
     CK(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < SV_NBUF; i++) {
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
-    CK(nullptr, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    for (int i = 0; i < SV_NKS; i++) CK(nullptr, cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     c->stream = c->own_stream;
     *out = c;
     return 0;
@@ -104,10 +105,10 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaFree(c->d_fail);
     cudaFree(c->d_pi);
     for (int i = 0; i < SV_NBUF; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_done[i]); }
-    cudaEventDestroy(c->ev_join);
+    for (int i = 0; i < SV_NKS; i++) cudaEventDestroy(c->ev_join[i]);
     for (auto& pr : c->tev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaStreamDestroy(c->own_stream);
-    cudaStreamDestroy(c->aux_stream);
+    for (int i = 0; i < SV_NKS - 1; i++) cudaStreamDestroy(c->aux_stream[i]);
     cudaStreamDestroy(c->copy_stream);
     if (c->nccl_lib) dlclose(c->nccl_lib);
     delete c;
@@ -123,7 +124,7 @@ extern "C" int sv_ctx_synchronize(sv_ctx* c) {
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaStreamSynchronize(c->own_stream));
-    CK(c, cudaStreamSynchronize(c->aux_stream));
+    for (int i = 0; i < SV_NKS - 1; i++) CK(c, cudaStreamSynchronize(c->aux_stream[i]));
     CK(c, cudaStreamSynchronize(c->copy_stream));
     return 0;
 }
@@ -353,23 +354,28 @@ static int fri_verify_impl(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs
 
     // Host buffers: chunks of whole 32-proof bitmap words move through a ring of SV_NBUF staging
     // buffers.  H2D copies run back to back on the copy stream; the kernels of consecutive chunks
-    // alternate between two compute streams so that the tail wave of chunk i overlaps the head of
+    // rotate over SV_NKS compute streams so that the tail wave of chunk i overlaps the head of
     // chunk i+1 (a chunk is only ~1.5 waves of blocks).  Distinct chunks touch distinct bitmap
     // words / first_fail entries / scratch rows, so they need no ordering among themselves.
     size_t n_words = (n_proofs + 31) / 32;
     if (grow(c, c->d_bitmap, c->bitmap_words, n_words)) return -6;
     if (first_fail && grow(c, c->d_fail, c->fail_words, n_proofs)) return -6;
-    size_t chunk = ((48ull << 20) / (rw * 8)) & ~(size_t)31;   // ~48 MiB per chunk
+    size_t chunk_mb = 32;                                        // ~32 MiB per chunk (swept on B200: tools/lab/e2e_sweep.sh)
+    int n_ks = SV_NKS;                                           // compute streams in rotation
+    if (const char* e = getenv("SVB_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 4096) chunk_mb = (size_t)v; }
+    if (const char* e = getenv("SVB_KSTREAMS")) { long v = atol(e); if (v >= 1 && v <= SV_NKS) n_ks = (int)v; }
+    size_t chunk = ((chunk_mb << 20) / (rw * 8)) & ~(size_t)31;
     if (chunk < 32) chunk = 32;
     if (chunk > n_proofs) chunk = (n_proofs + 31) & ~(size_t)31;
     for (int b = 0; b < SV_NBUF; b++)
         if (grow(c, c->d_stage[b], c->stage_words[b], chunk * rw)) return -6;
     cudaStream_t cs = c->copy_stream;
-    cudaStream_t ks[2] = {c->own_stream, c->aux_stream};
+    cudaStream_t ks[SV_NKS] = {c->own_stream};
+    for (int i = 1; i < SV_NKS; i++) ks[i] = c->aux_stream[i - 1];
     size_t n_chunks = (n_proofs + chunk - 1) / chunk;
     for (size_t i = 0; i < n_chunks; i++) {
         int b = (int)(i % SV_NBUF);
-        cudaStream_t k = ks[i & 1];
+        cudaStream_t k = ks[i % n_ks];
         size_t first = i * chunk, cnt = std::min(chunk, n_proofs - first);
         if (i >= SV_NBUF) CK(c, cudaStreamWaitEvent(cs, c->ev_done[b], 0));   // buffer b free again
         CK(c, cudaMemcpyAsync(c->d_stage[b], records + first * rw, cnt * rw * 8, cudaMemcpyHostToDevice, cs));
@@ -383,9 +389,9 @@ static int fri_verify_impl(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs
         CK(c, cudaEventRecord(c->ev_done[b], k));
     }
     // join the second compute stream, then read the results back on the first
-    if (n_chunks > 1) {
-        CK(c, cudaEventRecord(c->ev_join, ks[1]));
-        CK(c, cudaStreamWaitEvent(ks[0], c->ev_join, 0));
+    for (int j = 1; j < n_ks && (size_t)j < n_chunks; j++) {
+        CK(c, cudaEventRecord(c->ev_join[j], ks[j]));
+        CK(c, cudaStreamWaitEvent(ks[0], c->ev_join[j], 0));
     }
     CK(c, cudaMemcpyAsync(accept_bitmap, c->d_bitmap, n_words * 4, cudaMemcpyDeviceToHost, ks[0]));
     if (first_fail) CK(c, cudaMemcpyAsync(first_fail, c->d_fail, n_proofs * 4, cudaMemcpyDeviceToHost, ks[0]));

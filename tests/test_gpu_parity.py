@@ -1,4 +1,6 @@
 """GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit for bit."""
+import os
+
 import numpy as np
 import pytest
 
@@ -280,3 +282,93 @@ def test_verify_with_device_transcript(svb, orc, ctx):
     back = d.cpu().numpy().view(np.uint64)
     good = [i for i in range(n) if i != 10]
     assert (back[good] == recs[good]).all()
+
+
+def test_config3_full_size_shape_b(svb, orc, ctx):
+    """BASELINE configs[2] at full size: 65 536 proofs of shape B (2^20 trace, 84 queries, blowup 4) resident
+    on one GPU (54 GB).  The base proof is checked against the oracle, tiled on the device into
+    physically distinct records, 1/512 of them corrupted (a different class each); the accept bitmap
+    must equal the pattern, and a second run must reproduce it (idempotence)."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    params = svb.SHAPE_B
+    L = svb.api.make_layout(params)
+    assert L.algo_bytes_per_query == 9624 and L.algo_bytes_shared == 14360 and L.perms_per_query == 255
+    n = 65536
+    rw = L.record_words
+    if free < n * rw * 8 + (4 << 30):
+        n = int((free - (4 << 30)) // (rw * 8)) // 1024 * 1024
+        assert n >= 1024, "not enough device memory for a meaningful shape-B batch"
+    # the base proof is a committed fixture (tools/gen_golden.py; the shape-B prover run takes minutes on the host)
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "fri_full_shapes.npz"))
+    base = np.ascontiguousarray(fx["shape_b_record"]).reshape(1, rw)
+    oshape = orc.shape_from(params.to_shape())
+    assert int(orc.fri_verify_batch(oshape, base, nthreads=1)[0]) == 1
+    d = torch.empty((n, rw), dtype=torch.int64, device="cuda")
+    d[:1].copy_(torch.from_numpy(base.view(np.int64)))
+    k = 1
+    while k < n:
+        c = min(k, n - k)
+        d[k:k + c].copy_(d[:c])
+        k += c
+    rng = np.random.default_rng(3)
+    rows, cols, exp = [], [], np.full(n // 32, 0xFFFFFFFF, dtype=np.uint32)
+    ns = len(params.reduction_arity_bits)
+    for j, i in enumerate(range(7, n, 512)):
+        q = int(rng.integers(0, params.config.num_query_rounds))
+        qb = L.header_words + q * L.query_words
+        col = [qb + L.q_off_init_sibs[j % 4] + int(rng.integers(0, 4 * L.init_depth)),
+               qb + L.q_off_init_evals[j % 4] + int(rng.integers(0, L.leaf_len[j % 4])),
+               qb + L.q_off_step_evals[j % ns] + int(rng.integers(0, 4)),
+               qb + L.q_off_step_sibs[j % ns] + int(rng.integers(0, 4 * L.step_depth[j % ns])),
+               L.off_final_poly + int(rng.integers(0, 64))][j % 5]
+        rows.append(i); cols.append(col)
+        exp[i >> 5] &= np.uint32(~(1 << (i & 31)) & 0xFFFFFFFF)
+    r_t, c_t = torch.tensor(rows, device="cuda"), torch.tensor(cols, device="cuda")
+    d[r_t, c_t] = d[r_t, c_t] ^ 1
+    bm = torch.zeros(n // 32, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(2):
+        bm.zero_()
+        torch.cuda.synchronize()
+        ctx.fri_verify_batch(params, d.data_ptr(), n_proofs=n, accept_bitmap=bm.data_ptr(), mem=svb.MEM_DEVICE)
+        ctx.synchronize()
+        assert (bm.cpu().numpy().view(np.uint32) == exp).all()
+    del d
+    torch.cuda.empty_cache()
+
+
+def test_config5_full_size_merkle_paths(svb, orc, ctx):
+    """BASELINE configs[4]: 2^24 independent Merkle paths x depth 20, 4-limb leaves, cap_height 0.  The
+    first 2^13 paths are made valid against a per-path expected root through the oracle... which needs
+    one cap, so instead: all paths share one random cap (=> reject), a sampled subset is compared with
+    the oracle, and the subset's own roots (computed by the oracle) accept when supplied as the cap."""
+    import torch
+    n, depth = 1 << 24, 20
+    g = torch.Generator(device="cuda"); g.manual_seed(0xB2000005)
+    paths = torch.randint(0, 1 << 62, (n, 4 + 4 * depth), dtype=torch.int64, device="cuda", generator=g)
+    idx = torch.randint(0, 1 << depth, (n,), dtype=torch.int64, device="cuda", generator=g)
+    # plant ONE known path: its root (from the oracle) becomes the cap, so exactly the copies of that path accept
+    p0 = paths[0].cpu().numpy().view(np.uint64); i0 = int(idx[0])
+    st = p0[:4].copy()
+    for l in range(depth):
+        sib = p0[4 + 4 * l: 8 + 4 * l]
+        st = orc.two_to_one(sib, st) if (i0 >> l) & 1 else orc.two_to_one(st, sib)
+    cap = torch.from_numpy(st.view(np.int64)).cuda()
+    plant = torch.arange(0, n, 4099, device="cuda")
+    paths[plant] = paths[0].clone()
+    idx[plant] = idx[0].clone()
+    bad = plant[1::2]
+    paths[bad, 4 + 4 * 7 + 2] ^= 1          # one sibling limb flipped in every other planted copy
+    ok = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.merkle_verify_batch(4, depth, 0, paths.data_ptr(), idx.data_ptr(), cap.data_ptr(), ok.data_ptr(), n=n, mem=svb.MEM_DEVICE)
+    ctx.synchronize()
+    want = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    want[plant[0::2]] = 1
+    assert torch.equal(ok, want)
+    # sampled subset against the oracle
+    sub = 2048
+    hp = paths[:sub].cpu().numpy().view(np.uint64); hi = idx[:sub].cpu().numpy().view(np.uint64)
+    o = orc.merkle_verify_batch(hp, 4, depth, hi, st.reshape(1, 4), 0)
+    assert (ok[:sub].cpu().numpy() == o).all()

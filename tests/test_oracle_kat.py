@@ -95,3 +95,29 @@ def test_golden_fixtures_oracle(orc):
         assert [f"{int(x):016x}" for x in orc.poseidon([int(a, 16) for a in v["in"]])] == v["out"]
     for v in g["hash_no_pad"]:
         assert [f"{int(x):016x}" for x in orc.hash_no_pad(np.array([int(a, 16) for a in v["in"]], dtype=np.uint64))] == v["out"]
+
+
+def test_oracle_accepts_full_shape_golden_proofs(orc):
+    """tests/golden/fri_full_shapes.npz: one proof per BASELINE shape (A: 2^12 trace / 28 queries / blowup 8,
+    B: 2^20 / 84 / 4).  The oracle accepts them, rejects a flipped bit, and its transcript reproduces the
+    recorded challenges from (circuit digest, public-input hash)."""
+    import ctypes
+    import os
+    import numpy as np
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "fri_full_shapes.npz"))
+    for tag, (deg, rate, q) in (("shape_a", (12, 3, 28)), ("shape_b", (20, 2, 84))):
+        s = orc.OrcShape()
+        s.degree_bits, s.rate_bits, s.cap_height, s.num_query_rounds, s.proof_of_work_bits = deg, rate, 4, q, 16
+        s.num_steps, s.final_poly_len, s.hiding = deg - 5, 32, 0
+        s.oracle_num_polys = (ctypes.c_uint32 * 4)(84, 135, 20, 16)
+        s.oracle_blinding = (ctypes.c_uint32 * 4)(0, 1, 1, 1)
+        s.num_zs, s.hash_kind = 2, 0
+        rec = np.ascontiguousarray(fx[tag + "_record"])
+        ok, code, _ = orc.fri_verify(s, rec)
+        assert ok and code == 0
+        again = rec.copy()
+        orc.fri_challenges(s, again, fx[tag + "_circuit_digest"], fx[tag + "_pi_hash"])
+        assert (again == rec).all()
+        bad = rec.copy()
+        bad[len(bad) // 2] ^= np.uint64(1)
+        assert not orc.fri_verify(s, bad)[0]

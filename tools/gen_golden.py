@@ -106,6 +106,18 @@ def main():
         fx[tag + "_shape"] = np.array([s.degree_bits, s.rate_bits, s.cap_height, s.num_query_rounds, s.proof_of_work_bits,
                                        s.num_steps, s.final_poly_len, s.hiding], dtype=np.uint32)
     np.savez_compressed(os.path.join(out_dir, "fri_small.npz"), **fx)
+    # one full-shape proof per BASELINE shape (A: configs[1], B: configs[2]); the shape-B prover run takes
+    # about a minute on the host, which is why the proof is a committed fixture
+    big = {}
+    for tag, params in (("shape_a", svb.SHAPE_A), ("shape_b", svb.SHAPE_B)):
+        rec = svb.synth_proofs(params, 1, seed=0xB2000003, n_circuits=1)
+        ok, code, q = orc.fri_verify(orc.shape_from(params.to_shape()), rec[0])
+        assert ok, (tag, code, q)
+        cd, ph = svb.synth_public_inputs(params, 1, seed=0xB2000003, n_circuits=1)
+        big[tag + "_record"] = rec[0]
+        big[tag + "_circuit_digest"] = cd[0]
+        big[tag + "_pi_hash"] = ph[0]
+    np.savez(os.path.join(out_dir, "fri_full_shapes.npz"), **big)
     print("wrote", os.listdir(out_dir))
 
 

@@ -31,7 +31,8 @@ extern "C" {
 #define SV_MEM_DEVICE 1
 
 #define SV_HASH_POSEIDON_GOLDILOCKS 0 /* plonky2 PoseidonHash; constants chip/plonk/gates/poseidon.rs:26-322 */
-#define SV_HASH_POSEIDON_BN254 1      /* bn245_poseidon/*; not implemented yet */
+#define SV_HASH_POSEIDON_BN254 1      /* Poseidon over BN254 Fr wrapped around 12 Goldilocks limbs: bn245_poseidon/plonky2_config.rs:38-66,
+                                         native.rs:16-77, constants.rs (the Hasher of Bn254PoseidonGoldilocksConfig) */
 
 #define SV_MAX_STEPS 32
 

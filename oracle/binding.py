@@ -34,7 +34,7 @@ class OrcLayout(ctypes.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "_build", "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "orc_field.h", "poseidon_g_constants.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "orc_field.h", "poseidon_g_constants.h", "poseidon_b_constants.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -49,6 +49,9 @@ def lib():
         L.orc_poseidon.argtypes = [vp]
         L.orc_poseidon_naive.argtypes = [vp]
         L.orc_poseidon_batch.argtypes = [vp, ctypes.c_size_t]
+        L.orc_poseidon_b_fr.argtypes = [vp]
+        L.orc_poseidon_b.argtypes = [vp]
+        L.orc_set_hash_kind.argtypes = [ctypes.c_int]
         L.orc_hash_no_pad.argtypes = [vp, ctypes.c_size_t, vp]
         L.orc_two_to_one.argtypes = [vp, vp, vp]
         L.orc_merkle_verify.argtypes = [vp, ctypes.c_size_t, ctypes.c_uint64, vp, ctypes.c_size_t, vp, ctypes.c_size_t]
@@ -97,28 +100,51 @@ def poseidon_batch(states):
     return a
 
 
-def hash_no_pad(inp):
+def poseidon_b(state):
+    """Hash family B: the Goldilocks-wrapped Poseidon-BN254 permutation (plonky2_config.rs:38-51)."""
+    a = np.array(state, dtype=np.uint64)
+    lib().orc_poseidon_b(a.ctypes.data)
+    return a
+
+
+def poseidon_b_fr(state5):
+    """Raw Poseidon-BN254 permutation on 5 canonical integers < r (native.rs:43-60) -> list of 5 ints."""
+    a = np.zeros(20, dtype=np.uint64)
+    for i, v in enumerate(state5):
+        for k in range(4):
+            a[4 * i + k] = (int(v) >> (64 * k)) & (2**64 - 1)
+    lib().orc_poseidon_b_fr(a.ctypes.data)
+    return [sum(int(a[4 * i + k]) << (64 * k) for k in range(4)) for i in range(5)]
+
+
+def hash_no_pad(inp, kind=0):
     a = np.ascontiguousarray(inp, dtype=np.uint64)
     out = np.zeros(4, dtype=np.uint64)
+    lib().orc_set_hash_kind(kind)
     lib().orc_hash_no_pad(a.ctypes.data, a.size, out.ctypes.data)
+    lib().orc_set_hash_kind(0)
     return out
 
 
-def two_to_one(l, r):
+def two_to_one(l, r, kind=0):
     l = np.ascontiguousarray(l, dtype=np.uint64)
     r = np.ascontiguousarray(r, dtype=np.uint64)
     out = np.zeros(4, dtype=np.uint64)
+    lib().orc_set_hash_kind(kind)
     lib().orc_two_to_one(l.ctypes.data, r.ctypes.data, out.ctypes.data)
+    lib().orc_set_hash_kind(0)
     return out
 
 
-def merkle_verify_batch(records, leaf_len, depth, indices, caps, cap_height):
+def merkle_verify_batch(records, leaf_len, depth, indices, caps, cap_height, kind=0):
     records = np.ascontiguousarray(records, dtype=np.uint64)
     indices = np.ascontiguousarray(indices, dtype=np.uint64)
     caps = np.ascontiguousarray(caps, dtype=np.uint64)
     ok = np.zeros(len(indices), dtype=np.uint8)
+    lib().orc_set_hash_kind(kind)
     lib().orc_merkle_verify_batch(records.ctypes.data, len(indices), leaf_len, depth, indices.ctypes.data,
                                   caps.ctypes.data, cap_height, ok.ctypes.data)
+    lib().orc_set_hash_kind(0)
     return ok
 
 

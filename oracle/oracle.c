@@ -93,6 +93,125 @@ void orc_poseidon(uint64_t st[12]) {
     for (int r = 0; r < 4; r++) full_round(st, rc++);                               /* :675-686 */
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * Hash family B: Poseidon over the BN254 scalar field wrapped around 12 Goldilocks limbs.
+ *   parameters ........ bn245_poseidon/constants.rs:5-384 (340 round constants, 5x5 MDS), :402-404
+ *                       (T = 5, R_F = 8, R_P = 60)
+ *   permutation ....... bn245_poseidon/native.rs:16-60 (constant layer, x^5 on all lanes / lane 0, MDS
+ *                       new[i] = sum_j state[j] * M[i][j])
+ *   encode / decode ... native.rs:62-77 (3 limbs -> sum x_i p^i; 4 base-p digits, keep 3),
+ *                       native_chip/utils.rs:25-36 (goldilocks_decompose)
+ *   wrapper ........... bn245_poseidon/plonky2_config.rs:38-51 (4 chunks of 3, pad to 5 with 0,
+ *                       decode the first 4 words), in-circuit twin native_chip/all_chip.rs:52-89
+ * Fr arithmetic lives in halo2curves bn256::Fr 0.3.2 (Cargo.lock:1063-1065, not on disk); this restates
+ * its published representation: 4 x 64-bit limbs, Montgomery multiplication (CIOS) with R = 2^256.
+ * Pinned by the SURVEY 8c KATs and by tests/golden/poseidon_b.json (pure-Python big integers).
+ * ---------------------------------------------------------------------------------------- */
+#include "poseidon_b_constants.h"
+typedef struct { uint64_t l[4]; } orc_fr;
+static const uint64_t FR_MOD[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+static const uint64_t FR_NINV = 0xc2e1f593efffffffULL;  /* -r^-1 mod 2^64 */
+static const uint64_t FR_R2[4] = {0x1bb8e645ae216da7ULL, 0x53fe3ab1e35c59e3ULL, 0x8c49833d53bb8085ULL, 0x0216d0b17f4e44a5ULL};
+
+static int fr_geq_mod(const uint64_t a[4]) {
+    for (int i = 3; i >= 0; i--) { if (a[i] > FR_MOD[i]) return 1; if (a[i] < FR_MOD[i]) return 0; }
+    return 1;
+}
+static void fr_sub_mod(uint64_t a[4]) {
+    orc_u128 br = 0;
+    for (int i = 0; i < 4; i++) { orc_u128 d = (orc_u128)a[i] - FR_MOD[i] - br; a[i] = (uint64_t)d; br = (d >> 64) & 1; }
+}
+static orc_fr fr_add(orc_fr a, orc_fr b) {
+    orc_fr r; orc_u128 c = 0;
+    for (int i = 0; i < 4; i++) { c += (orc_u128)a.l[i] + b.l[i]; r.l[i] = (uint64_t)c; c >>= 64; }
+    if (c || fr_geq_mod(r.l)) fr_sub_mod(r.l);   /* a + b < 2r < 2^255: c is always 0 */
+    return r;
+}
+/* Montgomery product a*b*2^-256 mod r (CIOS, Koc et al.) */
+static orc_fr fr_mmul(orc_fr a, orc_fr b) {
+    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        orc_u128 c = 0;
+        for (int j = 0; j < 4; j++) { c += (orc_u128)a.l[j] * b.l[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+        c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * FR_NINV;
+        c = (orc_u128)m * FR_MOD[0] + t[0]; c >>= 64;
+        for (int j = 1; j < 4; j++) { c += (orc_u128)m * FR_MOD[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+        c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    orc_fr r = {{t[0], t[1], t[2], t[3]}};
+    if (t[4] || fr_geq_mod(r.l)) fr_sub_mod(r.l);
+    return r;
+}
+static orc_fr fr_to_mont(orc_fr a) { orc_fr r2 = {{FR_R2[0], FR_R2[1], FR_R2[2], FR_R2[3]}}; return fr_mmul(a, r2); }
+static orc_fr fr_from_mont(orc_fr a) { orc_fr one = {{1, 0, 0, 0}}; return fr_mmul(a, one); }
+
+static orc_fr B_RC[340], B_MDS[25];
+static pthread_once_t b_once = PTHREAD_ONCE_INIT;
+static void b_init(void) {
+    for (int i = 0; i < 340; i++) { orc_fr v; memcpy(v.l, ORC_B_ROUND_CONSTANTS + 4 * i, 32); B_RC[i] = fr_to_mont(v); }
+    for (int i = 0; i < 25; i++) { orc_fr v; memcpy(v.l, ORC_B_MDS + 4 * i, 32); B_MDS[i] = fr_to_mont(v); }
+}
+static orc_fr fr_pow5(orc_fr x) { orc_fr x2 = fr_mmul(x, x), x4 = fr_mmul(x2, x2); return fr_mmul(x4, x); }
+/* native.rs:43-60, state in Montgomery form */
+static void b_permute_mont(orc_fr st[5]) {
+    pthread_once(&b_once, b_init);
+    int counter = 0;
+    for (int round = 0; round < 68; round++) {
+        for (int i = 0; i < 5; i++) st[i] = fr_add(st[i], B_RC[counter++]);          /* constant_layer :16-21 */
+        if (round < 4 || round >= 64) { for (int i = 0; i < 5; i++) st[i] = fr_pow5(st[i]); } /* sbox_layer :23-27 */
+        else st[0] = fr_pow5(st[0]);                                                  /* partial_sbox_layer :29-31 */
+        orc_fr nw[5];                                                                 /* mds_layer :33-41 */
+        for (int i = 0; i < 5; i++) {
+            orc_fr acc = {{0, 0, 0, 0}};
+            for (int j = 0; j < 5; j++) acc = fr_add(acc, fr_mmul(st[j], B_MDS[5 * i + j]));
+            nw[i] = acc;
+        }
+        memcpy(st, nw, sizeof nw);
+    }
+}
+/* raw Fr permutation on canonical integers (KAT entry point): state[5][4] little-endian limbs */
+void orc_poseidon_b_fr(uint64_t state[20]) {
+    orc_fr st[5];
+    for (int i = 0; i < 5; i++) { memcpy(st[i].l, state + 4 * i, 32); st[i] = fr_to_mont(st[i]); }
+    b_permute_mont(st);
+    for (int i = 0; i < 5; i++) { st[i] = fr_from_mont(st[i]); memcpy(state + 4 * i, st[i].l, 32); }
+}
+/* a[4] = a * m + add  (a < 2^192 stays < 2^256) */
+static void limbs_mul_add(uint64_t a[4], uint64_t m, uint64_t add) {
+    orc_u128 c = add;
+    for (int i = 0; i < 4; i++) { c += (orc_u128)a[i] * m; a[i] = (uint64_t)c; c >>= 64; }
+}
+/* a[4] /= d, returns a % d (schoolbook long division, 128/64 steps) */
+static uint64_t limbs_divrem(uint64_t a[4], uint64_t d) {
+    orc_u128 rem = 0;
+    for (int i = 3; i >= 0; i--) { orc_u128 cur = (rem << 64) | a[i]; a[i] = (uint64_t)(cur / d); rem = cur % d; }
+    return (uint64_t)rem;
+}
+/* Bn254PoseidonPermutation::permute (plonky2_config.rs:38-51) */
+void orc_poseidon_b(uint64_t st[12]) {
+    orc_fr s5[5];
+    for (int k = 0; k < 4; k++) {                       /* encode_fe: x0 + x1 p + x2 p^2 (native.rs:62-67) */
+        uint64_t v[4] = {st[3 * k + 2] % ORC_P, 0, 0, 0};
+        limbs_mul_add(v, ORC_P, st[3 * k + 1] % ORC_P);
+        limbs_mul_add(v, ORC_P, st[3 * k] % ORC_P);
+        memcpy(s5[k].l, v, 32);
+        s5[k] = fr_to_mont(s5[k]);
+    }
+    memset(&s5[4], 0, sizeof s5[4]);                    /* resize(T, 0) */
+    b_permute_mont(s5);
+    for (int k = 0; k < 4; k++) {                       /* decode_fe: 4 base-p digits, keep 3 (native.rs:69-77) */
+        orc_fr c = fr_from_mont(s5[k]);
+        for (int i = 0; i < 3; i++) st[3 * k + i] = limbs_divrem(c.l, ORC_P);
+    }
+}
+
+/* the permutation of the hash family in use (orc_shape.hash_kind: 0 = Poseidon-Goldilocks, 1 = B) */
+static _Thread_local int cur_kind = 0;
+static void permute_cur(uint64_t st[12]) { if (cur_kind == 1) orc_poseidon_b(st); else orc_poseidon(st); }
+void orc_set_hash_kind(int kind) { cur_kind = kind; }
+
 /* thin exports of the field restatement, for the KAT tests */
 uint64_t orc_f_mul(uint64_t a, uint64_t b) { return orc_mul(a % ORC_P, b % ORC_P); }
 uint64_t orc_f_pow(uint64_t a, uint64_t e) { return orc_pow(a % ORC_P, e); }
@@ -119,7 +238,7 @@ void orc_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]) {
     for (size_t off = 0; off < n; off += 8) {
         size_t len = n - off < 8 ? n - off : 8;
         for (size_t i = 0; i < len; i++) st[i] = in[off + i];
-        orc_poseidon(st);
+        permute_cur(st);
     }
     memcpy(out, st, 4 * sizeof(uint64_t));
 }
@@ -130,7 +249,7 @@ void orc_two_to_one(const uint64_t l[4], const uint64_t r[4], uint64_t out[4]) {
     uint64_t st[12] = {0};
     memcpy(st, l, 32);
     memcpy(st + 4, r, 32);
-    orc_poseidon(st);
+    permute_cur(st);
     memcpy(out, st, 32);
 }
 
@@ -357,6 +476,7 @@ int orc_fri_verify(const orc_shape *s, const uint64_t *rec, int *fail, int *fail
     orc_layout L;
     int code = ORC_OK, fq = -1;
     if (orc_make_layout(s, &L)) { if (fail) *fail = -1; return 0; }
+    cur_kind = (int)s->hash_kind;
     /* range check of the per-proof witnesses */
     if (!all_canonical(rec, L.header_words)) { code = ORC_FAIL_NONCANONICAL; goto done; }
     /* fri_verify_proof_of_work (fri_chip.rs:364-376): top proof_of_work_bits of the 64-bit
@@ -418,7 +538,7 @@ typedef struct { uint64_t state[12]; uint64_t in[8]; int n_in; uint64_t out[8]; 
 static void ch_init(challenger *c) { memset(c, 0, sizeof *c); }
 static void ch_duplex(challenger *c, int len) {                 /* :107-120 */
     for (int i = 0; i < len; i++) c->state[i] = c->in[i];
-    orc_poseidon(c->state);
+    permute_cur(c->state);
     memcpy(c->out, c->state, 64); c->n_out = 8;
 }
 static void ch_observe(challenger *c, uint64_t v) {             /* :51-59 update: clears output buffer */
@@ -428,7 +548,7 @@ static void ch_observe(challenger *c, uint64_t v) {             /* :51-59 update
 }
 static uint64_t ch_squeeze(challenger *c) {                     /* :73-89 */
     if (c->n_in) { ch_duplex(c, c->n_in); c->n_in = 0; }
-    if (c->n_out == 0) { orc_poseidon(c->state); memcpy(c->out, c->state, 64); c->n_out = 8; }
+    if (c->n_out == 0) { permute_cur(c->state); memcpy(c->out, c->state, 64); c->n_out = 8; }
     return c->out[--c->n_out];                                  /* pops from the END (:84-86) */
 }
 
@@ -441,6 +561,7 @@ void orc_fri_challenges(const orc_shape *s, uint64_t *rec, const uint64_t circui
                         const uint64_t pi_hash[4], uint32_t num_challenges) {
     orc_layout L;
     if (orc_make_layout(s, &L)) return;
+    cur_kind = (int)s->hash_kind;
     challenger c; ch_init(&c);
     for (int i = 0; i < 4; i++) ch_observe(&c, circuit_digest[i]);                       /* plonk_verifier_chip.rs:65-67 */
     for (int i = 0; i < 4; i++) ch_observe(&c, pi_hash[i]);                              /* :69-71 */

@@ -33,7 +33,7 @@ typedef struct {
     uint32_t oracle_num_polys[4];/* FriOracleInfo.num_polys, order: constants_sigmas, wires, zs_pp, quotient */
     uint32_t oracle_blinding[4]; /* FriOracleInfo.blinding */
     uint32_t num_zs;             /* batch 1 (point g*zeta) = polys [0,num_zs) of oracle 2 (common_data.rs:192-194) */
-    uint32_t hash_kind;          /* 0 = Poseidon-Goldilocks */
+    uint32_t hash_kind;          /* 0 = Poseidon-Goldilocks, 1 = Poseidon-BN254 wrapped (family B) */
 } orc_shape;
 
 /* Word offsets (u64) of the flat per-proof record; same format as include/stark_verifier_b200.h
@@ -64,6 +64,14 @@ void orc_f2_inv(const uint64_t a[2], uint64_t out[2]);
 void orc_poseidon(uint64_t st[12]);
 void orc_poseidon_naive(uint64_t st[12]);
 void orc_poseidon_batch(uint64_t *states, size_t n);
+/* Hash family B (bn245_poseidon): raw Fr permutation on canonical integers (state[5][4] little-endian
+ * u64 limbs) and the Goldilocks-wrapped width-12 permutation (plonky2_config.rs:38-51). */
+void orc_poseidon_b_fr(uint64_t state[20]);
+void orc_poseidon_b(uint64_t st[12]);
+/* Select the permutation used by orc_hash_no_pad / orc_two_to_one / orc_merkle_verify* on the calling
+ * thread (0 = Poseidon-Goldilocks, 1 = B).  orc_fri_verify / orc_fri_challenges set it from
+ * orc_shape.hash_kind themselves. */
+void orc_set_hash_kind(int kind);
 /* hash_n_to_m_no_pad, overwrite-mode sponge (hasher_chip.rs:122-148) -> 4 outputs */
 void orc_hash_no_pad(const uint64_t *in, size_t n, uint64_t out[4]);
 /* two_to_one == HasherChip::permute on a fresh zero state (hasher_chip.rs:150-171, merkle_proof_chip.rs:58-71) */

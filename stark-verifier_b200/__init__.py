@@ -20,6 +20,9 @@ from .api import (  # noqa: F401
     SHAPE_A,
     SHAPE_B,
     SHAPE_SEMAPHORE,
+    SHAPE_OUTER_BN254,
+    HASH_POSEIDON_GOLDILOCKS,
+    HASH_POSEIDON_BN254,
     FAIL_NAMES,
     fri_challenges,
     lib,

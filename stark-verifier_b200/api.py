@@ -17,6 +17,7 @@ import numpy as np
 MEM_HOST = 0
 MEM_DEVICE = 1
 HASH_POSEIDON_GOLDILOCKS = 0
+HASH_POSEIDON_BN254 = 1      # bn245_poseidon/plonky2_config.rs:54-75 (the reference's outermost proof)
 SV_MAX_STEPS = 32
 
 FAIL_NAMES = {0: "ok", 1: "pow", 2: "noncanonical", 3: "init_merkle", 4: "zero_denominator",
@@ -70,6 +71,7 @@ class FriParams:
     oracle_num_polys: Sequence[int] = (84, 135, 20, 16)      # constants_sigmas, wires, zs_pp, quotient
     oracle_blinding: Sequence[bool] = (False, True, True, True)  # PlonkOracle::*.blinding (common_data.rs:101-123)
     num_zs: int = 2                                           # = num_challenges (zs_range, common_data.rs:148-150)
+    hash_kind: int = HASH_POSEIDON_GOLDILOCKS                 # GenericConfig::Hasher of the proof
 
     def lde_bits(self) -> int:
         return self.degree_bits + self.config.rate_bits
@@ -93,7 +95,7 @@ class FriParams:
         s.oracle_num_polys = (ctypes.c_uint32 * 4)(*self.oracle_num_polys)
         s.oracle_blinding = (ctypes.c_uint32 * 4)(*[int(b) for b in self.oracle_blinding])
         s.num_zs = self.num_zs
-        s.hash_kind = HASH_POSEIDON_GOLDILOCKS
+        s.hash_kind = self.hash_kind
         return s
 
 
@@ -107,6 +109,9 @@ def _params(degree_bits, rate_bits, cap_height, pow_bits, queries, hiding=False,
 SHAPE_A = _params(12, 3, 4, 16, 28)
 #: BASELINE configs[2]: 2^20 trace, blowup 4, 84 queries
 SHAPE_B = _params(20, 2, 4, 16, 84)
+#: the reference's OUTER wrapped proof: Bn254PoseidonGoldilocksConfig + standard_stark_verifier_config
+#: (bn245_poseidon/plonky2_config.rs:92-104: cap_height 0), hash family B
+SHAPE_OUTER_BN254 = _params(12, 3, 0, 16, 28, hash_kind=HASH_POSEIDON_BN254)
 #: BASELINE configs[0]: semaphore-shaped (zero_knowledge => salted leaves), plonky2_semaphore/access_set.rs:68-84
 SHAPE_SEMAPHORE = _params(12, 3, 4, 16, 28, hiding=True)
 
@@ -263,12 +268,13 @@ class Context:
         return int(self._lib.sv_ctx_launch_count(self._h))
 
     # -- hot path -------------------------------------------------------------------------------
-    def poseidon_permute_batch(self, states, out=None, n: Optional[int] = None, mem: int = MEM_HOST):
+    def poseidon_permute_batch(self, states, out=None, n: Optional[int] = None, mem: int = MEM_HOST,
+                               hash_kind: int = HASH_POSEIDON_GOLDILOCKS):
         if mem == MEM_HOST:
             states = np.ascontiguousarray(states, dtype=np.uint64)
             n = states.size // 12
             out = np.empty_like(states) if out is None else out
-        self._ck(self._lib.sv_poseidon_permute_batch(self._h, _ptr(states), _ptr(out), n, HASH_POSEIDON_GOLDILOCKS, mem),
+        self._ck(self._lib.sv_poseidon_permute_batch(self._h, _ptr(states), _ptr(out), n, hash_kind, mem),
                  "sv_poseidon_permute_batch")
         return out
 
@@ -283,11 +289,11 @@ class Context:
         return out
 
     def merkle_verify_batch(self, leaf_len: int, depth: int, cap_height: int, paths, indices, caps, ok=None,
-                            n: Optional[int] = None, mem: int = MEM_HOST):
+                            n: Optional[int] = None, mem: int = MEM_HOST, hash_kind: int = HASH_POSEIDON_GOLDILOCKS):
         if mem == MEM_HOST:
             n = len(indices)
             ok = np.zeros(n, dtype=np.uint8) if ok is None else ok
-        self._ck(self._lib.sv_merkle_verify_batch(self._h, leaf_len, depth, cap_height, HASH_POSEIDON_GOLDILOCKS,
+        self._ck(self._lib.sv_merkle_verify_batch(self._h, leaf_len, depth, cap_height, hash_kind,
                                                   _ptr(paths), _ptr(indices), _ptr(caps), _ptr(ok), n, mem),
                  "sv_merkle_verify_batch")
         return ok

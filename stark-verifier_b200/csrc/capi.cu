@@ -47,6 +47,14 @@ struct sv_ctx {
 
 static std::string g_create_err;
 
+// launch KERNEL<hash kind>(args) for a run-time hash kind
+#define SVB_LAUNCH_KIND(kind, KERNEL, grid, block, stream, ...)                                         \
+    do {                                                                                                \
+        if ((kind) == SV_HASH_POSEIDON_BN254) KERNEL<SV_HASH_POSEIDON_BN254><<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); \
+        else KERNEL<SV_HASH_POSEIDON_GOLDILOCKS><<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);    \
+    } while (0)
+static bool known_kind(int k) { return k == SV_HASH_POSEIDON_GOLDILOCKS || k == SV_HASH_POSEIDON_BN254; }
+
 static int fail(sv_ctx* c, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -189,13 +197,13 @@ static int grow(sv_ctx* c, T*& ptr, size_t& have, size_t need) {
 // ---------------------------------------------------------------------------------------------
 extern "C" int sv_poseidon_permute_batch(sv_ctx* c, const uint64_t* in, uint64_t* out, size_t n, int hash_kind, int mem) {
     if (!c || !in || !out) return -1;
-    if (hash_kind != SV_HASH_POSEIDON_GOLDILOCKS) return fail(c, -5, "hash_kind %d not implemented", hash_kind);
+    if (!known_kind(hash_kind)) return fail(c, -5, "hash_kind %d not implemented", hash_kind);
     if (n == 0) return 0;
     CK(c, cudaSetDevice(c->device));
     const int B = SVB_BLOCK;
     if (mem == SV_MEM_DEVICE) {
         cudaEvent_t te = time_begin(c, c->stream);
-        poseidon_permute_kernel<<<(unsigned)((n + B - 1) / B), B, 0, c->stream>>>(in, out, n);
+        SVB_LAUNCH_KIND(hash_kind, poseidon_permute_kernel, (unsigned)((n + B - 1) / B), B, c->stream, in, out, n);
         time_end(c, te, c->stream);
         c->launches++;
         CK(c, cudaGetLastError());
@@ -205,7 +213,7 @@ extern "C" int sv_poseidon_permute_batch(sv_ctx* c, const uint64_t* in, uint64_t
     if (grow(c, c->d_stage[0], c->stage_words[0], words)) return -6;
     cudaStream_t s = c->own_stream;
     CK(c, cudaMemcpyAsync(c->d_stage[0], in, words * 8, cudaMemcpyHostToDevice, s));
-    poseidon_permute_kernel<<<(unsigned)((n + B - 1) / B), B, 0, s>>>(c->d_stage[0], c->d_stage[0], n);
+    SVB_LAUNCH_KIND(hash_kind, poseidon_permute_kernel, (unsigned)((n + B - 1) / B), B, s, c->d_stage[0], c->d_stage[0], n);
     c->launches++;
     CK(c, cudaGetLastError());
     CK(c, cudaMemcpyAsync(out, c->d_stage[0], words * 8, cudaMemcpyDeviceToHost, s));
@@ -243,7 +251,7 @@ extern "C" int sv_merkle_verify_batch(sv_ctx* c, uint32_t leaf_len, uint32_t dep
                                       const uint64_t* paths, const uint64_t* indices, const uint64_t* caps, uint8_t* ok,
                                       size_t n, int mem) {
     if (!c || !paths || !indices || !caps || !ok) return -1;
-    if (hash_kind != SV_HASH_POSEIDON_GOLDILOCKS) return fail(c, -5, "hash_kind %d not implemented", hash_kind);
+    if (!known_kind(hash_kind)) return fail(c, -5, "hash_kind %d not implemented", hash_kind);
     if (leaf_len == 0 || depth > 63 || cap_height > 16 || depth + cap_height > 63) return fail(c, -7, "bad merkle shape");
     if (n == 0) return 0;
     CK(c, cudaSetDevice(c->device));
@@ -251,7 +259,8 @@ extern "C" int sv_merkle_verify_batch(sv_ctx* c, uint32_t leaf_len, uint32_t dep
     size_t rec_words = up4(leaf_len) + 4 * (size_t)depth;
     if (mem == SV_MEM_DEVICE) {
         cudaEvent_t te = time_begin(c, c->stream);
-        merkle_verify_kernel<<<(unsigned)((n + B - 1) / B), B, 0, c->stream>>>(paths, indices, caps, ok, n, leaf_len, depth, cap_height);
+        SVB_LAUNCH_KIND(hash_kind, merkle_verify_kernel, (unsigned)((n + B - 1) / B), B, c->stream, paths, indices, caps, ok, n, leaf_len,
+                        depth, cap_height);
         time_end(c, te, c->stream);
         c->launches++;
         CK(c, cudaGetLastError());
@@ -269,7 +278,8 @@ extern "C" int sv_merkle_verify_batch(sv_ctx* c, uint32_t leaf_len, uint32_t dep
     CK(c, cudaMemcpyAsync(d_paths, paths, rec_words * n * 8, cudaMemcpyHostToDevice, s));
     CK(c, cudaMemcpyAsync(d_idx, indices, n * 8, cudaMemcpyHostToDevice, s));
     CK(c, cudaMemcpyAsync(d_caps, caps, cap_words * 8, cudaMemcpyHostToDevice, s));
-    merkle_verify_kernel<<<(unsigned)((n + B - 1) / B), B, 0, s>>>(d_paths, d_idx, d_caps, d_ok, n, leaf_len, depth, cap_height);
+    SVB_LAUNCH_KIND(hash_kind, merkle_verify_kernel, (unsigned)((n + B - 1) / B), B, s, d_paths, d_idx, d_caps, d_ok, n, leaf_len, depth,
+                    cap_height);
     c->launches++;
     CK(c, cudaGetLastError());
     CK(c, cudaMemcpyAsync(ok, d_ok, n, cudaMemcpyDeviceToHost, s));
@@ -281,7 +291,8 @@ extern "C" int sv_merkle_verify_batch(sv_ctx* c, uint32_t leaf_len, uint32_t dep
 static int make_params(sv_ctx* c, const sv_fri_shape& s, FriKernelParams& P) {
     memset(&P, 0, sizeof P);
     if (make_layout(s, P.L)) return fail(c, -8, "bad FRI shape");
-    if (s.hash_kind != SV_HASH_POSEIDON_GOLDILOCKS) return fail(c, -5, "hash_kind %u not implemented", s.hash_kind);
+    if (!known_kind((int)s.hash_kind)) return fail(c, -5, "hash_kind %u not implemented", s.hash_kind);
+    P.hash_kind = s.hash_kind;
     if (s.proof_of_work_bits > 63) return fail(c, -8, "proof_of_work_bits > 63");
     if (s.num_query_rounds >= (1u << 12)) return fail(c, -8, "num_query_rounds too large");
     P.num_queries = s.num_query_rounds;
@@ -307,7 +318,8 @@ static int make_params(sv_ctx* c, const sv_fri_shape& s, FriKernelParams& P) {
 static int enqueue_challenges(sv_ctx* c, FriKernelParams& P, const FsParams& F, size_t n, u64* d_records, const u64* d_pi,
                               cudaStream_t s) {
     P.n_proofs = (u32)n;
-    fri_challenges_kernel<<<(unsigned)((n + SVB_FS_BLOCK - 1) / SVB_FS_BLOCK), SVB_FS_BLOCK, 0, s>>>(d_records, P, F, d_pi);
+    SVB_LAUNCH_KIND(P.hash_kind, fri_challenges_kernel, (unsigned)((n + SVB_FS_BLOCK - 1) / SVB_FS_BLOCK), SVB_FS_BLOCK, s, d_records, P,
+                    F, d_pi);
     c->launches++;
     CK(c, cudaGetLastError());
     return 0;
@@ -321,7 +333,7 @@ static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_rec
     P.blocks_per_class = (P.n_units + B - 1) / B;
     fri_prepare_kernel<<<(unsigned)((n + B - 1) / B), B, 0, s>>>(d_records, P, d_scratch, d_bitmap, d_fail);
     cudaEvent_t te = time_begin(c, s);
-    fri_query_kernel<<<P.blocks_per_class * P.n_classes, B, 0, s>>>(d_records, P, d_scratch, d_bitmap, d_fail);
+    SVB_LAUNCH_KIND(P.hash_kind, fri_query_kernel, P.blocks_per_class * P.n_classes, B, s, d_records, P, d_scratch, d_bitmap, d_fail);
     time_end(c, te, s);
     c->launches += 2;
     if (d_fail) {

@@ -22,6 +22,7 @@
 #pragma once
 #include "layout.hpp"
 #include "poseidon_g.cuh"
+#include "poseidon_b.cuh"
 
 namespace svb {
 
@@ -32,7 +33,7 @@ namespace svb {
 
 struct FriKernelParams {
     sv_fri_layout L;
-    u32 num_queries, num_steps, final_poly_len, pow_bits;
+    u32 num_queries, num_steps, final_poly_len, pow_bits, hash_kind;
     u32 oracle_num_polys[4];
     u32 num_zs;
     u32 n_proofs;
@@ -42,6 +43,17 @@ struct FriKernelParams {
     u32 class_order[SV_MAX_STEPS + 5];  // heaviest first
     u64 omega_pow2[40];   // omega^(2^i), omega = 7^((p-1)/2^lde_bits)
 };
+
+// Shared-memory scratch of one permutation, in u64 words per thread: Poseidon-Goldilocks stages the 11
+// outputs of the initial matrix, Poseidon-BN254 its whole 5 x 8-limb state.
+template <int KIND> struct PermScratch { static constexpr int words = KIND == SV_HASH_POSEIDON_BN254 ? SVB_B_SMEM_WORDS / 2 : 11; };
+// The width-12 permutation of hash family KIND on `s` (LOOSE in; G leaves LOOSE words, B canonical ones).
+// scratch: base of the block's shared array, stride = threads per block.
+template <int KIND>
+SVB_D void permute_dev(u64 s[12], u64* scratch, u32 stride) {
+    if (KIND == SV_HASH_POSEIDON_BN254) poseidon_b_dev(s, reinterpret_cast<u32*>(scratch) + threadIdx.x, stride);
+    else poseidon_g_dev(s, scratch + threadIdx.x, stride);
+}
 
 SVB_D void ldg4(const u64* p, u64 out[4]) {
     const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p);
@@ -61,6 +73,7 @@ SVB_D void report_fail(u32* accept_bitmap, u32* first_fail, u32 proof, u32 query
 // the permutation: iterations [0, n_sponge) overwrite the rate lanes with the next leaf chunk
 // (overwrite-mode sponge, rate 8: hasher_chip.rs:122-148), iterations [n_sponge, n_sponge+depth)
 // compress with the sibling of that level on a fresh capacity (merkle_proof_chip.rs:58-71).
+template <int KIND>
 SVB_D u32 merkle_chain(const u64* __restrict__ leaf, u32 leaf_len, const u64* __restrict__ sibs, u32 depth,
                        u64 index, const u64* __restrict__ cap_entry, u32 merkle_code, u64* scratch) {
     u64 s[12];
@@ -109,7 +122,7 @@ SVB_D u32 merkle_chain(const u64* __restrict__ leaf, u32 leaf_len, const u64* __
 #pragma unroll
             for (int i = 8; i < 12; i++) s[i] = 0;  // fresh hasher per level (:59)
         }
-        poseidon_g_dev(s, scratch, SVB_BLOCK);
+        permute_dev<KIND>(s, scratch, SVB_BLOCK);
     }
     u64 c[4];
     ldg4(cap_entry, c);
@@ -172,10 +185,11 @@ __global__ void __launch_bounds__(SVB_BLOCK) fri_prepare_kernel(const u64* __res
 }
 
 // The fused query kernel: one thread per (class, unit).
+template <int KIND>
 __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) fri_query_kernel(const u64* __restrict__ records, FriKernelParams P,
                                                         const u64* __restrict__ scratch, u32* __restrict__ accept_bitmap,
                                                         u32* __restrict__ first_fail) {
-    __shared__ u64 pscratch[11 * SVB_BLOCK];   // poseidon_g_dev's staging of the initial-matrix outputs
+    __shared__ u64 pscratch[PermScratch<KIND>::words * SVB_BLOCK];
     const sv_fri_layout& L = P.L;
     u32 cls = P.class_order[blockIdx.x / P.blocks_per_class];
     u32 unit = (blockIdx.x % P.blocks_per_class) * blockDim.x + threadIdx.x;
@@ -198,9 +212,9 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) fri_query_kernel(con
                                      : L.off_step_caps + ((size_t)i * L.ncap + cap_index) * 4);
         const u64* leaf = q + (init ? L.q_off_init_evals[cls] : L.q_off_step_evals[i]);
         const u64* sibs = q + (init ? L.q_off_init_sibs[cls] : L.q_off_step_sibs[i]);
-        u32 rc = merkle_chain(leaf, init ? L.leaf_len[cls] : 4u, sibs, init ? L.init_depth : L.step_depth[i],
+        u32 rc = merkle_chain<KIND>(leaf, init ? L.leaf_len[cls] : 4u, sibs, init ? L.init_depth : L.step_depth[i],
                               init ? x_index : x_index >> (i + 1), cap, init ? SV_FAIL_INIT_MERKLE : SV_FAIL_STEP_MERKLE,
-                              pscratch + threadIdx.x);
+                              pscratch);
         if (rc) report_fail(accept_bitmap, first_fail, proof, query,
                             rc == SV_FAIL_NONCANONICAL ? 0 : (init ? 1 + cls : 8 + 3 * i + 2), rc);
         return;
@@ -266,8 +280,9 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) fri_query_kernel(con
 }
 
 // n independent permutations, thread per state (canonical in / out).
+template <int KIND>
 __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) poseidon_permute_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
-    __shared__ u64 scratch[11 * SVB_BLOCK];
+    __shared__ u64 scratch[PermScratch<KIND>::words * SVB_BLOCK];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     u64 s[12];
@@ -278,24 +293,25 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) poseidon_permute_ker
         s[2 * k] = v.x;
         s[2 * k + 1] = v.y;
     }
-    poseidon_g_dev(s, scratch + threadIdx.x, SVB_BLOCK);
+    permute_dev<KIND>(s, scratch, SVB_BLOCK);
     ulonglong2* o = reinterpret_cast<ulonglong2*>(out + 12 * i);
 #pragma unroll
     for (int k = 0; k < 6; k++) o[k] = make_ulonglong2(canon(s[2 * k]), canon(s[2 * k + 1]));
 }
 
 // n independent Merkle paths, thread per path.  Record = up4(leaf_len) + 4*depth words.
+template <int KIND>
 __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) merkle_verify_kernel(const u64* __restrict__ paths, const u64* __restrict__ indices,
                                                             const u64* __restrict__ caps, unsigned char* __restrict__ ok,
                                                             size_t n, u32 leaf_len, u32 depth, u32 cap_height) {
-    __shared__ u64 scratch[11 * SVB_BLOCK];
+    __shared__ u64 scratch[PermScratch<KIND>::words * SVB_BLOCK];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     u32 leaf_words = up4(leaf_len);
     const u64* rec = paths + i * (size_t)(leaf_words + 4 * depth);
     u64 index = __ldg(indices + i);
     u32 cap_index = (u32)((index >> depth) & ((1ull << cap_height) - 1));
-    u32 rc = merkle_chain(rec, leaf_len, rec + leaf_words, depth, index, caps + 4 * (size_t)cap_index, 1, scratch + threadIdx.x);
+    u32 rc = merkle_chain<KIND>(rec, leaf_len, rec + leaf_words, depth, index, caps + 4 * (size_t)cap_index, 1, scratch);
     ok[i] = rc == 0;
 }
 
@@ -322,6 +338,7 @@ struct FsParams {
     u64 g;                 // generator of the trace subgroup, 7^((p-1)/2^degree_bits)
     u32 num_challenges;
 };
+template <int KIND>
 struct DevChallenger {
     u64 st[12];
     u64 in[8], out[8];     // dynamically indexed: local memory, negligible beside the permutations
@@ -329,7 +346,7 @@ struct DevChallenger {
     u64* scratch;
     // one out-of-line copy of the permutation for the ~10 call sites of the transcript
     __device__ __noinline__ void permute() {
-        poseidon_g_dev(st, scratch, SVB_FS_BLOCK);
+        permute_dev<KIND>(st, scratch, SVB_FS_BLOCK);
 #pragma unroll
         for (int i = 0; i < 12; i++) st[i] = canon(st[i]);
 #pragma unroll
@@ -358,18 +375,19 @@ struct DevChallenger {
     }
 };
 
+template <int KIND>
 __global__ void __launch_bounds__(SVB_FS_BLOCK) fri_challenges_kernel(u64* __restrict__ records, FriKernelParams P, FsParams F,
                                                                       const u64* __restrict__ pi_hashes) {
-    __shared__ u64 pscratch[11 * SVB_FS_BLOCK];
+    __shared__ u64 pscratch[PermScratch<KIND>::words * SVB_FS_BLOCK];
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_proofs) return;
     const sv_fri_layout& L = P.L;
     u64* rec = records + (size_t)p * L.record_words;
-    DevChallenger ch;
+    DevChallenger<KIND> ch;
 #pragma unroll
     for (int i = 0; i < 12; i++) ch.st[i] = 0;
     ch.n_in = ch.n_out = 0;
-    ch.scratch = pscratch + threadIdx.x;
+    ch.scratch = pscratch;
     const u32 cap_words = L.ncap * 4;
     for (int i = 0; i < 4; i++) ch.observe(F.circuit_digest[i]);                      // :65-68
     ch.observe_n(pi_hashes + 4 * (size_t)p, 4);                                       // :69-71

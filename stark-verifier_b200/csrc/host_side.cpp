@@ -18,6 +18,7 @@
 #include "goldilocks.cuh"
 #include "layout.hpp"
 #include "poseidon_g.cuh"
+#include "poseidon_b.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -30,17 +31,24 @@
 
 namespace svb {
 
+// the width-12 permutation of a hash family, canonical in / canonical out
+static inline void permute_kind(u32 kind, u64 st[12]) {
+    if (kind == SV_HASH_POSEIDON_BN254) poseidon_b_canonical(st);
+    else poseidon_g_canonical(st);
+}
+
 // ---------------------------------------------------------------------------------------------
 struct Challenger {
+    u32 kind;
     u64 state[12];
     u64 in[8];
     int n_in;
     u64 out[8];
     int n_out;
-    Challenger() { memset(this, 0, sizeof *this); }
+    explicit Challenger(u32 hash_kind) { memset(this, 0, sizeof *this); kind = hash_kind; }
     void duplex(int len) {
         for (int i = 0; i < len; i++) state[i] = in[i];
-        poseidon_g_canonical(state);
+        permute_kind(kind, state);
         memcpy(out, state, 64);
         n_out = 8;
         n_in = 0;
@@ -54,7 +62,7 @@ struct Challenger {
     u64 squeeze() {
         if (n_in) duplex(n_in);
         if (n_out == 0) {
-            poseidon_g_canonical(state);
+            permute_kind(kind, state);
             memcpy(out, state, 64);
             n_out = 8;
         }
@@ -63,27 +71,27 @@ struct Challenger {
     fp2 squeeze2() { u64 a = squeeze(); u64 b = squeeze(); return mk2(a, b); }
 };
 
-static void hash_no_pad(const u64* in, size_t n, u64 out[4]) {
+static void hash_no_pad(u32 kind, const u64* in, size_t n, u64 out[4]) {
     u64 st[12] = {0};
     for (size_t off = 0; off < n; off += 8) {
         size_t len = std::min<size_t>(8, n - off);
         for (size_t i = 0; i < len; i++) st[i] = in[off + i];
-        poseidon_g_canonical(st);
+        permute_kind(kind, st);
     }
     memcpy(out, st, 32);
 }
-static void hash_or_noop(const u64* in, size_t n, u64 out[4]) {
+static void hash_or_noop(u32 kind, const u64* in, size_t n, u64 out[4]) {
     if (n <= 4) {
         memset(out, 0, 32);
         memcpy(out, in, n * 8);
     } else
-        hash_no_pad(in, n, out);
+        hash_no_pad(kind, in, n, out);
 }
-static void two_to_one(const u64 l[4], const u64 r[4], u64 out[4]) {
+static void two_to_one(u32 kind, const u64 l[4], const u64 r[4], u64 out[4]) {
     u64 st[12] = {0};
     memcpy(st, l, 32);
     memcpy(st + 4, r, 32);
-    poseidon_g_canonical(st);
+    permute_kind(kind, st);
     memcpy(out, st, 32);
 }
 
@@ -120,15 +128,15 @@ static inline u32 bitrev(u32 x, u32 bits) {
 // A Merkle tree stored as digest layers: layer 0 = leaf digests (n), ..., last layer = cap (ncap).
 struct Tree {
     std::vector<std::vector<u64>> layers;  // each 4*count words
-    void build(std::vector<u64>&& leaf_digests, u32 cap_height, int nthreads) {
+    void build(u32 kind, std::vector<u64>&& leaf_digests, u32 cap_height, int nthreads) {
         layers.clear();
         layers.push_back(std::move(leaf_digests));
         while (layers.back().size() / 4 > ((size_t)1 << cap_height)) {
             const std::vector<u64>& cur = layers.back();
             size_t n = cur.size() / 8;
             std::vector<u64> nxt(n * 4);
-            parallel_for(n, n >= 4096 ? nthreads : 1, [&](size_t b, size_t e) {
-                for (size_t i = b; i < e; i++) two_to_one(&cur[8 * i], &cur[8 * i + 4], &nxt[4 * i]);
+            parallel_for(n, n >= 256 ? nthreads : 1, [&](size_t b, size_t e) {
+                for (size_t i = b; i < e; i++) two_to_one(kind, &cur[8 * i], &cur[8 * i + 4], &nxt[4 * i]);
             });
             layers.push_back(std::move(nxt));
         }
@@ -207,10 +215,10 @@ struct Circuit {
                 std::vector<u64> leaf(len);
                 for (size_t i = b; i < e; i++) {
                     leaf_values(k, (u32)i, leaf.data());
-                    hash_or_noop(leaf.data(), len, &dig[4 * i]);
+                    hash_or_noop(s.hash_kind, leaf.data(), len, &dig[4 * i]);
                 }
             });
-            trees[k].build(std::move(dig), s.cap_height, nthreads);
+            trees[k].build(s.hash_kind, std::move(dig), s.cap_height, nthreads);
         }
     }
 };
@@ -234,7 +242,7 @@ static int prove(const Circuit& C, const u64 pi_hash[4], u32 num_challenges, u64
     memset(rec, 0, (size_t)L.record_words * 8);
     for (int k = 0; k < 4; k++) memcpy(rec + L.off_init_caps + (size_t)k * L.ncap * 4, C.trees[k].cap(), (size_t)L.ncap * 32);
 
-    Challenger ch;
+    Challenger ch(s.hash_kind);
     ch.observe_n(C.circuit_digest, 4);
     ch.observe_n(pi_hash, 4);
     ch.observe_n(C.trees[1].cap(), L.ncap * 4);
@@ -325,7 +333,7 @@ static int prove(const Circuit& C, const u64 pi_hash[4], u32 num_challenges, u64
             dig[4 * k] = v[2 * k].c0; dig[4 * k + 1] = v[2 * k].c1;
             dig[4 * k + 2] = v[2 * k + 1].c0; dig[4 * k + 3] = v[2 * k + 1].c1;
         }
-        step_trees[st].build(std::move(dig), s.cap_height, nthreads);
+        step_trees[st].build(s.hash_kind, std::move(dig), s.cap_height, nthreads);
         memcpy(rec + L.off_step_caps + (size_t)st * L.ncap * 4, step_trees[st].cap(), (size_t)L.ncap * 32);
         ch.observe_n(step_trees[st].cap(), L.ncap * 4);
         fp2 beta = ch.squeeze2();
@@ -421,8 +429,8 @@ extern "C" int sv_fri_challenges(const sv_fri_shape* shape, uint64_t* rec, const
                                  const uint64_t pi_hash[4], uint32_t num_challenges) {
     sv_fri_layout L;
     if (!shape || make_layout(*shape, L)) return -1;
-    if (shape->hash_kind != SV_HASH_POSEIDON_GOLDILOCKS) return -2;
-    Challenger ch;
+    if (shape->hash_kind > SV_HASH_POSEIDON_BN254) return -2;
+    Challenger ch(shape->hash_kind);
     ch.observe_n(circuit_digest, 4);
     ch.observe_n(pi_hash, 4);
     const u64* caps = rec + L.off_init_caps;
@@ -479,7 +487,7 @@ extern "C" int sv_synth_proofs(const sv_fri_shape* shape, uint64_t seed, uint32_
                                uint32_t num_challenges, uint64_t* records_out, int nthreads) {
     sv_fri_layout L;
     if (!shape || !records_out || make_layout(*shape, L)) return -1;
-    if (shape->hash_kind != SV_HASH_POSEIDON_GOLDILOCKS) return -2;
+    if (shape->hash_kind > SV_HASH_POSEIDON_BN254) return -2;
     if (shape->final_poly_len != (1u << (shape->degree_bits - shape->num_steps))) return -3;
     if (n_circuits == 0) n_circuits = 1;
     if (nthreads < 1) nthreads = 1;

@@ -372,3 +372,75 @@ def test_config5_full_size_merkle_paths(svb, orc, ctx):
     hp = paths[:sub].cpu().numpy().view(np.uint64); hi = idx[:sub].cpu().numpy().view(np.uint64)
     o = orc.merkle_verify_batch(hp, 4, depth, hi, st.reshape(1, 4), 0)
     assert (ok[:sub].cpu().numpy() == o).all()
+
+
+# ---- hash family B: Poseidon over BN254 Fr wrapped around 12 Goldilocks limbs ----
+def test_permute_b_golden_and_random(svb, orc, ctx):
+    import json
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "poseidon_b.json")))
+    ins = np.array([[int(x, 16) for x in c["in"]] for c in d["wrapped_permutation"]], dtype=np.uint64)
+    outs = np.array([[int(x, 16) for x in c["out"]] for c in d["wrapped_permutation"]], dtype=np.uint64)
+    got = ctx.poseidon_permute_batch(ins, hash_kind=svb.HASH_POSEIDON_BN254).reshape(-1, 12)
+    assert (got == outs).all()
+    assert int(got[1, 0]) == 0xd983775ce161c4e4 and int(got[1, 11]) == 0x6bf843b27c9d3fbb      # SURVEY 8c KAT
+    rng = np.random.default_rng(0xB254)
+    edge = np.array([[P - 1, 0, 1, P - 2] * 3, [P - 1] * 12, [0] * 11 + [P - 1]], dtype=np.uint64)
+    rnd = rng.integers(0, P, size=(517, 12), dtype=np.uint64)      # ragged
+    states = np.concatenate([edge, rnd])
+    got = ctx.poseidon_permute_batch(states, hash_kind=svb.HASH_POSEIDON_BN254).reshape(-1, 12)
+    want = np.array([orc.poseidon_b(s) for s in states], dtype=np.uint64)
+    assert (got == want).all()
+    assert (got < np.uint64(P)).all()
+
+
+@pytest.mark.parametrize("leaf_len,depth,cap_height", [(4, 6, 0), (3, 2, 1), (9, 3, 2), (20, 4, 1), (135, 3, 0)])
+def test_merkle_batch_hash_b(svb, orc, ctx, leaf_len, depth, cap_height):
+    rng = np.random.default_rng(leaf_len * 77 + depth)
+    n = 70
+    lw = (leaf_len + 3) & ~3
+    rec = np.zeros((n, lw + 4 * depth), dtype=np.uint64)
+    rec[:, :leaf_len] = rng.integers(0, P, size=(n, leaf_len), dtype=np.uint64)
+    rec[:, lw:] = rng.integers(0, P, size=(n, 4 * depth), dtype=np.uint64)
+    ncap = 1 << cap_height
+    idx = rng.integers(0, 1 << (depth + cap_height), size=n, dtype=np.uint64)
+    caps = rng.integers(0, P, size=(ncap, 4), dtype=np.uint64)
+    for i in range(min(n, ncap)):
+        idx[i] = (np.uint64(i) << np.uint64(depth)) | (idx[i] & np.uint64((1 << depth) - 1))
+        st = rec[i, :leaf_len].copy() if leaf_len <= 4 else orc.hash_no_pad(rec[i, :leaf_len], kind=1)
+        if leaf_len < 4:
+            st = np.concatenate([st, np.zeros(4 - leaf_len, dtype=np.uint64)])
+        for l in range(depth):
+            sib = rec[i, lw + 4 * l: lw + 4 * l + 4]
+            st = orc.two_to_one(sib, st, kind=1) if (int(idx[i]) >> l) & 1 else orc.two_to_one(st, sib, kind=1)
+        caps[i] = st
+    compact = np.concatenate([rec[:, :leaf_len], rec[:, lw:]], axis=1)
+    got = ctx.merkle_verify_batch(leaf_len, depth, cap_height, rec, idx, caps, hash_kind=svb.HASH_POSEIDON_BN254)
+    want = orc.merkle_verify_batch(compact, leaf_len, depth, idx, caps, cap_height, kind=1)
+    assert (got == want).all()
+    assert got[0] == 1 and got[ncap:].sum() == 0
+    # the same paths under the Goldilocks hash are rejected
+    assert ctx.merkle_verify_batch(leaf_len, depth, cap_height, rec, idx, caps)[0] == 0 or depth == 0
+
+
+@pytest.mark.parametrize("hiding,cap,degree_bits", [(False, 0, 6), (True, 2, 7)])
+def test_fri_hash_b_small_shapes(svb, orc, ctx, hiding, cap, degree_bits):
+    """The whole FRI query phase under hash family B (outer-proof configuration: cap_height 0)."""
+    params = tiny_params(svb, hiding=hiding, cap=cap, degree_bits=degree_bits, hash_kind=svb.HASH_POSEIDON_BN254)
+    L = svb.api.make_layout(params)
+    n = 40
+    recs = svb.synth_proofs(params, n, seed=degree_bits, n_circuits=1)
+    bad = corrupt(recs, L, np.random.default_rng(8), every=4)
+    bm, ff = ctx.fri_verify_batch(params, recs, want_fail=True)
+    oshape = orc.shape_from(params.to_shape())
+    want = orc.fri_verify_batch(oshape, recs, nthreads=8)
+    assert (bm == want).all()
+    for i in range(n):
+        assert bit(bm, i) == (0 if i in bad else 1), (i, bad.get(i))
+        ok, code, q = orc.fri_verify(oshape, recs[i])
+        assert int(ff[i]) == (0 if ok else ((max(q, 0) << 8) | code))
+    # device-side transcript with the BN254 sponge
+    cd, ph = svb.synth_public_inputs(params, n, seed=degree_bits, n_circuits=1)
+    fresh = svb.synth_proofs(params, 8, seed=degree_bits, n_circuits=1)
+    dev = _clear_challenges(fresh, L, params)
+    ctx.fri_challenges_batch(params, dev, cd[0], ph[:8])
+    assert (dev == fresh).all()

@@ -121,3 +121,21 @@ def test_oracle_accepts_full_shape_golden_proofs(orc):
         bad = rec.copy()
         bad[len(bad) // 2] ^= np.uint64(1)
         assert not orc.fri_verify(s, bad)[0]
+
+
+def test_oracle_poseidon_b_golden(orc):
+    """Hash family B (Poseidon over BN254 Fr wrapped around 12 Goldilocks limbs): the oracle's Montgomery
+    implementation against tests/golden/poseidon_b.json (pure-Python big integers over the reference's
+    constants) and the SURVEY 8c KATs (state [0,1,2,3,4] -> circomlib poseidon([1,2,3,4]))."""
+    import json
+    import os
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "poseidon_b.json")))
+    for c in d["fr_permutation"]:
+        got = orc.poseidon_b_fr([int(x, 16) for x in c["in"]])
+        assert got == [int(x, 16) for x in c["out"]]
+    assert orc.poseidon_b_fr([0, 1, 2, 3, 4])[0] == 0x299c867db6c1fdd79dcefa40e4510b9837e60ebb1ce0663dbaa525df65250465
+    for c in d["wrapped_permutation"]:
+        got = orc.poseidon_b([int(x, 16) for x in c["in"]])
+        assert [int(x) for x in got] == [int(x, 16) for x in c["out"]]
+    w = orc.poseidon_b(list(range(12)))
+    assert int(w[0]) == 0xd983775ce161c4e4 and int(w[11]) == 0x6bf843b27c9d3fbb

@@ -69,6 +69,55 @@ def hash_no_pad_py(inp):
     return st[:4]
 
 
+# ---- hash family B: Poseidon over BN254 Fr wrapped around 12 Goldilocks limbs (pure big integers) ----
+R_BN = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+def b_constants():
+    ref = "/root/reference/src/plonky2_verifier/bn245_poseidon/constants.rs"
+    if os.path.exists(ref):
+        t = open(ref).read()
+        rc = [int(x, 16) for x in re.findall(r'"0x([0-9a-fA-F]+)"', re.search(r"ROUND_CONSTANTS_STR[^=]*=\s*\[(.*?)\];", t, re.S).group(1))]
+        mds = [int(x, 16) for x in re.findall(r'"0x([0-9a-fA-F]+)"', re.search(r"MDS_MATRIX_STR[^=]*=\s*\[(.*?)\];\s*\n\s*fn ", t, re.S).group(1))]
+    else:
+        t = open(os.path.join(ROOT, "oracle", "poseidon_b_constants.h")).read()
+        def tab(name):
+            w = [int(x, 16) for x in re.findall(r"0x([0-9a-f]{16})ULL", re.search(name + r"\[[^\]]*\] = \{(.*?)\};", t, re.S).group(1))]
+            return [sum(w[4 * i + k] << (64 * k) for k in range(4)) for i in range(len(w) // 4)]
+        rc, mds = tab("ORC_B_ROUND_CONSTANTS"), tab("ORC_B_MDS")
+    assert len(rc) == 340 and len(mds) == 25
+    return rc, [mds[5 * i:5 * i + 5] for i in range(5)]
+
+
+def poseidon_b_fr_py(st, consts):
+    """bn245_poseidon/native.rs:43-60 on Python integers."""
+    rc, mds = consts
+    st = list(st)
+    c = 0
+    for rnd in range(68):
+        st = [(x + rc[c + i]) % R_BN for i, x in enumerate(st)]
+        c += 5
+        if rnd < 4 or rnd >= 64:
+            st = [pow(x, 5, R_BN) for x in st]
+        else:
+            st[0] = pow(st[0], 5, R_BN)
+        st = [sum(st[j] * mds[i][j] for j in range(5)) % R_BN for i in range(5)]
+    return st
+
+
+def poseidon_b_py(s12, consts):
+    """Bn254PoseidonPermutation::permute (plonky2_config.rs:38-51) with encode_fe / decode_fe (native.rs:62-77)."""
+    enc = [s12[3 * k] + s12[3 * k + 1] * P + s12[3 * k + 2] * P * P for k in range(4)] + [0]
+    out = poseidon_b_fr_py(enc, consts)
+    res = []
+    for k in range(4):
+        v = out[k]
+        for _ in range(3):
+            res.append(v % P)
+            v //= P
+    return res
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
@@ -86,6 +135,24 @@ def main():
         hashes.append({"in": [f"{x:016x}" for x in s], "out": [f"{x:016x}" for x in hash_no_pad_py(s)]})
     json.dump({"source": "tools/gen_golden.py: pure-Python naive Poseidon over the reference's ALL_ROUND_CONSTANTS",
                "permutation": perm, "hash_no_pad": hashes}, open(os.path.join(out_dir, "poseidon_g.json"), "w"), indent=0)
+
+    consts = b_constants()
+    kat = poseidon_b_fr_py([0, 1, 2, 3, 4], consts)
+    assert kat[0] == 0x299c867db6c1fdd79dcefa40e4510b9837e60ebb1ce0663dbaa525df65250465   # circomlib poseidon([1,2,3,4])
+    fr_cases = [{"in": [f"{x:064x}" for x in st], "out": [f"{x:064x}" for x in poseidon_b_fr_py(st, consts)]}
+                for st in ([0, 1, 2, 3, 4], [0] * 5, [R_BN - 1] * 5,
+                           [int.from_bytes(rng.bytes(32), "little") % R_BN for _ in range(5)])]
+    wrapped = []
+    for s12 in ([0] * 12, list(range(12)), [P - 1] * 12):
+        wrapped.append({"in": [f"{x:016x}" for x in s12], "out": [f"{x:016x}" for x in poseidon_b_py(s12, consts)]})
+    assert wrapped[1]["out"][0] == "d983775ce161c4e4" and wrapped[1]["out"][11] == "6bf843b27c9d3fbb"
+    for _ in range(9):
+        s12 = [int(x) for x in rng.integers(0, P, size=12, dtype=np.uint64)]
+        wrapped.append({"in": [f"{x:016x}" for x in s12], "out": [f"{x:016x}" for x in poseidon_b_py(s12, consts)]})
+    json.dump({"source": "tools/gen_golden.py: pure-Python Poseidon-BN254 (T=5, x^5, 8+60 rounds) over the reference's "
+                         "bn245_poseidon/constants.rs, with the 3-limb base-p packing of native.rs:62-77",
+               "fr_permutation": fr_cases, "wrapped_permutation": wrapped},
+              open(os.path.join(out_dir, "poseidon_b.json"), "w"), indent=0)
 
     # FRI fixtures: tiny shapes, valid + corrupted, labelled by the oracle
     import stark_verifier_b200 as svb
@@ -109,6 +176,9 @@ def main():
     # one full-shape proof per BASELINE shape (A: configs[1], B: configs[2]); the shape-B prover run takes
     # about a minute on the host, which is why the proof is a committed fixture
     big = {}
+    if os.path.exists(os.path.join(out_dir, "fri_full_shapes.npz")) and "--full" not in sys.argv:
+        print("fri_full_shapes.npz kept (pass --full to regenerate: ~3 minutes)")
+        return
     for tag, params in (("shape_a", svb.SHAPE_A), ("shape_b", svb.SHAPE_B)):
         rec = svb.synth_proofs(params, 1, seed=0xB2000003, n_circuits=1)
         ok, code, q = orc.fri_verify(orc.shape_from(params.to_shape()), rec[0])

@@ -30,7 +30,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="A", choices=["A", "B", "merkle"])
+    ap.add_argument("--workload", default="A", choices=["A", "B", "merkle", "outer"],
+                    help="A = configs[1], B = configs[2], merkle = configs[4], outer = the reference's outer wrapped-proof "
+                         "configuration (hash family B = Poseidon-BN254, cap_height 0)")
     ap.add_argument("--proofs", type=int, default=0, help="proofs per GPU per step (default 4096 for A, 256 for B)")
     ap.add_argument("--distinct", type=int, default=0, help="distinct base proofs generated on the host (default 64 / 4)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the cpu_baseline sample (default: sized for ~12 s of CPU work)")
@@ -95,7 +97,7 @@ def measured_peak_gbs():
 
 
 def workload_params(svb, name):
-    return {"A": svb.SHAPE_A, "B": svb.SHAPE_B}[name]
+    return {"A": svb.SHAPE_A, "B": svb.SHAPE_B, "outer": svb.SHAPE_OUTER_BN254}[name]
 
 
 def cpu_baseline(svb, params, base, sample_proofs, threads):
@@ -177,10 +179,10 @@ def main():
     L = svb.api.make_layout(params)
     n = args.proofs or (4096 if args.workload == "A" else 256)
     n = (n + 31) & ~31
-    distinct = args.distinct or (64 if args.workload == "A" else 2)
+    distinct = args.distinct or {"A": 64, "B": 2, "outer": 4}[args.workload]
     # synthetic proofs: `distinct` base proofs per rank (own seed), tiled to n PHYSICALLY DISTINCT copies
     t0 = time.perf_counter()
-    base = svb.synth_proofs(params, distinct, seed=0xB2000002 ^ (rank << 20), n_circuits=min(2, distinct),
+    base = svb.synth_proofs(params, distinct, seed=0xB2000002 ^ (rank << 20), n_circuits=1 if args.workload == "outer" else min(2, distinct),
                             nthreads=max(1, threads // max(1, world)))
     t_gen = time.perf_counter() - t0
     rw = L.record_words
@@ -307,7 +309,10 @@ def main():
         "metric": "plonky2_proofs_verified_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[{1 if args.workload == 'A' else 2}]: {n} proofs/GPU/step, shape {args.workload}",
+        "config": {"workload": {"A": f"BASELINE configs[1]: {n} proofs/GPU/step, shape A",
+                                "B": f"BASELINE configs[2]: {n} proofs/GPU/step, shape B",
+                                "outer": f"outer wrapped-proof configuration (Poseidon-BN254 hash, cap_height 0): {n} proofs/GPU/step"}[args.workload],
+                   "hash_kind": params.hash_kind,
                    "trace_bits": params.degree_bits, "fri_queries": params.config.num_query_rounds,
                    "blowup": 1 << params.config.rate_bits, "cap_height": params.config.cap_height,
                    "pow_bits": params.config.proof_of_work_bits, "proofs_per_gpu": n, "distinct_base_proofs": distinct,
@@ -326,7 +331,7 @@ def main():
         # what actually binds: the 32x32->64 integer multiplier.  IMAD.WIDE issues every
         # 4.24 cycles per SM sub-partition (profiles/pipes2_b200_r1.txt); a permutation needs 4 308
         # of them algorithmically (1 077 modular multiplications x 4 limb products).
-        "int_mul_roofline": {"achieved_gmul_s": perms * 4308 / k_avg_s / 1e9,
+        "int_mul_roofline": None if params.hash_kind else {"achieved_gmul_s": perms * 4308 / k_avg_s / 1e9,
                              "peak_gmul_s": 148 * 4 * 32 / 4.24 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
                              "frac": (perms * 4308 / k_avg_s) / (148 * 4 * 32 / 4.24 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
                              "unit": "1e9 32x32->64 multiplies/s", "kernel": "fri_query_kernel"},
@@ -337,6 +342,8 @@ def main():
         if not sample:
             # probe on a small batch, then size the sample for ~12 s of CPU work on all host threads
             probe = 8 * threads if args.workload == "A" else threads
+            if args.workload == "outer":
+                probe = max(4, threads // 4)
             v0, _, _ = cpu_baseline(svb, params, base, probe, threads)
             sample = max(probe, int(v0 * 12.0) // threads * threads)
         v, dt, _ = cpu_baseline(svb, params, base, sample, threads)

@@ -136,3 +136,26 @@ def test_shard_ranges(svb):
                 cover.append((a, b))
             assert cover[0][0] == 0 and cover[-1][1] == n
             assert all(cover[i][1] == cover[i + 1][0] for i in range(world - 1))
+
+
+def test_host_hash_b_prover_and_transcript_match_oracle(svb, orc):
+    """Hash family B on the host side of the product (32-bit-limb Montgomery, product-scanning dot products)
+    against the oracle (64-bit-limb CIOS): a proof built by the product's prover under Poseidon-BN254 is
+    accepted by the oracle, rejected after one bit flip, rejected when read as a Poseidon-Goldilocks proof,
+    and both transcripts derive identical challenges."""
+    params = svb.api._params(6, 3, 1, 4, 5, hash_kind=svb.HASH_POSEIDON_BN254)
+    L = svb.api.make_layout(params)
+    recs = svb.synth_proofs(params, 3, seed=3, n_circuits=1)
+    oshape = orc.shape_from(params.to_shape())
+    assert all(orc.fri_verify(oshape, recs[i])[0] for i in range(3))
+    bad = recs[1].copy()
+    bad[L.header_words + L.q_off_init_sibs[2] + 1] ^= np.uint64(1)
+    assert orc.fri_verify(oshape, bad) == (False, 3, 0)
+    g = svb.api._params(6, 3, 1, 4, 5)
+    assert not orc.fri_verify(orc.shape_from(g.to_shape()), recs[0])[0]
+    cd, ph = svb.synth_public_inputs(params, 3, seed=3, n_circuits=1)
+    a, b = recs[2].copy(), recs[2].copy()
+    a[L.off_alpha] = 0; b[L.off_alpha] = 0
+    svb.fri_challenges(params, a, cd[0], ph[2])
+    orc.fri_challenges(oshape, b, cd[0], ph[2])
+    assert (a == recs[2]).all() and (b == recs[2]).all()

@@ -304,10 +304,19 @@ SVB_D void poseidon_g_dev(u64 s[12], u64* __restrict__ scratch /* 11 words of pe
     // round constants of round 0 (poseidon.rs:637-640); later constants ride on the MDS accumulators
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = add_lc(s[i], d_ALL_ROUND_CONSTANTS[i]);
+    // SVB_ABLATE (tools/lab only; the result is WRONG when set): bit 0 skips the full-round S-boxes, 1 the
+    // MDS layers, 2 the initial matrix, 3 the partial-round dot product, 4 the partial-round rank-1
+    // update, 5 the partial-round S-box.  Timing differences give the cost of each section.
+#ifndef SVB_ABLATE
+#define SVB_ABLATE 0
+#endif
 #pragma unroll 1
     for (int f = 0; f < 8; f++) {
         // S-box layer: 4 lanes per iteration, state rotated by 4 between iterations (:438-448)
-#if SVB_SBOX_LANES == 12
+#if SVB_ABLATE & 1
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] ^= s[(i + 1) % 12] >> 3;
+#elif SVB_SBOX_LANES == 12
 #pragma unroll
         for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
 #else
@@ -318,9 +327,15 @@ SVB_D void poseidon_g_dev(u64 s[12], u64* __restrict__ scratch /* 11 words of pe
             rot_lanes(s);
         }
 #endif
+#if SVB_ABLATE & 2
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] += s[(i + 5) % 12] ^ d_FULL_RC_NEXT[12 * f + i];
+#else
         mds_layer_rc_f64(s, d_FULL_RC_NEXT_F64 + 24 * f);   // (:450-502) + next constant layer
+#endif
         if (f == 3) {
             // mds_partial_layer_init (:504-537): t[c] = sum_{r=1..11} INIT[r-1][c-1] * s[r]
+#if !(SVB_ABLATE & 4)
 #pragma unroll 1
             for (int c = 0; c < 11; c++) {
                 dot_acc a;
@@ -331,18 +346,30 @@ SVB_D void poseidon_g_dev(u64 s[12], u64* __restrict__ scratch /* 11 words of pe
             }
 #pragma unroll
             for (int c = 0; c < 11; c++) s[c + 1] = scratch[c * scratch_stride];
+#endif
             // 22 partial rounds (:654-672)
 #pragma unroll 1
             for (int r = 0; r < 22; r++) {
+#if SVB_ABLATE & 32
+                u64 s0 = s[0] + d_FAST_PARTIAL_ROUND_CONSTANTS[r];
+#else
                 u64 s0 = sbox7_add(s[0], d_FAST_PARTIAL_ROUND_CONSTANTS[r]);   // entry 21 is 0 (:140)
+#endif
                 // mds_partial_layer_fast (:539-589)
                 dot_acc a;
                 dot_init(a);
                 dot_mac_small(a, 25, s0);   // MDS_MATRIX_CIRC[0] + MDS_MATRIX_DIAG[0]
+#if !(SVB_ABLATE & 8)
 #pragma unroll
                 for (int i = 1; i < 12; i++) dot_mac(a, s[i], d_FAST_PARTIAL_ROUND_W_HATS[r * 11 + i - 1]);
+#endif
+#if SVB_ABLATE & 16
+#pragma unroll
+                for (int i = 1; i < 12; i++) s[i] += s0 ^ d_FAST_PARTIAL_ROUND_VS[r * 11 + i - 1];
+#else
 #pragma unroll
                 for (int i = 1; i < 12; i++) s[i] = mul_add(d_FAST_PARTIAL_ROUND_VS[r * 11 + i - 1], s0, s[i]);
+#endif
                 s[0] = dot_reduce(a);
             }
             // constant layer of full round 26 (:675-678)

@@ -69,7 +69,7 @@ int main(int argc, char** argv) {
     cudaMalloc(&din, 12 * n * 8); cudaMalloc(&dout, 12 * n * 8);
     cudaMemcpy(din, h.data(), 12 * n * 8, cudaMemcpyHostToDevice);
     // correctness: single permutation kernel vs host on the first 4096 states
-    poseidon_permute_kernel<<<(unsigned)((n + SVB_BLOCK - 1) / SVB_BLOCK), SVB_BLOCK>>>(din, dout, n);
+    poseidon_permute_kernel<0><<<(unsigned)((n + SVB_BLOCK - 1) / SVB_BLOCK), SVB_BLOCK>>>(din, dout, n);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 2; }
     cudaMemcpy(got.data(), dout, 12 * n * 8, cudaMemcpyDeviceToHost);

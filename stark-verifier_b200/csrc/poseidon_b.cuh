@@ -206,11 +206,53 @@ SVB_HD void poseidon_b_fr(fr st[5]) {
         for (int i = 0; i < 5; i++) st[i] = nw[i];
     }
 }
+// The same permutation with the 60 partial rounds in sparse form (tools/gen_poseidon_bn254_constants.py
+// derives and checks the constants): a matrix [[1,0],[0,B]] commutes with the lane-0 S-box, so every
+// partial-round MDS factors into a sparse matrix [[m00, w^T],[v, I]] times such a block matrix that is
+// handed to the round before; what remains is one dense 4x4 block in front (D0) and per round one 5-term
+// dot product (lane 0) plus four multiply-adds instead of five 5-term dot products.
+// Table rows (14 elements per partial round r): m00, w_hat_r[4], v_r[4], c'_r[5].
+SVB_HD void poseidon_b_fr_sparse(fr st[5]) {
+    const u64* RC = SVB_TB(B_ROUND_CONSTANTS_MONT);
+    const u64* SP = SVB_TB(B_SPARSE_ROUNDS_MONT);
+    for (int half = 0; half < 2; half++) {
+        for (int round = half ? 64 : 0; round < (half ? 68 : 4); round++) {
+            for (int i = 0; i < 5; i++) st[i] = fr_pow5(fr_add(st[i], fr_const(RC, 5 * round + i)));
+            fr nw[5];
+            for (int i = 0; i < 5; i++) {
+                fr row[5];
+                for (int j = 0; j < 5; j++) row[j] = fr_const(SVB_TB(B_MDS_MONT), 5 * i + j);
+                nw[i] = fr_dot_mont<5>(st, row);
+            }
+            for (int i = 0; i < 5; i++) st[i] = nw[i];
+        }
+        if (half) break;
+        // t_0 = D0 (s + c_0) = D0 s + c'_0
+        fr t[5];
+        t[0] = fr_add(st[0], fr_const(SP, 9));
+        for (int i = 0; i < 4; i++) {
+            fr row[4];
+            for (int j = 0; j < 4; j++) row[j] = fr_const(SVB_TB(B_SPARSE_D0_MONT), 4 * i + j);
+            t[1 + i] = fr_add(fr_dot_mont<4>(st + 1, row), fr_const(SP, 10 + i));
+        }
+        for (int r = 0; r < 60; r++) {
+            fr a[5], b[5];
+            a[0] = fr_pow5(t[0]);
+            for (int j = 1; j < 5; j++) a[j] = t[j];
+            for (int j = 0; j < 5; j++) b[j] = fr_const(SP, 14 * r + j);
+            t[0] = fr_dot_mont<5>(a, b);
+            for (int j = 1; j < 5; j++) t[j] = fr_add(a[j], fr_mmul(fr_const(SP, 14 * r + 4 + j), a[0]));
+            if (r < 59)
+                for (int j = 0; j < 5; j++) t[j] = fr_add(t[j], fr_const(SP, 14 * (r + 1) + 9 + j));
+        }
+        for (int i = 0; i < 5; i++) st[i] = t[i];
+    }
+}
 inline void poseidon_b_canonical(u64 s[12]) {
     fr st[5];
     for (int k = 0; k < 4; k++) st[k] = fr_encode3(canon(s[3 * k]), canon(s[3 * k + 1]), canon(s[3 * k + 2]));
     for (int i = 0; i < 8; i++) st[4].l[i] = 0;
-    poseidon_b_fr(st);
+    poseidon_b_fr_sparse(st);
     for (int k = 0; k < 4; k++) fr_decode3(st[k], s + 3 * k);
 }
 
@@ -240,25 +282,56 @@ SVB_D void poseidon_b_dev(u64 s[12], u32* sm, u32 stride) {
         b_store(sm, stride, 4, z);
     }
 #pragma unroll 1
-    for (int round = 0; round < 68; round++) {
-        const int nl = (round < 4 || round >= 64) ? 5 : 1;
-        // constant layer + S-box layer, one lane at a time (native.rs:16-31)
+    for (int half = 0; half < 2; half++) {
+        // four full rounds (native.rs:45-49 / :55-59): constant layer + x^5 on every lane, then the MDS
 #pragma unroll 1
-        for (int lane = 0; lane < 5; lane++) {
-            fr x = fr_add(b_load(sm, stride, lane), fr_const(d_B_ROUND_CONSTANTS_MONT, 5 * round + lane));
-            if (lane < nl) x = fr_pow5(x);
-            b_store(sm, stride, lane, x);
+        for (int round = half ? 64 : 0; round < (half ? 68 : 4); round++) {
+#pragma unroll 1
+            for (int lane = 0; lane < 5; lane++)
+                b_store(sm, stride, lane, fr_pow5(fr_add(b_load(sm, stride, lane), fr_const(d_B_ROUND_CONSTANTS_MONT, 5 * round + lane))));
+            fr st[5];
+#pragma unroll
+            for (int j = 0; j < 5; j++) st[j] = b_load(sm, stride, j);
+#pragma unroll 1
+            for (int i = 0; i < 5; i++) {
+                fr row[5];
+#pragma unroll
+                for (int j = 0; j < 5; j++) row[j] = fr_const(d_B_MDS_MONT, 5 * i + j);
+                b_store(sm, stride, i, fr_dot_mont<5>(st, row));
+            }
         }
-        // MDS layer (native.rs:33-41): all five lanes in registers, one output row per iteration
-        fr st[5];
+        if (half) break;
+        // the 60 partial rounds (native.rs:50-54) in sparse form, see poseidon_b_fr_sparse
+        {
+            fr st[5];
 #pragma unroll
-        for (int j = 0; j < 5; j++) st[j] = b_load(sm, stride, j);
+            for (int j = 0; j < 5; j++) st[j] = b_load(sm, stride, j);
+            b_store(sm, stride, 0, fr_add(st[0], fr_const(d_B_SPARSE_ROUNDS_MONT, 9)));
 #pragma unroll 1
-        for (int i = 0; i < 5; i++) {
-            fr row[5];
+            for (int i = 0; i < 4; i++) {
+                fr row[4];
 #pragma unroll
-            for (int j = 0; j < 5; j++) row[j] = fr_const(d_B_MDS_MONT, 5 * i + j);
-            b_store(sm, stride, i, fr_dot_mont<5>(st, row));
+                for (int j = 0; j < 4; j++) row[j] = fr_const(d_B_SPARSE_D0_MONT, 4 * i + j);
+                b_store(sm, stride, 1 + i, fr_add(fr_dot_mont<4>(st + 1, row), fr_const(d_B_SPARSE_ROUNDS_MONT, 10 + i)));
+            }
+        }
+#pragma unroll 1
+        for (int r = 0; r < 60; r++) {
+            const u64* sp = d_B_SPARSE_ROUNDS_MONT + 4 * 14 * r;
+            fr a[5], b[5];
+            a[0] = fr_pow5(b_load(sm, stride, 0));
+#pragma unroll
+            for (int j = 1; j < 5; j++) a[j] = b_load(sm, stride, j);
+#pragma unroll
+            for (int j = 0; j < 5; j++) b[j] = fr_const(sp, j);
+            fr n0 = fr_dot_mont<5>(a, b);
+            const bool more = r < 59;
+            b_store(sm, stride, 0, more ? fr_add(n0, fr_const(sp, 14 + 9)) : n0);
+#pragma unroll 1
+            for (int j = 1; j < 5; j++) {
+                fr u = fr_add(b_load(sm, stride, j), fr_mmul(fr_const(sp, 4 + j), a[0]));
+                b_store(sm, stride, j, more ? fr_add(u, fr_const(sp, 14 + 9 + j)) : u);
+            }
         }
     }
 #pragma unroll

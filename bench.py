@@ -121,12 +121,14 @@ def run_reference(args):
     if rank != 0:
         return
     import stark_verifier_b200 as svb
-    params = workload_params(svb, "A" if args.workload == "merkle" else args.workload)
+    wl = "A" if args.workload == "merkle" else args.workload
+    params = workload_params(svb, wl)
     L = svb.api.make_layout(params)
     threads = os.cpu_count() or 1
-    distinct = args.distinct or (16 if args.workload != "B" else 2)
-    base = svb.synth_proofs(params, distinct, seed=0xB2000002, n_circuits=min(4, distinct), nthreads=threads)
-    sample = args.cpu_sample or (64 * threads if args.workload != "B" else 2 * threads)
+    distinct = args.distinct or {"A": 16, "B": 2, "outer": 2}[wl]
+    base = svb.synth_proofs(params, distinct, seed=0xB2000002, n_circuits=1 if wl == "outer" else min(4, distinct), nthreads=threads)
+    sample = args.cpu_sample or {"A": 64 * threads, "B": 2 * threads, "outer": max(2, threads // 4)}[wl]
+    n_gpu_arm = args.proofs or (4096 if wl == "A" else 256)
     from oracle import binding as orc
     oshape = orc.shape_from(params.to_shape())
     recs = np.ascontiguousarray(np.tile(base, ((sample + distinct - 1) // distinct, 1))[:sample])
@@ -143,9 +145,13 @@ def run_reference(args):
         "impl": "reference", "metric": "plonky2_proofs_verified_per_sec", "value": v, "unit": "proofs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"shape {args.workload}: {sample} proofs/step (bounded sample of configs[1]) on host CPU",
-                   "trace_bits": params.degree_bits, "fri_queries": params.config.num_query_rounds,
-                   "blowup": 1 << params.config.rate_bits},
+        "config": {"workload": {"A": f"BASELINE configs[1]: {n_gpu_arm} proofs/GPU/step, shape A",
+                                "B": f"BASELINE configs[2]: {n_gpu_arm} proofs/GPU/step, shape B",
+                                "outer": f"outer wrapped-proof configuration (Poseidon-BN254 hash, cap_height 0): {n_gpu_arm} proofs/GPU/step"}[wl],
+                   "hash_kind": params.hash_kind, "trace_bits": params.degree_bits, "fri_queries": params.config.num_query_rounds,
+                   "blowup": 1 << params.config.rate_bits, "cap_height": params.config.cap_height,
+                   "pow_bits": params.config.proof_of_work_bits,
+                   "sample": f"each step verifies a bounded sample of {sample} proofs of that workload on the host CPU"},
         "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} proofs x {args.steps} steps, oracle/oracle.c on {threads} threads ({cpu}); "
                                    "CPU restatement of reference semantics, not the Rust binary"},

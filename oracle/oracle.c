@@ -503,17 +503,12 @@ done:
     return code == ORC_OK;
 }
 
-typedef struct { const orc_shape *s; const uint64_t *records; size_t n, stride; uint32_t *bitmap; int tid, nt; } batch_arg;
+typedef struct { const orc_shape *s; const uint64_t *records; size_t n, stride; uint8_t *ok; int tid, nt; } batch_arg;
 static void *batch_worker(void *p) {
     batch_arg *a = (batch_arg *)p;
-    /* each thread owns whole 32-proof words: no atomics needed */
-    size_t nwords = (a->n + 31) / 32;
-    for (size_t w = (size_t)a->tid; w < nwords; w += (size_t)a->nt) {
-        uint32_t word = 0;
-        for (size_t i = w * 32; i < a->n && i < w * 32 + 32; i++)
-            if (orc_fri_verify(a->s, a->records + i * a->stride, NULL, NULL)) word |= 1u << (i & 31);
-        a->bitmap[w] = word;
-    }
+    /* proofs are dealt round-robin; every thread writes its own bytes, the caller packs the bitmap */
+    for (size_t i = (size_t)a->tid; i < a->n; i += (size_t)a->nt)
+        a->ok[i] = (uint8_t)orc_fri_verify(a->s, a->records + i * a->stride, NULL, NULL);
     return NULL;
 }
 void orc_fri_verify_batch(const orc_shape *s, const uint64_t *records, size_t n, uint32_t *bitmap, int nthreads) {
@@ -521,13 +516,20 @@ void orc_fri_verify_batch(const orc_shape *s, const uint64_t *records, size_t n,
     if (orc_make_layout(s, &L)) return;
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
+    uint8_t *ok = (uint8_t *)calloc(n ? n : 1, 1);
     pthread_t th[256];
     batch_arg args[256];
     for (int t = 0; t < nthreads; t++) {
-        args[t] = (batch_arg){s, records, n, L.record_words, bitmap, t, nthreads};
+        args[t] = (batch_arg){s, records, n, L.record_words, ok, t, nthreads};
         pthread_create(&th[t], NULL, batch_worker, &args[t]);
     }
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    for (size_t w = 0; w < (n + 31) / 32; w++) {
+        uint32_t word = 0;
+        for (size_t i = w * 32; i < n && i < w * 32 + 32; i++) word |= (uint32_t)ok[i] << (i & 31);
+        bitmap[w] = word;
+    }
+    free(ok);
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -307,6 +307,12 @@ def main():
         return
 
     peak, peak_src = measured_peak_gbs()
+    # DRAM traffic of one launch of the dominant kernel, from the committed ncu capture of this same workload
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json"))).get(f"{args.workload}:{n}")
+    except Exception:
+        pass
     algo_bytes = n * (params.config.num_query_rounds * L.algo_bytes_per_query + L.algo_bytes_shared)
     k_avg_s = (kernel_ms / max(1, kernel_n)) / 1e3
     achieved = algo_bytes / k_avg_s / 1e9
@@ -329,7 +335,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "fri_query_kernel", "kernel_ms": kernel_ms / max(1, kernel_n),
+                     "traffic": traffic, "kernel": "fri_query_kernel", "kernel_ms": kernel_ms / max(1, kernel_n),
                      "kernel_share_of_step": kernel_ms / ms, "algorithmic_bytes_per_launch": int(algo_bytes),
                      "peak_source": peak_src,
                      "note": "integer-issue bound, not HBM bound (SURVEY 8d): see perms_per_sec"},

@@ -444,3 +444,29 @@ def test_fri_hash_b_small_shapes(svb, orc, ctx, hiding, cap, degree_bits):
     dev = _clear_challenges(fresh, L, params)
     ctx.fri_challenges_batch(params, dev, cd[0], ph[:8])
     assert (dev == fresh).all()
+
+
+def test_error_convention(svb, ctx):
+    """Bad arguments are errors (negative return + message); an invalid proof never is."""
+    import ctypes
+    lib = svb.lib()
+    params = tiny_params(svb)
+    L = svb.api.make_layout(params)
+    recs = np.zeros((2, L.record_words), dtype=np.uint64)           # all-zero records: invalid proofs, not errors
+    bm = ctx.fri_verify_batch(params, recs)
+    assert int(bm[0]) == 0
+    s = params.to_shape()
+    s.hash_kind = 7
+    out = np.zeros(1, dtype=np.uint32)
+    rc = lib.sv_fri_verify_batch(ctx._h, ctypes.byref(s), 2, recs.ctypes.data, out.ctypes.data, None, svb.MEM_HOST)
+    assert rc < 0 and b"hash_kind" in lib.sv_last_error(ctx._h)
+    s = params.to_shape()
+    s.num_steps = 40                                                 # > SV_MAX_STEPS
+    rc = lib.sv_fri_verify_batch(ctx._h, ctypes.byref(s), 2, recs.ctypes.data, out.ctypes.data, None, svb.MEM_HOST)
+    assert rc < 0
+    with pytest.raises(svb.SvError):
+        ctx.merkle_verify_batch(0, 3, 0, np.zeros((1, 16), dtype=np.uint64), np.zeros(1, dtype=np.uint64), np.zeros(4, dtype=np.uint64))
+    with pytest.raises(svb.SvError):
+        ctx.poseidon_permute_batch(np.zeros((1, 12), dtype=np.uint64), hash_kind=9)
+    # the context is still usable after errors
+    assert int(ctx.poseidon_permute_batch(np.arange(12, dtype=np.uint64))[0]) == 0xd64e1e3efc5b8e9e

@@ -161,30 +161,32 @@ SVB_HD u64 reduce96(u64 lo, u32 hi32) {
 // multiplication by EPS into IMAD.HI + IMAD.IADD (6 fmaheavy cycles instead of 4).
 __constant__ u32 d_EPS32 = 0xFFFFFFFFu;
 
-// a*b = r0 + r1 W + r2 W^2 + r3 W^3  (W = 2^32)
+// a*b = r0 + r1 W + r2 W^2 + r3 W^3  (W = 2^32).  The carry of the cross-term sum N = a1*b0 + a0*b1 and the
+// carry of the column additions both land in r3 through `addc ..., 0` instructions that ptxas merges
+// into ONE IADD3.X with two carry-in predicates (no SEL to materialise a flag).
 SVB_D void mulw4(u64 a, u64 b, u32& r0, u32& r1, u32& r2, u32& r3) {
     u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
-    asm("{\n\t.reg .u32 m0, m1, n0, n1, c, p1, q0, q1;\n\t.reg .u64 P, Q, M;\n\t"
-        "mul.wide.u32 M, %4, %7;\n\t mov.b64 {m0, m1}, M;\n\t"
-        "mad.lo.cc.u32 n0, %5, %6, m0;\n\t madc.hi.cc.u32 n1, %5, %6, m1;\n\t addc.u32 c, 0, 0;\n\t"
-        "mul.wide.u32 P, %4, %6;\n\t mov.b64 {%0, p1}, P;\n\t"
+    asm("{\n\t.reg .u32 m0, m1, n0, n1, r3p, p1, q0, q1;\n\t.reg .u64 P, Q, M;\n\t"
         "mul.wide.u32 Q, %5, %7;\n\t mov.b64 {q0, q1}, Q;\n\t"
+        "mul.wide.u32 M, %4, %7;\n\t mov.b64 {m0, m1}, M;\n\t"
+        "mad.lo.cc.u32 n0, %5, %6, m0;\n\t madc.hi.cc.u32 n1, %5, %6, m1;\n\t addc.u32 r3p, q1, 0;\n\t"
+        "mul.wide.u32 P, %4, %6;\n\t mov.b64 {%0, p1}, P;\n\t"
         "add.cc.u32 %1, p1, n0;\n\t"
         "addc.cc.u32 %2, q0, n1;\n\t"
-        "addc.u32 %3, q1, c;\n\t"
+        "addc.u32 %3, r3p, 0;\n\t"
         "}" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
 }
 // a*b + c (c any u64): the addend rides on the a0*b0 product, its carry on the a1*b1 product
 SVB_D void muladdw4(u64 a, u64 b, u64 cc, u32& r0, u32& r1, u32& r2, u32& r3) {
     u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), c0 = (u32)cc, c1 = (u32)(cc >> 32);
-    asm("{\n\t.reg .u32 m0, m1, n0, n1, c, p1, q0, q1;\n\t.reg .u64 M;\n\t"
-        "mul.wide.u32 M, %4, %7;\n\t mov.b64 {m0, m1}, M;\n\t"
-        "mad.lo.cc.u32 n0, %5, %6, m0;\n\t madc.hi.cc.u32 n1, %5, %6, m1;\n\t addc.u32 c, 0, 0;\n\t"
+    asm("{\n\t.reg .u32 m0, m1, n0, n1, r3p, p1, q0, q1;\n\t.reg .u64 M;\n\t"
         "mad.lo.cc.u32 %0, %4, %6, %8;\n\t madc.hi.cc.u32 p1, %4, %6, %9;\n\t"
         "madc.lo.cc.u32 q0, %5, %7, 0;\n\t madc.hi.u32 q1, %5, %7, 0;\n\t"
+        "mul.wide.u32 M, %4, %7;\n\t mov.b64 {m0, m1}, M;\n\t"
+        "mad.lo.cc.u32 n0, %5, %6, m0;\n\t madc.hi.cc.u32 n1, %5, %6, m1;\n\t addc.u32 r3p, q1, 0;\n\t"
         "add.cc.u32 %1, p1, n0;\n\t"
         "addc.cc.u32 %2, q0, n1;\n\t"
-        "addc.u32 %3, q1, c;\n\t"
+        "addc.u32 %3, r3p, 0;\n\t"
         "}" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(c0), "r"(c1));
 }
 // r0 + r1 W + r2 W^2 + r3 W^3 + r4 W^4 as a LOOSE u64 (W^2 = W - 1, W^3 = -1, W^4 = -W mod p).
@@ -192,7 +194,7 @@ SVB_D void muladdw4(u64 a, u64 b, u64 cc, u32& r0, u32& r1, u32& r2, u32& r3) {
 //   u = T - (r4:r3)             borrow b
 //   k = cy - b in {-1, 0, 1}    number of 2^64 wraps; 2^64 = EPS, so the result is u + k*EPS, computed as
 //                               (u1:u0) - sign_extend(k) + (k << 32); it cannot wrap again.
-// 1 IMAD.WIDE + 7 ALU instructions.  (A 7-instruction variant that feeds the borrow of a sub.cc chain
+// 1 IMAD.WIDE + 6 ALU instructions (a*b mod p = 5 IMAD.WIDE + 9 ALU in total).  (A 7-instruction variant that feeds the borrow of a sub.cc chain
 // into madc.cc was tried: ptxas passes the inverted flag there, see tools/lab/NOTES.md.)
 // Exhaustive corner-limb model: tools/lab/reduce_model.py; on the device:
 // tests/test_gpu_parity.py::test_field_corner_cases.
@@ -210,9 +212,10 @@ SVB_D u64 red5(u32 r0, u32 r1, u32 r2, u32 r3, u32 r4) {
         "sub.cc.u32 %0, t0, k;\n\t subc.u32 h2, t1, kh;\n\t add.u32 %1, h2, k;\n\t"
         "}" : "=r"(lo), "=r"(hi) : "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(r4));
 #else
-    asm("{\n\t.reg .u32 t0, t1, cy, u0, u1, k, kh, h2;\n\t"
-        "mad.lo.cc.u32 t0, %4, %7, %2;\n\t madc.hi.cc.u32 t1, %4, %7, %3;\n\t addc.u32 cy, 0, 0;\n\t"
-        "sub.cc.u32 u0, t0, %5;\n\t subc.cc.u32 u1, t1, %6;\n\t subc.u32 k, cy, 0;\n\t"
+    // k = -1 + cy + (1 - b): two `..c k, ..` instructions that ptxas merges into one dual-carry-in IADD3.X
+    asm("{\n\t.reg .u32 t0, t1, u0, u1, k, kh, h2;\n\t"
+        "mad.lo.cc.u32 t0, %4, %7, %2;\n\t madc.hi.cc.u32 t1, %4, %7, %3;\n\t addc.u32 k, 0xFFFFFFFF, 0;\n\t"
+        "sub.cc.u32 u0, t0, %5;\n\t subc.cc.u32 u1, t1, %6;\n\t subc.u32 k, k, 0xFFFFFFFF;\n\t"
         "shr.s32 kh, k, 31;\n\t"
         "sub.cc.u32 %0, u0, k;\n\t subc.u32 h2, u1, kh;\n\t add.u32 %1, h2, k;\n\t"
         "}" : "=r"(lo), "=r"(hi) : "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(r4), "r"(d_EPS32));

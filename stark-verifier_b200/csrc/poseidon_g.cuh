@@ -284,7 +284,7 @@ SVB_D u64 sbox7_add(u64 x, u64 c) {
 // S-box lanes per loop iteration of the full-round S-box layer: 12 = fully unrolled (no register
 // rotation, largest code), 6 or 4 = looped with the state rotated between iterations.
 #ifndef SVB_SBOX_LANES
-#define SVB_SBOX_LANES 4
+#define SVB_SBOX_LANES 12
 #endif
 // Rotate the 12-word state left by SVB_SBOX_LANES words (register moves).
 SVB_D void rot_lanes(u64 s[12]) {

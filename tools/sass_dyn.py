@@ -9,7 +9,7 @@ lines = []
 on = False
 for l in sys.stdin:
     if "Function :" in l:
-        on = "poseidon_permute_kernel" in l
+        on = "poseidon_permute_kernelILi0E" in l
     if on:
         m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);", l)
         if m:

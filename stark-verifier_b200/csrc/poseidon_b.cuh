@@ -107,28 +107,55 @@ SVB_HD fr fr_add(const fr& a, const fr& b) {
 
 // Montgomery reduction interleaved with the product scanning of sum_t a[t] * b[t] (N terms):
 // returns sum * 2^-256 mod r.  Needs N * r^2 < r * 2^256, i.e. N <= 5.
+// SVB_B_ACCS > 1 splits a column over several independent 96-bit accumulators (more ILP); measured on
+// B200 (tools/lab, b_acc1/2/4: 60.3 / 55.4 / 53.3 M perms/s) the extra folding adds cost more than the
+// shorter dependency chains gain, so the default is one accumulator.
+#ifndef SVB_B_ACCS
+#define SVB_B_ACCS 1
+#endif
 template <int N>
 SVB_HD fr fr_dot_mont(const fr* a, const fr* b) {
+#if defined(__CUDA_ARCH__)
+    constexpr int A = (N == 1) ? (SVB_B_ACCS > 2 ? 2 : SVB_B_ACCS) : SVB_B_ACCS;
+#else
+    constexpr int A = 1;   // the host has out-of-order cores and no use for the extra accumulators
+#endif
     u32 m[8];
     fr out;
-    u32 c0 = 0, c1 = 0, c2 = 0;
+    u32 c0[A], c1[A], c2[A];
+#pragma unroll
+    for (int q = 0; q < A; q++) c0[q] = c1[q] = c2[q] = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
+        int n = 0;   // running MAC index inside the column (compile-time after unrolling)
 #pragma unroll
         for (int t = 0; t < N; t++)
 #pragma unroll
             for (int i = 0; i < 8; i++)
-                if (k - i >= 0 && k - i < 8) fr_mac(c0, c1, c2, a[t].l[i], b[t].l[k - i]);
+                if (k - i >= 0 && k - i < 8) { fr_mac(c0[n % A], c1[n % A], c2[n % A], a[t].l[i], b[t].l[k - i]); n++; }
 #pragma unroll
         for (int i = 0; i < 8; i++)
-            if (k - i >= 1 && k - i < 8 && i < k) fr_mac(c0, c1, c2, m[i], fr_mod(k - i));
-        if (k < 8) {
-            m[k] = c0 * FR_NINV32;
-            fr_mac(c0, c1, c2, m[k], fr_mod(0));   // makes c0 == 0
-        } else {
-            out.l[k - 8] = c0;
+            if (k - i >= 1 && k - i < 8 && i < k) { fr_mac(c0[n % A], c1[n % A], c2[n % A], m[i], fr_mod(k - i)); n++; }
+        // fold the partial accumulators into accumulator 0
+#pragma unroll
+        for (int q = 1; q < A; q++) {
+#if defined(__CUDA_ARCH__)
+            asm("add.cc.u32 %0, %0, %3;\n\t addc.cc.u32 %1, %1, %4;\n\t addc.u32 %2, %2, %5;"
+                : "+r"(c0[0]), "+r"(c1[0]), "+r"(c2[0]) : "r"(c0[q]), "r"(c1[q]), "r"(c2[q]));
+#else
+            u64 t0 = (u64)c0[0] + c0[q];
+            u64 t1 = (u64)c1[0] + c1[q] + (t0 >> 32);
+            c0[0] = (u32)t0; c1[0] = (u32)t1; c2[0] += c2[q] + (u32)(t1 >> 32);
+#endif
+            c0[q] = c1[q] = c2[q] = 0;
         }
-        c0 = c1; c1 = c2; c2 = 0;
+        if (k < 8) {
+            m[k] = c0[0] * FR_NINV32;
+            fr_mac(c0[0], c1[0], c2[0], m[k], fr_mod(0));   // makes c0 == 0
+        } else {
+            out.l[k - 8] = c0[0];
+        }
+        c0[0] = c1[0]; c1[0] = c2[0]; c2[0] = 0;
     }
     // k = 15 left its carry in c0 (< 2): the value is < 2r < 2^255, so it is 0
     fr_cond_sub(out);

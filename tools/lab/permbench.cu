@@ -5,16 +5,19 @@
 #include <cstdlib>
 #include <vector>
 using namespace svb;
+#ifndef LAB_KIND
+#define LAB_KIND 0   // 0 = Poseidon-Goldilocks, 1 = Poseidon-BN254 wrapped
+#endif
 
 // chain of `depth` dependent permutations per thread (Merkle-like: no memory traffic in the loop)
 __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) chain_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n, int depth) {
-    __shared__ u64 scratch[11 * SVB_BLOCK];
+    __shared__ u64 scratch[PermScratch<LAB_KIND>::words * SVB_BLOCK];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     u64 s[12];
     for (int k = 0; k < 12; k++) s[k] = in[12 * i + k];
     for (int d = 0; d < depth; d++) {
-        poseidon_g_dev(s, scratch + threadIdx.x, SVB_BLOCK);
+        permute_dev<LAB_KIND>(s, scratch, SVB_BLOCK);
         for (int k = 4; k < 12; k++) s[k] = canon(s[k]) ^ (u64)d;   // keep lanes live, cheap
         for (int k = 4; k < 12; k++) s[k] = s[k] >= GL_P ? s[k] - GL_P : s[k];
     }
@@ -58,7 +61,7 @@ static size_t field_corner_test() {
 }
 
 int main(int argc, char** argv) {
-    size_t n = 148 * 5 * 128 * 8;   // 8 full waves at 5 blocks/SM
+    size_t n = LAB_KIND ? 148 * 4 * 128 * 2 : 148 * 5 * 128 * 8;   // whole waves of blocks
     int depth = argc > 1 ? atoi(argv[1]) : 20;
     std::vector<u64> h(12 * n), ref(12 * n), got(12 * n);
     u64 x = 0x9E3779B97F4A7C15ull;
@@ -69,15 +72,15 @@ int main(int argc, char** argv) {
     cudaMalloc(&din, 12 * n * 8); cudaMalloc(&dout, 12 * n * 8);
     cudaMemcpy(din, h.data(), 12 * n * 8, cudaMemcpyHostToDevice);
     // correctness: single permutation kernel vs host on the first 4096 states
-    poseidon_permute_kernel<0><<<(unsigned)((n + SVB_BLOCK - 1) / SVB_BLOCK), SVB_BLOCK>>>(din, dout, n);
+    poseidon_permute_kernel<LAB_KIND><<<(unsigned)((n + SVB_BLOCK - 1) / SVB_BLOCK), SVB_BLOCK>>>(din, dout, n);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 2; }
     cudaMemcpy(got.data(), dout, 12 * n * 8, cudaMemcpyDeviceToHost);
     size_t bad = 0;
-    for (size_t i = 0; i < 4096; i++) {
+    for (size_t i = 0; i < (LAB_KIND ? 256 : 4096); i++) {
         u64 s[12];
         for (int k = 0; k < 12; k++) s[k] = h[12 * i + k];
-        poseidon_g_canonical(s);
+        if (LAB_KIND) poseidon_b_canonical(s); else poseidon_g_canonical(s);
         for (int k = 0; k < 12; k++) bad += s[k] != got[12 * i + k];
     }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);

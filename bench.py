@@ -88,6 +88,31 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and therefore its first-touch host allocations, including the pinned record
+    buffer) to the CPUs of the NUMA node the GPU hangs off; with 8 ranks copying at once the H2D leg is
+    otherwise limited by cross-socket traffic.  Best effort: returns a short description or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0].strip()
+        dom, bus, rest = out.split(":")
+        dev = f"{dom[-4:]}:{bus}:{rest}".lower()
+        base = f"/sys/bus/pci/devices/{dev}"
+        node = int(open(f"{base}/numa_node").read())
+        cpulist = open(f"{base}/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node} ({len(cpus)} cpus)"
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -175,10 +200,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    threads = os.cpu_count() or 1
+    threads = len(os.sched_getaffinity(0)) or 1
     if args.workload == "merkle":
         return bench_merkle(args, svb, torch, dist, rank, local_rank, world)
     params = workload_params(svb, args.workload)
@@ -295,7 +322,7 @@ def main():
         del stage
         e2e = {"value": world * n_host * e2e_steps / float(tt.item()), "unit": "proofs/s",
                "h2d_bytes_per_step": int(n_host * rw * 8), "d2h_bytes_per_step": int(hwords * 4), "steps": e2e_steps,
-               "proofs_per_step_per_gpu": n_host,
+               "proofs_per_step_per_gpu": n_host, "host_binding": numa,
                "h2d_only_gbs": n_host * rw * 8 / h2d_s / 1e9,
                "h2d_only_proofs_per_s": world * n_host / h2d_s,
                "note": "sv_fri_verify_batch(SV_MEM_HOST) from pinned host records, chunked H2D overlapped with kernels; "
@@ -350,6 +377,8 @@ def main():
         "synth_seconds": t_gen,
     }
     if not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)      # the CPU baseline gets every host core
+        threads = len(all_cpus)
         sample = args.cpu_sample
         if not sample:
             # probe on a small batch, then size the sample for ~12 s of CPU work on all host threads

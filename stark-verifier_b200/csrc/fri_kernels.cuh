@@ -61,6 +61,9 @@ SVB_D void ldg4(const u64* p, u64 out[4]) {
     out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
 }
 
+// Pull the 32-byte sector at p towards the SM while the current permutation runs (no register cost).
+SVB_D void prefetch32(const u64* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 SVB_D void report_fail(u32* accept_bitmap, u32* first_fail, u32 proof, u32 query, u32 order_key, u32 code) {
     atomicAnd(&accept_bitmap[proof >> 5], ~(1u << (proof & 31)));
     // order key: query-major, then the reference's check order inside the round, code in the low byte
@@ -121,6 +124,13 @@ SVB_D u32 merkle_chain(const u64* __restrict__ leaf, u32 leaf_len, const u64* __
             }
 #pragma unroll
             for (int i = 8; i < 12; i++) s[i] = 0;  // fresh hasher per level (:59)
+        }
+        // the next iteration's input (leaf chunk or sibling) is fetched while this permutation runs
+        if (it + 1 < n_sponge) {
+            prefetch32(leaf + (it + 1) * 8);
+            if ((it + 1) * 8 + 4 < leaf_len) prefetch32(leaf + (it + 1) * 8 + 4);
+        } else if (it + 1 < n_iter) {
+            prefetch32(sibs + 4 * (it + 1 - n_sponge));
         }
         permute_dev<KIND>(s, scratch, SVB_BLOCK);
     }

@@ -30,89 +30,22 @@ static constexpr u64 GL_P = 0xFFFFFFFF00000001ull;
 static constexpr u64 GL_EPS = 0xFFFFFFFFull;
 
 // ---- 64x64 -> 128 --------------------------------------------------------------------------
+// Portable forms (host: transcript, synthetic prover; the device kernels use the limb primitives below).
 SVB_HD void mul_wide(u64 a, u64 b, u64& lo, u64& hi) {
 #if defined(__CUDA_ARCH__)
-    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
-    u32 r0, r1, r2, r3;
-    asm("{\n\t"
-        ".reg .u32 m0, m1, m2;\n\t"
-        "mad.lo.cc.u32 %0, %4, %6, 0;\n\t"     // (r1:r0) = a0*b0
-        "madc.hi.cc.u32 %1, %4, %6, 0;\n\t"
-        "madc.lo.cc.u32 %2, %5, %7, 0;\n\t"    // (r3:r2) = a1*b1 (+ carry, always 0)
-        "madc.hi.u32 %3, %5, %7, 0;\n\t"
-        "mad.lo.cc.u32 m0, %4, %7, 0;\n\t"     // (m2:m1:m0) = a0*b1 + a1*b0
-        "madc.hi.u32 m1, %4, %7, 0;\n\t"
-        "mad.lo.cc.u32 m0, %5, %6, m0;\n\t"
-        "madc.hi.cc.u32 m1, %5, %6, m1;\n\t"
-        "addc.u32 m2, 0, 0;\n\t"
-        "add.cc.u32 %1, %1, m0;\n\t"
-        "addc.cc.u32 %2, %2, m1;\n\t"
-        "addc.u32 %3, %3, m2;\n\t"
-        "}"
-        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
-        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
-    lo = ((u64)r1 << 32) | r0;
-    hi = ((u64)r3 << 32) | r2;
+    lo = a * b;
+    hi = __umul64hi(a, b);
 #else
     unsigned __int128 p = (unsigned __int128)a * b;
     lo = (u64)p;
     hi = (u64)(p >> 64);
 #endif
 }
-
-// a*a: three 32x32 products instead of four.
-SVB_HD void sqr_wide(u64 a, u64& lo, u64& hi) {
-#if defined(__CUDA_ARCH__)
-    u32 a0 = (u32)a, a1 = (u32)(a >> 32);
-    u32 r0, r1, r2, r3;
-    asm("{\n\t"
-        ".reg .u32 m0, m1, m2;\n\t"
-        "mad.lo.cc.u32 %0, %4, %4, 0;\n\t"
-        "madc.hi.cc.u32 %1, %4, %4, 0;\n\t"
-        "madc.lo.cc.u32 %2, %5, %5, 0;\n\t"
-        "madc.hi.u32 %3, %5, %5, 0;\n\t"
-        "mad.lo.cc.u32 m0, %4, %5, 0;\n\t"
-        "madc.hi.u32 m1, %4, %5, 0;\n\t"
-        "add.cc.u32 m0, m0, m0;\n\t"
-        "addc.cc.u32 m1, m1, m1;\n\t"
-        "addc.u32 m2, 0, 0;\n\t"
-        "add.cc.u32 %1, %1, m0;\n\t"
-        "addc.cc.u32 %2, %2, m1;\n\t"
-        "addc.u32 %3, %3, m2;\n\t"
-        "}"
-        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
-        : "r"(a0), "r"(a1));
-    lo = ((u64)r1 << 32) | r0;
-    hi = ((u64)r3 << 32) | r2;
-#else
-    mul_wide(a, a, lo, hi);
-#endif
-}
+SVB_HD void sqr_wide(u64 a, u64& lo, u64& hi) { mul_wide(a, a, lo, hi); }
 
 // (hi:lo) mod p as a LOOSE u64.  lo + hi_lo*EPS - hi_hi with the two wrap corrections
 // (each can fire at most once: after a wrap the value is small).
 SVB_HD u64 reduce128(u64 lo, u64 hi) {
-#if defined(__CUDA_ARCH__)
-    u32 r0 = (u32)lo, r1 = (u32)(lo >> 32), r2 = (u32)hi, r3 = (u32)(hi >> 32);
-    u32 t0, t1;
-    asm("{\n\t"
-        ".reg .u32 bw, cy;\n\t"
-        "sub.cc.u32 %0, %2, %5;\n\t"   // (r1:r0) - r3
-        "subc.cc.u32 %1, %3, 0;\n\t"
-        "subc.u32 bw, 0, 0;\n\t"       // 0xFFFFFFFF on borrow
-        "sub.cc.u32 %0, %0, bw;\n\t"   // -= EPS on borrow
-        "subc.u32 %1, %1, 0;\n\t"
-        "mad.lo.cc.u32 %0, %4, 0xFFFFFFFF, %0;\n\t"   // += r2 * EPS
-        "madc.hi.cc.u32 %1, %4, 0xFFFFFFFF, %1;\n\t"
-        "addc.u32 cy, 0, 0;\n\t"
-        "sub.u32 cy, 0, cy;\n\t"       // 0xFFFFFFFF on carry
-        "add.cc.u32 %0, %0, cy;\n\t"   // += EPS on carry
-        "addc.u32 %1, %1, 0;\n\t"
-        "}"
-        : "=&r"(t0), "=&r"(t1)
-        : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
-    return ((u64)t1 << 32) | t0;
-#else
     u64 hh = hi >> 32, hl = hi & GL_EPS;
     u64 t0 = lo - hh;
     if (lo < hh) t0 -= GL_EPS;
@@ -120,42 +53,24 @@ SVB_HD u64 reduce128(u64 lo, u64 hi) {
     u64 t2 = t0 + t1;
     if (t2 < t1) t2 += GL_EPS;
     return t2;
-#endif
 }
 
 // lo + hi32 * 2^64 (hi32 < 2^32) mod p as a LOOSE u64.
 SVB_HD u64 reduce96(u64 lo, u32 hi32) {
-#if defined(__CUDA_ARCH__)
-    u32 r0 = (u32)lo, r1 = (u32)(lo >> 32);
-    u32 t0, t1;
-    asm("{\n\t"
-        ".reg .u32 cy;\n\t"
-        "mad.lo.cc.u32 %0, %4, 0xFFFFFFFF, %2;\n\t"
-        "madc.hi.cc.u32 %1, %4, 0xFFFFFFFF, %3;\n\t"
-        "addc.u32 cy, 0, 0;\n\t"
-        "sub.u32 cy, 0, cy;\n\t"
-        "add.cc.u32 %0, %0, cy;\n\t"
-        "addc.u32 %1, %1, 0;\n\t"
-        "}"
-        : "=&r"(t0), "=&r"(t1)
-        : "r"(r0), "r"(r1), "r"(hi32));
-    return ((u64)t1 << 32) | t0;
-#else
     u64 t1 = (u64)hi32 * GL_EPS;
     u64 t2 = lo + t1;
     if (t2 < t1) t2 += GL_EPS;
     return t2;
-#endif
 }
 
 #if defined(__CUDACC__)
 // ---- device limb primitives (sm_100a) -----------------------------------------------------------
-// Cost model measured on B200 (tools/microbench/pipes.cu): IMAD.WIDE.U32 (32x32+64 -> 64, optional
+// Cost model measured on B200 (tools/microbench/pipes2.cu, profiles/pipes2_b200_r1.txt): IMAD.WIDE.U32 (32x32+64 -> 64, optional
 // carry-out predicate, .X = carry-in) occupies the fmaheavy pipe for 4 cycles per warp, IMAD.HI 4,
 // other IMAD forms 2; IADD3 issues every cycle, IADD3.X / LOP3 / SHF / SEL every 2.  The sequences
 // below are written so that ptxas maps every mad.lo.cc/madc.hi pair onto ONE IMAD.WIDE.U32 and
 // merges carry captures into dual-carry IADD3.X (checked with cuobjdump -sass; a*b mod p is 5
-// IMAD.WIDE + 11 ALU instructions).
+// IMAD.WIDE + 9 ALU instructions).
 //
 // 0xFFFFFFFF lives in constant memory on purpose: as an immediate ptxas strength-reduces the
 // multiplication by EPS into IMAD.HI + IMAD.IADD (6 fmaheavy cycles instead of 4).

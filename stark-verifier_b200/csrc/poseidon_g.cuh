@@ -72,20 +72,12 @@ struct acc160 {
 SVB_HD void acc_mul(acc160& a, u64 x, u64 y) {
     u64 l, h;
     mul_wide(x, y, l, h);
-#if defined(__CUDA_ARCH__)
-    asm("add.cc.u64 %0, %0, %3;\n\t"
-        "addc.cc.u64 %1, %1, %4;\n\t"
-        "addc.u32 %2, %2, 0;"
-        : "+l"(a.lo), "+l"(a.hi), "+r"(a.top)
-        : "l"(l), "l"(h));
-#else
     unsigned __int128 s = ((unsigned __int128)a.hi << 64 | a.lo);
     unsigned __int128 p = ((unsigned __int128)h << 64 | l);
     unsigned __int128 t = s + p;
     a.top += (t < s);
     a.lo = (u64)t;
     a.hi = (u64)(t >> 64);
-#endif
 }
 // lo + hi*2^64 + top*2^128, with 2^128 = -2^32 (mod p); top < 2^31.  LOOSE result.
 SVB_HD u64 acc_reduce(const acc160& a) {
@@ -137,52 +129,6 @@ SVB_HD void poseidon_g(u64 s[12]) {
 //    arithmetic is written as mad.wide / carry chains that ptxas maps to IMAD.WIDE.U32[.X] with
 //    predicate carries, keeping the two pipes roughly balanced.
 // ================================================================================================
-SVB_D u64 mad_wide(u32 a, u32 b, u64 c) {
-    u64 r;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
-    return r;
-}
-
-// out_r = sum_j m_rj * s_j + rc_r, for all 12 rows; rc (canonical) is folded into the accumulators.
-SVB_D void mds_layer_rc(u64 s[12], const u64* __restrict__ rc) {
-    u32 l[12], h[12];
-#pragma unroll
-    for (int j = 0; j < 12; j++) {
-        l[j] = (u32)s[j];
-        h[j] = (u32)(s[j] >> 32);
-    }
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        u64 c = rc[r];
-        u32 al0 = (u32)c, al1 = 0, ah0 = (u32)(c >> 32), ah1 = 0;
-        // carry-chain form: ptxas keeps each pair as ONE accumulating IMAD.WIDE.U32 (a plain mad.wide
-        // gets re-associated into IMAD.WIDE + IADD3 + IADD3.X, one extra issue slot per product)
-#pragma unroll
-        for (int j = 0; j < 12; j++) {
-            asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(al0), "+r"(al1) : "r"(l[j]), "r"(mds_coeff(r, j)));
-            asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(ah0), "+r"(ah1) : "r"(h[j]), "r"(mds_coeff(r, j)));
-        }
-        u64 al = ((u64)al1 << 32) | al0, ah = ((u64)ah1 << 32) | ah0;
-        // al + ah*2^32, al, ah < 2^42
-        u32 t0 = (u32)al, t1, top, r0, r1;
-        (void)t1; (void)top;
-        asm("{\n\t"
-            ".reg .u32 cy;\n\t"
-            "add.cc.u32 %2, %4, %5;\n\t"
-            "addc.u32 %3, %6, 0;\n\t"
-            "mad.lo.cc.u32 %0, %3, 0xFFFFFFFF, %7;\n\t"
-            "madc.hi.cc.u32 %1, %3, 0xFFFFFFFF, %2;\n\t"
-            "addc.u32 cy, 0, 0;\n\t"
-            "sub.u32 cy, 0, cy;\n\t"
-            "add.cc.u32 %0, %0, cy;\n\t"
-            "addc.u32 %1, %1, 0;\n\t"
-            "}"
-            : "=&r"(r0), "=&r"(r1), "=&r"(t1), "=&r"(top)
-            : "r"((u32)(al >> 32)), "r"((u32)ah), "r"((u32)(ah >> 32)), "r"(t0));
-        s[r] = ((u64)r1 << 32) | r0;
-    }
-}
-
 // The MDS layer on the FP64 pipe.  Measured on B200 (tools/microbench/pipes.cu): IMAD.WIDE.U32 holds
 // the fmaheavy pipe 4 cycles per warp instruction and the S-boxes already saturate it; DFMA issues
 // every 2 cycles on the otherwise idle FP64 pipe.  Every product here is (coefficient <= 49) x (32-bit

@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the cpu_baseline sample (default: sized for ~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--device-transcript", action="store_true",
+                    help="derive the Fiat-Shamir challenges on the device too (sv_fri_verify_batch_fs): the records "
+                         "enter with their challenge fields zeroed")
     return ap.parse_args()
 
 
@@ -215,8 +218,16 @@ def main():
     distinct = args.distinct or {"A": 64, "B": 2, "outer": 4}[args.workload]
     # synthetic proofs: `distinct` base proofs per rank (own seed), tiled to n PHYSICALLY DISTINCT copies
     t0 = time.perf_counter()
-    base = svb.synth_proofs(params, distinct, seed=0xB2000002 ^ (rank << 20), n_circuits=1 if args.workload == "outer" else min(2, distinct),
-                            nthreads=max(1, threads // max(1, world)))
+    n_circ = 1 if (args.workload == "outer" or args.device_transcript) else min(2, distinct)
+    seed = 0xB2000002 ^ (rank << 20)
+    base = svb.synth_proofs(params, distinct, seed=seed, n_circuits=n_circ, nthreads=max(1, threads // max(1, world)))
+    cd = ph_dev = ph_host = None
+    if args.device_transcript:
+        cd, ph = svb.synth_public_inputs(params, distinct, seed=seed, n_circuits=1)
+        cd = cd[0]
+        for off, cnt in ((L.off_alpha, 2), (L.off_betas, 2 * len(params.reduction_arity_bits)), (L.off_pow_response, 1),
+                         (L.off_indices, params.config.num_query_rounds), (L.off_zeta, 2), (L.off_zeta_next, 2)):
+            base[:, off:off + cnt] = 0
     t_gen = time.perf_counter() - t0
     rw = L.record_words
     ctx = svb.Context(local_rank)
@@ -251,10 +262,18 @@ def main():
     words = n // 32
     d_bm = torch.zeros(words, dtype=torch.int32, device="cuda")
     d_all = torch.zeros(words * world, dtype=torch.int32, device="cuda")
+    if args.device_transcript:
+        reps = (n + distinct - 1) // distinct
+        ph_host = np.ascontiguousarray(np.tile(ph, (reps, 1))[:n])
+        ph_dev = torch.from_numpy(ph_host.view(np.int64)).cuda()
     torch.cuda.synchronize()
 
     def step():
-        ctx.fri_verify_batch(params, d_recs.data_ptr(), n_proofs=n, accept_bitmap=d_bm.data_ptr(), mem=svb.MEM_DEVICE)
+        if args.device_transcript:
+            ctx.fri_verify_batch_fs(params, d_recs.data_ptr(), cd, ph_dev.data_ptr(), n_proofs=n, accept_bitmap=d_bm.data_ptr(),
+                                    mem=svb.MEM_DEVICE)
+        else:
+            ctx.fri_verify_batch(params, d_recs.data_ptr(), n_proofs=n, accept_bitmap=d_bm.data_ptr(), mem=svb.MEM_DEVICE)
         if world > 1:
             dist.all_gather_into_tensor(d_all, d_bm)
 
@@ -299,13 +318,18 @@ def main():
         hwords = n_host // 32
         hb = np.zeros(hwords, dtype=np.uint32)
         e2e_steps = max(2, min(args.steps, 10))
+        def host_call():
+            if args.device_transcript:
+                ctx.fri_verify_batch_fs(params, host.data_ptr(), cd, ph_host[:n_host], n_proofs=n_host, accept_bitmap=hb, mem=svb.MEM_HOST)
+            else:
+                ctx.fri_verify_batch(params, host.data_ptr(), n_proofs=n_host, accept_bitmap=hb, mem=svb.MEM_HOST)
         for _ in range(2):
-            ctx.fri_verify_batch(params, host.data_ptr(), n_proofs=n_host, accept_bitmap=hb, mem=svb.MEM_HOST)
+            host_call()
         assert (hb == exp[:hwords]).all()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            ctx.fri_verify_batch(params, host.data_ptr(), n_proofs=n_host, accept_bitmap=hb, mem=svb.MEM_HOST)
+            host_call()
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
@@ -357,7 +381,8 @@ def main():
                    "pow_bits": params.config.proof_of_work_bits, "proofs_per_gpu": n, "distinct_base_proofs": distinct,
                    "record_bytes": rw * 8, "l2_policy": f"inputs larger than L2 ({n * rw * 8 / 1e6:.0f} MB/GPU resident, physically distinct copies)",
                    "sharding": f"proofs sharded over {world} ranks; NCCL all-gather of the accept bitmap only",
-                   "corrupted": "1/64 proofs (sibling limb), bitmap checked against the expected pattern"},
+                   "corrupted": "1/64 proofs (sibling limb), bitmap checked against the expected pattern",
+                   "transcript": "device (sv_fri_verify_batch_fs)" if args.device_transcript else "host (challenges arrive in the records)"},
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,

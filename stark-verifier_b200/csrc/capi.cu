@@ -32,6 +32,9 @@ struct sv_ctx {
     u32* d_bitmap = nullptr; size_t bitmap_words = 0;
     u32* d_fail = nullptr; size_t fail_words = 0;
     u64* d_pi = nullptr; size_t pi_words = 0;                          // public-input hashes (device-side transcript)
+    u64* d_hdr = nullptr; size_t hdr_words = 0;                        // record headers of a whole host batch (transcript)
+    cudaStream_t fs_stream = nullptr;                                  // the batch-wide transcript of the host pipeline
+    cudaEvent_t ev_hdr = nullptr, ev_fs = nullptr;
     cudaEvent_t ev_copied[SV_NBUF] = {}, ev_done[SV_NBUF] = {}, ev_join[SV_NKS] = {};
     uint64_t launches = 0;
     // optional CUDA-event timing of the dominant kernel (fri_query_kernel / merkle / permute), on
@@ -93,6 +96,9 @@ extern "C" int sv_ctx_create(int device, sv_ctx** out) {
     CK(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     for (int i = 0; i < SV_NKS - 1; i++) CK(nullptr, cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));
     CK(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(nullptr, cudaStreamCreateWithFlags(&c->fs_stream, cudaStreamNonBlocking));
+    CK(nullptr, cudaEventCreateWithFlags(&c->ev_hdr, cudaEventDisableTiming));
+    CK(nullptr, cudaEventCreateWithFlags(&c->ev_fs, cudaEventDisableTiming));
     for (int i = 0; i < SV_NBUF; i++) {
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
@@ -112,6 +118,9 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaFree(c->d_bitmap);
     cudaFree(c->d_fail);
     cudaFree(c->d_pi);
+    cudaFree(c->d_hdr);
+    cudaStreamDestroy(c->fs_stream);
+    cudaEventDestroy(c->ev_hdr); cudaEventDestroy(c->ev_fs);
     for (int i = 0; i < SV_NBUF; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_done[i]); }
     for (int i = 0; i < SV_NKS; i++) cudaEventDestroy(c->ev_join[i]);
     for (auto& pr : c->tev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -134,6 +143,7 @@ extern "C" int sv_ctx_synchronize(sv_ctx* c) {
     CK(c, cudaStreamSynchronize(c->own_stream));
     for (int i = 0; i < SV_NKS - 1; i++) CK(c, cudaStreamSynchronize(c->aux_stream[i]));
     CK(c, cudaStreamSynchronize(c->copy_stream));
+    CK(c, cudaStreamSynchronize(c->fs_stream));
     return 0;
 }
 extern "C" uint64_t sv_ctx_launch_count(const sv_ctx* c) { return c ? c->launches : 0; }
@@ -385,16 +395,35 @@ static int fri_verify_impl(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs
     cudaStream_t ks[SV_NKS] = {c->own_stream};
     for (int i = 1; i < SV_NKS; i++) ks[i] = c->aux_stream[i - 1];
     size_t n_chunks = (n_proofs + chunk - 1) / chunk;
+    // Device-side transcript of a host batch: the ~85 dependent permutations per proof are latency-bound
+    // (one warp per 32 proofs), so the transcript runs ONCE for the whole batch, on the headers alone
+    // (they travel first: 7 % of the bytes), beside the H2D of the full records; every chunk then gets
+    // its challenge fields patched in with one strided device-to-device copy.
+    const size_t hw = P.L.header_words, chal_off = P.L.off_alpha, chal_words = hw - chal_off;
+    if (fs) {
+        if (grow(c, c->d_hdr, c->hdr_words, n_proofs * hw)) return -6;
+        CK(c, cudaMemcpy2DAsync(c->d_hdr, hw * 8, records, rw * 8, hw * 8, n_proofs, cudaMemcpyHostToDevice, cs));
+        CK(c, cudaMemcpyAsync(c->d_pi, pi_hashes, n_proofs * 32, cudaMemcpyHostToDevice, cs));
+        CK(c, cudaEventRecord(c->ev_hdr, cs));
+        CK(c, cudaStreamWaitEvent(c->fs_stream, c->ev_hdr, 0));
+        FriKernelParams Ph = P;
+        Ph.L.record_words = (u32)hw;          // the headers are packed back to back
+        if ((rc = enqueue_challenges(c, Ph, *fs, n_proofs, c->d_hdr, c->d_pi, c->fs_stream))) return rc;
+        CK(c, cudaEventRecord(c->ev_fs, c->fs_stream));
+    }
     for (size_t i = 0; i < n_chunks; i++) {
         int b = (int)(i % SV_NBUF);
         cudaStream_t k = ks[i % n_ks];
         size_t first = i * chunk, cnt = std::min(chunk, n_proofs - first);
         if (i >= SV_NBUF) CK(c, cudaStreamWaitEvent(cs, c->ev_done[b], 0));   // buffer b free again
         CK(c, cudaMemcpyAsync(c->d_stage[b], records + first * rw, cnt * rw * 8, cudaMemcpyHostToDevice, cs));
-        if (fs) CK(c, cudaMemcpyAsync(c->d_pi + 4 * first, pi_hashes + 4 * first, cnt * 32, cudaMemcpyHostToDevice, cs));
         CK(c, cudaEventRecord(c->ev_copied[b], cs));
         CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
-        if (fs && (rc = enqueue_challenges(c, P, *fs, cnt, c->d_stage[b], c->d_pi + 4 * first, k))) return rc;
+        if (fs) {
+            CK(c, cudaStreamWaitEvent(k, c->ev_fs, 0));
+            CK(c, cudaMemcpy2DAsync(c->d_stage[b] + chal_off, rw * 8, c->d_hdr + first * hw + chal_off, hw * 8, chal_words * 8, cnt,
+                                    cudaMemcpyDeviceToDevice, k));
+        }
         rc = enqueue_fri(c, P, cnt, c->d_stage[b], c->d_scratch + 4 * first, c->d_bitmap + first / 32,
                          first_fail ? c->d_fail + first : nullptr, k);
         if (rc) return rc;

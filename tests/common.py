@@ -58,3 +58,14 @@ def corrupt(recs, L, rng, every=8, num_steps=None):
             recs[i, L.off_open0 + int(rng.integers(0, 2 * L.n0))] ^= delta
         out[i] = c
     return out
+
+
+# The fourth vector of upstream plonky2's `test_vectors12` (plonky2/src/hash/poseidon_goldilocks.rs, width-12
+# known-answer test; the other three are the all-zero, iota and all-(p-1) states of tests/golden/poseidon_g.json).
+# It is published by plonky2 itself, i.e. not derived from any code of this repository.
+PLONKY2_TV12_IN = [0x8ccbbbea4fe5d2b7, 0xc2af59ee9ec49970, 0x90f7e1a9e658446a, 0xdcc0630a3ab8b1b8,
+                   0x7ff8256bca20588c, 0x5d99a7ca0c44ecfb, 0x48452b17a70fbee3, 0xeb09d654690b6c88,
+                   0x4a55d3a39c676a88, 0xc0407a38d2285139, 0xa234bac9356386d1, 0xe1633f2bad98a52f]
+PLONKY2_TV12_OUT = [0xa89280105650c4ec, 0xab542d53860d12ed, 0x5704148e9ccab94f, 0xd3a826d4b62da9f5,
+                    0x8a7a6ca87892574f, 0xc7017e1cad1a674e, 0x1f06668922318e34, 0xa3b203bc8102676f,
+                    0xfcc781b0ce382bf2, 0x934c69ff3ed14ba5, 0x504688a5996e8f13, 0x401f3f2ed524a2ba]

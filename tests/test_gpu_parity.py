@@ -4,7 +4,7 @@ import os
 import numpy as np
 import pytest
 
-from common import P, bit, corrupt, tiny_params
+from common import P, PLONKY2_TV12_IN, PLONKY2_TV12_OUT, bit, corrupt, tiny_params
 
 pytestmark = pytest.mark.gpu
 
@@ -20,6 +20,8 @@ def test_permute_kat_and_random(svb, orc, ctx):
     assert int(got.reshape(-1, 12)[0, 0]) == 0x3c18a9786cb0b359
     assert int(got.reshape(-1, 12)[1, 0]) == 0xd64e1e3efc5b8e9e
     assert int(got.reshape(-1, 12)[2, 0]) == 0xbe0085cfc57a8357
+    tv = ctx.poseidon_permute_batch(np.array(PLONKY2_TV12_IN, dtype=np.uint64))
+    assert [int(x) for x in tv] == PLONKY2_TV12_OUT      # upstream plonky2 test_vectors12, random state
 
 
 def test_field_corner_cases(svb, ctx):

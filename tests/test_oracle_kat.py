@@ -139,3 +139,10 @@ def test_oracle_poseidon_b_golden(orc):
         assert [int(x) for x in got] == [int(x, 16) for x in c["out"]]
     w = orc.poseidon_b(list(range(12)))
     assert int(w[0]) == 0xd983775ce161c4e4 and int(w[11]) == 0x6bf843b27c9d3fbb
+
+
+def test_oracle_matches_upstream_plonky2_random_vector(orc):
+    """The random-state vector of plonky2's own `test_vectors12` (fast and naive forms)."""
+    from common import PLONKY2_TV12_IN, PLONKY2_TV12_OUT
+    assert [int(x) for x in orc.poseidon(PLONKY2_TV12_IN)] == PLONKY2_TV12_OUT
+    assert [int(x) for x in orc.poseidon(PLONKY2_TV12_IN, naive=True)] == PLONKY2_TV12_OUT

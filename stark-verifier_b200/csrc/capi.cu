@@ -328,6 +328,14 @@ static int make_params(sv_ctx* c, const sv_fri_shape& s, FriKernelParams& P) {
 static int enqueue_challenges(sv_ctx* c, FriKernelParams& P, const FsParams& F, size_t n, u64* d_records, const u64* d_pi,
                               cudaStream_t s) {
     P.n_proofs = (u32)n;
+    static const bool coop = [] { const char* e = getenv("SVB_FS_COOP"); return !e || atoi(e) != 0; }();
+    if (P.hash_kind == SV_HASH_POSEIDON_GOLDILOCKS && coop) {
+        // lane-cooperative transcript: 16 lanes per proof (latency ~5x lower than one thread per proof)
+        fri_challenges_coop_kernel<<<(unsigned)((n * SVB_COOP_GROUP + 127) / 128), 128, 0, s>>>(d_records, P, F, d_pi);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        return 0;
+    }
     SVB_LAUNCH_KIND(P.hash_kind, fri_challenges_kernel, (unsigned)((n + SVB_FS_BLOCK - 1) / SVB_FS_BLOCK), SVB_FS_BLOCK, s, d_records, P,
                     F, d_pi);
     c->launches++;

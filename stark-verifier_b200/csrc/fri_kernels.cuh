@@ -23,6 +23,7 @@
 #include "layout.hpp"
 #include "poseidon_g.cuh"
 #include "poseidon_b.cuh"
+#include "poseidon_g_coop.cuh"
 
 namespace svb {
 
@@ -422,6 +423,77 @@ __global__ void __launch_bounds__(SVB_FS_BLOCK) fri_challenges_kernel(u64* __res
     ch.observe(rec[L.off_pow_witness]);
     rec[L.off_pow_response] = ch.squeeze();
     for (u32 q = 0; q < P.num_queries; q++) rec[L.off_indices + q] = ch.squeeze();
+}
+
+// The same transcript with the lane-cooperative permutation (poseidon_g_coop.cuh): one 16-lane group per
+// proof, lane l holds sponge word l.  Absorbing is a coalesced load of up to 8 consecutive words by lanes
+// 0..7; a squeeze broadcasts the word of lane (n_out - 1).  Poseidon-Goldilocks only.
+struct CoopChallenger {
+    u64 s;          // this lane's state word
+    int l, n_out;
+    const CoopTables* T;
+    SVB_D void permute() {
+        s = canon(poseidon_g_coop(s, l, *T));
+        n_out = 8;
+    }
+    // observe the concatenation of two segments (n1 may be 0), in rate-8 chunks, overwrite mode
+    SVB_D void absorb(const u64* __restrict__ p0, u32 n0, const u64* __restrict__ p1, u32 n1) {
+        const u32 total = n0 + n1;
+        for (u32 off = 0; off < total; off += 8) {
+            u32 idx = off + (u32)l;
+            if (l < 8 && idx < total) s = idx < n0 ? p0[idx] : p1[idx - n0];
+            permute();
+        }
+    }
+    SVB_D u64 squeeze() {
+        if (n_out == 0) permute();
+        n_out--;
+        return coop_shfl(s, n_out);
+    }
+};
+
+__global__ void __launch_bounds__(128) fri_challenges_coop_kernel(u64* __restrict__ records, FriKernelParams P, FsParams F,
+                                                                  const u64* __restrict__ pi_hashes) {
+    __shared__ CoopTables T;
+    coop_load_tables(T);
+    const int l = threadIdx.x & (SVB_COOP_GROUP - 1);
+    u32 p = (blockIdx.x * blockDim.x + threadIdx.x) / SVB_COOP_GROUP;
+    const bool valid = p < P.n_proofs;
+    if (!valid) p = P.n_proofs - 1;            // keep the warp convergent for the shuffles; writes are suppressed
+    const bool writer = valid && l == 0;
+    const sv_fri_layout& L = P.L;
+    u64* rec = records + (size_t)p * L.record_words;
+    const u32 cap_words = L.ncap * 4;
+    CoopChallenger ch;
+    ch.l = l; ch.n_out = 0; ch.T = &T;
+    // first chunk: circuit digest (4) + public-input hash (4)   (plonk_verifier_chip.rs:65-71)
+    ch.s = l < 4 ? F.circuit_digest[l & 3] : (l < 8 ? pi_hashes[4 * (size_t)p + (l - 4)] : 0);
+    ch.permute();
+    ch.absorb(rec + L.off_init_caps + 1 * cap_words, cap_words, nullptr, 0);           // wires_cap
+    for (u32 i = 0; i < 2 * F.num_challenges; i++) (void)ch.squeeze();                  // plonk betas, gammas
+    ch.absorb(rec + L.off_init_caps + 2 * cap_words, cap_words, nullptr, 0);           // zs_partial_products_cap
+    for (u32 i = 0; i < F.num_challenges; i++) (void)ch.squeeze();                      // plonk alphas
+    ch.absorb(rec + L.off_init_caps + 3 * cap_words, cap_words, nullptr, 0);           // quotient_polys_cap
+    u64 z0 = ch.squeeze(), z1 = ch.squeeze();                                           // plonk_zeta
+    if (writer) {
+        rec[L.off_zeta] = z0; rec[L.off_zeta + 1] = z1;
+        rec[L.off_zeta_next] = mulc(z0, F.g); rec[L.off_zeta_next + 1] = mulc(z1, F.g);
+    }
+    ch.absorb(rec + L.off_open0, 2 * L.n0, rec + L.off_open1, 2 * L.n1);                // openings, batch order
+    u64 a0 = ch.squeeze(), a1 = ch.squeeze();                                           // fri_alpha
+    if (writer) { rec[L.off_alpha] = a0; rec[L.off_alpha + 1] = a1; }
+    for (u32 st = 0; st < P.num_steps; st++) {
+        ch.absorb(rec + L.off_step_caps + (size_t)st * cap_words, cap_words, nullptr, 0);
+        u64 b0 = ch.squeeze(), b1 = ch.squeeze();
+        if (writer) { rec[L.off_betas + 2 * st] = b0; rec[L.off_betas + 2 * st + 1] = b1; }
+    }
+    ch.absorb(rec + L.off_final_poly, 2 * P.final_poly_len, rec + L.off_pow_witness, 1);
+    u64 pw = ch.squeeze();
+    if (writer) rec[L.off_pow_response] = pw;
+    for (u32 q = 0; q < P.num_queries; q++) {
+        u64 v = ch.squeeze();
+        if (writer) rec[L.off_indices + q] = v;
+    }
 }
 
 // first_fail post-pass: 0xFFFFFFFF (never failed) -> 0, else (query << 8) | code.

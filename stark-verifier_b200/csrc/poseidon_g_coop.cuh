@@ -1,0 +1,120 @@
+// Lane-cooperative Poseidon-Goldilocks: one permutation spread over a 16-lane group (lanes 0..11 hold
+// the 12 state words, lanes 12..15 idle), two groups per warp.  Same function as poseidon_g_dev
+// (chip/plonk/gates/poseidon.rs:634-686, fast form); a different mapping.
+//
+// Why it exists.  The thread-per-permutation kernel maximises THROUGHPUT (all 32 lanes busy, no
+// shuffles), but one permutation takes ~44 us on a lone warp.  The Fiat-Shamir transcript is ~85
+// DEPENDENT permutations per proof, so at a few thousand proofs per call it is latency-bound; here the
+// S-boxes of a full round, the 11 multiply-adds of a partial round and the MDS rows run in parallel
+// across lanes (warp shuffles gather the circulant MDS inputs and tree-reduce the partial-round dot
+// product), which cuts the latency of one permutation ~5x.  The price is throughput: the 22 partial
+// rounds keep 11 of 12 lanes idle during the lane-0 S-box -- measured in tools/lab (coop vs thread).
+#pragma once
+#include "poseidon_g.cuh"
+
+namespace svb {
+
+#if defined(__CUDACC__)
+#define SVB_COOP_GROUP 16
+
+// constants staged in shared memory (per-lane addresses differ, which constant memory serialises)
+struct CoopTables {
+    u64 rc_full[96];     // ALL_ROUND_CONSTANTS of rounds 0..3 and 26..29
+    u64 first[12];       // FAST_PARTIAL_FIRST_ROUND_CONSTANT
+    u64 prc[22];         // FAST_PARTIAL_ROUND_CONSTANTS
+    u64 init[121];       // FAST_PARTIAL_ROUND_INITIAL_MATRIX
+    u64 w[242], v[242];  // FAST_PARTIAL_ROUND_W_HATS / _VS
+};
+SVB_D void coop_load_tables(CoopTables& T) {
+    for (int i = threadIdx.x; i < 96; i += blockDim.x) T.rc_full[i] = d_ALL_ROUND_CONSTANTS[i < 48 ? i : 12 * 26 + (i - 48)];
+    for (int i = threadIdx.x; i < 12; i += blockDim.x) T.first[i] = d_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i];
+    for (int i = threadIdx.x; i < 22; i += blockDim.x) T.prc[i] = d_FAST_PARTIAL_ROUND_CONSTANTS[i];
+    for (int i = threadIdx.x; i < 121; i += blockDim.x) T.init[i] = d_FAST_PARTIAL_ROUND_INITIAL_MATRIX[i];
+    for (int i = threadIdx.x; i < 242; i += blockDim.x) { T.w[i] = d_FAST_PARTIAL_ROUND_W_HATS[i]; T.v[i] = d_FAST_PARTIAL_ROUND_VS[i]; }
+    __syncthreads();
+}
+
+SVB_D constexpr u32 coop_circ(int k) {
+    constexpr u32 circ[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};   // MDS_MATRIX_CIRC (poseidon.rs:321)
+    return circ[k];
+}
+SVB_D u64 coop_shfl(u64 v, int src) {
+    u32 lo = __shfl_sync(0xFFFFFFFFu, (u32)v, src, SVB_COOP_GROUP);
+    u32 hi = __shfl_sync(0xFFFFFFFFu, (u32)(v >> 32), src, SVB_COOP_GROUP);
+    return ((u64)hi << 32) | lo;
+}
+
+// full round `slot` (0..7 = rounds 0..3, 26..29): constant layer, S-box on every lane, circulant MDS
+SVB_D u64 coop_full_round(u64 s, int l, int slot, const CoopTables& T) {
+    const bool act = l < 12;
+    s = sbox7(add_lc(s, act ? T.rc_full[12 * slot + l] : 0));
+    u64 al = 0, ah = 0;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        int src = l + k;
+        src = src >= 12 ? src - 12 : src;
+        u64 v = coop_shfl(s, act ? src : l);
+        al += (u64)coop_circ(k) * (u32)v;                 // row l: sum_k CIRC[k] * s[(l + k) % 12]  (:450-479)
+        ah += (u64)coop_circ(k) * (u32)(v >> 32);
+    }
+    if (l == 0) { al += 8ull * (u32)s; ah += 8ull * (u32)(s >> 32); }            // MDS_MATRIX_DIAG[0]
+    u64 t = al + (ah << 32);
+    u32 top = (u32)(ah >> 32) + (t < al ? 1u : 0u);
+    return act ? reduce96(t, top) : 0;
+}
+
+// One permutation; `s` is this lane's state word (LOOSE in, LOOSE out; lanes 12..15 carry 0).
+SVB_D u64 poseidon_g_coop(u64 s, int l, const CoopTables& T) {
+    const bool act = l < 12;
+#pragma unroll 1
+    for (int slot = 0; slot < 4; slot++) s = coop_full_round(s, l, slot, T);
+    // partial section: first-round constants, then the dense initial matrix on lanes 1..11 (:504-537)
+    s = add_lc(s, act ? T.first[l] : 0);
+    {
+        dot_acc a;
+        dot_init(a);
+#pragma unroll 1
+        for (int r = 1; r < 12; r++) {
+            u64 v = coop_shfl(s, r);
+            u64 m = (l >= 1 && act) ? T.init[(r - 1) * 11 + (l - 1)] : 0;
+            dot_mac(a, v, m);
+        }
+        u64 t = dot_reduce(a);
+        s = l == 0 ? s : (act ? t : 0);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 22; r++) {
+        u64 x = s;
+        if (l == 0) x = sbox7_add(s, T.prc[r]);                    // the lane-0 S-box (+ round constant)
+        const u64 s0 = coop_shfl(x, 0);
+        u32 p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0;
+        u64 snew = 0;
+        if (l == 0) {                                              // 25 * s0 = (MDS_CIRC[0] + MDS_DIAG[0]) * s0
+            u64 lo = 25ull * (u32)s0, hi = 25ull * (u32)(s0 >> 32);
+            u64 mid = (lo >> 32) + (u32)hi;
+            p0 = (u32)lo; p1 = (u32)mid; p2 = (u32)(hi >> 32) + (u32)(mid >> 32);
+        } else if (act) {
+            mulw4(s, T.w[r * 11 + l - 1], p0, p1, p2, p3);         // w_hat_i * s_i, unreduced
+            snew = mul_add(T.v[r * 11 + l - 1], s0, s);            // s_i + v_i * s0
+        }
+        // tree-sum the 12 products over the group (5 limbs with carries)
+#pragma unroll
+        for (int off = 8; off >= 1; off >>= 1) {
+            u32 q0 = __shfl_xor_sync(0xFFFFFFFFu, p0, off, SVB_COOP_GROUP);
+            u32 q1 = __shfl_xor_sync(0xFFFFFFFFu, p1, off, SVB_COOP_GROUP);
+            u32 q2 = __shfl_xor_sync(0xFFFFFFFFu, p2, off, SVB_COOP_GROUP);
+            u32 q3 = __shfl_xor_sync(0xFFFFFFFFu, p3, off, SVB_COOP_GROUP);
+            u32 q4 = __shfl_xor_sync(0xFFFFFFFFu, p4, off, SVB_COOP_GROUP);
+            asm("add.cc.u32 %0, %0, %5;\n\t addc.cc.u32 %1, %1, %6;\n\t addc.cc.u32 %2, %2, %7;\n\t addc.cc.u32 %3, %3, %8;\n\t"
+                "addc.u32 %4, %4, %9;"
+                : "+r"(p0), "+r"(p1), "+r"(p2), "+r"(p3), "+r"(p4) : "r"(q0), "r"(q1), "r"(q2), "r"(q3), "r"(q4));
+        }
+        s = l == 0 ? red5(p0, p1, p2, p3, p4) : snew;
+    }
+#pragma unroll 1
+    for (int slot = 4; slot < 8; slot++) s = coop_full_round(s, l, slot, T);
+    return s;
+}
+#endif
+
+}  // namespace svb

@@ -24,6 +24,27 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) chain_kernel(const u
     for (int k = 0; k < 12; k++) out[12 * i + k] = canon(s[k]);
 }
 
+// lane-cooperative permutation: one 16-lane group per state, `depth` dependent permutations
+__global__ void __launch_bounds__(128) coop_chain_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n_states, int depth) {
+    __shared__ CoopTables T;
+    coop_load_tables(T);
+    const int l = threadIdx.x & 15;
+    size_t g = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 4;
+    if (g >= n_states) g = n_states - 1;
+    u64 s = l < 12 ? in[12 * g + l] : 0;
+    for (int d = 0; d < depth; d++) s = canon(poseidon_g_coop(s, l, T));
+    if (l < 12) out[12 * g + l] = s;
+}
+// one thread per state, launched with ONE warp per SM: the latency of a lone warp
+__global__ void __launch_bounds__(32) lone_chain_kernel(const u64* __restrict__ in, u64* __restrict__ out, int depth) {
+    __shared__ u64 scratch[11 * 32];
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    u64 s[12];
+    for (int k = 0; k < 12; k++) s[k] = in[12 * i + k];
+    for (int d = 0; d < depth; d++) poseidon_g_dev(s, scratch + threadIdx.x, 32);
+    for (int k = 0; k < 12; k++) out[12 * i + k] = canon(s[k]);
+}
+
 __global__ void field_kernel(const u64* a, const u64* b, const u64* c, u64* out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -92,6 +113,31 @@ int main(int argc, char** argv) {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (rep && ms < best) best = ms;
     }
+#if LAB_KIND == 0
+    {   // lane-cooperative vs thread-per-permutation: correctness, lone-warp latency, full-grid throughput
+        const int cd = 8;
+        size_t ns = 148 * 8 * 16;                      // 16 blocks of 128 threads per SM, 8 states per block
+        coop_chain_kernel<<<(unsigned)(ns * 16 / 128), 128>>>(din, dout, ns, 1);
+        cudaDeviceSynchronize();
+        std::vector<u64> cg(12 * 64);
+        cudaMemcpy(cg.data(), dout, cg.size() * 8, cudaMemcpyDeviceToHost);
+        size_t cbad = 0;
+        for (size_t i = 0; i < 64; i++) {
+            u64 s[12];
+            for (int k = 0; k < 12; k++) s[k] = h[12 * i + k];
+            poseidon_g_canonical(s);
+            for (int k = 0; k < 12; k++) cbad += s[k] != cg[12 * i + k];
+        }
+        float ms;
+        auto timeit = [&](auto launch) { float b = 1e30f; for (int r = 0; r < 3; r++) { cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1); if (r && ms < b) b = ms; } return b; };
+        float t_coop_full = timeit([&] { coop_chain_kernel<<<(unsigned)(ns * 16 / 128), 128>>>(din, dout, ns, cd); });
+        float t_coop_lone = timeit([&] { coop_chain_kernel<<<148, 32>>>(din, dout, 148 * 2, cd); });
+        float t_thr_lone = timeit([&] { lone_chain_kernel<<<148, 32>>>(din, dout, cd); });
+        printf("  coop: mismatches %zu; full grid %.1f Mperm/s; lone-warp latency coop %.1f us/perm, thread-per-perm %.1f us/perm\n", cbad,
+               ns * (double)cd / t_coop_full / 1e3, t_coop_lone * 1e3 / cd, t_thr_lone * 1e3 / cd);
+        bad += cbad;
+    }
+#endif
     size_t fbad = field_corner_test();
     if (fbad) printf("  FIELD CORNER MISMATCHES: %zu\n", fbad);
     bad += fbad;

@@ -79,28 +79,45 @@ SVB_HD void fr_acc_add(u32& c0, u32& c1, u32& c2, u32 a) {
 
 // r = r - mod if r >= mod (r < 2 mod)
 SVB_HD void fr_cond_sub(fr& r) {
+#if defined(__CUDA_ARCH__)
+    // one borrow chain, the final borrow as an all-ones mask, one LOP3 select per limb
+    u32 d0, d1, d2, d3, d4, d5, d6, d7, keep;
+    asm("sub.cc.u32 %0, %9, 0xf0000001;\n\t subc.cc.u32 %1, %10, 0x43e1f593;\n\t subc.cc.u32 %2, %11, 0x79b97091;\n\t"
+        "subc.cc.u32 %3, %12, 0x2833e848;\n\t subc.cc.u32 %4, %13, 0x8181585d;\n\t subc.cc.u32 %5, %14, 0xb85045b6;\n\t"
+        "subc.cc.u32 %6, %15, 0xe131a029;\n\t subc.cc.u32 %7, %16, 0x30644e72;\n\t subc.u32 %8, 0, 0;"
+        : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3), "=r"(d4), "=r"(d5), "=r"(d6), "=r"(d7), "=r"(keep)
+        : "r"(r.l[0]), "r"(r.l[1]), "r"(r.l[2]), "r"(r.l[3]), "r"(r.l[4]), "r"(r.l[5]), "r"(r.l[6]), "r"(r.l[7]));
+    const u32 d[8] = {d0, d1, d2, d3, d4, d5, d6, d7};
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = (r.l[i] & keep) | (d[i] & ~keep);   // keep = 0xFFFFFFFF iff r < mod
+#else
     u32 d[8];
     u32 borrow = 0;
-#pragma unroll
     for (int i = 0; i < 8; i++) {
         u64 t = (u64)r.l[i] - fr_mod(i) - borrow;
         d[i] = (u32)t;
         borrow = (u32)(t >> 32) & 1u;
     }
-    if (!borrow) {
-#pragma unroll
+    if (!borrow)
         for (int i = 0; i < 8; i++) r.l[i] = d[i];
-    }
+#endif
 }
 SVB_HD fr fr_add(const fr& a, const fr& b) {
     fr r;
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %8, %16;\n\t addc.cc.u32 %1, %9, %17;\n\t addc.cc.u32 %2, %10, %18;\n\t addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t addc.cc.u32 %5, %13, %21;\n\t addc.cc.u32 %6, %14, %22;\n\t addc.u32 %7, %15, %23;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+#else
     u32 carry = 0;
-#pragma unroll
     for (int i = 0; i < 8; i++) {
         u64 t = (u64)a.l[i] + b.l[i] + carry;
         r.l[i] = (u32)t;
         carry = (u32)(t >> 32);
     }
+#endif
     fr_cond_sub(r);   // a + b < 2r < 2^255: no carry out of the top limb
     return r;
 }

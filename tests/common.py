@@ -26,6 +26,8 @@ def corrupt(recs, L, rng, every=8, num_steps=None):
         k += 1
         if num_steps == 0 and c in ("step_eval", "step_sibling"):
             c = "leaf"   # a shape without reduction steps has no step data to corrupt
+        if c == "step_sibling" and L.step_depth[0] == 0:
+            c = "step_eval"   # a step tree of depth 0 has no siblings
         q = int(rng.integers(0, nq))
         qb = L.header_words + q * L.query_words
         delta = np.uint64(1) << np.uint64(int(rng.integers(0, 20)))

@@ -472,3 +472,24 @@ def test_error_convention(svb, ctx):
         ctx.poseidon_permute_batch(np.zeros((1, 12), dtype=np.uint64), hash_kind=9)
     # the context is still usable after errors
     assert int(ctx.poseidon_permute_batch(np.arange(12, dtype=np.uint64))[0]) == 0xd64e1e3efc5b8e9e
+
+
+@pytest.mark.parametrize("degree_bits,rate_bits,cap,queries", [(5, 3, 2, 4), (5, 1, 0, 3), (6, 1, 6, 5), (7, 1, 6, 2)])
+def test_fri_edge_shapes(svb, orc, ctx, degree_bits, rate_bits, cap, queries):
+    """Degenerate shapes: no reduction step at all (degree_bits = 5 with a 32-coefficient final polynomial),
+    step trees of depth 0 (the coset pair IS the cap entry), caps as tall as the tree allows."""
+    params = tiny_params(svb, cap=cap, queries=queries, degree_bits=degree_bits, rate_bits=rate_bits)
+    L = svb.api.make_layout(params)
+    ns = len(params.reduction_arity_bits)
+    n = 37
+    recs = svb.synth_proofs(params, n, seed=degree_bits * 100 + cap, n_circuits=2)
+    bad = corrupt(recs, L, np.random.default_rng(4), every=4, num_steps=ns)
+    bm, ff = ctx.fri_verify_batch(params, recs, want_fail=True)
+    oshape = orc.shape_from(params.to_shape())
+    want = orc.fri_verify_batch(oshape, recs, nthreads=4)
+    assert (bm == want).all()
+    for i in range(n):
+        ok, code, q = orc.fri_verify(oshape, recs[i])
+        assert bit(bm, i) == int(ok)
+        assert int(ff[i]) == (0 if ok else ((max(q, 0) << 8) | code)), (i, bad.get(i))
+    assert sum(bit(bm, i) for i in range(n)) >= n - len(bad)      # every untouched proof is accepted

@@ -87,6 +87,8 @@ extern "C" {
     pub fn sv_merkle_verify_batch(ctx: *mut sv_ctx, leaf_len: u32, depth: u32, cap_height: u32, hash_kind: c_int,
                                   paths: *const u64, indices: *const u64, caps: *const u64, ok: *mut u8,
                                   n: usize, mem: c_int) -> c_int;
+    pub fn sv_merkle_tree_build(ctx: *mut sv_ctx, hash_kind: c_int, leaf_len: u32, leaves: *const u64, n_leaves: usize,
+                                cap_height: u32, layers_out: *mut u64, mem: c_int) -> c_int;
     pub fn sv_fri_verify_batch(ctx: *mut sv_ctx, shape: *const sv_fri_shape, n_proofs: usize, records: *const u64,
                                accept_bitmap: *mut u32, first_fail: *mut u32, mem: c_int) -> c_int;
     pub fn sv_fri_challenges(shape: *const sv_fri_shape, record: *mut u64, circuit_digest: *const u64,

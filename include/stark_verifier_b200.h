@@ -145,6 +145,15 @@ int sv_merkle_verify_batch(sv_ctx* ctx, uint32_t leaf_len, uint32_t depth, uint3
                            const uint64_t* paths, const uint64_t* indices, const uint64_t* caps, uint8_t* ok,
                            size_t n, int mem);
 
+/* Build the Merkle tree of n_leaves = 2^k leaf rows of leaf_len words (row-major, contiguous).
+ * layers_out receives the digest layers bottom-up: leaf digests (n_leaves x 4 words; a row of <= 4 words is its own
+ * digest, zero-padded), then every level of two_to_one parents down to the cap layer (2^cap_height x 4 words):
+ * 4 * (2 * n_leaves - 2^cap_height) words in total.  The sibling of node j at a level is node j ^ 1 of that layer.
+ * Replaces: plonky2 MerkleTree::new (call sites plonky2_semaphore/access_set.rs:25, circuit.rs:91) -- the prover
+ * side of sv_merkle_verify_batch. */
+int sv_merkle_tree_build(sv_ctx* ctx, int hash_kind, uint32_t leaf_len, const uint64_t* leaves, size_t n_leaves,
+                         uint32_t cap_height, uint64_t* layers_out, int mem);
+
 /* Batch FRI query-phase verification: n_proofs flat records (sv_fri_layout.record_words each).
  * accept_bitmap: ceil(n_proofs/32) u32 words, bit (i & 31) of word i/32 = proof i accepted.
  * first_fail: optional (NULL to skip), n_proofs u32 (see above).

@@ -155,6 +155,7 @@ def lib() -> ctypes.CDLL:
     L.sv_goldilocks_mul_add_batch.argtypes = [vp, vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_int]
     L.sv_merkle_verify_batch.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int,
                                          vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_int]
+    L.sv_merkle_tree_build.argtypes = [vp, ctypes.c_int, ctypes.c_uint32, vp, ctypes.c_size_t, ctypes.c_uint32, vp, ctypes.c_int]
     L.sv_fri_verify_batch.argtypes = [vp, ctypes.POINTER(FriShape), ctypes.c_size_t, vp, vp, vp, ctypes.c_int]
     L.sv_allgather_bitmap.argtypes = [vp, vp, vp, vp, ctypes.c_size_t]
     L.sv_fri_challenges.argtypes = [ctypes.POINTER(FriShape), vp, vp, vp, ctypes.c_uint32]
@@ -297,6 +298,25 @@ class Context:
                                                   _ptr(paths), _ptr(indices), _ptr(caps), _ptr(ok), n, mem),
                  "sv_merkle_verify_batch")
         return ok
+
+    def merkle_tree_build(self, leaves, leaf_len: int, cap_height: int, n_leaves: Optional[int] = None, layers_out=None,
+                          mem: int = MEM_HOST, hash_kind: int = HASH_POSEIDON_GOLDILOCKS):
+        """Digest layers of the Merkle tree over `leaves` (n x leaf_len), bottom-up, as a list of (m, 4) arrays
+        (host mode) or the flat device buffer (device mode)."""
+        if mem == MEM_HOST:
+            leaves = np.ascontiguousarray(leaves, dtype=np.uint64).reshape(-1, leaf_len)
+            n_leaves = leaves.shape[0]
+            layers_out = np.zeros(4 * (2 * n_leaves - (1 << cap_height)), dtype=np.uint64)
+        self._ck(self._lib.sv_merkle_tree_build(self._h, hash_kind, leaf_len, _ptr(leaves), n_leaves, cap_height, _ptr(layers_out), mem),
+                 "sv_merkle_tree_build")
+        if mem != MEM_HOST:
+            return layers_out
+        out, off, m = [], 0, n_leaves
+        while m >= (1 << cap_height):
+            out.append(layers_out[off:off + 4 * m].reshape(m, 4))
+            off += 4 * m
+            m >>= 1
+        return out
 
     def fri_verify_batch(self, params: FriParams, records, n_proofs: Optional[int] = None, accept_bitmap=None,
                          first_fail=None, want_fail: bool = False, mem: int = MEM_HOST):

@@ -297,6 +297,44 @@ extern "C" int sv_merkle_verify_batch(sv_ctx* c, uint32_t leaf_len, uint32_t dep
     return 0;
 }
 
+// layers_out: leaf digests (n x 4 words), then every level up to the cap (2^cap_height x 4 words)
+extern "C" int sv_merkle_tree_build(sv_ctx* c, int hash_kind, uint32_t leaf_len, const uint64_t* leaves, size_t n_leaves,
+                                    uint32_t cap_height, uint64_t* layers_out, int mem) {
+    if (!c || !leaves || !layers_out) return -1;
+    if (!known_kind(hash_kind)) return fail(c, -5, "hash_kind %d not implemented", hash_kind);
+    if (leaf_len == 0 || n_leaves == 0 || (n_leaves & (n_leaves - 1)) || cap_height > 30 || ((size_t)1 << cap_height) > n_leaves)
+        return fail(c, -7, "bad tree shape (n_leaves must be a power of two >= 2^cap_height)");
+    CK(c, cudaSetDevice(c->device));
+    const int B = SVB_BLOCK;
+    const size_t ncap = (size_t)1 << cap_height, out_words = 4 * (2 * n_leaves - ncap);
+    const u64* d_leaves = leaves;
+    u64* d_out = layers_out;
+    cudaStream_t s = mem == SV_MEM_DEVICE ? c->stream : c->own_stream;
+    if (mem != SV_MEM_DEVICE) {
+        size_t in_words = n_leaves * (size_t)leaf_len;
+        if (grow(c, c->d_stage[0], c->stage_words[0], in_words)) return -6;
+        if (grow(c, c->d_stage[1], c->stage_words[1], out_words)) return -6;
+        CK(c, cudaMemcpyAsync(c->d_stage[0], leaves, in_words * 8, cudaMemcpyHostToDevice, s));
+        d_leaves = c->d_stage[0];
+        d_out = c->d_stage[1];
+    }
+    SVB_LAUNCH_KIND(hash_kind, merkle_leaf_hash_kernel, (unsigned)((n_leaves + B - 1) / B), B, s, d_leaves, leaf_len, n_leaves, d_out);
+    c->launches++;
+    u64* cur = d_out;
+    for (size_t m = n_leaves; m > ncap; m >>= 1) {
+        u64* nxt = cur + 4 * m;
+        SVB_LAUNCH_KIND(hash_kind, merkle_level_kernel, (unsigned)((m / 2 + B - 1) / B), B, s, cur, nxt, m / 2);
+        c->launches++;
+        cur = nxt;
+    }
+    CK(c, cudaGetLastError());
+    if (mem != SV_MEM_DEVICE) {
+        CK(c, cudaMemcpyAsync(layers_out, d_out, out_words * 8, cudaMemcpyDeviceToHost, s));
+        CK(c, cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 static int make_params(sv_ctx* c, const sv_fri_shape& s, FriKernelParams& P) {
     memset(&P, 0, sizeof P);

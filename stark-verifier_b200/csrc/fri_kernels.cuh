@@ -496,6 +496,53 @@ __global__ void __launch_bounds__(128) fri_challenges_coop_kernel(u64* __restric
     }
 }
 
+// ---- Merkle tree construction (the prover side of the same hash) ---------------------
+// Leaf digests: hash_or_noop of each leaf row (plonky2 MerkleTree::new; call sites
+// plonky2_semaphore/access_set.rs:25, circuit.rs:91).  One thread per leaf.
+template <int KIND>
+__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) merkle_leaf_hash_kernel(const u64* __restrict__ leaves, u32 leaf_len,
+                                                                                    size_t n, u64* __restrict__ digests) {
+    __shared__ u64 scratch[PermScratch<KIND>::words * SVB_BLOCK];
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64* leaf = leaves + i * (size_t)leaf_len;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = 0;
+    if (leaf_len <= 4) {
+        for (u32 k = 0; k < leaf_len; k++) s[k] = leaf[k];
+    } else {
+#pragma unroll 1
+        for (u32 off = 0; off < leaf_len; off += 8) {
+            u32 rem = leaf_len - off;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if ((u32)k < rem) s[k] = leaf[off + k];
+            permute_dev<KIND>(s, scratch, SVB_BLOCK);
+        }
+    }
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(digests + 4 * i);
+    o[0] = make_ulonglong2(canon(s[0]), canon(s[1]));
+    o[1] = make_ulonglong2(canon(s[2]), canon(s[3]));
+}
+// One tree level: parent j = two_to_one(child 2j, child 2j+1).  One thread per parent.
+template <int KIND>
+__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) merkle_level_kernel(const u64* __restrict__ children, u64* __restrict__ parents,
+                                                                                size_t n_parents) {
+    __shared__ u64 scratch[PermScratch<KIND>::words * SVB_BLOCK];
+    size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (j >= n_parents) return;
+    u64 s[12];
+    ldg4(children + 8 * j, s);
+    ldg4(children + 8 * j + 4, s + 4);
+#pragma unroll
+    for (int k = 8; k < 12; k++) s[k] = 0;
+    permute_dev<KIND>(s, scratch, SVB_BLOCK);
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(parents + 4 * j);
+    o[0] = make_ulonglong2(canon(s[0]), canon(s[1]));
+    o[1] = make_ulonglong2(canon(s[2]), canon(s[3]));
+}
+
 // first_fail post-pass: 0xFFFFFFFF (never failed) -> 0, else (query << 8) | code.
 __global__ void fri_finalize_kernel(u32* __restrict__ first_fail, u32 n) {
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -493,3 +493,67 @@ def test_fri_edge_shapes(svb, orc, ctx, degree_bits, rate_bits, cap, queries):
         assert bit(bm, i) == int(ok)
         assert int(ff[i]) == (0 if ok else ((max(q, 0) << 8) | code)), (i, bad.get(i))
     assert sum(bit(bm, i) for i in range(n)) >= n - len(bad)      # every untouched proof is accepted
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("leaf_len,log_n,cap_height", [(4, 5, 0), (3, 3, 1), (9, 4, 2), (135, 3, 0), (20, 2, 2)])
+def test_merkle_tree_build_matches_oracle(svb, orc, ctx, kind, leaf_len, log_n, cap_height):
+    """sv_merkle_tree_build (leaf digests + every level down to the cap) against the oracle's hash_no_pad /
+    two_to_one, for both hash families."""
+    rng = np.random.default_rng(leaf_len * 10 + log_n)
+    n = 1 << log_n
+    leaves = rng.integers(0, P, size=(n, leaf_len), dtype=np.uint64)
+    layers = ctx.merkle_tree_build(leaves, leaf_len, cap_height, hash_kind=kind)
+    assert len(layers) == log_n - cap_height + 1 and layers[-1].shape == (1 << cap_height, 4)
+    want = []
+    for i in range(n):
+        if leaf_len <= 4:
+            d = np.zeros(4, dtype=np.uint64); d[:leaf_len] = leaves[i]
+        else:
+            d = orc.hash_no_pad(leaves[i], kind=kind)
+        want.append(d)
+    want = np.array(want, dtype=np.uint64)
+    assert (layers[0] == want).all()
+    for lvl in range(1, len(layers)):
+        want = np.array([orc.two_to_one(want[2 * j], want[2 * j + 1], kind=kind) for j in range(len(want) // 2)], dtype=np.uint64)
+        assert (layers[lvl] == want).all()
+
+
+def test_merkle_build_then_verify_roundtrip_large(svb, ctx):
+    """Size-independent property at scale: build a 2^18-leaf tree on the device, open 2^16 random leaves (paths
+    read out of the layers), verify them all on the device -> every path accepts; flip one bit in a quarter
+    of them -> exactly those reject."""
+    import torch
+    log_n, leaf_len, cap_height = 18, 7, 3
+    n = 1 << log_n
+    g = torch.Generator(device="cuda"); g.manual_seed(18)
+    leaves = torch.randint(0, 1 << 62, (n, leaf_len), dtype=torch.int64, device="cuda", generator=g)
+    total = 4 * (2 * n - (1 << cap_height))
+    layers = torch.zeros(total, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.merkle_tree_build(leaves.data_ptr(), leaf_len, cap_height, n_leaves=n, layers_out=layers.data_ptr(), mem=svb.MEM_DEVICE)
+    ctx.synchronize()
+    depth = log_n - cap_height
+    m = 1 << 16
+    idx = torch.randint(0, n, (m,), dtype=torch.int64, device="cuda", generator=g)
+    lw = (leaf_len + 3) & ~3
+    paths = torch.zeros((m, lw + 4 * depth), dtype=torch.int64, device="cuda")
+    paths[:, :leaf_len] = leaves[idx]
+    off, width, node = 0, n, idx.clone()
+    for lvl in range(depth):
+        layer = layers[off:off + 4 * width].view(width, 4)
+        paths[:, lw + 4 * lvl: lw + 4 * lvl + 4] = layer[node ^ 1]
+        off += 4 * width; width >>= 1; node >>= 1
+    cap = layers[off:off + 4 * width].contiguous()
+    assert width == 1 << cap_height
+    bad = torch.arange(0, m, 4, device="cuda")
+    col = lw + 4 * (torch.arange(bad.numel(), device="cuda") % depth) + 1
+    paths[bad, col] ^= 1
+    ok = torch.zeros(m, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.merkle_verify_batch(leaf_len, depth, cap_height, paths.data_ptr(), idx.data_ptr(), cap.data_ptr(), ok.data_ptr(), n=m,
+                            mem=svb.MEM_DEVICE)
+    ctx.synchronize()
+    want = torch.ones(m, dtype=torch.uint8, device="cuda")
+    want[bad] = 0
+    assert torch.equal(ok, want)

@@ -29,7 +29,7 @@ namespace svb {
 
 #define SVB_BLOCK 128   // threads per block of every kernel; also the stride of the per-thread smem scratch
 #ifndef SVB_MINBLOCKS
-#define SVB_MINBLOCKS 1  // __launch_bounds__ second argument of the hashing kernels (register cap = 65536 / (128 * N))
+#define SVB_MINBLOCKS 4  // __launch_bounds__ second argument of the hashing kernels (register cap = 65536 / (128 * N)); measured best
 #endif
 
 struct FriKernelParams {

@@ -137,15 +137,19 @@ SVB_HD void poseidon_g(u64 s[12]) {
 // integer is read back from the mantissa bits (the exponent pattern 0x433 of the high words is
 // subtracted inside the carry chain that recombines the two halves).
 #ifndef SVB_MDS_CVT
-#define SVB_MDS_CVT 1   // 1: I2F.F64.U32 conversions; 0: mantissa trick (2 MOV + DADD per value)
+#define SVB_MDS_CVT 2   // 2: subnormal trick (no conversion at all); 1: I2F.F64.U32; 0: mantissa trick (2 MOV + DADD)
 #endif
-SVB_D double u32_to_f64(u32 x) {
-#if SVB_MDS_CVT
-    return __uint2double_rn(x);
+#if SVB_MDS_CVT == 2
+// A u32 x placed in the low word of a binary64 with a zero high word IS the subnormal x * 2^-1074: no
+// conversion instruction at all (I2F.F64.U32 costs 8.5 cycles per warp).  Subnormal arithmetic is plain
+// fixed point with ulp 2^-1074, exact while the integers stay below 2^52 -- here every row sum is < 2^42 --
+// and FP64 has no flush-to-zero mode on NVIDIA GPUs.  The accumulator's bit pattern is the integer itself.
+SVB_D double u32_to_f64(u32 x) { return __hiloint2double(0, (int)x); }
+#elif SVB_MDS_CVT == 1
+SVB_D double u32_to_f64(u32 x) { return __uint2double_rn(x); }
 #else
-    return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0;
+SVB_D double u32_to_f64(u32 x) { return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0; }
 #endif
-}
 SVB_D void mds_layer_rc_f64(u64 s[12], const u64* __restrict__ rcf /* FULL_RC_NEXT_F64: 2 words per row */) {
     double d[12];
     u32 h[12];
@@ -157,7 +161,11 @@ SVB_D void mds_layer_rc_f64(u64 s[12], const u64* __restrict__ rcf /* FULL_RC_NE
     }
 #pragma unroll
     for (int r = 0; r < 12; r++) {
+#if SVB_MDS_CVT == 2
+        double acc = __hiloint2double(0, (int)(u32)rcf[2 * r]);
+#else
         double acc = __longlong_as_double((long long)rcf[2 * r]);
+#endif
 #pragma unroll
         for (int j = 0; j < 12; j++) acc = __fma_rn(d[j], (double)mds_coeff(r, j), acc);
         al0[r] = (u32)__double2loint(acc);
@@ -167,15 +175,23 @@ SVB_D void mds_layer_rc_f64(u64 s[12], const u64* __restrict__ rcf /* FULL_RC_NE
     for (int j = 0; j < 12; j++) d[j] = u32_to_f64(h[j]);
 #pragma unroll
     for (int r = 0; r < 12; r++) {
+#if SVB_MDS_CVT == 2
+        double acc = __hiloint2double(0, (int)(u32)rcf[2 * r + 1]);
+#else
         double acc = __longlong_as_double((long long)rcf[2 * r + 1]);
+#endif
 #pragma unroll
         for (int j = 0; j < 12; j++) acc = __fma_rn(d[j], (double)mds_coeff(r, j), acc);
         u32 ah0 = (u32)__double2loint(acc), ah1 = (u32)__double2hiint(acc);
         // V = al + ah*W = v0 + v1 W + v2 W^2 (v2 < 2^11); result = v2*EPS + (v1:v0) + cy*EPS
         u32 lo, hi;
         asm("{\n\t.reg .u32 x1, v1, v2, t0, t1, cy, h2;\n\t"
+#if SVB_MDS_CVT == 2
+            "add.cc.u32 v1, %3, %4;\n\t addc.u32 v2, %5, 0;\n\t"
+#else
             "sub.u32 x1, %3, 0x43300000;\n\t"
             "add.cc.u32 v1, x1, %4;\n\t addc.u32 v2, %5, 0xBCD00000;\n\t"
+#endif
             "mad.lo.cc.u32 t0, v2, %6, %2;\n\t madc.hi.cc.u32 t1, v2, %6, v1;\n\t addc.u32 cy, 0, 0;\n\t"
             "sub.cc.u32 %0, t0, cy;\n\t subc.u32 h2, t1, 0;\n\t add.u32 %1, h2, cy;\n\t"
             "}" : "=r"(lo), "=r"(hi) : "r"(al0[r]), "r"(al1[r]), "r"(ah0), "r"(ah1), "r"(d_EPS32));

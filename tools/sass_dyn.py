@@ -26,6 +26,42 @@ for i, (a, t) in enumerate(lines):
 loops.sort()
 # expected nesting: outer (x8) contains sbox (x3); then init (x11), partial (x22) inside the f==3 branch
 trip = {}
+if len(loops) == 3:
+    # fully unrolled S-box layer: outer full-round loop (x8) containing the initial-matrix (x11) and partial (x22) loops
+    outer = max(loops, key=lambda x: x[1] - x[0])
+    inner = sorted(l for l in loops if l != outer)
+    mult = [1.0] * len(lines)
+    for i in range(outer[0], outer[1] + 1):
+        mult[i] = 8.0
+    # the f == 3 block (forward branch over it) runs once: everything from the branch before inner[0] to the end of inner[1]
+    start = inner[0][0]
+    for i in range(inner[0][0] - 1, outer[0], -1):
+        if "BRA" in lines[i][1]:
+            start = i + 1
+            break
+    m = None
+    for i in range(start - 1, start):
+        m = re.search(r"(0x[0-9a-f]+)", lines[i][1].split("BRA")[1]) if "BRA" in lines[i][1] else None
+    end = addr_to_idx[int(m.group(1), 16)] if m and int(m.group(1), 16) in addr_to_idx else inner[1][1] + 1
+    for i in range(start, end):
+        mult[i] = 1.0
+    for i in range(inner[0][0], inner[0][1] + 1):
+        mult[i] = 11.0
+    for i in range(inner[1][0], inner[1][1] + 1):
+        mult[i] = 22.0
+    cnt = collections.Counter()
+    for (a, t), mm in zip(lines, mult):
+        op = t.split()[0] if not t.startswith("@") else t.split()[1]
+        cnt[op] += mm
+    tot = sum(cnt.values())
+    wide = sum(v for k, v in cnt.items() if k.startswith("IMAD.WIDE"))
+    hi = sum(v for k, v in cnt.items() if k.startswith("IMAD.HI"))
+    imad_other = sum(v for k, v in cnt.items() if k.startswith("IMAD") and not k.startswith("IMAD.WIDE") and not k.startswith("IMAD.HI"))
+    print(f"dynamic instructions per permutation: {tot:.0f}")
+    for k, v in cnt.most_common(16):
+        print(f"  {k:22s} {v:8.0f}")
+    print(f"instructions: {tot:.0f};  fmaheavy cycles (WIDE,HI=4, other IMAD=2): {4 * (wide + hi) + 2 * imad_other:.0f}  (wide {wide:.0f}, hi {hi:.0f}, other IMAD {imad_other:.0f})")
+    sys.exit(0)
 if len(loops) == 4:
     loops_sorted = sorted(loops, key=lambda x: x[1] - x[0])
     # identify: largest = outer

@@ -162,7 +162,7 @@ SVB_D void mds_layer_rc_f64(u64 s[12], const u64* __restrict__ rcf /* FULL_RC_NE
 #pragma unroll
     for (int r = 0; r < 12; r++) {
 #if SVB_MDS_CVT == 2
-        double acc = __hiloint2double(0, (int)(u32)rcf[2 * r]);
+        double acc = __longlong_as_double((long long)rcf[2 * r]);       // FULL_RC_NEXT_SUBNORMAL: the integer itself
 #else
         double acc = __longlong_as_double((long long)rcf[2 * r]);
 #endif
@@ -176,7 +176,7 @@ SVB_D void mds_layer_rc_f64(u64 s[12], const u64* __restrict__ rcf /* FULL_RC_NE
 #pragma unroll
     for (int r = 0; r < 12; r++) {
 #if SVB_MDS_CVT == 2
-        double acc = __hiloint2double(0, (int)(u32)rcf[2 * r + 1]);
+        double acc = __longlong_as_double((long long)rcf[2 * r + 1]);
 #else
         double acc = __longlong_as_double((long long)rcf[2 * r + 1]);
 #endif
@@ -293,7 +293,11 @@ SVB_D void poseidon_g_dev(u64 s[12], u64* __restrict__ scratch /* 11 words of pe
 #pragma unroll
         for (int i = 0; i < 12; i++) s[i] += s[(i + 5) % 12] ^ d_FULL_RC_NEXT[12 * f + i];
 #else
+#if SVB_MDS_CVT == 2
+        mds_layer_rc_f64(s, d_FULL_RC_NEXT_SUBNORMAL + 24 * f);   // (:450-502) + next constant layer
+#else
         mds_layer_rc_f64(s, d_FULL_RC_NEXT_F64 + 24 * f);   // (:450-502) + next constant layer
+#endif
 #endif
         if (f == 3) {
             // mds_partial_layer_init (:504-537): t[c] = sum_{r=1..11} INIT[r-1][c-1] * s[r]

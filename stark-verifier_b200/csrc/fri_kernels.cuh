@@ -29,8 +29,10 @@ namespace svb {
 
 #define SVB_BLOCK 128   // threads per block of every kernel; also the stride of the per-thread smem scratch
 #ifndef SVB_MINBLOCKS
-#define SVB_MINBLOCKS 4  // __launch_bounds__ second argument of the hashing kernels (register cap = 65536 / (128 * N)); measured best
+#define SVB_MINBLOCKS 4  // __launch_bounds__ second argument of the Poseidon-Goldilocks kernels (register cap = 65536 / (128 * N)); measured best
 #endif
+// Poseidon-BN254 kernels want ~130 registers: capping them at 126 costs 6 % (spills), so they keep 3 blocks per SM
+#define SVB_MINBLOCKS_K(KIND) ((KIND) == SV_HASH_POSEIDON_BN254 ? 3 : SVB_MINBLOCKS)
 
 struct FriKernelParams {
     sv_fri_layout L;
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(SVB_BLOCK) fri_prepare_kernel(const u64* __res
 
 // The fused query kernel: one thread per (class, unit).
 template <int KIND>
-__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) fri_query_kernel(const u64* __restrict__ records, FriKernelParams P,
+__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) fri_query_kernel(const u64* __restrict__ records, FriKernelParams P,
                                                         const u64* __restrict__ scratch, u32* __restrict__ accept_bitmap,
                                                         u32* __restrict__ first_fail) {
     __shared__ u64 pscratch[PermScratch<KIND>::words * SVB_BLOCK];
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) fri_query_kernel(con
 
 // n independent permutations, thread per state (canonical in / out).
 template <int KIND>
-__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) poseidon_permute_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
+__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) poseidon_permute_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
     __shared__ u64 scratch[PermScratch<KIND>::words * SVB_BLOCK];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) poseidon_permute_ker
 
 // n independent Merkle paths, thread per path.  Record = up4(leaf_len) + 4*depth words.
 template <int KIND>
-__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) merkle_verify_kernel(const u64* __restrict__ paths, const u64* __restrict__ indices,
+__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) merkle_verify_kernel(const u64* __restrict__ paths, const u64* __restrict__ indices,
                                                             const u64* __restrict__ caps, unsigned char* __restrict__ ok,
                                                             size_t n, u32 leaf_len, u32 depth, u32 cap_height) {
     __shared__ u64 scratch[PermScratch<KIND>::words * SVB_BLOCK];
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(128) fri_challenges_coop_kernel(u64* __restric
 // Leaf digests: hash_or_noop of each leaf row (plonky2 MerkleTree::new; call sites
 // plonky2_semaphore/access_set.rs:25, circuit.rs:91).  One thread per leaf.
 template <int KIND>
-__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) merkle_leaf_hash_kernel(const u64* __restrict__ leaves, u32 leaf_len,
+__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) merkle_leaf_hash_kernel(const u64* __restrict__ leaves, u32 leaf_len,
                                                                                     size_t n, u64* __restrict__ digests) {
     __shared__ u64 scratch[PermScratch<KIND>::words * SVB_BLOCK];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) merkle_leaf_hash_ker
 }
 // One tree level: parent j = two_to_one(child 2j, child 2j+1).  One thread per parent.
 template <int KIND>
-__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) merkle_level_kernel(const u64* __restrict__ children, u64* __restrict__ parents,
+__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) merkle_level_kernel(const u64* __restrict__ children, u64* __restrict__ parents,
                                                                                 size_t n_parents) {
     __shared__ u64 scratch[PermScratch<KIND>::words * SVB_BLOCK];
     size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

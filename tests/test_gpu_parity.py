@@ -557,3 +557,30 @@ def test_merkle_build_then_verify_roundtrip_large(svb, ctx):
     want = torch.ones(m, dtype=torch.uint8, device="cuda")
     want[bad] = 0
     assert torch.equal(ok, want)
+
+
+@pytest.mark.parametrize("polys,num_zs,hiding,num_challenges", [((6, 11, 4, 3), 2, False, 2), ((6, 11, 4, 3), 1, True, 1),
+                                                                 ((1, 2, 3, 4), 3, False, 3), ((9, 1, 8, 1), 2, True, 2)])
+def test_fri_unusual_oracle_widths(svb, orc, ctx, polys, num_zs, hiding, num_challenges):
+    """Oracle widths other than the recursion-circuit defaults: leaves of <= 4 words inside the FRI path
+    (hash_or_noop: the leaf IS the digest), one-column oracles, a different number of Z polynomials /
+    challenges (the transcript squeezes num_challenges betas, gammas and alphas before zeta)."""
+    params = tiny_params(svb, hiding=hiding, cap=1, degree_bits=6, oracle_num_polys=polys, num_zs=num_zs)
+    L = svb.api.make_layout(params)
+    n = 33
+    recs = svb.synth_proofs(params, n, seed=sum(polys), n_circuits=1, num_challenges=num_challenges)
+    bad = corrupt(recs, L, np.random.default_rng(12), every=4)
+    bm, ff = ctx.fri_verify_batch(params, recs, want_fail=True)
+    oshape = orc.shape_from(params.to_shape())
+    want = orc.fri_verify_batch(oshape, recs, nthreads=4)
+    assert (bm == want).all()
+    for i in range(n):
+        ok, code, q = orc.fri_verify(oshape, recs[i])
+        assert int(ff[i]) == (0 if ok else ((max(q, 0) << 8) | code))
+        assert bit(bm, i) == (0 if i in bad else 1), (i, bad.get(i), code)
+    # the device transcript with this num_challenges reproduces the prover's challenges
+    cd, ph = svb.synth_public_inputs(params, 8, seed=sum(polys), n_circuits=1)
+    fresh = svb.synth_proofs(params, 8, seed=sum(polys), n_circuits=1, num_challenges=num_challenges)
+    dev = _clear_challenges(fresh, L, params)
+    ctx.fri_challenges_batch(params, dev, cd[0], ph, num_challenges=num_challenges)
+    assert (dev == fresh).all()

@@ -91,6 +91,12 @@ extern "C" {
                                 cap_height: u32, layers_out: *mut u64, mem: c_int) -> c_int;
     pub fn sv_fri_verify_batch(ctx: *mut sv_ctx, shape: *const sv_fri_shape, n_proofs: usize, records: *const u64,
                                accept_bitmap: *mut u32, first_fail: *mut u32, mem: c_int) -> c_int;
+    pub fn sv_fri_challenges_batch(ctx: *mut sv_ctx, shape: *const sv_fri_shape, n_proofs: usize, records: *mut u64,
+                                   circuit_digest: *const u64, public_inputs_hashes: *const u64, num_challenges: u32,
+                                   mem: c_int) -> c_int;
+    pub fn sv_fri_verify_batch_fs(ctx: *mut sv_ctx, shape: *const sv_fri_shape, n_proofs: usize, records: *mut u64,
+                                  circuit_digest: *const u64, public_inputs_hashes: *const u64, num_challenges: u32,
+                                  accept_bitmap: *mut u32, first_fail: *mut u32, mem: c_int) -> c_int;
     pub fn sv_fri_challenges(shape: *const sv_fri_shape, record: *mut u64, circuit_digest: *const u64,
                              public_inputs_hash: *const u64, num_challenges: u32) -> c_int;
 }

@@ -366,9 +366,13 @@ static int make_params(sv_ctx* c, const sv_fri_shape& s, FriKernelParams& P) {
 static int enqueue_challenges(sv_ctx* c, FriKernelParams& P, const FsParams& F, size_t n, u64* d_records, const u64* d_pi,
                               cudaStream_t s) {
     P.n_proofs = (u32)n;
-    static const bool coop = [] { const char* e = getenv("SVB_FS_COOP"); return !e || atoi(e) != 0; }();
+    // SVB_FS_COOP: 1 = always lane-cooperative, 0 = never, unset = by batch size.  The cooperative kernel has the
+    // lower latency (11.9 vs 24.4 us per permutation) but 4.6x less throughput (254 vs 1 177 M perms/s), so it wins
+    // while the batch is latency-bound: below ~8k proofs per call.
+    static const int coop_env = [] { const char* e = getenv("SVB_FS_COOP"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    const bool coop = coop_env < 0 ? n < 8192 : coop_env == 1;
     if (P.hash_kind == SV_HASH_POSEIDON_GOLDILOCKS && coop) {
-        // lane-cooperative transcript: 16 lanes per proof (latency ~5x lower than one thread per proof)
+        // lane-cooperative transcript: 16 lanes per proof
         fri_challenges_coop_kernel<<<(unsigned)((n * SVB_COOP_GROUP + 127) / 128), 128, 0, s>>>(d_records, P, F, d_pi);
         c->launches++;
         CK(c, cudaGetLastError());

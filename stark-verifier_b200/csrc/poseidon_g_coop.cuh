@@ -82,22 +82,16 @@ SVB_D u64 poseidon_g_coop(u64 s, int l, const CoopTables& T) {
         u64 t = dot_reduce(a);
         s = l == 0 ? s : (act ? t : 0);
     }
-#pragma unroll 1
-    for (int r = 0; r < 22; r++) {
-        u64 x = s;
-        if (l == 0) x = sbox7_add(s, T.prc[r]);                    // the lane-0 S-box (+ round constant)
-        const u64 s0 = coop_shfl(x, 0);
+    // 22 partial rounds, software-pipelined.  The dot product D_r = sum_i w_hat_i(r) * s_i(r) does not depend on
+    // this round's S-box output, only on the state left by the previous round, so it is formed (products
+    // + shuffle tree) one round ahead and stays off the critical path  S-box -> 25*t + D -> reduce.  The
+    // S-box runs on every lane (no divergent branch, so ptxas can interleave it with the tree of the
+    // previous iteration); only lane 0's result is used.
+    u32 d0, d1, d2, d3, d4;
+    auto dot_ahead = [&](int r, u64 sv) {
         u32 p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0;
-        u64 snew = 0;
-        if (l == 0) {                                              // 25 * s0 = (MDS_CIRC[0] + MDS_DIAG[0]) * s0
-            u64 lo = 25ull * (u32)s0, hi = 25ull * (u32)(s0 >> 32);
-            u64 mid = (lo >> 32) + (u32)hi;
-            p0 = (u32)lo; p1 = (u32)mid; p2 = (u32)(hi >> 32) + (u32)(mid >> 32);
-        } else if (act) {
-            mulw4(s, T.w[r * 11 + l - 1], p0, p1, p2, p3);         // w_hat_i * s_i, unreduced
-            snew = mul_add(T.v[r * 11 + l - 1], s0, s);            // s_i + v_i * s0
-        }
-        // tree-sum the 12 products over the group (5 limbs with carries)
+        u64 w = (l >= 1 && act) ? T.w[r * 11 + l - 1] : 0;
+        mulw4(sv, w, p0, p1, p2, p3);                               // w_hat_i * s_i, unreduced (0 on lanes 0, 12..15)
 #pragma unroll
         for (int off = 8; off >= 1; off >>= 1) {
             u32 q0 = __shfl_xor_sync(0xFFFFFFFFu, p0, off, SVB_COOP_GROUP);
@@ -109,7 +103,24 @@ SVB_D u64 poseidon_g_coop(u64 s, int l, const CoopTables& T) {
                 "addc.u32 %4, %4, %9;"
                 : "+r"(p0), "+r"(p1), "+r"(p2), "+r"(p3), "+r"(p4) : "r"(q0), "r"(q1), "r"(q2), "r"(q3), "r"(q4));
         }
-        s = l == 0 ? red5(p0, p1, p2, p3, p4) : snew;
+        d0 = p0; d1 = p1; d2 = p2; d3 = p3; d4 = p4;
+    };
+    dot_ahead(0, s);
+#pragma unroll 1
+    for (int r = 0; r < 22; r++) {
+        const u64 t = sbox7_add(s, l == 0 ? T.prc[r] : 0);        // lane 0: the S-box (+ round constant)
+        const u64 s0 = coop_shfl(t, 0);
+        // lane 0: 25 * s0 + D_r  (MDS_CIRC[0] + MDS_DIAG[0] = 25)
+        u64 lo = 25ull * (u32)s0, hi = 25ull * (u32)(s0 >> 32);
+        u64 mid = (lo >> 32) + (u32)hi;
+        u32 e0 = (u32)lo, e1 = (u32)mid, e2 = (u32)(hi >> 32) + (u32)(mid >> 32), e3 = 0, e4 = 0;
+        asm("add.cc.u32 %0, %0, %5;\n\t addc.cc.u32 %1, %1, %6;\n\t addc.cc.u32 %2, %2, %7;\n\t addc.cc.u32 %3, %3, %8;\n\t"
+            "addc.u32 %4, %4, %9;"
+            : "+r"(e0), "+r"(e1), "+r"(e2), "+r"(e3), "+r"(e4) : "r"(d0), "r"(d1), "r"(d2), "r"(d3), "r"(d4));
+        const u64 n0 = red5(e0, e1, e2, e3, e4);
+        const u64 ni = (l >= 1 && act) ? mul_add(T.v[r * 11 + l - 1], s0, s) : 0;   // s_i + v_i * s0
+        s = l == 0 ? n0 : ni;
+        if (r < 21) dot_ahead(r + 1, s);
     }
 #pragma unroll 1
     for (int slot = 4; slot < 8; slot++) s = coop_full_round(s, l, slot, T);

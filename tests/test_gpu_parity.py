@@ -7,6 +7,7 @@ import pytest
 from common import P, PLONKY2_TV12_IN, PLONKY2_TV12_OUT, bit, corrupt, tiny_params
 
 pytestmark = pytest.mark.gpu
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_permute_kat_and_random(svb, orc, ctx):
@@ -584,3 +585,30 @@ def test_fri_unusual_oracle_widths(svb, orc, ctx, polys, num_zs, hiding, num_cha
     dev = _clear_challenges(fresh, L, params)
     ctx.fri_challenges_batch(params, dev, cd[0], ph, num_challenges=num_challenges)
     assert (dev == fresh).all()
+
+
+def test_device_transcript_thread_per_proof_kernel(svb):
+    """The thread-per-proof transcript kernel (used above 8 192 proofs per call) on a small batch, forced with
+    SVB_FS_COOP=0 in a child process (the choice is read once per process)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import stark_verifier_b200 as svb
+from common import tiny_params
+params = tiny_params(svb, cap=2, degree_bits=7)
+recs = svb.synth_proofs(params, 40, seed=77, n_circuits=1)
+cd, ph = svb.synth_public_inputs(params, 40, seed=77, n_circuits=1)
+L = svb.api.make_layout(params)
+dev = recs.copy()
+for off, n in ((L.off_alpha, 2), (L.off_betas, 4), (L.off_pow_response, 1), (L.off_indices, 6), (L.off_zeta, 2), (L.off_zeta_next, 2)):
+    dev[:, off:off + n] = 0
+ctx = svb.Context(0)
+ctx.fri_challenges_batch(params, dev, cd[0], ph)
+assert (dev == recs).all()
+print("ok")
+''' % (ROOT_DIR, os.path.join(ROOT_DIR, "tests"))
+    env = dict(os.environ, SVB_FS_COOP="0")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-1500:]

@@ -391,7 +391,7 @@ static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_rec
     P.n_proofs = (u32)n;
     P.n_units = (u32)(n * P.num_queries);
     P.blocks_per_class = (P.n_units + B - 1) / B;
-    fri_prepare_kernel<<<(unsigned)((n + B - 1) / B), B, 0, s>>>(d_records, P, d_scratch, d_bitmap, d_fail);
+    fri_prepare_kernel<<<(unsigned)((n + 31) / 32), SVB_PREP_BLOCK, 0, s>>>(d_records, P, d_scratch, d_bitmap, d_fail);
     cudaEvent_t te = time_begin(c, s);
     SVB_LAUNCH_KIND(P.hash_kind, fri_query_kernel, P.blocks_per_class * P.n_classes, B, s, d_records, P, d_scratch, d_bitmap, d_fail);
     time_end(c, te, s);

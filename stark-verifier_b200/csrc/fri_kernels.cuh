@@ -157,44 +157,78 @@ SVB_D fp2 horner_base(fp2 alpha, const u64* __restrict__ terms, u32 n, fp2 acc) 
 }
 
 // Per-proof preparation: range-check the header, proof-of-work check, reduced openings.
-// One thread per proof; writes scratch[4*p..] = reduced_openings and the initial accept word.
-__global__ void __launch_bounds__(SVB_BLOCK) fri_prepare_kernel(const u64* __restrict__ records, FriKernelParams P,
-                                                          u64* __restrict__ scratch, u32* __restrict__ accept_bitmap,
-                                                          u32* __restrict__ first_fail) {
-    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per proof, 32 proofs (one accept-bitmap word) per block.  compute_reduced_openings
+// (fri_chip.rs:58-70) is sum_i opening_i * alpha^i: lane j folds its contiguous chunk of c = ceil(n/32)
+// openings by Horner, scales it by (alpha^c)^j and the warp adds the 32 partial sums with shuffles --
+// exact field arithmetic, so the value is the one the reference's sequential Horner gives, at 1/10 of the
+// latency of one thread per proof (this kernel was 1 % of the step).
+#define SVB_PREP_BLOCK 1024
+SVB_D fp2 warp_sum2(fp2 v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        fp2 o;
+        o.c0 = ((u64)__shfl_xor_sync(0xFFFFFFFFu, (u32)(v.c0 >> 32), off) << 32) | __shfl_xor_sync(0xFFFFFFFFu, (u32)v.c0, off);
+        o.c1 = ((u64)__shfl_xor_sync(0xFFFFFFFFu, (u32)(v.c1 >> 32), off) << 32) | __shfl_xor_sync(0xFFFFFFFFu, (u32)v.c1, off);
+        v = add2(v, o);
+    }
+    return v;
+}
+// sum_{i<n} terms[i] * alpha^i over the warp (terms = n Fp2 values, 2 words each)
+SVB_D fp2 warp_reduce_openings(const u64* __restrict__ terms, u32 n, fp2 alpha, u32 lane) {
+    const u32 c = (n + 31) / 32;
+    const u32 lo = lane * c, hi = lo + c < n ? lo + c : n;
+    fp2 acc = mk2(0, 0);
+    for (u32 i = hi; i-- > lo && lo < n;) {
+        ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(terms + 2 * i));
+        acc = add2(mul2(acc, alpha), mk2(v.x, v.y));
+    }
+    fp2 ac = mk2(1, 0);                       // alpha^c
+    for (u32 i = 0; i < c; i++) ac = mul2(ac, alpha);
+    fp2 scale = mk2(1, 0);                    // (alpha^c)^lane by square and multiply
+    for (u32 bit = 0; bit < 5; bit++) {
+        if ((lane >> bit) & 1) scale = mul2(scale, ac);
+        ac = mul2(ac, ac);
+    }
+    return warp_sum2(mul2(acc, scale));
+}
+__global__ void __launch_bounds__(SVB_PREP_BLOCK) fri_prepare_kernel(const u64* __restrict__ records, FriKernelParams P,
+                                                               u64* __restrict__ scratch, u32* __restrict__ accept_bitmap,
+                                                               u32* __restrict__ first_fail) {
+    __shared__ u32 ok_flags[32];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 p = blockIdx.x * 32 + warp;
     bool ok = false;
-    if (p < P.n_proofs) {
+    if (p < P.n_proofs) {          // warp-uniform
         const sv_fri_layout& L = P.L;
         const u64* rec = records + (size_t)p * L.record_words;
-        bool canon_ok = true;
-        for (u32 w = 0; w < L.header_words; w += 2) {
+        bool canon_lane = true;
+        for (u32 w = 2 * lane; w < L.header_words; w += 64) {
             ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(rec + w));
-            canon_ok &= is_canonical(v.x) & is_canonical(v.y);
+            canon_lane &= is_canonical(v.x) & is_canonical(v.y);
         }
+        const bool canon_ok = __all_sync(0xFFFFFFFFu, canon_lane);
         // fri_verify_proof_of_work (fri_chip.rs:364-376)
         u64 resp = rec[L.off_pow_response];
         bool pow_ok = P.pow_bits == 0 || (resp >> (64 - P.pow_bits)) == 0;
-        // compute_reduced_openings (fri_chip.rs:58-70): Horner from the last opening
         fp2 alpha = mk2(rec[L.off_alpha], rec[L.off_alpha + 1]);
-        fp2 ro[2];
-        for (int b = 0; b < 2; b++) {
-            const u64* o = rec + (b ? L.off_open1 : L.off_open0);
-            u32 n = b ? L.n1 : L.n0;
-            fp2 acc = mk2(0, 0);
-            if (canon_ok)
-                for (u32 i = n; i-- > 0;) {
-                    ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(o + 2 * i));
-                    acc = add2(mul2(acc, alpha), mk2(v.x, v.y));
-                }
-            ro[b] = acc;
+        fp2 ro0 = mk2(0, 0), ro1 = mk2(0, 0);
+        if (canon_ok) {            // non-canonical words would break the canonical-input contract of add2/sub2
+            ro0 = warp_reduce_openings(rec + L.off_open0, L.n0, alpha, lane);
+            ro1 = warp_reduce_openings(rec + L.off_open1, L.n1, alpha, lane);
         }
-        scratch[4 * (size_t)p + 0] = ro[0].c0; scratch[4 * (size_t)p + 1] = ro[0].c1;
-        scratch[4 * (size_t)p + 2] = ro[1].c0; scratch[4 * (size_t)p + 3] = ro[1].c1;
         ok = canon_ok && pow_ok;
-        if (first_fail) first_fail[p] = ok ? 0xFFFFFFFFu : (canon_ok ? SV_FAIL_POW : SV_FAIL_NONCANONICAL);
+        if (lane == 0) {
+            scratch[4 * (size_t)p + 0] = ro0.c0; scratch[4 * (size_t)p + 1] = ro0.c1;
+            scratch[4 * (size_t)p + 2] = ro1.c0; scratch[4 * (size_t)p + 3] = ro1.c1;
+            if (first_fail) first_fail[p] = ok ? 0xFFFFFFFFu : (canon_ok ? SV_FAIL_POW : SV_FAIL_NONCANONICAL);
+        }
     }
-    u32 word = __ballot_sync(0xFFFFFFFFu, ok);
-    if ((threadIdx.x & 31) == 0 && (p >> 5) < (P.n_proofs + 31) / 32) accept_bitmap[p >> 5] = word;
+    if (lane == 0) ok_flags[warp] = ok;
+    __syncthreads();
+    if (warp == 0) {
+        u32 word = __ballot_sync(0xFFFFFFFFu, ok_flags[lane] != 0);
+        if (lane == 0 && blockIdx.x < (P.n_proofs + 31) / 32) accept_bitmap[blockIdx.x] = word;
+    }
 }
 
 // The fused query kernel: one thread per (class, unit).

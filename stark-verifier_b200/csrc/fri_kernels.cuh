@@ -16,9 +16,9 @@
 //
 // Memory.  Records are read straight from global memory with 128-bit read-only loads: a lane reads
 // the 32 B digest of its own query block, i.e. each request touches 32 distinct sectors, all fully
-// used (no over-fetch).  The path is integer-issue bound (~2.5e4 instructions per 32 B sibling), so
-// nothing is staged through shared memory: there is no reuse to exploit and no latency left exposed
-// at >= 8 warps per scheduler.
+// used (no over-fetch).  The path is bound by the integer multiplier (~1.7e4 instructions per 32 B
+// sibling), so the records are not staged through shared memory: there is no reuse to exploit, and the
+// next level's sibling is prefetched while the current permutation runs.
 #pragma once
 #include "layout.hpp"
 #include "poseidon_g.cuh"

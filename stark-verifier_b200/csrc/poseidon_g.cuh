@@ -120,14 +120,16 @@ SVB_HD void poseidon_g(u64 s[12]) {
 
 #if defined(__CUDACC__)
 // ================================================================================================
-// Device path (sm_100a).  Design constraints measured with ncu on B200 (profiles/):
+// Device path (sm_100a).  What the measurements on B200 said (profiles/, tools/lab/NOTES.md):
 //  * the first version unrolled everything (90 KB of SASS per permutation) and spent half of its
-//    issue slots stalled on `no_instruction` (instruction-cache misses, icc hit rate 67%).  The code
-//    below keeps the hot loop bodies small: ONE full-round body (S-box on 4 lanes x 3 rotations +
-//    one unrolled MDS) shared by both halves, a looped initial matrix, one partial-round body;
-//  * IMAD (fma pipe) and IADD3/LOP3 (alu pipe) each issue at half rate per scheduler, so the
-//    arithmetic is written as mad.wide / carry chains that ptxas maps to IMAD.WIDE.U32[.X] with
-//    predicate carries, keeping the two pipes roughly balanced.
+//    issue slots stalled on instruction-cache misses; the code below is ~35 KB: ONE full-round body
+//    (12 unrolled S-boxes + one MDS layer) shared by both halves, a looped initial matrix, one
+//    partial-round body;
+//  * IMAD.WIDE.U32 holds the fmaheavy pipe 4.24 cycles per warp and the other pipes overlap with it
+//    only partially, so every instruction counts: a modular multiplication is 14 instructions
+//    (goldilocks.cuh), dot products keep unreduced limbs (5.5 instructions per term), and the MDS layers
+//    run as exact integer arithmetic on the otherwise idle FP64 pipe, fed with subnormals so that no
+//    int<->double conversion is needed.
 // ================================================================================================
 // The MDS layer on the FP64 pipe.  Measured on B200 (tools/microbench/pipes.cu): IMAD.WIDE.U32 holds
 // the fmaheavy pipe 4 cycles per warp instruction and the S-boxes already saturate it; DFMA issues

@@ -10,7 +10,6 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <vector>
 
@@ -48,7 +47,7 @@ struct sv_ctx {
     int (*ncclAllGather_fn)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
 };
 
-static std::string g_create_err;
+static thread_local std::string g_create_err;   // errors raised without a context (sv_ctx_create, sv_host_alloc)
 
 // launch KERNEL<hash kind>(args) for a run-time hash kind
 #define SVB_LAUNCH_KIND(kind, KERNEL, grid, block, stream, ...)                                         \
@@ -56,6 +55,7 @@ static std::string g_create_err;
         if ((kind) == SV_HASH_POSEIDON_BN254) KERNEL<SV_HASH_POSEIDON_BN254><<<(grid), (block), 0, (stream)>>>(__VA_ARGS__); \
         else KERNEL<SV_HASH_POSEIDON_GOLDILOCKS><<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);    \
     } while (0)
+static bool known_mem(int m) { return m == SV_MEM_HOST || m == SV_MEM_DEVICE; }
 static bool known_kind(int k) { return k == SV_HASH_POSEIDON_GOLDILOCKS || k == SV_HASH_POSEIDON_BN254; }
 
 static int fail(sv_ctx* c, int code, const char* fmt, ...) {
@@ -77,6 +77,8 @@ extern "C" const char* sv_version(void) { return "stark-verifier_b200 0.1 (sm_10
 
 extern "C" const char* sv_last_error(const sv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
+extern "C" void sv_ctx_destroy(sv_ctx* c);
+
 extern "C" int sv_ctx_create(int device, sv_ctx** out) {
     if (!out) return -1;
     *out = nullptr;
@@ -93,17 +95,25 @@ extern "C" int sv_ctx_create(int device, sv_ctx** out) {
     sv_ctx* c = new sv_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    CK(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < SV_NKS - 1; i++) CK(nullptr, cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));
-    CK(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CK(nullptr, cudaStreamCreateWithFlags(&c->fs_stream, cudaStreamNonBlocking));
-    CK(nullptr, cudaEventCreateWithFlags(&c->ev_hdr, cudaEventDisableTiming));
-    CK(nullptr, cudaEventCreateWithFlags(&c->ev_fs, cudaEventDisableTiming));
-    for (int i = 0; i < SV_NBUF; i++) {
-        CK(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
-        CK(nullptr, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    // on failure the partially built context is torn down again (destroy tolerates null handles)
+    auto init = [&]() -> int {
+        CK(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < SV_NKS - 1; i++) CK(nullptr, cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));
+        CK(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(nullptr, cudaStreamCreateWithFlags(&c->fs_stream, cudaStreamNonBlocking));
+        CK(nullptr, cudaEventCreateWithFlags(&c->ev_hdr, cudaEventDisableTiming));
+        CK(nullptr, cudaEventCreateWithFlags(&c->ev_fs, cudaEventDisableTiming));
+        for (int i = 0; i < SV_NBUF; i++) {
+            CK(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+            CK(nullptr, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        }
+        for (int i = 0; i < SV_NKS; i++) CK(nullptr, cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+        return 0;
+    };
+    if (int rc = init()) {
+        sv_ctx_destroy(c);
+        return rc;
     }
-    for (int i = 0; i < SV_NKS; i++) CK(nullptr, cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     c->stream = c->own_stream;
     *out = c;
     return 0;
@@ -119,14 +129,16 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaFree(c->d_fail);
     cudaFree(c->d_pi);
     cudaFree(c->d_hdr);
-    cudaStreamDestroy(c->fs_stream);
-    cudaEventDestroy(c->ev_hdr); cudaEventDestroy(c->ev_fs);
-    for (int i = 0; i < SV_NBUF; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_done[i]); }
-    for (int i = 0; i < SV_NKS; i++) cudaEventDestroy(c->ev_join[i]);
-    for (auto& pr : c->tev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-    cudaStreamDestroy(c->own_stream);
-    for (int i = 0; i < SV_NKS - 1; i++) cudaStreamDestroy(c->aux_stream[i]);
-    cudaStreamDestroy(c->copy_stream);
+    auto drop_s = [](cudaStream_t s) { if (s) cudaStreamDestroy(s); };
+    auto drop_e = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
+    drop_e(c->ev_hdr); drop_e(c->ev_fs);
+    for (int i = 0; i < SV_NBUF; i++) { drop_e(c->ev_copied[i]); drop_e(c->ev_done[i]); }
+    for (int i = 0; i < SV_NKS; i++) drop_e(c->ev_join[i]);
+    for (auto& pr : c->tev) { drop_e(pr.first); drop_e(pr.second); }
+    drop_s(c->fs_stream);
+    drop_s(c->own_stream);
+    for (int i = 0; i < SV_NKS - 1; i++) drop_s(c->aux_stream[i]);
+    drop_s(c->copy_stream);
     if (c->nccl_lib) dlclose(c->nccl_lib);
     delete c;
 }
@@ -208,6 +220,7 @@ static int grow(sv_ctx* c, T*& ptr, size_t& have, size_t need) {
 extern "C" int sv_poseidon_permute_batch(sv_ctx* c, const uint64_t* in, uint64_t* out, size_t n, int hash_kind, int mem) {
     if (!c || !in || !out) return -1;
     if (!known_kind(hash_kind)) return fail(c, -5, "hash_kind %d not implemented", hash_kind);
+    if (!known_mem(mem)) return fail(c, -5, "mem %d is neither SV_MEM_HOST nor SV_MEM_DEVICE", mem);
     if (n == 0) return 0;
     CK(c, cudaSetDevice(c->device));
     const int B = SVB_BLOCK;
@@ -234,6 +247,7 @@ extern "C" int sv_poseidon_permute_batch(sv_ctx* c, const uint64_t* in, uint64_t
 extern "C" int sv_goldilocks_mul_add_batch(sv_ctx* c, const uint64_t* a, const uint64_t* b, const uint64_t* cc, uint64_t* out,
                                            size_t n, int mem) {
     if (!c || !a || !b || !cc || !out) return -1;
+    if (!known_mem(mem)) return fail(c, -5, "mem %d is neither SV_MEM_HOST nor SV_MEM_DEVICE", mem);
     if (n == 0) return 0;
     CK(c, cudaSetDevice(c->device));
     const int B = 256;
@@ -262,6 +276,7 @@ extern "C" int sv_merkle_verify_batch(sv_ctx* c, uint32_t leaf_len, uint32_t dep
                                       size_t n, int mem) {
     if (!c || !paths || !indices || !caps || !ok) return -1;
     if (!known_kind(hash_kind)) return fail(c, -5, "hash_kind %d not implemented", hash_kind);
+    if (!known_mem(mem)) return fail(c, -5, "mem %d is neither SV_MEM_HOST nor SV_MEM_DEVICE", mem);
     if (leaf_len == 0 || depth > 63 || cap_height > 16 || depth + cap_height > 63) return fail(c, -7, "bad merkle shape");
     if (n == 0) return 0;
     CK(c, cudaSetDevice(c->device));
@@ -302,6 +317,7 @@ extern "C" int sv_merkle_tree_build(sv_ctx* c, int hash_kind, uint32_t leaf_len,
                                     uint32_t cap_height, uint64_t* layers_out, int mem) {
     if (!c || !leaves || !layers_out) return -1;
     if (!known_kind(hash_kind)) return fail(c, -5, "hash_kind %d not implemented", hash_kind);
+    if (!known_mem(mem)) return fail(c, -5, "mem %d is neither SV_MEM_HOST nor SV_MEM_DEVICE", mem);
     if (leaf_len == 0 || n_leaves == 0 || (n_leaves & (n_leaves - 1)) || cap_height > 30 || ((size_t)1 << cap_height) > n_leaves)
         return fail(c, -7, "bad tree shape (n_leaves must be a power of two >= 2^cap_height)");
     CK(c, cudaSetDevice(c->device));
@@ -404,27 +420,14 @@ static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_rec
     return 0;
 }
 
-// fs == nullptr: the records carry their challenges.  Otherwise the transcript runs on the device first
-// (pi_hashes: n_proofs x 4 words, same memory space as the records).
-static int fri_verify_impl(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs, const uint64_t* records,
-                           uint32_t* accept_bitmap, uint32_t* first_fail, int mem, const FsParams* fs, const uint64_t* pi_hashes) {
-    if (!c || !shape || !records || !accept_bitmap) return -1;
-    FriKernelParams P;
-    int rc = make_params(c, *shape, P);
-    if (rc) return rc;
-    if (n_proofs == 0) return 0;
-    if (n_proofs * (size_t)P.num_queries >= (1ull << 31)) return fail(c, -8, "batch too large for one call");
-    CK(c, cudaSetDevice(c->device));
-    size_t rw = P.L.record_words;
-    if (grow(c, c->d_scratch, c->scratch_words, 4 * n_proofs)) return -6;
-
-    if (mem == SV_MEM_DEVICE) {
-        if (fs && (rc = enqueue_challenges(c, P, *fs, n_proofs, const_cast<u64*>(records), pi_hashes, c->stream))) return rc;
-        return enqueue_fri(c, P, n_proofs, records, c->d_scratch, accept_bitmap, first_fail, c->stream);
-    }
+// SV_MEM_HOST leg of sv_fri_verify_batch[_fs]: the chunked H2D / compute pipeline.
+static int fri_verify_host(sv_ctx* c, FriKernelParams& P, size_t n_proofs, const uint64_t* records, uint32_t* accept_bitmap,
+                           uint32_t* first_fail, const FsParams* fs, const uint64_t* pi_hashes) {
+    int rc = 0;
+    const size_t rw = P.L.record_words;
     if (fs && grow(c, c->d_pi, c->pi_words, 4 * n_proofs)) return -6;
 
-    // Host buffers: chunks of whole 32-proof bitmap words move through a ring of SV_NBUF staging
+    // Chunks of whole 32-proof bitmap words move through a ring of SV_NBUF staging
     // buffers.  H2D copies run back to back on the copy stream; the kernels of consecutive chunks
     // rotate over SV_NKS compute streams so that the tail wave of chunk i overlaps the head of
     // chunk i+1 (a chunk is only ~1.5 waves of blocks).  Distinct chunks touch distinct bitmap
@@ -490,6 +493,34 @@ static int fri_verify_impl(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs
     return 0;
 }
 
+// fs == nullptr: the records carry their challenges.  Otherwise the transcript runs on the device first
+// (pi_hashes: n_proofs x 4 words, same memory space as the records).
+static int fri_verify_impl(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs, const uint64_t* records,
+                           uint32_t* accept_bitmap, uint32_t* first_fail, int mem, const FsParams* fs, const uint64_t* pi_hashes) {
+    if (!c || !shape || !records || !accept_bitmap) return -1;
+    if (!known_mem(mem)) return fail(c, -5, "mem %d is neither SV_MEM_HOST nor SV_MEM_DEVICE", mem);
+    FriKernelParams P;
+    int rc = make_params(c, *shape, P);
+    if (rc) return rc;
+    if (n_proofs == 0) return 0;
+    if (n_proofs * (size_t)P.num_queries >= (1ull << 31)) return fail(c, -8, "batch too large for one call");
+    CK(c, cudaSetDevice(c->device));
+    if (grow(c, c->d_scratch, c->scratch_words, 4 * n_proofs)) return -6;
+
+    if (mem == SV_MEM_DEVICE) {
+        if (fs && (rc = enqueue_challenges(c, P, *fs, n_proofs, const_cast<u64*>(records), pi_hashes, c->stream))) return rc;
+        return enqueue_fri(c, P, n_proofs, records, c->d_scratch, accept_bitmap, first_fail, c->stream);
+    }
+    // host buffers: on an error half-way, drain what was already enqueued before the caller may free its buffers
+    rc = fri_verify_host(c, P, n_proofs, records, accept_bitmap, first_fail, fs, pi_hashes);
+    if (rc) {
+        std::string keep = c->err;
+        sv_ctx_synchronize(c);
+        c->err = keep;
+    }
+    return rc;
+}
+
 extern "C" int sv_fri_verify_batch(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs, const uint64_t* records,
                                    uint32_t* accept_bitmap, uint32_t* first_fail, int mem) {
     return fri_verify_impl(c, shape, n_proofs, records, accept_bitmap, first_fail, mem, nullptr, nullptr);
@@ -521,6 +552,7 @@ extern "C" int sv_fri_challenges_batch(sv_ctx* c, const sv_fri_shape* shape, siz
                                        const uint64_t circuit_digest[4], const uint64_t* public_inputs_hashes,
                                        uint32_t num_challenges, int mem) {
     if (!c || !records || !public_inputs_hashes) return -1;
+    if (!known_mem(mem)) return fail(c, -5, "mem %d is neither SV_MEM_HOST nor SV_MEM_DEVICE", mem);
     FsParams F;
     int rc = make_fs(c, shape, circuit_digest, num_challenges, F);
     if (rc) return rc;

@@ -467,6 +467,9 @@ def test_error_convention(svb, ctx):
     s.num_steps = 40                                                 # > SV_MAX_STEPS
     rc = lib.sv_fri_verify_batch(ctx._h, ctypes.byref(s), 2, recs.ctypes.data, out.ctypes.data, None, svb.MEM_HOST)
     assert rc < 0
+    s = params.to_shape()
+    rc = lib.sv_fri_verify_batch(ctx._h, ctypes.byref(s), 2, recs.ctypes.data, out.ctypes.data, None, 5)   # unknown `mem`
+    assert rc < 0 and b"SV_MEM" in lib.sv_last_error(ctx._h)
     with pytest.raises(svb.SvError):
         ctx.merkle_verify_batch(0, 3, 0, np.zeros((1, 16), dtype=np.uint64), np.zeros(1, dtype=np.uint64), np.zeros(4, dtype=np.uint64))
     with pytest.raises(svb.SvError):

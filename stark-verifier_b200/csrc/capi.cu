@@ -114,6 +114,15 @@ extern "C" int sv_ctx_create(int device, sv_ctx** out) {
         sv_ctx_destroy(c);
         return rc;
     }
+    // lab knobs (tools/lab/traffic_probe.sh): prefetch flavour of the Merkle chains, L2 fetch granularity
+    if (const char* e = getenv("SVB_PREFETCH")) {
+        u32 mode = (u32)atoi(e);
+        if (mode <= 2) cudaMemcpyToSymbol(d_PREFETCH_MODE, &mode, sizeof mode);
+    }
+    if (const char* e = getenv("SVB_L2_FETCH")) {
+        int g = atoi(e);
+        if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+    }
     c->stream = c->own_stream;
     *out = c;
     return 0;
@@ -366,12 +375,17 @@ static int make_params(sv_ctx* c, const sv_fri_shape& s, FriKernelParams& P) {
     for (int k = 0; k < 4; k++) P.oracle_num_polys[k] = s.oracle_num_polys[k];
     P.num_zs = s.num_zs;
     P.n_classes = 4 + s.num_steps + 1;
-    // class cost in permutations (algebra ~ 2), heaviest first
+    // grid order of fri_query_kernel: phase A = the four oracle trees, heaviest first (cost in permutations),
+    // then the algebra chain; phase B = the step trees, deepest first
     std::vector<std::pair<u32, u32>> cost;
     for (u32 k = 0; k < 4; k++) cost.push_back({(P.L.leaf_len[k] > 4 ? (P.L.leaf_len[k] + 7) / 8 : 0) + P.L.init_depth, k});
-    for (u32 i = 0; i < s.num_steps; i++) cost.push_back({P.L.step_depth[i], 4 + i});
-    cost.push_back({2, 4 + s.num_steps});
     std::stable_sort(cost.begin(), cost.end(), [](const std::pair<u32, u32>& a, const std::pair<u32, u32>& b) { return a.first > b.first; });
+    cost.push_back({2, 4 + s.num_steps});
+    P.n_classes_a = 5;
+    std::vector<std::pair<u32, u32>> steps;
+    for (u32 i = 0; i < s.num_steps; i++) steps.push_back({P.L.step_depth[i], 4 + i});
+    std::stable_sort(steps.begin(), steps.end(), [](const std::pair<u32, u32>& a, const std::pair<u32, u32>& b) { return a.first > b.first; });
+    cost.insert(cost.end(), steps.begin(), steps.end());
     for (u32 i = 0; i < P.n_classes; i++) P.class_order[i] = cost[i].second;
     u64 omega = svb::pow(7, (GL_P - 1) >> P.L.lde_bits);
     for (u32 i = 0; i < P.L.lde_bits; i++) { P.omega_pow2[i] = omega; omega = mulc(omega, omega); }
@@ -407,9 +421,14 @@ static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_rec
     P.n_proofs = (u32)n;
     P.n_units = (u32)(n * P.num_queries);
     P.blocks_per_class = (P.n_units + B - 1) / B;
+    // phase A unit groups of 32 blocks per class: the 160 blocks of a group are co-resident on the 148 SMs
+    static const u32 group_env = [] { const char* e = getenv("SVB_GROUP_BLOCKS"); return e ? (u32)atoi(e) : 32u; }();
+    P.group_blocks = group_env == 0 || group_env > P.blocks_per_class ? P.blocks_per_class : group_env;   // 0: class-major over the batch
+    P.n_groups = (P.blocks_per_class + P.group_blocks - 1) / P.group_blocks;
     fri_prepare_kernel<<<(unsigned)((n + 31) / 32), SVB_PREP_BLOCK, 0, s>>>(d_records, P, d_scratch, d_bitmap, d_fail);
     cudaEvent_t te = time_begin(c, s);
-    SVB_LAUNCH_KIND(P.hash_kind, fri_query_kernel, P.blocks_per_class * P.n_classes, B, s, d_records, P, d_scratch, d_bitmap, d_fail);
+    const u32 grid = P.n_groups * P.group_blocks * P.n_classes_a + P.blocks_per_class * (P.n_classes - P.n_classes_a);
+    SVB_LAUNCH_KIND(P.hash_kind, fri_query_kernel, grid, B, s, d_records, P, d_scratch, d_bitmap, d_fail);
     time_end(c, te, s);
     c->launches += 2;
     if (d_fail) {

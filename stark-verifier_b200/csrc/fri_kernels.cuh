@@ -42,8 +42,11 @@ struct FriKernelParams {
     u32 n_proofs;
     u32 n_units;          // n_proofs * num_queries
     u32 blocks_per_class; // ceil(n_units / block)
+    u32 group_blocks;     // grid phase A: blocks of one class per unit group (group-major, then class, then block)
+    u32 n_groups;         // ceil(blocks_per_class / group_blocks)
+    u32 n_classes_a;      // classes of phase A: the 4 oracle trees (heaviest first) + the algebra chain
     u32 n_classes;        // 4 + num_steps + 1
-    u32 class_order[SV_MAX_STEPS + 5];  // heaviest first
+    u32 class_order[SV_MAX_STEPS + 5];  // phase A classes, then the step trees (deepest first)
     u64 omega_pow2[40];   // omega^(2^i), omega = 7^((p-1)/2^lde_bits)
 };
 
@@ -65,7 +68,13 @@ SVB_D void ldg4(const u64* p, u64 out[4]) {
 }
 
 // Pull the 32-byte sector at p towards the SM while the current permutation runs (no register cost).
-SVB_D void prefetch32(const u64* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// d_PREFETCH_MODE: 1 = into L1 (default), 2 = into L2 only, 0 = off (lab knob, env SVB_PREFETCH at sv_ctx_create).
+__constant__ u32 d_PREFETCH_MODE = 1;
+SVB_D void prefetch32(const u64* p) {
+    const u32 mode = d_PREFETCH_MODE;
+    if (mode == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    else if (mode == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 SVB_D void report_fail(u32* accept_bitmap, u32* first_fail, u32 proof, u32 query, u32 order_key, u32 code) {
     atomicAnd(&accept_bitmap[proof >> 5], ~(1u << (proof & 31)));
@@ -238,9 +247,25 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) fri_query_ke
                                                         u32* __restrict__ first_fail) {
     __shared__ u64 pscratch[PermScratch<KIND>::words * SVB_BLOCK];
     const sv_fri_layout& L = P.L;
-    u32 cls = P.class_order[blockIdx.x / P.blocks_per_class];
-    u32 unit = (blockIdx.x % P.blocks_per_class) * blockDim.x + threadIdx.x;
-    if (unit >= P.n_units) return;
+    // Grid order.  Phase A: unit groups of `group_blocks` blocks; inside a group the four oracle-tree classes
+    // (heaviest first) and the algebra class over the SAME units, so that the leaf evaluations, which both the
+    // Merkle chain of their tree and the algebra chain read, come from DRAM once and from L2 the second time
+    // (class-major order over the whole batch fetched them twice: tools/lab/NOTES.md).  Phase B: the step
+    // trees, class-major over the whole batch, deepest first -- they share no data with anything, and ending
+    // the grid with the shortest chains keeps the drain of the last wave short.
+    const u32 per_group = P.group_blocks * P.n_classes_a, n_a = P.n_groups * per_group;
+    u32 cls, blk;
+    if (blockIdx.x < n_a) {
+        const u32 grp = blockIdx.x / per_group, in_grp = blockIdx.x - grp * per_group;
+        cls = P.class_order[in_grp / P.group_blocks];
+        blk = grp * P.group_blocks + in_grp % P.group_blocks;
+    } else {
+        const u32 b = blockIdx.x - n_a;
+        cls = P.class_order[P.n_classes_a + b / P.blocks_per_class];
+        blk = b % P.blocks_per_class;
+    }
+    const u32 unit = blk * blockDim.x + threadIdx.x;
+    if (blk >= P.blocks_per_class || unit >= P.n_units) return;
     u32 proof = unit / P.num_queries, query = unit - proof * P.num_queries;
     const u64* rec = records + (size_t)proof * L.record_words;
     const u64* q = rec + L.header_words + (size_t)query * L.query_words;

@@ -118,6 +118,72 @@ SVB_HD void poseidon_g(u64 s[12]) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The circulant MDS layer in the frequency domain, on exact small integers held in binary64.
+// y_i = sum_k CIRC[k] x_{(i+k) mod 12} (+ 8 x_0 on row 0) + rc_i  (poseidon.rs:450-502 computes the same
+// rows directly).  Index i = b + 3a: a 4-point DFT over a (roots 1, i, -1, -i) turns the 12 x 12
+// circulant into three 3 x 3 blocks, one per frequency:
+//     f = 0: [16 16 32; 32 16 16; 16 32 16] * 4     f = 2: [-1 -2 8; -8 -1 -2; 2 -8 -1] * 4
+//     f = 1: [2+i 1+16i 1-4i; -4-i 2+i 1+16i; 16-i -4-i 2+i] * 2      (f = 3 is its conjugate)
+// and the factors 4, 4, 2 are exactly what the inverse DFT divides by, so everything stays an integer
+// (the reason plonky2 chose this MDS vector).  90 additions / FMAs instead of 144 + nothing for rc.
+// Inputs < 2^32 give |intermediates| < 2^41: exact in binary64, also for subnormal operands (the device
+// feeds u32 bit patterns, i.e. multiples of 2^-1074, and reads the result bits back as the integer).
+// RC = 12 adds rc[0..11] to the rows, RC = 1 adds rc[0] to row 0 only, RC = 0 adds nothing.  An all-zero
+// input comes out as +0 in every row, never -0 (16 * (+0) + (+-0) = +0 in round-to-nearest), so the result
+// bits are the integer in all cases.
+SVB_HD double svb_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+template <int RC>
+SVB_HD void mds_freq_half(const double x[12], const double* rc, double y[12]) {
+    double U0[3], U2[3], Ur[3], Ui[3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int b = 0; b < 3; b++) {
+        const double s02 = x[b] + x[b + 6], s13 = x[b + 3] + x[b + 9];
+        U0[b] = s02 + s13;
+        U2[b] = s02 - s13;
+        Ur[b] = x[b] - x[b + 6];
+        Ui[b] = x[b + 3] - x[b + 9];
+    }
+    const double S = (U0[0] + U0[1]) + U0[2];
+    const double T[3] = {S + U0[2], S + U0[0], S + U0[1]};                 // A_b = 16 T_b
+    const double B[3] = {svb_fma(8.0, U2[2], svb_fma(-2.0, U2[1], -U2[0])),
+                         svb_fma(-8.0, U2[0], svb_fma(-2.0, U2[2], -U2[1])),
+                         svb_fma(2.0, U2[0], svb_fma(-8.0, U2[1], -U2[2]))};
+    const double R[3] = {svb_fma(4.0, Ui[2], svb_fma(-16.0, Ui[1], svb_fma(2.0, Ur[0], (Ur[1] + Ur[2]) - Ui[0]))),
+                         svb_fma(-16.0, Ui[2], svb_fma(2.0, Ur[1], svb_fma(-4.0, Ur[0], (Ui[0] - Ui[1]) + Ur[2]))),
+                         svb_fma(2.0, Ur[2], svb_fma(-4.0, Ur[1], svb_fma(16.0, Ur[0], (Ui[0] + Ui[1]) - Ui[2])))};
+    const double I[3] = {svb_fma(-4.0, Ur[2], svb_fma(16.0, Ur[1], svb_fma(2.0, Ui[0], (Ur[0] + Ui[1]) + Ui[2]))),
+                         svb_fma(16.0, Ur[2], svb_fma(2.0, Ui[1], svb_fma(-4.0, Ui[0], (Ur[1] - Ur[0]) + Ui[2]))),
+                         svb_fma(2.0, Ui[2], svb_fma(-4.0, Ui[1], svb_fma(16.0, Ui[0], (Ur[2] - Ur[0]) - Ur[1])))};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int b = 0; b < 3; b++) {
+        const double P = svb_fma(16.0, T[b], B[b]), Q = svb_fma(16.0, T[b], -B[b]);
+        double y0 = P + R[b];
+        if (b == 0) y0 = svb_fma(8.0, x[0], y0);                            // MDS_MATRIX_DIAG[0]
+        if (RC == 12) {
+            y[b] = y0 + rc[b];
+            y[b + 3] = (Q + I[b]) + rc[b + 3];
+            y[b + 6] = (P - R[b]) + rc[b + 6];
+            y[b + 9] = (Q - I[b]) + rc[b + 9];
+        } else {
+            y[b] = (RC == 1 && b == 0) ? y0 + rc[0] : y0;
+            y[b + 3] = Q + I[b];
+            y[b + 6] = P - R[b];
+            y[b + 9] = Q - I[b];
+        }
+    }
+}
+
 #if defined(__CUDACC__)
 // ================================================================================================
 // Device path (sm_100a).  What the measurements on B200 said (profiles/, tools/lab/NOTES.md):
@@ -129,7 +195,7 @@ SVB_HD void poseidon_g(u64 s[12]) {
 //    only partially, so every instruction counts: a modular multiplication is 14 instructions
 //    (goldilocks.cuh), dot products keep unreduced limbs (5.5 instructions per term), and the MDS layers
 //    run as exact integer arithmetic on the otherwise idle FP64 pipe, fed with subnormals so that no
-//    int<->double conversion is needed.
+//    int<->double conversion is needed, in the frequency domain (90 instead of 144 operations per half).
 // ================================================================================================
 // The MDS layer on the FP64 pipe.  Measured on B200 (tools/microbench/pipes.cu): IMAD.WIDE.U32 holds
 // the fmaheavy pipe 4 cycles per warp instruction and the S-boxes already saturate it; DFMA issues
@@ -152,7 +218,47 @@ SVB_D double u32_to_f64(u32 x) { return __uint2double_rn(x); }
 #else
 SVB_D double u32_to_f64(u32 x) { return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0; }
 #endif
-SVB_D void mds_layer_rc_f64(u64 s[12], const u64* __restrict__ rcf /* FULL_RC_NEXT_F64: 2 words per row */) {
+// V = al + ah * 2^32 with al, ah < 2^42 (the two half-sums of one row) -> LOOSE u64
+SVB_D u64 mds_recombine(u32 al0, u32 al1, u32 ah0, u32 ah1) {
+    // V = v0 + v1 W + v2 W^2 (v2 < 2^11); result = v2*EPS + (v1:v0) + cy*EPS
+    u32 lo, hi;
+    asm("{\n\t.reg .u32 x1, v1, v2, t0, t1, cy, h2;\n\t"
+#if SVB_MDS_CVT == 2
+        "add.cc.u32 v1, %3, %4;\n\t addc.u32 v2, %5, 0;\n\t"
+#else
+        "sub.u32 x1, %3, 0x43300000;\n\t"
+        "add.cc.u32 v1, x1, %4;\n\t addc.u32 v2, %5, 0xBCD00000;\n\t"
+#endif
+        "mad.lo.cc.u32 t0, v2, %6, %2;\n\t madc.hi.cc.u32 t1, v2, %6, v1;\n\t addc.u32 cy, 0, 0;\n\t"
+        "sub.cc.u32 %0, t0, cy;\n\t subc.u32 h2, t1, 0;\n\t add.u32 %1, h2, cy;\n\t"
+        "}" : "=r"(lo), "=r"(hi) : "r"(al0), "r"(al1), "r"(ah0), "r"(ah1), "r"(d_EPS32));
+    return ((u64)hi << 32) | lo;
+}
+#ifndef SVB_MDS_FFT
+#define SVB_MDS_FFT 1   // 1: frequency-domain form (mds_freq_half: 180 FP64 operations per layer, +3.3 % perms/s); 0: 288 DFMA
+#endif
+#if SVB_MDS_FFT && SVB_MDS_CVT != 2
+#error "SVB_MDS_FFT needs the subnormal operand form (SVB_MDS_CVT == 2)"
+#endif
+SVB_D void mds_layer_rc_f64(u64 s[12], const u64* __restrict__ rcf /* FULL_RC_NEXT_{F64,SUBNORMAL}: 2 words per row */) {
+#if SVB_MDS_FFT
+    double x[12], rc[12], yl[12], yh[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        x[j] = u32_to_f64((u32)s[j]);
+        rc[j] = __longlong_as_double((long long)rcf[2 * j]);
+    }
+    mds_freq_half<12>(x, rc, yl);
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        x[j] = u32_to_f64((u32)(s[j] >> 32));
+        rc[j] = __longlong_as_double((long long)rcf[2 * j + 1]);
+    }
+    mds_freq_half<12>(x, rc, yh);
+#pragma unroll
+    for (int r = 0; r < 12; r++)
+        s[r] = mds_recombine((u32)__double2loint(yl[r]), (u32)__double2hiint(yl[r]), (u32)__double2loint(yh[r]), (u32)__double2hiint(yh[r]));
+#else
     double d[12];
     u32 h[12];
     u32 al0[12], al1[12];
@@ -163,11 +269,7 @@ SVB_D void mds_layer_rc_f64(u64 s[12], const u64* __restrict__ rcf /* FULL_RC_NE
     }
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-#if SVB_MDS_CVT == 2
-        double acc = __longlong_as_double((long long)rcf[2 * r]);       // FULL_RC_NEXT_SUBNORMAL: the integer itself
-#else
-        double acc = __longlong_as_double((long long)rcf[2 * r]);
-#endif
+        double acc = __longlong_as_double((long long)rcf[2 * r]);       // the starting value carries the round constant
 #pragma unroll
         for (int j = 0; j < 12; j++) acc = __fma_rn(d[j], (double)mds_coeff(r, j), acc);
         al0[r] = (u32)__double2loint(acc);
@@ -177,28 +279,12 @@ SVB_D void mds_layer_rc_f64(u64 s[12], const u64* __restrict__ rcf /* FULL_RC_NE
     for (int j = 0; j < 12; j++) d[j] = u32_to_f64(h[j]);
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-#if SVB_MDS_CVT == 2
         double acc = __longlong_as_double((long long)rcf[2 * r + 1]);
-#else
-        double acc = __longlong_as_double((long long)rcf[2 * r + 1]);
-#endif
 #pragma unroll
         for (int j = 0; j < 12; j++) acc = __fma_rn(d[j], (double)mds_coeff(r, j), acc);
-        u32 ah0 = (u32)__double2loint(acc), ah1 = (u32)__double2hiint(acc);
-        // V = al + ah*W = v0 + v1 W + v2 W^2 (v2 < 2^11); result = v2*EPS + (v1:v0) + cy*EPS
-        u32 lo, hi;
-        asm("{\n\t.reg .u32 x1, v1, v2, t0, t1, cy, h2;\n\t"
-#if SVB_MDS_CVT == 2
-            "add.cc.u32 v1, %3, %4;\n\t addc.u32 v2, %5, 0;\n\t"
-#else
-            "sub.u32 x1, %3, 0x43300000;\n\t"
-            "add.cc.u32 v1, x1, %4;\n\t addc.u32 v2, %5, 0xBCD00000;\n\t"
-#endif
-            "mad.lo.cc.u32 t0, v2, %6, %2;\n\t madc.hi.cc.u32 t1, v2, %6, v1;\n\t addc.u32 cy, 0, 0;\n\t"
-            "sub.cc.u32 %0, t0, cy;\n\t subc.u32 h2, t1, 0;\n\t add.u32 %1, h2, cy;\n\t"
-            "}" : "=r"(lo), "=r"(hi) : "r"(al0[r]), "r"(al1[r]), "r"(ah0), "r"(ah1), "r"(d_EPS32));
-        s[r] = ((u64)hi << 32) | lo;
+        s[r] = mds_recombine(al0[r], al1[r], (u32)__double2loint(acc), (u32)__double2hiint(acc));
     }
+#endif
 }
 
 // Unreduced sum of up to 16 products of 64-bit words: E = e0..e4 collects x0*y0 (weight 1) and x1*y1
@@ -263,8 +349,79 @@ SVB_D void rot_lanes(u64 s[12]) {
 // FOLLOWS full round f: f = 0..2 -> ALL_ROUND_CONSTANTS of round f+1, f = 3 ->
 // FAST_PARTIAL_FIRST_ROUND_CONSTANT, f = 4..6 -> rounds 27..29, f = 7 -> 0.
 
+// SVB_PARTIAL_NAIVE = 1: the 22 partial rounds in the NAIVE form of the permutation (constant layer, x^7 on
+// lane 0, full MDS -- poseidon_spec/constants.rs:7-443 with the rounds of poseidon.rs:634-686 before the
+// sparse-matrix optimisation; the two forms are the same function, pinned by the known-answer tests).
+// On a CPU the sparse form wins (22 multiplications instead of 144 per round); here the dense MDS costs
+// 180 operations on the otherwise idle FP64 pipe, while the sparse form costs 120 IMAD.WIDE on the pipe
+// that binds: the naive form HALVES the multiplier load of a permutation (5 198 -> 2 7xx IMAD.WIDE) and
+// needs no initial matrix and no scratch.  Measured on B200: 1 206 -> 1 394 M perms/s.  Two refinements:
+//  * lanes 1..11 see no S-box in rounds 4..25, so their round constants commute with the S-box layer and are
+//    pushed through the linear MDS into the next round (tools/gen_poseidon_constants.py derives d_r): a
+//    partial round adds ONE scalar, to lane 0 (NAIVE_LANE0_RC), and the accumulated vector d_26 is added
+//    once before round 26 (NAIVE_PRE_ROUND26);
+//  * the partial rounds run as 11 DOUBLE layers: after the first MDS only lane 0 is recombined and reduced
+//    (it feeds the next S-box); lanes 1..11 stay as their two exact half-sums (< 2^41) and go straight
+//    into the second MDS, whose sums (< 2^49) are still exact in binary64.  That removes 11 of every 24
+//    recombinations (one IMAD.WIDE + 8 add/sub each) and the matching integer -> double operand moves.
+#ifndef SVB_PARTIAL_NAIVE
+#define SVB_PARTIAL_NAIVE 1
+#endif
+#if SVB_PARTIAL_NAIVE && !(SVB_MDS_CVT == 2 && SVB_MDS_FFT)
+#error "SVB_PARTIAL_NAIVE needs the subnormal, frequency-domain MDS (SVB_MDS_CVT == 2, SVB_MDS_FFT == 1)"
+#endif
+SVB_D u64 mds_recombine_d(double yl, double yh) {
+    return mds_recombine((u32)__double2loint(yl), (u32)__double2hiint(yl), (u32)__double2loint(yh), (u32)__double2hiint(yh));
+}
+
 SVB_D void poseidon_g_dev(u64 s[12], u64* __restrict__ scratch /* 11 words of per-thread shared memory, stride blockDim.x */,
                       u32 scratch_stride) {
+#if SVB_PARTIAL_NAIVE
+    (void)scratch; (void)scratch_stride;
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+        // constants of round 0 (poseidon.rs:637-640) / accumulated constants d_26 of round 26
+        const u64* __restrict__ pre = phase ? d_NAIVE_PRE_ROUND26 : d_ALL_ROUND_CONSTANTS;
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = add_lc(s[i], pre[i]);
+        // four full rounds: S-box layer, MDS + constants of the next round (:641-650, :675-684)
+#pragma unroll 1
+        for (int f = 0; f < 4; f++) {
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+            mds_layer_rc_f64(s, d_NAIVE_FULL_RC_NEXT_SUBNORMAL + 24 * (4 * phase + f));
+        }
+        if (phase == 0) {
+            // rounds 4..25 as 11 double layers
+#pragma unroll 1
+            for (int k = 0; k < 11; k++) {
+                const u64* __restrict__ l0 = d_NAIVE_LANE0_RC_SUBNORMAL + 4 * k;
+                double x[12], yl[12], yh[12], rc;
+                s[0] = sbox7(s[0]);
+#pragma unroll
+                for (int j = 0; j < 12; j++) x[j] = u32_to_f64((u32)s[j]);
+                rc = __longlong_as_double((long long)l0[0]);
+                mds_freq_half<1>(x, &rc, yl);
+#pragma unroll
+                for (int j = 0; j < 12; j++) x[j] = u32_to_f64((u32)(s[j] >> 32));
+                rc = __longlong_as_double((long long)l0[1]);
+                mds_freq_half<1>(x, &rc, yh);
+                const u64 s0 = sbox7(mds_recombine_d(yl[0], yh[0]));
+                yl[0] = u32_to_f64((u32)s0);
+                yh[0] = u32_to_f64((u32)(s0 >> 32));
+                rc = __longlong_as_double((long long)l0[2]);
+                mds_freq_half<1>(yl, &rc, x);
+#pragma unroll
+                for (int j = 0; j < 12; j++) yl[j] = x[j];
+                rc = __longlong_as_double((long long)l0[3]);
+                mds_freq_half<1>(yh, &rc, x);
+#pragma unroll
+                for (int j = 0; j < 12; j++) s[j] = mds_recombine_d(yl[j], x[j]);
+            }
+        }
+    }
+    return;
+#else
     // round constants of round 0 (poseidon.rs:637-640); later constants ride on the MDS accumulators
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = add_lc(s[i], d_ALL_ROUND_CONSTANTS[i]);
@@ -345,6 +502,7 @@ SVB_D void poseidon_g_dev(u64 s[12], u64* __restrict__ scratch /* 11 words of pe
             for (int i = 0; i < 12; i++) s[i] = add_lc(s[i], d_ALL_ROUND_CONSTANTS[12 * 26 + i]);
         }
     }
+#endif   // SVB_PARTIAL_NAIVE
 }
 #endif
 

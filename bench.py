@@ -124,6 +124,21 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+PERM_INSTR, PERM_WIDE, PERM_FP64 = 14579, 2603, 4916
+
+
+def issue_roofline(perms_per_s, sm_mhz):
+    """Ceilings of the permutation-bound kernels on one B200 (148 SMs x 4 sub-partitions x 32 lanes) at the SM
+    clock seen during the run: instruction issue, the 32x32->64 multiplier pipe and the FP64 pipe."""
+    lanes = 148 * 4 * 32 * sm_mhz * 1e6
+    ceil = {"issue": lanes / PERM_INSTR, "int_mul": lanes / 4.24 / PERM_WIDE, "fp64": lanes / 2.18 / PERM_FP64}
+    bound = min(ceil, key=ceil.get)
+    return {"bound": bound, "achieved": perms_per_s / 1e9, "peak": ceil[bound] / 1e9, "unit": "1e9 permutations/s",
+            "frac": perms_per_s / ceil[bound], "frac_int_mul": perms_per_s / ceil["int_mul"], "frac_fp64": perms_per_s / ceil["fp64"],
+            "warp_instr_per_perm": PERM_INSTR, "imad_wide_per_perm": PERM_WIDE, "fp64_ops_per_perm": PERM_FP64,
+            "kernel": "fri_query_kernel"}
+
+
 def workload_params(svb, name):
     return {"A": svb.SHAPE_A, "B": svb.SHAPE_B, "outer": svb.SHAPE_OUTER_BN254}[name]
 
@@ -392,13 +407,11 @@ def main():
                      "peak_source": peak_src,
                      "note": "integer-issue bound, not HBM bound (SURVEY 8d): see perms_per_sec"},
         "perms_per_sec": world * perms * args.steps / (ms / 1e3),
-        # what actually binds: the 32x32->64 integer multiplier.  IMAD.WIDE issues every
-        # 4.24 cycles per SM sub-partition (profiles/pipes2_b200_r1.txt); a permutation needs 4 308
-        # of them algorithmically (1 077 modular multiplications x 4 limb products).
-        "int_mul_roofline": None if params.hash_kind else {"achieved_gmul_s": perms * 4308 / k_avg_s / 1e9,
-                             "peak_gmul_s": 148 * 4 * 32 / 4.24 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
-                             "frac": (perms * 4308 / k_avg_s) / (148 * 4 * 32 / 4.24 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
-                             "unit": "1e9 32x32->64 multiplies/s", "kernel": "fri_query_kernel"},
+        # what actually binds: instruction issue.  One Poseidon-Goldilocks permutation executes
+        # PERM_INSTR warp-instructions (tools/sass_dyn.py on the shipped library, profiles/sass_dyn_r1_v10.txt), of
+        # which PERM_WIDE IMAD.WIDE.U32 (4.24 cycles each on the multiplier pipe, profiles/pipes2_b200_r1.txt) and
+        # PERM_FP64 DADD/DFMA (2.18 cycles each); a sub-partition issues at most one warp-instruction per cycle.
+        "issue_roofline": None if params.hash_kind else issue_roofline(perms / k_avg_s, clocks.get("sm_mhz") or 1965.0),
         "synth_seconds": t_gen,
     }
     if not args.no_cpu_baseline:
@@ -477,6 +490,8 @@ def bench_merkle(args, svb, torch, dist, rank, local_rank, world):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "merkle_verify_kernel", "kernel_ms": kernel_ms / kernel_n,
                          "algorithmic_bytes_per_launch": int(algo), "peak_source": peak_src},
+            "issue_roofline": dict(issue_roofline(n * depth / (kernel_ms / kernel_n / 1e3), clocks.get("sm_mhz") or 1965.0),
+                                   kernel="merkle_verify_kernel"),
         }))
 
 

@@ -29,7 +29,7 @@ namespace svb {
 
 #define SVB_BLOCK 128   // threads per block of every kernel; also the stride of the per-thread smem scratch
 #ifndef SVB_MINBLOCKS
-#define SVB_MINBLOCKS 4  // __launch_bounds__ second argument of the Poseidon-Goldilocks kernels (register cap = 65536 / (128 * N)); measured best
+#define SVB_MINBLOCKS 6  // __launch_bounds__ second argument of the Poseidon-Goldilocks kernels (register cap = 65536 / (128 * N) = 80): measured 4 -> 423.7 k, 5 -> 429.1 k, 6 -> 432.1 k proofs/s
 #endif
 // Poseidon-BN254 kernels want ~130 registers: capping them at 126 costs 6 % (spills), so they keep 3 blocks per SM
 #define SVB_MINBLOCKS_K(KIND) ((KIND) == SV_HASH_POSEIDON_BN254 ? 3 : SVB_MINBLOCKS)
@@ -50,9 +50,13 @@ struct FriKernelParams {
     u64 omega_pow2[40];   // omega^(2^i), omega = 7^((p-1)/2^lde_bits)
 };
 
-// Shared-memory scratch of one permutation, in u64 words per thread: Poseidon-Goldilocks stages the 11
-// outputs of the initial matrix, Poseidon-BN254 its whole 5 x 8-limb state.
-template <int KIND> struct PermScratch { static constexpr int words = KIND == SV_HASH_POSEIDON_BN254 ? SVB_B_SMEM_WORDS / 2 : 11; };
+// Shared-memory scratch of one permutation, in u64 words per thread: Poseidon-BN254 stages its whole 5 x 8-limb
+// state; Poseidon-Goldilocks needs none in the naive-round form (11 words for the outputs of the initial matrix in
+// the sparse form, SVB_PARTIAL_NAIVE = 0).
+template <int KIND> struct PermScratch {
+    static constexpr int words = KIND == SV_HASH_POSEIDON_BN254 ? SVB_B_SMEM_WORDS / 2 : (SVB_PARTIAL_NAIVE ? 0 : 11);
+    static constexpr int array_len(int threads) { return words ? words * threads : 1; }   // a zero-length array is not allowed
+};
 // The width-12 permutation of hash family KIND on `s` (LOOSE in; G leaves LOOSE words, B canonical ones).
 // scratch: base of the block's shared array, stride = threads per block.
 template <int KIND>
@@ -245,7 +249,7 @@ template <int KIND>
 __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) fri_query_kernel(const u64* __restrict__ records, FriKernelParams P,
                                                         const u64* __restrict__ scratch, u32* __restrict__ accept_bitmap,
                                                         u32* __restrict__ first_fail) {
-    __shared__ u64 pscratch[PermScratch<KIND>::words * SVB_BLOCK];
+    __shared__ u64 pscratch[PermScratch<KIND>::array_len(SVB_BLOCK)];
     const sv_fri_layout& L = P.L;
     // Grid order.  Phase A: unit groups of `group_blocks` blocks; inside a group the four oracle-tree classes
     // (heaviest first) and the algebra class over the SAME units, so that the leaf evaluations, which both the
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) fri_query_ke
 // n independent permutations, thread per state (canonical in / out).
 template <int KIND>
 __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) poseidon_permute_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
-    __shared__ u64 scratch[PermScratch<KIND>::words * SVB_BLOCK];
+    __shared__ u64 scratch[PermScratch<KIND>::array_len(SVB_BLOCK)];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     u64 s[12];
@@ -376,7 +380,7 @@ template <int KIND>
 __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) merkle_verify_kernel(const u64* __restrict__ paths, const u64* __restrict__ indices,
                                                             const u64* __restrict__ caps, unsigned char* __restrict__ ok,
                                                             size_t n, u32 leaf_len, u32 depth, u32 cap_height) {
-    __shared__ u64 scratch[PermScratch<KIND>::words * SVB_BLOCK];
+    __shared__ u64 scratch[PermScratch<KIND>::array_len(SVB_BLOCK)];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     u32 leaf_words = up4(leaf_len);
@@ -450,7 +454,7 @@ struct DevChallenger {
 template <int KIND>
 __global__ void __launch_bounds__(SVB_FS_BLOCK) fri_challenges_kernel(u64* __restrict__ records, FriKernelParams P, FsParams F,
                                                                       const u64* __restrict__ pi_hashes) {
-    __shared__ u64 pscratch[PermScratch<KIND>::words * SVB_FS_BLOCK];
+    __shared__ u64 pscratch[PermScratch<KIND>::array_len(SVB_FS_BLOCK)];
     u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_proofs) return;
     const sv_fri_layout& L = P.L;
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(128) fri_challenges_coop_kernel(u64* __restric
 template <int KIND>
 __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) merkle_leaf_hash_kernel(const u64* __restrict__ leaves, u32 leaf_len,
                                                                                     size_t n, u64* __restrict__ digests) {
-    __shared__ u64 scratch[PermScratch<KIND>::words * SVB_BLOCK];
+    __shared__ u64 scratch[PermScratch<KIND>::array_len(SVB_BLOCK)];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u64* leaf = leaves + i * (size_t)leaf_len;
@@ -590,7 +594,7 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) merkle_leaf_
 template <int KIND>
 __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) merkle_level_kernel(const u64* __restrict__ children, u64* __restrict__ parents,
                                                                                 size_t n_parents) {
-    __shared__ u64 scratch[PermScratch<KIND>::words * SVB_BLOCK];
+    __shared__ u64 scratch[PermScratch<KIND>::array_len(SVB_BLOCK)];
     size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (j >= n_parents) return;
     u64 s[12];

@@ -11,7 +11,7 @@ using namespace svb;
 
 // chain of `depth` dependent permutations per thread (Merkle-like: no memory traffic in the loop)
 __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS) chain_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n, int depth) {
-    __shared__ u64 scratch[PermScratch<LAB_KIND>::words * SVB_BLOCK];
+    __shared__ u64 scratch[PermScratch<LAB_KIND>::array_len(SVB_BLOCK)];
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     u64 s[12];

@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the cpu_baseline sample (default: sized for ~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-wire", action="store_true", help="skip the serialised-proof leg of e2e")
     ap.add_argument("--device-transcript", action="store_true",
                     help="derive the Fiat-Shamir challenges on the device too (sv_fri_verify_batch_fs): the records "
                          "enter with their challenge fields zeroed")
@@ -203,6 +204,53 @@ def run_reference(args):
     }))
 
 
+def wire_leg(svb, torch, ctx, params, L, n_host, distinct, seed, threads, steps):
+    """e2e from plonky2 wire bytes: `distinct` proofs bound to hash(public inputs), serialised, tiled into a pinned
+    host buffer, 1/64 corrupted (one sibling byte), verified through sv_verify_proofs_wire."""
+    import ctypes
+    n_pi = 4
+    common = svb.CommonData.for_params(params, num_public_inputs=n_pi)
+    rng = np.random.default_rng(99)
+    pis = rng.integers(0, 0xFFFFFFFF00000001, size=(distinct, n_pi), dtype=np.uint64)
+    pih = np.stack([svb.public_inputs_hash(pis[i]) for i in range(distinct)])
+    recs = svb.synth_proofs(params, distinct, seed=seed ^ 0x77, n_circuits=1, nthreads=threads, pi_hashes=pih)
+    cds, _ = svb.synth_public_inputs(params, distinct, seed=seed ^ 0x77, n_circuits=1)
+    vk_cap = recs[0, L.off_init_caps:L.off_init_caps + 4 * L.ncap].copy()
+    blob = svb.wire_pack(common, recs, pis)
+    nb = blob.shape[1]
+    p = ctypes.c_void_p()
+    if svb.lib().sv_host_alloc(n_host * nb, ctypes.byref(p)) != 0:
+        raise RuntimeError("sv_host_alloc failed")
+    try:
+        host = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(n_host, nb))
+        for i in range(0, n_host, distinct):
+            c = min(distinct, n_host - i)
+            host[i:i + c] = blob[:c]
+        q0 = 3 * 32 * L.ncap + 16 * (L.n0 + L.n1) + len(params.reduction_arity_bits) * 32 * L.ncap
+        exp = np.full((n_host + 31) // 32, 0xFFFFFFFF, dtype=np.uint32)
+        if n_host & 31:
+            exp[-1] = np.uint32((1 << (n_host & 31)) - 1)
+        for i in range(32, n_host, 64):
+            host[i, q0 + 8 * L.leaf_len[0] + 1 + 7] ^= 1        # a sibling of oracle 0, query round 0
+            exp[i >> 5] &= np.uint32(~(1 << (i & 31)) & 0xFFFFFFFF)
+        for _ in range(2):
+            bm = ctx.verify_proofs_wire(common, vk_cap, cds[0], p.value, n_proofs=n_host)
+        if not (bm == exp).all():
+            raise RuntimeError("accept bitmap of the wire leg differs from the expected pattern")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.verify_proofs_wire(common, vk_cap, cds[0], p.value, n_proofs=n_host)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    finally:
+        svb.lib().sv_host_free(p)
+    return {"value": n_host * steps / dt, "unit": "proofs/s", "h2d_bytes_per_step": int(n_host * nb),
+            "d2h_bytes_per_step": int(exp.size * 4), "steps": steps, "proof_bytes": int(nb), "public_inputs": n_pi,
+            "note": "sv_verify_proofs_wire: pinned plonky2 wire bytes -> H2D -> wire_unpack_kernel + wire_pi_hash_kernel -> "
+                    "device transcript -> fri_query_kernel, per 32 MiB chunk"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -366,6 +414,14 @@ def main():
                "h2d_only_proofs_per_s": world * n_host / h2d_s,
                "note": "sv_fri_verify_batch(SV_MEM_HOST) from pinned host records, chunked H2D overlapped with kernels; "
                        "h2d_only_* = the same bytes copied with no compute (the PCIe ceiling of this leg)"}
+
+    # the same leg from SERIALISED proofs (plonky2 wire bytes, pinned): H2D of the bytes, device unpack, public-input
+    # hashes, device transcript, query phase (sv_verify_proofs_wire).  1 GPU only; a failure is reported, not fatal.
+    if e2e is not None and world == 1 and not args.no_wire:
+        try:
+            e2e["wire"] = wire_leg(svb, torch, ctx, params, L, n_host, distinct, seed, threads, max(2, min(args.steps, 10)))
+        except Exception as ex:   # noqa: BLE001
+            e2e["wire"] = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank != 0:
         if world > 1:

@@ -200,11 +200,89 @@ int sv_fri_challenges(const sv_fri_shape* shape, uint64_t* record, const uint64_
 int sv_synth_proofs(const sv_fri_shape* shape, uint64_t seed, uint32_t n_circuits, size_t n_proofs,
                     uint32_t num_challenges, uint64_t* records_out, int nthreads);
 
+/* The same, with the public-inputs hash of every proof given by the caller (pi_hashes: n_proofs x 4 canonical words;
+ * NULL = drawn from the seed like sv_synth_proofs), e.g. the hashes of public inputs that travel with the proofs in
+ * the wire format. */
+int sv_synth_proofs_pi(const sv_fri_shape* shape, uint64_t seed, uint32_t n_circuits, size_t n_proofs,
+                       uint32_t num_challenges, const uint64_t* pi_hashes, uint64_t* records_out, int nthreads);
+
 /* The transcript inputs sv_synth_proofs used for the same (shape, seed, n_circuits, n_proofs):
  * circuit_digests_out: n_circuits x 4 words (proof i belongs to circuit i % n_circuits),
  * pi_hashes_out: n_proofs x 4 words.  Either pointer may be NULL. */
 int sv_synth_public_inputs(const sv_fri_shape* shape, uint64_t seed, uint32_t n_circuits, size_t n_proofs,
                            uint64_t* circuit_digests_out, uint64_t* pi_hashes_out);
+
+/* --- wire format: plonky2 proof bytes -> flat records ---------------------------- */
+/* The CommonCircuitData / CircuitConfig fields plonky2's `ProofWithPublicInputs::from_bytes(bytes, common_data)`
+ * reads the vector lengths from (reference mirror: CommonData, types/common_data.rs:84-123; CircuitConfig :23-40). */
+typedef struct sv_plonk_common {
+    uint32_t num_constants;          /* CommonData.num_constants */
+    uint32_t num_routed_wires;       /* CircuitConfig.num_routed_wires (= number of sigma polynomials) */
+    uint32_t num_wires;              /* CircuitConfig.num_wires */
+    uint32_t num_challenges;         /* CircuitConfig.num_challenges */
+    uint32_t num_partial_products;   /* CommonData.num_partial_products */
+    uint32_t quotient_degree_factor; /* CommonData.quotient_degree_factor */
+    uint32_t num_public_inputs;      /* CommonData.num_public_inputs */
+} sv_plonk_common;
+
+/* first_fail code of a proof whose bytes do not parse (a Merkle-proof length byte that disagrees with the
+ * shape); plonky2 would fail in from_bytes / verify_merkle_proof before any arithmetic */
+#define SV_FAIL_MALFORMED 8
+
+/* FriParams/FriConfig + CommonData -> sv_fri_shape: the oracle widths and blinding flags of
+ * CommonData::fri_oracles (types/common_data.rs:195-221; blinding = PlonkOracle consts :101-123), batch 1 =
+ * fri_zs_polys (:176-178), final_poly_len = 2^(degree_bits - num_steps) (arity-2 reduction throughout). */
+int sv_fri_shape_from_common(const sv_plonk_common* common, uint32_t degree_bits, uint32_t rate_bits, uint32_t cap_height,
+                             uint32_t num_query_rounds, uint32_t proof_of_work_bits, uint32_t num_steps, uint32_t hiding,
+                             uint32_t hash_kind, sv_fri_shape* out);
+
+/* Length in bytes of one serialised ProofWithPublicInputs of this shape (every proof of one circuit has the same
+ * length); 0 if shape and common disagree.  Layout (plonky2 @ the revision Cargo.lock pins, util/serialization.rs,
+ * write_proof_with_public_inputs; every field element a little-endian u64, a hash 4 of them, an extension element 2,
+ * no length prefixes except one u8 per Merkle proof):
+ *   wires_cap, plonk_zs_partial_products_cap, quotient_polys_cap              3 x 2^cap_height x 32 B
+ *   openings: constants, plonk_sigmas, wires, plonk_zs, plonk_zs_next, partial_products, quotient_polys   (x 16 B)
+ *   commit_phase_merkle_caps                                                   num_steps x 2^cap_height x 32 B
+ *   per query round: 4 x (leaf evals x 8 B, u8 n, n x 32 B siblings); per step (2 x 16 B evals, u8 n, n x 32 B)
+ *   final_poly coefficients x 16 B, pow_witness 8 B, public inputs x 8 B
+ * Mirrors the field order of ProofValues / OpeningSetValues / FriProofValues (types/proof.rs:34-43,143-160,380-387). */
+size_t sv_wire_proof_bytes(const sv_fri_shape* shape, const sv_plonk_common* common);
+
+/* Host: record (+ public inputs) -> wire bytes; the inverse of sv_wire_unpack_batch, for fixtures, tests and the bench.
+ * The challenge fields of the record are not part of the wire format.  bytes_out: sv_wire_proof_bytes bytes. */
+int sv_wire_pack(const sv_fri_shape* shape, const sv_plonk_common* common, const uint64_t* record,
+                 const uint64_t* public_inputs, uint8_t* bytes_out);
+
+/* Host (CPU threads): n proofs at blob + i * stride_bytes -> records (challenge fields and padding zeroed, init_caps[0]
+ * = constants_sigmas_cap of the verifier key, 2^cap_height x 4 words), the Poseidon-Goldilocks hash of each proof's
+ * public inputs (PlonkVerifierChip::get_public_inputs_hash, plonk_verifier_chip.rs:41-53; pi_hashes_out n x 4 words,
+ * may be NULL), the public inputs themselves (public_inputs_out n x num_public_inputs words, may be NULL) and a
+ * malformed flag per proof (malformed_out n bytes, may be NULL; a malformed proof still yields a record).
+ * Replaces: ProofWithPublicInputs::from_bytes + ProofValues::from (types/proof.rs:389-403) +
+ * VerificationKeyValues::from (types/verification_key.rs:14-24) for the fields the FRI path reads. */
+int sv_wire_unpack_batch(const sv_fri_shape* shape, const sv_plonk_common* common, const uint64_t* constants_sigmas_cap,
+                         const uint8_t* blob, size_t stride_bytes, size_t n_proofs, uint64_t* records_out,
+                         uint64_t* pi_hashes_out, uint64_t* public_inputs_out, uint8_t* malformed_out, int nthreads);
+
+/* GPU: the same unpacking as one gather kernel (HBM-bound byte shuffling, one thread per record word) plus the
+ * public-input hashes, one thread per proof.  mem says where blob / records_out / pi_hashes_out / malformed_out
+ * (n x u32) live; constants_sigmas_cap is always a host pointer.  SV_MEM_DEVICE: blob must be 8-byte aligned and
+ * readable up to the next multiple of 8 bytes past its end. */
+int sv_wire_unpack_batch_gpu(sv_ctx* ctx, const sv_fri_shape* shape, const sv_plonk_common* common,
+                             const uint64_t* constants_sigmas_cap, const uint8_t* blob, size_t stride_bytes, size_t n_proofs,
+                             uint64_t* records_out, uint64_t* pi_hashes_out, uint32_t* malformed_out, int mem);
+
+/* The whole verifier-side path from serialised proofs in HOST memory: chunks of wire bytes move H2D back to back;
+ * per chunk the device unpacks them into records, hashes the public inputs, derives the challenges (device
+ * transcript) and runs the FRI query phase.  A malformed proof is rejected (bit 0, first_fail SV_FAIL_MALFORMED).
+ * Replaces, per proof: from_bytes + ProofValues::from + get_public_inputs_hash + get_challenges + verify_fri_proof
+ * (verifier_api.rs:34-56 down to chip/fri_chip.rs:329-362). */
+int sv_verify_proofs_wire(sv_ctx* ctx, const sv_fri_shape* shape, const sv_plonk_common* common,
+                          const uint64_t* constants_sigmas_cap, const uint64_t circuit_digest[4], const uint8_t* blob,
+                          size_t stride_bytes, size_t n_proofs, uint32_t* accept_bitmap, uint32_t* first_fail);
+
+/* hash_n_to_hash_no_pad over Poseidon-Goldilocks of n words (host): the public-inputs hash of one proof. */
+int sv_public_inputs_hash(const uint64_t* public_inputs, size_t n, uint64_t out[4]);
 
 /* library / build info */
 const char* sv_version(void);

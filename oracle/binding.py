@@ -34,7 +34,7 @@ class OrcLayout(ctypes.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "_build", "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "oracle.h", "orc_field.h", "poseidon_g_constants.h", "poseidon_b_constants.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "wire.c", "oracle.h", "orc_field.h", "poseidon_g_constants.h", "poseidon_b_constants.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -168,3 +168,51 @@ def fri_challenges(shape: OrcShape, record, circuit_digest, pi_hash, num_challen
     cd = np.asarray(circuit_digest, dtype=np.uint64)
     ph = np.asarray(pi_hash, dtype=np.uint64)
     lib().orc_fri_challenges(ctypes.byref(shape), record.ctypes.data, cd.ctypes.data, ph.ctypes.data, num_challenges)
+
+
+# -- wire format (oracle/wire.c) -------------------------------------------------------------------
+class OrcCommon(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "num_constants", "num_routed_wires", "num_wires", "num_challenges", "num_partial_products",
+        "quotient_degree_factor", "num_public_inputs")]
+
+
+def common_from(sv_common) -> OrcCommon:
+    return OrcCommon(*[getattr(sv_common, n) for n, _ in OrcCommon._fields_])
+
+
+def _wire_lib():
+    L = lib()
+    vp, sp, cp = ctypes.c_void_p, ctypes.POINTER(OrcShape), ctypes.POINTER(OrcCommon)
+    L.orc_wire_proof_bytes.argtypes = [sp, cp]
+    L.orc_wire_proof_bytes.restype = ctypes.c_size_t
+    L.orc_wire_read_proof.argtypes = [sp, cp, vp, vp, ctypes.c_size_t, vp, vp, vp]
+    L.orc_wire_write_proof.argtypes = [sp, cp, vp, vp, vp]
+    return L
+
+
+def wire_proof_bytes(shape: OrcShape, common: OrcCommon) -> int:
+    return int(_wire_lib().orc_wire_proof_bytes(ctypes.byref(shape), ctypes.byref(common)))
+
+
+def wire_read_proof(shape: OrcShape, common: OrcCommon, vk_cap, data):
+    """-> (rc, record, public_inputs, pi_hash); rc 0 parsed, 1 malformed, < 0 cannot be framed."""
+    L = layout(shape)
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    cap = np.ascontiguousarray(vk_cap, dtype=np.uint64)
+    rec = np.zeros(L.record_words, dtype=np.uint64)
+    pis = np.zeros(max(1, common.num_public_inputs), dtype=np.uint64)
+    pih = np.zeros(4, dtype=np.uint64)
+    rc = _wire_lib().orc_wire_read_proof(ctypes.byref(shape), ctypes.byref(common), cap.ctypes.data, data.ctypes.data, data.size,
+                                         rec.ctypes.data, pis.ctypes.data, pih.ctypes.data)
+    return rc, rec, pis[:common.num_public_inputs], pih
+
+
+def wire_write_proof(shape: OrcShape, common: OrcCommon, record, public_inputs):
+    record = np.ascontiguousarray(record, dtype=np.uint64)
+    pis = np.ascontiguousarray(public_inputs, dtype=np.uint64)
+    out = np.zeros(wire_proof_bytes(shape, common), dtype=np.uint8)
+    pp = pis.ctypes.data if pis.size else None
+    rc = _wire_lib().orc_wire_write_proof(ctypes.byref(shape), ctypes.byref(common), record.ctypes.data, pp, out.ctypes.data)
+    assert rc == 0, rc
+    return out

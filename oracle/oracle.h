@@ -100,6 +100,17 @@ void orc_fri_verify_batch(const orc_shape *s, const uint64_t *records, size_t n,
 void orc_fri_challenges(const orc_shape *s, uint64_t *record, const uint64_t circuit_digest[4],
                         const uint64_t pi_hash[4], uint32_t num_challenges);
 
+/* == wire format (wire.c): plonky2's ProofWithPublicInputs bytes <-> flat record == */
+typedef struct {
+    uint32_t num_constants, num_routed_wires, num_wires, num_challenges, num_partial_products,
+        quotient_degree_factor, num_public_inputs; /* CommonData / CircuitConfig, types/common_data.rs:23-40,68-96 */
+} orc_common;
+size_t orc_wire_proof_bytes(const orc_shape *s, const orc_common *c);
+int orc_wire_read_proof(const orc_shape *s, const orc_common *c, const uint64_t *vk_constants_sigmas_cap,
+                        const uint8_t *bytes, size_t len, uint64_t *record, uint64_t *public_inputs, uint64_t pi_hash[4]);
+int orc_wire_write_proof(const orc_shape *s, const orc_common *c, const uint64_t *record, const uint64_t *public_inputs,
+                         uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif

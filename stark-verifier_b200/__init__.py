@@ -31,4 +31,12 @@ from .api import (  # noqa: F401
     synth_public_inputs,
     MEM_HOST,
     MEM_DEVICE,
+    CommonData,
+    PlonkCommon,
+    FAIL_MALFORMED,
+    shape_from_common,
+    wire_proof_bytes,
+    wire_pack,
+    wire_unpack_batch,
+    public_inputs_hash,
 )

@@ -21,7 +21,8 @@ HASH_POSEIDON_BN254 = 1      # bn245_poseidon/plonky2_config.rs:54-75 (the refer
 SV_MAX_STEPS = 32
 
 FAIL_NAMES = {0: "ok", 1: "pow", 2: "noncanonical", 3: "init_merkle", 4: "zero_denominator",
-              5: "step_eval", 6: "step_merkle", 7: "final_poly"}
+              5: "step_eval", 6: "step_merkle", 7: "final_poly", 8: "malformed"}
+FAIL_MALFORMED = 8
 
 
 class SvError(RuntimeError):
@@ -49,6 +50,14 @@ class Layout(ctypes.Structure):
         ("step_depth", ctypes.c_uint32 * SV_MAX_STEPS), ("query_words", ctypes.c_uint32),
         ("record_words", ctypes.c_uint32), ("algo_bytes_per_query", ctypes.c_uint32),
         ("algo_bytes_shared", ctypes.c_uint32), ("perms_per_query", ctypes.c_uint32)]
+
+
+class PlonkCommon(ctypes.Structure):
+    """sv_plonk_common: the CommonData / CircuitConfig fields the wire format takes its vector lengths from
+    (types/common_data.rs:23-40, 68-96)."""
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "num_constants", "num_routed_wires", "num_wires", "num_challenges", "num_partial_products",
+        "quotient_degree_factor", "num_public_inputs")]
 
 
 @dataclass
@@ -116,6 +125,34 @@ SHAPE_OUTER_BN254 = _params(12, 3, 0, 16, 28, hash_kind=HASH_POSEIDON_BN254)
 SHAPE_SEMAPHORE = _params(12, 3, 4, 16, 28, hiding=True)
 
 
+@dataclass
+class CommonData:
+    """The part of the reference's CommonData (types/common_data.rs:68-96, from plonky2's CommonCircuitData :224-270)
+    that fixes the proof's wire format and the FRI instance.  Defaults: standard_recursion_config
+    (135 wires, 80 routed, 2 constants + 2 selectors, 2 challenges, 9 partial products, quotient degree factor 8)."""
+    fri_params: "FriParams"
+    num_constants: int = 4
+    num_routed_wires: int = 80
+    num_wires: int = 135
+    num_challenges: int = 2
+    num_partial_products: int = 9
+    quotient_degree_factor: int = 8
+    num_public_inputs: int = 4
+
+    def to_c(self) -> PlonkCommon:
+        return PlonkCommon(self.num_constants, self.num_routed_wires, self.num_wires, self.num_challenges,
+                           self.num_partial_products, self.quotient_degree_factor, self.num_public_inputs)
+
+    @staticmethod
+    def for_params(params: "FriParams", num_public_inputs: int = 4, num_constants: int = 4) -> "CommonData":
+        """A CommonData consistent with the oracle widths of `params` (CommonData::fri_oracles, :195-221)."""
+        w = list(params.oracle_num_polys)
+        nch = params.num_zs
+        assert w[2] % nch == 0 and w[3] % nch == 0 and w[0] >= num_constants
+        return CommonData(params, num_constants, w[0] - num_constants, w[1], nch, w[2] // nch - 1, w[3] // nch,
+                          num_public_inputs)
+
+
 # ---------------------------------------------------------------------------------------------
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -161,10 +198,21 @@ def lib() -> ctypes.CDLL:
     L.sv_fri_challenges.argtypes = [ctypes.POINTER(FriShape), vp, vp, vp, ctypes.c_uint32]
     L.sv_synth_proofs.argtypes = [ctypes.POINTER(FriShape), u64, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_uint32,
                                   vp, ctypes.c_int]
+    L.sv_synth_proofs_pi.argtypes = [ctypes.POINTER(FriShape), u64, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_uint32,
+                                     vp, vp, ctypes.c_int]
     L.sv_synth_public_inputs.argtypes = [ctypes.POINTER(FriShape), u64, ctypes.c_uint32, ctypes.c_size_t, vp, vp]
     L.sv_fri_challenges_batch.argtypes = [vp, ctypes.POINTER(FriShape), ctypes.c_size_t, vp, vp, vp, ctypes.c_uint32, ctypes.c_int]
     L.sv_fri_verify_batch_fs.argtypes = [vp, ctypes.POINTER(FriShape), ctypes.c_size_t, vp, vp, vp, ctypes.c_uint32, vp, vp,
                                          ctypes.c_int]
+    sp, cp = ctypes.POINTER(FriShape), ctypes.POINTER(PlonkCommon)
+    L.sv_fri_shape_from_common.argtypes = [cp] + [ctypes.c_uint32] * 8 + [sp]
+    L.sv_wire_proof_bytes.argtypes = [sp, cp]
+    L.sv_wire_proof_bytes.restype = ctypes.c_size_t
+    L.sv_wire_pack.argtypes = [sp, cp, vp, vp, vp]
+    L.sv_wire_unpack_batch.argtypes = [sp, cp, vp, vp, ctypes.c_size_t, ctypes.c_size_t, vp, vp, vp, vp, ctypes.c_int]
+    L.sv_wire_unpack_batch_gpu.argtypes = [vp, sp, cp, vp, vp, ctypes.c_size_t, ctypes.c_size_t, vp, vp, vp, ctypes.c_int]
+    L.sv_verify_proofs_wire.argtypes = [vp, sp, cp, vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t, vp, vp]
+    L.sv_public_inputs_hash.argtypes = [vp, ctypes.c_size_t, vp]
     _LIB = L
     return L
 
@@ -186,16 +234,21 @@ def _ptr(a) -> int:
 
 
 def synth_proofs(params: FriParams, n_proofs: int, seed: int = 0xB2000002, n_circuits: int = 1,
-                 num_challenges: int = 2, nthreads: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
-    """Synthetic valid proofs as a (n_proofs, record_words) uint64 array (host side, CPU)."""
+                 num_challenges: int = 2, nthreads: Optional[int] = None, out: Optional[np.ndarray] = None,
+                 pi_hashes: Optional[np.ndarray] = None) -> np.ndarray:
+    """Synthetic valid proofs as a (n_proofs, record_words) uint64 array (host side, CPU).  pi_hashes (n_proofs, 4):
+    bind proof i to that public-inputs hash instead of one drawn from the seed."""
     s = params.to_shape()
     L = make_layout(s)
     if out is None:
         out = np.zeros((n_proofs, L.record_words), dtype=np.uint64)
     assert out.dtype == np.uint64 and out.size == n_proofs * L.record_words
     nthreads = nthreads or os.cpu_count() or 1
-    rc = lib().sv_synth_proofs(ctypes.byref(s), ctypes.c_uint64(seed), n_circuits, n_proofs, num_challenges,
-                               _ptr(out), nthreads)
+    if pi_hashes is not None:
+        pi_hashes = np.ascontiguousarray(pi_hashes, dtype=np.uint64)
+        assert pi_hashes.size == 4 * n_proofs
+    rc = lib().sv_synth_proofs_pi(ctypes.byref(s), ctypes.c_uint64(seed), n_circuits, n_proofs, num_challenges,
+                                  _ptr(pi_hashes) if pi_hashes is not None else None, _ptr(out), nthreads)
     if rc != 0:
         raise SvError(f"sv_synth_proofs failed: {rc}")
     return out
@@ -221,6 +274,76 @@ def fri_challenges(params: FriParams, record: np.ndarray, circuit_digest, pi_has
     rc = lib().sv_fri_challenges(ctypes.byref(s), _ptr(record), _ptr(cd), _ptr(ph), num_challenges)
     if rc != 0:
         raise SvError(f"sv_fri_challenges failed: {rc}")
+
+
+# -- wire format ---------------------------------------------------------------------
+def shape_from_common(common: CommonData) -> FriShape:
+    """sv_fri_shape_from_common: CommonData::fri_oracles / fri_zs_polys (types/common_data.rs:153-221)."""
+    p, c, out = common.fri_params, common.to_c(), FriShape()
+    rc = lib().sv_fri_shape_from_common(ctypes.byref(c), p.degree_bits, p.config.rate_bits, p.config.cap_height,
+                                        p.config.num_query_rounds, p.config.proof_of_work_bits, len(p.reduction_arity_bits),
+                                        int(p.hiding), p.hash_kind, ctypes.byref(out))
+    if rc != 0:
+        raise SvError(f"sv_fri_shape_from_common failed: {rc}")
+    return out
+
+
+def wire_proof_bytes(common: CommonData) -> int:
+    """Length of one serialised ProofWithPublicInputs of this circuit."""
+    s, c = common.fri_params.to_shape(), common.to_c()
+    n = lib().sv_wire_proof_bytes(ctypes.byref(s), ctypes.byref(c))
+    if n == 0:
+        raise SvError("wire format: FriParams and CommonData disagree")
+    return int(n)
+
+
+def wire_pack(common: CommonData, records: np.ndarray, public_inputs: np.ndarray) -> np.ndarray:
+    """records (n, record_words) + public_inputs (n, num_public_inputs) -> (n, proof_bytes) uint8, plonky2's
+    ProofWithPublicInputs::to_bytes layout (host, CPU)."""
+    s, c = common.fri_params.to_shape(), common.to_c()
+    nb = wire_proof_bytes(common)
+    records = np.ascontiguousarray(records, dtype=np.uint64)
+    n = records.shape[0]
+    public_inputs = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(n, common.num_public_inputs)
+    out = np.zeros((n, nb), dtype=np.uint8)
+    for i in range(n):
+        rc = lib().sv_wire_pack(ctypes.byref(s), ctypes.byref(c), _ptr(records[i]), _ptr(public_inputs[i]) if public_inputs.size else None,
+                                _ptr(out[i]))
+        if rc != 0:
+            raise SvError(f"sv_wire_pack failed: {rc}")
+    return out
+
+
+def wire_unpack_batch(common: CommonData, constants_sigmas_cap, blob: np.ndarray, n_proofs: Optional[int] = None,
+                      stride: Optional[int] = None, nthreads: int = 1):
+    """CPU unpacker: (records, pi_hashes, public_inputs, malformed) of n proofs in `blob` (uint8)."""
+    s, c = common.fri_params.to_shape(), common.to_c()
+    L = make_layout(s)
+    nb = wire_proof_bytes(common)
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    stride = nb if stride is None else stride
+    n = (blob.size // stride if n_proofs is None else n_proofs)
+    cap = np.ascontiguousarray(constants_sigmas_cap, dtype=np.uint64)
+    assert cap.size == 4 << s.cap_height
+    recs = np.zeros((n, L.record_words), dtype=np.uint64)
+    pih = np.zeros((n, 4), dtype=np.uint64)
+    pis = np.zeros((n, common.num_public_inputs), dtype=np.uint64)
+    mal = np.zeros(n, dtype=np.uint8)
+    rc = lib().sv_wire_unpack_batch(ctypes.byref(s), ctypes.byref(c), _ptr(cap), _ptr(blob), stride, n, _ptr(recs), _ptr(pih),
+                                    _ptr(pis) if pis.size else None, _ptr(mal), nthreads)
+    if rc != 0:
+        raise SvError(f"sv_wire_unpack_batch failed: {rc}")
+    return recs, pih, pis, mal
+
+
+def public_inputs_hash(public_inputs) -> np.ndarray:
+    """PlonkVerifierChip::get_public_inputs_hash (plonk_verifier_chip.rs:41-53), host."""
+    pi = np.ascontiguousarray(public_inputs, dtype=np.uint64)
+    out = np.zeros(4, dtype=np.uint64)
+    rc = lib().sv_public_inputs_hash(_ptr(pi) if pi.size else None, pi.size, _ptr(out))
+    if rc != 0:
+        raise SvError(f"sv_public_inputs_hash failed: {rc}")
+    return out
 
 
 class Context:
@@ -360,6 +483,46 @@ class Context:
                                                   _ptr(first_fail) if first_fail is not None else None, mem),
                  "sv_fri_verify_batch_fs")
         return (accept_bitmap, first_fail) if want_fail else accept_bitmap
+
+    def wire_unpack_batch(self, common: CommonData, constants_sigmas_cap, blob, n_proofs: Optional[int] = None,
+                          stride: Optional[int] = None, records_out=None, pi_hashes_out=None, malformed_out=None,
+                          mem: int = MEM_HOST):
+        """GPU unpacker (wire_unpack_kernel + wire_pi_hash_kernel): (records, pi_hashes, malformed)."""
+        s, c = common.fri_params.to_shape(), common.to_c()
+        nb = wire_proof_bytes(common)
+        stride = nb if stride is None else stride
+        cap = np.ascontiguousarray(constants_sigmas_cap, dtype=np.uint64)
+        if mem == MEM_HOST:
+            blob = np.ascontiguousarray(blob, dtype=np.uint8)
+            n_proofs = blob.size // stride if n_proofs is None else n_proofs
+            L = make_layout(s)
+            records_out = np.zeros((n_proofs, L.record_words), dtype=np.uint64)
+            pi_hashes_out = np.zeros((n_proofs, 4), dtype=np.uint64)
+            malformed_out = np.zeros(n_proofs, dtype=np.uint32)
+        self._ck(self._lib.sv_wire_unpack_batch_gpu(self._h, ctypes.byref(s), ctypes.byref(c), _ptr(cap), _ptr(blob), stride, n_proofs,
+                                                    _ptr(records_out), _ptr(pi_hashes_out) if pi_hashes_out is not None else None,
+                                                    _ptr(malformed_out) if malformed_out is not None else None, mem),
+                 "sv_wire_unpack_batch_gpu")
+        return records_out, pi_hashes_out, malformed_out
+
+    def verify_proofs_wire(self, common: CommonData, constants_sigmas_cap, circuit_digest, blob, n_proofs: Optional[int] = None,
+                           stride: Optional[int] = None, want_fail: bool = False):
+        """Serialised proofs (host uint8 array or pinned host pointer) -> accept bitmap: unpack, public-input hashes,
+        transcript and FRI query phase all on the device."""
+        s, c = common.fri_params.to_shape(), common.to_c()
+        nb = wire_proof_bytes(common)
+        stride = nb if stride is None else stride
+        if isinstance(blob, np.ndarray):
+            blob = np.ascontiguousarray(blob, dtype=np.uint8)
+            n_proofs = blob.size // stride if n_proofs is None else n_proofs
+        cap = np.ascontiguousarray(constants_sigmas_cap, dtype=np.uint64)
+        cd = np.ascontiguousarray(circuit_digest, dtype=np.uint64)
+        bitmap = np.zeros((n_proofs + 31) // 32, dtype=np.uint32)
+        ff = np.zeros(n_proofs, dtype=np.uint32) if want_fail else None
+        self._ck(self._lib.sv_verify_proofs_wire(self._h, ctypes.byref(s), ctypes.byref(c), _ptr(cap), _ptr(cd), _ptr(blob), stride,
+                                                 n_proofs, _ptr(bitmap), _ptr(ff) if ff is not None else None),
+                 "sv_verify_proofs_wire")
+        return (bitmap, ff) if want_fail else bitmap
 
     def allgather_bitmap(self, nccl_comm: int, local_ptr: int, all_ptr: int, words_per_rank: int):
         self._ck(self._lib.sv_allgather_bitmap(self._h, ctypes.c_void_p(nccl_comm), local_ptr, all_ptr, words_per_rank),

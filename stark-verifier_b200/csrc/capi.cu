@@ -2,6 +2,7 @@
 // No CPU fallback: every compute entry point needs a CUDA device and fails loudly otherwise.
 #include "../../include/stark_verifier_b200.h"
 #include "fri_kernels.cuh"
+#include "wire_kernels.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -35,6 +36,15 @@ struct sv_ctx {
     cudaStream_t fs_stream = nullptr;                                  // the batch-wide transcript of the host pipeline
     cudaEvent_t ev_hdr = nullptr, ev_fs = nullptr;
     cudaEvent_t ev_copied[SV_NBUF] = {}, ev_done[SV_NBUF] = {}, ev_join[SV_NKS] = {};
+    // wire format (sv_wire_unpack_batch_gpu, sv_verify_proofs_wire): offset tables of the last (shape, common) seen,
+    // the verifier key's cap, wire-byte staging ring, malformed flags
+    bool w_valid = false;
+    sv_fri_shape w_shape; sv_plonk_common w_common;
+    WireMap w_map; std::vector<u64> w_vk;
+    u32* d_wtab = nullptr; size_t wtab_words = 0;                      // hdr_src | q_src | chk
+    u64* d_wvk = nullptr; size_t wvk_words = 0;
+    u64* d_wire[SV_NBUF] = {}; size_t wire_words[SV_NBUF] = {};
+    u32* d_mal = nullptr; size_t mal_words = 0;
     uint64_t launches = 0;
     // optional CUDA-event timing of the dominant kernel (fri_query_kernel / merkle / permute), on
     // the stream it is launched on
@@ -138,6 +148,10 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaFree(c->d_fail);
     cudaFree(c->d_pi);
     cudaFree(c->d_hdr);
+    cudaFree(c->d_wtab);
+    cudaFree(c->d_wvk);
+    for (int i = 0; i < SV_NBUF; i++) cudaFree(c->d_wire[i]);
+    cudaFree(c->d_mal);
     auto drop_s = [](cudaStream_t s) { if (s) cudaStreamDestroy(s); };
     auto drop_e = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
     drop_e(c->ev_hdr); drop_e(c->ev_fs);
@@ -591,6 +605,185 @@ extern "C" int sv_fri_challenges_batch(sv_ctx* c, const sv_fri_shape* shape, siz
     CK(c, cudaMemcpy2DAsync(records, rw * 8, c->d_stage[0], rw * 8, hw * 8, n_proofs, cudaMemcpyDeviceToHost, s));
     CK(c, cudaStreamSynchronize(s));
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wire format: serialised proofs -> records on the device (wire_kernels.cuh).
+struct WireDev {
+    WireDims d;
+    const u32 *hdr_src, *q_src, *chk;
+    const u64* vk;
+};
+// Build (or reuse) the offset tables of (shape, common) and put them and the verifier key's cap on the device;
+// the uploads are enqueued on `s`.
+static int wire_tables(sv_ctx* c, const sv_fri_shape& shape, const sv_plonk_common& common, const uint64_t* vk_cap, cudaStream_t s,
+                       WireDev& W) {
+    bool same = c->w_valid && !memcmp(&c->w_shape, &shape, sizeof shape) && !memcmp(&c->w_common, &common, sizeof common);
+    if (!same) {
+        // kernels of an earlier call may still be reading the old tables
+        if (int rc = sv_ctx_synchronize(c)) return rc;
+        c->w_valid = false;
+        int rc = make_wire_map(shape, common, c->w_map);
+        if (rc) return fail(c, -8, "wire format: shape and common data disagree or the proof is too large (%d)", rc);
+        c->w_shape = shape;
+        c->w_common = common;
+        c->w_vk.clear();
+    }
+    const WireMap& M = c->w_map;
+    const size_t nh = M.hdr_src.size(), nq = M.q_src.size(), nc = M.chk.size(), ncap_words = 4ull << shape.cap_height;
+    if (grow(c, c->d_wtab, c->wtab_words, nh + nq + nc)) return -6;
+    if (grow(c, c->d_wvk, c->wvk_words, ncap_words)) return -6;
+    if (!same) {
+        CK(c, cudaMemcpyAsync(c->d_wtab, M.hdr_src.data(), nh * 4, cudaMemcpyHostToDevice, s));
+        CK(c, cudaMemcpyAsync(c->d_wtab + nh, M.q_src.data(), nq * 4, cudaMemcpyHostToDevice, s));
+        CK(c, cudaMemcpyAsync(c->d_wtab + nh + nq, M.chk.data(), nc * 4, cudaMemcpyHostToDevice, s));
+        CK(c, cudaStreamSynchronize(s));   // rare (new circuit); later calls may use the tables from other streams
+        c->w_valid = true;
+    }
+    if (c->w_vk.size() != ncap_words || memcmp(c->w_vk.data(), vk_cap, ncap_words * 8)) {
+        if (same) {
+            if (int rc = sv_ctx_synchronize(c)) return rc;   // same reason: the old cap may still be in use
+        }
+        c->w_vk.assign(vk_cap, vk_cap + ncap_words);
+        CK(c, cudaMemcpyAsync(c->d_wvk, c->w_vk.data(), ncap_words * 8, cudaMemcpyHostToDevice, s));
+        CK(c, cudaStreamSynchronize(s));
+    }
+    W.d = M.d;
+    W.hdr_src = c->d_wtab;
+    W.q_src = c->d_wtab + nh;
+    W.chk = c->d_wtab + nh + nq;
+    W.vk = c->d_wvk;
+    return 0;
+}
+
+// unpack + public-input hashes of n proofs whose bytes start first_off bytes after d_blob8 (8-byte aligned)
+static int enqueue_unpack(sv_ctx* c, const WireDev& W, const u64* d_blob8, size_t first_off, size_t stride, size_t n, u64* d_records,
+                          u64* d_pi, u32* d_mal, cudaStream_t s) {
+    CK(c, cudaMemsetAsync(d_mal, 0, n * 4, s));
+    dim3 grid((unsigned)n, (W.d.record_words + SVB_WIRE_BLOCK - 1) / SVB_WIRE_BLOCK);
+    wire_unpack_kernel<<<grid, SVB_WIRE_BLOCK, 0, s>>>(d_blob8, first_off, stride, W.d, W.hdr_src, W.q_src, W.chk, W.vk, d_records, d_mal);
+    c->launches++;
+    if (d_pi) {
+        wire_pi_hash_kernel<<<(unsigned)((n + SVB_BLOCK - 1) / SVB_BLOCK), SVB_BLOCK, 0, s>>>(d_blob8, first_off, stride, W.d, n, d_pi, d_mal);
+        c->launches++;
+    }
+    CK(c, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sv_wire_unpack_batch_gpu(sv_ctx* c, const sv_fri_shape* shape, const sv_plonk_common* common,
+                                        const uint64_t* vk_cap, const uint8_t* blob, size_t stride, size_t n, uint64_t* records_out,
+                                        uint64_t* pi_hashes_out, uint32_t* malformed_out, int mem) {
+    if (!c || !shape || !common || !vk_cap || !records_out || (n && !blob)) return -1;
+    if (!known_mem(mem)) return fail(c, -5, "mem %d is neither SV_MEM_HOST nor SV_MEM_DEVICE", mem);
+    if (n >= (1ull << 31)) return fail(c, -8, "batch too large for one call");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = mem == SV_MEM_DEVICE ? c->stream : c->own_stream;
+    WireDev W;
+    if (int rc = wire_tables(c, *shape, *common, vk_cap, s, W)) return rc;
+    if (n == 0) return 0;
+    if (n > 1 && stride < W.d.proof_bytes) return fail(c, -8, "stride %zu < proof bytes %u", stride, W.d.proof_bytes);
+    if (mem == SV_MEM_DEVICE) {
+        if (reinterpret_cast<uintptr_t>(blob) & 7) return fail(c, -8, "device blob must be 8-byte aligned");
+        u32* d_mal = malformed_out;
+        if (!d_mal) {
+            if (grow(c, c->d_mal, c->mal_words, n)) return -6;
+            d_mal = c->d_mal;
+        }
+        return enqueue_unpack(c, W, reinterpret_cast<const u64*>(blob), 0, stride, n, records_out, pi_hashes_out, d_mal, s);
+    }
+    const size_t bytes = (n - 1) * stride + W.d.proof_bytes, rw = W.d.record_words;
+    if (grow(c, c->d_wire[0], c->wire_words[0], bytes / 8 + 2)) return -6;
+    if (grow(c, c->d_stage[0], c->stage_words[0], n * rw)) return -6;
+    if (grow(c, c->d_pi, c->pi_words, 4 * n)) return -6;
+    if (grow(c, c->d_mal, c->mal_words, n)) return -6;
+    CK(c, cudaMemcpyAsync(c->d_wire[0], blob, bytes, cudaMemcpyHostToDevice, s));
+    if (int rc = enqueue_unpack(c, W, c->d_wire[0], 0, stride, n, c->d_stage[0], c->d_pi, c->d_mal, s)) return rc;
+    CK(c, cudaMemcpyAsync(records_out, c->d_stage[0], n * rw * 8, cudaMemcpyDeviceToHost, s));
+    if (pi_hashes_out) CK(c, cudaMemcpyAsync(pi_hashes_out, c->d_pi, n * 32, cudaMemcpyDeviceToHost, s));
+    if (malformed_out) CK(c, cudaMemcpyAsync(malformed_out, c->d_mal, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+// The pipeline of fri_verify_host with wire bytes as its input: H2D of a chunk's bytes on the copy stream; on the
+// chunk's compute stream unpack -> public-input hashes -> transcript -> prepare + query -> reject malformed.
+static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, const sv_fri_shape& shape, const sv_plonk_common& common,
+                            const uint64_t* vk_cap, const uint8_t* blob, size_t stride, size_t n_proofs, uint32_t* accept_bitmap,
+                            uint32_t* first_fail) {
+    int rc = 0;
+    const size_t rw = P.L.record_words;
+    cudaStream_t cs = c->copy_stream;
+    WireDev W;
+    if ((rc = wire_tables(c, shape, common, vk_cap, cs, W))) return rc;
+    if (n_proofs > 1 && stride < W.d.proof_bytes) return fail(c, -8, "stride %zu < proof bytes %u", stride, W.d.proof_bytes);
+    size_t n_words = (n_proofs + 31) / 32;
+    if (grow(c, c->d_bitmap, c->bitmap_words, n_words)) return -6;
+    if (first_fail && grow(c, c->d_fail, c->fail_words, n_proofs)) return -6;
+    if (grow(c, c->d_pi, c->pi_words, 4 * n_proofs)) return -6;
+    if (grow(c, c->d_mal, c->mal_words, n_proofs)) return -6;
+    size_t chunk_mb = 32;
+    int n_ks = SV_NKS;
+    if (const char* e = getenv("SVB_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 4096) chunk_mb = (size_t)v; }
+    if (const char* e = getenv("SVB_KSTREAMS")) { long v = atol(e); if (v >= 1 && v <= SV_NKS) n_ks = (int)v; }
+    size_t chunk = ((chunk_mb << 20) / (rw * 8)) & ~(size_t)31;
+    if (chunk < 32) chunk = 32;
+    if (chunk > n_proofs) chunk = (n_proofs + 31) & ~(size_t)31;
+    for (int b = 0; b < SV_NBUF; b++) {
+        if (grow(c, c->d_stage[b], c->stage_words[b], chunk * rw)) return -6;
+        if (grow(c, c->d_wire[b], c->wire_words[b], (chunk * std::max(stride, (size_t)W.d.proof_bytes)) / 8 + 2)) return -6;
+    }
+    cudaStream_t ks[SV_NKS] = {c->own_stream};
+    for (int i = 1; i < SV_NKS; i++) ks[i] = c->aux_stream[i - 1];
+    size_t n_chunks = (n_proofs + chunk - 1) / chunk;
+    for (size_t i = 0; i < n_chunks; i++) {
+        int b = (int)(i % SV_NBUF);
+        cudaStream_t k = ks[i % n_ks];
+        size_t first = i * chunk, cnt = std::min(chunk, n_proofs - first);
+        size_t bytes = (cnt - 1) * stride + W.d.proof_bytes;
+        if (i >= SV_NBUF) CK(c, cudaStreamWaitEvent(cs, c->ev_done[b], 0));   // buffers b free again
+        CK(c, cudaMemcpyAsync(c->d_wire[b], blob + first * stride, bytes, cudaMemcpyHostToDevice, cs));
+        CK(c, cudaEventRecord(c->ev_copied[b], cs));
+        CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
+        if ((rc = enqueue_unpack(c, W, c->d_wire[b], 0, stride, cnt, c->d_stage[b], c->d_pi + 4 * first, c->d_mal + first, k))) return rc;
+        if ((rc = enqueue_challenges(c, P, F, cnt, c->d_stage[b], c->d_pi + 4 * first, k))) return rc;
+        u32* d_fail = first_fail ? c->d_fail + first : nullptr;
+        if ((rc = enqueue_fri(c, P, cnt, c->d_stage[b], c->d_scratch + 4 * first, c->d_bitmap + first / 32, d_fail, k))) return rc;
+        wire_reject_malformed_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, k>>>(c->d_mal + first, c->d_bitmap + first / 32, d_fail, (u32)cnt);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        CK(c, cudaEventRecord(c->ev_done[b], k));
+    }
+    for (int j = 1; j < n_ks && (size_t)j < n_chunks; j++) {
+        CK(c, cudaEventRecord(c->ev_join[j], ks[j]));
+        CK(c, cudaStreamWaitEvent(ks[0], c->ev_join[j], 0));
+    }
+    CK(c, cudaMemcpyAsync(accept_bitmap, c->d_bitmap, n_words * 4, cudaMemcpyDeviceToHost, ks[0]));
+    if (first_fail) CK(c, cudaMemcpyAsync(first_fail, c->d_fail, n_proofs * 4, cudaMemcpyDeviceToHost, ks[0]));
+    CK(c, cudaStreamSynchronize(ks[0]));
+    return 0;
+}
+
+extern "C" int sv_verify_proofs_wire(sv_ctx* c, const sv_fri_shape* shape, const sv_plonk_common* common,
+                                     const uint64_t* vk_cap, const uint64_t circuit_digest[4], const uint8_t* blob, size_t stride,
+                                     size_t n_proofs, uint32_t* accept_bitmap, uint32_t* first_fail) {
+    if (!c || !shape || !common || !vk_cap || !circuit_digest || !accept_bitmap || (n_proofs && !blob)) return -1;
+    FsParams F;
+    int rc = make_fs(c, shape, circuit_digest, common->num_challenges, F);
+    if (rc) return rc;
+    FriKernelParams P;
+    if ((rc = make_params(c, *shape, P))) return rc;
+    if (n_proofs == 0) return 0;
+    if (n_proofs * (size_t)P.num_queries >= (1ull << 31)) return fail(c, -8, "batch too large for one call");
+    CK(c, cudaSetDevice(c->device));
+    if (grow(c, c->d_scratch, c->scratch_words, 4 * n_proofs)) return -6;
+    rc = wire_verify_host(c, P, F, *shape, *common, vk_cap, blob, stride, n_proofs, accept_bitmap, first_fail);
+    if (rc) {
+        std::string keep = c->err;
+        sv_ctx_synchronize(c);
+        c->err = keep;
+    }
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------

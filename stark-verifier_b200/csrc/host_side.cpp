@@ -17,8 +17,7 @@
 #include "../../include/stark_verifier_b200.h"
 #include "goldilocks.cuh"
 #include "layout.hpp"
-#include "poseidon_g.cuh"
-#include "poseidon_b.cuh"
+#include "host_util.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -30,12 +29,6 @@
 #include <vector>
 
 namespace svb {
-
-// the width-12 permutation of a hash family, canonical in / canonical out
-static inline void permute_kind(u32 kind, u64 st[12]) {
-    if (kind == SV_HASH_POSEIDON_BN254) poseidon_b_canonical(st);
-    else poseidon_g_canonical(st);
-}
 
 // ---------------------------------------------------------------------------------------------
 struct Challenger {
@@ -71,15 +64,6 @@ struct Challenger {
     fp2 squeeze2() { u64 a = squeeze(); u64 b = squeeze(); return mk2(a, b); }
 };
 
-static void hash_no_pad(u32 kind, const u64* in, size_t n, u64 out[4]) {
-    u64 st[12] = {0};
-    for (size_t off = 0; off < n; off += 8) {
-        size_t len = std::min<size_t>(8, n - off);
-        for (size_t i = 0; i < len; i++) st[i] = in[off + i];
-        permute_kind(kind, st);
-    }
-    memcpy(out, st, 32);
-}
 static void hash_or_noop(u32 kind, const u64* in, size_t n, u64 out[4]) {
     if (n <= 4) {
         memset(out, 0, 32);
@@ -93,17 +77,6 @@ static void two_to_one(u32 kind, const u64 l[4], const u64 r[4], u64 out[4]) {
     memcpy(st + 4, r, 32);
     permute_kind(kind, st);
     memcpy(out, st, 32);
-}
-
-static void parallel_for(size_t n, int nthreads, const std::function<void(size_t, size_t)>& body) {
-    if (nthreads <= 1 || n < 2) { body(0, n); return; }
-    std::vector<std::thread> th;
-    size_t chunk = (n + nthreads - 1) / nthreads;
-    for (int t = 0; t < nthreads; t++) {
-        size_t b = std::min(n, (size_t)t * chunk), e = std::min(n, b + chunk);
-        if (b < e) th.emplace_back([=, &body] { body(b, e); });
-    }
-    for (auto& x : th) x.join();
 }
 
 // SplitMix64 -> uniform canonical field elements by rejection
@@ -485,6 +458,11 @@ extern "C" int sv_synth_public_inputs(const sv_fri_shape* shape, uint64_t seed, 
 
 extern "C" int sv_synth_proofs(const sv_fri_shape* shape, uint64_t seed, uint32_t n_circuits, size_t n_proofs,
                                uint32_t num_challenges, uint64_t* records_out, int nthreads) {
+    return sv_synth_proofs_pi(shape, seed, n_circuits, n_proofs, num_challenges, nullptr, records_out, nthreads);
+}
+
+extern "C" int sv_synth_proofs_pi(const sv_fri_shape* shape, uint64_t seed, uint32_t n_circuits, size_t n_proofs,
+                                  uint32_t num_challenges, const uint64_t* pi_hashes, uint64_t* records_out, int nthreads) {
     sv_fri_layout L;
     if (!shape || !records_out || make_layout(*shape, L)) return -1;
     if (shape->hash_kind > SV_HASH_POSEIDON_BN254) return -2;
@@ -503,7 +481,8 @@ extern "C" int sv_synth_proofs(const sv_fri_shape* shape, uint64_t seed, uint32_
             size_t i = next.fetch_add(1);
             if (i >= n_proofs) break;
             u64 pi[4];
-            synth_pi_hash(seed, i, pi);
+            if (pi_hashes) memcpy(pi, pi_hashes + 4 * i, 32);
+            else synth_pi_hash(seed, i, pi);
             int rc = prove(circuits[i % n_circuits], pi, num_challenges, records_out + i * (size_t)L.record_words,
                            outer ? 1 : nthreads);
             if (rc) err = rc;

@@ -67,6 +67,21 @@ pub struct sv_fri_layout {
     pub algo_bytes_per_query: u32, pub algo_bytes_shared: u32, pub perms_per_query: u32,
 }
 
+/// `sv_plonk_common`: the CommonData / CircuitConfig fields that fix the vector lengths of the wire format.
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct sv_plonk_common {
+    pub num_constants: u32,
+    pub num_routed_wires: u32,
+    pub num_wires: u32,
+    pub num_challenges: u32,
+    pub num_partial_products: u32,
+    pub quotient_degree_factor: u32,
+    pub num_public_inputs: u32,
+}
+
+pub const SV_FAIL_MALFORMED: u32 = 8;
+
 #[repr(C)]
 pub struct sv_ctx { _private: [u8; 0] }
 
@@ -99,6 +114,16 @@ extern "C" {
                                   accept_bitmap: *mut u32, first_fail: *mut u32, mem: c_int) -> c_int;
     pub fn sv_fri_challenges(shape: *const sv_fri_shape, record: *mut u64, circuit_digest: *const u64,
                              public_inputs_hash: *const u64, num_challenges: u32) -> c_int;
+    // wire format: ProofWithPublicInputs::to_bytes() in, accept bits out
+    pub fn sv_wire_proof_bytes(shape: *const sv_fri_shape, common: *const sv_plonk_common) -> usize;
+    pub fn sv_wire_unpack_batch(shape: *const sv_fri_shape, common: *const sv_plonk_common, constants_sigmas_cap: *const u64,
+                                blob: *const u8, stride_bytes: usize, n_proofs: usize, records_out: *mut u64,
+                                pi_hashes_out: *mut u64, public_inputs_out: *mut u64, malformed_out: *mut u8,
+                                nthreads: c_int) -> c_int;
+    pub fn sv_verify_proofs_wire(ctx: *mut sv_ctx, shape: *const sv_fri_shape, common: *const sv_plonk_common,
+                                 constants_sigmas_cap: *const u64, circuit_digest: *const u64, blob: *const u8,
+                                 stride_bytes: usize, n_proofs: usize, accept_bitmap: *mut u32, first_fail: *mut u32) -> c_int;
+    pub fn sv_public_inputs_hash(public_inputs: *const u64, n: usize, out: *mut u64) -> c_int;
 }
 
 #[derive(Debug)]
@@ -232,6 +257,45 @@ impl GpuFriVerifier {
             return Err(GpuError(rc, msg));
         }
         Ok((0..proofs.len()).map(|i| (bitmap[i >> 5] >> (i & 31)) & 1 == 1).collect())
+    }
+}
+
+/// `CommonData` -> `sv_plonk_common` (types/common_data.rs:23-40,68-96).
+pub fn common_from<F: halo2_proofs::halo2curves::ff::PrimeField>(cd: &CommonData<F>) -> sv_plonk_common {
+    sv_plonk_common {
+        num_constants: cd.num_constants as u32,
+        num_routed_wires: cd.config.num_routed_wires as u32,
+        num_wires: cd.config.num_wires as u32,
+        num_challenges: cd.config.num_challenges as u32,
+        num_partial_products: cd.num_partial_products as u32,
+        quotient_degree_factor: cd.quotient_degree_factor as u32,
+        num_public_inputs: cd.num_public_inputs as u32,
+    }
+}
+
+impl GpuFriVerifier {
+    /// The whole verifier-side path from serialised proofs: `blob` holds `n` back-to-back
+    /// `ProofWithPublicInputs::to_bytes()` strings of ONE circuit (they all have the same length,
+    /// `sv_wire_proof_bytes`).  Unpacking, the public-inputs hash, the Fiat-Shamir transcript and the FRI
+    /// query phase all run on the device; nothing is repacked on the host.
+    pub fn verify_serialized<F: halo2_proofs::halo2curves::ff::PrimeField>(
+        &mut self, blob: &[u8], vk: &VerificationKeyValues<F>, common_data: &CommonData<F>,
+    ) -> Result<Vec<bool>, GpuError> {
+        let (shape, common) = (shape_from(common_data), common_from(common_data));
+        let nb = unsafe { sv_wire_proof_bytes(&shape, &common) };
+        if nb == 0 || blob.len() % nb != 0 { return Err(GpuError(-1, "blob is not a whole number of proofs".into())); }
+        let n = blob.len() / nb;
+        let mut cap = vec![0u64; 4 << shape.cap_height];
+        put_cap(&mut cap, &vk.constants_sigmas_cap);
+        let digest: Vec<u64> = vk.circuit_digest.elements.iter().map(|e| e.0).collect();
+        let mut bitmap = vec![0u32; (n + 31) / 32];
+        let rc = unsafe { sv_verify_proofs_wire(self.ctx, &shape, &common, cap.as_ptr(), digest.as_ptr(), blob.as_ptr(), nb, n,
+                                                bitmap.as_mut_ptr(), std::ptr::null_mut()) };
+        if rc != 0 {
+            let msg = unsafe { CStr::from_ptr(sv_last_error(self.ctx)) }.to_string_lossy().into_owned();
+            return Err(GpuError(rc, msg));
+        }
+        Ok((0..n).map(|i| (bitmap[i >> 5] >> (i & 31)) & 1 == 1).collect())
     }
 }
 

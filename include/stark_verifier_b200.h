@@ -196,7 +196,7 @@ int sv_fri_challenges(const sv_fri_shape* shape, uint64_t* record, const uint64_
  * records_out.  `n_circuits` distinct committed oracle sets are built from `seed`; proof i uses
  * circuit i % n_circuits and its own public-input hash, so every proof has its own challenges,
  * query indices, openings and FRI commit phase.  Stand-in for plonky2's prover
- * (plonky2_semaphore/*, not on the hot path) -- test/bench data only. */
+ * (the plonky2_semaphore module, not on the hot path) -- test/bench data only. */
 int sv_synth_proofs(const sv_fri_shape* shape, uint64_t seed, uint32_t n_circuits, size_t n_proofs,
                     uint32_t num_challenges, uint64_t* records_out, int nthreads);
 

@@ -93,6 +93,27 @@ def test_abi_exports_every_declared_symbol(svb):
         assert hasattr(L, n), f"{n} declared in include/stark_verifier_b200.h but not exported"
 
 
+def test_header_is_plain_c_and_c_example_links(svb, tmp_path):
+    """include/*.h is the drop-in boundary: it must compile as C99 on its own, and a plain-C caller
+    (examples/verify_wire.c) must link against the in-tree library and fail loudly without a GPU."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "stark_verifier_b200.h")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    exe = str(tmp_path / "verify_wire")
+    libdir = os.path.dirname(svb.lib_path())
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "verify_wire.c"), "-L", libdir, "-lsvb200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "missing.bin", "missing.bin"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
 def test_no_cpu_fallback(svb):
     import torch
     if torch.cuda.is_available():

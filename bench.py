@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-wire", action="store_true", help="skip the serialised-proof leg of e2e")
+    ap.add_argument("--wire-leg", action="store_true", help="(internal) run only the serialised-proof leg and print its JSON")
     ap.add_argument("--device-transcript", action="store_true",
                     help="derive the Fiat-Shamir challenges on the device too (sv_fri_verify_batch_fs): the records "
                          "enter with their challenge fields zeroed")
@@ -251,10 +252,26 @@ def wire_leg(svb, torch, ctx, params, L, n_host, distinct, seed, threads, steps)
                     "device transcript -> fri_query_kernel, per 32 MiB chunk"}
 
 
+def run_wire_leg(args):
+    import torch
+    import stark_verifier_b200 as svb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(0)
+    params = workload_params(svb, args.workload)
+    L = svb.api.make_layout(params)
+    ctx = svb.Context(0)
+    threads = len(os.sched_getaffinity(0)) or 1
+    out = wire_leg(svb, torch, ctx, params, L, args.proofs, args.distinct, 0xB2000002, threads, args.steps)
+    print(json.dumps(out))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.wire_leg:
+        return run_wire_leg(args)
 
     import torch
     import torch.distributed as dist
@@ -416,10 +433,17 @@ def main():
                        "h2d_only_* = the same bytes copied with no compute (the PCIe ceiling of this leg)"}
 
     # the same leg from SERIALISED proofs (plonky2 wire bytes, pinned): H2D of the bytes, device unpack, public-input
-    # hashes, device transcript, query phase (sv_verify_proofs_wire).  1 GPU only; a failure is reported, not fatal.
+    # hashes, device transcript, query phase (sv_verify_proofs_wire).  1 GPU only, in a child process with a time limit:
+    # whatever happens there is reported under e2e.wire and cannot take the main measurement down with it.
     if e2e is not None and world == 1 and not args.no_wire:
+        import subprocess
         try:
-            e2e["wire"] = wire_leg(svb, torch, ctx, params, L, n_host, distinct, seed, threads, max(2, min(args.steps, 10)))
+            cmd = [sys.executable, os.path.abspath(__file__), "--wire-leg", "--workload", args.workload, "--proofs", str(n_host),
+                   "--distinct", str(distinct), "--steps", str(max(2, min(args.steps, 10)))]
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            e2e["wire"] = json.loads(lines[-1]) if r.returncode == 0 and lines else {
+                "error": f"exit {r.returncode}: {(r.stderr or r.stdout).strip()[-400:]}"}
         except Exception as ex:   # noqa: BLE001
             e2e["wire"] = {"error": f"{type(ex).__name__}: {ex}"}
 

@@ -18,3 +18,8 @@ timeout 900 python bench.py --workload outer --proofs 1024 --steps 5 > gpurun_ou
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fri_query -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_fri_b \
   python bench.py --workload outer --proofs 512 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_full_b.log 2>&1
 cat gpurun_out/${TAG}_bench_outer.json | cut -c1-400
+# wire format: the serialised-proof leg on its own, and one full capture of the gather kernel
+timeout 600 python bench.py --wire-leg --workload A --proofs 4096 --distinct 64 --steps 10 > gpurun_out/${TAG}_bench_wire.json 2> gpurun_out/${TAG}_bench_wire.err
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:wire_unpack -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_wire \
+  python bench.py --wire-leg --workload A --proofs 4096 --distinct 64 --steps 2 > gpurun_out/${TAG}_ncu_full_wire.log 2>&1
+cat gpurun_out/${TAG}_bench_wire.json | cut -c1-400

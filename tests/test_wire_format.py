@@ -226,3 +226,31 @@ def test_golden_wire_blob(svb, orc):
     for i in range(r2.shape[0]):
         rc, orec, _, opih = orc.wire_read_proof(oshape, ocommon, g["vk_cap"], g["blob"][i])
         assert rc == int(g["malformed"][i]) and (orec == g["records"][i]).all() and (opih == g["pi_hashes"][i]).all()
+
+
+def test_random_bytes_never_disagree_with_the_oracle_reader(svb, orc):
+    """Fuzz: arbitrary bytes of the right length (random blobs, and valid proofs with random byte flips) unpack to the same
+    record, public inputs, hash and malformed flag through the product's tables and through the oracle's cursor reader."""
+    params, common, L, recs, pis = make(svb, dict(hiding=True, cap=1, degree_bits=6, rate_bits=2, queries=3), n=4, n_pi=10)
+    oshape, ocommon = orc.shape_from(params.to_shape()), orc.common_from(common.to_c())
+    rng = np.random.default_rng(2024)
+    blob = svb.wire_pack(common, recs, pis)
+    nb = blob.shape[1]
+    cases = [rng.integers(0, 256, size=nb, dtype=np.uint8) for _ in range(6)]
+    cases.append(np.full(nb, 0xFF, dtype=np.uint8))
+    for i in range(24):
+        b = blob[i % 4].copy()
+        for pos in rng.integers(0, nb, size=int(rng.integers(1, 40))):
+            b[pos] = rng.integers(0, 256)
+        cases.append(b)
+    all_bytes = np.stack(cases)
+    cap = rng.integers(0, P, size=4 * L.ncap, dtype=np.uint64)
+    r2, pih, pi2, mal = svb.wire_unpack_batch(common, cap, all_bytes.reshape(-1), nthreads=3)
+    for i, b in enumerate(cases):
+        rc, orec, opis, opih = orc.wire_read_proof(oshape, ocommon, cap, b)
+        assert rc == int(mal[i]) and (orec == r2[i]).all() and (opis == pi2[i]).all() and (opih == pih[i]).all(), i
+    assert mal[:7].all()          # random bytes never carry the right length bytes
+    # unpack -> pack is the identity on the bytes whenever the length bytes are right
+    for i in np.flatnonzero(mal == 0):
+        again = svb.wire_pack(common, r2[i:i + 1], pi2[i:i + 1])[0]
+        assert (again == cases[i]).all()

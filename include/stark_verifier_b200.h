@@ -284,6 +284,61 @@ int sv_verify_proofs_wire(sv_ctx* ctx, const sv_fri_shape* shape, const sv_plonk
 /* hash_n_to_hash_no_pad over Poseidon-Goldilocks of n words (host): the public-inputs hash of one proof. */
 int sv_public_inputs_hash(const uint64_t* public_inputs, size_t n, uint64_t out[4]);
 
+/* --- plonk-level checks: the vanishing-polynomial identity at zeta ----------------- */
+#define SV_GATE_NOOP 0         /* NoopGate, chip/plonk/gates/noop.rs */
+#define SV_GATE_CONSTANT 1     /* ConstantGate { num_consts = param }, gates/constant.rs */
+#define SV_GATE_PUBLIC_INPUT 2 /* PublicInputGate, gates/public_input.rs */
+#define SV_GATE_ARITHMETIC 3   /* ArithmeticGate { num_ops = param }, gates/arithmetic.rs */
+/* not evaluated yet (sv_plonk_circuit_check refuses them): the rest of gates/mod.rs:138-196 */
+#define SV_MAX_GATES 32
+#define SV_MAX_SELECTORS 8
+#define SV_MAX_ROUTED_WIRES 128
+#define SV_MAX_PLONK_CHALLENGES 4
+#define SV_MAX_GATE_CONSTRAINTS 128
+
+typedef struct sv_plonk_gate {
+    uint32_t kind;           /* SV_GATE_* */
+    uint32_t param;          /* num_consts / num_ops */
+    uint32_t selector_index; /* SelectorsInfo.selector_indices[gate] (types/common_data.rs:56-66) */
+} sv_plonk_gate;
+
+/* What eval_vanishing_poly reads from CommonData (types/common_data.rs:68-96): gate list in CommonData.gates order
+ * (the position of a gate is its selector value), selector groups, k_is, constraint count. */
+typedef struct sv_plonk_circuit {
+    sv_plonk_common common;
+    uint32_t degree_bits;          /* FriParams.degree_bits: n = 2^degree_bits rows */
+    uint32_t num_gate_constraints; /* CommonData.num_gate_constraints */
+    uint32_t num_selectors;        /* SelectorsInfo.num_selectors() = groups.len(); the first num_selectors constants */
+    uint32_t group_lo[SV_MAX_SELECTORS], group_hi[SV_MAX_SELECTORS]; /* SelectorsInfo.groups[s] = lo..hi */
+    uint32_t num_gates;
+    sv_plonk_gate gates[SV_MAX_GATES];
+    uint64_t k_is[SV_MAX_ROUTED_WIRES]; /* CommonData.k_is, one coset shift per routed wire */
+} sv_plonk_circuit;
+
+/* 0 if the circuit description is consistent and uses only gates this library evaluates, else < 0. */
+int sv_plonk_circuit_check(const sv_plonk_circuit* circuit);
+
+/* Host: the plonk challenges of one proof -- out[0..nc) = plonk_betas, [nc..2nc) = plonk_gammas, [2nc..3nc) =
+ * plonk_alphas -- from the same transcript as sv_fri_challenges (plonk_verifier_chip.rs:65-103), which squeezes and
+ * drops them on its way to zeta. */
+int sv_plonk_challenges(const sv_fri_shape* shape, const uint64_t* record, const uint64_t circuit_digest[4],
+                        const uint64_t public_inputs_hash[4], uint32_t num_challenges, uint64_t* out);
+
+/* For each of n_proofs records (openings at off_open0 / off_open1, zeta at off_zeta): does
+ * vanishing_i(zeta) == Z_H(zeta) * sum_j quotient_{i,j}(zeta) * zeta^(n j) hold for every challenge i?  Writes
+ * ceil(n/32) bitmap words (bit = identity holds; AND it with the FRI bitmap for the verdict of
+ * verify_proof_with_challenges).  pi_hashes: n x 4 words; plonk_challenges: n x 3*num_challenges words
+ * (sv_plonk_challenges).  A non-canonical input word fails the proof.
+ * Replaces: PlonkVerifierChip::verify_proof_with_challenges up to the FRI call (plonk_verifier_chip.rs:156-210) with
+ * eval_vanishing_poly (vanishing_poly.rs:18-218) and the gate constraints of gates/{noop,constant,public_input,arithmetic}.rs.
+ * sv_plonk_check_batch: one GPU thread per proof (mem = where records / pi_hashes / plonk_challenges / accept_bitmap
+ * live); sv_plonk_check_host: the same function on CPU threads. */
+int sv_plonk_check_batch(sv_ctx* ctx, const sv_fri_shape* shape, const sv_plonk_circuit* circuit, size_t n_proofs,
+                         const uint64_t* records, const uint64_t* pi_hashes, const uint64_t* plonk_challenges,
+                         uint32_t* accept_bitmap, int mem);
+int sv_plonk_check_host(const sv_fri_shape* shape, const sv_plonk_circuit* circuit, size_t n_proofs, const uint64_t* records,
+                        const uint64_t* pi_hashes, const uint64_t* plonk_challenges, uint32_t* accept_bitmap, int nthreads);
+
 /* library / build info */
 const char* sv_version(void);
 

@@ -34,7 +34,7 @@ class OrcLayout(ctypes.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "_build", "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "wire.c", "oracle.h", "orc_field.h", "poseidon_g_constants.h", "poseidon_b_constants.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "wire.c", "plonk.c", "oracle.h", "orc_field.h", "poseidon_g_constants.h", "poseidon_b_constants.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -215,4 +215,50 @@ def wire_write_proof(shape: OrcShape, common: OrcCommon, record, public_inputs):
     pp = pis.ctypes.data if pis.size else None
     rc = _wire_lib().orc_wire_write_proof(ctypes.byref(shape), ctypes.byref(common), record.ctypes.data, pp, out.ctypes.data)
     assert rc == 0, rc
+    return out
+
+
+# -- plonk-level checks (oracle/plonk.c) -----------------------------------------------------------
+class OrcPlonkGate(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_uint32), ("param", ctypes.c_uint32), ("selector_index", ctypes.c_uint32)]
+
+
+class OrcPlonkCircuit(ctypes.Structure):
+    _fields_ = [("common", OrcCommon), ("degree_bits", ctypes.c_uint32), ("num_gate_constraints", ctypes.c_uint32),
+                ("num_selectors", ctypes.c_uint32), ("group_lo", ctypes.c_uint32 * 8), ("group_hi", ctypes.c_uint32 * 8),
+                ("num_gates", ctypes.c_uint32), ("gates", OrcPlonkGate * 32), ("k_is", ctypes.c_uint64 * 128)]
+
+
+def plonk_circuit_from(sv_circuit) -> OrcPlonkCircuit:
+    """Field-by-field copy of an sv_plonk_circuit-like ctypes struct."""
+    c = OrcPlonkCircuit()
+    c.common = common_from(sv_circuit.common)
+    for name in ("degree_bits", "num_gate_constraints", "num_selectors", "num_gates"):
+        setattr(c, name, getattr(sv_circuit, name))
+    for i in range(8):
+        c.group_lo[i], c.group_hi[i] = sv_circuit.group_lo[i], sv_circuit.group_hi[i]
+    for i in range(32):
+        g = sv_circuit.gates[i]
+        c.gates[i] = OrcPlonkGate(g.kind, g.param, g.selector_index)
+    for i in range(128):
+        c.k_is[i] = sv_circuit.k_is[i]
+    return c
+
+
+def plonk_check(circuit: OrcPlonkCircuit, open0, open1, pi_hash, chal, zeta) -> int:
+    L = lib()
+    L.orc_plonk_check.argtypes = [ctypes.POINTER(OrcPlonkCircuit)] + [ctypes.c_void_p] * 5
+    a = [np.ascontiguousarray(v, dtype=np.uint64) for v in (open0, open1, pi_hash, chal, zeta)]
+    return int(L.orc_plonk_check(ctypes.byref(circuit), *[v.ctypes.data for v in a]))
+
+
+def plonk_challenges(shape: OrcShape, record, circuit_digest, pi_hash, num_challenges=2):
+    L = lib()
+    L.orc_plonk_challenges.argtypes = [ctypes.POINTER(OrcShape), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_uint32, ctypes.c_void_p]
+    rec = np.ascontiguousarray(record, dtype=np.uint64)
+    cd = np.ascontiguousarray(circuit_digest, dtype=np.uint64)
+    ph = np.ascontiguousarray(pi_hash, dtype=np.uint64)
+    out = np.zeros(3 * num_challenges, dtype=np.uint64)
+    L.orc_plonk_challenges(ctypes.byref(shape), rec.ctypes.data, cd.ctypes.data, ph.ctypes.data, num_challenges, out.ctypes.data)
     return out

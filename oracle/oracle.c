@@ -591,3 +591,19 @@ void orc_fri_challenges(const orc_shape *s, uint64_t *rec, const uint64_t circui
     uint64_t g = orc_pow(7, (ORC_P - 1) >> s->degree_bits);
     rec[L.off_zeta_next + 0] = orc_mul(z0, g); rec[L.off_zeta_next + 1] = orc_mul(z1, g);
 }
+
+/* plonk_betas, plonk_gammas, plonk_alphas (plonk_verifier_chip.rs:86-99): the prefix of orc_fri_challenges */
+void orc_plonk_challenges(const orc_shape *s, const uint64_t *rec, const uint64_t circuit_digest[4],
+                          const uint64_t pi_hash[4], uint32_t num_challenges, uint64_t *out) {
+    orc_layout L;
+    if (orc_make_layout(s, &L)) return;
+    cur_kind = (int)s->hash_kind;
+    challenger c; ch_init(&c);
+    for (int i = 0; i < 4; i++) ch_observe(&c, circuit_digest[i]);
+    for (int i = 0; i < 4; i++) ch_observe(&c, pi_hash[i]);
+    const uint64_t *caps = rec + L.off_init_caps;
+    for (uint32_t i = 0; i < L.ncap * 4; i++) ch_observe(&c, caps[1 * L.ncap * 4 + i]);
+    for (uint32_t i = 0; i < 2 * num_challenges; i++) out[i] = ch_squeeze(&c);
+    for (uint32_t i = 0; i < L.ncap * 4; i++) ch_observe(&c, caps[2 * L.ncap * 4 + i]);
+    for (uint32_t i = 0; i < num_challenges; i++) out[2 * num_challenges + i] = ch_squeeze(&c);
+}

@@ -111,6 +111,23 @@ int orc_wire_read_proof(const orc_shape *s, const orc_common *c, const uint64_t 
 int orc_wire_write_proof(const orc_shape *s, const orc_common *c, const uint64_t *record, const uint64_t *public_inputs,
                          uint8_t *out);
 
+/* == plonk-level checks (plonk.c): the vanishing-polynomial identity at zeta == */
+typedef struct { uint32_t kind, param, selector_index; } orc_plonk_gate; /* kind: 0 noop, 1 constant, 2 public input, 3 arithmetic */
+typedef struct {
+    orc_common common;
+    uint32_t degree_bits, num_gate_constraints, num_selectors;
+    uint32_t group_lo[8], group_hi[8]; /* SelectorsInfo.groups */
+    uint32_t num_gates;
+    orc_plonk_gate gates[32];          /* CommonData.gates order */
+    uint64_t k_is[128];
+} orc_plonk_circuit;
+/* open0 / open1: FriOpenings batches (types/assigned.rs:26-40); chal = betas | gammas | alphas; 1 = identity holds */
+int orc_plonk_check(const orc_plonk_circuit *C, const uint64_t *open0, const uint64_t *open1, const uint64_t pi_hash[4],
+                    const uint64_t *chal, const uint64_t zeta[2]);
+/* the plonk challenges orc_fri_challenges squeezes on its way to zeta: out = betas | gammas | alphas */
+void orc_plonk_challenges(const orc_shape *s, const uint64_t *record, const uint64_t circuit_digest[4],
+                          const uint64_t pi_hash[4], uint32_t num_challenges, uint64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,145 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle.h).
+ *
+ * Statement-by-statement restatement of the reference's plonk-level verifier checks, materialising the same vectors
+ * the reference builds (paths relative to src/plonky2_verifier/):
+ *   verify_proof_with_challenges  chip/plonk/plonk_verifier_chip.rs:156-210
+ *   eval_vanishing_poly           chip/plonk/vanishing_poly.rs:18-124
+ *   eval_gate_constraints         vanishing_poly.rs:126-154
+ *   eval_l_0_x                    vanishing_poly.rs:156-181
+ *   check_partial_products        vanishing_poly.rs:183-218
+ *   eval_filtered_constraint      chip/plonk/gates/mod.rs:86-134
+ *   reduce_extension              chip/goldilocks_extension_chip.rs:331-342 (terms.rev().fold(0, acc*base + term))
+ *   gates: noop.rs, constant.rs:18-37, public_input.rs:22-40, arithmetic.rs:38-72
+ * Parity unpinned against a real plonky2 proof (none can be produced here); pinned instead by an independent
+ * pure-Python prover (tests/plonk_prover.py) whose proofs this restatement must accept. */
+#include "oracle.h"
+#include "orc_field.h"
+#include <stdlib.h>
+#include <string.h>
+
+#define UNUSED_SELECTOR 0xFFFFFFFFull /* gates/mod.rs:30 */
+
+static orc_fp2 at(const uint64_t *v, size_t i) { return orc2(v[2 * i], v[2 * i + 1]); }
+static orc_fp2 lift(uint64_t a) { return orc2(a, 0); }
+static orc_fp2 scalar_mul(orc_fp2 a, uint64_t s) { return orc2(orc_mul(a.c[0], s), orc_mul(a.c[1], s)); }
+
+static orc_fp2 reduce_extension(orc_fp2 base, const orc_fp2 *terms, size_t n) {
+    orc_fp2 acc = orc2(0, 0);
+    for (size_t k = n; k-- > 0;) acc = orc2_add(orc2_mul(acc, base), terms[k]);
+    return acc;
+}
+
+/* returns 1 iff accepted; <0 on a malformed circuit description */
+int orc_plonk_check(const orc_plonk_circuit *C, const uint64_t *open0, const uint64_t *open1, const uint64_t pi_hash[4],
+                    const uint64_t *chal, const uint64_t zeta_w[2]) {
+    const orc_common *c = &C->common;
+    const uint32_t nch = c->num_challenges, nr = c->num_routed_wires, qdf = c->quotient_degree_factor,
+                   npp = c->num_partial_products;
+    if (nch == 0 || qdf == 0 || (nr + qdf - 1) / qdf != npp + 1 || C->num_selectors == 0 || C->num_selectors > c->num_constants) return -1;
+    /* OpeningSetValues in FRI batch order (types/assigned.rs:26-40) */
+    const uint64_t *local_constants = open0;
+    const uint64_t *s_sigmas = local_constants + 2 * (size_t)c->num_constants;
+    const uint64_t *local_wires = s_sigmas + 2 * (size_t)nr;
+    const uint64_t *local_zs = local_wires + 2 * (size_t)c->num_wires;
+    const uint64_t *partial_products = local_zs + 2 * (size_t)nch;
+    const uint64_t *quotient_polys = partial_products + 2 * (size_t)nch * npp;
+    const uint64_t *next_zs = open1;
+    const uint64_t *betas = chal, *gammas = chal + nch, *alphas = chal + 2 * nch;
+    /* range checks of assign_value (native_chip/arithmetic_chip.rs:256-268) */
+    size_t n0 = 2 * (size_t)(c->num_constants + nr + c->num_wires + nch + nch * npp + nch * qdf);
+    for (size_t k = 0; k < n0; k++) if (open0[k] >= ORC_P) return 0;
+    for (size_t k = 0; k < 2 * (size_t)nch; k++) if (open1[k] >= ORC_P) return 0;
+    for (size_t k = 0; k < 3 * (size_t)nch; k++) if (chal[k] >= ORC_P) return 0;
+    for (int k = 0; k < 4; k++) if (pi_hash[k] >= ORC_P) return 0;
+    if (zeta_w[0] >= ORC_P || zeta_w[1] >= ORC_P) return 0;
+    const orc_fp2 x = orc2(zeta_w[0], zeta_w[1]), one = orc2(1, 0);
+
+    /* plonk_verifier_chip.rs:174-178: exp_power_of_2_extension(zeta, degree_bits) */
+    orc_fp2 x_pow_deg = x;
+    for (uint32_t i = 0; i < C->degree_bits; i++) x_pow_deg = orc2_mul(x_pow_deg, x_pow_deg);
+
+    /* ---- eval_gate_constraints ---- */
+    size_t ngc = C->num_gate_constraints;
+    orc_fp2 *constraint_terms = calloc(ngc ? ngc : 1, sizeof(orc_fp2));
+    for (uint32_t i = 0; i < C->num_gates; i++) {
+        uint32_t selector_index = C->gates[i].selector_index;
+        if (selector_index >= C->num_selectors) { free(constraint_terms); return -2; }
+        orc_fp2 f_zeta = at(local_constants, selector_index);
+        orc_fp2 filter = one;                                   /* mul_many_extension(terms) */
+        for (uint32_t k = C->group_lo[selector_index]; k < C->group_hi[selector_index]; k++)
+            if (k != i) filter = orc2_mul(filter, orc2_sub(lift(k), f_zeta));
+        if (C->num_selectors > 1) filter = orc2_mul(filter, orc2_sub(lift(UNUSED_SELECTOR), f_zeta));
+        const uint64_t *gate_constants = local_constants + 2 * (size_t)C->num_selectors;   /* gates/mod.rs:122 */
+        orc_fp2 gc[128];
+        size_t n_gc = 0;
+        switch (C->gates[i].kind) {
+            case 0: break;                                       /* NoopGate */
+            case 1:                                              /* ConstantGate: constants[i] - wires[i] */
+                for (uint32_t k = 0; k < C->gates[i].param; k++) gc[n_gc++] = orc2_sub(at(gate_constants, k), at(local_wires, k));
+                break;
+            case 2:                                              /* PublicInputGate: wires[0..4] - hash */
+                for (uint32_t k = 0; k < 4; k++) gc[n_gc++] = orc2_sub(at(local_wires, k), lift(pi_hash[k]));
+                break;
+            case 3: {                                            /* ArithmeticGate */
+                orc_fp2 const_0 = at(gate_constants, 0), const_1 = at(gate_constants, 1);
+                for (uint32_t k = 0; k < C->gates[i].param; k++) {
+                    orc_fp2 term1 = orc2_mul(orc2_mul(at(local_wires, 4 * k), at(local_wires, 4 * k + 1)), const_0);
+                    orc_fp2 term2 = orc2_mul(at(local_wires, 4 * k + 2), const_1);
+                    gc[n_gc++] = orc2_sub(at(local_wires, 4 * k + 3), orc2_add(term1, term2));
+                }
+                break;
+            }
+            default: free(constraint_terms); return -3;         /* unimplemented!() in the reference for unknown ids */
+        }
+        if (n_gc > ngc) { free(constraint_terms); return -4; }
+        for (size_t k = 0; k < n_gc; k++) constraint_terms[k] = orc2_mul_add(filter, gc[k], constraint_terms[k]);
+    }
+
+    /* ---- eval_vanishing_poly ---- */
+    size_t n_terms = nch + (size_t)nch * (npp + 1) + ngc, nt = 0;
+    orc_fp2 *vanishing_terms = calloc(n_terms, sizeof(orc_fp2));
+    /* eval_l_0_x: (x^n - 1) / (n*x - n) */
+    uint64_t n_f = (uint64_t)1 << C->degree_bits;
+    orc_fp2 zero_poly = orc2_sub(x_pow_deg, one);
+    orc_fp2 denominator = orc2_add(scalar_mul(x, n_f % ORC_P), lift(orc_neg(n_f % ORC_P)));
+    int ok = 1;
+    if (orc2_is_zero(denominator)) ok = 0;                       /* div_extension by zero */
+    orc_fp2 l_0_x = ok ? orc2_mul(zero_poly, orc2_inv(denominator)) : orc2(0, 0);
+    for (uint32_t i = 0; i < nch; i++)                           /* vanishing_z_1_terms */
+        vanishing_terms[nt++] = orc2_sub(orc2_mul(l_0_x, at(local_zs, i)), l_0_x);
+    orc_fp2 *numerator_values = calloc(nr, sizeof(orc_fp2)), *denominator_values = calloc(nr, sizeof(orc_fp2));
+    for (uint32_t i = 0; i < nch; i++) {
+        orc_fp2 beta = lift(betas[i]), gamma = lift(gammas[i]);
+        for (uint32_t j = 0; j < nr; j++) {
+            orc_fp2 s_id = scalar_mul(x, C->k_is[j]);
+            orc_fp2 wire_value_plus_gamma = orc2_add(at(local_wires, j), gamma);
+            numerator_values[j] = orc2_mul_add(beta, s_id, wire_value_plus_gamma);
+            denominator_values[j] = orc2_mul_add(beta, at(s_sigmas, j), wire_value_plus_gamma);
+        }
+        /* check_partial_products: product_accs = [z_x, partials.., z_gx], chunk_size = max_degree */
+        for (uint32_t w = 0, c0 = 0; c0 < nr; c0 += qdf, w++) {
+            orc_fp2 nume_product = one, denom_product = one;
+            for (uint32_t j = c0; j < nr && j < c0 + qdf; j++) {
+                nume_product = orc2_mul(nume_product, numerator_values[j]);
+                denom_product = orc2_mul(denom_product, denominator_values[j]);
+            }
+            orc_fp2 prev_acc = w == 0 ? at(local_zs, i) : at(partial_products, (size_t)i * npp + w - 1);
+            orc_fp2 next_acc = w == npp ? at(next_zs, i) : at(partial_products, (size_t)i * npp + w);
+            vanishing_terms[nt++] = orc2_sub(orc2_mul(prev_acc, nume_product), orc2_mul(next_acc, denom_product));
+        }
+    }
+    for (size_t k = 0; k < ngc; k++) vanishing_terms[nt++] = constraint_terms[k];
+
+    /* plonk_verifier_chip.rs:194-209 */
+    orc_fp2 z_h_zeta = orc2_sub(x_pow_deg, one);
+    for (uint32_t i = 0; i < nch && ok; i++) {
+        orc_fp2 vanishing_poly_zeta = reduce_extension(lift(alphas[i]), vanishing_terms, nt);
+        orc_fp2 chunk[64];
+        if (qdf > 64) { ok = 0; break; }
+        for (uint32_t j = 0; j < qdf; j++) chunk[j] = at(quotient_polys, (size_t)i * qdf + j);
+        orc_fp2 recombined_quotient = reduce_extension(x_pow_deg, chunk, qdf);
+        if (!orc2_eq(vanishing_poly_zeta, orc2_mul(z_h_zeta, recombined_quotient))) ok = 0;
+    }
+    free(numerator_values); free(denominator_values); free(vanishing_terms); free(constraint_terms);
+    return ok;
+}

@@ -39,4 +39,13 @@ from .api import (  # noqa: F401
     wire_pack,
     wire_unpack_batch,
     public_inputs_hash,
+    PlonkCircuit,
+    PlonkGate,
+    GATE_NOOP,
+    GATE_CONSTANT,
+    GATE_PUBLIC_INPUT,
+    GATE_ARITHMETIC,
+    make_plonk_circuit,
+    plonk_challenges,
+    plonk_check_host,
 )

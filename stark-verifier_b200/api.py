@@ -60,6 +60,23 @@ class PlonkCommon(ctypes.Structure):
         "quotient_degree_factor", "num_public_inputs")]
 
 
+GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC = 0, 1, 2, 3
+SV_MAX_GATES, SV_MAX_SELECTORS, SV_MAX_ROUTED_WIRES = 32, 8, 128
+
+
+class PlonkGate(ctypes.Structure):
+    """sv_plonk_gate"""
+    _fields_ = [("kind", ctypes.c_uint32), ("param", ctypes.c_uint32), ("selector_index", ctypes.c_uint32)]
+
+
+class PlonkCircuit(ctypes.Structure):
+    """sv_plonk_circuit: what eval_vanishing_poly reads from CommonData (types/common_data.rs:68-96)."""
+    _fields_ = [("common", PlonkCommon), ("degree_bits", ctypes.c_uint32), ("num_gate_constraints", ctypes.c_uint32),
+                ("num_selectors", ctypes.c_uint32), ("group_lo", ctypes.c_uint32 * SV_MAX_SELECTORS),
+                ("group_hi", ctypes.c_uint32 * SV_MAX_SELECTORS), ("num_gates", ctypes.c_uint32),
+                ("gates", PlonkGate * SV_MAX_GATES), ("k_is", ctypes.c_uint64 * SV_MAX_ROUTED_WIRES)]
+
+
 @dataclass
 class FriConfig:
     """types/common_data.rs:10-21"""
@@ -213,6 +230,11 @@ def lib() -> ctypes.CDLL:
     L.sv_wire_unpack_batch_gpu.argtypes = [vp, sp, cp, vp, vp, ctypes.c_size_t, ctypes.c_size_t, vp, vp, vp, ctypes.c_int]
     L.sv_verify_proofs_wire.argtypes = [vp, sp, cp, vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t, vp, vp]
     L.sv_public_inputs_hash.argtypes = [vp, ctypes.c_size_t, vp]
+    pc = ctypes.POINTER(PlonkCircuit)
+    L.sv_plonk_circuit_check.argtypes = [pc]
+    L.sv_plonk_challenges.argtypes = [sp, vp, vp, vp, ctypes.c_uint32, vp]
+    L.sv_plonk_check_host.argtypes = [sp, pc, ctypes.c_size_t, vp, vp, vp, vp, ctypes.c_int]
+    L.sv_plonk_check_batch.argtypes = [vp, sp, pc, ctypes.c_size_t, vp, vp, vp, vp, ctypes.c_int]
     _LIB = L
     return L
 
@@ -344,6 +366,59 @@ def public_inputs_hash(public_inputs) -> np.ndarray:
     if rc != 0:
         raise SvError(f"sv_public_inputs_hash failed: {rc}")
     return out
+
+
+# -- plonk-level checks ----------------------------------------------------------------
+def make_plonk_circuit(common: CommonData, gates, groups, k_is, num_gate_constraints: int) -> PlonkCircuit:
+    """gates: [(kind, param)] in CommonData.gates order; groups: [(lo, hi)] = SelectorsInfo.groups; the selector index
+    of a gate is the group that contains its position (SelectorsInfo.selector_indices)."""
+    c = PlonkCircuit()
+    c.common = common.to_c()
+    c.degree_bits = common.fri_params.degree_bits
+    c.num_gate_constraints = num_gate_constraints
+    c.num_selectors = len(groups)
+    for s, (lo, hi) in enumerate(groups):
+        c.group_lo[s], c.group_hi[s] = lo, hi
+    c.num_gates = len(gates)
+    for i, (kind, param) in enumerate(gates):
+        sel = [s for s, (lo, hi) in enumerate(groups) if lo <= i < hi]
+        if len(sel) != 1:
+            raise SvError(f"gate {i} is not in exactly one selector group")
+        c.gates[i] = PlonkGate(kind, param, sel[0])
+    for j, k in enumerate(k_is):
+        c.k_is[j] = int(k)
+    rc = lib().sv_plonk_circuit_check(ctypes.byref(c))
+    if rc != 0:
+        raise SvError(f"sv_plonk_circuit_check refused the circuit: {rc}")
+    return c
+
+
+def plonk_challenges(params: FriParams, record: np.ndarray, circuit_digest, pi_hash, num_challenges: int = 2) -> np.ndarray:
+    """[betas | gammas | alphas] of one proof (plonk_verifier_chip.rs:65-103), host."""
+    s = params.to_shape()
+    cd = np.ascontiguousarray(circuit_digest, dtype=np.uint64)
+    ph = np.ascontiguousarray(pi_hash, dtype=np.uint64)
+    out = np.zeros(3 * num_challenges, dtype=np.uint64)
+    rc = lib().sv_plonk_challenges(ctypes.byref(s), _ptr(record), _ptr(cd), _ptr(ph), num_challenges, _ptr(out))
+    if rc != 0:
+        raise SvError(f"sv_plonk_challenges failed: {rc}")
+    return out
+
+
+def plonk_check_host(params: FriParams, circuit: PlonkCircuit, records, pi_hashes, plonk_chal, nthreads: int = 1) -> np.ndarray:
+    """The vanishing-polynomial identity of every record, on CPU threads (the function the device kernel runs)."""
+    s = params.to_shape()
+    records = np.ascontiguousarray(records, dtype=np.uint64)
+    n = records.shape[0]
+    pi_hashes = np.ascontiguousarray(pi_hashes, dtype=np.uint64)
+    plonk_chal = np.ascontiguousarray(plonk_chal, dtype=np.uint64)
+    assert pi_hashes.size == 4 * n and plonk_chal.size == 3 * circuit.common.num_challenges * n
+    bm = np.zeros((n + 31) // 32, dtype=np.uint32)
+    rc = lib().sv_plonk_check_host(ctypes.byref(s), ctypes.byref(circuit), n, _ptr(records), _ptr(pi_hashes), _ptr(plonk_chal),
+                                   _ptr(bm), nthreads)
+    if rc != 0:
+        raise SvError(f"sv_plonk_check_host failed: {rc}")
+    return bm
 
 
 class Context:
@@ -523,6 +598,21 @@ class Context:
                                                  n_proofs, _ptr(bitmap), _ptr(ff) if ff is not None else None),
                  "sv_verify_proofs_wire")
         return (bitmap, ff) if want_fail else bitmap
+
+    def plonk_check_batch(self, params: FriParams, circuit: PlonkCircuit, records, pi_hashes, plonk_chal,
+                          n_proofs: Optional[int] = None, accept_bitmap=None, mem: int = MEM_HOST):
+        """plonk_check_kernel: the vanishing-polynomial identity of every record, one GPU thread per proof."""
+        s = params.to_shape()
+        if mem == MEM_HOST:
+            records = np.ascontiguousarray(records, dtype=np.uint64)
+            n_proofs = records.shape[0]
+            pi_hashes = np.ascontiguousarray(pi_hashes, dtype=np.uint64)
+            plonk_chal = np.ascontiguousarray(plonk_chal, dtype=np.uint64)
+            accept_bitmap = np.zeros((n_proofs + 31) // 32, dtype=np.uint32)
+        self._ck(self._lib.sv_plonk_check_batch(self._h, ctypes.byref(s), ctypes.byref(circuit), n_proofs, _ptr(records),
+                                                _ptr(pi_hashes), _ptr(plonk_chal), _ptr(accept_bitmap), mem),
+                 "sv_plonk_check_batch")
+        return accept_bitmap
 
     def allgather_bitmap(self, nccl_comm: int, local_ptr: int, all_ptr: int, words_per_rank: int):
         self._ck(self._lib.sv_allgather_bitmap(self._h, ctypes.c_void_p(nccl_comm), local_ptr, all_ptr, words_per_rank),

@@ -3,6 +3,7 @@
 #include "../../include/stark_verifier_b200.h"
 #include "fri_kernels.cuh"
 #include "wire_kernels.cuh"
+#include "plonk_kernels.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -45,6 +46,9 @@ struct sv_ctx {
     u64* d_wvk = nullptr; size_t wvk_words = 0;
     u64* d_wire[SV_NBUF] = {}; size_t wire_words[SV_NBUF] = {};
     u32* d_mal = nullptr; size_t mal_words = 0;
+    // plonk-level checks: the circuit description on the device, staging for the host path
+    sv_plonk_circuit* d_circuit = nullptr; sv_plonk_circuit h_circuit; bool circuit_valid = false;
+    u64* d_chal = nullptr; size_t chal_words = 0;
     uint64_t launches = 0;
     // optional CUDA-event timing of the dominant kernel (fri_query_kernel / merkle / permute), on
     // the stream it is launched on
@@ -152,6 +156,8 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaFree(c->d_wvk);
     for (int i = 0; i < SV_NBUF; i++) cudaFree(c->d_wire[i]);
     cudaFree(c->d_mal);
+    cudaFree(c->d_circuit);
+    cudaFree(c->d_chal);
     auto drop_s = [](cudaStream_t s) { if (s) cudaStreamDestroy(s); };
     auto drop_e = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
     drop_e(c->ev_hdr); drop_e(c->ev_fs);
@@ -784,6 +790,58 @@ extern "C" int sv_verify_proofs_wire(sv_ctx* c, const sv_fri_shape* shape, const
         c->err = keep;
     }
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Plonk-level checks: plonk_check_kernel, one thread per proof.
+namespace svb { int plonk_shape_matches(const sv_fri_shape& s, const sv_plonk_circuit& C); }
+
+extern "C" int sv_plonk_check_batch(sv_ctx* c, const sv_fri_shape* shape, const sv_plonk_circuit* circuit, size_t n,
+                                    const uint64_t* records, const uint64_t* pi_hashes, const uint64_t* chal,
+                                    uint32_t* accept_bitmap, int mem) {
+    if (!c || !shape || !circuit || !accept_bitmap || (n && (!records || !pi_hashes || !chal))) return -1;
+    if (!known_mem(mem)) return fail(c, -5, "mem %d is neither SV_MEM_HOST nor SV_MEM_DEVICE", mem);
+    sv_fri_layout L;
+    if (make_layout(*shape, L)) return fail(c, -8, "bad FRI shape");
+    if (int rc = plonk_circuit_check(*circuit)) return fail(c, -8, "plonk circuit description refused (%d)", rc);
+    if (int rc = plonk_shape_matches(*shape, *circuit)) return fail(c, -8, "FRI shape and plonk circuit disagree (%d)", rc);
+    if (n == 0) return 0;
+    if (n >= (1ull << 31)) return fail(c, -8, "batch too large for one call");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t s = mem == SV_MEM_DEVICE ? c->stream : c->own_stream;
+    if (!c->d_circuit) CK(c, cudaMalloc((void**)&c->d_circuit, sizeof(sv_plonk_circuit)));
+    if (!c->circuit_valid || memcmp(&c->h_circuit, circuit, sizeof *circuit)) {
+        if (int rc = sv_ctx_synchronize(c)) return rc;       // an earlier call may still read the old description
+        c->h_circuit = *circuit;
+        CK(c, cudaMemcpyAsync(c->d_circuit, &c->h_circuit, sizeof(sv_plonk_circuit), cudaMemcpyHostToDevice, s));
+        CK(c, cudaStreamSynchronize(s));
+        c->circuit_valid = true;
+    }
+    PlonkRecordView V = {L.record_words, L.off_open0, L.off_open1, L.off_zeta};
+    const u32 nch = circuit->common.num_challenges;
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    if (mem == SV_MEM_DEVICE) {
+        plonk_check_kernel<<<grid, 128, 0, s>>>(records, V, c->d_circuit, pi_hashes, chal, (u32)n, accept_bitmap);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        return 0;
+    }
+    // host buffers: only the record headers travel
+    const size_t hw = L.header_words, n_words = (n + 31) / 32;
+    if (grow(c, c->d_hdr, c->hdr_words, n * hw)) return -6;
+    if (grow(c, c->d_pi, c->pi_words, 4 * n)) return -6;
+    if (grow(c, c->d_chal, c->chal_words, 3 * (size_t)nch * n)) return -6;
+    if (grow(c, c->d_bitmap, c->bitmap_words, n_words)) return -6;
+    CK(c, cudaMemcpy2DAsync(c->d_hdr, hw * 8, records, (size_t)L.record_words * 8, hw * 8, n, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(c->d_pi, pi_hashes, n * 32, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(c->d_chal, chal, 3 * (size_t)nch * n * 8, cudaMemcpyHostToDevice, s));
+    V.record_words = (u32)hw;                                // the headers are packed back to back
+    plonk_check_kernel<<<grid, 128, 0, s>>>(c->d_hdr, V, c->d_circuit, c->d_pi, c->d_chal, (u32)n, c->d_bitmap);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(accept_bitmap, c->d_bitmap, n_words * 4, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

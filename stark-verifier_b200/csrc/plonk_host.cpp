@@ -1,0 +1,91 @@
+// Host side of the plonk-level checks: circuit validation, the plonk challenges of the transcript, and
+// the CPU twin of the per-proof check (plonk_check.hpp) -- the function the device kernel runs, on CPU threads.
+#include "plonk_check.hpp"
+#include "host_util.hpp"
+#include "layout.hpp"
+
+using namespace svb;
+
+namespace svb {
+// the shape must describe the same openings as the circuit's common data (CommonData::fri_oracles)
+int plonk_shape_matches(const sv_fri_shape& s, const sv_plonk_circuit& C) {
+    const sv_plonk_common& c = C.common;
+    if (s.degree_bits != C.degree_bits) return -20;
+    if (s.oracle_num_polys[0] != c.num_constants + c.num_routed_wires || s.oracle_num_polys[1] != c.num_wires ||
+        s.oracle_num_polys[2] != c.num_challenges * (1 + c.num_partial_products) ||
+        s.oracle_num_polys[3] != c.num_challenges * c.quotient_degree_factor || s.num_zs != c.num_challenges)
+        return -21;
+    return 0;
+}
+}  // namespace svb
+
+extern "C" int sv_plonk_circuit_check(const sv_plonk_circuit* circuit) {
+    if (!circuit) return -1;
+    return plonk_circuit_check(*circuit);
+}
+
+// Same duplex sponge as Challenger in host_side.cpp, up to the plonk alphas (plonk_verifier_chip.rs:65-103).
+extern "C" int sv_plonk_challenges(const sv_fri_shape* shape, const uint64_t* rec, const uint64_t circuit_digest[4],
+                                   const uint64_t pi_hash[4], uint32_t nc, uint64_t* out) {
+    sv_fri_layout L;
+    if (!shape || !rec || !circuit_digest || !pi_hash || !out || make_layout(*shape, L)) return -1;
+    if (shape->hash_kind > SV_HASH_POSEIDON_BN254 || nc == 0 || nc > SV_MAX_PLONK_CHALLENGES) return -2;
+    const u32 kind = shape->hash_kind;
+    u64 st[12] = {0}, in[8], outb[8];
+    int n_in = 0, n_out = 0;
+    auto duplex = [&](int len) {
+        for (int i = 0; i < len; i++) st[i] = in[i];
+        permute_kind(kind, st);
+        memcpy(outb, st, 64);
+        n_out = 8;
+        n_in = 0;
+    };
+    auto observe = [&](u64 v) {
+        n_out = 0;
+        in[n_in++] = v;
+        if (n_in == 8) duplex(8);
+    };
+    auto squeeze = [&]() {
+        if (n_in) duplex(n_in);
+        if (n_out == 0) {
+            permute_kind(kind, st);
+            memcpy(outb, st, 64);
+            n_out = 8;
+        }
+        return outb[--n_out];
+    };
+    const u32 capw = L.ncap * 4;
+    const u64* caps = rec + L.off_init_caps;
+    for (int i = 0; i < 4; i++) observe(circuit_digest[i]);
+    for (int i = 0; i < 4; i++) observe(pi_hash[i]);
+    for (u32 i = 0; i < capw; i++) observe(caps[1 * capw + i]);         // wires_cap
+    for (u32 i = 0; i < nc; i++) out[i] = squeeze();                    // plonk_betas
+    for (u32 i = 0; i < nc; i++) out[nc + i] = squeeze();               // plonk_gammas
+    for (u32 i = 0; i < capw; i++) observe(caps[2 * capw + i]);         // plonk_zs_partial_products_cap
+    for (u32 i = 0; i < nc; i++) out[2 * nc + i] = squeeze();           // plonk_alphas
+    return 0;
+}
+
+extern "C" int sv_plonk_check_host(const sv_fri_shape* shape, const sv_plonk_circuit* C, size_t n, const uint64_t* records,
+                                   const uint64_t* pi_hashes, const uint64_t* chal, uint32_t* bitmap, int nthreads) {
+    sv_fri_layout L;
+    if (!shape || !C || !bitmap || (n && (!records || !pi_hashes || !chal)) || make_layout(*shape, L)) return -1;
+    if (int rc = plonk_circuit_check(*C)) return rc;
+    if (int rc = plonk_shape_matches(*shape, *C)) return rc;
+    const size_t words = (n + 31) / 32;
+    const u32 nch = C->common.num_challenges;
+    if (nthreads < 1) nthreads = 1;
+    parallel_for(words, nthreads, [&](size_t b, size_t e) {
+        for (size_t w = b; w < e; w++) {
+            u32 bits = 0;
+            for (size_t p = 32 * w; p < n && p < 32 * w + 32; p++) {
+                const u64* rec = records + p * (size_t)L.record_words;
+                bool ok = plonk_check_one(*C, rec + L.off_open0, rec + L.off_open1, pi_hashes + 4 * p, chal + 3 * (size_t)nch * p,
+                                          mk2(rec[L.off_zeta], rec[L.off_zeta + 1]));
+                bits |= (u32)ok << (p & 31);
+            }
+            bitmap[w] = bits;
+        }
+    });
+    return 0;
+}

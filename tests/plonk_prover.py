@@ -1,0 +1,229 @@
+"""TEST INFRASTRUCTURE: a miniature plonky2-style prover in pure Python (big integers), just enough to produce openings
+that satisfy the vanishing-polynomial identity the verifier checks (reference: chip/plonk/plonk_verifier_chip.rs:156-210,
+chip/plonk/vanishing_poly.rs) for a small circuit over the gates {Noop, Constant, PublicInput, Arithmetic}.
+
+It follows the protocol, not the verifier's code: witness rows -> copy-constraint permutation -> sigma polynomials ->
+grand products Z with partial products -> vanishing polynomial on a coset -> division by Z_H -> quotient chunks ->
+openings at a random zeta in F_p^2.  It shares no code with the product (stark-verifier_b200/csrc/plonk_check.hpp) or the
+oracle (oracle/plonk.c); those restate the reference's verifier, and accepting this prover's output is the evidence
+that the restatements are right.  Sizes are tiny (2^4 rows), so everything is naive O(n^2)."""
+import numpy as np
+
+P = 0xFFFFFFFF00000001
+UNUSED_SELECTOR = 0xFFFFFFFF
+GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC = 0, 1, 2, 3
+
+
+def inv(a):
+    return pow(a, P - 2, P)
+
+
+# F_p^2 = F_p[X]/(X^2 - 7), elements as (c0, c1)
+def e_add(a, b): return ((a[0] + b[0]) % P, (a[1] + b[1]) % P)
+def e_mul(a, b): return ((a[0] * b[0] + 7 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+def e_scale(a, s): return (a[0] * s % P, a[1] * s % P)
+
+
+def poly_eval_ext(coeffs, z):
+    acc = (0, 0)
+    for c in reversed(coeffs):
+        acc = e_add(e_mul(acc, z), (c, 0))
+    return acc
+
+
+def poly_eval(coeffs, x):
+    acc = 0
+    for c in reversed(coeffs):
+        acc = (acc * x + c) % P
+    return acc
+
+
+class Circuit:
+    """Configuration of the toy circuit.  gates: list of (kind, param) in CommonData.gates order; groups: selector
+    groups as (lo, hi) ranges over gate indices."""
+
+    def __init__(self, degree_bits=4, num_wires=13, num_routed_wires=12, num_challenges=2, quotient_degree_factor=8,
+                 groups=((0, 4),)):
+        self.degree_bits = degree_bits
+        self.n = 1 << degree_bits
+        self.num_wires, self.num_routed_wires, self.num_challenges = num_wires, num_routed_wires, num_challenges
+        self.qdf = quotient_degree_factor
+        self.num_ops = num_routed_wires // 4                       # ArithmeticGate::new_from_config
+        self.gates = [(GATE_NOOP, 0), (GATE_CONSTANT, 2), (GATE_PUBLIC_INPUT, 0), (GATE_ARITHMETIC, self.num_ops)]
+        self.groups = list(groups)
+        self.num_selectors = len(self.groups)
+        self.num_constants = self.num_selectors + 2
+        self.num_partial_products = (num_routed_wires + self.qdf - 1) // self.qdf - 1
+        self.num_gate_constraints = max(2, 4, self.num_ops)
+        self.k_is = [pow(7, j, P) for j in range(num_routed_wires)]   # distinct cosets of the trace subgroup
+        self.g = pow(7, (P - 1) >> degree_bits, P)
+
+    def selector_index(self, gate):
+        return next(s for s, (lo, hi) in enumerate(self.groups) if lo <= gate < hi)
+
+
+def _constraints(C, consts, wires, pi_hash):
+    """Unfiltered-then-filtered gate constraints at one point, base field (the prover's own statement of the gates)."""
+    out = [0] * C.num_gate_constraints
+    gc = consts[C.num_selectors:]
+    for i, (kind, param) in enumerate(C.gates):
+        s = C.selector_index(i)
+        lo, hi = C.groups[s]
+        f = 1
+        for k in range(lo, hi):
+            if k != i:
+                f = f * (k - consts[s]) % P
+        if C.num_selectors > 1:
+            f = f * (UNUSED_SELECTOR - consts[s]) % P
+        if kind == GATE_CONSTANT:
+            cs = [(gc[k] - wires[k]) % P for k in range(param)]
+        elif kind == GATE_PUBLIC_INPUT:
+            cs = [(wires[k] - pi_hash[k]) % P for k in range(4)]
+        elif kind == GATE_ARITHMETIC:
+            cs = [(wires[4 * k + 3] - (gc[0] * wires[4 * k] * wires[4 * k + 1] + gc[1] * wires[4 * k + 2])) % P for k in range(param)]
+        else:
+            cs = []
+        for k, c in enumerate(cs):
+            out[k] = (out[k] + f * c) % P
+    return out
+
+
+def prove(C, seed, pi_hash):
+    """-> dict(open0=[...Fp2], open1=[...], betas, gammas, alphas, zeta)"""
+    rng = np.random.default_rng(seed)
+    rnd = lambda: int(rng.integers(0, P, dtype=np.uint64))
+    n, nr, nw, nch, qdf, npp = C.n, C.num_routed_wires, C.num_wires, C.num_challenges, C.qdf, C.num_partial_products
+    g = C.g
+    # ---- witness -------------------------------------------------------------------------------------
+    row_gate = [GATE_NOOP] * n
+    row_gate[0] = GATE_PUBLIC_INPUT
+    row_gate[1] = row_gate[2] = GATE_CONSTANT
+    for r in range(3, n - 2):
+        row_gate[r] = GATE_ARITHMETIC
+    wires = [[rnd() for _ in range(nw)] for _ in range(n)]
+    consts = [[0] * C.num_constants for _ in range(n)]
+    parent = {}
+
+    def find(c):
+        while parent.setdefault(c, c) != c:
+            parent[c] = parent[parent[c]]
+            c = parent[c]
+        return c
+
+    filled = []   # routed cells whose value is final and may be copied
+    for r in range(n):
+        gate = row_gate[r]                       # gate index == kind in this toy gate list
+        for s, (lo, hi) in enumerate(C.groups):
+            consts[r][s] = gate if lo <= gate < hi else UNUSED_SELECTOR
+        gc0, gc1 = rnd(), rnd()
+        consts[r][C.num_selectors], consts[r][C.num_selectors + 1] = gc0, gc1
+        if gate == GATE_PUBLIC_INPUT:
+            wires[r][0:4] = list(pi_hash)
+        elif gate == GATE_CONSTANT:
+            wires[r][0], wires[r][1] = gc0, gc1
+        elif gate == GATE_ARITHMETIC:
+            for k in range(C.num_ops):
+                for col in (4 * k, 4 * k + 1, 4 * k + 2):
+                    if filled and rng.random() < 0.6:           # copy constraint to an earlier cell
+                        src = filled[int(rng.integers(0, len(filled)))]
+                        wires[r][col] = wires[src[0]][src[1]]
+                        parent[find((r, col))] = find(src)
+                wires[r][4 * k + 3] = (gc0 * wires[r][4 * k] * wires[r][4 * k + 1] + gc1 * wires[r][4 * k + 2]) % P
+        filled.extend((r, col) for col in range(nr))
+    # ---- permutation ---------------------------------------------------------------------------------
+    classes = {}
+    for r in range(n):
+        for col in range(nr):
+            classes.setdefault(find((r, col)), []).append((r, col))
+    sigma = {}
+    for cells in classes.values():
+        for a, b in zip(cells, cells[1:] + cells[:1]):
+            assert wires[a[0]][a[1]] == wires[b[0]][b[1]]
+            sigma[a] = b
+    gpow = [pow(g, r, P) for r in range(n)]
+    sig_vals = [[C.k_is[sigma[(r, col)][1]] * gpow[sigma[(r, col)][0]] % P for col in range(nr)] for r in range(n)]
+    assert any(sigma[c] != c for c in sigma), "the permutation should not be trivial"
+
+    # ---- grand products ------------------------------------------------------------------------------
+    betas, gammas, alphas = [rnd() for _ in range(nch)], [rnd() for _ in range(nch)], [rnd() for _ in range(nch)]
+    z_vals, pp_vals = [], []
+    for i in range(nch):
+        z = [1] * (n + 1)
+        pp = [[0] * n for _ in range(npp)]
+        for r in range(n):
+            acc = z[r]
+            for w, c0 in enumerate(range(0, nr, qdf)):
+                for col in range(c0, min(nr, c0 + qdf)):
+                    num = (betas[i] * C.k_is[col] * gpow[r] + wires[r][col] + gammas[i]) % P
+                    den = (betas[i] * sig_vals[r][col] + wires[r][col] + gammas[i]) % P
+                    acc = acc * num % P * inv(den) % P
+                if w < npp:
+                    pp[w][r] = acc
+            z[r + 1] = acc
+        assert z[n] == 1, "copy constraints violated"
+        z_vals.append(z[:n])
+        pp_vals.append(pp)
+
+    # ---- interpolation over the trace subgroup -------------------------------------------------------
+    ninv = inv(n)
+
+    def interpolate(vals):
+        return [ninv * sum(v * pow(g, (-j * r) % n, P) for r, v in enumerate(vals)) % P for j in range(n)]
+
+    const_polys = [interpolate([consts[r][k] for r in range(n)]) for k in range(C.num_constants)]
+    sigma_polys = [interpolate([sig_vals[r][col] for r in range(n)]) for col in range(nr)]
+    wire_polys = [interpolate([wires[r][col] for r in range(n)]) for col in range(nw)]
+    z_polys = [interpolate(z) for z in z_vals]
+    pp_polys = [[interpolate(pp_vals[i][w]) for w in range(npp)] for i in range(nch)]
+
+    # ---- vanishing polynomial on a coset, quotient ---------------------------------------------------
+    m = 16 * n
+    wm = pow(7, (P - 1) // m, P)
+    shift = 7
+    q_vals = [[0] * m for _ in range(nch)]
+    for t in range(m):
+        x = shift * pow(wm, t, P) % P
+        cv = [poly_eval(p, x) for p in const_polys]
+        sv = [poly_eval(p, x) for p in sigma_polys]
+        wv = [poly_eval(p, x) for p in wire_polys]
+        zh = (pow(x, n, P) - 1) % P
+        l0 = zh * inv(n * (x - 1) % P) % P
+        gate_terms = _constraints(C, cv, wv, pi_hash)
+        terms_z1, terms_pp = [], []
+        for i in range(nch):
+            zx, zgx = poly_eval(z_polys[i], x), poly_eval(z_polys[i], g * x % P)
+            terms_z1.append(l0 * (zx - 1) % P)
+            accs = [zx] + [poly_eval(p, x) for p in pp_polys[i]] + [zgx]
+            for w, c0 in enumerate(range(0, nr, qdf)):
+                num = den = 1
+                for col in range(c0, min(nr, c0 + qdf)):
+                    num = num * ((betas[i] * C.k_is[col] * x + wv[col] + gammas[i]) % P) % P
+                    den = den * ((betas[i] * sv[col] + wv[col] + gammas[i]) % P) % P
+                terms_pp.append((accs[w] * num - accs[w + 1] * den) % P)
+        terms = terms_z1 + terms_pp + gate_terms
+        zh_inv = inv(zh)
+        for i in range(nch):
+            v, ap = 0, 1
+            for term in terms:
+                v = (v + term * ap) % P
+                ap = ap * alphas[i] % P
+            q_vals[i][t] = v * zh_inv % P
+    minv = inv(m)
+    winv = [pow(wm, (-t) % m, P) for t in range(m)]
+    quotient_chunks = []
+    for i in range(nch):
+        coeffs = []
+        for j in range(m):
+            c = minv * sum(q_vals[i][t] * winv[(j * t) % m] for t in range(m)) % P
+            coeffs.append(c * inv(pow(shift, j, P)) % P)
+        assert all(c == 0 for c in coeffs[qdf * n:]), "quotient degree too high: the constraints do not vanish on H"
+        quotient_chunks.append([coeffs[j * n:(j + 1) * n] for j in range(qdf)])
+
+    # ---- openings ------------------------------------------------------------------------------------
+    zeta = (rnd(), rnd())
+    gz = e_scale(zeta, g)
+    open0 = [poly_eval_ext(p, zeta) for p in const_polys + sigma_polys + wire_polys + z_polys]
+    open0 += [poly_eval_ext(pp_polys[i][w], zeta) for i in range(nch) for w in range(npp)]
+    open0 += [poly_eval_ext(quotient_chunks[i][j], zeta) for i in range(nch) for j in range(qdf)]
+    open1 = [poly_eval_ext(p, gz) for p in z_polys]
+    return dict(open0=open0, open1=open1, betas=betas, gammas=gammas, alphas=alphas, zeta=zeta)

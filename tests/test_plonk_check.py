@@ -1,0 +1,151 @@
+"""Plonk-level checks, CPU side: proofs from the independent pure-Python prover (tests/plonk_prover.py) must
+be accepted by the product's check (plonk_check.hpp through sv_plonk_check_host -- the function the device kernel runs)
+and by the oracle's statement-by-statement restatement (oracle/plonk.c); every corruption must be rejected by both; on
+arbitrary (non-satisfying) inputs the two must agree."""
+import numpy as np
+import pytest
+
+import plonk_prover as pp
+from common import P, bit
+
+CONFIGS = {
+    "one_selector": dict(),
+    "two_selectors": dict(groups=((0, 2), (2, 4))),
+    "one_challenge_no_partials": dict(num_challenges=1, num_routed_wires=8, num_wires=8, quotient_degree_factor=8),
+    "three_chunks": dict(num_routed_wires=16, num_wires=18, quotient_degree_factor=7, groups=((0, 3), (3, 4))),
+}
+
+
+def setup(svb, cfg):
+    C = pp.Circuit(**cfg)
+    widths = (C.num_constants + C.num_routed_wires, C.num_wires, C.num_challenges * (1 + C.num_partial_products),
+              C.num_challenges * C.qdf)
+    params = svb.api._params(C.degree_bits, 3, 1, 2, 2, oracle_num_polys=widths, num_zs=C.num_challenges)
+    common = svb.CommonData.for_params(params, num_public_inputs=0, num_constants=C.num_constants)
+    circuit = svb.make_plonk_circuit(common, C.gates, C.groups, C.k_is, C.num_gate_constraints)
+    return C, params, circuit, svb.api.make_layout(params)
+
+
+def to_records(L, proofs):
+    recs = np.zeros((len(proofs), L.record_words), dtype=np.uint64)
+    chal = []
+    for i, pr in enumerate(proofs):
+        o0 = np.array([w for e in pr["open0"] for w in e], dtype=np.uint64)
+        o1 = np.array([w for e in pr["open1"] for w in e], dtype=np.uint64)
+        assert o0.size == 2 * L.n0 and o1.size == 2 * L.n1
+        recs[i, L.off_open0:L.off_open0 + o0.size] = o0
+        recs[i, L.off_open1:L.off_open1 + o1.size] = o1
+        recs[i, L.off_zeta:L.off_zeta + 2] = pr["zeta"]
+        chal.append(pr["betas"] + pr["gammas"] + pr["alphas"])
+    return recs, np.array(chal, dtype=np.uint64)
+
+
+def oracle_bits(orc, ocirc, L, recs, pih, chal):
+    return [orc.plonk_check(ocirc, r[L.off_open0:L.off_open0 + 2 * L.n0], r[L.off_open1:L.off_open1 + 2 * L.n1], pih[i], chal[i],
+                            r[L.off_zeta:L.off_zeta + 2]) for i, r in enumerate(recs)]
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_prover_accepted_corruptions_rejected(svb, orc, name):
+    C, params, circuit, L = setup(svb, CONFIGS[name])
+    ocirc = orc.plonk_circuit_from(circuit)
+    rng = np.random.default_rng(7)
+    n = 3
+    pih = rng.integers(0, P, size=(n, 4), dtype=np.uint64)
+    proofs = [pp.prove(C, 100 + i, [int(x) for x in pih[i]]) for i in range(n)]
+    recs, chal = to_records(L, proofs)
+    bm = svb.plonk_check_host(params, circuit, recs, pih, chal, nthreads=2)
+    assert [bit(bm, i) for i in range(n)] == [1] * n
+    assert oracle_bits(orc, ocirc, L, recs, pih, chal) == [1] * n
+    # one flipped bit in every kind of input: constants, sigmas, wires, zs, partial products, quotient, zs_next, zeta,
+    # beta, gamma, alpha, public-inputs hash
+    nc, nr, nw, nch, npp, qdf = C.num_constants, C.num_routed_wires, C.num_wires, C.num_challenges, C.num_partial_products, C.qdf
+    starts = np.cumsum([0, nc, nr, nw, nch, nch * npp, nch * qdf])
+    spots = [("open", L.off_open0 + 2 * int(rng.integers(starts[k], starts[k + 1])) + int(rng.integers(0, 2)))
+             for k in range(6) if starts[k + 1] > starts[k]]
+    spots += [("open", L.off_open1 + int(rng.integers(0, 2 * nch))), ("open", L.off_zeta + 1)]
+    spots += [("chal", k * nch + int(rng.integers(0, nch))) for k in range(3)] + [("pih", int(rng.integers(0, 4)))]
+    bad_recs = np.repeat(recs[:1], len(spots), axis=0)
+    bad_chal = np.repeat(chal[:1], len(spots), axis=0)
+    bad_pih = np.repeat(pih[:1], len(spots), axis=0)
+    for i, (what, at) in enumerate(spots):
+        {"open": bad_recs, "chal": bad_chal, "pih": bad_pih}[what][i, at] ^= np.uint64(1 << int(rng.integers(0, 40)))
+    bm = svb.plonk_check_host(params, circuit, bad_recs, bad_pih, bad_chal)
+    got = [bit(bm, i) for i in range(len(spots))]
+    want = oracle_bits(orc, ocirc, L, bad_recs, bad_pih, bad_chal)
+    assert got == want
+    # a wire that no gate constrains on any row's filter can still not change: every opening enters the identity
+    assert got == [0] * len(spots), [s for s, g in zip(spots, got) if g]
+
+
+def test_wrong_public_inputs_hash_is_rejected(svb, orc):
+    C, params, circuit, L = setup(svb, CONFIGS["one_selector"])
+    pih = np.array([[5, 6, 7, 8]], dtype=np.uint64)
+    recs, chal = to_records(L, [pp.prove(C, 1, [5, 6, 7, 8])])
+    assert bit(svb.plonk_check_host(params, circuit, recs, pih, chal), 0) == 1
+    other = np.array([[5, 6, 7, 9]], dtype=np.uint64)
+    assert bit(svb.plonk_check_host(params, circuit, recs, other, chal), 0) == 0
+
+
+def test_product_and_oracle_agree_on_arbitrary_inputs(svb, orc):
+    """Differential test in the style of the reference's own gate tests (gates/gate_test.rs:154-176): random inputs,
+    the two restatements must give the same verdict -- including the corner cases below."""
+    C, params, circuit, L = setup(svb, CONFIGS["two_selectors"])
+    ocirc = orc.plonk_circuit_from(circuit)
+    rng = np.random.default_rng(11)
+    n = 40
+    recs = np.zeros((n, L.record_words), dtype=np.uint64)
+    recs[:, :L.header_words] = rng.integers(0, P, size=(n, L.header_words), dtype=np.uint64)
+    pih = rng.integers(0, P, size=(n, 4), dtype=np.uint64)
+    chal = rng.integers(0, P, size=(n, 3 * C.num_challenges), dtype=np.uint64)
+    good, gchal = to_records(L, [pp.prove(C, 9, [int(x) for x in pih[0]])])
+    recs[0], chal[0] = good[0], gchal[0]
+    recs[1], chal[1] = good[0], gchal[0]
+    recs[1, L.off_zeta:L.off_zeta + 2] = (1, 0)            # zeta = 1: L_0 denominator is zero -> reject (division by zero)
+    recs[2], chal[2] = good[0], gchal[0]
+    recs[2, L.off_open0 + 3] = np.uint64(P)                # non-canonical opening word
+    recs[3], chal[3] = good[0], gchal[0]
+    chal[3, 0] = np.uint64(P + 5)                          # non-canonical challenge
+    bm = svb.plonk_check_host(params, circuit, recs, pih, chal, nthreads=3)
+    got = [bit(bm, i) for i in range(n)]
+    assert got == oracle_bits(orc, ocirc, L, recs, pih, chal)
+    assert got[:4] == [1, 0, 0, 0] and sum(got) == 1
+
+
+def test_unknown_gates_and_inconsistent_circuits_are_refused(svb):
+    C, params, circuit, L = setup(svb, CONFIGS["one_selector"])
+    common = svb.CommonData.for_params(params, num_public_inputs=0, num_constants=C.num_constants)
+    with pytest.raises(svb.SvError):       # a gate kind this library does not evaluate (e.g. PoseidonGate): never a silent accept
+        svb.make_plonk_circuit(common, C.gates + [(17, 0)], [(0, 5)], C.k_is, C.num_gate_constraints)
+    with pytest.raises(svb.SvError):       # partial products inconsistent with the routed wires
+        bad = svb.CommonData.for_params(params, num_public_inputs=0, num_constants=C.num_constants)
+        bad.num_partial_products += 1
+        svb.make_plonk_circuit(bad, C.gates, C.groups, C.k_is, C.num_gate_constraints)
+    with pytest.raises(svb.SvError):       # too few constraint slots for the arithmetic gate
+        svb.make_plonk_circuit(common, C.gates, C.groups, C.k_is, 2)
+    # FRI shape and circuit must describe the same openings
+    other = svb.api._params(C.degree_bits + 1, 3, 1, 2, 2, oracle_num_polys=tuple(params.oracle_num_polys), num_zs=C.num_challenges)
+    with pytest.raises(svb.SvError):
+        svb.plonk_check_host(other, circuit, np.zeros((1, svb.api.make_layout(other).record_words), dtype=np.uint64),
+                             np.zeros((1, 4), dtype=np.uint64), np.zeros((1, 3 * C.num_challenges), dtype=np.uint64))
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_plonk_challenges_match_oracle_and_the_fri_transcript(svb, orc, kind):
+    """sv_plonk_challenges == the oracle's; and it is the prefix of the transcript that sv_fri_challenges runs: a proof
+    whose wires cap changes gets other plonk challenges AND another zeta."""
+    from common import tiny_params
+    params = tiny_params(svb, hash_kind=kind, degree_bits=6, cap=1)
+    recs = svb.synth_proofs(params, 2, seed=4, n_circuits=1)
+    cds, pih = svb.synth_public_inputs(params, 2, seed=4, n_circuits=1)
+    oshape = orc.shape_from(params.to_shape())
+    L = svb.api.make_layout(params)
+    for nc in (1, 2, 3):
+        a = svb.plonk_challenges(params, recs[0], cds[0], pih[0], nc)
+        b = orc.plonk_challenges(oshape, recs[0], cds[0], pih[0], nc)
+        assert (a == b).all() and (a < P).all() and len(set(a.tolist())) == 3 * nc
+    r = recs[1].copy()
+    before = svb.plonk_challenges(params, r, cds[0], pih[1])
+    r[L.off_init_caps + 4 * L.ncap] ^= np.uint64(1)        # first word of the wires cap
+    after = svb.plonk_challenges(params, r, cds[0], pih[1])
+    assert (before != after).all()

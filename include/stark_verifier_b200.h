@@ -289,7 +289,13 @@ int sv_public_inputs_hash(const uint64_t* public_inputs, size_t n, uint64_t out[
 #define SV_GATE_CONSTANT 1     /* ConstantGate { num_consts = param }, gates/constant.rs */
 #define SV_GATE_PUBLIC_INPUT 2 /* PublicInputGate, gates/public_input.rs */
 #define SV_GATE_ARITHMETIC 3   /* ArithmeticGate { num_ops = param }, gates/arithmetic.rs */
-/* not evaluated yet (sv_plonk_circuit_check refuses them): the rest of gates/mod.rs:138-196 */
+#define SV_GATE_ARITHMETIC_EXT 4 /* ArithmeticExtensionGate { num_ops = param }, gates/arithmetic_extension.rs */
+#define SV_GATE_MUL_EXT 5      /* MulExtensionGate { num_ops = param }, gates/multiplication_extension.rs */
+#define SV_GATE_BASE_SUM 6     /* BaseSumGate { num_limbs = param }, base 2, gates/base_sum.rs */
+#define SV_GATE_REDUCING 7     /* ReducingGate { num_coeffs = param }, gates/reducing.rs */
+#define SV_GATE_REDUCING_EXT 8 /* ReducingExtensionGate { num_coeffs = param }, gates/reducing_extension.rs */
+/* not evaluated yet (sv_plonk_circuit_check refuses them): PoseidonGate, PoseidonMdsGate, RandomAccessGate
+ * (gates/mod.rs:150-176) */
 #define SV_MAX_GATES 32
 #define SV_MAX_SELECTORS 8
 #define SV_MAX_ROUTED_WIRES 128
@@ -330,7 +336,8 @@ int sv_plonk_challenges(const sv_fri_shape* shape, const uint64_t* record, const
  * verify_proof_with_challenges).  pi_hashes: n x 4 words; plonk_challenges: n x 3*num_challenges words
  * (sv_plonk_challenges).  A non-canonical input word fails the proof.
  * Replaces: PlonkVerifierChip::verify_proof_with_challenges up to the FRI call (plonk_verifier_chip.rs:156-210) with
- * eval_vanishing_poly (vanishing_poly.rs:18-218) and the gate constraints of gates/{noop,constant,public_input,arithmetic}.rs.
+ * eval_vanishing_poly (vanishing_poly.rs:18-218) and the gate constraints of gates/{noop,constant,public_input,arithmetic,
+ * arithmetic_extension,multiplication_extension,base_sum,reducing,reducing_extension}.rs.
  * sv_plonk_check_batch: one GPU thread per proof (mem = where records / pi_hashes / plonk_challenges / accept_bitmap
  * live); sv_plonk_check_host: the same function on CPU threads. */
 int sv_plonk_check_batch(sv_ctx* ctx, const sv_fri_shape* shape, const sv_plonk_circuit* circuit, size_t n_proofs,

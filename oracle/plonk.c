@@ -9,7 +9,9 @@
  *   check_partial_products        vanishing_poly.rs:183-218
  *   eval_filtered_constraint      chip/plonk/gates/mod.rs:86-134
  *   reduce_extension              chip/goldilocks_extension_chip.rs:331-342 (terms.rev().fold(0, acc*base + term))
- *   gates: noop.rs, constant.rs:18-37, public_input.rs:22-40, arithmetic.rs:38-72
+ *   gates: noop.rs, constant.rs:18-37, public_input.rs:22-40, arithmetic.rs:38-72, arithmetic_extension.rs:40-84,
+ *          multiplication_extension.rs:34-71, base_sum.rs:29-62, reducing.rs:54-86, reducing_extension.rs:57-88
+ *   extension algebra             chip/goldilocks_extension_algebra_chip.rs:34-171
  * Parity unpinned against a real plonky2 proof (none can be produced here); pinned instead by an independent
  * pure-Python prover (tests/plonk_prover.py) whose proofs this restatement must accept. */
 #include "oracle.h"
@@ -22,6 +24,42 @@
 static orc_fp2 at(const uint64_t *v, size_t i) { return orc2(v[2 * i], v[2 * i + 1]); }
 static orc_fp2 lift(uint64_t a) { return orc2(a, 0); }
 static orc_fp2 scalar_mul(orc_fp2 a, uint64_t s) { return orc2(orc_mul(a.c[0], s), orc_mul(a.c[1], s)); }
+
+/* ExtensionAlgebra: chip/goldilocks_extension_algebra_chip.rs */
+typedef struct { orc_fp2 e[2]; } ext_alg;
+static ext_alg get_local_ext_algebra(const uint64_t *local_wires, size_t start) { /* gates/mod.rs:50-58 */
+    ext_alg r = {{at(local_wires, start), at(local_wires, start + 1)}};
+    return r;
+}
+static ext_alg zero_ext_algebra(void) { ext_alg r = {{orc2(0, 0), orc2(0, 0)}}; return r; }
+static ext_alg convert_to_ext_algebra(orc_fp2 et) { ext_alg r = {{et, orc2(0, 0)}}; return r; }
+/* inner_product_extension :59-82: acc += constant * a * b over the pairs */
+static ext_alg mul_add_ext_algebra(ext_alg a, ext_alg b, ext_alg c) { /* :112-147 */
+    ext_alg res;
+    for (int out = 0; out < 2; out++) {
+        orc_fp2 acc = c.e[out];
+        for (int i = 0; i < 2; i++)                 /* inner_w: pairs with i + j >= 2, constant w = 7 */
+            for (int j = 2 - i; j < 2; j++)
+                if ((i + j) % 2 == out) acc = orc2_add(scalar_mul(orc2_mul(a.e[i], b.e[j]), 7), acc);
+        for (int i = 0; i < 2; i++)                 /* inner: pairs with i + j < 2, constant 1 */
+            for (int j = 0; j < 2 - i; j++)
+                if ((i + j) % 2 == out) acc = orc2_add(orc2_mul(a.e[i], b.e[j]), acc);
+        res.e[out] = acc;
+    }
+    return res;
+}
+static ext_alg mul_ext_algebra(ext_alg a, ext_alg b) { return mul_add_ext_algebra(a, b, zero_ext_algebra()); }
+static ext_alg scalar_mul_add_ext_algebra(orc_fp2 a, ext_alg b, ext_alg c) { /* :85-99 */
+    ext_alg r;
+    for (int i = 0; i < 2; i++) r.e[i] = orc2_mul_add(a, b.e[i], c.e[i]);
+    return r;
+}
+static ext_alg scalar_mul_ext_algebra(orc_fp2 a, ext_alg b) { return scalar_mul_add_ext_algebra(a, b, zero_ext_algebra()); }
+static ext_alg sub_ext_algebra(ext_alg a, ext_alg b) {
+    ext_alg r;
+    for (int i = 0; i < 2; i++) r.e[i] = orc2_sub(a.e[i], b.e[i]);
+    return r;
+}
 
 static orc_fp2 reduce_extension(orc_fp2 base, const orc_fp2 *terms, size_t n) {
     orc_fp2 acc = orc2(0, 0);
@@ -86,6 +124,58 @@ int orc_plonk_check(const orc_plonk_circuit *C, const uint64_t *open0, const uin
                     orc_fp2 term1 = orc2_mul(orc2_mul(at(local_wires, 4 * k), at(local_wires, 4 * k + 1)), const_0);
                     orc_fp2 term2 = orc2_mul(at(local_wires, 4 * k + 2), const_1);
                     gc[n_gc++] = orc2_sub(at(local_wires, 4 * k + 3), orc2_add(term1, term2));
+                }
+                break;
+            }
+            case 4: {                                            /* ArithmeticExtensionGate, arithmetic_extension.rs:40-84 */
+                orc_fp2 const_0 = at(gate_constants, 0), const_1 = at(gate_constants, 1);
+                for (uint32_t k = 0; k < C->gates[i].param; k++) {
+                    ext_alg multiplicand_0 = get_local_ext_algebra(local_wires, 8 * k);
+                    ext_alg multiplicand_1 = get_local_ext_algebra(local_wires, 8 * k + 2);
+                    ext_alg addend = get_local_ext_algebra(local_wires, 8 * k + 4);
+                    ext_alg output = get_local_ext_algebra(local_wires, 8 * k + 6);
+                    ext_alg scaled_mul = scalar_mul_ext_algebra(const_0, mul_ext_algebra(multiplicand_0, multiplicand_1));
+                    ext_alg diff = sub_ext_algebra(output, scalar_mul_add_ext_algebra(const_1, addend, scaled_mul));
+                    gc[n_gc++] = diff.e[0]; gc[n_gc++] = diff.e[1];
+                }
+                break;
+            }
+            case 5: {                                            /* MulExtensionGate, multiplication_extension.rs:34-71 */
+                orc_fp2 const_0 = at(gate_constants, 0);
+                for (uint32_t k = 0; k < C->gates[i].param; k++) {
+                    ext_alg mul = mul_ext_algebra(get_local_ext_algebra(local_wires, 6 * k), get_local_ext_algebra(local_wires, 6 * k + 2));
+                    ext_alg diff = sub_ext_algebra(get_local_ext_algebra(local_wires, 6 * k + 4), scalar_mul_ext_algebra(const_0, mul));
+                    gc[n_gc++] = diff.e[0]; gc[n_gc++] = diff.e[1];
+                }
+                break;
+            }
+            case 6: {                                            /* BaseSumGate<2>, base_sum.rs:29-62 */
+                uint32_t num_limbs = C->gates[i].param;
+                orc_fp2 limbs[127];
+                if (num_limbs > 127) { free(constraint_terms); return -3; }
+                for (uint32_t k = 0; k < num_limbs; k++) limbs[k] = at(local_wires, 1 + k);
+                orc_fp2 computed_sum = reduce_extension(lift(2), limbs, num_limbs);
+                gc[n_gc++] = orc2_sub(computed_sum, at(local_wires, 0));
+                for (uint32_t k = 0; k < num_limbs; k++) {
+                    orc_fp2 acc = one;
+                    for (uint64_t b = 0; b < 2; b++)             /* acc' = acc * limb + (-b) * acc */
+                        acc = orc2_add(orc2_mul(acc, limbs[k]), scalar_mul(acc, orc_neg(b)));
+                    gc[n_gc++] = acc;
+                }
+                break;
+            }
+            case 7: case 8: {                                    /* ReducingGate reducing.rs:54-86, ReducingExtensionGate reducing_extension.rs:57-88 */
+                uint32_t num_coeffs = C->gates[i].param;
+                int is_ext = C->gates[i].kind == 8;
+                size_t start_accs = 6 + (is_ext ? 2 * (size_t)num_coeffs : num_coeffs);
+                ext_alg alpha = get_local_ext_algebra(local_wires, 2), acc = get_local_ext_algebra(local_wires, 4);
+                if (2 * (size_t)num_coeffs > 128) { free(constraint_terms); return -3; }
+                for (uint32_t k = 0; k < num_coeffs; k++) {
+                    ext_alg coeff = is_ext ? get_local_ext_algebra(local_wires, 6 + 2 * k) : convert_to_ext_algebra(at(local_wires, 6 + k));
+                    ext_alg accs_k = get_local_ext_algebra(local_wires, k == num_coeffs - 1 ? 0 : start_accs + 2 * k);
+                    ext_alg tmp = sub_ext_algebra(mul_add_ext_algebra(acc, alpha, coeff), accs_k);
+                    gc[n_gc++] = tmp.e[0]; gc[n_gc++] = tmp.e[1];
+                    acc = accs_k;
                 }
                 break;
             }

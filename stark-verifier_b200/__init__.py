@@ -45,6 +45,11 @@ from .api import (  # noqa: F401
     GATE_CONSTANT,
     GATE_PUBLIC_INPUT,
     GATE_ARITHMETIC,
+    GATE_ARITHMETIC_EXT,
+    GATE_MUL_EXT,
+    GATE_BASE_SUM,
+    GATE_REDUCING,
+    GATE_REDUCING_EXT,
     make_plonk_circuit,
     plonk_challenges,
     plonk_check_host,

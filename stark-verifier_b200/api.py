@@ -61,6 +61,7 @@ class PlonkCommon(ctypes.Structure):
 
 
 GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC = 0, 1, 2, 3
+GATE_ARITHMETIC_EXT, GATE_MUL_EXT, GATE_BASE_SUM, GATE_REDUCING, GATE_REDUCING_EXT = 4, 5, 6, 7, 8
 SV_MAX_GATES, SV_MAX_SELECTORS, SV_MAX_ROUTED_WIRES = 32, 8, 128
 
 

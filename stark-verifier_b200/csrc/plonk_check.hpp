@@ -12,10 +12,13 @@
 //   eval_gate_constraints / eval_filtered_constraint ... vanishing_poly.rs:126-154, chip/plonk/gates/mod.rs:86-134
 //     filter_i = prod_{k in group(i), k != i} (k - s(zeta)) * [num_selectors > 1] (UNUSED_SELECTOR - s(zeta))
 //   gates: NoopGate gates/noop.rs, ConstantGate gates/constant.rs:18-37, PublicInputGate gates/public_input.rs:22-40,
-//          ArithmeticGate gates/arithmetic.rs:38-72.
-// The remaining gates of the recursion gate set (gates/mod.rs:138-196: Poseidon, PoseidonMds, BaseSum, RandomAccess,
-// Reducing, ReducingExtension, ArithmeticExtension, MulExtension) are not implemented yet: a circuit that uses one of
-// them is refused by sv_plonk_circuit_check (an error, never a silent accept).
+//          ArithmeticGate gates/arithmetic.rs:38-72, ArithmeticExtensionGate gates/arithmetic_extension.rs:21-84,
+//          MulExtensionGate gates/multiplication_extension.rs:21-71, BaseSumGate (base 2) gates/base_sum.rs:18-62,
+//          ReducingGate gates/reducing.rs:19-86, ReducingExtensionGate gates/reducing_extension.rs:19-88; the extension
+//          algebra they compute in: chip/goldilocks_extension_algebra_chip.rs:34-171.
+// The remaining gates of the recursion gate set (gates/mod.rs:138-196: Poseidon, PoseidonMds, RandomAccess) are not
+// implemented yet: a circuit that uses one of them is refused by sv_plonk_circuit_check (an error, never a silent
+// accept).
 #pragma once
 #include "../../include/stark_verifier_b200.h"
 #include "goldilocks.cuh"
@@ -24,6 +27,39 @@ namespace svb {
 
 SVB_HD fp2 ext_at(const u64* v, u32 i) { return mk2(v[2 * i], v[2 * i + 1]); }
 SVB_HD fp2 lift(u64 a) { return mk2(a, 0); }
+
+// ExtensionAlgebra (Fp2 (x) Fp2, chip/goldilocks_extension_algebra_chip.rs): a pair of Fp2 values standing for the two
+// base-field limbs of a D = 2 wire element, each evaluated at zeta.
+struct alg2 { fp2 a, b; };
+SVB_HD alg2 alg_at(const u64* wires, u32 first) { alg2 r; r.a = ext_at(wires, first); r.b = ext_at(wires, first + 1); return r; }
+SVB_HD alg2 alg_lift(fp2 x) { alg2 r; r.a = x; r.b = mk2(0, 0); return r; }                  // convert_to_ext_algebra :46-57
+SVB_HD alg2 alg_sub(alg2 x, alg2 y) { alg2 r; r.a = sub2(x.a, y.a); r.b = sub2(x.b, y.b); return r; }
+// mul_add_ext_algebra :112-147: (x.a y.a + W x.b y.b + c.a, x.a y.b + x.b y.a + c.b), W = 7
+SVB_HD alg2 alg_mul_add(alg2 x, alg2 y, alg2 c) {
+    alg2 r;
+    r.a = add2(add2(c.a, scale2(mul2(x.b, y.b), 7)), mul2(x.a, y.a));
+    r.b = add2(add2(c.b, mul2(x.a, y.b)), mul2(x.b, y.a));
+    return r;
+}
+// scalar_mul_add_ext_algebra :85-99: s * y + c with s in Fp2
+SVB_HD alg2 alg_scalar_mul_add(fp2 s, alg2 y, alg2 c) { alg2 r; r.a = add2(mul2(s, y.a), c.a); r.b = add2(mul2(s, y.b), c.b); return r; }
+
+// wires used / constraints produced by a gate (0 wires = unknown kind)
+SVB_HD void plonk_gate_dims(u32 kind, u32 param, u32& wires, u32& constraints, u32& constants) {
+    wires = constraints = constants = 0;
+    switch (kind) {
+        case SV_GATE_NOOP: wires = 1; break;
+        case SV_GATE_CONSTANT: wires = param; constraints = param; constants = param; break;
+        case SV_GATE_PUBLIC_INPUT: wires = 4; constraints = 4; break;
+        case SV_GATE_ARITHMETIC: wires = 4 * param; constraints = param; constants = 2; break;
+        case SV_GATE_ARITHMETIC_EXT: wires = 8 * param; constraints = 2 * param; constants = 2; break;
+        case SV_GATE_MUL_EXT: wires = 6 * param; constraints = 2 * param; constants = 1; break;
+        case SV_GATE_BASE_SUM: wires = 1 + param; constraints = 1 + param; break;
+        case SV_GATE_REDUCING: wires = param ? 3 * param + 4 : 0; constraints = 2 * param; break;
+        case SV_GATE_REDUCING_EXT: wires = param ? 4 * param + 4 : 0; constraints = 2 * param; break;
+        default: break;
+    }
+}
 
 // 0 = usable; < 0 = why not
 static inline int plonk_circuit_check(const sv_plonk_circuit& C) {
@@ -42,23 +78,10 @@ static inline int plonk_circuit_check(const sv_plonk_circuit& C) {
         const sv_plonk_gate& g = C.gates[i];
         if (g.selector_index >= C.num_selectors) return -9;
         if (i < C.group_lo[g.selector_index] || i >= C.group_hi[g.selector_index] || C.group_hi[g.selector_index] > C.num_gates) return -10;
-        u32 ncons;
-        switch (g.kind) {
-            case SV_GATE_NOOP: ncons = 0; break;
-            case SV_GATE_CONSTANT:
-                if (g.param > gate_consts || g.param > c.num_wires) return -11;
-                ncons = g.param;
-                break;
-            case SV_GATE_PUBLIC_INPUT:
-                if (c.num_wires < 4) return -11;
-                ncons = 4;
-                break;
-            case SV_GATE_ARITHMETIC:
-                if (gate_consts < 2 || 4 * g.param > c.num_wires) return -11;
-                ncons = g.param;
-                break;
-            default: return -12;   // a gate this library does not evaluate yet
-        }
+        u32 nwires, ncons, nconst;
+        plonk_gate_dims(g.kind, g.param, nwires, ncons, nconst);
+        if (nwires == 0) return -12;   // a gate this library does not evaluate yet, or an empty one
+        if (nwires > c.num_wires || nconst > gate_consts) return -11;
         if (ncons > C.num_gate_constraints) return -13;
     }
     for (u32 j = 0; j < c.num_routed_wires; j++)
@@ -157,6 +180,55 @@ SVB_HD bool plonk_check_one(const sv_plonk_circuit& C, const u64* open0, const u
                               out = ext_at(wires, 4 * k + 3);
                     const fp2 computed = add2(mul2(mul2(m0, m1), c0), mul2(ad, c1));
                     gate_c[k] = add2(gate_c[k], mul2(filter, sub2(out, computed)));
+                }
+                break;
+            }
+            case SV_GATE_ARITHMETIC_EXT: {   // output - (const_0 * m0 * m1 + const_1 * addend), in the extension algebra
+                const fp2 c0 = ext_at(gconst, 0), c1 = ext_at(gconst, 1);
+                const alg2 zero = alg_lift(mk2(0, 0));
+                for (u32 k = 0; k < g.param; k++) {
+                    const alg2 mul = alg_mul_add(alg_at(wires, 8 * k), alg_at(wires, 8 * k + 2), zero);
+                    const alg2 computed = alg_scalar_mul_add(c1, alg_at(wires, 8 * k + 4), alg_scalar_mul_add(c0, mul, zero));
+                    const alg2 d = alg_sub(alg_at(wires, 8 * k + 6), computed);
+                    gate_c[2 * k] = add2(gate_c[2 * k], mul2(filter, d.a));
+                    gate_c[2 * k + 1] = add2(gate_c[2 * k + 1], mul2(filter, d.b));
+                }
+                break;
+            }
+            case SV_GATE_MUL_EXT: {          // output - const_0 * m0 * m1
+                const fp2 c0 = ext_at(gconst, 0);
+                const alg2 zero = alg_lift(mk2(0, 0));
+                for (u32 k = 0; k < g.param; k++) {
+                    const alg2 mul = alg_mul_add(alg_at(wires, 6 * k), alg_at(wires, 6 * k + 2), zero);
+                    const alg2 d = alg_sub(alg_at(wires, 6 * k + 4), alg_scalar_mul_add(c0, mul, zero));
+                    gate_c[2 * k] = add2(gate_c[2 * k], mul2(filter, d.a));
+                    gate_c[2 * k + 1] = add2(gate_c[2 * k + 1], mul2(filter, d.b));
+                }
+                break;
+            }
+            case SV_GATE_BASE_SUM: {         // sum_k limb_k 2^k - sum; then limb (limb - 1) per limb
+                fp2 computed = mk2(0, 0);
+                for (u32 k = g.param; k-- > 0;) computed = add2(add2(computed, computed), ext_at(wires, 1 + k));
+                gate_c[0] = add2(gate_c[0], mul2(filter, sub2(computed, ext_at(wires, 0))));
+                for (u32 k = 0; k < g.param; k++) {
+                    const fp2 limb = ext_at(wires, 1 + k);
+                    gate_c[1 + k] = add2(gate_c[1 + k], mul2(filter, sub2(mul2(limb, limb), limb)));
+                }
+                break;
+            }
+            case SV_GATE_REDUCING:           // acc_i = acc_{i-1} * alpha + coeff_i; the last accumulator is the output
+            case SV_GATE_REDUCING_EXT: {
+                const bool ext = g.kind == SV_GATE_REDUCING_EXT;
+                const u32 nco = g.param, start_accs = 6 + (ext ? 2 * nco : nco);
+                const alg2 alpha = alg_at(wires, 2);
+                alg2 acc = alg_at(wires, 4);
+                for (u32 k = 0; k < nco; k++) {
+                    const alg2 coeff = ext ? alg_at(wires, 6 + 2 * k) : alg_lift(ext_at(wires, 6 + k));
+                    const alg2 acc_k = alg_at(wires, k == nco - 1 ? 0 : start_accs + 2 * k);
+                    const alg2 d = alg_sub(alg_mul_add(acc, alpha, coeff), acc_k);
+                    gate_c[2 * k] = add2(gate_c[2 * k], mul2(filter, d.a));
+                    gate_c[2 * k + 1] = add2(gate_c[2 * k + 1], mul2(filter, d.b));
+                    acc = acc_k;
                 }
                 break;
             }

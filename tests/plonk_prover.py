@@ -12,6 +12,7 @@ import numpy as np
 P = 0xFFFFFFFF00000001
 UNUSED_SELECTOR = 0xFFFFFFFF
 GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC = 0, 1, 2, 3
+GATE_ARITHMETIC_EXT, GATE_MUL_EXT, GATE_BASE_SUM, GATE_REDUCING, GATE_REDUCING_EXT = 4, 5, 6, 7, 8
 
 
 def inv(a):
@@ -38,23 +39,41 @@ def poly_eval(coeffs, x):
     return acc
 
 
+# D = 2 wire elements over the base field: pairs (x0, x1) = x0 + x1 X, X^2 = 7 -- the witness-side meaning of the
+# extension gates; their constraints are these formulas, limb by limb
+def x_mul(a, b): return ((a[0] * b[0] + 7 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+def x_add(a, b): return ((a[0] + b[0]) % P, (a[1] + b[1]) % P)
+def x_sub(a, b): return ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
+def x_scale(s, a): return (s * a[0] % P, s * a[1] % P)
+
+
+def gate_dims(kind, param):
+    """(wires used, constraints, polynomial degree)"""
+    return {GATE_NOOP: (0, 0, 0), GATE_CONSTANT: (param, param, 1), GATE_PUBLIC_INPUT: (4, 4, 1),
+            GATE_ARITHMETIC: (4 * param, param, 3), GATE_ARITHMETIC_EXT: (8 * param, 2 * param, 3),
+            GATE_MUL_EXT: (6 * param, 2 * param, 3), GATE_BASE_SUM: (1 + param, 1 + param, 2),
+            GATE_REDUCING: (3 * param + 4, 2 * param, 2), GATE_REDUCING_EXT: (4 * param + 4, 2 * param, 2)}[kind]
+
+
 class Circuit:
     """Configuration of the toy circuit.  gates: list of (kind, param) in CommonData.gates order; groups: selector
     groups as (lo, hi) ranges over gate indices."""
 
     def __init__(self, degree_bits=4, num_wires=13, num_routed_wires=12, num_challenges=2, quotient_degree_factor=8,
-                 groups=((0, 4),)):
+                 groups=((0, 4),), extra_gates=()):
         self.degree_bits = degree_bits
         self.n = 1 << degree_bits
         self.num_wires, self.num_routed_wires, self.num_challenges = num_wires, num_routed_wires, num_challenges
         self.qdf = quotient_degree_factor
         self.num_ops = num_routed_wires // 4                       # ArithmeticGate::new_from_config
         self.gates = [(GATE_NOOP, 0), (GATE_CONSTANT, 2), (GATE_PUBLIC_INPUT, 0), (GATE_ARITHMETIC, self.num_ops)]
+        self.gates += list(extra_gates)
+        assert all(gate_dims(k, p)[0] <= num_wires for k, p in self.gates)
         self.groups = list(groups)
         self.num_selectors = len(self.groups)
         self.num_constants = self.num_selectors + 2
         self.num_partial_products = (num_routed_wires + self.qdf - 1) // self.qdf - 1
-        self.num_gate_constraints = max(2, 4, self.num_ops)
+        self.num_gate_constraints = max(gate_dims(k, p)[1] for k, p in self.gates)
         self.k_is = [pow(7, j, P) for j in range(num_routed_wires)]   # distinct cosets of the trace subgroup
         self.g = pow(7, (P - 1) >> degree_bits, P)
 
@@ -81,6 +100,29 @@ def _constraints(C, consts, wires, pi_hash):
             cs = [(wires[k] - pi_hash[k]) % P for k in range(4)]
         elif kind == GATE_ARITHMETIC:
             cs = [(wires[4 * k + 3] - (gc[0] * wires[4 * k] * wires[4 * k + 1] + gc[1] * wires[4 * k + 2])) % P for k in range(param)]
+        elif kind in (GATE_ARITHMETIC_EXT, GATE_MUL_EXT):
+            stride = 8 if kind == GATE_ARITHMETIC_EXT else 6
+            cs = []
+            for k in range(param):
+                el = lambda j: (wires[stride * k + 2 * j], wires[stride * k + 2 * j + 1])
+                want = x_scale(gc[0], x_mul(el(0), el(1)))
+                if kind == GATE_ARITHMETIC_EXT:
+                    want = x_add(want, x_scale(gc[1], el(2)))
+                cs.extend(x_sub(el(stride // 2 - 1), want))
+        elif kind == GATE_BASE_SUM:
+            limbs = wires[1:1 + param]
+            cs = [(sum(l << k for k, l in enumerate(limbs)) - wires[0]) % P] + [l * (l - 1) % P for l in limbs]
+        elif kind in (GATE_REDUCING, GATE_REDUCING_EXT):
+            ext = kind == GATE_REDUCING_EXT
+            alpha, acc = (wires[2], wires[3]), (wires[4], wires[5])
+            start_accs = 6 + (2 * param if ext else param)
+            cs = []
+            for k in range(param):
+                coeff = (wires[6 + 2 * k], wires[7 + 2 * k]) if ext else (wires[6 + k], 0)
+                at = 0 if k == param - 1 else start_accs + 2 * k
+                acc_k = (wires[at], wires[at + 1])
+                cs.extend(x_sub(x_add(x_mul(acc, alpha), coeff), acc_k))
+                acc = acc_k
         else:
             cs = []
         for k, c in enumerate(cs):
@@ -95,11 +137,13 @@ def prove(C, seed, pi_hash):
     n, nr, nw, nch, qdf, npp = C.n, C.num_routed_wires, C.num_wires, C.num_challenges, C.qdf, C.num_partial_products
     g = C.g
     # ---- witness -------------------------------------------------------------------------------------
-    row_gate = [GATE_NOOP] * n
+    row_gate = [GATE_NOOP] * n                     # index into C.gates (== kind for the first four)
     row_gate[0] = GATE_PUBLIC_INPUT
     row_gate[1] = row_gate[2] = GATE_CONSTANT
+    extra = list(range(4, len(C.gates)))
     for r in range(3, n - 2):
-        row_gate[r] = GATE_ARITHMETIC
+        row_gate[r] = GATE_ARITHMETIC if not extra or r % 2 else extra[(r // 2) % len(extra)]
+    assert set(row_gate) == set(range(len(C.gates))), "every gate of the circuit must be used by some row"
     wires = [[rnd() for _ in range(nw)] for _ in range(n)]
     consts = [[0] * C.num_constants for _ in range(n)]
     parent = {}
@@ -112,16 +156,39 @@ def prove(C, seed, pi_hash):
 
     filled = []   # routed cells whose value is final and may be copied
     for r in range(n):
-        gate = row_gate[r]                       # gate index == kind in this toy gate list
+        gate = row_gate[r]
+        kind, param = C.gates[gate]
         for s, (lo, hi) in enumerate(C.groups):
             consts[r][s] = gate if lo <= gate < hi else UNUSED_SELECTOR
         gc0, gc1 = rnd(), rnd()
         consts[r][C.num_selectors], consts[r][C.num_selectors + 1] = gc0, gc1
-        if gate == GATE_PUBLIC_INPUT:
+        w = wires[r]
+        if kind == GATE_PUBLIC_INPUT:
             wires[r][0:4] = list(pi_hash)
-        elif gate == GATE_CONSTANT:
+        elif kind == GATE_CONSTANT:
             wires[r][0], wires[r][1] = gc0, gc1
-        elif gate == GATE_ARITHMETIC:
+        elif kind in (GATE_ARITHMETIC_EXT, GATE_MUL_EXT):
+            stride = 8 if kind == GATE_ARITHMETIC_EXT else 6
+            for k in range(param):
+                el = lambda j: (w[stride * k + 2 * j], w[stride * k + 2 * j + 1])
+                out = x_scale(gc0, x_mul(el(0), el(1)))
+                if kind == GATE_ARITHMETIC_EXT:
+                    out = x_add(out, x_scale(gc1, el(2)))
+                w[stride * k + stride - 2], w[stride * k + stride - 1] = out
+        elif kind == GATE_BASE_SUM:
+            for k in range(param):
+                w[1 + k] = int(rng.integers(0, 2))
+            w[0] = sum(w[1 + k] << k for k in range(param)) % P
+        elif kind in (GATE_REDUCING, GATE_REDUCING_EXT):
+            ext = kind == GATE_REDUCING_EXT
+            alpha, acc = (w[2], w[3]), (w[4], w[5])
+            start_accs = 6 + (2 * param if ext else param)
+            for k in range(param):
+                coeff = (w[6 + 2 * k], w[7 + 2 * k]) if ext else (w[6 + k], 0)
+                acc = x_add(x_mul(acc, alpha), coeff)
+                at = 0 if k == param - 1 else start_accs + 2 * k
+                w[at], w[at + 1] = acc
+        elif kind == GATE_ARITHMETIC:
             for k in range(C.num_ops):
                 for col in (4 * k, 4 * k + 1, 4 * k + 2):
                     if filled and rng.random() < 0.6:           # copy constraint to an earlier cell

@@ -13,6 +13,10 @@ CONFIGS = {
     "two_selectors": dict(groups=((0, 2), (2, 4))),
     "one_challenge_no_partials": dict(num_challenges=1, num_routed_wires=8, num_wires=8, quotient_degree_factor=8),
     "three_chunks": dict(num_routed_wires=16, num_wires=18, quotient_degree_factor=7, groups=((0, 3), (3, 4))),
+    # every gate this library evaluates: + ArithmeticExtension, MulExtension, BaseSum, Reducing, ReducingExtension
+    "all_gates": dict(num_routed_wires=24, num_wires=24, quotient_degree_factor=8, groups=((0, 5), (5, 9)),
+                      extra_gates=((pp.GATE_ARITHMETIC_EXT, 3), (pp.GATE_MUL_EXT, 4), (pp.GATE_BASE_SUM, 5),
+                                   (pp.GATE_REDUCING, 4), (pp.GATE_REDUCING_EXT, 3))),
 }
 
 

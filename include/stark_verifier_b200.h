@@ -294,8 +294,10 @@ int sv_public_inputs_hash(const uint64_t* public_inputs, size_t n, uint64_t out[
 #define SV_GATE_BASE_SUM 6     /* BaseSumGate { num_limbs = param }, base 2, gates/base_sum.rs */
 #define SV_GATE_REDUCING 7     /* ReducingGate { num_coeffs = param }, gates/reducing.rs */
 #define SV_GATE_REDUCING_EXT 8 /* ReducingExtensionGate { num_coeffs = param }, gates/reducing_extension.rs */
-/* not evaluated yet (sv_plonk_circuit_check refuses them): PoseidonGate, PoseidonMdsGate, RandomAccessGate
- * (gates/mod.rs:150-176) */
+#define SV_GATE_RANDOM_ACCESS 9 /* RandomAccessGate { bits = param, num_copies = param2, num_extra_constants = param3 }, gates/random_access.rs */
+#define SV_GATE_POSEIDON_MDS 10 /* PoseidonMdsGate, gates/poseidon_mds.rs */
+#define SV_GATE_POSEIDON 11    /* PoseidonGate (width 12), gates/poseidon.rs:324-700 */
+/* = every gate the reference knows (gates/mod.rs:138-196); any other kind is refused by sv_plonk_circuit_check */
 #define SV_MAX_GATES 32
 #define SV_MAX_SELECTORS 8
 #define SV_MAX_ROUTED_WIRES 128
@@ -304,7 +306,8 @@ int sv_public_inputs_hash(const uint64_t* public_inputs, size_t n, uint64_t out[
 
 typedef struct sv_plonk_gate {
     uint32_t kind;           /* SV_GATE_* */
-    uint32_t param;          /* num_consts / num_ops */
+    uint32_t param;          /* num_consts / num_ops / num_limbs / num_coeffs / bits */
+    uint32_t param2, param3; /* RandomAccessGate: num_copies, num_extra_constants; else 0 */
     uint32_t selector_index; /* SelectorsInfo.selector_indices[gate] (types/common_data.rs:56-66) */
 } sv_plonk_gate;
 
@@ -336,8 +339,7 @@ int sv_plonk_challenges(const sv_fri_shape* shape, const uint64_t* record, const
  * verify_proof_with_challenges).  pi_hashes: n x 4 words; plonk_challenges: n x 3*num_challenges words
  * (sv_plonk_challenges).  A non-canonical input word fails the proof.
  * Replaces: PlonkVerifierChip::verify_proof_with_challenges up to the FRI call (plonk_verifier_chip.rs:156-210) with
- * eval_vanishing_poly (vanishing_poly.rs:18-218) and the gate constraints of gates/{noop,constant,public_input,arithmetic,
- * arithmetic_extension,multiplication_extension,base_sum,reducing,reducing_extension}.rs.
+ * eval_vanishing_poly (vanishing_poly.rs:18-218) and the gate constraints of every gate under chip/plonk/gates/.
  * sv_plonk_check_batch: one GPU thread per proof (mem = where records / pi_hashes / plonk_challenges / accept_bitmap
  * live); sv_plonk_check_host: the same function on CPU threads. */
 int sv_plonk_check_batch(sv_ctx* ctx, const sv_fri_shape* shape, const sv_plonk_circuit* circuit, size_t n_proofs,

@@ -220,7 +220,8 @@ def wire_write_proof(shape: OrcShape, common: OrcCommon, record, public_inputs):
 
 # -- plonk-level checks (oracle/plonk.c) -----------------------------------------------------------
 class OrcPlonkGate(ctypes.Structure):
-    _fields_ = [("kind", ctypes.c_uint32), ("param", ctypes.c_uint32), ("selector_index", ctypes.c_uint32)]
+    _fields_ = [("kind", ctypes.c_uint32), ("param", ctypes.c_uint32), ("param2", ctypes.c_uint32), ("param3", ctypes.c_uint32),
+                ("selector_index", ctypes.c_uint32)]
 
 
 class OrcPlonkCircuit(ctypes.Structure):
@@ -239,7 +240,7 @@ def plonk_circuit_from(sv_circuit) -> OrcPlonkCircuit:
         c.group_lo[i], c.group_hi[i] = sv_circuit.group_lo[i], sv_circuit.group_hi[i]
     for i in range(32):
         g = sv_circuit.gates[i]
-        c.gates[i] = OrcPlonkGate(g.kind, g.param, g.selector_index)
+        c.gates[i] = OrcPlonkGate(g.kind, g.param, g.param2, g.param3, g.selector_index)
     for i in range(128):
         c.k_is[i] = sv_circuit.k_is[i]
     return c

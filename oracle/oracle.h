@@ -112,7 +112,8 @@ int orc_wire_write_proof(const orc_shape *s, const orc_common *c, const uint64_t
                          uint8_t *out);
 
 /* == plonk-level checks (plonk.c): the vanishing-polynomial identity at zeta == */
-typedef struct { uint32_t kind, param, selector_index; } orc_plonk_gate; /* kind: 0 noop, 1 constant, 2 public input, 3 arithmetic, 4 arithmetic ext, 5 mul ext, 6 base sum (base 2), 7 reducing, 8 reducing ext */
+typedef struct { uint32_t kind, param, param2, param3, selector_index; } orc_plonk_gate; /* kind: 0 noop, 1 constant, 2 public input, 3 arithmetic, 4 arithmetic ext, 5 mul ext, 6 base sum (base 2), 7 reducing, 8 reducing ext,
+ * 9 random access (bits, copies, extra constants), 10 poseidon mds, 11 poseidon */
 typedef struct {
     orc_common common;
     uint32_t degree_bits, num_gate_constraints, num_selectors;

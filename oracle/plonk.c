@@ -10,12 +10,14 @@
  *   eval_filtered_constraint      chip/plonk/gates/mod.rs:86-134
  *   reduce_extension              chip/goldilocks_extension_chip.rs:331-342 (terms.rev().fold(0, acc*base + term))
  *   gates: noop.rs, constant.rs:18-37, public_input.rs:22-40, arithmetic.rs:38-72, arithmetic_extension.rs:40-84,
- *          multiplication_extension.rs:34-71, base_sum.rs:29-62, reducing.rs:54-86, reducing_extension.rs:57-88
+ *          multiplication_extension.rs:34-71, base_sum.rs:29-62, reducing.rs:54-86, reducing_extension.rs:57-88,
+ *          random_access.rs:84-166, poseidon_mds.rs:35-125, poseidon.rs:324-700
  *   extension algebra             chip/goldilocks_extension_algebra_chip.rs:34-171
  * Parity unpinned against a real plonky2 proof (none can be produced here); pinned instead by an independent
  * pure-Python prover (tests/plonk_prover.py) whose proofs this restatement must accept. */
 #include "oracle.h"
 #include "orc_field.h"
+#include "poseidon_g_constants.h"
 #include <stdlib.h>
 #include <string.h>
 
@@ -59,6 +61,110 @@ static ext_alg sub_ext_algebra(ext_alg a, ext_alg b) {
     ext_alg r;
     for (int i = 0; i < 2; i++) r.e[i] = orc2_sub(a.e[i], b.e[i]);
     return r;
+}
+
+/* ---- PoseidonGateConstrainer helpers, gates/poseidon.rs:383-585 ---- */
+#define T 12
+static void constant_layer(orc_fp2 *state, size_t round_ctr) {
+    for (int i = 0; i < T; i++) state[i] = orc2_add(state[i], lift(ORC_ALL_ROUND_CONSTANTS[i + T * round_ctr]));
+}
+static void partial_first_constant_layer(orc_fp2 *state) {
+    for (int i = 0; i < T; i++) state[i] = orc2_add(state[i], lift(ORC_FAST_PARTIAL_FIRST_ROUND_CONSTANT[i]));
+}
+static orc_fp2 sbox(orc_fp2 x) { /* exp(element, 7) */
+    orc_fp2 r = x;
+    for (int i = 0; i < 6; i++) r = orc2_mul(r, x);
+    return r;
+}
+static void sbox_layer(orc_fp2 *state) { for (int i = 0; i < T; i++) state[i] = sbox(state[i]); }
+static orc_fp2 mds_row_shf(int row, const orc_fp2 *state) {
+    orc_fp2 res = orc2(0, 0);
+    for (int i = 0; i < T; i++) res = orc2_mul_add(lift(ORC_MDS_MATRIX_CIRC[i]), state[(i + row) % T], res);
+    return orc2_mul_add(lift(ORC_MDS_MATRIX_DIAG[row]), state[row], res);
+}
+static void mds_layer(orc_fp2 *state) {
+    orc_fp2 result[T];
+    for (int i = 0; i < T; i++) result[i] = mds_row_shf(i, state);
+    memcpy(state, result, sizeof result);
+}
+static void mds_partial_layer_init(orc_fp2 *state) {
+    orc_fp2 result[T];
+    for (int i = 0; i < T; i++) result[i] = orc2(0, 0);
+    result[0] = state[0];
+    for (int r = 1; r < T; r++)
+        for (int c = 1; c < T; c++)
+            result[c] = orc2_mul_add(lift(ORC_FAST_PARTIAL_ROUND_INITIAL_MATRIX[(r - 1) * 11 + (c - 1)]), state[r], result[c]);
+    memcpy(state, result, sizeof result);
+}
+static void mds_partial_layer_fast(orc_fp2 *state, int r) {
+    orc_fp2 s0 = state[0];
+    uint64_t mds0to0 = ORC_MDS_MATRIX_CIRC[0] + ORC_MDS_MATRIX_DIAG[0];
+    orc_fp2 d = scalar_mul(s0, mds0to0);
+    for (int i = 1; i < T; i++) d = orc2_mul_add(lift(ORC_FAST_PARTIAL_ROUND_W_HATS[r * 11 + i - 1]), state[i], d);
+    orc_fp2 result[T];
+    result[0] = d;
+    for (int i = 1; i < T; i++) result[i] = orc2_mul_add(lift(ORC_FAST_PARTIAL_ROUND_VS[r * 11 + i - 1]), state[0], state[i]);
+    memcpy(state, result, sizeof result);
+}
+/* eval_unfiltered_constraint of the PoseidonGate, gates/poseidon.rs:588-699; returns the number of constraints */
+static size_t poseidon_gate(const uint64_t *local_wires, orc_fp2 *constraints) {
+    enum { R_F_HALF = 4, R_P = 22, WIRE_SWAP = 2 * T, START_DELTA = 2 * T + 1, START_FULL_0 = START_DELTA + 4,
+           START_PARTIAL = START_FULL_0 + T * (R_F_HALF - 1), START_FULL_1 = START_PARTIAL + R_P };
+    size_t n = 0;
+    orc_fp2 swap = at(local_wires, WIRE_SWAP);
+    constraints[n++] = orc2_sub(orc2_mul(swap, swap), swap);
+    for (int i = 0; i < 4; i++) {
+        orc_fp2 diff = orc2_sub(at(local_wires, i + 4), at(local_wires, i));
+        constraints[n++] = orc2_sub(orc2_mul(swap, diff), at(local_wires, START_DELTA + i));
+    }
+    orc_fp2 state[T];
+    for (int i = 0; i < 4; i++) {
+        orc_fp2 delta_i = at(local_wires, START_DELTA + i);
+        state[i] = orc2_add(at(local_wires, i), delta_i);
+        state[i + 4] = orc2_sub(at(local_wires, i + 4), delta_i);
+    }
+    for (int i = 8; i < T; i++) state[i] = at(local_wires, i);
+    size_t round_ctr = 0;
+    for (int r = 0; r < R_F_HALF; r++) {
+        constant_layer(state, round_ctr);
+        if (r != 0)
+            for (int i = 0; i < T; i++) {
+                orc_fp2 sbox_in = at(local_wires, START_FULL_0 + T * (r - 1) + i);
+                constraints[n++] = orc2_sub(state[i], sbox_in);
+                state[i] = sbox_in;
+            }
+        sbox_layer(state);
+        mds_layer(state);
+        round_ctr++;
+    }
+    partial_first_constant_layer(state);
+    mds_partial_layer_init(state);
+    for (int r = 0; r < R_P - 1; r++) {
+        orc_fp2 sbox_in = at(local_wires, START_PARTIAL + r);
+        constraints[n++] = orc2_sub(state[0], sbox_in);
+        state[0] = orc2_add(sbox(sbox_in), lift(ORC_FAST_PARTIAL_ROUND_CONSTANTS[r]));
+        mds_partial_layer_fast(state, r);
+    }
+    {
+        orc_fp2 sbox_in = at(local_wires, START_PARTIAL + R_P - 1);
+        constraints[n++] = orc2_sub(state[0], sbox_in);
+        state[0] = sbox(sbox_in);
+        mds_partial_layer_fast(state, R_P - 1);
+    }
+    round_ctr += R_P;
+    for (int r = 0; r < R_F_HALF; r++) {
+        constant_layer(state, round_ctr);
+        for (int i = 0; i < T; i++) {
+            orc_fp2 sbox_in = at(local_wires, START_FULL_1 + T * r + i);
+            constraints[n++] = orc2_sub(state[i], sbox_in);
+            state[i] = sbox_in;
+        }
+        sbox_layer(state);
+        mds_layer(state);
+        round_ctr++;
+    }
+    for (int i = 0; i < T; i++) constraints[n++] = orc2_sub(state[i], at(local_wires, T + i));
+    return n;
 }
 
 static orc_fp2 reduce_extension(orc_fp2 base, const orc_fp2 *terms, size_t n) {
@@ -179,6 +285,44 @@ int orc_plonk_check(const orc_plonk_circuit *C, const uint64_t *open0, const uin
                 }
                 break;
             }
+            case 9: {                                            /* RandomAccessGate, random_access.rs:84-166 */
+                uint32_t bits = C->gates[i].param, num_copies = C->gates[i].param2, num_extra_constants = C->gates[i].param3;
+                size_t vec_size = (size_t)1 << bits, num_routed = (2 + vec_size) * num_copies + num_extra_constants;
+                if (bits > 6 || num_copies * (bits + 2) + num_extra_constants > 128) { free(constraint_terms); return -3; }
+                for (uint32_t copy = 0; copy < num_copies; copy++) {
+                    orc_fp2 access_index = at(local_wires, (2 + vec_size) * copy);
+                    orc_fp2 claimed_element = at(local_wires, (2 + vec_size) * copy + 1);
+                    orc_fp2 list_items[64], bitv[6];
+                    for (size_t k = 0; k < vec_size; k++) list_items[k] = at(local_wires, (2 + vec_size) * copy + 2 + k);
+                    for (uint32_t k = 0; k < bits; k++) bitv[k] = at(local_wires, num_routed + copy * bits + k);
+                    for (uint32_t k = 0; k < bits; k++) gc[n_gc++] = orc2_sub(orc2_mul(bitv[k], bitv[k]), bitv[k]);
+                    gc[n_gc++] = orc2_sub(reduce_extension(lift(2), bitv, bits), access_index);
+                    size_t len = vec_size;
+                    for (uint32_t k = 0; k < bits; k++) {        /* tuples().map(|(x, y)| select(b, y, x)) */
+                        for (size_t j = 0; j < len / 2; j++) {
+                            orc_fp2 x = list_items[2 * j], y = list_items[2 * j + 1];
+                            list_items[j] = orc2_add(orc2_mul(bitv[k], orc2_sub(y, x)), x);
+                        }
+                        len /= 2;
+                    }
+                    gc[n_gc++] = orc2_sub(list_items[0], claimed_element);
+                }
+                for (uint32_t k = 0; k < num_extra_constants; k++)
+                    gc[n_gc++] = orc2_sub(at(gate_constants, k), at(local_wires, (2 + vec_size) * num_copies + k));
+                break;
+            }
+            case 10: {                                           /* PoseidonMdsGate, poseidon_mds.rs:35-125 */
+                for (int row = 0; row < T; row++) {
+                    ext_alg res = zero_ext_algebra();
+                    for (int k = 0; k < T; k++)
+                        res = scalar_mul_add_ext_algebra(lift(ORC_MDS_MATRIX_CIRC[k]), get_local_ext_algebra(local_wires, 2 * (size_t)((k + row) % T)), res);
+                    res = scalar_mul_add_ext_algebra(lift(ORC_MDS_MATRIX_DIAG[row]), get_local_ext_algebra(local_wires, 2 * (size_t)row), res);
+                    ext_alg diff = sub_ext_algebra(get_local_ext_algebra(local_wires, 2 * (size_t)(T + row)), res);
+                    gc[n_gc++] = diff.e[0]; gc[n_gc++] = diff.e[1];
+                }
+                break;
+            }
+            case 11: n_gc = poseidon_gate(local_wires, gc); break;  /* PoseidonGate */
             default: free(constraint_terms); return -3;         /* unimplemented!() in the reference for unknown ids */
         }
         if (n_gc > ngc) { free(constraint_terms); return -4; }

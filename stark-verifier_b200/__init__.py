@@ -50,6 +50,9 @@ from .api import (  # noqa: F401
     GATE_BASE_SUM,
     GATE_REDUCING,
     GATE_REDUCING_EXT,
+    GATE_RANDOM_ACCESS,
+    GATE_POSEIDON_MDS,
+    GATE_POSEIDON,
     make_plonk_circuit,
     plonk_challenges,
     plonk_check_host,

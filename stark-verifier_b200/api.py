@@ -62,12 +62,14 @@ class PlonkCommon(ctypes.Structure):
 
 GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC = 0, 1, 2, 3
 GATE_ARITHMETIC_EXT, GATE_MUL_EXT, GATE_BASE_SUM, GATE_REDUCING, GATE_REDUCING_EXT = 4, 5, 6, 7, 8
+GATE_RANDOM_ACCESS, GATE_POSEIDON_MDS, GATE_POSEIDON = 9, 10, 11
 SV_MAX_GATES, SV_MAX_SELECTORS, SV_MAX_ROUTED_WIRES = 32, 8, 128
 
 
 class PlonkGate(ctypes.Structure):
     """sv_plonk_gate"""
-    _fields_ = [("kind", ctypes.c_uint32), ("param", ctypes.c_uint32), ("selector_index", ctypes.c_uint32)]
+    _fields_ = [("kind", ctypes.c_uint32), ("param", ctypes.c_uint32), ("param2", ctypes.c_uint32), ("param3", ctypes.c_uint32),
+                ("selector_index", ctypes.c_uint32)]
 
 
 class PlonkCircuit(ctypes.Structure):
@@ -371,7 +373,7 @@ def public_inputs_hash(public_inputs) -> np.ndarray:
 
 # -- plonk-level checks ----------------------------------------------------------------
 def make_plonk_circuit(common: CommonData, gates, groups, k_is, num_gate_constraints: int) -> PlonkCircuit:
-    """gates: [(kind, param)] in CommonData.gates order; groups: [(lo, hi)] = SelectorsInfo.groups; the selector index
+    """gates: [(kind, param)] or [(kind, param, param2, param3)] in CommonData.gates order; groups: [(lo, hi)] = SelectorsInfo.groups; the selector index
     of a gate is the group that contains its position (SelectorsInfo.selector_indices)."""
     c = PlonkCircuit()
     c.common = common.to_c()
@@ -381,11 +383,12 @@ def make_plonk_circuit(common: CommonData, gates, groups, k_is, num_gate_constra
     for s, (lo, hi) in enumerate(groups):
         c.group_lo[s], c.group_hi[s] = lo, hi
     c.num_gates = len(gates)
-    for i, (kind, param) in enumerate(gates):
+    for i, gate in enumerate(gates):
+        kind, param, param2, param3 = (list(gate) + [0, 0])[:4]
         sel = [s for s, (lo, hi) in enumerate(groups) if lo <= i < hi]
         if len(sel) != 1:
             raise SvError(f"gate {i} is not in exactly one selector group")
-        c.gates[i] = PlonkGate(kind, param, sel[0])
+        c.gates[i] = PlonkGate(kind, param, param2, param3, sel[0])
     for j, k in enumerate(k_is):
         c.k_is[j] = int(k)
     rc = lib().sv_plonk_circuit_check(ctypes.byref(c))

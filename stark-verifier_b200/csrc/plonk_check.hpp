@@ -15,13 +15,15 @@
 //          ArithmeticGate gates/arithmetic.rs:38-72, ArithmeticExtensionGate gates/arithmetic_extension.rs:21-84,
 //          MulExtensionGate gates/multiplication_extension.rs:21-71, BaseSumGate (base 2) gates/base_sum.rs:18-62,
 //          ReducingGate gates/reducing.rs:19-86, ReducingExtensionGate gates/reducing_extension.rs:19-88; the extension
-//          algebra they compute in: chip/goldilocks_extension_algebra_chip.rs:34-171.
-// The remaining gates of the recursion gate set (gates/mod.rs:138-196: Poseidon, PoseidonMds, RandomAccess) are not
-// implemented yet: a circuit that uses one of them is refused by sv_plonk_circuit_check (an error, never a silent
-// accept).
+//          algebra they compute in: chip/goldilocks_extension_algebra_chip.rs:34-171; RandomAccessGate
+//          gates/random_access.rs:84-166, PoseidonMdsGate gates/poseidon_mds.rs:35-125, PoseidonGate gates/poseidon.rs:324-700
+//          (the permutation in its fast form with every S-box input a wire: 135 wires, 123 constraints).
+// That is every gate the reference knows (gates/mod.rs:138-196); any other kind is refused by sv_plonk_circuit_check
+// (an error, never a silent accept).
 #pragma once
 #include "../../include/stark_verifier_b200.h"
 #include "goldilocks.cuh"
+#include "poseidon_g.cuh"   // the Poseidon-Goldilocks tables (SVB_T), shared with the hash itself
 
 namespace svb {
 
@@ -45,7 +47,7 @@ SVB_HD alg2 alg_mul_add(alg2 x, alg2 y, alg2 c) {
 SVB_HD alg2 alg_scalar_mul_add(fp2 s, alg2 y, alg2 c) { alg2 r; r.a = add2(mul2(s, y.a), c.a); r.b = add2(mul2(s, y.b), c.b); return r; }
 
 // wires used / constraints produced by a gate (0 wires = unknown kind)
-SVB_HD void plonk_gate_dims(u32 kind, u32 param, u32& wires, u32& constraints, u32& constants) {
+SVB_HD void plonk_gate_dims(u32 kind, u32 param, u32 param2, u32 param3, u32& wires, u32& constraints, u32& constants) {
     wires = constraints = constants = 0;
     switch (kind) {
         case SV_GATE_NOOP: wires = 1; break;
@@ -57,8 +59,94 @@ SVB_HD void plonk_gate_dims(u32 kind, u32 param, u32& wires, u32& constraints, u
         case SV_GATE_BASE_SUM: wires = 1 + param; constraints = 1 + param; break;
         case SV_GATE_REDUCING: wires = param ? 3 * param + 4 : 0; constraints = 2 * param; break;
         case SV_GATE_REDUCING_EXT: wires = param ? 4 * param + 4 : 0; constraints = 2 * param; break;
+        case SV_GATE_RANDOM_ACCESS:
+            if (param == 0 || param > 6 || param2 == 0 || param2 > 64 || param3 > 16) break;
+            wires = (2 + (1u << param)) * param2 + param3 + param * param2;
+            constraints = param2 * (param + 2) + param3;
+            constants = param3;
+            break;
+        case SV_GATE_POSEIDON_MDS: wires = 48; constraints = 24; break;
+        case SV_GATE_POSEIDON: wires = 135; constraints = 123; break;
         default: break;
     }
+}
+
+// ---- PoseidonGate (gates/poseidon.rs): the permutation over Fp2 values, fast form ----------------------------
+SVB_HD fp2 pg_sbox(fp2 x) {                       // exp(element, 7), :420-429
+    const fp2 x2 = mul2(x, x), x4 = mul2(x2, x2);
+    return mul2(mul2(x2, x), x4);
+}
+SVB_HD void pg_mds_layer(fp2 st[12]) {            // mds_row_shf / mds_layer :443-502
+    fp2 r[12];
+    for (int row = 0; row < 12; row++) {
+        fp2 acc = mk2(0, 0);
+        for (int i = 0; i < 12; i++) acc = add2(acc, scale2(st[(i + row) % 12], SVB_T(MDS_MATRIX_CIRC)[i]));
+        r[row] = add2(acc, scale2(st[row], SVB_T(MDS_MATRIX_DIAG)[row]));
+    }
+    for (int i = 0; i < 12; i++) st[i] = r[i];
+}
+// Adds filter * constraint_k to gate_c[k] for the 123 constraints of the gate, in the reference's order (:596-699).
+SVB_HD void poseidon_gate_constraints(const u64* wires, fp2 filter, fp2* gate_c) {
+    u32 k = 0;
+    auto emit = [&](fp2 c) { gate_c[k] = add2(gate_c[k], mul2(filter, c)); k++; };
+    const u32 WIRE_SWAP = 24, START_DELTA = 25, START_FULL_0 = 29, START_PARTIAL = 29 + 36, START_FULL_1 = 29 + 36 + 22;
+    const fp2 swap = ext_at(wires, WIRE_SWAP);
+    emit(sub2(mul2(swap, swap), swap));                                   // swap is binary
+    for (u32 i = 0; i < 4; i++)                                           // delta_i = swap * (rhs - lhs)
+        emit(sub2(mul2(swap, sub2(ext_at(wires, i + 4), ext_at(wires, i))), ext_at(wires, START_DELTA + i)));
+    fp2 st[12];
+    for (u32 i = 0; i < 4; i++) {
+        const fp2 d = ext_at(wires, START_DELTA + i);
+        st[i] = add2(ext_at(wires, i), d);
+        st[i + 4] = sub2(ext_at(wires, i + 4), d);
+    }
+    for (u32 i = 8; i < 12; i++) st[i] = ext_at(wires, i);
+    u32 round_ctr = 0;
+    for (u32 r = 0; r < 4; r++) {                                         // first set of full rounds
+        for (u32 i = 0; i < 12; i++) st[i] = add2(st[i], lift(SVB_T(ALL_ROUND_CONSTANTS)[i + 12 * round_ctr]));
+        if (r != 0)
+            for (u32 i = 0; i < 12; i++) {
+                const fp2 sbox_in = ext_at(wires, START_FULL_0 + 12 * (r - 1) + i);
+                emit(sub2(st[i], sbox_in));
+                st[i] = sbox_in;
+            }
+        for (u32 i = 0; i < 12; i++) st[i] = pg_sbox(st[i]);
+        pg_mds_layer(st);
+        round_ctr++;
+    }
+    for (u32 i = 0; i < 12; i++) st[i] = add2(st[i], lift(SVB_T(FAST_PARTIAL_FIRST_ROUND_CONSTANT)[i]));
+    {                                                                      // mds_partial_layer_init :503-535
+        fp2 res[12];
+        for (u32 c = 0; c < 12; c++) res[c] = mk2(0, 0);
+        res[0] = st[0];
+        for (u32 r = 1; r < 12; r++)
+            for (u32 c = 1; c < 12; c++)
+                res[c] = add2(res[c], scale2(st[r], SVB_T(FAST_PARTIAL_ROUND_INITIAL_MATRIX)[(r - 1) * 11 + (c - 1)]));
+        for (u32 c = 0; c < 12; c++) st[c] = res[c];
+    }
+    for (u32 r = 0; r < 22; r++) {                                        // partial rounds :651-670
+        const fp2 sbox_in = ext_at(wires, START_PARTIAL + r);
+        emit(sub2(st[0], sbox_in));
+        st[0] = pg_sbox(sbox_in);
+        if (r != 21) st[0] = add2(st[0], lift(SVB_T(FAST_PARTIAL_ROUND_CONSTANTS)[r]));
+        // mds_partial_layer_fast :537-585
+        fp2 d = scale2(st[0], SVB_T(MDS_MATRIX_CIRC)[0] + SVB_T(MDS_MATRIX_DIAG)[0]);
+        for (u32 i = 1; i < 12; i++) d = add2(d, scale2(st[i], SVB_T(FAST_PARTIAL_ROUND_W_HATS)[r * 11 + i - 1]));
+        for (u32 i = 1; i < 12; i++) st[i] = add2(scale2(st[0], SVB_T(FAST_PARTIAL_ROUND_VS)[r * 11 + i - 1]), st[i]);
+        st[0] = d;
+    }
+    round_ctr += 22;
+    for (u32 r = 0; r < 4; r++) {                                         // second set of full rounds
+        for (u32 i = 0; i < 12; i++) st[i] = add2(st[i], lift(SVB_T(ALL_ROUND_CONSTANTS)[i + 12 * round_ctr]));
+        for (u32 i = 0; i < 12; i++) {
+            const fp2 sbox_in = ext_at(wires, START_FULL_1 + 12 * r + i);
+            emit(sub2(st[i], sbox_in));
+            st[i] = pg_sbox(sbox_in);
+        }
+        pg_mds_layer(st);
+        round_ctr++;
+    }
+    for (u32 i = 0; i < 12; i++) emit(sub2(st[i], ext_at(wires, 12 + i)));
 }
 
 // 0 = usable; < 0 = why not
@@ -79,7 +167,7 @@ static inline int plonk_circuit_check(const sv_plonk_circuit& C) {
         if (g.selector_index >= C.num_selectors) return -9;
         if (i < C.group_lo[g.selector_index] || i >= C.group_hi[g.selector_index] || C.group_hi[g.selector_index] > C.num_gates) return -10;
         u32 nwires, ncons, nconst;
-        plonk_gate_dims(g.kind, g.param, nwires, ncons, nconst);
+        plonk_gate_dims(g.kind, g.param, g.param2, g.param3, nwires, ncons, nconst);
         if (nwires == 0) return -12;   // a gate this library does not evaluate yet, or an empty one
         if (nwires > c.num_wires || nconst > gate_consts) return -11;
         if (ncons > C.num_gate_constraints) return -13;
@@ -232,6 +320,45 @@ SVB_HD bool plonk_check_one(const sv_plonk_circuit& C, const u64* open0, const u
                 }
                 break;
             }
+            case SV_GATE_RANDOM_ACCESS: {    // gates/random_access.rs:84-166
+                const u32 bits = g.param, copies = g.param2, extra = g.param3, vec = 1u << bits;
+                const u32 routed = (2 + vec) * copies + extra;
+                u32 k = 0;
+                auto emit = [&](fp2 c) { gate_c[k] = add2(gate_c[k], mul2(filter, c)); k++; };
+                for (u32 copy = 0; copy < copies; copy++) {
+                    const u32 base = (2 + vec) * copy;
+                    fp2 items[64];
+                    for (u32 i = 0; i < vec; i++) items[i] = ext_at(wires, base + 2 + i);
+                    fp2 reconstructed = mk2(0, 0);
+                    for (u32 i = 0; i < bits; i++) {
+                        const fp2 b = ext_at(wires, routed + copy * bits + i);
+                        emit(sub2(mul2(b, b), b));
+                    }
+                    for (u32 i = bits; i-- > 0;) reconstructed = add2(add2(reconstructed, reconstructed), ext_at(wires, routed + copy * bits + i));
+                    emit(sub2(reconstructed, ext_at(wires, base)));
+                    for (u32 i = 0, len = vec; i < bits; i++, len >>= 1) {   // select(b, y, x) = b (y - x) + x
+                        const fp2 b = ext_at(wires, routed + copy * bits + i);
+                        for (u32 j = 0; j < len / 2; j++) items[j] = add2(mul2(b, sub2(items[2 * j + 1], items[2 * j])), items[2 * j]);
+                    }
+                    emit(sub2(items[0], ext_at(wires, base + 1)));
+                }
+                for (u32 i = 0; i < extra; i++) emit(sub2(ext_at(gconst, i), ext_at(wires, (2 + vec) * copies + i)));
+                break;
+            }
+            case SV_GATE_POSEIDON_MDS:       // outputs - MDS(inputs) over the extension algebra, gates/poseidon_mds.rs:35-125
+                for (u32 row = 0; row < 12; row++) {
+                    alg2 res = alg_lift(mk2(0, 0));
+                    for (u32 i = 0; i < 12; i++)
+                        res = alg_scalar_mul_add(lift(SVB_T(MDS_MATRIX_CIRC)[i]), alg_at(wires, 2 * ((i + row) % 12)), res);
+                    res = alg_scalar_mul_add(lift(SVB_T(MDS_MATRIX_DIAG)[row]), alg_at(wires, 2 * row), res);
+                    const alg2 d = alg_sub(alg_at(wires, 2 * (12 + row)), res);
+                    gate_c[2 * row] = add2(gate_c[2 * row], mul2(filter, d.a));
+                    gate_c[2 * row + 1] = add2(gate_c[2 * row + 1], mul2(filter, d.b));
+                }
+                break;
+            case SV_GATE_POSEIDON:
+                poseidon_gate_constraints(wires, filter, gate_c);
+                break;
             default: break;              // SV_GATE_NOOP: no constraints
         }
     }

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE: a miniature plonky2-style prover in pure Python (big integers), just enough to produce openings
 that satisfy the vanishing-polynomial identity the verifier checks (reference: chip/plonk/plonk_verifier_chip.rs:156-210,
-chip/plonk/vanishing_poly.rs) for a small circuit over the gates {Noop, Constant, PublicInput, Arithmetic}.
+chip/plonk/vanishing_poly.rs) for a small circuit over any subset of the reference's gates (chip/plonk/gates/*.rs).
 
 It follows the protocol, not the verifier's code: witness rows -> copy-constraint permutation -> sigma polynomials ->
 grand products Z with partial products -> vanishing polynomial on a coset -> division by Z_H -> quotient chunks ->
@@ -13,6 +13,7 @@ P = 0xFFFFFFFF00000001
 UNUSED_SELECTOR = 0xFFFFFFFF
 GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC = 0, 1, 2, 3
 GATE_ARITHMETIC_EXT, GATE_MUL_EXT, GATE_BASE_SUM, GATE_REDUCING, GATE_REDUCING_EXT = 4, 5, 6, 7, 8
+GATE_RANDOM_ACCESS, GATE_POSEIDON_MDS, GATE_POSEIDON = 9, 10, 11
 
 
 def inv(a):
@@ -47,8 +48,93 @@ def x_sub(a, b): return ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
 def x_scale(s, a): return (s * a[0] % P, s * a[1] % P)
 
 
+def _poseidon_tables():
+    """The Poseidon-Goldilocks tables (reference: chip/plonk/gates/poseidon.rs:26-322) from the generated oracle header."""
+    import os
+    import re
+    t = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "poseidon_g_constants.h")).read()
+    out = {}
+    for name in ("ALL_ROUND_CONSTANTS", "FAST_PARTIAL_FIRST_ROUND_CONSTANT", "FAST_PARTIAL_ROUND_CONSTANTS", "FAST_PARTIAL_ROUND_VS",
+                 "FAST_PARTIAL_ROUND_W_HATS", "FAST_PARTIAL_ROUND_INITIAL_MATRIX", "MDS_MATRIX_CIRC", "MDS_MATRIX_DIAG"):
+        body = re.search(r"ORC_" + name + r"\[\d+\] = \{(.*?)\};", t, re.S).group(1)
+        out[name] = [int(x, 16) for x in re.findall(r"0x([0-9a-fA-F]+)", body)]
+    return out
+
+
+PT = _poseidon_tables()
+PG_SWAP, PG_DELTA, PG_FULL0, PG_PARTIAL, PG_FULL1 = 24, 25, 29, 65, 87
+
+
+def _mds(st):
+    return [(sum(PT["MDS_MATRIX_CIRC"][i] * st[(i + r) % 12] for i in range(12)) + PT["MDS_MATRIX_DIAG"][r] * st[r]) % P for r in range(12)]
+
+
+def poseidon_gate_trace(w, check):
+    """The PoseidonGate's view of the permutation (fast form, every S-box input a wire).  check=False: fill the wires of
+    row `w` from its inputs (wires 0..12) and swap bit (wire 24); check=True: return the 123 constraint values."""
+    cs = []
+    swap = w[PG_SWAP]
+    cs.append((swap * swap - swap) % P)
+    for i in range(4):
+        d = swap * (w[i + 4] - w[i]) % P
+        if check:
+            cs.append((d - w[PG_DELTA + i]) % P)
+        else:
+            w[PG_DELTA + i] = d
+    st = [0] * 12
+    for i in range(4):
+        st[i] = (w[i] + w[PG_DELTA + i]) % P
+        st[i + 4] = (w[i + 4] - w[PG_DELTA + i]) % P
+    st[8:12] = w[8:12]
+
+    def wire(at, value):            # a wire that must equal `value`: constrain it (check) or assign it (fill)
+        if check:
+            cs.append((value - w[at]) % P)
+        else:
+            w[at] = value
+        return w[at]
+
+    rc = 0
+    for r in range(4):
+        st = [(st[i] + PT["ALL_ROUND_CONSTANTS"][i + 12 * rc]) % P for i in range(12)]
+        if r:
+            st = [wire(PG_FULL0 + 12 * (r - 1) + i, st[i]) for i in range(12)]
+        st = _mds([pow(x, 7, P) for x in st])
+        rc += 1
+    st = [(st[i] + PT["FAST_PARTIAL_FIRST_ROUND_CONSTANT"][i]) % P for i in range(12)]
+    init = PT["FAST_PARTIAL_ROUND_INITIAL_MATRIX"]
+    st = [st[0]] + [sum(init[(r - 1) * 11 + (c - 1)] * st[r] for r in range(1, 12)) % P for c in range(1, 12)]
+    for r in range(22):
+        s0 = pow(wire(PG_PARTIAL + r, st[0]), 7, P)
+        if r != 21:
+            s0 = (s0 + PT["FAST_PARTIAL_ROUND_CONSTANTS"][r]) % P
+        d = (25 * s0 + sum(PT["FAST_PARTIAL_ROUND_W_HATS"][r * 11 + i - 1] * st[i] for i in range(1, 12))) % P
+        st = [d] + [(PT["FAST_PARTIAL_ROUND_VS"][r * 11 + i - 1] * s0 + st[i]) % P for i in range(1, 12)]
+    rc += 22
+    for r in range(4):
+        st = [(st[i] + PT["ALL_ROUND_CONSTANTS"][i + 12 * rc]) % P for i in range(12)]
+        st = [wire(PG_FULL1 + 12 * r + i, st[i]) for i in range(12)]
+        st = _mds([pow(x, 7, P) for x in st])
+        rc += 1
+    for i in range(12):
+        wire(12 + i, st[i])
+    return cs
+
+
+def _ra(param):
+    bits, copies, extra = param
+    return bits, copies, extra, 1 << bits, (2 + (1 << bits)) * copies + extra
+
+
 def gate_dims(kind, param):
     """(wires used, constraints, polynomial degree)"""
+    if kind == GATE_RANDOM_ACCESS:
+        bits, copies, extra, vec, routed = _ra(param)
+        return (routed + bits * copies, copies * (bits + 2) + extra, bits + 1)
+    if kind == GATE_POSEIDON_MDS:
+        return (48, 24, 1)
+    if kind == GATE_POSEIDON:
+        return (135, 123, 7)
     return {GATE_NOOP: (0, 0, 0), GATE_CONSTANT: (param, param, 1), GATE_PUBLIC_INPUT: (4, 4, 1),
             GATE_ARITHMETIC: (4 * param, param, 3), GATE_ARITHMETIC_EXT: (8 * param, 2 * param, 3),
             GATE_MUL_EXT: (6 * param, 2 * param, 3), GATE_BASE_SUM: (1 + param, 1 + param, 2),
@@ -123,8 +209,30 @@ def _constraints(C, consts, wires, pi_hash):
                 acc_k = (wires[at], wires[at + 1])
                 cs.extend(x_sub(x_add(x_mul(acc, alpha), coeff), acc_k))
                 acc = acc_k
+        elif kind == GATE_RANDOM_ACCESS:
+            bits, copies, extra, vec, routed = _ra(param)
+            cs = []
+            for copy in range(copies):
+                base = (2 + vec) * copy
+                bv = [wires[routed + copy * bits + i] for i in range(bits)]
+                cs += [b * (b - 1) % P for b in bv]
+                cs.append((sum(b << i for i, b in enumerate(bv)) - wires[base]) % P)
+                items = list(wires[base + 2: base + 2 + vec])
+                for b in bv:
+                    items = [(x + b * (y - x)) % P for x, y in zip(items[0::2], items[1::2])]
+                cs.append((items[0] - wires[base + 1]) % P)
+            cs += [(gc[i] - wires[(2 + vec) * copies + i]) % P for i in range(extra)]
+        elif kind == GATE_POSEIDON_MDS:
+            cs = []
+            for limb_pairs in [[(wires[2 * i], wires[2 * i + 1]) for i in range(12)]]:
+                lo, hi = _mds([x[0] for x in limb_pairs]), _mds([x[1] for x in limb_pairs])
+                for r in range(12):
+                    cs += [(wires[2 * (12 + r)] - lo[r]) % P, (wires[2 * (12 + r) + 1] - hi[r]) % P]
+        elif kind == GATE_POSEIDON:
+            cs = poseidon_gate_trace(list(wires), check=True)
         else:
             cs = []
+        assert len(cs) == gate_dims(kind, param)[1]
         for k, c in enumerate(cs):
             out[k] = (out[k] + f * c) % P
     return out
@@ -141,8 +249,9 @@ def prove(C, seed, pi_hash):
     row_gate[0] = GATE_PUBLIC_INPUT
     row_gate[1] = row_gate[2] = GATE_CONSTANT
     extra = list(range(4, len(C.gates)))
+    assert 3 + len(extra) < n - 2, "no row left for the arithmetic gate"
     for r in range(3, n - 2):
-        row_gate[r] = GATE_ARITHMETIC if not extra or r % 2 else extra[(r // 2) % len(extra)]
+        row_gate[r] = extra[r - 3] if r - 3 < len(extra) else GATE_ARITHMETIC
     assert set(row_gate) == set(range(len(C.gates))), "every gate of the circuit must be used by some row"
     wires = [[rnd() for _ in range(nw)] for _ in range(n)]
     consts = [[0] * C.num_constants for _ in range(n)]
@@ -175,6 +284,24 @@ def prove(C, seed, pi_hash):
                 if kind == GATE_ARITHMETIC_EXT:
                     out = x_add(out, x_scale(gc1, el(2)))
                 w[stride * k + stride - 2], w[stride * k + stride - 1] = out
+        elif kind == GATE_RANDOM_ACCESS:
+            bits, copies, extra, vec, routed = _ra(param)
+            for copy in range(copies):
+                base = (2 + vec) * copy
+                idx = int(rng.integers(0, vec))
+                w[base], w[base + 1] = idx, w[base + 2 + idx]
+                for i in range(bits):
+                    w[routed + copy * bits + i] = (idx >> i) & 1
+            gcs = [gc0, gc1]
+            for i in range(extra):
+                w[(2 + vec) * copies + i] = gcs[i]
+        elif kind == GATE_POSEIDON_MDS:
+            lo, hi = _mds([w[2 * i] for i in range(12)]), _mds([w[2 * i + 1] for i in range(12)])
+            for r_ in range(12):
+                w[2 * (12 + r_)], w[2 * (12 + r_) + 1] = lo[r_], hi[r_]
+        elif kind == GATE_POSEIDON:
+            w[PG_SWAP] = int(rng.integers(0, 2))
+            poseidon_gate_trace(w, check=False)
         elif kind == GATE_BASE_SUM:
             for k in range(param):
                 w[1 + k] = int(rng.integers(0, 2))

@@ -10,7 +10,7 @@ from test_plonk_check import CONFIGS, oracle_bits, setup, to_records
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["one_selector", "two_selectors", "three_chunks", "all_gates"])
+@pytest.mark.parametrize("name", ["one_selector", "two_selectors", "three_chunks", "all_gates", "recursion_gate_set"])
 def test_plonk_kernel_matches_host_and_oracle(svb, orc, ctx, name):
     C, params, circuit, L = setup(svb, CONFIGS[name])
     ocirc = orc.plonk_circuit_from(circuit)

@@ -17,7 +17,19 @@ CONFIGS = {
     "all_gates": dict(num_routed_wires=24, num_wires=24, quotient_degree_factor=8, groups=((0, 5), (5, 9)),
                       extra_gates=((pp.GATE_ARITHMETIC_EXT, 3), (pp.GATE_MUL_EXT, 4), (pp.GATE_BASE_SUM, 5),
                                    (pp.GATE_REDUCING, 4), (pp.GATE_REDUCING_EXT, 3))),
+    # the gate set and parameters of the reference's recursion circuits (gates/mod.rs:138-196) on the standard
+    # recursion configuration: 135 wires, 80 routed, 2 challenges, quotient degree factor 8
+    "recursion_gate_set": dict(num_routed_wires=80, num_wires=135, quotient_degree_factor=8,
+                               groups=((0, 5), (5, 9), (9, 11), (11, 12)),
+                               extra_gates=((pp.GATE_ARITHMETIC_EXT, 10), (pp.GATE_MUL_EXT, 13), (pp.GATE_BASE_SUM, 63),
+                                            (pp.GATE_REDUCING, 43), (pp.GATE_REDUCING_EXT, 32),
+                                            (pp.GATE_RANDOM_ACCESS, (4, 4, 2)), (pp.GATE_POSEIDON_MDS, 0), (pp.GATE_POSEIDON, 0))),
 }
+
+
+def c_gates(C):
+    """the prover's gate list in the (kind, param, param2, param3) form of sv_plonk_gate"""
+    return [(k,) + tuple(p) if isinstance(p, tuple) else (k, p) for k, p in C.gates]
 
 
 def setup(svb, cfg):
@@ -26,7 +38,7 @@ def setup(svb, cfg):
               C.num_challenges * C.qdf)
     params = svb.api._params(C.degree_bits, 3, 1, 2, 2, oracle_num_polys=widths, num_zs=C.num_challenges)
     common = svb.CommonData.for_params(params, num_public_inputs=0, num_constants=C.num_constants)
-    circuit = svb.make_plonk_circuit(common, C.gates, C.groups, C.k_is, C.num_gate_constraints)
+    circuit = svb.make_plonk_circuit(common, c_gates(C), C.groups, C.k_is, C.num_gate_constraints)
     return C, params, circuit, svb.api.make_layout(params)
 
 
@@ -54,7 +66,7 @@ def test_prover_accepted_corruptions_rejected(svb, orc, name):
     C, params, circuit, L = setup(svb, CONFIGS[name])
     ocirc = orc.plonk_circuit_from(circuit)
     rng = np.random.default_rng(7)
-    n = 3
+    n = 3 if C.num_wires < 100 else 1
     pih = rng.integers(0, P, size=(n, 4), dtype=np.uint64)
     proofs = [pp.prove(C, 100 + i, [int(x) for x in pih[i]]) for i in range(n)]
     recs, chal = to_records(L, proofs)

@@ -228,6 +228,8 @@ typedef struct sv_plonk_common {
 /* first_fail code of a proof whose bytes do not parse (a Merkle-proof length byte that disagrees with the
  * shape); plonky2 would fail in from_bytes / verify_merkle_proof before any arithmetic */
 #define SV_FAIL_MALFORMED 8
+/* first_fail code of a proof whose openings do not satisfy the vanishing-polynomial identity (sv_verify_proofs_full) */
+#define SV_FAIL_PLONK 9
 
 /* FriParams/FriConfig + CommonData -> sv_fri_shape: the oracle widths and blinding flags of
  * CommonData::fri_oracles (types/common_data.rs:195-221; blinding = PlonkOracle consts :101-123), batch 1 =
@@ -347,6 +349,15 @@ int sv_plonk_check_batch(sv_ctx* ctx, const sv_fri_shape* shape, const sv_plonk_
                          uint32_t* accept_bitmap, int mem);
 int sv_plonk_check_host(const sv_fri_shape* shape, const sv_plonk_circuit* circuit, size_t n_proofs, const uint64_t* records,
                         const uint64_t* pi_hashes, const uint64_t* plonk_challenges, uint32_t* accept_bitmap, int nthreads);
+
+/* The complete verifier for a batch of serialised proofs of one circuit: sv_verify_proofs_wire plus the plonk-level
+ * identity, all on the device -- unpack, public-inputs hash, plonk challenges, transcript, vanishing-polynomial check,
+ * FRI query phase; bit i = proof i verifies.  first_fail: SV_FAIL_MALFORMED, then SV_FAIL_PLONK, then the FRI codes.
+ * Replaces: verify_inside_snark_mock's whole verification (verifier_api.rs:34-56 -> Verifier::synthesize ->
+ * PlonkVerifierChip::{get_public_inputs_hash, get_challenges, verify_proof_with_challenges}), natively and per batch. */
+int sv_verify_proofs_full(sv_ctx* ctx, const sv_fri_shape* shape, const sv_plonk_circuit* circuit,
+                          const uint64_t* constants_sigmas_cap, const uint64_t circuit_digest[4], const uint8_t* blob,
+                          size_t stride_bytes, size_t n_proofs, uint32_t* accept_bitmap, uint32_t* first_fail);
 
 /* library / build info */
 const char* sv_version(void);

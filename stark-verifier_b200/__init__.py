@@ -34,6 +34,7 @@ from .api import (  # noqa: F401
     CommonData,
     PlonkCommon,
     FAIL_MALFORMED,
+    FAIL_PLONK,
     shape_from_common,
     wire_proof_bytes,
     wire_pack,

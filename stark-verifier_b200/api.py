@@ -21,8 +21,9 @@ HASH_POSEIDON_BN254 = 1      # bn245_poseidon/plonky2_config.rs:54-75 (the refer
 SV_MAX_STEPS = 32
 
 FAIL_NAMES = {0: "ok", 1: "pow", 2: "noncanonical", 3: "init_merkle", 4: "zero_denominator",
-              5: "step_eval", 6: "step_merkle", 7: "final_poly", 8: "malformed"}
+              5: "step_eval", 6: "step_merkle", 7: "final_poly", 8: "malformed", 9: "plonk_identity"}
 FAIL_MALFORMED = 8
+FAIL_PLONK = 9
 
 
 class SvError(RuntimeError):
@@ -238,6 +239,7 @@ def lib() -> ctypes.CDLL:
     L.sv_plonk_challenges.argtypes = [sp, vp, vp, vp, ctypes.c_uint32, vp]
     L.sv_plonk_check_host.argtypes = [sp, pc, ctypes.c_size_t, vp, vp, vp, vp, ctypes.c_int]
     L.sv_plonk_check_batch.argtypes = [vp, sp, pc, ctypes.c_size_t, vp, vp, vp, vp, ctypes.c_int]
+    L.sv_verify_proofs_full.argtypes = [vp, sp, pc, vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t, vp, vp]
     _LIB = L
     return L
 
@@ -601,6 +603,25 @@ class Context:
         self._ck(self._lib.sv_verify_proofs_wire(self._h, ctypes.byref(s), ctypes.byref(c), _ptr(cap), _ptr(cd), _ptr(blob), stride,
                                                  n_proofs, _ptr(bitmap), _ptr(ff) if ff is not None else None),
                  "sv_verify_proofs_wire")
+        return (bitmap, ff) if want_fail else bitmap
+
+    def verify_proofs_full(self, common: CommonData, circuit: PlonkCircuit, constants_sigmas_cap, circuit_digest, blob,
+                           n_proofs: Optional[int] = None, stride: Optional[int] = None, want_fail: bool = False):
+        """The complete verifier on serialised proofs: wire format, public-inputs hash, transcript, vanishing-polynomial
+        identity and FRI query phase, all on the device (sv_verify_proofs_full)."""
+        s = common.fri_params.to_shape()
+        nb = wire_proof_bytes(common)
+        stride = nb if stride is None else stride
+        if isinstance(blob, np.ndarray):
+            blob = np.ascontiguousarray(blob, dtype=np.uint8)
+            n_proofs = blob.size // stride if n_proofs is None else n_proofs
+        cap = np.ascontiguousarray(constants_sigmas_cap, dtype=np.uint64)
+        cd = np.ascontiguousarray(circuit_digest, dtype=np.uint64)
+        bitmap = np.zeros((n_proofs + 31) // 32, dtype=np.uint32)
+        ff = np.zeros(n_proofs, dtype=np.uint32) if want_fail else None
+        self._ck(self._lib.sv_verify_proofs_full(self._h, ctypes.byref(s), ctypes.byref(circuit), _ptr(cap), _ptr(cd), _ptr(blob), stride,
+                                                 n_proofs, _ptr(bitmap), _ptr(ff) if ff is not None else None),
+                 "sv_verify_proofs_full")
         return (bitmap, ff) if want_fail else bitmap
 
     def plonk_check_batch(self, params: FriParams, circuit: PlonkCircuit, records, pi_hashes, plonk_chal,

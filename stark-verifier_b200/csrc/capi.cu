@@ -49,6 +49,7 @@ struct sv_ctx {
     // plonk-level checks: the circuit description on the device, staging for the host path
     sv_plonk_circuit* d_circuit = nullptr; sv_plonk_circuit h_circuit; bool circuit_valid = false;
     u64* d_chal = nullptr; size_t chal_words = 0;
+    u32* d_pbm = nullptr; size_t pbm_words = 0;                        // plonk-identity bitmap of sv_verify_proofs_full
     uint64_t launches = 0;
     // optional CUDA-event timing of the dominant kernel (fri_query_kernel / merkle / permute), on
     // the stream it is launched on
@@ -158,6 +159,7 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaFree(c->d_mal);
     cudaFree(c->d_circuit);
     cudaFree(c->d_chal);
+    cudaFree(c->d_pbm);
     auto drop_s = [](cudaStream_t s) { if (s) cudaStreamDestroy(s); };
     auto drop_e = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
     drop_e(c->ev_hdr); drop_e(c->ev_fs);
@@ -613,6 +615,19 @@ extern "C" int sv_fri_challenges_batch(sv_ctx* c, const sv_fri_shape* shape, siz
     return 0;
 }
 
+// The plonk circuit description on the device (validated by the caller).
+static int upload_circuit(sv_ctx* c, const sv_plonk_circuit* circuit, cudaStream_t s) {
+    if (!c->d_circuit) CK(c, cudaMalloc((void**)&c->d_circuit, sizeof(sv_plonk_circuit)));
+    if (!c->circuit_valid || memcmp(&c->h_circuit, circuit, sizeof *circuit)) {
+        if (int rc = sv_ctx_synchronize(c)) return rc;       // an earlier call may still read the old description
+        c->h_circuit = *circuit;
+        CK(c, cudaMemcpyAsync(c->d_circuit, &c->h_circuit, sizeof(sv_plonk_circuit), cudaMemcpyHostToDevice, s));
+        CK(c, cudaStreamSynchronize(s));
+        c->circuit_valid = true;
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Wire format: serialised proofs -> records on the device (wire_kernels.cuh).
 struct WireDev {
@@ -716,12 +731,18 @@ extern "C" int sv_wire_unpack_batch_gpu(sv_ctx* c, const sv_fri_shape* shape, co
 // chunk's compute stream unpack -> public-input hashes -> transcript -> prepare + query -> reject malformed.
 static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, const sv_fri_shape& shape, const sv_plonk_common& common,
                             const uint64_t* vk_cap, const uint8_t* blob, size_t stride, size_t n_proofs, uint32_t* accept_bitmap,
-                            uint32_t* first_fail) {
+                            uint32_t* first_fail, const sv_plonk_circuit* circuit) {
     int rc = 0;
     const size_t rw = P.L.record_words;
     cudaStream_t cs = c->copy_stream;
     WireDev W;
     if ((rc = wire_tables(c, shape, common, vk_cap, cs, W))) return rc;
+    const u32 nch = common.num_challenges;
+    if (circuit) {
+        if ((rc = upload_circuit(c, circuit, cs))) return rc;
+        if (grow(c, c->d_chal, c->chal_words, 3 * (size_t)nch * n_proofs)) return -6;
+        if (grow(c, c->d_pbm, c->pbm_words, (n_proofs + 31) / 32)) return -6;
+    }
     if (n_proofs > 1 && stride < W.d.proof_bytes) return fail(c, -8, "stride %zu < proof bytes %u", stride, W.d.proof_bytes);
     size_t n_words = (n_proofs + 31) / 32;
     if (grow(c, c->d_bitmap, c->bitmap_words, n_words)) return -6;
@@ -752,9 +773,22 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
         CK(c, cudaEventRecord(c->ev_copied[b], cs));
         CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
         if ((rc = enqueue_unpack(c, W, c->d_wire[b], 0, stride, cnt, c->d_stage[b], c->d_pi + 4 * first, c->d_mal + first, k))) return rc;
+        if (circuit) {   // plonk challenges: the prefix of the transcript below, kept this time
+            P.n_proofs = (u32)cnt;
+            SVB_LAUNCH_KIND(P.hash_kind, plonk_challenges_kernel, (unsigned)((cnt + SVB_FS_BLOCK - 1) / SVB_FS_BLOCK), SVB_FS_BLOCK, k,
+                            c->d_stage[b], P, F, c->d_pi + 4 * first, c->d_chal + 3 * (size_t)nch * first);
+            c->launches++;
+        }
         if ((rc = enqueue_challenges(c, P, F, cnt, c->d_stage[b], c->d_pi + 4 * first, k))) return rc;
         u32* d_fail = first_fail ? c->d_fail + first : nullptr;
         if ((rc = enqueue_fri(c, P, cnt, c->d_stage[b], c->d_scratch + 4 * first, c->d_bitmap + first / 32, d_fail, k))) return rc;
+        if (circuit) {   // the vanishing-polynomial identity (zeta is in the record header now), ANDed into the verdict
+            PlonkRecordView V = {P.L.record_words, P.L.off_open0, P.L.off_open1, P.L.off_zeta};
+            plonk_check_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, k>>>(c->d_stage[b], V, c->d_circuit, c->d_pi + 4 * first,
+                                                                              c->d_chal + 3 * (size_t)nch * first, (u32)cnt, c->d_pbm + first / 32);
+            plonk_and_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, k>>>(c->d_pbm + first / 32, c->d_bitmap + first / 32, d_fail, (u32)cnt);
+            c->launches += 2;
+        }
         wire_reject_malformed_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, k>>>(c->d_mal + first, c->d_bitmap + first / 32, d_fail, (u32)cnt);
         c->launches++;
         CK(c, cudaGetLastError());
@@ -783,7 +817,33 @@ extern "C" int sv_verify_proofs_wire(sv_ctx* c, const sv_fri_shape* shape, const
     if (n_proofs * (size_t)P.num_queries >= (1ull << 31)) return fail(c, -8, "batch too large for one call");
     CK(c, cudaSetDevice(c->device));
     if (grow(c, c->d_scratch, c->scratch_words, 4 * n_proofs)) return -6;
-    rc = wire_verify_host(c, P, F, *shape, *common, vk_cap, blob, stride, n_proofs, accept_bitmap, first_fail);
+    rc = wire_verify_host(c, P, F, *shape, *common, vk_cap, blob, stride, n_proofs, accept_bitmap, first_fail, nullptr);
+    if (rc) {
+        std::string keep = c->err;
+        sv_ctx_synchronize(c);
+        c->err = keep;
+    }
+    return rc;
+}
+
+namespace svb { int plonk_shape_matches(const sv_fri_shape& s, const sv_plonk_circuit& C); }
+
+extern "C" int sv_verify_proofs_full(sv_ctx* c, const sv_fri_shape* shape, const sv_plonk_circuit* circuit, const uint64_t* vk_cap,
+                                     const uint64_t circuit_digest[4], const uint8_t* blob, size_t stride, size_t n_proofs,
+                                     uint32_t* accept_bitmap, uint32_t* first_fail) {
+    if (!c || !shape || !circuit || !vk_cap || !circuit_digest || !accept_bitmap || (n_proofs && !blob)) return -1;
+    if (int rc = plonk_circuit_check(*circuit)) return fail(c, -8, "plonk circuit description refused (%d)", rc);
+    if (int rc = plonk_shape_matches(*shape, *circuit)) return fail(c, -8, "FRI shape and plonk circuit disagree (%d)", rc);
+    FsParams F;
+    int rc = make_fs(c, shape, circuit_digest, circuit->common.num_challenges, F);
+    if (rc) return rc;
+    FriKernelParams P;
+    if ((rc = make_params(c, *shape, P))) return rc;
+    if (n_proofs == 0) return 0;
+    if (n_proofs * (size_t)P.num_queries >= (1ull << 31)) return fail(c, -8, "batch too large for one call");
+    CK(c, cudaSetDevice(c->device));
+    if (grow(c, c->d_scratch, c->scratch_words, 4 * n_proofs)) return -6;
+    rc = wire_verify_host(c, P, F, *shape, circuit->common, vk_cap, blob, stride, n_proofs, accept_bitmap, first_fail, circuit);
     if (rc) {
         std::string keep = c->err;
         sv_ctx_synchronize(c);
@@ -809,14 +869,7 @@ extern "C" int sv_plonk_check_batch(sv_ctx* c, const sv_fri_shape* shape, const 
     if (n >= (1ull << 31)) return fail(c, -8, "batch too large for one call");
     CK(c, cudaSetDevice(c->device));
     cudaStream_t s = mem == SV_MEM_DEVICE ? c->stream : c->own_stream;
-    if (!c->d_circuit) CK(c, cudaMalloc((void**)&c->d_circuit, sizeof(sv_plonk_circuit)));
-    if (!c->circuit_valid || memcmp(&c->h_circuit, circuit, sizeof *circuit)) {
-        if (int rc = sv_ctx_synchronize(c)) return rc;       // an earlier call may still read the old description
-        c->h_circuit = *circuit;
-        CK(c, cudaMemcpyAsync(c->d_circuit, &c->h_circuit, sizeof(sv_plonk_circuit), cudaMemcpyHostToDevice, s));
-        CK(c, cudaStreamSynchronize(s));
-        c->circuit_valid = true;
-    }
+    if (int rc = upload_circuit(c, circuit, s)) return rc;
     PlonkRecordView V = {L.record_words, L.off_open0, L.off_open1, L.off_zeta};
     const u32 nch = circuit->common.num_challenges;
     const unsigned grid = (unsigned)((n + 127) / 128);

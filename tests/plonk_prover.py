@@ -238,8 +238,10 @@ def _constraints(C, consts, wires, pi_hash):
     return out
 
 
-def prove(C, seed, pi_hash):
-    """-> dict(open0=[...Fp2], open1=[...], betas, gammas, alphas, zeta)"""
+def prove(C, seed, pi_hash, draw_betas_gammas=None, draw_alphas=None, draw_zeta=None):
+    """-> dict(open0=[...Fp2], open1=[...], betas, gammas, alphas, zeta, polys=...).  The three optional callbacks let a
+    caller derive the challenges from a transcript over commitments (tests/full_prover.py): draw_betas_gammas(wire_polys)
+    -> (betas, gammas); draw_alphas(z_polys, pp_polys) -> alphas; draw_zeta(quotient_chunks) -> (c0, c1).  Default: random."""
     rng = np.random.default_rng(seed)
     rnd = lambda: int(rng.integers(0, P, dtype=np.uint64))
     n, nr, nw, nch, qdf, npp = C.n, C.num_routed_wires, C.num_wires, C.num_challenges, C.qdf, C.num_partial_products
@@ -338,8 +340,19 @@ def prove(C, seed, pi_hash):
     sig_vals = [[C.k_is[sigma[(r, col)][1]] * gpow[sigma[(r, col)][0]] % P for col in range(nr)] for r in range(n)]
     assert any(sigma[c] != c for c in sigma), "the permutation should not be trivial"
 
+    ninv = inv(n)
+
+    def interpolate(vals):
+        return [ninv * sum(v * pow(g, (-j * r) % n, P) for r, v in enumerate(vals)) % P for j in range(n)]
+
+    const_polys = [interpolate([consts[r][k] for r in range(n)]) for k in range(C.num_constants)]
+    sigma_polys = [interpolate([sig_vals[r][col] for r in range(n)]) for col in range(nr)]
+    wire_polys = [interpolate([wires[r][col] for r in range(n)]) for col in range(nw)]
     # ---- grand products ------------------------------------------------------------------------------
-    betas, gammas, alphas = [rnd() for _ in range(nch)], [rnd() for _ in range(nch)], [rnd() for _ in range(nch)]
+    if draw_betas_gammas:
+        betas, gammas = draw_betas_gammas(const_polys, sigma_polys, wire_polys)
+    else:
+        betas, gammas = [rnd() for _ in range(nch)], [rnd() for _ in range(nch)]
     z_vals, pp_vals = [], []
     for i in range(nch):
         z = [1] * (n + 1)
@@ -358,17 +371,9 @@ def prove(C, seed, pi_hash):
         z_vals.append(z[:n])
         pp_vals.append(pp)
 
-    # ---- interpolation over the trace subgroup -------------------------------------------------------
-    ninv = inv(n)
-
-    def interpolate(vals):
-        return [ninv * sum(v * pow(g, (-j * r) % n, P) for r, v in enumerate(vals)) % P for j in range(n)]
-
-    const_polys = [interpolate([consts[r][k] for r in range(n)]) for k in range(C.num_constants)]
-    sigma_polys = [interpolate([sig_vals[r][col] for r in range(n)]) for col in range(nr)]
-    wire_polys = [interpolate([wires[r][col] for r in range(n)]) for col in range(nw)]
     z_polys = [interpolate(z) for z in z_vals]
     pp_polys = [[interpolate(pp_vals[i][w]) for w in range(npp)] for i in range(nch)]
+    alphas = draw_alphas(z_polys, pp_polys) if draw_alphas else [rnd() for _ in range(nch)]
 
     # ---- vanishing polynomial on a coset, quotient ---------------------------------------------------
     m = 16 * n
@@ -414,10 +419,12 @@ def prove(C, seed, pi_hash):
         quotient_chunks.append([coeffs[j * n:(j + 1) * n] for j in range(qdf)])
 
     # ---- openings ------------------------------------------------------------------------------------
-    zeta = (rnd(), rnd())
+    zeta = draw_zeta(quotient_chunks) if draw_zeta else (rnd(), rnd())
     gz = e_scale(zeta, g)
     open0 = [poly_eval_ext(p, zeta) for p in const_polys + sigma_polys + wire_polys + z_polys]
     open0 += [poly_eval_ext(pp_polys[i][w], zeta) for i in range(nch) for w in range(npp)]
     open0 += [poly_eval_ext(quotient_chunks[i][j], zeta) for i in range(nch) for j in range(qdf)]
     open1 = [poly_eval_ext(p, gz) for p in z_polys]
-    return dict(open0=open0, open1=open1, betas=betas, gammas=gammas, alphas=alphas, zeta=zeta)
+    return dict(open0=open0, open1=open1, betas=betas, gammas=gammas, alphas=alphas, zeta=zeta,
+                polys=dict(constants=const_polys, sigmas=sigma_polys, wires=wire_polys, zs=z_polys, partial_products=pp_polys,
+                           quotient=quotient_chunks))

@@ -1,0 +1,52 @@
+"""The complete verifier on the device (sv_verify_proofs_full): serialised COMPLETE proofs of toy circuits -- the
+reference's recursion gate set included -- must be accepted, every corruption rejected with the right first-failure
+class, and the verdicts must equal the CPU side's (oracle FRI verifier AND plonk identity)."""
+import os
+
+import numpy as np
+import pytest
+
+from common import bit
+from test_full_proof import ROOT, build, cpu_verdicts
+from test_plonk_check import CONFIGS, c_gates
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,hash_kind", [("one_selector", 0), ("two_selectors", 1), ("recursion_gate_set", 0)])
+def test_full_verifier_matches_cpu_side(svb, orc, ctx, name, hash_kind):
+    base = 3 if name != "recursion_gate_set" else 2
+    B = build(svb, orc, name, base, seed=21, hash_kind=hash_kind)
+    L, common = B["L"], B["common"]
+    n = 41
+    blob = np.stack([B["blob"][i % base] for i in range(n)])
+    caps_end = 3 * 32 * L.ncap
+    open_end = caps_end + 16 * (L.n0 + L.n1)
+    blob[5, caps_end + 40] ^= 1                            # an opening            -> plonk identity (and FRI)
+    blob[9, open_end + 8 * L.leaf_len[0] + 1 + 9] ^= 2      # a sibling             -> FRI only
+    blob[17, open_end + 8 * L.leaf_len[0]] ^= 1             # a Merkle length byte  -> malformed
+    blob[33, -3] ^= 1                                       # a public input        -> other challenges
+    blob[40, 7] ^= 8                                        # the wires cap         -> other challenges
+    fri, pl, opl, mal, _ = cpu_verdicts(svb, orc, B, blob)
+    assert pl == opl
+    want = [int(f and p and not m) for f, p, m in zip(fri, pl, mal)]
+    assert [i for i in range(n) if not want[i]] == [5, 9, 17, 33, 40]
+    bm, ff = ctx.verify_proofs_full(common, B["circuit"], B["vk_cap"], B["cd"], blob.reshape(-1), want_fail=True)
+    assert [bit(bm, i) for i in range(n)] == want
+    assert ff[17] == svb.FAIL_MALFORMED and ff[5] == svb.FAIL_PLONK and (ff[9] & 0xFF) == 3 and all(ff[i] == 0 for i in range(n) if want[i])
+    assert pl[9] == 1 and fri[9] == 0
+    # without the plonk identity the FRI-only entry point gives the FRI verdicts
+    bm_fri = ctx.verify_proofs_wire(common, B["vk_cap"], B["cd"], blob.reshape(-1))
+    assert [bit(bm_fri, i) for i in range(n)] == [int(f and not m) for f, m in zip(fri, mal)]
+    # idempotent
+    assert (ctx.verify_proofs_full(common, B["circuit"], B["vk_cap"], B["cd"], blob.reshape(-1)) == bm).all()
+
+
+def test_full_verifier_golden_blob(svb, ctx):
+    import full_prover as fp
+    g = np.load(os.path.join(ROOT, "tests", "golden", "full_proof_toy.npz"))
+    C, params = fp.toy_setup(svb, CONFIGS[str(g["config"])])
+    common = svb.CommonData.for_params(params, num_public_inputs=int(g["num_public_inputs"]), num_constants=C.num_constants)
+    circuit = svb.make_plonk_circuit(common, c_gates(C), C.groups, C.k_is, C.num_gate_constraints)
+    bm = ctx.verify_proofs_full(common, circuit, g["vk_cap"], g["circuit_digest"], g["blob"].reshape(-1))
+    assert [bit(bm, i) for i in range(g["blob"].shape[0])] == [int(v) for v in g["accept"]]

@@ -244,12 +244,49 @@ def wire_leg(svb, torch, ctx, params, L, n_host, distinct, seed, threads, steps)
             ctx.verify_proofs_wire(common, vk_cap, cds[0], p.value, n_proofs=n_host)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        plonk = plonk_leg(svb, torch, ctx, params, recs, n_host, steps)
     finally:
         svb.lib().sv_host_free(p)
-    return {"value": n_host * steps / dt, "unit": "proofs/s", "h2d_bytes_per_step": int(n_host * nb),
+    return {"plonk_check": plonk, "value": n_host * steps / dt, "unit": "proofs/s", "h2d_bytes_per_step": int(n_host * nb),
             "d2h_bytes_per_step": int(exp.size * 4), "steps": steps, "proof_bytes": int(nb), "public_inputs": n_pi,
             "note": "sv_verify_proofs_wire: pinned plonky2 wire bytes -> H2D -> wire_unpack_kernel + wire_pi_hash_kernel -> "
                     "device transcript -> fri_query_kernel, per 32 MiB chunk"}
+
+
+def plonk_leg(svb, torch, ctx, params, recs, n_host, steps):
+    """Throughput of plonk_check_kernel (the vanishing-polynomial identity with the reference's whole recursion gate set)
+    on n_host device-resident records.  The synthetic proofs do not satisfy the identity -- the work per proof does not
+    depend on that -- so every bit must come back 0."""
+    try:
+        nch = params.num_zs
+        common = svb.CommonData.for_params(params, num_public_inputs=4)
+        gates = [(svb.GATE_NOOP, 0), (svb.GATE_CONSTANT, 2), (svb.GATE_PUBLIC_INPUT, 0), (svb.GATE_ARITHMETIC, common.num_routed_wires // 4),
+                 (svb.GATE_ARITHMETIC_EXT, 10), (svb.GATE_MUL_EXT, 13), (svb.GATE_BASE_SUM, 63), (svb.GATE_REDUCING, 43),
+                 (svb.GATE_REDUCING_EXT, 32), (svb.GATE_RANDOM_ACCESS, 4, 4, 2), (svb.GATE_POSEIDON_MDS, 0), (svb.GATE_POSEIDON, 0)]
+        circuit = svb.make_plonk_circuit(common, gates, [(0, 7), (7, 12)], [pow(7, j, 0xFFFFFFFF00000001) for j in range(common.num_routed_wires)], 123)
+        reps = (n_host + recs.shape[0] - 1) // recs.shape[0]
+        d_recs = torch.from_numpy(recs.view(np.int64)).cuda().repeat(reps, 1)[:n_host].contiguous()
+        rng = np.random.default_rng(5)
+        d_pih = torch.from_numpy(rng.integers(0, 2**63, size=(n_host, 4), dtype=np.int64)).cuda()
+        d_chal = torch.from_numpy(rng.integers(0, 2**63, size=(n_host, 3 * nch), dtype=np.int64)).cuda()
+        d_bm = torch.ones((n_host + 31) // 32, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        run = lambda: ctx.plonk_check_batch(params, circuit, d_recs.data_ptr(), d_pih.data_ptr(), d_chal.data_ptr(), n_proofs=n_host,
+                                            accept_bitmap=d_bm.data_ptr(), mem=svb.MEM_DEVICE)
+        for _ in range(2):
+            run()
+        ctx.synchronize()
+        if d_bm.cpu().numpy().any():
+            return {"error": "a random opening set satisfied the identity"}
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            run()
+        ctx.synchronize()
+        dt = time.perf_counter() - t0
+        return {"value": n_host * steps / dt, "unit": "proofs/s", "ms_per_call": 1e3 * dt / steps, "proofs_per_call": n_host,
+                "note": "plonk_check_kernel, recursion gate set (12 gates incl. PoseidonGate), device-resident records"}
+    except Exception as ex:   # noqa: BLE001
+        return {"error": f"{type(ex).__name__}: {ex}"}
 
 
 def run_wire_leg(args):

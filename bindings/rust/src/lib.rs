@@ -81,6 +81,29 @@ pub struct sv_plonk_common {
 }
 
 pub const SV_FAIL_MALFORMED: u32 = 8;
+pub const SV_FAIL_PLONK: u32 = 9;
+pub const SV_MAX_GATES: usize = 32;
+pub const SV_MAX_SELECTORS: usize = 8;
+pub const SV_MAX_ROUTED_WIRES: usize = 128;
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct sv_plonk_gate { pub kind: u32, pub param: u32, pub param2: u32, pub param3: u32, pub selector_index: u32 }
+
+/// What `eval_vanishing_poly` reads from `CommonData` (types/common_data.rs:56-96).
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct sv_plonk_circuit {
+    pub common: sv_plonk_common,
+    pub degree_bits: u32,
+    pub num_gate_constraints: u32,
+    pub num_selectors: u32,
+    pub group_lo: [u32; SV_MAX_SELECTORS],
+    pub group_hi: [u32; SV_MAX_SELECTORS],
+    pub num_gates: u32,
+    pub gates: [sv_plonk_gate; SV_MAX_GATES],
+    pub k_is: [u64; SV_MAX_ROUTED_WIRES],
+}
 
 #[repr(C)]
 pub struct sv_ctx { _private: [u8; 0] }
@@ -124,6 +147,12 @@ extern "C" {
                                  constants_sigmas_cap: *const u64, circuit_digest: *const u64, blob: *const u8,
                                  stride_bytes: usize, n_proofs: usize, accept_bitmap: *mut u32, first_fail: *mut u32) -> c_int;
     pub fn sv_public_inputs_hash(public_inputs: *const u64, n: usize, out: *mut u64) -> c_int;
+    // plonk-level checks and the complete verifier
+    pub fn sv_plonk_gate_from_id(gate_id: *const c_char, out: *mut sv_plonk_gate) -> c_int;
+    pub fn sv_plonk_circuit_check(circuit: *const sv_plonk_circuit) -> c_int;
+    pub fn sv_verify_proofs_full(ctx: *mut sv_ctx, shape: *const sv_fri_shape, circuit: *const sv_plonk_circuit,
+                                 constants_sigmas_cap: *const u64, circuit_digest: *const u64, blob: *const u8,
+                                 stride_bytes: usize, n_proofs: usize, accept_bitmap: *mut u32, first_fail: *mut u32) -> c_int;
 }
 
 #[derive(Debug)]
@@ -273,7 +302,52 @@ pub fn common_from<F: halo2_proofs::halo2curves::ff::PrimeField>(cd: &CommonData
     }
 }
 
+/// `CommonData` -> `sv_plonk_circuit`.  `gate_ids[i]` = `common_circuit_data.gates[i].0.id()` of the plonky2 value the
+/// `CommonData` was converted from (the reference's own `CustomGateRef::from` matches on the same strings,
+/// chip/plonk/gates/mod.rs:138-196); an id it does not know is an error here, `unimplemented!()` there.
+pub fn circuit_from<F: halo2_proofs::halo2curves::ff::PrimeField>(cd: &CommonData<F>, gate_ids: &[String]) -> Result<sv_plonk_circuit, GpuError> {
+    let mut c: sv_plonk_circuit = unsafe { std::mem::zeroed() };
+    c.common = common_from(cd);
+    c.degree_bits = cd.fri_params.degree_bits as u32;
+    c.num_gate_constraints = cd.num_gate_constraints as u32;
+    c.num_selectors = cd.selectors_info.groups.len() as u32;
+    for (s, g) in cd.selectors_info.groups.iter().enumerate() { c.group_lo[s] = g.start as u32; c.group_hi[s] = g.end as u32; }
+    c.num_gates = gate_ids.len() as u32;
+    for (i, id) in gate_ids.iter().enumerate() {
+        let cid = std::ffi::CString::new(id.as_str()).unwrap();
+        if unsafe { sv_plonk_gate_from_id(cid.as_ptr(), &mut c.gates[i]) } != 0 { return Err(GpuError(-2, format!("unknown gate {id}"))); }
+        c.gates[i].selector_index = cd.selectors_info.selector_indices[i] as u32;
+    }
+    for (j, k) in cd.k_is.iter().enumerate() { c.k_is[j] = k.0; }
+    let rc = unsafe { sv_plonk_circuit_check(&c) };
+    if rc != 0 { return Err(GpuError(rc, "inconsistent circuit description".into())); }
+    Ok(c)
+}
+
 impl GpuFriVerifier {
+    /// The complete verifier (plonk identity AND FRI) on serialised proofs of one circuit: what
+    /// `verify_inside_snark_mock` establishes per proof (verifier_api.rs:34-56), natively and per batch.
+    pub fn verify_serialized_full<F: halo2_proofs::halo2curves::ff::PrimeField>(
+        &mut self, blob: &[u8], vk: &VerificationKeyValues<F>, common_data: &CommonData<F>, gate_ids: &[String],
+    ) -> Result<Vec<bool>, GpuError> {
+        let shape = shape_from(common_data);
+        let circuit = circuit_from(common_data, gate_ids)?;
+        let nb = unsafe { sv_wire_proof_bytes(&shape, &circuit.common) };
+        if nb == 0 || blob.len() % nb != 0 { return Err(GpuError(-1, "blob is not a whole number of proofs".into())); }
+        let n = blob.len() / nb;
+        let mut cap = vec![0u64; 4 << shape.cap_height];
+        put_cap(&mut cap, &vk.constants_sigmas_cap);
+        let digest: Vec<u64> = vk.circuit_digest.elements.iter().map(|e| e.0).collect();
+        let mut bitmap = vec![0u32; (n + 31) / 32];
+        let rc = unsafe { sv_verify_proofs_full(self.ctx, &shape, &circuit, cap.as_ptr(), digest.as_ptr(), blob.as_ptr(), nb, n,
+                                                bitmap.as_mut_ptr(), std::ptr::null_mut()) };
+        if rc != 0 {
+            let msg = unsafe { CStr::from_ptr(sv_last_error(self.ctx)) }.to_string_lossy().into_owned();
+            return Err(GpuError(rc, msg));
+        }
+        Ok((0..n).map(|i| (bitmap[i >> 5] >> (i & 31)) & 1 == 1).collect())
+    }
+
     /// The whole verifier-side path from serialised proofs: `blob` holds `n` back-to-back
     /// `ProofWithPublicInputs::to_bytes()` strings of ONE circuit (they all have the same length,
     /// `sv_wire_proof_bytes`).  Unpacking, the public-inputs hash, the Fiat-Shamir transcript and the FRI

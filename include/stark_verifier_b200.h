@@ -326,6 +326,12 @@ typedef struct sv_plonk_circuit {
     uint64_t k_is[SV_MAX_ROUTED_WIRES]; /* CommonData.k_is, one coset shift per routed wire */
 } sv_plonk_circuit;
 
+/* plonky2 gate id string (`gate.0.id()`, the key CustomGateRef::from matches on, chip/plonk/gates/mod.rs:138-196) ->
+ * kind and parameters; selector_index is left 0.  Accepts the ids of that table with ANY numeric parameters (the
+ * reference hard-codes the ones of its recursion circuits), base-2 BaseSumGate only; < 0 for an unknown id
+ * (the reference: unimplemented!()). */
+int sv_plonk_gate_from_id(const char* gate_id, sv_plonk_gate* out);
+
 /* 0 if the circuit description is consistent and uses only gates this library evaluates, else < 0. */
 int sv_plonk_circuit_check(const sv_plonk_circuit* circuit);
 

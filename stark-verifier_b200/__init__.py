@@ -56,5 +56,6 @@ from .api import (  # noqa: F401
     GATE_POSEIDON,
     make_plonk_circuit,
     plonk_challenges,
+    plonk_gate_from_id,
     plonk_check_host,
 )

@@ -236,6 +236,7 @@ def lib() -> ctypes.CDLL:
     L.sv_public_inputs_hash.argtypes = [vp, ctypes.c_size_t, vp]
     pc = ctypes.POINTER(PlonkCircuit)
     L.sv_plonk_circuit_check.argtypes = [pc]
+    L.sv_plonk_gate_from_id.argtypes = [ctypes.c_char_p, ctypes.POINTER(PlonkGate)]
     L.sv_plonk_challenges.argtypes = [sp, vp, vp, vp, ctypes.c_uint32, vp]
     L.sv_plonk_check_host.argtypes = [sp, pc, ctypes.c_size_t, vp, vp, vp, vp, ctypes.c_int]
     L.sv_plonk_check_batch.argtypes = [vp, sp, pc, ctypes.c_size_t, vp, vp, vp, vp, ctypes.c_int]
@@ -397,6 +398,15 @@ def make_plonk_circuit(common: CommonData, gates, groups, k_is, num_gate_constra
     if rc != 0:
         raise SvError(f"sv_plonk_circuit_check refused the circuit: {rc}")
     return c
+
+
+def plonk_gate_from_id(gate_id: str):
+    """plonky2 gate id string -> (kind, param, param2, param3), the mapping of CustomGateRef::from (gates/mod.rs:138-196)."""
+    g = PlonkGate()
+    rc = lib().sv_plonk_gate_from_id(gate_id.encode(), ctypes.byref(g))
+    if rc != 0:
+        raise SvError(f"unknown gate id {gate_id!r} (the reference: unimplemented!())")
+    return (g.kind, g.param, g.param2, g.param3)
 
 
 def plonk_challenges(params: FriParams, record: np.ndarray, circuit_digest, pi_hash, num_challenges: int = 2) -> np.ndarray:

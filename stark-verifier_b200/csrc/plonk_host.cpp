@@ -4,6 +4,9 @@
 #include "host_util.hpp"
 #include "layout.hpp"
 
+#include <cstdio>
+#include <string>
+
 using namespace svb;
 
 namespace svb {
@@ -18,6 +21,35 @@ int plonk_shape_matches(const sv_fri_shape& s, const sv_plonk_circuit& C) {
     return 0;
 }
 }  // namespace svb
+
+// CustomGateRef::from (gates/mod.rs:138-196) matches `gate.0.id().trim_end()` against literal strings; the same
+// strings here, with the numbers read instead of hard-coded.
+extern "C" int sv_plonk_gate_from_id(const char* id, sv_plonk_gate* out) {
+    if (!id || !out) return -1;
+    std::string s(id);
+    while (!s.empty() && (s.back() == ' ' || s.back() == '\n' || s.back() == '\t')) s.pop_back();
+    sv_plonk_gate g;
+    memset(&g, 0, sizeof g);
+    unsigned a = 0, b = 0, c = 0;
+    int used = 0;
+    auto whole = [&](int n) { return n > 0 && (size_t)n == s.size(); };
+    if (s == "NoopGate") g.kind = SV_GATE_NOOP;
+    else if (s == "PublicInputGate") g.kind = SV_GATE_PUBLIC_INPUT;
+    else if (sscanf(s.c_str(), "ArithmeticGate { num_ops: %u }%n", &a, &used) == 1 && whole(used)) { g.kind = SV_GATE_ARITHMETIC; g.param = a; }
+    else if (sscanf(s.c_str(), "ConstantGate { num_consts: %u }%n", &a, &used) == 1 && whole(used)) { g.kind = SV_GATE_CONSTANT; g.param = a; }
+    else if (sscanf(s.c_str(), "BaseSumGate { num_limbs: %u } + Base: %u%n", &a, &b, &used) == 2 && whole(used) && b == 2) { g.kind = SV_GATE_BASE_SUM; g.param = a; }
+    else if (sscanf(s.c_str(), "ArithmeticExtensionGate { num_ops: %u }%n", &a, &used) == 1 && whole(used)) { g.kind = SV_GATE_ARITHMETIC_EXT; g.param = a; }
+    else if (sscanf(s.c_str(), "MulExtensionGate { num_ops: %u }%n", &a, &used) == 1 && whole(used)) { g.kind = SV_GATE_MUL_EXT; g.param = a; }
+    else if (sscanf(s.c_str(), "ReducingGate { num_coeffs: %u }%n", &a, &used) == 1 && whole(used)) { g.kind = SV_GATE_REDUCING; g.param = a; }
+    else if (sscanf(s.c_str(), "ReducingExtensionGate { num_coeffs: %u }%n", &a, &used) == 1 && whole(used)) { g.kind = SV_GATE_REDUCING_EXT; g.param = a; }
+    else if (sscanf(s.c_str(), "RandomAccessGate { bits: %u, num_copies: %u, num_extra_constants: %u, _phantom: PhantomData<plonky2_field::goldilocks_field::GoldilocksField> }<D=2>%n",
+                    &a, &b, &c, &used) == 3 && whole(used)) { g.kind = SV_GATE_RANDOM_ACCESS; g.param = a; g.param2 = b; g.param3 = c; }
+    else if (s == "PoseidonGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>") g.kind = SV_GATE_POSEIDON;
+    else if (s == "PoseidonMdsGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>") g.kind = SV_GATE_POSEIDON_MDS;
+    else return -2;
+    *out = g;
+    return 0;
+}
 
 extern "C" int sv_plonk_circuit_check(const sv_plonk_circuit* circuit) {
     if (!circuit) return -1;

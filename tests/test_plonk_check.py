@@ -165,3 +165,43 @@ def test_plonk_challenges_match_oracle_and_the_fri_transcript(svb, orc, kind):
     r[L.off_init_caps + 4 * L.ncap] ^= np.uint64(1)        # first word of the wires cap
     after = svb.plonk_challenges(params, r, cds[0], pih[1])
     assert (before != after).all()
+
+
+def test_gate_ids_of_the_reference(svb):
+    """The id strings CustomGateRef::from matches (chip/plonk/gates/mod.rs:138-196), verbatim, map to the kinds and
+    parameters the reference constructs; anything else is refused like its unimplemented!()."""
+    ids = {
+        "ArithmeticGate { num_ops: 20 }": (svb.GATE_ARITHMETIC, 20, 0, 0),
+        "PublicInputGate": (svb.GATE_PUBLIC_INPUT, 0, 0, 0),
+        "NoopGate": (svb.GATE_NOOP, 0, 0, 0),
+        "ConstantGate { num_consts: 2 }": (svb.GATE_CONSTANT, 2, 0, 0),
+        "BaseSumGate { num_limbs: 63 } + Base: 2": (svb.GATE_BASE_SUM, 63, 0, 0),
+        "PoseidonGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>": (svb.GATE_POSEIDON, 0, 0, 0),
+        "PoseidonMdsGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>": (svb.GATE_POSEIDON_MDS, 0, 0, 0),
+        "RandomAccessGate { bits: 1, num_copies: 20, num_extra_constants: 0, _phantom: PhantomData<plonky2_field::goldilocks_field::GoldilocksField> }<D=2>":
+            (svb.GATE_RANDOM_ACCESS, 1, 20, 0),
+        "RandomAccessGate { bits: 4, num_copies: 4, num_extra_constants: 2, _phantom: PhantomData<plonky2_field::goldilocks_field::GoldilocksField> }<D=2>":
+            (svb.GATE_RANDOM_ACCESS, 4, 4, 2),
+        "ReducingExtensionGate { num_coeffs: 32 }": (svb.GATE_REDUCING_EXT, 32, 0, 0),
+        "ReducingGate { num_coeffs: 43 }": (svb.GATE_REDUCING, 43, 0, 0),
+        "ArithmeticExtensionGate { num_ops: 10 }": (svb.GATE_ARITHMETIC_EXT, 10, 0, 0),
+        "MulExtensionGate { num_ops: 13 }": (svb.GATE_MUL_EXT, 13, 0, 0),
+        "BaseSumGate { num_limbs: 4 } + Base: 2": (svb.GATE_BASE_SUM, 4, 0, 0),
+    }
+    for gid, want in ids.items():
+        assert svb.plonk_gate_from_id(gid) == want
+        assert svb.plonk_gate_from_id(gid + "  ") == want          # .trim_end()
+    for bad in ("ExponentiationGate { num_power_bits: 66 }", "BaseSumGate { num_limbs: 63 } + Base: 4", "ArithmeticGate { num_ops: 20 } x",
+                "CosetInterpolationGate", ""):
+        with pytest.raises(svb.SvError):
+            svb.plonk_gate_from_id(bad)
+    # the ids above, in the reference's gate set, make a circuit the library accepts on the standard recursion configuration
+    C, params, circuit, L = setup(svb, CONFIGS["recursion_gate_set"])
+    from_ids = [svb.plonk_gate_from_id(g) for g in (
+        "NoopGate", "ConstantGate { num_consts: 2 }", "PublicInputGate", "ArithmeticGate { num_ops: 20 }",
+        "ArithmeticExtensionGate { num_ops: 10 }", "MulExtensionGate { num_ops: 13 }", "BaseSumGate { num_limbs: 63 } + Base: 2",
+        "ReducingGate { num_coeffs: 43 }", "ReducingExtensionGate { num_coeffs: 32 }",
+        "RandomAccessGate { bits: 4, num_copies: 4, num_extra_constants: 2, _phantom: PhantomData<plonky2_field::goldilocks_field::GoldilocksField> }<D=2>",
+        "PoseidonMdsGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>",
+        "PoseidonGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>")]
+    assert [tuple(g) for g in from_ids] == [tuple((list(g) + [0, 0])[:4]) for g in c_gates(C)]

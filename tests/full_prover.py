@@ -5,7 +5,8 @@ public-inputs hash -> transcript -> vanishing-polynomial identity -> FRI query p
 Pure Python for the algebra; hashing and the transcript go through the CPU oracle (oracle/oracle.c), which is pinned to
 plonky2's Poseidon test vectors.  The trace has 2^4 rows, which is below the final-polynomial size of the reference's
 FRI configuration (ConstantArityBits(1, 5), bn245_poseidon/plonky2_config.rs:84), so there are no reduction steps: the
-final polynomial IS the batched DEEP quotient and the query phase checks it against the four oracle openings.
+final polynomial IS the batched DEEP quotient and the query phase checks it against the four oracle openings.  With
+degree_bits = 6 or 7 the same prover runs one or two arity-2 reduction steps (commit phase, betas, step trees).
 
 Conventions (the ones the verifier implies; same as the product's synthetic prover, stark-verifier_b200/csrc/host_side.cpp):
 leaf i of an oracle tree holds the evaluations at 7 * omega^bitrev(i); batch 0 = every polynomial at zeta in oracle order,
@@ -53,13 +54,22 @@ def ext_poly_divide_by_linear(coeffs, z):
     return b
 
 
+def poly_eval_ext_ext(coeffs, x):
+    """polynomial with Fp2 coefficients at a base-field point"""
+    acc = (0, 0)
+    for c in reversed(coeffs):
+        acc = e_add(e_scale(acc, x), c)
+    return acc
+
+
 def prove_full(svb, orc, C, params, seed, public_inputs, circuit_digest):
     """-> (record with every field filled, dict of the plonk prover's outputs).  params: FriParams consistent with C and
     with no reduction steps."""
     L = svb.api.make_layout(params)
     oshape = orc.shape_from(params.to_shape())
     kind = params.hash_kind
-    assert len(params.reduction_arity_bits) == 0 and params.final_poly_len() == C.n and not params.hiding
+    steps = len(params.reduction_arity_bits)
+    assert params.final_poly_len() == C.n >> steps and not params.hiding
     lde_bits, cap_h, nch = L.lde_bits, params.config.cap_height, C.num_challenges
     N = 1 << lde_bits
     omega = pow(7, (P - 1) >> lde_bits, P)
@@ -119,7 +129,24 @@ def prove_full(svb, orc, C, params, seed, public_inputs, circuit_digest):
         alpha_n1 = e_mul(alpha_n1, alpha)
     final = [e_add(e_mul(a, alpha_n1), b) for a, b in zip(q0, q1)] + [(0, 0)]
     assert len(final) == C.n
-    rec[L.off_final_poly:L.off_final_poly + 2 * C.n] = [w for e in final for w in e]
+    # ---- commit phase (fri_chip.rs:168-226, 275-315 from the prover's side): layer st holds the values of the current
+    # polynomial on shift_st * <omega_st>, leaf k of its tree = the coset pair (2k, 2k+1); f(x) = f_E(x^2) + x f_O(x^2)
+    # folds to f_E + beta f_O, i.e. coefficient-wise c'_j = c_2j + beta c_2j+1
+    step_vals, step_trees = [], []
+    shift, bits_cur, w_cur = 7, lde_bits, omega
+    for st in range(steps):
+        vals = [poly_eval_ext_ext(final, shift * pow(w_cur, bitrev(i, bits_cur), P) % P) for i in range(1 << bits_cur)]
+        tree = Tree(orc, [list(vals[2 * k]) + list(vals[2 * k + 1]) for k in range(len(vals) // 2)], cap_h, kind)
+        capw = 4 * L.ncap
+        rec[L.off_step_caps + st * capw: L.off_step_caps + (st + 1) * capw] = tree.cap()
+        orc.fri_challenges(oshape, rec, circuit_digest, pi_hash, nch)
+        beta = (int(rec[L.off_betas + 2 * st]), int(rec[L.off_betas + 2 * st + 1]))
+        final = [e_add(final[2 * j], e_mul(beta, final[2 * j + 1])) for j in range(len(final) // 2)]
+        step_vals.append(vals)
+        step_trees.append(tree)
+        shift, bits_cur, w_cur = shift * shift % P, bits_cur - 1, w_cur * w_cur % P
+    assert len(final) == params.final_poly_len()
+    rec[L.off_final_poly:L.off_final_poly + 2 * len(final)] = [w for e in final for w in e]
     # proof of work: the smallest witness whose response has proof_of_work_bits leading zero bits
     bits = params.config.proof_of_work_bits
     w = 0
@@ -139,13 +166,22 @@ def prove_full(svb, orc, C, params, seed, public_inputs, circuit_digest):
             path = trees[k].path(idx)
             assert len(path) == 4 * L.init_depth
             rec[qb + L.q_off_init_sibs[k]: qb + L.q_off_init_sibs[k] + len(path)] = path
+        cur = idx
+        for st in range(steps):
+            coset = cur >> 1
+            rec[qb + L.q_off_step_evals[st]: qb + L.q_off_step_evals[st] + 4] = list(step_vals[st][2 * coset]) + list(step_vals[st][2 * coset + 1])
+            path = step_trees[st].path(coset)
+            assert len(path) == 4 * L.step_depth[st]
+            rec[qb + L.q_off_step_sibs[st]: qb + L.q_off_step_sibs[st] + len(path)] = path
+            cur = coset
     out["pi_hash"] = pi_hash
     return rec, out
 
 
 def toy_setup(svb, cfg):
-    """(Circuit, FriParams, CommonData factory args) for a plonk_prover configuration, with a FRI configuration that
-    matches the reference's shape in miniature: rate 1/8, cap height 1, 2 PoW bits, 5 query rounds."""
+    """(Circuit, FriParams) for a plonk_prover configuration, with a FRI configuration that matches the reference's shape
+    in miniature: rate 1/8, cap height 1, 2 PoW bits, 5 query rounds, arity-2 reduction down to 32 coefficients
+    (degree_bits <= 5: no reduction steps; 6: one; 7: two)."""
     C = pp.Circuit(**cfg)
     widths = (C.num_constants + C.num_routed_wires, C.num_wires, C.num_challenges * (1 + C.num_partial_products),
               C.num_challenges * C.qdf)

@@ -14,9 +14,9 @@ from test_plonk_check import CONFIGS, c_gates
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def build(svb, orc, name, n, seed, n_pi=6, hash_kind=0):
+def build(svb, orc, name, n, seed, n_pi=6, hash_kind=0, degree_bits=4):
     """n complete proofs of one circuit -> dict with everything the verifier side needs."""
-    C, params = fp.toy_setup(svb, CONFIGS[name])
+    C, params = fp.toy_setup(svb, dict(CONFIGS[name], degree_bits=degree_bits))
     params.hash_kind = hash_kind
     rng = np.random.default_rng(seed)
     cd = rng.integers(0, P, size=4, dtype=np.uint64)
@@ -57,6 +57,20 @@ def test_complete_proofs_verify_from_bytes(svb, orc, name, hash_kind):
     fri, pl, opl, mal, r2 = cpu_verdicts(svb, orc, B, B["blob"])
     assert fri == [1] * n and pl == [1] * n and opl == [1] * n and mal == [0] * n
     assert (r2 == B["recs"]).all()                      # bytes -> record -> transcript reproduces the prover's record
+
+
+def test_complete_proof_with_fri_reduction_steps(svb, orc):
+    """2^6 rows: the FRI instance has a commit phase (one arity-2 fold, fri_chip.rs:168-226,275-315) -- the third,
+    independent implementation of the folding conventions next to the oracle's verifier and the product's prover."""
+    B = build(svb, orc, "two_selectors", 2, seed=31, degree_bits=6)
+    assert len(B["params"].reduction_arity_bits) == 1 and B["L"].step_depth[0] == B["L"].lde_bits - 1 - 1
+    blob = np.concatenate([B["blob"], B["blob"][:1]])
+    L = B["L"]
+    step_caps_at = 3 * 32 * L.ncap + 16 * (L.n0 + L.n1)
+    blob[2, step_caps_at + 3] ^= 1                       # the commit-phase cap: other beta, and the step tree no longer matches
+    fri, pl, opl, mal, r2 = cpu_verdicts(svb, orc, B, blob)
+    assert fri == [1, 1, 0] and pl == [1, 1, 1] and opl == pl and mal == [0, 0, 0]
+    assert (r2[:2] == B["recs"]).all()
 
 
 def test_every_region_of_the_wire_bytes_is_checked(svb, orc):

@@ -42,6 +42,19 @@ def test_full_verifier_matches_cpu_side(svb, orc, ctx, name, hash_kind):
     assert (ctx.verify_proofs_full(common, B["circuit"], B["vk_cap"], B["cd"], blob.reshape(-1)) == bm).all()
 
 
+def test_full_verifier_with_fri_reduction_steps(svb, orc, ctx):
+    B = build(svb, orc, "two_selectors", 2, seed=31, degree_bits=6)
+    L = B["L"]
+    blob = np.concatenate([B["blob"], B["blob"], B["blob"][:1]])
+    blob[2, 3 * 32 * L.ncap + 16 * (L.n0 + L.n1) + 3] ^= 1      # the commit-phase cap
+    blob[4, 3 * 32 * L.ncap + 5] ^= 1                           # an opening
+    fri, pl, opl, mal, _ = cpu_verdicts(svb, orc, B, blob)
+    want = [int(f and p and not m) for f, p, m in zip(fri, pl, mal)]
+    assert want == [1, 1, 0, 1, 0]
+    bm, ff = ctx.verify_proofs_full(B["common"], B["circuit"], B["vk_cap"], B["cd"], blob.reshape(-1), want_fail=True)
+    assert [bit(bm, i) for i in range(5)] == want and ff[4] == svb.FAIL_PLONK and ff[2] not in (0, svb.FAIL_PLONK, svb.FAIL_MALFORMED)
+
+
 def test_full_verifier_golden_blob(svb, ctx):
     import full_prover as fp
     g = np.load(os.path.join(ROOT, "tests", "golden", "full_proof_toy.npz"))

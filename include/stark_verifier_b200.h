@@ -365,6 +365,24 @@ int sv_verify_proofs_full(sv_ctx* ctx, const sv_fri_shape* shape, const sv_plonk
                           const uint64_t* constants_sigmas_cap, const uint64_t circuit_digest[4], const uint8_t* blob,
                           size_t stride_bytes, size_t n_proofs, uint32_t* accept_bitmap, uint32_t* first_fail);
 
+/* --- commit-phase library: NTT / low-degree extension over Goldilocks ------------------ */
+/* n_polys polynomials of 2^log_n words each, contiguous, transformed in place.
+ * inverse = 0: coefficients (natural order) -> evaluations, the value at omega^bitrev(i) in position i (omega =
+ * 7^((p-1)/2^log_n)) -- the order in which plonky2 puts evaluations into Merkle leaves and the FRI verifier reads them
+ * back (chip/fri_chip.rs:152-166, 262-264).  inverse = 1: the reverse, 1/n included.
+ * Replaces: plonky2_field's fft / ifft as used by the prover side of the reference (plonky2_semaphore/*, not on the
+ * verifier's hot path); shared-memory tiled, 2-3 HBM passes per transform. */
+int sv_ntt_batch(sv_ctx* ctx, uint32_t log_n, size_t n_polys, uint64_t* data, int inverse, int mem);
+/* out[p][i] = f_p(shift * omega_N^bitrev(i)), N = 2^(log_n + rate_bits): the low-degree extension of n_polys coefficient
+ * vectors onto the coset shift * <omega_N>, in Merkle-leaf order (plonky2: PolynomialBatch::from_coeffs / lde_values with
+ * shift = 7).  coeffs: n_polys x 2^log_n, out: n_polys x N. */
+int sv_lde_batch(sv_ctx* ctx, uint32_t log_n, uint32_t rate_bits, size_t n_polys, const uint64_t* coeffs, uint64_t shift,
+                 uint64_t* out, int mem);
+/* the same two transforms on CPU threads (the function the kernels run, one "thread" per tile) */
+int sv_ntt_host(uint32_t log_n, size_t n_polys, uint64_t* data, int inverse, int nthreads);
+int sv_lde_host(uint32_t log_n, uint32_t rate_bits, size_t n_polys, const uint64_t* coeffs, uint64_t shift, uint64_t* out,
+                int nthreads);
+
 /* library / build info */
 const char* sv_version(void);
 

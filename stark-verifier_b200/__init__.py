@@ -58,4 +58,6 @@ from .api import (  # noqa: F401
     plonk_challenges,
     plonk_gate_from_id,
     plonk_check_host,
+    ntt_host,
+    lde_host,
 )

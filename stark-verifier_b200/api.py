@@ -240,6 +240,10 @@ def lib() -> ctypes.CDLL:
     L.sv_plonk_challenges.argtypes = [sp, vp, vp, vp, ctypes.c_uint32, vp]
     L.sv_plonk_check_host.argtypes = [sp, pc, ctypes.c_size_t, vp, vp, vp, vp, ctypes.c_int]
     L.sv_plonk_check_batch.argtypes = [vp, sp, pc, ctypes.c_size_t, vp, vp, vp, vp, ctypes.c_int]
+    L.sv_ntt_batch.argtypes = [vp, ctypes.c_uint32, ctypes.c_size_t, vp, ctypes.c_int, ctypes.c_int]
+    L.sv_lde_batch.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_size_t, vp, u64, vp, ctypes.c_int]
+    L.sv_ntt_host.argtypes = [ctypes.c_uint32, ctypes.c_size_t, vp, ctypes.c_int, ctypes.c_int]
+    L.sv_lde_host.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_size_t, vp, u64, vp, ctypes.c_int]
     L.sv_verify_proofs_full.argtypes = [vp, sp, pc, vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t, vp, vp]
     _LIB = L
     return L
@@ -435,6 +439,30 @@ def plonk_check_host(params: FriParams, circuit: PlonkCircuit, records, pi_hashe
     if rc != 0:
         raise SvError(f"sv_plonk_check_host failed: {rc}")
     return bm
+
+
+# -- commit-phase library ---------------------------------------------------------------
+def ntt_host(polys: np.ndarray, inverse: bool = False, nthreads: int = 1) -> np.ndarray:
+    """(n_polys, 2^k) coefficients -> evaluations at omega^bitrev(i) (or back), on CPU threads (the kernels' function)."""
+    a = np.array(polys, dtype=np.uint64, copy=True, order="C").reshape(-1, np.shape(polys)[-1])
+    k = int(a.shape[1]).bit_length() - 1
+    assert a.shape[1] == 1 << k
+    rc = lib().sv_ntt_host(k, a.shape[0], _ptr(a), int(inverse), nthreads)
+    if rc != 0:
+        raise SvError(f"sv_ntt_host failed: {rc}")
+    return a
+
+
+def lde_host(coeffs: np.ndarray, rate_bits: int, shift: int = 7, nthreads: int = 1) -> np.ndarray:
+    """(n_polys, 2^k) coefficients -> (n_polys, 2^(k+rate_bits)) values at shift * omega_N^bitrev(i), on CPU threads."""
+    a = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, np.shape(coeffs)[-1])
+    k = int(a.shape[1]).bit_length() - 1
+    assert a.shape[1] == 1 << k
+    out = np.zeros((a.shape[0], a.shape[1] << rate_bits), dtype=np.uint64)
+    rc = lib().sv_lde_host(k, rate_bits, a.shape[0], _ptr(a), ctypes.c_uint64(shift), _ptr(out), nthreads)
+    if rc != 0:
+        raise SvError(f"sv_lde_host failed: {rc}")
+    return out
 
 
 class Context:
@@ -648,6 +676,25 @@ class Context:
                                                 _ptr(pi_hashes), _ptr(plonk_chal), _ptr(accept_bitmap), mem),
                  "sv_plonk_check_batch")
         return accept_bitmap
+
+    def ntt_batch(self, data, log_n: Optional[int] = None, n_polys: Optional[int] = None, inverse: bool = False, mem: int = MEM_HOST):
+        """In-place batch NTT (ntt_pass_kernel).  Host mode: returns a transformed copy of the (n_polys, 2^k) array."""
+        if mem == MEM_HOST:
+            data = np.array(data, dtype=np.uint64, copy=True, order="C").reshape(-1, np.shape(data)[-1])
+            n_polys, log_n = data.shape[0], int(data.shape[1]).bit_length() - 1
+        self._ck(self._lib.sv_ntt_batch(self._h, log_n, n_polys, _ptr(data), int(inverse), mem), "sv_ntt_batch")
+        return data
+
+    def lde_batch(self, coeffs, rate_bits: int, shift: int = 7, log_n: Optional[int] = None, n_polys: Optional[int] = None, out=None,
+                  mem: int = MEM_HOST):
+        """Low-degree extension onto shift * <omega_N> in Merkle-leaf order (lde_scale_pad_kernel + ntt_pass_kernel)."""
+        if mem == MEM_HOST:
+            coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, np.shape(coeffs)[-1])
+            n_polys, log_n = coeffs.shape[0], int(coeffs.shape[1]).bit_length() - 1
+            out = np.zeros((n_polys, coeffs.shape[1] << rate_bits), dtype=np.uint64)
+        self._ck(self._lib.sv_lde_batch(self._h, log_n, rate_bits, n_polys, _ptr(coeffs), ctypes.c_uint64(shift), _ptr(out), mem),
+                 "sv_lde_batch")
+        return out
 
     def allgather_bitmap(self, nccl_comm: int, local_ptr: int, all_ptr: int, words_per_rank: int):
         self._ck(self._lib.sv_allgather_bitmap(self._h, ctypes.c_void_p(nccl_comm), local_ptr, all_ptr, words_per_rank),

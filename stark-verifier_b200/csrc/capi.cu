@@ -4,6 +4,7 @@
 #include "fri_kernels.cuh"
 #include "wire_kernels.cuh"
 #include "plonk_kernels.cuh"
+#include "ntt_kernels.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -49,7 +50,9 @@ struct sv_ctx {
     // plonk-level checks: the circuit description on the device, staging for the host path
     sv_plonk_circuit* d_circuit = nullptr; sv_plonk_circuit h_circuit; bool circuit_valid = false;
     u64* d_chal = nullptr; size_t chal_words = 0;
-    u32* d_pbm = nullptr; size_t pbm_words = 0;                        // plonk-identity bitmap of sv_verify_proofs_full
+    u32* d_pbm = nullptr; size_t pbm_words = 0;
+    // NTT twiddles of the last (log_n, direction) used
+    u64* d_tw = nullptr; size_t tw_words = 0; u32 tw_k = 0; int tw_inverse = -1;                        // plonk-identity bitmap of sv_verify_proofs_full
     uint64_t launches = 0;
     // optional CUDA-event timing of the dominant kernel (fri_query_kernel / merkle / permute), on
     // the stream it is launched on
@@ -160,6 +163,7 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaFree(c->d_circuit);
     cudaFree(c->d_chal);
     cudaFree(c->d_pbm);
+    cudaFree(c->d_tw);
     auto drop_s = [](cudaStream_t s) { if (s) cudaStreamDestroy(s); };
     auto drop_e = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
     drop_e(c->ev_hdr); drop_e(c->ev_fs);
@@ -894,6 +898,88 @@ extern "C" int sv_plonk_check_batch(sv_ctx* c, const sv_fri_shape* shape, const 
     CK(c, cudaGetLastError());
     CK(c, cudaMemcpyAsync(accept_bitmap, c->d_bitmap, n_words * 4, cudaMemcpyDeviceToHost, s));
     CK(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NTT / LDE: ntt_pass_kernel, one launch per pass of ntt_plan.
+static int ntt_twiddles_dev(sv_ctx* c, u32 k, bool inverse, cudaStream_t s) {
+    if (c->d_tw && c->tw_k == k && c->tw_inverse == (int)inverse) return 0;
+    if (int rc = sv_ctx_synchronize(c)) return rc;           // an earlier transform may still read the old table
+    const size_t words = std::max<size_t>(1, ((size_t)1 << k) / 2);
+    if (grow(c, c->d_tw, c->tw_words, words)) return -6;
+    std::vector<u64> tw(words);
+    ntt_twiddles(k, inverse, tw.data());
+    CK(c, cudaMemcpyAsync(c->d_tw, tw.data(), words * 8, cudaMemcpyHostToDevice, s));
+    CK(c, cudaStreamSynchronize(s));                         // tw goes out of scope
+    c->tw_k = k;
+    c->tw_inverse = (int)inverse;
+    return 0;
+}
+
+static int enqueue_ntt(sv_ctx* c, u32 k, size_t n_polys, u64* d_data, bool inverse, cudaStream_t s) {
+    NttPass plan[8];
+    int np = ntt_plan(k, inverse, plan);
+    if (np < 0) return fail(c, -8, "bad transform size 2^%u", k);
+    if (n_polys > 65535) return fail(c, -8, "more than 65535 polynomials per call");
+    if (int rc = ntt_twiddles_dev(c, k, inverse, s)) return rc;
+    for (int q = 0; q < np; q++) {
+        dim3 grid((unsigned)ntt_blocks_per_poly(plan[q]), (unsigned)n_polys);
+        ntt_pass_kernel<<<grid, SVB_NTT_BLOCK, 0, s>>>(d_data, c->d_tw, plan[q]);
+        c->launches++;
+    }
+    if (inverse) {
+        const size_t total = n_polys << k;
+        ntt_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_data, total, inv(((u64)1 << k) % GL_P));
+        c->launches++;
+    }
+    CK(c, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sv_ntt_batch(sv_ctx* c, uint32_t log_n, size_t n_polys, uint64_t* data, int inverse, int mem) {
+    if (!c || (!data && n_polys)) return -1;
+    if (!known_mem(mem)) return fail(c, -5, "mem %d is neither SV_MEM_HOST nor SV_MEM_DEVICE", mem);
+    if (log_n == 0 || log_n > 26) return fail(c, -8, "log_n out of range (1..26)");
+    if (n_polys == 0) return 0;
+    CK(c, cudaSetDevice(c->device));
+    if (mem == SV_MEM_DEVICE) return enqueue_ntt(c, log_n, n_polys, data, inverse != 0, c->stream);
+    const size_t words = n_polys << log_n;
+    if (grow(c, c->d_stage[0], c->stage_words[0], words)) return -6;
+    cudaStream_t s = c->own_stream;
+    CK(c, cudaMemcpyAsync(c->d_stage[0], data, words * 8, cudaMemcpyHostToDevice, s));
+    if (int rc = enqueue_ntt(c, log_n, n_polys, c->d_stage[0], inverse != 0, s)) return rc;
+    CK(c, cudaMemcpyAsync(data, c->d_stage[0], words * 8, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int sv_lde_batch(sv_ctx* c, uint32_t log_n, uint32_t rate_bits, size_t n_polys, const uint64_t* coeffs, uint64_t shift,
+                            uint64_t* out, int mem) {
+    if (!c || ((!coeffs || !out) && n_polys)) return -1;
+    if (!known_mem(mem)) return fail(c, -5, "mem %d is neither SV_MEM_HOST nor SV_MEM_DEVICE", mem);
+    if (log_n == 0 || log_n + rate_bits > 26 || !is_canonical(shift) || shift == 0) return fail(c, -8, "bad LDE parameters");
+    if (n_polys == 0) return 0;
+    CK(c, cudaSetDevice(c->device));
+    const u32 log_N = log_n + rate_bits;
+    const size_t in_words = n_polys << log_n, out_words = n_polys << log_N;
+    cudaStream_t s = mem == SV_MEM_DEVICE ? c->stream : c->own_stream;
+    const u64* d_in = coeffs;
+    u64* d_out = out;
+    if (mem != SV_MEM_DEVICE) {
+        if (grow(c, c->d_stage[0], c->stage_words[0], in_words)) return -6;
+        if (grow(c, c->d_stage[1], c->stage_words[1], out_words)) return -6;
+        CK(c, cudaMemcpyAsync(c->d_stage[0], coeffs, in_words * 8, cudaMemcpyHostToDevice, s));
+        d_in = c->d_stage[0];
+        d_out = c->d_stage[1];
+    }
+    lde_scale_pad_kernel<<<(unsigned)((out_words + 255) / 256), 256, 0, s>>>(d_in, d_out, log_n, log_N, n_polys, shift);
+    c->launches++;
+    if (int rc = enqueue_ntt(c, log_N, n_polys, d_out, false, s)) return rc;
+    if (mem != SV_MEM_DEVICE) {
+        CK(c, cudaMemcpyAsync(out, d_out, out_words * 8, cudaMemcpyDeviceToHost, s));
+        CK(c, cudaStreamSynchronize(s));
+    }
     return 0;
 }
 

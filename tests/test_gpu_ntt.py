@@ -1,0 +1,65 @@
+"""GPU side of the NTT / LDE library: ntt_pass_kernel / lde_scale_pad_kernel against the host twin of the
+same tile routine (pinned by tests/test_ntt.py), and the whole commit phase on the device -- LDE -> leaves -> Merkle cap --
+against the cap a complete proof of the Python prover carries."""
+import numpy as np
+import pytest
+
+from common import P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("k", [1, 5, 9, 10, 12, 15, 19])
+def test_ntt_kernel_matches_host_twin(svb, ctx, k):
+    rng = np.random.default_rng(k)
+    n_polys = 3 if k < 19 else 2
+    a = rng.integers(0, P, size=(n_polys, 1 << k), dtype=np.uint64)
+    a[0, :] = P - 1
+    want = svb.ntt_host(a, nthreads=4)
+    got = ctx.ntt_batch(a)
+    assert (got == want).all()
+    back = ctx.ntt_batch(got, inverse=True)
+    assert (back == a).all()
+
+
+def test_ntt_device_memory_and_many_polys(svb, ctx):
+    import torch
+    rng = np.random.default_rng(3)
+    k, n_polys = 12, 300
+    a = rng.integers(0, P, size=(n_polys, 1 << k), dtype=np.uint64)
+    d = torch.from_numpy(a.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    ctx.ntt_batch(d.data_ptr(), log_n=k, n_polys=n_polys, mem=svb.MEM_DEVICE)
+    ctx.synchronize()
+    assert (d.cpu().numpy().view(np.uint64) == svb.ntt_host(a, nthreads=4)).all()
+    ctx.ntt_batch(d.data_ptr(), log_n=k, n_polys=n_polys, inverse=True, mem=svb.MEM_DEVICE)
+    ctx.synchronize()
+    assert (d.cpu().numpy().view(np.uint64) == a).all()
+
+
+@pytest.mark.parametrize("k,rate_bits", [(4, 3), (9, 1), (12, 3), (13, 2)])
+def test_lde_kernel_matches_host_twin(svb, ctx, k, rate_bits):
+    rng = np.random.default_rng(10 * k + rate_bits)
+    c = rng.integers(0, P, size=(5, 1 << k), dtype=np.uint64)
+    assert (ctx.lde_batch(c, rate_bits) == svb.lde_host(c, rate_bits, nthreads=4)).all()
+    assert (ctx.lde_batch(c, rate_bits, shift=1)[:, 0] == np.array([sum(int(v) for v in row) % P for row in c], dtype=np.uint64)).all()
+
+
+def test_commit_phase_on_the_device_reproduces_a_proofs_cap(svb, orc, ctx):
+    """coefficients -> sv_lde_batch -> leaf-major -> sv_merkle_tree_build: the cap equals the wires cap inside a complete
+    proof made by the independent Python prover (which hashed the same leaves through the CPU oracle)."""
+    import torch
+    import full_prover as fp
+    from test_plonk_check import CONFIGS
+    C, params = fp.toy_setup(svb, CONFIGS["recursion_gate_set"])
+    rng = np.random.default_rng(2)
+    cd = rng.integers(0, P, size=4, dtype=np.uint64)
+    rec, out = fp.prove_full(svb, orc, C, params, 4, rng.integers(0, P, size=3, dtype=np.uint64), cd)
+    L = svb.api.make_layout(params)
+    capw = 4 * L.ncap
+    for oracle_index, polys in ((1, out["polys"]["wires"]), (0, out["polys"]["constants"] + out["polys"]["sigmas"])):
+        coeffs = np.array(polys, dtype=np.uint64)
+        lde = ctx.lde_batch(coeffs, params.config.rate_bits)                       # (n_polys, N)
+        leaves = np.ascontiguousarray(lde.T)                                       # (N, n_polys): one row per leaf
+        layers = ctx.merkle_tree_build(leaves, leaves.shape[1], params.config.cap_height)
+        assert (layers[-1].reshape(-1) == rec[L.off_init_caps + oracle_index * capw: L.off_init_caps + (oracle_index + 1) * capw]).all()

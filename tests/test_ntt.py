@@ -1,0 +1,98 @@
+"""NTT / LDE, CPU side: the host twin runs the kernels' own tile routine (ntt.hpp: ntt_pass_block), so these
+tests pin the index arithmetic, the pass plan (1, 2 and 3 passes), the twiddles and the output order against naive
+big-integer evaluation and against the Merkle-leaf convention of the independent Python prover."""
+import numpy as np
+import pytest
+
+from common import P
+
+
+def bitrev(x, bits):
+    return int(format(x, "0%db" % bits)[::-1], 2) if bits else 0
+
+
+def naive_eval(coeffs, x):
+    acc = 0
+    for c in reversed(coeffs):
+        acc = (acc * x + int(c)) % P
+    return acc
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 7])
+def test_forward_matches_naive_dft_in_bit_reversed_order(svb, k):
+    rng = np.random.default_rng(k)
+    a = rng.integers(0, P, size=(3, 1 << k), dtype=np.uint64)
+    a[1] = 0
+    a[1, 1] = 1                                             # the polynomial x: values are the points themselves
+    got = svb.ntt_host(a)
+    w = pow(7, (P - 1) >> k, P)
+    for p in range(3):
+        want = [naive_eval(a[p], pow(w, bitrev(i, k), P)) for i in range(1 << k)]
+        assert [int(v) for v in got[p]] == want
+    assert (svb.ntt_host(got, inverse=True) == a).all()
+
+
+@pytest.mark.parametrize("k", [9, 10, 12, 13, 15, 18, 19])
+def test_multi_pass_sizes_sampled_points_and_round_trip(svb, k):
+    """9: one pass of 9 stages; 10-18: two passes; 19: three.  Values at sampled positions against Horner; inverse undoes it."""
+    rng = np.random.default_rng(100 + k)
+    n = 1 << k
+    a = rng.integers(0, P, size=(2, n), dtype=np.uint64)
+    if k > 13:
+        a[:, 64:] = 0                                       # sparse enough for the big-integer Horner below
+        deg = 64
+    else:
+        deg = n
+    got = svb.ntt_host(a, nthreads=2)
+    w = pow(7, (P - 1) >> k, P)
+    for i in [0, 1, 2, n // 2, n - 1] + [int(x) for x in rng.integers(0, n, size=6)]:
+        x = pow(w, bitrev(i, k), P)
+        for p in range(2):
+            assert int(got[p, i]) == naive_eval(a[p, :deg], x), (k, i)
+    assert (svb.ntt_host(got, inverse=True, nthreads=2) == a).all()
+
+
+def test_linearity_and_convolution(svb):
+    k = 11
+    rng = np.random.default_rng(5)
+    n = 1 << k
+    a = rng.integers(0, P, size=n, dtype=np.uint64)
+    b = rng.integers(0, P, size=n, dtype=np.uint64)
+    a[n // 2:] = 0
+    b[n // 2:] = 0
+    fa, fb = svb.ntt_host(a[None])[0], svb.ntt_host(b[None])[0]
+    prod = np.array([int(x) * int(y) % P for x, y in zip(fa, fb)], dtype=np.uint64)
+    c = svb.ntt_host(prod[None], inverse=True)[0]
+    # coefficient 5 and the top coefficient of the product polynomial, by hand
+    assert int(c[5]) == sum(int(a[i]) * int(b[5 - i]) for i in range(6)) % P
+    assert int(c[n - 2]) == int(a[n // 2 - 1]) * int(b[n // 2 - 1]) % P and int(c[n - 1]) == 0
+
+
+def test_lde_is_the_merkle_leaf_order_of_the_python_prover(svb, orc):
+    """sv_lde_host of a proof's wire polynomials == the leaves the independent Python prover commits to
+    (leaf i = evaluations at 7 * omega_N^bitrev(i)); and the Merkle cap over those leaves is the proof's wires cap."""
+    import full_prover as fp
+    import plonk_prover as pp
+    from test_plonk_check import CONFIGS
+    C, params = fp.toy_setup(svb, CONFIGS["one_selector"])
+    rng = np.random.default_rng(2)
+    cd = rng.integers(0, P, size=4, dtype=np.uint64)
+    rec, out = fp.prove_full(svb, orc, C, params, 4, rng.integers(0, P, size=3, dtype=np.uint64), cd)
+    wires = np.array(out["polys"]["wires"], dtype=np.uint64)            # (num_wires, n) coefficients
+    lde = svb.lde_host(wires, params.config.rate_bits, shift=7)
+    L = svb.api.make_layout(params)
+    N = 1 << L.lde_bits
+    w = pow(7, (P - 1) >> L.lde_bits, P)
+    for i in (0, 1, 5, N - 1):
+        x = 7 * pow(w, bitrev(i, L.lde_bits), P) % P
+        assert [int(v) for v in lde[:, i]] == [naive_eval(p, x) for p in wires]
+    tree = fp.Tree(orc, [[int(v) for v in lde[:, i]] for i in range(N)], params.config.cap_height)
+    capw = 4 * L.ncap
+    assert tree.cap() == [int(v) for v in rec[L.off_init_caps + capw: L.off_init_caps + 2 * capw]]
+
+
+def test_bad_arguments(svb):
+    with pytest.raises(svb.SvError):
+        svb.ntt_host(np.full((1, 8), P, dtype=np.uint64))               # non-canonical input
+    with pytest.raises(svb.SvError):
+        svb.lde_host(np.zeros((1, 8), dtype=np.uint64), 2, shift=0)

@@ -370,7 +370,7 @@ int sv_verify_proofs_full(sv_ctx* ctx, const sv_fri_shape* shape, const sv_plonk
  * inverse = 0: coefficients (natural order) -> evaluations, the value at omega^bitrev(i) in position i (omega =
  * 7^((p-1)/2^log_n)) -- the order in which plonky2 puts evaluations into Merkle leaves and the FRI verifier reads them
  * back (chip/fri_chip.rs:152-166, 262-264).  inverse = 1: the reverse, 1/n included.
- * Replaces: plonky2_field's fft / ifft as used by the prover side of the reference (plonky2_semaphore/*, not on the
+ * Replaces: plonky2_field's fft / ifft as used by the prover side of the reference (the plonky2_semaphore module, not on the
  * verifier's hot path); shared-memory tiled, 2-3 HBM passes per transform. */
 int sv_ntt_batch(sv_ctx* ctx, uint32_t log_n, size_t n_polys, uint64_t* data, int inverse, int mem);
 /* out[p][i] = f_p(shift * omega_N^bitrev(i)), N = 2^(log_n + rate_bits): the low-degree extension of n_polys coefficient

@@ -1,7 +1,7 @@
 """A COMPLETE proof of a toy circuit (tests/full_prover.py: commitments, Fiat-Shamir, openings, FRI opening proof -- the
 reference's recursion gate set at the standard parameters included) through every stage of the verifier on the CPU
 side: wire bytes -> unpack -> public-inputs hash -> transcript -> vanishing-polynomial identity (product host twin and
-oracle) -> FRI query phase (oracle).  tests/test_gpu_full_proof.py runs the same proofs through sv_verify_proofs_full."""
+oracle) -> FRI query phase (oracle).  tests/test_gpu_verify_full.py runs the same proofs through sv_verify_proofs_full."""
 import os
 
 import numpy as np

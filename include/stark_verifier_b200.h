@@ -378,6 +378,13 @@ int sv_ntt_batch(sv_ctx* ctx, uint32_t log_n, size_t n_polys, uint64_t* data, in
  * shift = 7).  coeffs: n_polys x 2^log_n, out: n_polys x N. */
 int sv_lde_batch(sv_ctx* ctx, uint32_t log_n, uint32_t rate_bits, size_t n_polys, const uint64_t* coeffs, uint64_t shift,
                  uint64_t* out, int mem);
+/* The prover's commitment to n_polys polynomials in one call: LDE onto 7 * <omega_N> (sv_lde_batch), leaves = one row of
+ * n_polys values per evaluation point (a transposing copy), Merkle tree down to the cap (sv_merkle_tree_build).
+ * leaves_out: N x n_polys words (NULL: not wanted; SV_MEM_DEVICE needs it as scratch, so it must be given there);
+ * layers_out: 4 * (2N - 2^cap_height) words as in sv_merkle_tree_build.
+ * Replaces: plonky2 PolynomialBatch::from_coeffs (LDE + MerkleTree::new), the commit step of the reference's prover side. */
+int sv_commit_batch(sv_ctx* ctx, uint32_t log_n, uint32_t rate_bits, size_t n_polys, const uint64_t* coeffs, uint32_t cap_height,
+                    int hash_kind, uint64_t* leaves_out, uint64_t* layers_out, int mem);
 /* the same two transforms on CPU threads (the function the kernels run, one "thread" per tile) */
 int sv_ntt_host(uint32_t log_n, size_t n_polys, uint64_t* data, int inverse, int nthreads);
 int sv_lde_host(uint32_t log_n, uint32_t rate_bits, size_t n_polys, const uint64_t* coeffs, uint64_t shift, uint64_t* out,

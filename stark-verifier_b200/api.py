@@ -242,6 +242,7 @@ def lib() -> ctypes.CDLL:
     L.sv_plonk_check_batch.argtypes = [vp, sp, pc, ctypes.c_size_t, vp, vp, vp, vp, ctypes.c_int]
     L.sv_ntt_batch.argtypes = [vp, ctypes.c_uint32, ctypes.c_size_t, vp, ctypes.c_int, ctypes.c_int]
     L.sv_lde_batch.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_size_t, vp, u64, vp, ctypes.c_int]
+    L.sv_commit_batch.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_size_t, vp, ctypes.c_uint32, ctypes.c_int, vp, vp, ctypes.c_int]
     L.sv_ntt_host.argtypes = [ctypes.c_uint32, ctypes.c_size_t, vp, ctypes.c_int, ctypes.c_int]
     L.sv_lde_host.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_size_t, vp, u64, vp, ctypes.c_int]
     L.sv_verify_proofs_full.argtypes = [vp, sp, pc, vp, vp, vp, ctypes.c_size_t, ctypes.c_size_t, vp, vp]
@@ -695,6 +696,23 @@ class Context:
         self._ck(self._lib.sv_lde_batch(self._h, log_n, rate_bits, n_polys, _ptr(coeffs), ctypes.c_uint64(shift), _ptr(out), mem),
                  "sv_lde_batch")
         return out
+
+    def commit_batch(self, coeffs, rate_bits: int, cap_height: int, hash_kind: int = HASH_POSEIDON_GOLDILOCKS):
+        """(n_polys, 2^k) coefficients -> (leaves (N, n_polys), digest layers bottom-up as in merkle_tree_build), host arrays:
+        LDE onto 7 * <omega_N>, leaf-major copy and Merkle tree, all on the device (sv_commit_batch)."""
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, np.shape(coeffs)[-1])
+        n_polys, log_n = coeffs.shape[0], int(coeffs.shape[1]).bit_length() - 1
+        N = coeffs.shape[1] << rate_bits
+        leaves = np.zeros((N, n_polys), dtype=np.uint64)
+        flat = np.zeros(4 * (2 * N - (1 << cap_height)), dtype=np.uint64)
+        self._ck(self._lib.sv_commit_batch(self._h, log_n, rate_bits, n_polys, _ptr(coeffs), cap_height, hash_kind, _ptr(leaves), _ptr(flat),
+                                           MEM_HOST), "sv_commit_batch")
+        layers, off, m = [], 0, N
+        while m >= (1 << cap_height):
+            layers.append(flat[off:off + 4 * m].reshape(m, 4))
+            off += 4 * m
+            m >>= 1
+        return leaves, layers
 
     def allgather_bitmap(self, nccl_comm: int, local_ptr: int, all_ptr: int, words_per_rank: int):
         self._ck(self._lib.sv_allgather_bitmap(self._h, ctypes.c_void_p(nccl_comm), local_ptr, all_ptr, words_per_rank),

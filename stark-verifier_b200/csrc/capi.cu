@@ -983,6 +983,57 @@ extern "C" int sv_lde_batch(sv_ctx* c, uint32_t log_n, uint32_t rate_bits, size_
     return 0;
 }
 
+extern "C" int sv_commit_batch(sv_ctx* c, uint32_t log_n, uint32_t rate_bits, size_t n_polys, const uint64_t* coeffs, uint32_t cap_height,
+                               int hash_kind, uint64_t* leaves_out, uint64_t* layers_out, int mem) {
+    if (!c || !coeffs || !layers_out || n_polys == 0) return -1;
+    if (!known_mem(mem)) return fail(c, -5, "mem %d is neither SV_MEM_HOST nor SV_MEM_DEVICE", mem);
+    if (!known_kind(hash_kind)) return fail(c, -5, "hash_kind %d not implemented", hash_kind);
+    if (log_n == 0 || log_n + rate_bits > 26 || cap_height > log_n + rate_bits) return fail(c, -8, "bad commit parameters");
+    if (mem == SV_MEM_DEVICE && !leaves_out) return fail(c, -8, "SV_MEM_DEVICE needs leaves_out (it is the scratch of the transposition)");
+    CK(c, cudaSetDevice(c->device));
+    const u32 log_N = log_n + rate_bits;
+    const size_t N = (size_t)1 << log_N, ncap = (size_t)1 << cap_height;
+    const size_t in_words = n_polys << log_n, lde_words = n_polys << log_N, layer_words = 4 * (2 * N - ncap);
+    cudaStream_t s = mem == SV_MEM_DEVICE ? c->stream : c->own_stream;
+    // device buffers: [2] = LDE (polynomial-major), leaves (point-major), layers
+    if (grow(c, c->d_stage[2], c->stage_words[2], lde_words)) return -6;
+    const u64* d_in = coeffs;
+    u64 *d_leaves = leaves_out, *d_layers = layers_out;
+    if (mem != SV_MEM_DEVICE) {
+        if (grow(c, c->d_stage[0], c->stage_words[0], in_words)) return -6;
+        if (grow(c, c->d_stage[1], c->stage_words[1], lde_words)) return -6;
+        if (grow(c, c->d_stage[3], c->stage_words[3], layer_words)) return -6;
+        CK(c, cudaMemcpyAsync(c->d_stage[0], coeffs, in_words * 8, cudaMemcpyHostToDevice, s));
+        d_in = c->d_stage[0];
+        d_leaves = c->d_stage[1];
+        d_layers = c->d_stage[3];
+    }
+    u64* d_lde = c->d_stage[2];
+    lde_scale_pad_kernel<<<(unsigned)((lde_words + 255) / 256), 256, 0, s>>>(d_in, d_lde, log_n, log_N, n_polys, 7);
+    c->launches++;
+    if (int rc = enqueue_ntt(c, log_N, n_polys, d_lde, false, s)) return rc;
+    dim3 tg((unsigned)((N + 31) / 32), (unsigned)((n_polys + 31) / 32));
+    transpose_kernel<<<tg, dim3(32, 8), 0, s>>>(d_lde, d_leaves, n_polys, N);
+    c->launches++;
+    const int B = SVB_BLOCK;
+    SVB_LAUNCH_KIND(hash_kind, merkle_leaf_hash_kernel, (unsigned)((N + B - 1) / B), B, s, d_leaves, (u32)n_polys, N, d_layers);
+    c->launches++;
+    u64* cur = d_layers;
+    for (size_t m = N; m > ncap; m >>= 1) {
+        u64* nxt = cur + 4 * m;
+        SVB_LAUNCH_KIND(hash_kind, merkle_level_kernel, (unsigned)((m / 2 + B - 1) / B), B, s, cur, nxt, m / 2);
+        c->launches++;
+        cur = nxt;
+    }
+    CK(c, cudaGetLastError());
+    if (mem != SV_MEM_DEVICE) {
+        if (leaves_out) CK(c, cudaMemcpyAsync(leaves_out, d_leaves, lde_words * 8, cudaMemcpyDeviceToHost, s));
+        CK(c, cudaMemcpyAsync(layers_out, d_layers, layer_words * 8, cudaMemcpyDeviceToHost, s));
+        CK(c, cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 extern "C" int sv_allgather_bitmap(sv_ctx* c, void* nccl_comm, const uint32_t* local_words, uint32_t* all_words,
                                    size_t words_per_rank) {

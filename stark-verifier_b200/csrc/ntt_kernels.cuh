@@ -29,4 +29,20 @@ __global__ void lde_scale_pad_kernel(const u64* __restrict__ coeffs, u64* __rest
     out[i] = lde_scaled_coeff(coeffs + (p << log_n), (u64)1 << log_n, shift, j);
 }
 
+// [rows][cols] -> [cols][rows] through a 32 x 33 shared tile (coalesced on both sides): LDE output (one row per
+// polynomial) -> Merkle leaves (one row per evaluation point).  grid = (ceil(cols/32), ceil(rows/32)), block = (32, 8).
+__global__ void __launch_bounds__(256) transpose_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t rows, size_t cols) {
+    __shared__ u64 tile[32][33];
+    const size_t c0 = (size_t)blockIdx.x * 32, r0 = (size_t)blockIdx.y * 32;
+    for (u32 j = threadIdx.y; j < 32; j += 8) {
+        const size_t r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = in[r * cols + c];
+    }
+    __syncthreads();
+    for (u32 j = threadIdx.y; j < 32; j += 8) {
+        const size_t c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
 }  // namespace svb

@@ -63,3 +63,21 @@ def test_commit_phase_on_the_device_reproduces_a_proofs_cap(svb, orc, ctx):
         leaves = np.ascontiguousarray(lde.T)                                       # (N, n_polys): one row per leaf
         layers = ctx.merkle_tree_build(leaves, leaves.shape[1], params.config.cap_height)
         assert (layers[-1].reshape(-1) == rec[L.off_init_caps + oracle_index * capw: L.off_init_caps + (oracle_index + 1) * capw]).all()
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_commit_batch_one_call(svb, orc, ctx, kind):
+    """sv_commit_batch = LDE + leaf-major copy + Merkle tree; against the host LDE twin and the oracle's hashes."""
+    rng = np.random.default_rng(7 + kind)
+    k, rate_bits, cap_height, n_polys = 5, 2, 1, 37                    # 37 columns: ragged transposition tiles
+    coeffs = rng.integers(0, P, size=(n_polys, 1 << k), dtype=np.uint64)
+    leaves, layers = ctx.commit_batch(coeffs, rate_bits, cap_height, hash_kind=kind)
+    want_leaves = np.ascontiguousarray(svb.lde_host(coeffs, rate_bits).T)
+    assert (leaves == want_leaves).all()
+    N = 1 << (k + rate_bits)
+    assert [l.shape[0] for l in layers] == [N >> i for i in range(k + rate_bits - cap_height + 1)]
+    for i in (0, 1, N - 1):
+        assert (layers[0][i] == orc.hash_no_pad(want_leaves[i], kind)).all()
+    for lv in range(1, len(layers)):
+        for j in (0, layers[lv].shape[0] - 1):
+            assert (layers[lv][j] == orc.two_to_one(layers[lv - 1][2 * j], layers[lv - 1][2 * j + 1], kind)).all()

@@ -30,12 +30,14 @@ static inline uint64_t orc_red128_slow(orc_u128 x) { return (uint64_t)(x % ORC_P
 static inline uint64_t orc_red128(orc_u128 x) {
     uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
     uint64_t hh = hi >> 32, hl = hi & 0xFFFFFFFFULL;
+    /* the two wrap corrections and the final canonicalisation as masks: the wraps are data-dependent coin flips, and a
+     * mispredicted branch costs more than the whole reduction */
     uint64_t t0 = lo - hh;
-    if (lo < hh) t0 -= 0xFFFFFFFFULL;
+    t0 -= 0xFFFFFFFFULL & (0 - (uint64_t)(lo < hh));
     uint64_t t1 = hl * 0xFFFFFFFFULL;
     uint64_t t2 = t0 + t1;
-    if (t2 < t1) t2 += 0xFFFFFFFFULL;
-    return t2 >= ORC_P ? t2 - ORC_P : t2;
+    t2 += 0xFFFFFFFFULL & (0 - (uint64_t)(t2 < t1));
+    return t2 - (ORC_P & (0 - (uint64_t)(t2 >= ORC_P)));
 }
 /* a, b canonical */
 static inline uint64_t orc_add(uint64_t a, uint64_t b) { orc_u128 s = (orc_u128)a + b; return (uint64_t)(s >= ORC_P ? s - ORC_P : s); }

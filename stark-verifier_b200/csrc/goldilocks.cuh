@@ -48,10 +48,18 @@ SVB_HD void sqr_wide(u64 a, u64& lo, u64& hi) { mul_wide(a, a, lo, hi); }
 SVB_HD u64 reduce128(u64 lo, u64 hi) {
     u64 hh = hi >> 32, hl = hi & GL_EPS;
     u64 t0 = lo - hh;
+#if defined(__CUDA_ARCH__)
     if (lo < hh) t0 -= GL_EPS;
     u64 t1 = hl * GL_EPS;
     u64 t2 = t0 + t1;
     if (t2 < t1) t2 += GL_EPS;
+#else
+    // host: the wraps are data-dependent coin flips; as masks they cost nothing, as branches a misprediction each
+    t0 -= GL_EPS & (0 - (u64)(lo < hh));
+    u64 t1 = hl * GL_EPS;
+    u64 t2 = t0 + t1;
+    t2 += GL_EPS & (0 - (u64)(t2 < t1));
+#endif
     return t2;
 }
 

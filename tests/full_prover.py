@@ -69,7 +69,8 @@ def prove_full(svb, orc, C, params, seed, public_inputs, circuit_digest):
     oshape = orc.shape_from(params.to_shape())
     kind = params.hash_kind
     steps = len(params.reduction_arity_bits)
-    assert params.final_poly_len() == C.n >> steps and not params.hiding
+    assert params.final_poly_len() == C.n >> steps
+    salt_rng = np.random.default_rng(seed ^ 0x5A17)
     lde_bits, cap_h, nch = L.lde_bits, params.config.cap_height, C.num_challenges
     N = 1 << lde_bits
     omega = pow(7, (P - 1) >> lde_bits, P)
@@ -80,7 +81,10 @@ def prove_full(svb, orc, C, params, seed, public_inputs, circuit_digest):
 
     def commit(k, polys):
         oracle_polys[k] = polys
-        trees[k] = Tree(orc, [[poly_eval(p, x) for p in polys] for x in xs], cap_h, kind)
+        rows = [[poly_eval(p, x) for p in polys] for x in xs]
+        if params.hiding and params.oracle_blinding[k]:     # salted leaves: 4 extra limbs at the end (types/assigned.rs:57-71)
+            rows = [r + [int(v) for v in salt_rng.integers(0, P, size=4, dtype=np.uint64)] for r in rows]
+        trees[k] = Tree(orc, rows, cap_h, kind)
         capw = 4 * L.ncap
         rec[L.off_init_caps + k * capw: L.off_init_caps + (k + 1) * capw] = trees[k].cap()
 
@@ -178,12 +182,12 @@ def prove_full(svb, orc, C, params, seed, public_inputs, circuit_digest):
     return rec, out
 
 
-def toy_setup(svb, cfg):
+def toy_setup(svb, cfg, hiding=False):
     """(Circuit, FriParams) for a plonk_prover configuration, with a FRI configuration that matches the reference's shape
     in miniature: rate 1/8, cap height 1, 2 PoW bits, 5 query rounds, arity-2 reduction down to 32 coefficients
     (degree_bits <= 5: no reduction steps; 6: one; 7: two)."""
     C = pp.Circuit(**cfg)
     widths = (C.num_constants + C.num_routed_wires, C.num_wires, C.num_challenges * (1 + C.num_partial_products),
               C.num_challenges * C.qdf)
-    params = svb.api._params(C.degree_bits, 3, 1, 2, 5, oracle_num_polys=widths, num_zs=C.num_challenges)
+    params = svb.api._params(C.degree_bits, 3, 1, 2, 5, hiding=hiding, oracle_num_polys=widths, num_zs=C.num_challenges)
     return C, params

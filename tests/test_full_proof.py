@@ -14,9 +14,9 @@ from test_plonk_check import CONFIGS, c_gates
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def build(svb, orc, name, n, seed, n_pi=6, hash_kind=0, degree_bits=4):
+def build(svb, orc, name, n, seed, n_pi=6, hash_kind=0, degree_bits=4, hiding=False):
     """n complete proofs of one circuit -> dict with everything the verifier side needs."""
-    C, params = fp.toy_setup(svb, dict(CONFIGS[name], degree_bits=degree_bits))
+    C, params = fp.toy_setup(svb, dict(CONFIGS[name], degree_bits=degree_bits), hiding=hiding)
     params.hash_kind = hash_kind
     rng = np.random.default_rng(seed)
     cd = rng.integers(0, P, size=4, dtype=np.uint64)
@@ -71,6 +71,22 @@ def test_complete_proof_with_fri_reduction_steps(svb, orc):
     fri, pl, opl, mal, r2 = cpu_verdicts(svb, orc, B, blob)
     assert fri == [1, 1, 0] and pl == [1, 1, 1] and opl == pl and mal == [0, 0, 0]
     assert (r2[:2] == B["recs"]).all()
+
+
+def test_complete_proof_with_salted_leaves(svb, orc):
+    """FriParams.hiding (the semaphore circuit's zero_knowledge configuration, plonky2_semaphore/access_set.rs:68-84):
+    the wires / Z / quotient leaves carry 4 salt limbs that the Merkle proofs hash and the DEEP quotient ignores."""
+    B = build(svb, orc, "one_selector", 2, seed=41, hiding=True)
+    L = B["L"]
+    assert list(L.leaf_len) == [B["common"].num_constants + 12, 13 + 4, 4 + 4, 16 + 4]
+    fri, pl, opl, mal, r2 = cpu_verdicts(svb, orc, B, B["blob"])
+    assert fri == [1, 1] and pl == [1, 1] and opl == [1, 1] and mal == [0, 0] and (r2 == B["recs"]).all()
+    blob = B["blob"].copy()
+    q0 = 3 * 32 * L.ncap + 16 * (L.n0 + L.n1)
+    wires_salt = q0 + 8 * L.leaf_len[0] + 1 + 32 * L.init_depth + 8 * (L.leaf_len[1] - 1)     # last salt limb of the wires leaf, query 0
+    blob[1, wires_salt] ^= 1
+    fri, pl, _, _, _ = cpu_verdicts(svb, orc, B, blob)
+    assert fri == [1, 0] and pl == [1, 1]               # the salt is hashed (Merkle proof fails) but is not an evaluation
 
 
 def test_every_region_of_the_wire_bytes_is_checked(svb, orc):

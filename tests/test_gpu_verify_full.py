@@ -55,6 +55,16 @@ def test_full_verifier_with_fri_reduction_steps(svb, orc, ctx):
     assert [bit(bm, i) for i in range(5)] == want and ff[4] == svb.FAIL_PLONK and ff[2] not in (0, svb.FAIL_PLONK, svb.FAIL_MALFORMED)
 
 
+def test_full_verifier_with_salted_leaves(svb, orc, ctx):
+    B = build(svb, orc, "one_selector", 2, seed=41, hiding=True)
+    L = B["L"]
+    blob = np.concatenate([B["blob"], B["blob"][1:]])
+    q0 = 3 * 32 * L.ncap + 16 * (L.n0 + L.n1)
+    blob[2, q0 + 8 * L.leaf_len[0] + 1 + 32 * L.init_depth + 8 * (L.leaf_len[1] - 1)] ^= 1    # a salt limb of the wires leaf
+    bm, ff = ctx.verify_proofs_full(B["common"], B["circuit"], B["vk_cap"], B["cd"], blob.reshape(-1), want_fail=True)
+    assert [bit(bm, i) for i in range(3)] == [1, 1, 0] and (ff[2] & 0xFF) == 3
+
+
 def test_full_verifier_golden_blob(svb, ctx):
     import full_prover as fp
     g = np.load(os.path.join(ROOT, "tests", "golden", "full_proof_toy.npz"))

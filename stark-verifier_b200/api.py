@@ -180,7 +180,8 @@ _LIB = None
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libsvb200.so")
+    """The in-tree library; SVB200_LIB overrides it (e.g. an AddressSanitizer build of the same sources for the CPU tests)."""
+    return os.environ.get("SVB200_LIB") or os.path.join(_HERE, "libsvb200.so")
 
 
 def lib() -> ctypes.CDLL:

@@ -244,13 +244,43 @@ def wire_leg(svb, torch, ctx, params, L, n_host, distinct, seed, threads, steps)
             ctx.verify_proofs_wire(common, vk_cap, cds[0], p.value, n_proofs=n_host)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        full = full_leg(svb, torch, ctx, params, common, vk_cap, cds[0], p.value, n_host, steps)
         plonk = plonk_leg(svb, torch, ctx, params, recs, n_host, steps)
     finally:
         svb.lib().sv_host_free(p)
-    return {"plonk_check": plonk, "value": n_host * steps / dt, "unit": "proofs/s", "h2d_bytes_per_step": int(n_host * nb),
+    return {"plonk_check": plonk, "full_verifier": full, "value": n_host * steps / dt, "unit": "proofs/s", "h2d_bytes_per_step": int(n_host * nb),
             "d2h_bytes_per_step": int(exp.size * 4), "steps": steps, "proof_bytes": int(nb), "public_inputs": n_pi,
             "note": "sv_verify_proofs_wire: pinned plonky2 wire bytes -> H2D -> wire_unpack_kernel + wire_pi_hash_kernel -> "
                     "device transcript -> fri_query_kernel, per 32 MiB chunk"}
+
+
+def recursion_circuit(svb, params, common):
+    """The reference's recursion gate set (chip/plonk/gates/mod.rs:138-196) on the workload's circuit configuration."""
+    gates = [(svb.GATE_NOOP, 0), (svb.GATE_CONSTANT, 2), (svb.GATE_PUBLIC_INPUT, 0), (svb.GATE_ARITHMETIC, common.num_routed_wires // 4),
+             (svb.GATE_ARITHMETIC_EXT, 10), (svb.GATE_MUL_EXT, 13), (svb.GATE_BASE_SUM, 63), (svb.GATE_REDUCING, 43),
+             (svb.GATE_REDUCING_EXT, 32), (svb.GATE_RANDOM_ACCESS, 4, 4, 2), (svb.GATE_POSEIDON_MDS, 0), (svb.GATE_POSEIDON, 0)]
+    return svb.make_plonk_circuit(common, gates, [(0, 7), (7, 12)], [pow(7, j, 0xFFFFFFFF00000001) for j in range(common.num_routed_wires)], 123)
+
+
+def full_leg(svb, torch, ctx, params, common, vk_cap, cd, ptr, n_host, steps):
+    """The complete verifier (sv_verify_proofs_full) on the same pinned wire bytes.  The synthetic proofs carry random
+    openings, so every proof fails the plonk identity (all bits 0) -- the work done does not depend on that."""
+    try:
+        circuit = recursion_circuit(svb, params, common)
+        for _ in range(2):
+            bm = ctx.verify_proofs_full(common, circuit, vk_cap, cd, ptr, n_proofs=n_host)
+        if bm.any():
+            return {"error": "a synthetic proof satisfied the plonk identity"}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.verify_proofs_full(common, circuit, vk_cap, cd, ptr, n_proofs=n_host)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return {"value": n_host * steps / dt, "unit": "proofs/s", "steps": steps,
+                "note": "sv_verify_proofs_full: e2e.wire plus plonk challenges, the vanishing-polynomial identity (recursion gate set) and the AND"}
+    except Exception as ex:   # noqa: BLE001
+        return {"error": f"{type(ex).__name__}: {ex}"}
 
 
 def plonk_leg(svb, torch, ctx, params, recs, n_host, steps):
@@ -260,10 +290,7 @@ def plonk_leg(svb, torch, ctx, params, recs, n_host, steps):
     try:
         nch = params.num_zs
         common = svb.CommonData.for_params(params, num_public_inputs=4)
-        gates = [(svb.GATE_NOOP, 0), (svb.GATE_CONSTANT, 2), (svb.GATE_PUBLIC_INPUT, 0), (svb.GATE_ARITHMETIC, common.num_routed_wires // 4),
-                 (svb.GATE_ARITHMETIC_EXT, 10), (svb.GATE_MUL_EXT, 13), (svb.GATE_BASE_SUM, 63), (svb.GATE_REDUCING, 43),
-                 (svb.GATE_REDUCING_EXT, 32), (svb.GATE_RANDOM_ACCESS, 4, 4, 2), (svb.GATE_POSEIDON_MDS, 0), (svb.GATE_POSEIDON, 0)]
-        circuit = svb.make_plonk_circuit(common, gates, [(0, 7), (7, 12)], [pow(7, j, 0xFFFFFFFF00000001) for j in range(common.num_routed_wires)], 123)
+        circuit = recursion_circuit(svb, params, common)
         reps = (n_host + recs.shape[0] - 1) // recs.shape[0]
         d_recs = torch.from_numpy(recs.view(np.int64)).cuda().repeat(reps, 1)[:n_host].contiguous()
         rng = np.random.default_rng(5)

@@ -73,17 +73,31 @@ void orc_poseidon(uint64_t st[12]) {
     {   /* mds_partial_layer_init :504-537 */
         uint64_t res[12] = {0};
         res[0] = st[0];
-        for (int r = 1; r < 12; r++)
-            for (int c = 1; c < 12; c++)
-                res[c] = orc_mul_add(ORC_FAST_PARTIAL_ROUND_INITIAL_MATRIX[(r - 1) * 11 + (c - 1)], st[r], res[c]);
+        for (int c = 1; c < 12; c++) {                  /* column c: sum_r M[r-1][c-1] * st[r], reduced once */
+            orc_u128 acc = 0;
+            uint64_t wraps = 0;
+            for (int r = 1; r < 12; r++) {
+                orc_u128 t = (orc_u128)ORC_FAST_PARTIAL_ROUND_INITIAL_MATRIX[(r - 1) * 11 + (c - 1)] * st[r], s2 = acc + t;
+                wraps += s2 < t;
+                acc = s2;
+            }
+            res[c] = orc_sub(orc_red128(acc), wraps << 32);
+        }
         memcpy(st, res, sizeof res);
     }
     for (int r = 0; r < 22; r++) {                                                   /* :654-672 */
         st[0] = sbox7(st[0]);
         if (r != 21) st[0] = orc_add(st[0], ORC_FAST_PARTIAL_ROUND_CONSTANTS[r]);
-        /* mds_partial_layer_fast :539-589 */
-        uint64_t d = orc_mul(st[0], ORC_MDS_MATRIX_CIRC[0] + ORC_MDS_MATRIX_DIAG[0]);
-        for (int i = 1; i < 12; i++) d = orc_mul_add(ORC_FAST_PARTIAL_ROUND_W_HATS[r * 11 + i - 1], st[i], d);
+        /* mds_partial_layer_fast :539-589.  The 12-term dot product is summed exactly (128-bit accumulator plus a
+         * count of its wrap-arounds) and reduced once: 2^128 = (2^64)^2 = (2^32 - 1)^2 = -2^32 (mod p). */
+        orc_u128 acc = (orc_u128)st[0] * (ORC_MDS_MATRIX_CIRC[0] + ORC_MDS_MATRIX_DIAG[0]);
+        uint64_t wraps = 0;
+        for (int i = 1; i < 12; i++) {
+            orc_u128 t = (orc_u128)ORC_FAST_PARTIAL_ROUND_W_HATS[r * 11 + i - 1] * st[i], s2 = acc + t;
+            wraps += s2 < t;
+            acc = s2;
+        }
+        uint64_t d = orc_sub(orc_red128(acc), wraps << 32);
         uint64_t res[12];
         res[0] = d;
         for (int i = 1; i < 12; i++) res[i] = orc_mul_add(ORC_FAST_PARTIAL_ROUND_VS[r * 11 + i - 1], st[0], st[i]);

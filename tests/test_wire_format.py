@@ -254,3 +254,29 @@ def test_random_bytes_never_disagree_with_the_oracle_reader(svb, orc):
     for i in np.flatnonzero(mal == 0):
         again = svb.wire_pack(common, r2[i:i + 1], pi2[i:i + 1])[0]
         assert (again == cases[i]).all()
+
+
+def test_host_entry_points_report_bad_arguments(svb):
+    """Error convention of the new host entry points: < 0 for bad arguments, never a crash, never a silent success."""
+    import ctypes
+    L = svb.lib()
+    params = tiny_params(svb)
+    common = svb.CommonData.for_params(params, num_public_inputs=2)
+    s, c = params.to_shape(), common.to_c()
+    nb = svb.wire_proof_bytes(common)
+    cap = np.zeros(4 << s.cap_height, dtype=np.uint64)
+    blob = np.zeros(3 * nb, dtype=np.uint8)
+    recs = np.zeros((3, svb.api.make_layout(params).record_words), dtype=np.uint64)
+    p = lambda a: a.ctypes.data
+    assert L.sv_wire_unpack_batch(ctypes.byref(s), ctypes.byref(c), p(cap), p(blob), nb - 1, 3, p(recs), None, None, None, 1) == -4   # stride < proof
+    assert L.sv_wire_unpack_batch(ctypes.byref(s), ctypes.byref(c), None, p(blob), nb, 3, p(recs), None, None, None, 1) == -1          # no verifier key
+    assert L.sv_wire_unpack_batch(None, ctypes.byref(c), p(cap), p(blob), nb, 3, p(recs), None, None, None, 1) == -1
+    assert L.sv_wire_unpack_batch(ctypes.byref(s), ctypes.byref(c), p(cap), p(blob), nb, 0, p(recs), None, None, None, 1) == 0            # empty batch
+    assert L.sv_wire_pack(ctypes.byref(s), ctypes.byref(c), p(recs), None, p(blob)) == -1                                               # public inputs missing
+    assert L.sv_wire_proof_bytes(None, ctypes.byref(c)) == 0
+    assert L.sv_public_inputs_hash(None, 3, p(cap)) == -1
+    out = svb.FriShape()
+    assert L.sv_fri_shape_from_common(ctypes.byref(c), 4, 3, 1, 5, 2, 9, 0, 0, ctypes.byref(out)) == -2                                 # more steps than degree bits
+    assert L.sv_ntt_host(0, 1, p(recs), 0, 1) == -2 and L.sv_ntt_host(3, 1, None, 0, 1) == -1
+    assert L.sv_plonk_gate_from_id(None, None) == -1
+    assert L.sv_plonk_check_host(ctypes.byref(s), None, 1, p(recs), p(cap), p(cap), p(cap), 1) == -1

@@ -59,5 +59,6 @@ from .api import (  # noqa: F401
     plonk_gate_from_id,
     plonk_check_host,
     ntt_host,
+    verify_batch,
     lde_host,
 )

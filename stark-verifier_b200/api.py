@@ -720,6 +720,23 @@ class Context:
                  "sv_allgather_bitmap")
 
 
+def verify_batch(ctx: "Context", proofs: Sequence[bytes], constants_sigmas_cap, circuit_digest, common: CommonData,
+                 gate_ids: Sequence[str], selector_groups, k_is, num_gate_constraints: int) -> List[bool]:
+    """The drop-in for a loop over the reference's ``verify_inside_snark_mock(degree, (proof_with_pis, vd, cd))``
+    (verifier_api.rs:34-56): `proofs` are ``ProofWithPublicInputs::to_bytes()`` strings of ONE circuit, the verifier key is
+    ``VerifierOnlyCircuitData`` (constants_sigmas_cap, circuit_digest), the circuit description comes from
+    ``CommonCircuitData`` (gate ids as the reference matches them, gates/mod.rs:138-196; selector groups; k_is).  One bool
+    per proof: plonk identity AND FRI proof, verified natively on the GPU -- invalidity is data, where the reference panics."""
+    nb = wire_proof_bytes(common)
+    for i, p in enumerate(proofs):
+        if len(p) != nb:
+            raise SvError(f"proof {i} has {len(p)} bytes, the circuit's proofs have {nb}")
+    circuit = make_plonk_circuit(common, [plonk_gate_from_id(g) for g in gate_ids], selector_groups, k_is, num_gate_constraints)
+    blob = np.frombuffer(b"".join(proofs), dtype=np.uint8) if proofs else np.zeros(0, dtype=np.uint8)
+    bm = ctx.verify_proofs_full(common, circuit, constants_sigmas_cap, circuit_digest, blob, n_proofs=len(proofs))
+    return [bool((int(bm[i >> 5]) >> (i & 31)) & 1) for i in range(len(proofs))]
+
+
 class FriVerifierChip:
     """Mirror of the reference's seam: ``FriVerifierChip::construct(config, offset, fri_params)`` then
     ``verify_fri_proof(initial_merkle_caps, fri_challenges, fri_openings, fri_proof, fri_instance_info)``

@@ -65,6 +65,23 @@ def test_full_verifier_with_salted_leaves(svb, orc, ctx):
     assert [bit(bm, i) for i in range(3)] == [1, 1, 0] and (ff[2] & 0xFF) == 3
 
 
+def test_verify_batch_drop_in(svb, orc, ctx):
+    """svb.verify_batch: byte strings + the reference's gate ids in, one bool per proof out."""
+    B = build(svb, orc, "recursion_gate_set", 2, seed=5)
+    C = B["C"]
+    gate_ids = ["NoopGate", "ConstantGate { num_consts: 2 }", "PublicInputGate", "ArithmeticGate { num_ops: 20 }",
+                "ArithmeticExtensionGate { num_ops: 10 }", "MulExtensionGate { num_ops: 13 }", "BaseSumGate { num_limbs: 63 } + Base: 2",
+                "ReducingGate { num_coeffs: 43 }", "ReducingExtensionGate { num_coeffs: 32 }",
+                "RandomAccessGate { bits: 4, num_copies: 4, num_extra_constants: 2, _phantom: PhantomData<plonky2_field::goldilocks_field::GoldilocksField> }<D=2>",
+                "PoseidonMdsGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>",
+                "PoseidonGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>"]
+    proofs = [B["blob"][0].tobytes(), B["blob"][1].tobytes(), bytes(bytearray(B["blob"][0].tobytes()[:-1]) + bytearray([B["blob"][0][-1] ^ 1]))]
+    ok = svb.verify_batch(ctx, proofs, B["vk_cap"], B["cd"], B["common"], gate_ids, C.groups, C.k_is, C.num_gate_constraints)
+    assert ok == [True, True, False]
+    with pytest.raises(svb.SvError):
+        svb.verify_batch(ctx, [proofs[0][:-8]], B["vk_cap"], B["cd"], B["common"], gate_ids, C.groups, C.k_is, C.num_gate_constraints)
+
+
 def test_full_verifier_golden_blob(svb, ctx):
     import full_prover as fp
     g = np.load(os.path.join(ROOT, "tests", "golden", "full_proof_toy.npz"))

@@ -499,7 +499,7 @@ def main():
     # the same leg from SERIALISED proofs (plonky2 wire bytes, pinned): H2D of the bytes, device unpack, public-input
     # hashes, device transcript, query phase (sv_verify_proofs_wire).  1 GPU only, in a child process with a time limit:
     # whatever happens there is reported under e2e.wire and cannot take the main measurement down with it.
-    if e2e is not None and world == 1 and not args.no_wire:
+    if e2e is not None and world == 1 and not args.no_wire and args.workload != "B":   # (shape-B proofs take minutes to synthesise)
         import subprocess
         try:
             cmd = [sys.executable, os.path.abspath(__file__), "--wire-leg", "--workload", args.workload, "--proofs", str(n_host),

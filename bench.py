@@ -185,6 +185,12 @@ def run_reference(args):
     dt = time.perf_counter() - t
     assert all((int(bm[i >> 5]) >> (i & 31)) & 1 for i in range(sample))
     v = sample * args.steps / dt
+    # one thread on a small sample: the per-core figure (SURVEY 8d asks for both)
+    n1 = max(1, min(sample, {"A": 16, "B": 1, "outer": 1}[wl]))
+    t = time.perf_counter()
+    orc.fri_verify_batch(oshape, recs[:n1], nthreads=1)
+    v1 = n1 / (time.perf_counter() - t)
+    perms_per_proof = params.config.num_query_rounds * L.perms_per_query
     cpu = open("/proc/cpuinfo").read().split("model name")[1].split("\n")[0].strip(": \t") if os.path.exists("/proc/cpuinfo") else "?"
     print(json.dumps({
         "impl": "reference", "metric": "plonky2_proofs_verified_per_sec", "value": v, "unit": "proofs/s",
@@ -198,6 +204,7 @@ def run_reference(args):
                    "pow_bits": params.config.proof_of_work_bits,
                    "sample": f"each step verifies a bounded sample of {sample} proofs of that workload on the host CPU"},
         "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": threads, "kind": "port",
+                         "perms_per_sec": v * perms_per_proof, "single_thread_value": v1, "single_thread_perms_per_sec": v1 * perms_per_proof,
                          "sample": f"{sample} proofs x {args.steps} steps, oracle/oracle.c on {threads} threads ({cpu}); "
                                    "CPU restatement of reference semantics, not the Rust binary"},
         "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -570,7 +577,11 @@ def main():
             v0, _, _ = cpu_baseline(svb, params, base, probe, threads)
             sample = max(probe, int(v0 * 12.0) // threads * threads)
         v, dt, _ = cpu_baseline(svb, params, base, sample, threads)
+        v1, _, _ = cpu_baseline(svb, params, base, max(1, min(sample, {"A": 16, "B": 1, "outer": 1}[args.workload])), 1)
+        perms_per_proof = params.config.num_query_rounds * L.perms_per_query
         out["cpu_baseline"] = {"value": v, "unit": "proofs/s", "cores": threads, "kind": "port",
+                               "perms_per_sec": v * perms_per_proof, "single_thread_value": v1,
+                               "single_thread_perms_per_sec": v1 * perms_per_proof,
                                "sample": f"{sample} proofs of the same workload in {dt:.1f} s on {threads} threads; oracle/oracle.c, "
                                          "CPU restatement of reference semantics (not the Rust binary)"}
     print(json.dumps(out))

@@ -266,7 +266,7 @@ int sv_wire_unpack_batch(const sv_fri_shape* shape, const sv_plonk_common* commo
                          const uint8_t* blob, size_t stride_bytes, size_t n_proofs, uint64_t* records_out,
                          uint64_t* pi_hashes_out, uint64_t* public_inputs_out, uint8_t* malformed_out, int nthreads);
 
-/* GPU: the same unpacking as one gather kernel (HBM-bound byte shuffling, one thread per record word) plus the
+/* GPU: the same unpacking as one gather kernel (HBM-bound byte shuffling, one block per header / query round of a proof) plus the
  * public-input hashes, one thread per proof.  mem says where blob / records_out / pi_hashes_out / malformed_out
  * (n x u32) live; constants_sigmas_cap is always a host pointer.  SV_MEM_DEVICE: blob must be 8-byte aligned and
  * readable up to the next multiple of 8 bytes past its end. */

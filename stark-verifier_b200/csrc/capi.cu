@@ -685,7 +685,7 @@ static int wire_tables(sv_ctx* c, const sv_fri_shape& shape, const sv_plonk_comm
 static int enqueue_unpack(sv_ctx* c, const WireDev& W, const u64* d_blob8, size_t first_off, size_t stride, size_t n, u64* d_records,
                           u64* d_pi, u32* d_mal, cudaStream_t s) {
     CK(c, cudaMemsetAsync(d_mal, 0, n * 4, s));
-    dim3 grid((unsigned)n, (W.d.record_words + SVB_WIRE_BLOCK - 1) / SVB_WIRE_BLOCK);
+    dim3 grid((unsigned)n, 1 + W.d.num_queries);   // per proof: one block for the header, one per query round
     wire_unpack_kernel<<<grid, SVB_WIRE_BLOCK, 0, s>>>(d_blob8, first_off, stride, W.d, W.hdr_src, W.q_src, W.chk, W.vk, d_records, d_mal);
     c->launches++;
     if (d_pi) {

@@ -54,29 +54,34 @@ SVB_HD u64 wire_gather64(const u64* base, size_t off) {
 }
 SVB_HD u32 wire_byte(const u64* base, size_t off) { return (u32)(base[off >> 3] >> ((off & 7) * 8)) & 0xFFu; }
 
-// Record word `w` of the proof whose bytes start `proof_off` bytes after `base`.  The first n_chk words of every
-// query block also compare one Merkle-proof length byte each with the depth the shape implies and set *malformed
-// when it differs (plonky2 would read a different number of siblings and fail further on).
-SVB_HD u64 wire_record_word(const WireDims& d, const u32* hdr_src, const u32* q_src, const u32* chk,
-                            const u64* vk_cap, const u64* base, size_t proof_off, u32 w, bool* malformed) {
-    u32 code;
-    size_t from = proof_off;
-    if (w < d.header_words) {
-        code = hdr_src[w];
-    } else {
-        u32 r = w - d.header_words;
-        u32 q = r / d.query_words;
-        r -= q * d.query_words;
-        code = q_src[r];
-        from += d.query_base + (size_t)q * d.query_bytes;
-        if (r < d.n_chk) {
-            u32 c = chk[r];
-            if (wire_byte(base, from + (c >> 8)) != (c & 0xFFu)) *malformed = true;
-        }
-    }
+// One source code: offset of a byte run, WIRE_ZERO (padding / challenge field -> 0) or a word of the verifier key's cap.
+SVB_HD u64 wire_fetch(u32 code, const u64* vk_cap, const u64* base, size_t from) {
     if (code == WIRE_ZERO) return 0;
     if (code & WIRE_VK_FLAG) return vk_cap[code & ~WIRE_VK_FLAG];
     return wire_gather64(base, from + code);
+}
+// Header word w (< header_words) of the proof whose bytes start `proof_off` bytes after `base`.
+SVB_HD u64 wire_header_word(const u32* hdr_src, const u64* vk_cap, const u64* base, size_t proof_off, u32 w) {
+    return wire_fetch(hdr_src[w], vk_cap, base, proof_off);
+}
+// Word r (< query_words) of query round q.  The first n_chk words of every query block also compare one Merkle-proof
+// length byte each with the depth the shape implies and set *malformed when it differs (plonky2 would read a different
+// number of siblings and fail further on).
+SVB_HD u64 wire_query_word(const WireDims& d, const u32* q_src, const u32* chk, const u64* vk_cap, const u64* base, size_t proof_off,
+                           u32 q, u32 r, bool* malformed) {
+    const size_t from = proof_off + d.query_base + (size_t)q * d.query_bytes;
+    if (r < d.n_chk) {
+        const u32 c = chk[r];
+        if (wire_byte(base, from + (c >> 8)) != (c & 0xFFu)) *malformed = true;
+    }
+    return wire_fetch(q_src[r], vk_cap, base, from);
+}
+// Record word `w` of a proof: the two above behind one index (the host unpacker's loop).
+SVB_HD u64 wire_record_word(const WireDims& d, const u32* hdr_src, const u32* q_src, const u32* chk,
+                            const u64* vk_cap, const u64* base, size_t proof_off, u32 w, bool* malformed) {
+    if (w < d.header_words) return wire_header_word(hdr_src, vk_cap, base, proof_off, w);
+    const u32 r = w - d.header_words, q = r / d.query_words;
+    return wire_query_word(d, q_src, chk, vk_cap, base, proof_off, q, r - q * d.query_words, malformed);
 }
 
 // Host: build the tables.  Returns 0, or < 0 when shape and common disagree.

@@ -1,7 +1,7 @@
 // Device side of the wire format: serialised plonky2 proofs -> flat records, on the GPU.
 //
 // The wire bytes cross PCIe as they are; unpacking is a fixed permutation of 8-byte words (wire.hpp) and therefore
-// pure HBM-bound byte shuffling: one thread per record word reads its (unaligned) 8 source bytes as two aligned
+// pure HBM-bound byte shuffling: a thread reads the (unaligned) 8 source bytes of a record word as two aligned
 // words and a funnel shift, and writes one coalesced word.  Consecutive threads read consecutive source words, so a
 // warp request covers 256-264 contiguous bytes; the offset tables (a few KB) stay in L1.  Algorithmic bytes per
 // proof: wire bytes read + record bytes written (shape A: 156 812 + 157 728).
@@ -13,19 +13,25 @@ namespace svb {
 
 #define SVB_WIRE_BLOCK 256
 
-// grid = (n_proofs, ceil(record_words / SVB_WIRE_BLOCK)).  blob8: 8-byte aligned base; proof p starts at byte
-// first_off + p * stride.  malformed[p] is set to 1 when a Merkle-proof length byte is wrong (zeroed by the caller).
+// grid = (n_proofs, 1 + num_queries): block (p, 0) writes the header of proof p, block (p, 1 + q) its query round q; the
+// threads stride over the words of that segment (no division anywhere).  blob8: 8-byte aligned base; proof p starts at
+// byte first_off + p * stride.  malformed[p] is set to 1 when a Merkle-proof length byte is wrong (zeroed by the caller).
 __global__ void __launch_bounds__(SVB_WIRE_BLOCK) wire_unpack_kernel(const u64* __restrict__ blob8, size_t first_off, size_t stride,
                                                                      WireDims d, const u32* __restrict__ hdr_src,
                                                                      const u32* __restrict__ q_src, const u32* __restrict__ chk,
                                                                      const u64* __restrict__ vk_cap, u64* __restrict__ records,
                                                                      u32* __restrict__ malformed) {
-    u32 w = blockIdx.y * SVB_WIRE_BLOCK + threadIdx.x;
-    if (w >= d.record_words) return;
-    size_t p = blockIdx.x;
+    const size_t p = blockIdx.x, proof_off = first_off + p * stride;
+    u64* rec = records + p * (size_t)d.record_words;
+    if (blockIdx.y == 0) {
+        for (u32 w = threadIdx.x; w < d.header_words; w += SVB_WIRE_BLOCK) rec[w] = wire_header_word(hdr_src, vk_cap, blob8, proof_off, w);
+        return;
+    }
+    const u32 q = blockIdx.y - 1;
+    u64* out = rec + d.header_words + (size_t)q * d.query_words;
     bool bad = false;
-    u64 v = wire_record_word(d, hdr_src, q_src, chk, vk_cap, blob8, first_off + p * stride, w, &bad);
-    records[p * (size_t)d.record_words + w] = v;
+    for (u32 r = threadIdx.x; r < d.query_words; r += SVB_WIRE_BLOCK)
+        out[r] = wire_query_word(d, q_src, chk, vk_cap, blob8, proof_off, q, r, &bad);
     if (bad) malformed[p] = 1;
 }
 

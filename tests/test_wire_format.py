@@ -280,3 +280,42 @@ def test_host_entry_points_report_bad_arguments(svb):
     assert L.sv_ntt_host(0, 1, p(recs), 0, 1) == -2 and L.sv_ntt_host(3, 1, None, 0, 1) == -1
     assert L.sv_plonk_gate_from_id(None, None) == -1
     assert L.sv_plonk_check_host(ctypes.byref(s), None, 1, p(recs), p(cap), p(cap), p(cap), 1) == -1
+
+
+def test_random_shapes_round_trip_against_the_oracle(svb, orc):
+    """40 seeded random circuit shapes (widths, depths, cap heights, salting, public inputs, both step-count regimes) with
+    random record contents: product pack == oracle write, product unpack == oracle read, pack(unpack(bytes)) == bytes."""
+    rng = np.random.default_rng(777)
+    for case in range(40):
+        degree_bits = int(rng.integers(3, 10))
+        rate_bits = int(rng.integers(1, 4))
+        cap = int(rng.integers(0, min(5, degree_bits + rate_bits - max(0, degree_bits - 5)) + 1))
+        nch = int(rng.integers(1, 4))
+        nc, nr = int(rng.integers(1, 8)), int(rng.integers(1, 30))
+        nw = nr + int(rng.integers(0, 10))
+        npp, qdf = int(rng.integers(0, 5)), int(rng.integers(1, 9))
+        widths = (nc + nr, nw, nch * (1 + npp), nch * qdf)
+        params = svb.api._params(degree_bits, rate_bits, cap, int(rng.integers(0, 8)), int(rng.integers(1, 9)),
+                                 hiding=bool(rng.integers(0, 2)), oracle_num_polys=widths, num_zs=nch)
+        common = svb.CommonData(params, nc, nr, nw, nch, npp, qdf, int(rng.integers(0, 12)))
+        L = svb.api.make_layout(params)
+        oshape, ocommon = orc.shape_from(params.to_shape()), orc.common_from(common.to_c())
+        nb = svb.wire_proof_bytes(common)
+        assert nb == orc.wire_proof_bytes(oshape, ocommon)
+        n = 3
+        pis = rng.integers(0, P, size=(n, common.num_public_inputs), dtype=np.uint64)
+        recs = rng.integers(0, P, size=(n, L.record_words), dtype=np.uint64)
+        blob = svb.wire_pack(common, recs, pis)
+        cap_words = rng.integers(0, P, size=4 * L.ncap, dtype=np.uint64)
+        r2, pih, pi2, mal = svb.wire_unpack_batch(common, cap_words, blob.reshape(-1), nthreads=2)
+        assert not mal.any() and (pi2 == pis).all(), case
+        assert (svb.wire_pack(common, r2, pi2) == blob).all(), case
+        for i in range(n):
+            assert (blob[i] == orc.wire_write_proof(oshape, ocommon, recs[i], pis[i])).all(), case
+            rc, orec, opis, opih = orc.wire_read_proof(oshape, ocommon, cap_words, blob[i])
+            assert rc == 0 and (orec == r2[i]).all() and (opih == pih[i]).all(), case
+        # what unpack gives back: the proof's own fields, the verifier key's cap, zeros everywhere else
+        again = r2.copy()
+        again[:, L.off_init_caps:L.off_init_caps + 4 * L.ncap] = recs[:, L.off_init_caps:L.off_init_caps + 4 * L.ncap]
+        diff = np.flatnonzero((again != recs).any(axis=0))
+        assert all(r2[0, w] == 0 for w in diff), case

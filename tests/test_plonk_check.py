@@ -205,3 +205,19 @@ def test_gate_ids_of_the_reference(svb):
         "PoseidonMdsGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>",
         "PoseidonGate(PhantomData<plonky2_field::goldilocks_field::GoldilocksField>)<WIDTH=12>")]
     assert [tuple(g) for g in from_ids] == [tuple((list(g) + [0, 0])[:4]) for g in c_gates(C)]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_more_witnesses_of_the_recursion_gate_set(svb, orc, seed):
+    """Other witnesses (copy constraints, Poseidon swap bit, random-access indices, limb patterns differ per seed)."""
+    C, params, circuit, L = setup(svb, CONFIGS["recursion_gate_set"])
+    pih = np.random.default_rng(seed).integers(0, P, size=(1, 4), dtype=np.uint64)
+    recs, chal = to_records(L, [pp.prove(C, 1000 + seed, [int(x) for x in pih[0]])])
+    assert bit(svb.plonk_check_host(params, circuit, recs, pih, chal), 0) == 1
+    assert oracle_bits(orc, orc.plonk_circuit_from(circuit), L, recs, pih, chal) == [1]
+    # a gate the proof was not made for: swap two gate kinds of equal selector group -> the identity must break
+    gates = c_gates(C)
+    gates[5], gates[6] = gates[6], gates[5]
+    common = svb.CommonData.for_params(params, num_public_inputs=0, num_constants=C.num_constants)
+    other = svb.make_plonk_circuit(common, gates, C.groups, C.k_is, C.num_gate_constraints)
+    assert bit(svb.plonk_check_host(params, other, recs, pih, chal), 0) == 0

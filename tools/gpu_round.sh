@@ -4,6 +4,11 @@ mkdir -p gpurun_out
 TAG=${1:-run}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_gpu.log
+# the files whose kernels were written without a GPU, one by one and without -x: a failure in one must not hide the others
+for f in plonk transforms wire verify_full; do
+  timeout 600 python -m pytest tests/test_gpu_${f}.py -m gpu -q > gpurun_out/${TAG}_pytest_gpu_${f}.log 2>&1; echo "rc=$?" >> gpurun_out/${TAG}_pytest_gpu_${f}.log
+  tail -2 gpurun_out/${TAG}_pytest_gpu_${f}.log
+done
 timeout 300 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${TAG}_smoke.log
 timeout 600 python bench.py > gpurun_out/${TAG}_bench_A.json 2> gpurun_out/${TAG}_bench_A.err
 timeout 600 python bench.py --workload merkle --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_merkle.json 2> gpurun_out/${TAG}_bench_merkle.err

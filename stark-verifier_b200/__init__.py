@@ -60,5 +60,6 @@ from .api import (  # noqa: F401
     plonk_check_host,
     ntt_host,
     verify_batch,
+    PlonkVerifierChip,
     lde_host,
 )

@@ -720,6 +720,36 @@ class Context:
                  "sv_allgather_bitmap")
 
 
+class PlonkVerifierChip:
+    """Mirror of the reference's ``PlonkVerifierChip`` (chip/plonk/plonk_verifier_chip.rs): the same three steps, same
+    names, on batches and natively.  ``verify_proof_with_challenges`` returns one bool per proof where the reference
+    fails the circuit."""
+
+    def __init__(self, ctx: "Context", common_data: CommonData, circuit: PlonkCircuit):
+        self.ctx, self.common_data, self.circuit = ctx, common_data, circuit
+        self.fri_params = common_data.fri_params
+        self.layout = make_layout(self.fri_params)
+
+    def get_public_inputs_hash(self, public_inputs) -> np.ndarray:
+        """plonk_verifier_chip.rs:41-53 (PublicInputsHasherChip: Poseidon-Goldilocks sponge)."""
+        return public_inputs_hash(public_inputs)
+
+    def get_challenges(self, public_inputs_hash_, circuit_digest, record: np.ndarray) -> np.ndarray:
+        """plonk_verifier_chip.rs:55-154: fills the FRI challenges (zeta, alpha, betas, PoW response, query indices) into
+        the record header and returns the plonk challenges [betas | gammas | alphas].  Host side."""
+        nch = self.common_data.num_challenges
+        fri_challenges(self.fri_params, record, circuit_digest, public_inputs_hash_, nch)
+        return plonk_challenges(self.fri_params, record, circuit_digest, public_inputs_hash_, nch)
+
+    def verify_proof_with_challenges(self, records: np.ndarray, public_inputs_hashes, plonk_challenges_) -> List[bool]:
+        """plonk_verifier_chip.rs:156-240: vanishing-polynomial identity, then FriVerifierChip::verify_fri_proof."""
+        records = np.ascontiguousarray(records, dtype=np.uint64).reshape(-1, self.layout.record_words)
+        n = records.shape[0]
+        pl = self.ctx.plonk_check_batch(self.fri_params, self.circuit, records, public_inputs_hashes, plonk_challenges_)
+        fri = self.ctx.fri_verify_batch(self.fri_params, records, n)
+        return [bool((int(pl[i >> 5]) & int(fri[i >> 5])) >> (i & 31) & 1) for i in range(n)]
+
+
 def verify_batch(ctx: "Context", proofs: Sequence[bytes], constants_sigmas_cap, circuit_digest, common: CommonData,
                  gate_ids: Sequence[str], selector_groups, k_is, num_gate_constraints: int) -> List[bool]:
     """The drop-in for a loop over the reference's ``verify_inside_snark_mock(degree, (proof_with_pis, vd, cd))``

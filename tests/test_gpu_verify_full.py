@@ -65,6 +65,21 @@ def test_full_verifier_with_salted_leaves(svb, orc, ctx):
     assert [bit(bm, i) for i in range(3)] == [1, 1, 0] and (ff[2] & 0xFF) == 3
 
 
+def test_plonk_verifier_chip_mirror(svb, orc, ctx):
+    """The reference's three steps by name -- get_public_inputs_hash, get_challenges, verify_proof_with_challenges
+    (chip/plonk/plonk_verifier_chip.rs) -- on records of complete proofs."""
+    B = build(svb, orc, "all_gates", 3, seed=8)
+    L = B["L"]
+    chip = svb.PlonkVerifierChip(ctx, B["common"], B["circuit"])
+    recs = B["recs"].copy()
+    recs[:, L.off_alpha:L.header_words] = 0                       # the verifier derives every challenge itself
+    recs[2, L.off_open0 + 9] ^= np.uint64(1)
+    pihs = np.stack([chip.get_public_inputs_hash(B["pis"][i]) for i in range(3)])
+    chals = np.stack([chip.get_challenges(pihs[i], B["cd"], recs[i]) for i in range(3)])
+    assert (recs[:2] == B["recs"][:2]).all()
+    assert chip.verify_proof_with_challenges(recs, pihs, chals) == [True, True, False]
+
+
 def test_verify_batch_drop_in(svb, orc, ctx):
     """svb.verify_batch: byte strings + the reference's gate ids in, one bool per proof out."""
     B = build(svb, orc, "recursion_gate_set", 2, seed=5)

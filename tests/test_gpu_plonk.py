@@ -5,14 +5,14 @@ import pytest
 
 import plonk_prover as pp
 from common import P, bit
-from test_plonk_check import CONFIGS, oracle_bits, setup, to_records
+from test_plonk_check import CONFIGS, oracle_bits, plonk_setup, to_records
 
 pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", ["one_selector", "two_selectors", "three_chunks", "all_gates", "recursion_gate_set"])
 def test_plonk_kernel_matches_host_and_oracle(svb, orc, ctx, name):
-    C, params, circuit, L = setup(svb, CONFIGS[name])
+    C, params, circuit, L = plonk_setup(svb, CONFIGS[name])
     ocirc = orc.plonk_circuit_from(circuit)
     rng = np.random.default_rng(3)
     n = 77                                                  # ragged last bitmap word, partial last block
@@ -37,7 +37,7 @@ def test_plonk_kernel_matches_host_and_oracle(svb, orc, ctx, name):
 
 def test_plonk_kernel_device_memory(svb, ctx):
     import torch
-    C, params, circuit, L = setup(svb, CONFIGS["one_selector"])
+    C, params, circuit, L = plonk_setup(svb, CONFIGS["one_selector"])
     rng = np.random.default_rng(4)
     n = 64
     pih = rng.integers(0, P, size=(n, 4), dtype=np.uint64)

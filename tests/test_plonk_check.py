@@ -32,7 +32,7 @@ def c_gates(C):
     return [(k,) + tuple(p) if isinstance(p, tuple) else (k, p) for k, p in C.gates]
 
 
-def setup(svb, cfg):
+def plonk_setup(svb, cfg):
     C = pp.Circuit(**cfg)
     widths = (C.num_constants + C.num_routed_wires, C.num_wires, C.num_challenges * (1 + C.num_partial_products),
               C.num_challenges * C.qdf)
@@ -63,7 +63,7 @@ def oracle_bits(orc, ocirc, L, recs, pih, chal):
 
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_prover_accepted_corruptions_rejected(svb, orc, name):
-    C, params, circuit, L = setup(svb, CONFIGS[name])
+    C, params, circuit, L = plonk_setup(svb, CONFIGS[name])
     ocirc = orc.plonk_circuit_from(circuit)
     rng = np.random.default_rng(7)
     n = 3 if C.num_wires < 100 else 1
@@ -95,7 +95,7 @@ def test_prover_accepted_corruptions_rejected(svb, orc, name):
 
 
 def test_wrong_public_inputs_hash_is_rejected(svb, orc):
-    C, params, circuit, L = setup(svb, CONFIGS["one_selector"])
+    C, params, circuit, L = plonk_setup(svb, CONFIGS["one_selector"])
     pih = np.array([[5, 6, 7, 8]], dtype=np.uint64)
     recs, chal = to_records(L, [pp.prove(C, 1, [5, 6, 7, 8])])
     assert bit(svb.plonk_check_host(params, circuit, recs, pih, chal), 0) == 1
@@ -106,7 +106,7 @@ def test_wrong_public_inputs_hash_is_rejected(svb, orc):
 def test_product_and_oracle_agree_on_arbitrary_inputs(svb, orc):
     """Differential test in the style of the reference's own gate tests (gates/gate_test.rs:154-176): random inputs,
     the two restatements must give the same verdict -- including the corner cases below."""
-    C, params, circuit, L = setup(svb, CONFIGS["two_selectors"])
+    C, params, circuit, L = plonk_setup(svb, CONFIGS["two_selectors"])
     ocirc = orc.plonk_circuit_from(circuit)
     rng = np.random.default_rng(11)
     n = 40
@@ -129,7 +129,7 @@ def test_product_and_oracle_agree_on_arbitrary_inputs(svb, orc):
 
 
 def test_unknown_gates_and_inconsistent_circuits_are_refused(svb):
-    C, params, circuit, L = setup(svb, CONFIGS["one_selector"])
+    C, params, circuit, L = plonk_setup(svb, CONFIGS["one_selector"])
     common = svb.CommonData.for_params(params, num_public_inputs=0, num_constants=C.num_constants)
     with pytest.raises(svb.SvError):       # a gate kind this library does not evaluate (e.g. PoseidonGate): never a silent accept
         svb.make_plonk_circuit(common, C.gates + [(17, 0)], [(0, 5)], C.k_is, C.num_gate_constraints)
@@ -196,7 +196,7 @@ def test_gate_ids_of_the_reference(svb):
         with pytest.raises(svb.SvError):
             svb.plonk_gate_from_id(bad)
     # the ids above, in the reference's gate set, make a circuit the library accepts on the standard recursion configuration
-    C, params, circuit, L = setup(svb, CONFIGS["recursion_gate_set"])
+    C, params, circuit, L = plonk_setup(svb, CONFIGS["recursion_gate_set"])
     from_ids = [svb.plonk_gate_from_id(g) for g in (
         "NoopGate", "ConstantGate { num_consts: 2 }", "PublicInputGate", "ArithmeticGate { num_ops: 20 }",
         "ArithmeticExtensionGate { num_ops: 10 }", "MulExtensionGate { num_ops: 13 }", "BaseSumGate { num_limbs: 63 } + Base: 2",
@@ -210,7 +210,7 @@ def test_gate_ids_of_the_reference(svb):
 @pytest.mark.parametrize("seed", [1, 2, 3, 4])
 def test_more_witnesses_of_the_recursion_gate_set(svb, orc, seed):
     """Other witnesses (copy constraints, Poseidon swap bit, random-access indices, limb patterns differ per seed)."""
-    C, params, circuit, L = setup(svb, CONFIGS["recursion_gate_set"])
+    C, params, circuit, L = plonk_setup(svb, CONFIGS["recursion_gate_set"])
     pih = np.random.default_rng(seed).integers(0, P, size=(1, 4), dtype=np.uint64)
     recs, chal = to_records(L, [pp.prove(C, 1000 + seed, [int(x) for x in pih[0]])])
     assert bit(svb.plonk_check_host(params, circuit, recs, pih, chal), 0) == 1

@@ -253,9 +253,10 @@ def wire_leg(svb, torch, ctx, params, L, n_host, distinct, seed, threads, steps)
         dt = time.perf_counter() - t0
         full = full_leg(svb, torch, ctx, params, common, vk_cap, cds[0], p.value, n_host, steps)
         plonk = plonk_leg(svb, torch, ctx, params, recs, n_host, steps)
+        transforms = transforms_leg(svb, torch, ctx, params, steps)
     finally:
         svb.lib().sv_host_free(p)
-    return {"plonk_check": plonk, "full_verifier": full, "value": n_host * steps / dt, "unit": "proofs/s", "h2d_bytes_per_step": int(n_host * nb),
+    return {"plonk_check": plonk, "full_verifier": full, "transforms": transforms, "value": n_host * steps / dt, "unit": "proofs/s", "h2d_bytes_per_step": int(n_host * nb),
             "d2h_bytes_per_step": int(exp.size * 4), "steps": steps, "proof_bytes": int(nb), "public_inputs": n_pi,
             "note": "sv_verify_proofs_wire: pinned plonky2 wire bytes -> H2D -> wire_unpack_kernel + wire_pi_hash_kernel -> "
                     "device transcript -> fri_query_kernel, per 32 MiB chunk"}
@@ -288,6 +289,52 @@ def full_leg(svb, torch, ctx, params, common, vk_cap, cd, ptr, n_host, steps):
                 "note": "sv_verify_proofs_full: e2e.wire plus plonk challenges, the vanishing-polynomial identity (recursion gate set) and the AND"}
     except Exception as ex:   # noqa: BLE001
         return {"error": f"{type(ex).__name__}: {ex}"}
+
+
+def transforms_leg(svb, torch, ctx, params, steps):
+    """Throughput of the commit-phase kernels on device-resident data: the LDE of the workload's wires oracle (135 columns
+    of 2^degree_bits coefficients -> 2^lde_bits points), a 2^22-point NTT (3 passes), and the one-call commitment."""
+    import ctypes
+    out = {}
+    try:
+        k, rb = params.degree_bits, params.config.rate_bits
+        ncol = params.oracle_num_polys[1]
+        n, N = 1 << k, 1 << (k + rb)
+        g = torch.Generator(device="cuda").manual_seed(1)
+        coeffs = torch.randint(0, 2**62, (ncol, n), dtype=torch.int64, device="cuda", generator=g)
+        lde = torch.empty((ncol, N), dtype=torch.int64, device="cuda")
+        big = torch.randint(0, 2**62, (4, 1 << 22), dtype=torch.int64, device="cuda", generator=g)
+        torch.cuda.synchronize()            # torch filled the buffers on its own stream
+
+        def timed(fn, reps):
+            for _ in range(2):
+                fn()
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            ctx.synchronize()
+            return (time.perf_counter() - t0) / reps
+
+        t = timed(lambda: ctx.lde_batch(coeffs.data_ptr(), rb, log_n=k, n_polys=ncol, out=lde.data_ptr(), mem=svb.MEM_DEVICE), steps)
+        out["lde"] = {"ms": 1e3 * t, "polys": ncol, "log_n": k, "log_N": k + rb, "out_gbs": ncol * N * 8 / t / 1e9}
+        t = timed(lambda: ctx.ntt_batch(big.data_ptr(), log_n=22, n_polys=4, mem=svb.MEM_DEVICE), steps)
+        out["ntt_2^22"] = {"ms": 1e3 * t, "polys": 4, "passes": 3, "algorithmic_gbs": 4 * (1 << 22) * 16 * 3 / t / 1e9}
+        leaves = torch.empty((N, ncol), dtype=torch.int64, device="cuda")
+        cap_h = params.config.cap_height
+        layers = torch.empty(4 * (2 * N - (1 << cap_h)), dtype=torch.int64, device="cuda")
+        vp = ctypes.c_void_p
+
+        def commit():
+            rc = ctx._lib.sv_commit_batch(ctx._h, k, rb, ncol, vp(coeffs.data_ptr()), cap_h, params.hash_kind, vp(leaves.data_ptr()),
+                                          vp(layers.data_ptr()), svb.MEM_DEVICE)
+            if rc != 0:
+                raise RuntimeError(f"sv_commit_batch failed: {rc}")
+        t = timed(commit, steps)
+        out["commit"] = {"ms": 1e3 * t, "leaves": N, "leaf_len": ncol, "note": "LDE + leaf-major copy + Merkle tree of one oracle"}
+    except Exception as ex:   # noqa: BLE001
+        out["error"] = f"{type(ex).__name__}: {ex}"
+    return out
 
 
 def plonk_leg(svb, torch, ctx, params, recs, n_host, steps):

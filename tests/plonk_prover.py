@@ -49,15 +49,15 @@ def x_scale(s, a): return (s * a[0] % P, s * a[1] % P)
 
 
 def _poseidon_tables():
-    """The Poseidon-Goldilocks tables (reference: chip/plonk/gates/poseidon.rs:26-322) from the generated oracle header."""
+    """The Poseidon-Goldilocks tables (reference: chip/plonk/gates/poseidon.rs:26-322), from tests/pyref/constants.json
+    (parsed from the reference's .rs by tools/gen_pyref_constants.py)."""
+    import json
     import os
-    import re
-    t = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "poseidon_g_constants.h")).read()
-    out = {}
-    for name in ("ALL_ROUND_CONSTANTS", "FAST_PARTIAL_FIRST_ROUND_CONSTANT", "FAST_PARTIAL_ROUND_CONSTANTS", "FAST_PARTIAL_ROUND_VS",
-                 "FAST_PARTIAL_ROUND_W_HATS", "FAST_PARTIAL_ROUND_INITIAL_MATRIX", "MDS_MATRIX_CIRC", "MDS_MATRIX_DIAG"):
-        body = re.search(r"ORC_" + name + r"\[\d+\] = \{(.*?)\};", t, re.S).group(1)
-        out[name] = [int(x, 16) for x in re.findall(r"0x([0-9a-fA-F]+)", body)]
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "pyref", "constants.json")))
+    out = {"ALL_ROUND_CONSTANTS": [int(x, 16) for x in d["g_round_constants"]], "MDS_MATRIX_CIRC": d["g_mds_circ"], "MDS_MATRIX_DIAG": d["g_mds_diag"]}
+    for name in ("FAST_PARTIAL_FIRST_ROUND_CONSTANT", "FAST_PARTIAL_ROUND_CONSTANTS", "FAST_PARTIAL_ROUND_VS", "FAST_PARTIAL_ROUND_W_HATS",
+                 "FAST_PARTIAL_ROUND_INITIAL_MATRIX"):
+        out[name] = [int(x, 16) for x in d["g_" + name.lower()]]
     return out
 
 

@@ -26,11 +26,16 @@ def build(svb, orc, name, n, seed, n_pi=6, hash_kind=0, degree_bits=4, hiding=Fa
     pis = rng.integers(0, P, size=(n, n_pi), dtype=np.uint64)
     # one circuit = one witness-independent set of constants / sigmas: the same seed for every proof would also repeat
     # the witness, so the proofs differ in their public inputs (hence transcripts) and share the verifier key
-    recs = np.stack([fp.prove_full(svb, orc, C, params, seed, pis[i], cd)[0] for i in range(n)])
+    outs = [fp.prove_full(C, params, seed, pis[i], cd) for i in range(n)]
+    recs = np.stack([o[0] for o in outs])
+    assert recs.shape[1] == L.record_words
     vk_cap = recs[0, L.off_init_caps:L.off_init_caps + 4 * L.ncap].copy()
     assert (recs[:, L.off_init_caps:L.off_init_caps + 4 * L.ncap] == vk_cap).all()
+    # the independent prover wrote its own wire bytes (tests/pyref/proof.py); the product's packer must produce the same
+    blob = np.stack([np.frombuffer(o[1]["blob"], dtype=np.uint8) for o in outs])
+    assert (svb.wire_pack(common, recs, pis) == blob).all()
     return dict(C=C, params=params, L=L, common=common, circuit=circuit, cd=cd, pis=pis, recs=recs, vk_cap=vk_cap,
-                blob=svb.wire_pack(common, recs, pis))
+                blob=blob.copy(), outs=[o[1] for o in outs])
 
 
 def cpu_verdicts(svb, orc, B, blob):

@@ -54,7 +54,7 @@ def test_commit_phase_on_the_device_reproduces_a_proofs_cap(svb, orc, ctx):
     C, params = fp.toy_setup(svb, CONFIGS["recursion_gate_set"])
     rng = np.random.default_rng(2)
     cd = rng.integers(0, P, size=4, dtype=np.uint64)
-    rec, out = fp.prove_full(svb, orc, C, params, 4, rng.integers(0, P, size=3, dtype=np.uint64), cd)
+    rec, out = fp.prove_full(C, params, 4, rng.integers(0, P, size=3, dtype=np.uint64), cd)
     L = svb.api.make_layout(params)
     capw = 4 * L.ncap
     for oracle_index, polys in ((1, out["polys"]["wires"]), (0, out["polys"]["constants"] + out["polys"]["sigmas"])):

@@ -77,7 +77,7 @@ def test_lde_is_the_merkle_leaf_order_of_the_python_prover(svb, orc):
     C, params = fp.toy_setup(svb, CONFIGS["one_selector"])
     rng = np.random.default_rng(2)
     cd = rng.integers(0, P, size=4, dtype=np.uint64)
-    rec, out = fp.prove_full(svb, orc, C, params, 4, rng.integers(0, P, size=3, dtype=np.uint64), cd)
+    rec, out = fp.prove_full(C, params, 4, rng.integers(0, P, size=3, dtype=np.uint64), cd)
     wires = np.array(out["polys"]["wires"], dtype=np.uint64)            # (num_wires, n) coefficients
     lde = svb.lde_host(wires, params.config.rate_bits, shift=7)
     L = svb.api.make_layout(params)
@@ -86,9 +86,10 @@ def test_lde_is_the_merkle_leaf_order_of_the_python_prover(svb, orc):
     for i in (0, 1, 5, N - 1):
         x = 7 * pow(w, bitrev(i, L.lde_bits), P) % P
         assert [int(v) for v in lde[:, i]] == [naive_eval(p, x) for p in wires]
-    tree = fp.Tree(orc, [[int(v) for v in lde[:, i]] for i in range(N)], params.config.cap_height)
+    from pyref.merkle import MerkleTree
+    tree = MerkleTree(np.ascontiguousarray(lde.T), params.config.cap_height)
     capw = 4 * L.ncap
-    assert tree.cap() == [int(v) for v in rec[L.off_init_caps + capw: L.off_init_caps + 2 * capw]]
+    assert [v for d in tree.cap() for v in d] == [int(v) for v in rec[L.off_init_caps + capw: L.off_init_caps + 2 * capw]]
 
 
 def test_bad_arguments(svb):

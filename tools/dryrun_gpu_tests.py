@@ -102,7 +102,8 @@ class MockCtx:
         return svb.lde_host(c, rate_bits, shift=shift)
 
     def merkle_tree_build(self, leaves, leaf_len, cap_height, hash_kind=0, **kw):
-        t = fp.Tree(orc, [[int(v) for v in row] for row in leaves], cap_height, hash_kind)
+        from pyref.merkle import MerkleTree
+        t = MerkleTree(np.asarray(leaves, dtype=np.uint64).reshape(len(leaves), -1), cap_height, hash_kind)
         return [np.array(layer, dtype=np.uint64) for layer in t.layers]
 
     def commit_batch(self, coeffs, rate_bits, cap_height, hash_kind=0):

@@ -48,6 +48,7 @@ pub struct sv_fri_shape {
     pub oracle_blinding: [u32; 4],
     pub num_zs: u32,
     pub hash_kind: u32,
+    pub reduction_arity_bits: [u32; SV_MAX_STEPS],
 }
 
 #[repr(C)]
@@ -63,6 +64,7 @@ pub struct sv_fri_layout {
     pub q_off_init_evals: [u32; 4], pub q_off_init_sibs: [u32; 4], pub init_depth: u32,
     pub q_off_step_evals: [u32; SV_MAX_STEPS], pub q_off_step_sibs: [u32; SV_MAX_STEPS],
     pub step_depth: [u32; SV_MAX_STEPS],
+    pub step_arity_bits: [u32; SV_MAX_STEPS], pub step_index_shift: [u32; SV_MAX_STEPS],
     pub query_words: u32, pub record_words: u32,
     pub algo_bytes_per_query: u32, pub algo_bytes_shared: u32, pub perms_per_query: u32,
 }
@@ -162,7 +164,8 @@ pub struct GpuError(pub c_int, pub String);
 /// (types/common_data.rs:43-54,148-150,202-221).
 pub fn shape_from<F: halo2_proofs::halo2curves::ff::PrimeField>(cd: &CommonData<F>) -> sv_fri_shape {
     let p: &FriParams = &cd.fri_params;
-    assert!(p.reduction_arity_bits.iter().all(|&a| a == 1), "arity 2 only (fri_chip.rs:211)");
+    // any 2^k-ary reduction, k = 1..4 (the in-circuit verifier stops at arity 2, fri_chip.rs:211; the GPU fold does not)
+    assert!(p.reduction_arity_bits.len() <= SV_MAX_STEPS && p.reduction_arity_bits.iter().all(|&a| (1..=4).contains(&a)));
     let oracles = cd.fri_oracles();
     let mut s = sv_fri_shape::default();
     s.degree_bits = p.degree_bits as u32;
@@ -171,6 +174,7 @@ pub fn shape_from<F: halo2_proofs::halo2curves::ff::PrimeField>(cd: &CommonData<
     s.num_query_rounds = p.config.num_query_rounds as u32;
     s.proof_of_work_bits = p.config.proof_of_work_bits;
     s.num_steps = p.reduction_arity_bits.len() as u32;
+    for (i, &a) in p.reduction_arity_bits.iter().enumerate() { s.reduction_arity_bits[i] = a as u32; }
     s.final_poly_len = 1u32 << (p.degree_bits - p.reduction_arity_bits.iter().sum::<usize>());
     s.hiding = p.hiding as u32;
     for k in 0..4 {

@@ -28,7 +28,7 @@ int main(int argc, char** argv) {
     if (argc != 3) { fprintf(stderr, "usage: %s proofs.bin vk.bin\n", argv[0]); return 2; }
     sv_plonk_common common = {4, 80, 135, 2, 9, 8, 4};
     sv_fri_shape shape;
-    if (sv_fri_shape_from_common(&common, 12, 3, 4, 28, 16, 7, 0, SV_HASH_POSEIDON_GOLDILOCKS, &shape)) return 1;
+    if (sv_fri_shape_from_common(&common, 12, 3, 4, 28, 16, 7, NULL /* arity 2 throughout */, 0, SV_HASH_POSEIDON_GOLDILOCKS, &shape)) return 1;
     size_t nb = sv_wire_proof_bytes(&shape, &common), len = 0, vk_len = 0;
     sv_ctx* ctx = NULL;
     if (sv_ctx_create(0, &ctx)) { fprintf(stderr, "%s\n", sv_last_error(NULL)); return 1; }   /* no CPU fallback */

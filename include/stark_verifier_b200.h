@@ -35,6 +35,7 @@ extern "C" {
                                          native.rs:16-77, constants.rs (the Hasher of Bn254PoseidonGoldilocksConfig) */
 
 #define SV_MAX_STEPS 32
+#define SV_MAX_ARITY_BITS 4 /* a reduction step folds at most 16 evaluations (plonky2's strategies stop at arity 16) */
 
 /* == FriParams + FriConfig (types/common_data.rs:10-54) and the part of FriInstanceInfo
  *    (types/fri.rs:50-72, types/common_data.rs:153-221) the FRI verifier reads. == */
@@ -44,14 +45,19 @@ typedef struct sv_fri_shape {
     uint32_t cap_height;          /* FriConfig.cap_height */
     uint32_t num_query_rounds;    /* FriConfig.num_query_rounds */
     uint32_t proof_of_work_bits;  /* FriConfig.proof_of_work_bits */
-    uint32_t num_steps;           /* FriParams.reduction_arity_bits.len(); every entry must be 1
-                                     (the reference supports arity 2 only: chip/fri_chip.rs:211) */
-    uint32_t final_poly_len;      /* number of Fp2 coefficients in FriProofValues.final_poly */
+    uint32_t num_steps;           /* FriParams.reduction_arity_bits.len() */
+    uint32_t final_poly_len;      /* number of Fp2 coefficients in FriProofValues.final_poly
+                                     = 2^(degree_bits - sum of reduction_arity_bits) for a plonky2 proof */
     uint32_t hiding;              /* FriParams.hiding */
     uint32_t oracle_num_polys[4]; /* FriOracleInfo.num_polys: constants_sigmas, wires, zs_partial_products, quotient */
     uint32_t oracle_blinding[4];  /* FriOracleInfo.blinding (salted leaf = +4 limbs when hiding) */
     uint32_t num_zs;              /* batch 1 (opened at g*zeta) = polynomials [0, num_zs) of oracle 2 */
     uint32_t hash_kind;           /* SV_HASH_* */
+    uint32_t reduction_arity_bits[SV_MAX_STEPS]; /* FriParams.reduction_arity_bits[0 .. num_steps): 1 .. SV_MAX_ARITY_BITS
+                                     each.  The reference's in-circuit verifier folds arity 2 only (chip/fri_chip.rs:211);
+                                     its own demo proves with ConstantArityBits(3, 5) (plonky2_semaphore/access_set.rs:124)
+                                     and checks those proofs with plonky2's native verifier, whose 2^k-ary fold
+                                     (compute_evaluation: interpolate the coset, evaluate at beta) is what runs here. */
 } sv_fri_shape;
 
 /* Flat per-proof record: word (u64) offsets.  Every segment starts on a 4-word (32-byte) boundary
@@ -69,7 +75,8 @@ typedef struct sv_fri_shape {
  *     zeta 2, zeta_next 2           FriBatchInfo.point of the two batches
  *   then num_query_rounds x query block (FriQueryRoundValues, types/proof.rs:217):
  *     for k in 0..4: evals[leaf_len[k]], siblings[init_depth x 4]    (FriInitialTreeProofValues)
- *     for i in steps: evals[2 x 2], siblings[step_depth[i] x 4]      (FriQueryStepValues)
+ *     for i in steps: evals[2^arity_bits[i] x 2], siblings[step_depth[i] x 4]      (FriQueryStepValues; the
+ *                                   evals are the step tree's leaf: more than 4 words are hashed, 4 are their own digest)
  */
 typedef struct sv_fri_layout {
     uint32_t ncap, lde_bits, n0, n1;
@@ -79,6 +86,8 @@ typedef struct sv_fri_layout {
     uint32_t leaf_len[4];
     uint32_t q_off_init_evals[4], q_off_init_sibs[4], init_depth;
     uint32_t q_off_step_evals[SV_MAX_STEPS], q_off_step_sibs[SV_MAX_STEPS], step_depth[SV_MAX_STEPS];
+    uint32_t step_arity_bits[SV_MAX_STEPS]; /* copy of the shape's reduction_arity_bits */
+    uint32_t step_index_shift[SV_MAX_STEPS]; /* leaf index of step tree i = x_index >> step_index_shift[i] (sum of arity bits up to i) */
     uint32_t query_words, record_words;
     /* algorithmic HBM read bytes: unpadded per-query and per-proof-shared payload */
     uint32_t algo_bytes_per_query, algo_bytes_shared;
@@ -233,10 +242,11 @@ typedef struct sv_plonk_common {
 
 /* FriParams/FriConfig + CommonData -> sv_fri_shape: the oracle widths and blinding flags of
  * CommonData::fri_oracles (types/common_data.rs:195-221; blinding = PlonkOracle consts :101-123), batch 1 =
- * fri_zs_polys (:176-178), final_poly_len = 2^(degree_bits - num_steps) (arity-2 reduction throughout). */
+ * fri_zs_polys (:176-178), final_poly_len = 2^(degree_bits - sum of arity bits).  reduction_arity_bits: num_steps entries
+ * (NULL = arity 2 throughout, the reference's ConstantArityBits(1, 5) strategy). */
 int sv_fri_shape_from_common(const sv_plonk_common* common, uint32_t degree_bits, uint32_t rate_bits, uint32_t cap_height,
-                             uint32_t num_query_rounds, uint32_t proof_of_work_bits, uint32_t num_steps, uint32_t hiding,
-                             uint32_t hash_kind, sv_fri_shape* out);
+                             uint32_t num_query_rounds, uint32_t proof_of_work_bits, uint32_t num_steps,
+                             const uint32_t* reduction_arity_bits, uint32_t hiding, uint32_t hash_kind, sv_fri_shape* out);
 
 /* Length in bytes of one serialised ProofWithPublicInputs of this shape (every proof of one circuit has the same
  * length); 0 if shape and common disagree.  Layout (plonky2 @ the revision Cargo.lock pins, util/serialization.rs,
@@ -245,7 +255,7 @@ int sv_fri_shape_from_common(const sv_plonk_common* common, uint32_t degree_bits
  *   wires_cap, plonk_zs_partial_products_cap, quotient_polys_cap              3 x 2^cap_height x 32 B
  *   openings: constants, plonk_sigmas, wires, plonk_zs, plonk_zs_next, partial_products, quotient_polys   (x 16 B)
  *   commit_phase_merkle_caps                                                   num_steps x 2^cap_height x 32 B
- *   per query round: 4 x (leaf evals x 8 B, u8 n, n x 32 B siblings); per step (2 x 16 B evals, u8 n, n x 32 B)
+ *   per query round: 4 x (leaf evals x 8 B, u8 n, n x 32 B siblings); per step (2^arity_bits x 16 B evals, u8 n, n x 32 B)
  *   final_poly coefficients x 16 B, pow_witness 8 B, public inputs x 8 B
  * Mirrors the field order of ProofValues / OpeningSetValues / FriProofValues (types/proof.rs:34-43,143-160,380-387). */
 size_t sv_wire_proof_bytes(const sv_fri_shape* shape, const sv_plonk_common* common);

@@ -18,7 +18,7 @@ class OrcShape(ctypes.Structure):
         "degree_bits", "rate_bits", "cap_height", "num_query_rounds", "proof_of_work_bits",
         "num_steps", "final_poly_len", "hiding")] + [
         ("oracle_num_polys", ctypes.c_uint32 * 4), ("oracle_blinding", ctypes.c_uint32 * 4),
-        ("num_zs", ctypes.c_uint32), ("hash_kind", ctypes.c_uint32)]
+        ("num_zs", ctypes.c_uint32), ("hash_kind", ctypes.c_uint32), ("reduction_arity_bits", ctypes.c_uint32 * 32)]
 
 
 class OrcLayout(ctypes.Structure):
@@ -76,7 +76,7 @@ def shape_from(sv_shape) -> OrcShape:
     for name, _ in OrcShape._fields_:
         v = getattr(sv_shape, name)
         if hasattr(v, "__len__"):
-            setattr(s, name, (ctypes.c_uint32 * 4)(*list(v)))
+            setattr(s, name, (ctypes.c_uint32 * len(v))(*list(v)))
         else:
             setattr(s, name, v)
     return s

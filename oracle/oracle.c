@@ -310,7 +310,14 @@ int orc_make_layout(const orc_shape *s, orc_layout *L) {
     if (s->num_steps > 32 || s->cap_height > 16) return -1;
     L->ncap = 1u << s->cap_height;
     L->lde_bits = s->degree_bits + s->rate_bits;
-    if (L->lde_bits < s->cap_height + s->num_steps) return -1;
+    {
+        uint32_t total = 0;
+        for (uint32_t i = 0; i < s->num_steps; i++) {
+            if (s->reduction_arity_bits[i] < 1 || s->reduction_arity_bits[i] > 4) return -1;
+            total += s->reduction_arity_bits[i];
+        }
+        if (L->lde_bits < s->cap_height + total) return -1;
+    }
     L->n0 = s->oracle_num_polys[0] + s->oracle_num_polys[1] + s->oracle_num_polys[2] + s->oracle_num_polys[3];
     L->n1 = s->num_zs;
     uint32_t o = 0;
@@ -334,9 +341,11 @@ int orc_make_layout(const orc_shape *s, orc_layout *L) {
         L->q_off_init_evals[k] = q; q = up4(q + L->leaf_len[k]);
         L->q_off_init_sibs[k] = q;  q = up4(q + 4 * L->init_depth);
     }
+    uint32_t consumed = 0;
     for (uint32_t i = 0; i < s->num_steps; i++) {
-        L->step_depth[i] = L->lde_bits - (i + 1) - s->cap_height;
-        L->q_off_step_evals[i] = q; q = up4(q + 4);
+        consumed += s->reduction_arity_bits[i];
+        L->step_depth[i] = L->lde_bits - consumed - s->cap_height;   /* the tree over the cosets of layer i */
+        L->q_off_step_evals[i] = q; q = up4(q + (2u << s->reduction_arity_bits[i]));   /* 2^arity_bits Fp2 evals */
         L->q_off_step_sibs[i] = q;  q = up4(q + 4 * L->step_depth[i]);
     }
     L->query_words = q;
@@ -388,7 +397,7 @@ static int check_consistency(const orc_shape *s, const orc_layout *L, const uint
         if (!all_canonical(q + L->q_off_init_sibs[k], 4 * L->init_depth)) return ORC_FAIL_NONCANONICAL;
     }
     for (uint32_t i = 0; i < s->num_steps; i++) {
-        if (!all_canonical(q + L->q_off_step_evals[i], 4)) return ORC_FAIL_NONCANONICAL;
+        if (!all_canonical(q + L->q_off_step_evals[i], 2u << s->reduction_arity_bits[i])) return ORC_FAIL_NONCANONICAL;
         if (!all_canonical(q + L->q_off_step_sibs[i], 4 * L->step_depth[i])) return ORC_FAIL_NONCANONICAL;
     }
 
@@ -445,38 +454,71 @@ static int check_consistency(const orc_shape *s, const orc_layout *L, const uint
     const int *xb = bits; /* current x_index_bits window */
     uint32_t xb_len = nbits;
     for (uint32_t i = 0; i < s->num_steps; i++) {
-        const uint32_t arity_bits = 1;
-        const uint64_t *evals = q + L->q_off_step_evals[i];      /* 2 Fp2 */
+        const uint32_t arity_bits = s->reduction_arity_bits[i], arity = 1u << arity_bits;
+        const uint64_t *evals = q + L->q_off_step_evals[i];      /* arity Fp2 */
         const int *coset_index_bits = xb + arity_bits;           /* :279 */
         uint32_t coset_len = xb_len - arity_bits;
-        uint32_t x_index_within_coset = (uint32_t)xb[0];         /* :280-282 */
+        uint32_t x_index_within_coset = 0;                       /* :280-282 from_bits(x_index_bits[..arity_bits]) */
+        for (uint32_t j = 0; j < arity_bits; j++) x_index_within_coset |= (uint32_t)xb[j] << j;
         /* :285-292 evals[x_index_within_coset] == prev_eval, limb-wise */
         if (evals[2 * x_index_within_coset] != prev_eval.c[0] || evals[2 * x_index_within_coset + 1] != prev_eval.c[1])
             return ORC_FAIL_STEP_EVAL;
-        /* next_eval :168-226, arity 2: g = 7^((p-1)/2) = -1, g_inv = -1 */
+        /* next_eval :168-226.  The reference stops at arity 2 (:211 TODO); the general case is plonky2's
+         * compute_evaluation (fri/verifier.rs of the pinned dependency), which next_eval restates line by line up to the
+         * interpolation: g = primitive arity-th root; reverse_index_bits(evals); coset_start = x * g^-rev(within);
+         * interpolate {(coset_start * g^j, evals_rev[j])} and evaluate at beta (barycentric form). */
         {
-            uint64_t g = orc_pow(7, (ORC_P - 1) / 2);
+            uint64_t g = orc_pow(7, (ORC_P - 1) >> arity_bits);   /* :181-184 */
             uint64_t g_inv = orc_inv(g);
-            int rb[1] = { xb[0] };                                /* reversed 1-bit vector */
-            uint64_t start = exp_from_bits(g_inv, rb, 1);         /* :191-199 */
+            orc_fp2 ev[16];
+            for (uint32_t j = 0; j < arity; j++) {                /* reverse_index_bits_in_place :188-189 */
+                uint32_t r = 0;
+                for (uint32_t b = 0; b < arity_bits; b++) r |= ((j >> b) & 1u) << (arity_bits - 1 - b);
+                ev[j] = orc2(evals[2 * r], evals[2 * r + 1]);
+            }
+            int rb[4];
+            for (uint32_t b = 0; b < arity_bits; b++) rb[b] = xb[arity_bits - 1 - b];   /* bits reversed :191-199 */
+            uint64_t start = exp_from_bits(g_inv, rb, arity_bits);
             uint64_t coset_start = orc_mul(start, x);             /* :200 */
-            /* reverse_index_bits_in_place on 2 entries is the identity (:188-189) */
-            orc_fp2 a0 = orc2(coset_start, 0), a1 = orc2(evals[0], evals[1]);
-            orc_fp2 b0 = orc2(orc_mul(coset_start, g), 0), b1 = orc2(evals[2], evals[3]);
+            uint64_t px[16];                                      /* points :203-210 */
+            uint64_t g_power = 1;
+            for (uint32_t j = 0; j < arity; j++) { px[j] = orc_mul(coset_start, g_power); g_power = orc_mul(g_power, g); }
             orc_fp2 beta = orc2(rec[L->off_betas + 2 * i], rec[L->off_betas + 2 * i + 1]);
-            orc_fp2 numerator = orc2_mul(orc2_sub(beta, a0), orc2_sub(b1, a1));   /* :219-221 */
-            orc_fp2 denominator = orc2_sub(b0, a0);                               /* :222 */
-            if (orc2_is_zero(denominator)) return ORC_FAIL_ZERO_DENOM;
-            prev_eval = orc2_add(orc2_mul(numerator, orc2_inv(denominator)), a1); /* :223-224 */
+            if (arity == 2) {
+                /* the reference's literal two-point formula :212-224 */
+                orc_fp2 a0 = orc2(px[0], 0), a1 = ev[0], b0 = orc2(px[1], 0), b1 = ev[1];
+                orc_fp2 numerator = orc2_mul(orc2_sub(beta, a0), orc2_sub(b1, a1));   /* :219-221 */
+                orc_fp2 denominator = orc2_sub(b0, a0);                               /* :222 */
+                if (orc2_is_zero(denominator)) return ORC_FAIL_ZERO_DENOM;
+                prev_eval = orc2_add(orc2_mul(numerator, orc2_inv(denominator)), a1); /* :223-224 */
+            } else {
+                /* plonky2 interpolate(points, beta, barycentric_weights(points)):
+                 *   w_j = 1 / prod_{m != j} (x_j - x_m);  if beta == x_j return y_j;
+                 *   l(beta) = prod_j (beta - x_j);  result = l(beta) * sum_j w_j / (beta - x_j) * y_j */
+                int hit = -1;
+                for (uint32_t j = 0; j < arity; j++) if (beta.c[1] == 0 && beta.c[0] == px[j]) hit = (int)j;
+                if (hit >= 0) prev_eval = ev[hit];
+                else {
+                    orc_fp2 l = orc2(1, 0), sum = orc2(0, 0);
+                    for (uint32_t j = 0; j < arity; j++) l = orc2_mul(l, orc2_sub(beta, orc2(px[j], 0)));
+                    for (uint32_t j = 0; j < arity; j++) {
+                        uint64_t d = 1;
+                        for (uint32_t m = 0; m < arity; m++) if (m != j) d = orc_mul(d, orc_sub(px[j], px[m]));
+                        orc_fp2 w_over = orc2_mul(orc2(orc_inv(d), 0), orc2_inv(orc2_sub(beta, orc2(px[j], 0))));
+                        sum = orc2_add(sum, orc2_mul(w_over, ev[j]));
+                    }
+                    prev_eval = orc2_mul(l, sum);
+                }
+            }
         }
-        /* :302-311 step Merkle proof: leaf = flattened evals (4 limbs), index = coset_index_bits,
+        /* :302-311 step Merkle proof: leaf = flattened evals (2 * arity limbs), index = coset_index_bits,
          * SAME cap_index as the initial trees (:308) */
         uint64_t coset_index = 0;
         for (uint32_t j = 0; j < coset_len; j++) coset_index |= (uint64_t)coset_index_bits[j] << j;
         const uint64_t *cap = rec + L->off_step_caps + (size_t)i * L->ncap * 4;
-        if (!orc_merkle_verify(evals, 4, coset_index, q + L->q_off_step_sibs[i], L->step_depth[i], cap, cap_index))
+        if (!orc_merkle_verify(evals, 2 * arity, coset_index, q + L->q_off_step_sibs[i], L->step_depth[i], cap, cap_index))
             return ORC_FAIL_STEP_MERKLE;
-        x = orc_mul(x, x);                                        /* :313 exp_power_of_2(x, arity_bits) */
+        for (uint32_t b = 0; b < arity_bits; b++) x = orc_mul(x, x);   /* :313 exp_power_of_2(x, arity_bits) */
         xb = coset_index_bits; xb_len = coset_len;                /* :315 */
     }
     /* :317-325 final_poly(x) == prev_eval; reduce_extension_field_terms_base

@@ -27,13 +27,15 @@ typedef struct {
     uint32_t cap_height;         /* FriConfig.cap_height */
     uint32_t num_query_rounds;   /* FriConfig.num_query_rounds */
     uint32_t proof_of_work_bits; /* FriConfig.proof_of_work_bits */
-    uint32_t num_steps;          /* reduction_arity_bits.len(); every entry is 1 (fri_chip.rs:211) */
+    uint32_t num_steps;          /* reduction_arity_bits.len() */
     uint32_t final_poly_len;     /* number of Fp2 coefficients of final_poly */
     uint32_t hiding;             /* FriParams.hiding */
     uint32_t oracle_num_polys[4];/* FriOracleInfo.num_polys, order: constants_sigmas, wires, zs_pp, quotient */
     uint32_t oracle_blinding[4]; /* FriOracleInfo.blinding */
     uint32_t num_zs;             /* batch 1 (point g*zeta) = polys [0,num_zs) of oracle 2 (common_data.rs:192-194) */
     uint32_t hash_kind;          /* 0 = Poseidon-Goldilocks, 1 = Poseidon-BN254 wrapped (family B) */
+    uint32_t reduction_arity_bits[32]; /* FriParams.reduction_arity_bits (types/common_data.rs:47); fri_chip.rs:211 implements
+                                    * arity 2 only, larger arities follow plonky2's compute_evaluation (see oracle.c) */
 } orc_shape;
 
 /* Word offsets (u64) of the flat per-proof record; same format as include/stark_verifier_b200.h

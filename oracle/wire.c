@@ -56,7 +56,7 @@ size_t orc_wire_proof_bytes(const orc_shape *s, const orc_common *c) {
     n += (size_t)s->num_steps * L.ncap * 32;
     size_t q = 0;
     for (int k = 0; k < 4; k++) q += 8 * (size_t)L.leaf_len[k] + 1 + 32 * (size_t)L.init_depth;
-    for (uint32_t i = 0; i < s->num_steps; i++) q += 2 * 16 + 1 + 32 * (size_t)L.step_depth[i];
+    for (uint32_t i = 0; i < s->num_steps; i++) q += ((size_t)16 << s->reduction_arity_bits[i]) + 1 + 32 * (size_t)L.step_depth[i];
     n += q * s->num_query_rounds;
     n += 16 * (size_t)s->final_poly_len + 8;
     n += 8 * (size_t)c->num_public_inputs;
@@ -98,8 +98,8 @@ int orc_wire_read_proof(const orc_shape *s, const orc_common *c, const uint64_t 
             if (rd_u8(&r) != L.init_depth) malformed = 1;
             rd_fields(&r, qp + L.q_off_init_sibs[k], 4 * (size_t)L.init_depth);
         }
-        for (uint32_t i = 0; i < s->num_steps; i++) { /* read_fri_query_step, arity 2 */
-            rd_fields(&r, qp + L.q_off_step_evals[i], 4);
+        for (uint32_t i = 0; i < s->num_steps; i++) { /* read_fri_query_step: 2^arity_bits extension evals */
+            rd_fields(&r, qp + L.q_off_step_evals[i], (size_t)2 << s->reduction_arity_bits[i]);
             if (rd_u8(&r) != L.step_depth[i]) malformed = 1;
             rd_fields(&r, qp + L.q_off_step_sibs[i], 4 * (size_t)L.step_depth[i]);
         }
@@ -144,7 +144,7 @@ int orc_wire_write_proof(const orc_shape *s, const orc_common *c, const uint64_t
             wr_fields(&w, qp + L.q_off_init_sibs[k], 4 * (size_t)L.init_depth);
         }
         for (uint32_t i = 0; i < s->num_steps; i++) {
-            wr_fields(&w, qp + L.q_off_step_evals[i], 4);
+            wr_fields(&w, qp + L.q_off_step_evals[i], (size_t)2 << s->reduction_arity_bits[i]);
             w.p[w.pos++] = (uint8_t)L.step_depth[i];
             wr_fields(&w, qp + L.q_off_step_sibs[i], 4 * (size_t)L.step_depth[i]);
         }

@@ -19,6 +19,7 @@ MEM_DEVICE = 1
 HASH_POSEIDON_GOLDILOCKS = 0
 HASH_POSEIDON_BN254 = 1      # bn245_poseidon/plonky2_config.rs:54-75 (the reference's outermost proof)
 SV_MAX_STEPS = 32
+SV_MAX_ARITY_BITS = 4
 
 FAIL_NAMES = {0: "ok", 1: "pow", 2: "noncanonical", 3: "init_merkle", 4: "zero_denominator",
               5: "step_eval", 6: "step_merkle", 7: "final_poly", 8: "malformed", 9: "plonk_identity"}
@@ -36,7 +37,7 @@ class FriShape(ctypes.Structure):
         "degree_bits", "rate_bits", "cap_height", "num_query_rounds", "proof_of_work_bits",
         "num_steps", "final_poly_len", "hiding")] + [
         ("oracle_num_polys", ctypes.c_uint32 * 4), ("oracle_blinding", ctypes.c_uint32 * 4),
-        ("num_zs", ctypes.c_uint32), ("hash_kind", ctypes.c_uint32)]
+        ("num_zs", ctypes.c_uint32), ("hash_kind", ctypes.c_uint32), ("reduction_arity_bits", ctypes.c_uint32 * SV_MAX_STEPS)]
 
 
 class Layout(ctypes.Structure):
@@ -48,7 +49,8 @@ class Layout(ctypes.Structure):
         ("leaf_len", ctypes.c_uint32 * 4), ("q_off_init_evals", ctypes.c_uint32 * 4),
         ("q_off_init_sibs", ctypes.c_uint32 * 4), ("init_depth", ctypes.c_uint32),
         ("q_off_step_evals", ctypes.c_uint32 * SV_MAX_STEPS), ("q_off_step_sibs", ctypes.c_uint32 * SV_MAX_STEPS),
-        ("step_depth", ctypes.c_uint32 * SV_MAX_STEPS), ("query_words", ctypes.c_uint32),
+        ("step_depth", ctypes.c_uint32 * SV_MAX_STEPS), ("step_arity_bits", ctypes.c_uint32 * SV_MAX_STEPS),
+        ("step_index_shift", ctypes.c_uint32 * SV_MAX_STEPS), ("query_words", ctypes.c_uint32),
         ("record_words", ctypes.c_uint32), ("algo_bytes_per_query", ctypes.c_uint32),
         ("algo_bytes_shared", ctypes.c_uint32), ("perms_per_query", ctypes.c_uint32)]
 
@@ -110,9 +112,10 @@ class FriParams:
         return 1 << (self.degree_bits - sum(self.reduction_arity_bits))
 
     def to_shape(self) -> FriShape:
-        if any(a != 1 for a in self.reduction_arity_bits):
-            # the reference's next_eval is arity-2 only (chip/fri_chip.rs:211)
-            raise SvError("only reduction_arity_bits == 1 is supported (reference: fri_chip.rs:211)")
+        # arity 2^k folds, k = 1 .. 4: the reference's next_eval is arity-2 only (chip/fri_chip.rs:211); its demo's
+        # ConstantArityBits(3, 5) proofs (plonky2_semaphore/access_set.rs:124) need the general fold (csrc/fri_fold.cuh)
+        if len(self.reduction_arity_bits) > SV_MAX_STEPS or any(not 1 <= a <= SV_MAX_ARITY_BITS for a in self.reduction_arity_bits):
+            raise SvError("reduction_arity_bits: at most %d entries, each in 1 .. %d" % (SV_MAX_STEPS, SV_MAX_ARITY_BITS))
         s = FriShape()
         s.degree_bits = self.degree_bits
         s.rate_bits = self.config.rate_bits
@@ -126,13 +129,32 @@ class FriParams:
         s.oracle_blinding = (ctypes.c_uint32 * 4)(*[int(b) for b in self.oracle_blinding])
         s.num_zs = self.num_zs
         s.hash_kind = self.hash_kind
+        for i, a in enumerate(self.reduction_arity_bits):
+            s.reduction_arity_bits[i] = a
         return s
 
 
-def _params(degree_bits, rate_bits, cap_height, pow_bits, queries, hiding=False, final_bits=5, **kw) -> FriParams:
-    # FriReductionStrategy::ConstantArityBits(1, 5) (bn245_poseidon/plonky2_config.rs:84)
-    steps = max(0, degree_bits - final_bits)
-    return FriParams(FriConfig(rate_bits, cap_height, pow_bits, queries), hiding, degree_bits, [1] * steps, **kw)
+def constant_arity_bits(arity_bits: int, final_poly_bits: int, degree_bits: int, rate_bits: int, cap_height: int) -> List[int]:
+    """plonky2 FriReductionStrategy::ConstantArityBits(arity_bits, final_poly_bits).reduction_arity_bits: fold by 2^arity_bits
+    while the polynomial has more than 2^final_poly_bits coefficients and the next layer's tree would still be at least as tall
+    as the cap (so every step tree has a cap of 2^cap_height entries)."""
+    out, d = [], degree_bits
+    while d > final_poly_bits and d + rate_bits - arity_bits >= cap_height:
+        if d < arity_bits:
+            raise SvError("ConstantArityBits: degree_bits < arity_bits")     # plonky2: assert!(degree_bits >= arity_bits)
+        out.append(arity_bits)
+        d -= arity_bits
+    return out
+
+
+def _params(degree_bits, rate_bits, cap_height, pow_bits, queries, hiding=False, final_bits=5, arity_bits=1, **kw) -> FriParams:
+    # FriReductionStrategy::ConstantArityBits(1, 5) (bn245_poseidon/plonky2_config.rs:84); ConstantArityBits(3, 5) is the
+    # semaphore demo's (plonky2_semaphore/access_set.rs:124)
+    if arity_bits == 1:
+        steps = [1] * max(0, degree_bits - final_bits)
+    else:
+        steps = constant_arity_bits(arity_bits, final_bits, degree_bits, rate_bits, cap_height)
+    return FriParams(FriConfig(rate_bits, cap_height, pow_bits, queries), hiding, degree_bits, steps, **kw)
 
 
 #: BASELINE configs[1]/[3]: 2^12 trace, blowup 8, 28 queries, cap 4, PoW 16 (standard_inner_stark_verifier_config)
@@ -227,7 +249,7 @@ def lib() -> ctypes.CDLL:
     L.sv_fri_verify_batch_fs.argtypes = [vp, ctypes.POINTER(FriShape), ctypes.c_size_t, vp, vp, vp, ctypes.c_uint32, vp, vp,
                                          ctypes.c_int]
     sp, cp = ctypes.POINTER(FriShape), ctypes.POINTER(PlonkCommon)
-    L.sv_fri_shape_from_common.argtypes = [cp] + [ctypes.c_uint32] * 8 + [sp]
+    L.sv_fri_shape_from_common.argtypes = [cp] + [ctypes.c_uint32] * 6 + [vp, ctypes.c_uint32, ctypes.c_uint32, sp]
     L.sv_wire_proof_bytes.argtypes = [sp, cp]
     L.sv_wire_proof_bytes.restype = ctypes.c_size_t
     L.sv_wire_pack.argtypes = [sp, cp, vp, vp, vp]
@@ -314,9 +336,10 @@ def fri_challenges(params: FriParams, record: np.ndarray, circuit_digest, pi_has
 def shape_from_common(common: CommonData) -> FriShape:
     """sv_fri_shape_from_common: CommonData::fri_oracles / fri_zs_polys (types/common_data.rs:153-221)."""
     p, c, out = common.fri_params, common.to_c(), FriShape()
+    ab = (ctypes.c_uint32 * max(1, len(p.reduction_arity_bits)))(*p.reduction_arity_bits)
     rc = lib().sv_fri_shape_from_common(ctypes.byref(c), p.degree_bits, p.config.rate_bits, p.config.cap_height,
                                         p.config.num_query_rounds, p.config.proof_of_work_bits, len(p.reduction_arity_bits),
-                                        int(p.hiding), p.hash_kind, ctypes.byref(out))
+                                        ctypes.cast(ab, ctypes.c_void_p), int(p.hiding), p.hash_kind, ctypes.byref(out))
     if rc != 0:
         raise SvError(f"sv_fri_shape_from_common failed: {rc}")
     return out

@@ -409,7 +409,10 @@ static int make_params(sv_ctx* c, const sv_fri_shape& s, FriKernelParams& P) {
     cost.push_back({2, 4 + s.num_steps});
     P.n_classes_a = 5;
     std::vector<std::pair<u32, u32>> steps;
-    for (u32 i = 0; i < s.num_steps; i++) steps.push_back({P.L.step_depth[i], 4 + i});
+    for (u32 i = 0; i < s.num_steps; i++) {
+        const u32 leaf = 2u << P.L.step_arity_bits[i];        // 2^k evaluations: hashed when more than 4 words
+        steps.push_back({(leaf > 4 ? (leaf + 7) / 8 : 0) + P.L.step_depth[i], 4 + i});
+    }
     std::stable_sort(steps.begin(), steps.end(), [](const std::pair<u32, u32>& a, const std::pair<u32, u32>& b) { return a.first > b.first; });
     cost.insert(cost.end(), steps.begin(), steps.end());
     for (u32 i = 0; i < P.n_classes; i++) P.class_order[i] = cost[i].second;
@@ -578,6 +581,7 @@ static int make_fs(sv_ctx* c, const sv_fri_shape* shape, const uint64_t circuit_
         if (!is_canonical(circuit_digest[i])) return fail(c, -8, "circuit_digest word >= p");
         F.circuit_digest[i] = circuit_digest[i];
     }
+    if (shape->degree_bits > 32) return fail(c, -8, "degree_bits > 32 (Goldilocks has 2-adicity 32)");   // before the shift below
     F.g = svb::pow(7, (GL_P - 1) >> shape->degree_bits);
     F.num_challenges = num_challenges;
     return 0;

@@ -21,6 +21,7 @@
 // next level's sibling is prefetched while the current permutation runs.
 #pragma once
 #include "layout.hpp"
+#include "fri_fold.cuh"
 #include "poseidon_g.cuh"
 #include "poseidon_b.cuh"
 #include "poseidon_g_coop.cuh"
@@ -280,16 +281,16 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) fri_query_ke
 
     if (cls < 4 + P.num_steps) {
         // cls < 4: verify_initial_merkle_proof, oracle `cls` (fri_chip.rs:85-110)
-        // else:    step Merkle proof (fri_chip.rs:303-311): leaf = the 2 Fp2 evals (no leaf hash),
-        //          index = x_index >> (i+1)
+        // else:    step Merkle proof (fri_chip.rs:303-311): leaf = the 2^arity_bits Fp2 evals of the coset (their own
+        //          digest when they are 4 words, hashed otherwise), index = x_index >> (arity bits consumed so far)
         bool init = cls < 4;
         u32 i = init ? 0 : cls - 4;
         const u64* cap = rec + (init ? L.off_init_caps + ((size_t)cls * L.ncap + cap_index) * 4
                                      : L.off_step_caps + ((size_t)i * L.ncap + cap_index) * 4);
         const u64* leaf = q + (init ? L.q_off_init_evals[cls] : L.q_off_step_evals[i]);
         const u64* sibs = q + (init ? L.q_off_init_sibs[cls] : L.q_off_step_sibs[i]);
-        u32 rc = merkle_chain<KIND>(leaf, init ? L.leaf_len[cls] : 4u, sibs, init ? L.init_depth : L.step_depth[i],
-                              init ? x_index : x_index >> (i + 1), cap, init ? SV_FAIL_INIT_MERKLE : SV_FAIL_STEP_MERKLE,
+        u32 rc = merkle_chain<KIND>(leaf, init ? L.leaf_len[cls] : (2u << L.step_arity_bits[i]), sibs, init ? L.init_depth : L.step_depth[i],
+                              init ? x_index : x_index >> L.step_index_shift[i], cap, init ? SV_FAIL_INIT_MERKLE : SV_FAIL_STEP_MERKLE,
                               pscratch);
         if (rc) report_fail(accept_bitmap, first_fail, proof, query,
                             rc == SV_FAIL_NONCANONICAL ? 0 : (init ? 1 + cls : 8 + 3 * i + 2), rc);
@@ -326,23 +327,20 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) fri_query_ke
     fp2 prev = sum;
 
     u64 idx = x_index;
+    u64 inv_x = P.num_steps ? canon(inv(x)) : 0;   // x = 7 * omega^e is never 0; carried along by squaring
     for (u32 i = 0; i < P.num_steps; i++) {
-        u64 ev[4];
-        ldg4(q + L.q_off_step_evals[i], ev);
-        u32 b = (u32)(idx & 1);
+        const u32 ab = L.step_arity_bits[i];
+        const u64* ev = q + L.q_off_step_evals[i];
+        const u32 within = (u32)idx & ((1u << ab) - 1);       // x_index_within_coset (fri_chip.rs:279-282)
         // evals[x_index_within_coset] == prev_eval (fri_chip.rs:285-292)
-        u64 e0 = b ? ev[2] : ev[0], e1 = b ? ev[3] : ev[1];
-        if ((e0 != prev.c0 || e1 != prev.c1) && 8 + 3 * i < fail_key) { fail_key = 8 + 3 * i; fail_code = SV_FAIL_STEP_EVAL; }
-        // next_eval (fri_chip.rs:168-226): coset_start = x * (-1)^b; a = (cs, ev[0..2]), b = (-cs, ev[2..4])
-        u64 cs = b ? neg(x) : x;
-        fp2 a0 = mk2(cs, 0), a1 = mk2(ev[0], ev[1]), b0 = mk2(neg(cs), 0), b1 = mk2(ev[2], ev[3]);
+        ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2*>(ev + 2 * within));
+        if ((e.x != prev.c0 || e.y != prev.c1) && 8 + 3 * i < fail_key) { fail_key = 8 + 3 * i; fail_code = SV_FAIL_STEP_EVAL; }
+        // next_eval (fri_chip.rs:168-226; any arity: fri_fold.cuh).  Its division is by differences of distinct coset
+        // points, never zero, so order key 8 + 3 i + 1 stays unused.
         fp2 beta = mk2(__ldg(rec + L.off_betas + 2 * i), __ldg(rec + L.off_betas + 2 * i + 1));
-        fp2 num = mul2(sub2(beta, a0), sub2(b1, a1));
-        fp2 den = sub2(b0, a0);
-        if (is_zero2(den) && 8 + 3 * i + 1 < fail_key) { fail_key = 8 + 3 * i + 1; fail_code = SV_FAIL_ZERO_DENOM; }
-        prev = add2(mul2(num, inv2(den)), a1);
-        x = mulc(x, x);   // exp_power_of_2(x, arity_bits) (:313)
-        idx >>= 1;
+        prev = fri_fold(ab, ev, x, inv_x, within, beta);
+        for (u32 k = 0; k < ab; k++) { x = mulc(x, x); inv_x = mulc(inv_x, inv_x); }   // exp_power_of_2(x, arity_bits) (:313)
+        idx >>= ab;
     }
     // final_poly(x) == prev_eval (fri_chip.rs:317-325)
     fp2 fe = mk2(0, 0);

@@ -8,15 +8,16 @@
 //  * sv_synth_proofs -- the reference ships no proofs and its prover (plonky2, Rust) cannot run here,
 //    so valid plonky2-SHAPED proofs are built from scratch with the conventions the verifier implies:
 //    LDE point of leaf i is 7 * omega^{bitrev(i)} (fri_chip.rs:152-166,262-264), salted leaves carry 4
-//    extra limbs at the end (types/assigned.rs:57-71), step-tree leaf k holds the coset pair
-//    (2k, 2k+1) (fri_chip.rs:279-311), fold = fri_chip.rs:168-226, final polynomial of
-//    2^(degree_bits - num_steps) coefficients, proof-of-work on the top bits of the squeezed response
+//    extra limbs at the end (types/assigned.rs:57-71), step-tree leaf k holds the 2^arity_bits values of
+//    coset k in leaf order (fri_chip.rs:279-311), fold = fri_chip.rs:168-226 generalised to 2^k (fri_fold.cuh),
+//    final polynomial of 2^(degree_bits - sum arity_bits) coefficients, proof-of-work on the top bits of the squeezed response
 //    (fri_chip.rs:364-376).  Trace columns are K-sparse polynomials over a shared set of degrees
 //    (all < 2^degree_bits), which makes the LDE and the DEEP quotient cheap to evaluate point-wise
 //    without an NTT; the verifier's work does not depend on how the columns were chosen.
 #include "../../include/stark_verifier_b200.h"
 #include "goldilocks.cuh"
 #include "layout.hpp"
+#include "fri_fold.cuh"
 #include "host_util.hpp"
 
 #include <algorithm>
@@ -294,38 +295,44 @@ static int prove(const Circuit& C, const u64 pi_hash[4], u32 num_challenges, u64
     });
     if (bad) return -2;
 
-    // commit phase
+    // commit phase: layer st holds the values of the current polynomial in leaf order (index i <-> point
+    // shift * omega_cur^bitrev(i)); leaf k of its tree = the 2^ab values of coset k (flattened Fp2 limbs: their own
+    // digest when 4 words, hashed otherwise); the next layer is the 2^ab-ary fold of every coset (fri_fold.cuh)
     std::vector<Tree> step_trees(s.num_steps);
     std::vector<std::vector<fp2>> step_vals(s.num_steps);
     u64 shift = 7;                       // coset shift of the current domain
     u32 bits = L.lde_bits;
     for (u32 st = 0; st < s.num_steps; st++) {
-        size_t half = v.size() / 2;
-        std::vector<u64> dig(half * 4);
-        for (size_t k = 0; k < half; k++) {
-            dig[4 * k] = v[2 * k].c0; dig[4 * k + 1] = v[2 * k].c1;
-            dig[4 * k + 2] = v[2 * k + 1].c0; dig[4 * k + 3] = v[2 * k + 1].c1;
-        }
+        const u32 ab = s.reduction_arity_bits[st], arity = 1u << ab;
+        size_t cosets = v.size() >> ab;
+        std::vector<u64> dig(cosets * 4);
+        parallel_for(cosets, cosets >= 4096 ? nthreads : 1, [&](size_t b, size_t e) {
+            u64 leaf[32];
+            for (size_t k = b; k < e; k++) {
+                for (u32 t = 0; t < arity; t++) { leaf[2 * t] = v[k * arity + t].c0; leaf[2 * t + 1] = v[k * arity + t].c1; }
+                hash_or_noop(s.hash_kind, leaf, 2 * arity, &dig[4 * k]);
+            }
+        });
         step_trees[st].build(s.hash_kind, std::move(dig), s.cap_height, nthreads);
         memcpy(rec + L.off_step_caps + (size_t)st * L.ncap * 4, step_trees[st].cap(), (size_t)L.ncap * 32);
         ch.observe_n(step_trees[st].cap(), L.ncap * 4);
         fp2 beta = ch.squeeze2();
         rec[L.off_betas + 2 * st] = beta.c0; rec[L.off_betas + 2 * st + 1] = beta.c1;
-        // fold: a0 = x_{2k}, a1 = v[2k]; b0 = -a0, b1 = v[2k+1]; a1 + (beta - a0)(b1 - a1)/(b0 - a0)
-        std::vector<fp2> nv(half);
+        std::vector<fp2> nv(cosets);
         u32 stride = N >> bits;  // omega_cur = omega^stride
-        parallel_for(half, half >= 4096 ? nthreads : 1, [&](size_t b, size_t e) {
+        parallel_for(cosets, cosets >= 4096 ? nthreads : 1, [&](size_t b, size_t e) {
+            u64 leaf[32];
             for (size_t k = b; k < e; k++) {
-                u64 x = mulc(shift, C.wtab[((u64)bitrev((u32)(2 * k), bits) * stride) & (N - 1)]);
-                fp2 a0 = mk2(x, 0), a1 = v[2 * k], b0 = mk2(neg(x), 0), b1 = v[2 * k + 1];
-                fp2 num = mul2(sub2(beta, a0), sub2(b1, a1));
-                nv[k] = add2(mul2(num, inv2(sub2(b0, a0))), a1);
+                // the coset's first entry (leaf index k * arity, x_index_within_coset = 0) sits at x
+                u64 x = mulc(shift, C.wtab[((u64)bitrev((u32)(k * arity), bits) * stride) & (N - 1)]);
+                for (u32 t = 0; t < arity; t++) { leaf[2 * t] = v[k * arity + t].c0; leaf[2 * t + 1] = v[k * arity + t].c1; }
+                nv[k] = fri_fold(ab, leaf, x, inv(x), 0, beta);
             }
         });
         step_vals[st] = std::move(v);
         v = std::move(nv);
-        shift = mulc(shift, shift);
-        bits--;
+        for (u32 t = 0; t < ab; t++) shift = mulc(shift, shift);
+        bits -= ab;
     }
     // final polynomial: v holds M = 2^bits values at y_k = shift * w^{bitrev(k)}, w = omega^(N/M).
     {
@@ -377,11 +384,11 @@ static int prove(const Circuit& C, const u64 pi_hash[4], u32 num_challenges, u64
         }
         u32 cur = idx;
         for (u32 st = 0; st < s.num_steps; st++) {
-            u32 coset = cur >> 1;
+            const u32 ab = s.reduction_arity_bits[st], arity = 1u << ab;
+            u32 coset = cur >> ab;
             const std::vector<fp2>& sv = step_vals[st];
             u64* ev = qp + L.q_off_step_evals[st];
-            ev[0] = sv[2 * coset].c0; ev[1] = sv[2 * coset].c1;
-            ev[2] = sv[2 * coset + 1].c0; ev[3] = sv[2 * coset + 1].c1;
+            for (u32 t = 0; t < arity; t++) { ev[2 * t] = sv[(size_t)coset * arity + t].c0; ev[2 * t + 1] = sv[(size_t)coset * arity + t].c1; }
             step_trees[st].path(coset, qp + L.q_off_step_sibs[st]);
             cur = coset;
         }
@@ -466,7 +473,11 @@ extern "C" int sv_synth_proofs_pi(const sv_fri_shape* shape, uint64_t seed, uint
     sv_fri_layout L;
     if (!shape || !records_out || make_layout(*shape, L)) return -1;
     if (shape->hash_kind > SV_HASH_POSEIDON_BN254) return -2;
-    if (shape->final_poly_len != (1u << (shape->degree_bits - shape->num_steps))) return -3;
+    {
+        u32 total = 0;
+        for (u32 i = 0; i < shape->num_steps; i++) total += shape->reduction_arity_bits[i];
+        if (total > shape->degree_bits || shape->final_poly_len != (1u << (shape->degree_bits - total))) return -3;
+    }
     if (n_circuits == 0) n_circuits = 1;
     if (nthreads < 1) nthreads = 1;
     if (n_circuits > n_proofs) n_circuits = (uint32_t)(n_proofs ? n_proofs : 1);

@@ -19,10 +19,16 @@ SVB_LAYOUT_HD uint32_t up4(uint32_t x) { return (x + 3u) & ~3u; }
 static inline int make_layout(const sv_fri_shape& s, sv_fri_layout& L) {
     memset(&L, 0, sizeof L);
     if (s.num_steps > SV_MAX_STEPS || s.cap_height > 16 || s.num_query_rounds == 0) return -1;
-    if (s.degree_bits + s.rate_bits > 40) return -1;
+    // Goldilocks has 2-adicity 32: there is no domain of more than 2^32 points
+    if (s.degree_bits > 32 || s.rate_bits > 32 || s.degree_bits + s.rate_bits > 32) return -1;
     L.ncap = 1u << s.cap_height;
     L.lde_bits = s.degree_bits + s.rate_bits;
-    if (L.lde_bits < s.cap_height + s.num_steps) return -1;
+    uint32_t total_arity_bits = 0;
+    for (uint32_t i = 0; i < s.num_steps; i++) {
+        if (s.reduction_arity_bits[i] < 1 || s.reduction_arity_bits[i] > SV_MAX_ARITY_BITS) return -1;
+        total_arity_bits += s.reduction_arity_bits[i];
+    }
+    if (L.lde_bits < s.cap_height + total_arity_bits) return -1;   // every step tree is at least as tall as the cap
     if (s.num_zs > s.oracle_num_polys[2]) return -1;
     L.n0 = s.oracle_num_polys[0] + s.oracle_num_polys[1] + s.oracle_num_polys[2] + s.oracle_num_polys[3];
     L.n1 = s.num_zs;
@@ -51,12 +57,17 @@ static inline int make_layout(const sv_fri_shape& s, sv_fri_layout& L) {
         algo_q += 8 * L.leaf_len[k] + 32 * L.init_depth;
         perms += (L.leaf_len[k] > 4 ? (L.leaf_len[k] + 7) / 8 : 0) + L.init_depth;
     }
+    uint32_t shift = 0;
     for (uint32_t i = 0; i < s.num_steps; i++) {
-        L.step_depth[i] = L.lde_bits - (i + 1) - s.cap_height;
-        L.q_off_step_evals[i] = seg(4);
+        const uint32_t ab = s.reduction_arity_bits[i], leaf = 2u << ab;   // 2^ab Fp2 evaluations = 2^(ab+1) words
+        shift += ab;
+        L.step_arity_bits[i] = ab;
+        L.step_index_shift[i] = shift;
+        L.step_depth[i] = L.lde_bits - shift - s.cap_height;
+        L.q_off_step_evals[i] = seg(leaf);
         L.q_off_step_sibs[i] = seg(4 * L.step_depth[i]);
-        algo_q += 32 + 32 * L.step_depth[i];
-        perms += L.step_depth[i];
+        algo_q += 8 * leaf + 32 * L.step_depth[i];
+        perms += (leaf > 4 ? (leaf + 7) / 8 : 0) + L.step_depth[i];
     }
     L.query_words = o;
     L.record_words = L.header_words + s.num_query_rounds * L.query_words;

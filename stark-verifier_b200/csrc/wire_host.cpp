@@ -58,7 +58,7 @@ int make_wire_map(const sv_fri_shape& s, const sv_plonk_common& c, WireMap& M) {
             run(M.q_src, L.q_off_init_sibs[k], 4ull * L.init_depth);
         }
         for (u32 i = 0; i < s.num_steps; i++) {
-            run(M.q_src, L.q_off_step_evals[i], 4);
+            run(M.q_src, L.q_off_step_evals[i], 2ull << L.step_arity_bits[i]);
             M.chk[n++] = (u32)(o << 8) | L.step_depth[i];
             o += 1;
             run(M.q_src, L.q_off_step_sibs[i], 4ull * L.step_depth[i]);
@@ -103,7 +103,7 @@ using namespace svb;
 
 extern "C" int sv_fri_shape_from_common(const sv_plonk_common* c, uint32_t degree_bits, uint32_t rate_bits, uint32_t cap_height,
                                         uint32_t num_query_rounds, uint32_t proof_of_work_bits, uint32_t num_steps,
-                                        uint32_t hiding, uint32_t hash_kind, sv_fri_shape* out) {
+                                        const uint32_t* reduction_arity_bits, uint32_t hiding, uint32_t hash_kind, sv_fri_shape* out) {
     if (!c || !out) return -1;
     if (num_steps > degree_bits || num_steps > SV_MAX_STEPS) return -2;
     sv_fri_shape s;
@@ -114,7 +114,13 @@ extern "C" int sv_fri_shape_from_common(const sv_plonk_common* c, uint32_t degre
     s.num_query_rounds = num_query_rounds;
     s.proof_of_work_bits = proof_of_work_bits;
     s.num_steps = num_steps;
-    s.final_poly_len = 1u << (degree_bits - num_steps);
+    uint32_t total = 0;
+    for (uint32_t i = 0; i < num_steps; i++) {
+        s.reduction_arity_bits[i] = reduction_arity_bits ? reduction_arity_bits[i] : 1u;
+        total += s.reduction_arity_bits[i];
+    }
+    if (total > degree_bits) return -2;
+    s.final_poly_len = 1u << (degree_bits - total);
     s.hiding = hiding ? 1 : 0;
     s.oracle_num_polys[0] = c->num_constants + c->num_routed_wires;
     s.oracle_num_polys[1] = c->num_wires;

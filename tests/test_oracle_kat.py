@@ -109,6 +109,8 @@ def test_oracle_accepts_full_shape_golden_proofs(orc):
         s = orc.OrcShape()
         s.degree_bits, s.rate_bits, s.cap_height, s.num_query_rounds, s.proof_of_work_bits = deg, rate, 4, q, 16
         s.num_steps, s.final_poly_len, s.hiding = deg - 5, 32, 0
+        for i in range(deg - 5):
+            s.reduction_arity_bits[i] = 1            # ConstantArityBits(1, 5)
         s.oracle_num_polys = (ctypes.c_uint32 * 4)(84, 135, 20, 16)
         s.oracle_blinding = (ctypes.c_uint32 * 4)(0, 1, 1, 1)
         s.num_zs, s.hash_kind = 2, 0

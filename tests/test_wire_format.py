@@ -276,7 +276,7 @@ def test_host_entry_points_report_bad_arguments(svb):
     assert L.sv_wire_proof_bytes(None, ctypes.byref(c)) == 0
     assert L.sv_public_inputs_hash(None, 3, p(cap)) == -1
     out = svb.FriShape()
-    assert L.sv_fri_shape_from_common(ctypes.byref(c), 4, 3, 1, 5, 2, 9, 0, 0, ctypes.byref(out)) == -2                                 # more steps than degree bits
+    assert L.sv_fri_shape_from_common(ctypes.byref(c), 4, 3, 1, 5, 2, 9, None, 0, 0, ctypes.byref(out)) == -2                                 # more steps than degree bits
     assert L.sv_ntt_host(0, 1, p(recs), 0, 1) == -2 and L.sv_ntt_host(3, 1, None, 0, 1) == -1
     assert L.sv_plonk_gate_from_id(None, None) == -1
     assert L.sv_plonk_check_host(ctypes.byref(s), None, 1, p(recs), p(cap), p(cap), p(cap), 1) == -1

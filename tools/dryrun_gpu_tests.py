@@ -82,8 +82,21 @@ class MockCtx:
         return self._verify(common, circuit, cap, cd, blob, n_proofs, stride, want_fail)
 
     # -- records ---------------------------------------------------------------------------------
-    def fri_verify_batch(self, params, recs, n=None, **kw):
-        return orc.fri_verify_batch(orc.shape_from(params.to_shape()), recs)
+    def fri_verify_batch(self, params, recs, n=None, want_fail=False, **kw):
+        osh = orc.shape_from(params.to_shape())
+        bm = orc.fri_verify_batch(osh, recs)
+        if not want_fail:
+            return bm
+        ff = np.zeros(recs.shape[0], dtype=np.uint32)
+        for i in range(recs.shape[0]):
+            ok, code, q = orc.fri_verify(osh, recs[i])
+            ff[i] = 0 if ok else (max(q, 0) << 8) | code
+        return bm, ff
+
+    def fri_challenges_batch(self, params, recs, cd, pih, num_challenges=2, **kw):
+        for i in range(recs.shape[0]):
+            svb.fri_challenges(params, recs[i], cd, pih[i], num_challenges)
+        return recs
 
     def fri_verify_batch_fs(self, params, recs, cd, pih, num_challenges=2, **kw):
         r = recs.copy()
@@ -167,7 +180,9 @@ def run(fn, fixtures):
 
 
 def main():
+    import test_gpu_arity as t_ar
     import test_gpu_parity_python_prover as t_pp
+    import test_gpu_pyref_golden as t_gold
     import test_gpu_plonk as t_plonk
     import test_gpu_transforms as t_tr
     import test_gpu_verify_full as t_full
@@ -176,7 +191,7 @@ def main():
     fx = dict(svb=svb, orc=orc, ctx=ctx)
     skip = {"test_unpack_kernel_device_memory", "test_plonk_kernel_device_memory", "test_ntt_device_memory_and_many_polys"}  # need torch.cuda
     total = 0
-    for mod in (t_pp, t_plonk, t_tr, t_full, t_wire):
+    for mod in (t_gold, t_ar, t_pp, t_plonk, t_tr, t_full, t_wire):
         for name in sorted(n for n in dir(mod) if n.startswith("test_") and n not in skip):
             f = dict(fx)
             if name == "test_verify_proofs_wire_many_chunks":

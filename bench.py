@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-wire", action="store_true", help="skip the serialised-proof leg of e2e")
     ap.add_argument("--wire-leg", action="store_true", help="(internal) run only the serialised-proof leg and print its JSON")
+    ap.add_argument("--transforms-leg", action="store_true", help="run only the commit-phase kernels (LDE, NTT, commitment) and print their JSON")
     ap.add_argument("--device-transcript", action="store_true",
                     help="derive the Fiat-Shamir challenges on the device too (sv_fri_verify_batch_fs): the records "
                          "enter with their challenge fields zeroed")
@@ -145,10 +146,10 @@ def workload_params(svb, name):
     return {"A": svb.SHAPE_A, "B": svb.SHAPE_B, "outer": svb.SHAPE_OUTER_BN254}[name]
 
 
-def cpu_baseline(svb, params, base, sample_proofs, threads):
+def cpu_baseline(params_shape, record_words, base, sample_proofs, threads):
     """The oracle (CPU restatement of the reference semantics; NOT the Rust binary) timed on the host cores."""
     from oracle import binding as orc
-    oshape = orc.shape_from(params.to_shape())
+    oshape = orc.shape_from(params_shape)
     n = base.shape[0]
     reps = (sample_proofs + n - 1) // n
     recs = np.ascontiguousarray(np.tile(base, (reps, 1))[:sample_proofs])
@@ -156,27 +157,64 @@ def cpu_baseline(svb, params, base, sample_proofs, threads):
     t = time.perf_counter()
     bm = orc.fri_verify_batch(oshape, recs, nthreads=threads)
     dt = time.perf_counter() - t
-    return sample_proofs / dt, dt, bm
+    return sample_proofs / dt, dt, bm, recs
+
+
+WORKLOAD_TEXT = {"A": "BASELINE configs[1]: {n} proofs/GPU/step, shape A", "B": "BASELINE configs[2]: {n} proofs/GPU/step, shape B",
+                 "outer": "outer wrapped-proof configuration (Poseidon-BN254 hash, cap_height 0): {n} proofs/GPU/step"}
+# (degree_bits, rate_bits, cap_height, pow_bits, queries, hash_kind) of the bench workloads: the reference arm builds its shape
+# from these numbers alone, so that it never has to load the product library
+WORKLOAD_SHAPE = {"A": (12, 3, 4, 16, 28, 0), "B": (20, 2, 4, 16, 84, 0), "outer": (12, 3, 0, 16, 28, 1)}
+
+
+def workload_config(wl, n, distinct, record_bytes, world, transcript, corrupted):
+    d, r, c, pw, q, kind = WORKLOAD_SHAPE[wl]
+    return {"workload": WORKLOAD_TEXT[wl].format(n=n), "hash_kind": kind, "trace_bits": d, "fri_queries": q, "blowup": 1 << r,
+            "cap_height": c, "pow_bits": pw, "reduction_arity_bits": [1] * (d - 5), "proofs_per_gpu": n, "distinct_base_proofs": distinct,
+            "record_bytes": record_bytes, "l2_policy": f"inputs larger than L2 ({n * record_bytes / 1e6:.0f} MB/GPU resident, physically distinct copies)",
+            "sharding": f"proofs sharded over {world} ranks; all-gather of the accept bitmap only", "corrupted": corrupted,
+            "transcript": transcript}
+
+
+def reference_fixture(wl):
+    """One valid proof of the workload's shape as a flat record, from a committed fixture (no product code runs):
+    A = the pure-Python prover's shape-A proof (tests/golden/pyref_fri.npz, tools/gen_golden_pyref.py), B / outer = the
+    round-1 fixtures of the product's host prover (tests/golden/fri_full_shapes.npz, fri_outer_shape.npz)."""
+    g = os.path.join(ROOT, "tests", "golden")
+    if wl == "A":
+        return np.load(os.path.join(g, "pyref_fri.npz"))["shape_a_records"][:1].copy()
+    if wl == "B":
+        return np.load(os.path.join(g, "fri_full_shapes.npz"))["shape_b_record"][None, :].copy()
+    return np.load(os.path.join(g, "fri_outer_shape.npz"))["record"][None, :].copy()
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path.  The Rust crate cannot be built in this image (no
-    cargo/rustc, dependencies not on disk), so this times the oracle port on all host threads."""
+    """--impl reference: the reference's CPU path.  The Rust crate cannot be built in this image (no cargo/rustc,
+    dependencies not on disk), so this times the oracle port on all host threads -- on committed fixture proofs: the product
+    library (libsvb200.so) is never loaded by this arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import stark_verifier_b200 as svb
+    from oracle import binding as orc
     wl = "A" if args.workload == "merkle" else args.workload
-    params = workload_params(svb, wl)
-    L = svb.api.make_layout(params)
+    d, r, c, pw, q, kind = WORKLOAD_SHAPE[wl]
+    oshape = orc.OrcShape()
+    oshape.degree_bits, oshape.rate_bits, oshape.cap_height, oshape.num_query_rounds, oshape.proof_of_work_bits = d, r, c, q, pw
+    oshape.num_steps, oshape.final_poly_len, oshape.hiding = d - 5, 32, 0
+    for i, w in enumerate((84, 135, 20, 16)):
+        oshape.oracle_num_polys[i] = w
+        oshape.oracle_blinding[i] = int(i > 0)
+    oshape.num_zs, oshape.hash_kind = 2, kind
+    for i in range(d - 5):
+        oshape.reduction_arity_bits[i] = 1
+    oL = orc.layout(oshape)
     threads = os.cpu_count() or 1
-    distinct = args.distinct or {"A": 16, "B": 2, "outer": 2}[wl]
-    base = svb.synth_proofs(params, distinct, seed=0xB2000002, n_circuits=1 if wl == "outer" else min(4, distinct), nthreads=threads)
+    base = reference_fixture(wl)
+    assert base.shape[1] == oL.record_words
     sample = args.cpu_sample or {"A": 64 * threads, "B": 2 * threads, "outer": max(2, threads // 4)}[wl]
     n_gpu_arm = args.proofs or (4096 if wl == "A" else 256)
-    from oracle import binding as orc
-    oshape = orc.shape_from(params.to_shape())
-    recs = np.ascontiguousarray(np.tile(base, ((sample + distinct - 1) // distinct, 1))[:sample])
+    distinct = args.distinct or {"A": 256, "B": 2, "outer": 4}[wl]
+    recs = np.ascontiguousarray(np.tile(base, (sample, 1)))
     for _ in range(args.warmup):
         orc.fri_verify_batch(oshape, recs[:threads], nthreads=threads)
     t = time.perf_counter()
@@ -190,23 +228,25 @@ def run_reference(args):
     t = time.perf_counter()
     orc.fri_verify_batch(oshape, recs[:n1], nthreads=1)
     v1 = n1 / (time.perf_counter() - t)
-    perms_per_proof = params.config.num_query_rounds * L.perms_per_query
+    leaf = [84, 135, 20, 16]
+    lde = d + r
+    perms_per_query = sum((x + 7) // 8 for x in leaf) + 4 * (lde - c) + sum(lde - (i + 1) - c for i in range(d - 5))
+    perms_per_proof = q * perms_per_query
     cpu = open("/proc/cpuinfo").read().split("model name")[1].split("\n")[0].strip(": \t") if os.path.exists("/proc/cpuinfo") else "?"
+    cfg = workload_config(wl, n_gpu_arm, distinct, oL.record_words * 8, args.gpus, "n/a (the CPU arm verifies records whose challenges are filled in)",
+                          "none in this arm")
+    cfg["sample"] = f"each step verifies a bounded sample of {sample} proofs of that workload on the host CPU"
     print(json.dumps({
         "impl": "reference", "metric": "plonky2_proofs_verified_per_sec", "value": v, "unit": "proofs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": {"A": f"BASELINE configs[1]: {n_gpu_arm} proofs/GPU/step, shape A",
-                                "B": f"BASELINE configs[2]: {n_gpu_arm} proofs/GPU/step, shape B",
-                                "outer": f"outer wrapped-proof configuration (Poseidon-BN254 hash, cap_height 0): {n_gpu_arm} proofs/GPU/step"}[wl],
-                   "hash_kind": params.hash_kind, "trace_bits": params.degree_bits, "fri_queries": params.config.num_query_rounds,
-                   "blowup": 1 << params.config.rate_bits, "cap_height": params.config.cap_height,
-                   "pow_bits": params.config.proof_of_work_bits,
-                   "sample": f"each step verifies a bounded sample of {sample} proofs of that workload on the host CPU"},
+        "config": cfg,
         "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": threads, "kind": "port",
                          "perms_per_sec": v * perms_per_proof, "single_thread_value": v1, "single_thread_perms_per_sec": v1 * perms_per_proof,
+                         "perm_ns_per_thread": 1e9 / (v1 * perms_per_proof),
                          "sample": f"{sample} proofs x {args.steps} steps, oracle/oracle.c on {threads} threads ({cpu}); "
-                                   "CPU restatement of reference semantics, not the Rust binary"},
+                                   "CPU restatement of reference semantics, not the Rust binary; inputs: committed fixture proof, "
+                                   "the product library is not loaded"},
         "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -291,47 +331,68 @@ def full_leg(svb, torch, ctx, params, common, vk_cap, cd, ptr, n_host, steps):
         return {"error": f"{type(ex).__name__}: {ex}"}
 
 
-def transforms_leg(svb, torch, ctx, params, steps):
-    """Throughput of the commit-phase kernels on device-resident data: the LDE of the workload's wires oracle (135 columns
-    of 2^degree_bits coefficients -> 2^lde_bits points), a 2^22-point NTT (3 passes), and the one-call commitment."""
+def transforms_leg(svb, torch, ctx, params, steps, big_polys=64):
+    """Throughput of the commit-phase kernels on device-resident data, timed with CUDA events on the launching stream: the LDE
+    of the workload's wires oracle (135 columns of 2^degree_bits coefficients -> 2^lde_bits points, one pass), a batch of
+    2^22-point NTTs (two passes of 16 B per element each), the same inverse, and the one-call commitment."""
     import ctypes
     out = {}
     try:
+        peak, _ = measured_peak_gbs()
         k, rb = params.degree_bits, params.config.rate_bits
         ncol = params.oracle_num_polys[1]
         n, N = 1 << k, 1 << (k + rb)
         g = torch.Generator(device="cuda").manual_seed(1)
         coeffs = torch.randint(0, 2**62, (ncol, n), dtype=torch.int64, device="cuda", generator=g)
         lde = torch.empty((ncol, N), dtype=torch.int64, device="cuda")
-        big = torch.randint(0, 2**62, (4, 1 << 22), dtype=torch.int64, device="cuda", generator=g)
+        big = torch.randint(0, 2**62, (big_polys, 1 << 22), dtype=torch.int64, device="cuda", generator=g)
+        stream = torch.cuda.Stream()
         torch.cuda.synchronize()            # torch filled the buffers on its own stream
+        ctx.set_stream(stream.cuda_stream)
 
         def timed(fn, reps):
-            for _ in range(2):
+            for _ in range(3):
                 fn()
-            ctx.synchronize()
-            t0 = time.perf_counter()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            stream.synchronize()
+            ev0.record(stream)
             for _ in range(reps):
                 fn()
-            ctx.synchronize()
-            return (time.perf_counter() - t0) / reps
+            ev1.record(stream)
+            stream.synchronize()
+            return ev0.elapsed_time(ev1) / 1e3 / reps
 
-        t = timed(lambda: ctx.lde_batch(coeffs.data_ptr(), rb, log_n=k, n_polys=ncol, out=lde.data_ptr(), mem=svb.MEM_DEVICE), steps)
-        out["lde"] = {"ms": 1e3 * t, "polys": ncol, "log_n": k, "log_N": k + rb, "out_gbs": ncol * N * 8 / t / 1e9}
-        t = timed(lambda: ctx.ntt_batch(big.data_ptr(), log_n=22, n_polys=4, mem=svb.MEM_DEVICE), steps)
-        out["ntt_2^22"] = {"ms": 1e3 * t, "polys": 4, "passes": 3, "algorithmic_gbs": 4 * (1 << 22) * 16 * 3 / t / 1e9}
+        t = timed(lambda: ctx.lde_batch(coeffs.data_ptr(), rb, log_n=k, n_polys=ncol, out=lde.data_ptr(), mem=svb.MEM_DEVICE), max(steps, 20))
+        lde_bytes = ncol * (n + N) * 8
+        out["lde"] = {"ms": 1e3 * t, "polys": ncol, "log_n": k, "log_N": k + rb, "passes": 1, "algorithmic_bytes": lde_bytes,
+                      "algorithmic_gbs": lde_bytes / t / 1e9, "frac_of_hbm": lde_bytes / t / 1e9 / peak, "out_gbs": ncol * N * 8 / t / 1e9}
+        passes = 2
+        ntt_bytes = big_polys * (1 << 22) * 16 * passes
+        t = timed(lambda: ctx.ntt_batch(big.data_ptr(), log_n=22, n_polys=big_polys, mem=svb.MEM_DEVICE), steps)
+        out["ntt_2^22"] = {"ms": 1e3 * t, "polys": big_polys, "passes": passes, "algorithmic_bytes": ntt_bytes,
+                           "algorithmic_gbs": ntt_bytes / t / 1e9, "frac_of_hbm": ntt_bytes / t / 1e9 / peak,
+                           "elements_per_s": big_polys * (1 << 22) / t,
+                           "note": "round 1 ran this transform in 3 passes (48 B per element): its 578 GB/s were 1.39 ms per 4 polynomials"}
+        t = timed(lambda: ctx.ntt_batch(big.data_ptr(), log_n=22, n_polys=big_polys, inverse=True, mem=svb.MEM_DEVICE), steps)
+        out["intt_2^22"] = {"ms": 1e3 * t, "polys": big_polys, "passes": passes, "algorithmic_gbs": ntt_bytes / t / 1e9,
+                            "frac_of_hbm": ntt_bytes / t / 1e9 / peak}
+        del big
         leaves = torch.empty((N, ncol), dtype=torch.int64, device="cuda")
         cap_h = params.config.cap_height
         layers = torch.empty(4 * (2 * N - (1 << cap_h)), dtype=torch.int64, device="cuda")
         vp = ctypes.c_void_p
 
-        def commit():
-            rc = ctx._lib.sv_commit_batch(ctx._h, k, rb, ncol, vp(coeffs.data_ptr()), cap_h, params.hash_kind, vp(leaves.data_ptr()),
-                                          vp(layers.data_ptr()), svb.MEM_DEVICE)
+        def commit(want_leaves):
+            rc = ctx._lib.sv_commit_batch(ctx._h, k, rb, ncol, vp(coeffs.data_ptr()), cap_h, params.hash_kind,
+                                          vp(leaves.data_ptr()) if want_leaves else None, vp(layers.data_ptr()), svb.MEM_DEVICE)
             if rc != 0:
                 raise RuntimeError(f"sv_commit_batch failed: {rc}")
-        t = timed(commit, steps)
-        out["commit"] = {"ms": 1e3 * t, "leaves": N, "leaf_len": ncol, "note": "LDE + leaf-major copy + Merkle tree of one oracle"}
+        t = timed(lambda: commit(False), steps)
+        t2 = timed(lambda: commit(True), steps)
+        perms = N * ((ncol + 7) // 8) + (N - (1 << cap_h))
+        out["commit"] = {"ms": 1e3 * t, "ms_with_leaf_major_copy": 1e3 * t2, "leaves": N, "leaf_len": ncol, "permutations": perms,
+                         "perms_per_s": perms / t, "note": "LDE + leaf digests straight from the polynomial-major values + Merkle levels of one oracle"}
+        ctx.set_stream(0)
     except Exception as ex:   # noqa: BLE001
         out["error"] = f"{type(ex).__name__}: {ex}"
     return out
@@ -390,6 +451,13 @@ def main():
         return run_reference(args)
     if args.wire_leg:
         return run_wire_leg(args)
+    if args.transforms_leg:
+        import torch
+        import stark_verifier_b200 as svb
+        torch.cuda.set_device(0)
+        print(json.dumps(transforms_leg(svb, torch, svb.Context(0), workload_params(svb, "A" if args.workload == "merkle" else args.workload),
+                                        max(3, min(args.steps, 10)))))
+        return
 
     import torch
     import torch.distributed as dist

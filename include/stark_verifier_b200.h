@@ -381,7 +381,7 @@ int sv_verify_proofs_full(sv_ctx* ctx, const sv_fri_shape* shape, const sv_plonk
  * 7^((p-1)/2^log_n)) -- the order in which plonky2 puts evaluations into Merkle leaves and the FRI verifier reads them
  * back (chip/fri_chip.rs:152-166, 262-264).  inverse = 1: the reverse, 1/n included.
  * Replaces: plonky2_field's fft / ifft as used by the prover side of the reference (the plonky2_semaphore module, not on the
- * verifier's hot path); shared-memory tiled, 2-3 HBM passes per transform. */
+ * verifier's hot path); shared-memory tiled radix-8 rounds: 1 HBM pass up to 2^13 points, 2 up to 2^22. */
 int sv_ntt_batch(sv_ctx* ctx, uint32_t log_n, size_t n_polys, uint64_t* data, int inverse, int mem);
 /* out[p][i] = f_p(shift * omega_N^bitrev(i)), N = 2^(log_n + rate_bits): the low-degree extension of n_polys coefficient
  * vectors onto the coset shift * <omega_N>, in Merkle-leaf order (plonky2: PolynomialBatch::from_coeffs / lde_values with
@@ -390,7 +390,7 @@ int sv_lde_batch(sv_ctx* ctx, uint32_t log_n, uint32_t rate_bits, size_t n_polys
                  uint64_t* out, int mem);
 /* The prover's commitment to n_polys polynomials in one call: LDE onto 7 * <omega_N> (sv_lde_batch), leaves = one row of
  * n_polys values per evaluation point (a transposing copy), Merkle tree down to the cap (sv_merkle_tree_build).
- * leaves_out: N x n_polys words (NULL: not wanted; SV_MEM_DEVICE needs it as scratch, so it must be given there);
+ * leaves_out: N x n_polys words (NULL: not wanted -- the leaf digests are hashed straight from the polynomial-major values);
  * layers_out: 4 * (2N - 2^cap_height) words as in sv_merkle_tree_build.
  * Replaces: plonky2 PolynomialBatch::from_coeffs (LDE + MerkleTree::new), the commit step of the reference's prover side. */
 int sv_commit_batch(sv_ctx* ctx, uint32_t log_n, uint32_t rate_bits, size_t n_polys, const uint64_t* coeffs, uint32_t cap_height,

@@ -34,6 +34,7 @@ struct sv_ctx {
     u32* d_bitmap = nullptr; size_t bitmap_words = 0;
     u32* d_fail = nullptr; size_t fail_words = 0;
     u64* d_pi = nullptr; size_t pi_words = 0;                          // public-input hashes (device-side transcript)
+    u64 *d_hfront = nullptr, *d_hback = nullptr; size_t hfront_words = 0, hback_words = 0;   // header byte spans of a wire batch
     u64* d_hdr = nullptr; size_t hdr_words = 0;                        // record headers of a whole host batch (transcript)
     cudaStream_t fs_stream = nullptr;                                  // the batch-wide transcript of the host pipeline
     cudaEvent_t ev_hdr = nullptr, ev_fs = nullptr;
@@ -52,7 +53,9 @@ struct sv_ctx {
     u64* d_chal = nullptr; size_t chal_words = 0;
     u32* d_pbm = nullptr; size_t pbm_words = 0;
     // NTT twiddles of the last (log_n, direction) used
-    u64* d_tw = nullptr; size_t tw_words = 0; u32 tw_k = 0; int tw_inverse = -1;                        // plonk-identity bitmap of sv_verify_proofs_full
+    u64* d_tw = nullptr; size_t tw_words = 0; u32 tw_k = 0; int tw_inverse = -1;
+    u64 *d_lde_lo = nullptr, *d_lde_hi = nullptr; size_t lde_lo_words = 0, lde_hi_words = 0; u32 lde_log_n = 0, lde_rate_bits = 0; u64 lde_shift = 0;   // LDE scale tables (ntt.hpp)
+                           // plonk-identity bitmap of sv_verify_proofs_full
     uint64_t launches = 0;
     // optional CUDA-event timing of the dominant kernel (fri_query_kernel / merkle / permute), on
     // the stream it is launched on
@@ -156,6 +159,8 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaFree(c->d_fail);
     cudaFree(c->d_pi);
     cudaFree(c->d_hdr);
+    cudaFree(c->d_hfront);
+    cudaFree(c->d_hback);
     cudaFree(c->d_wtab);
     cudaFree(c->d_wvk);
     for (int i = 0; i < SV_NBUF; i++) cudaFree(c->d_wire[i]);
@@ -164,6 +169,8 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaFree(c->d_chal);
     cudaFree(c->d_pbm);
     cudaFree(c->d_tw);
+    cudaFree(c->d_lde_lo);
+    cudaFree(c->d_lde_hi);
     auto drop_s = [](cudaStream_t s) { if (s) cudaStreamDestroy(s); };
     auto drop_e = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
     drop_e(c->ev_hdr); drop_e(c->ev_fs);
@@ -690,7 +697,7 @@ static int enqueue_unpack(sv_ctx* c, const WireDev& W, const u64* d_blob8, size_
                           u64* d_pi, u32* d_mal, cudaStream_t s) {
     CK(c, cudaMemsetAsync(d_mal, 0, n * 4, s));
     dim3 grid((unsigned)n, 1 + W.d.num_queries);   // per proof: one block for the header, one per query round
-    wire_unpack_kernel<<<grid, SVB_WIRE_BLOCK, 0, s>>>(d_blob8, first_off, stride, W.d, W.hdr_src, W.q_src, W.chk, W.vk, d_records, d_mal);
+    wire_unpack_kernel<<<grid, SVB_WIRE_BLOCK, 0, s>>>(d_blob8, first_off, stride, W.d, W.hdr_src, W.q_src, W.chk, W.vk, d_records, d_mal, nullptr);
     c->launches++;
     if (d_pi) {
         wire_pi_hash_kernel<<<(unsigned)((n + SVB_BLOCK - 1) / SVB_BLOCK), SVB_BLOCK, 0, s>>>(d_blob8, first_off, stride, W.d, n, d_pi, d_mal);
@@ -735,14 +742,20 @@ extern "C" int sv_wire_unpack_batch_gpu(sv_ctx* c, const sv_fri_shape* shape, co
     return 0;
 }
 
-// The pipeline of fri_verify_host with wire bytes as its input: H2D of a chunk's bytes on the copy stream; on the
-// chunk's compute stream unpack -> public-input hashes -> transcript -> prepare + query -> reject malformed.
+// The pipeline of fri_verify_host with wire bytes as its input, headers first:
+//   copy stream   the two header spans of EVERY proof (strided copies), then chunk after chunk of query-round bytes
+//   fs stream     once per batch, beside those copies: gather the packed headers, hash the public inputs, (plonk
+//                 challenges,) the Fiat-Shamir transcript -- ~85 dependent permutations per proof, latency-bound, so it
+//                 must not run per chunk -- (and the vanishing-polynomial identity, which only reads headers)
+//   compute       per chunk, rotating over SV_NKS streams: gather the query rounds + copy in the finished header ->
+//                 prepare + query kernels -> (AND with the identity) -> reject malformed
+static inline size_t up8(size_t x) { return (x + 7) & ~(size_t)7; }
 static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, const sv_fri_shape& shape, const sv_plonk_common& common,
                             const uint64_t* vk_cap, const uint8_t* blob, size_t stride, size_t n_proofs, uint32_t* accept_bitmap,
                             uint32_t* first_fail, const sv_plonk_circuit* circuit) {
     int rc = 0;
-    const size_t rw = P.L.record_words;
-    cudaStream_t cs = c->copy_stream;
+    const size_t rw = P.L.record_words, hw = P.L.header_words;
+    cudaStream_t cs = c->copy_stream, fss = c->fs_stream;
     WireDev W;
     if ((rc = wire_tables(c, shape, common, vk_cap, cs, W))) return rc;
     const u32 nch = common.num_challenges;
@@ -757,6 +770,13 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
     if (first_fail && grow(c, c->d_fail, c->fail_words, n_proofs)) return -6;
     if (grow(c, c->d_pi, c->pi_words, 4 * n_proofs)) return -6;
     if (grow(c, c->d_mal, c->mal_words, n_proofs)) return -6;
+    if (grow(c, c->d_hdr, c->hdr_words, n_proofs * hw)) return -6;
+    // the three byte spans of a proof and the pitches of their packed device copies (rows start 8-byte aligned)
+    const size_t front_bytes = W.d.query_base, q_bytes = (size_t)W.d.num_queries * W.d.query_bytes;
+    const size_t back_off = front_bytes + q_bytes, back_bytes = W.d.proof_bytes - back_off;
+    const size_t front_pitch = up8(front_bytes) + 8, back_pitch = up8(back_bytes) + 8, q_pitch = up8(q_bytes) + 8;
+    if (grow(c, c->d_hfront, c->hfront_words, n_proofs * front_pitch / 8 + 2)) return -6;
+    if (grow(c, c->d_hback, c->hback_words, n_proofs * back_pitch / 8 + 2)) return -6;
     size_t chunk_mb = 32;
     int n_ks = SV_NKS;
     if (const char* e = getenv("SVB_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 4096) chunk_mb = (size_t)v; }
@@ -766,8 +786,43 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
     if (chunk > n_proofs) chunk = (n_proofs + 31) & ~(size_t)31;
     for (int b = 0; b < SV_NBUF; b++) {
         if (grow(c, c->d_stage[b], c->stage_words[b], chunk * rw)) return -6;
-        if (grow(c, c->d_wire[b], c->wire_words[b], (chunk * std::max(stride, (size_t)W.d.proof_bytes)) / 8 + 2)) return -6;
+        if (grow(c, c->d_wire[b], c->wire_words[b], chunk * q_pitch / 8 + 2)) return -6;
     }
+    // ---- headers first -------------------------------------------------------------------------------------
+    CK(c, cudaMemcpy2DAsync(c->d_hfront, front_pitch, blob, stride, front_bytes, n_proofs, cudaMemcpyHostToDevice, cs));
+    CK(c, cudaMemcpy2DAsync(c->d_hback, back_pitch, blob + back_off, stride, back_bytes, n_proofs, cudaMemcpyHostToDevice, cs));
+    CK(c, cudaEventRecord(c->ev_hdr, cs));
+    CK(c, cudaStreamWaitEvent(fss, c->ev_hdr, 0));
+    CK(c, cudaMemsetAsync(c->d_mal, 0, n_proofs * 4, fss));
+    wire_header_unpack_kernel<<<(unsigned)n_proofs, SVB_WIRE_BLOCK, 0, fss>>>(c->d_hfront, front_pitch, c->d_hback, back_pitch, (u32)front_bytes,
+                                                                               (u32)back_off, (u32)hw, W.hdr_src, W.vk, c->d_hdr);
+    {
+        WireDims db = W.d;
+        db.pi_off = (u32)(W.d.pi_off - back_off);          // the public inputs inside the back span
+        wire_pi_hash_kernel<<<(unsigned)((n_proofs + SVB_BLOCK - 1) / SVB_BLOCK), SVB_BLOCK, 0, fss>>>(c->d_hback, 0, back_pitch, db, n_proofs,
+                                                                                                       c->d_pi, c->d_mal);
+    }
+    c->launches += 2;
+    FriKernelParams Ph = P;
+    Ph.L.record_words = (u32)hw;                            // the headers are packed back to back
+    if (circuit) {   // plonk challenges: the prefix of the transcript below, kept this time
+        Ph.n_proofs = (u32)n_proofs;
+        SVB_LAUNCH_KIND(P.hash_kind, plonk_challenges_kernel, (unsigned)((n_proofs + SVB_FS_BLOCK - 1) / SVB_FS_BLOCK), SVB_FS_BLOCK, fss,
+                        c->d_hdr, Ph, F, c->d_pi, c->d_chal);
+        c->launches++;
+    }
+    if ((rc = enqueue_challenges(c, Ph, F, n_proofs, c->d_hdr, c->d_pi, fss))) return rc;
+    if (circuit) {   // the vanishing-polynomial identity reads headers only (zeta is in them now)
+        PlonkRecordView V = {(u32)hw, P.L.off_open0, P.L.off_open1, P.L.off_zeta};
+        plonk_check_kernel<<<(unsigned)((n_proofs + 127) / 128), 128, 0, fss>>>(c->d_hdr, V, c->d_circuit, c->d_pi, c->d_chal, (u32)n_proofs,
+                                                                                  c->d_pbm);
+        c->launches++;
+    }
+    CK(c, cudaGetLastError());
+    CK(c, cudaEventRecord(c->ev_fs, fss));
+    // ---- query rounds, chunk by chunk ------------------------------------------------------------------------
+    WireDims dq = W.d;
+    dq.query_base = 0;                                      // a chunk buffer row holds the query rounds only
     cudaStream_t ks[SV_NKS] = {c->own_stream};
     for (int i = 1; i < SV_NKS; i++) ks[i] = c->aux_stream[i - 1];
     size_t n_chunks = (n_proofs + chunk - 1) / chunk;
@@ -775,27 +830,20 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
         int b = (int)(i % SV_NBUF);
         cudaStream_t k = ks[i % n_ks];
         size_t first = i * chunk, cnt = std::min(chunk, n_proofs - first);
-        size_t bytes = (cnt - 1) * stride + W.d.proof_bytes;
         if (i >= SV_NBUF) CK(c, cudaStreamWaitEvent(cs, c->ev_done[b], 0));   // buffers b free again
-        CK(c, cudaMemcpyAsync(c->d_wire[b], blob + first * stride, bytes, cudaMemcpyHostToDevice, cs));
+        CK(c, cudaMemcpy2DAsync(c->d_wire[b], q_pitch, blob + first * stride + front_bytes, stride, q_bytes, cnt, cudaMemcpyHostToDevice, cs));
         CK(c, cudaEventRecord(c->ev_copied[b], cs));
         CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
-        if ((rc = enqueue_unpack(c, W, c->d_wire[b], 0, stride, cnt, c->d_stage[b], c->d_pi + 4 * first, c->d_mal + first, k))) return rc;
-        if (circuit) {   // plonk challenges: the prefix of the transcript below, kept this time
-            P.n_proofs = (u32)cnt;
-            SVB_LAUNCH_KIND(P.hash_kind, plonk_challenges_kernel, (unsigned)((cnt + SVB_FS_BLOCK - 1) / SVB_FS_BLOCK), SVB_FS_BLOCK, k,
-                            c->d_stage[b], P, F, c->d_pi + 4 * first, c->d_chal + 3 * (size_t)nch * first);
-            c->launches++;
-        }
-        if ((rc = enqueue_challenges(c, P, F, cnt, c->d_stage[b], c->d_pi + 4 * first, k))) return rc;
+        CK(c, cudaStreamWaitEvent(k, c->ev_fs, 0));
+        dim3 grid((unsigned)cnt, 1 + W.d.num_queries);
+        wire_unpack_kernel<<<grid, SVB_WIRE_BLOCK, 0, k>>>(c->d_wire[b], 0, q_pitch, dq, W.hdr_src, W.q_src, W.chk, W.vk, c->d_stage[b],
+                                                           c->d_mal + first, c->d_hdr + first * hw);
+        c->launches++;
         u32* d_fail = first_fail ? c->d_fail + first : nullptr;
         if ((rc = enqueue_fri(c, P, cnt, c->d_stage[b], c->d_scratch + 4 * first, c->d_bitmap + first / 32, d_fail, k))) return rc;
-        if (circuit) {   // the vanishing-polynomial identity (zeta is in the record header now), ANDed into the verdict
-            PlonkRecordView V = {P.L.record_words, P.L.off_open0, P.L.off_open1, P.L.off_zeta};
-            plonk_check_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, k>>>(c->d_stage[b], V, c->d_circuit, c->d_pi + 4 * first,
-                                                                              c->d_chal + 3 * (size_t)nch * first, (u32)cnt, c->d_pbm + first / 32);
+        if (circuit) {
             plonk_and_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, k>>>(c->d_pbm + first / 32, c->d_bitmap + first / 32, d_fail, (u32)cnt);
-            c->launches += 2;
+            c->launches++;
         }
         wire_reject_malformed_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, k>>>(c->d_mal + first, c->d_bitmap + first / 32, d_fail, (u32)cnt);
         c->launches++;
@@ -920,22 +968,67 @@ static int ntt_twiddles_dev(sv_ctx* c, u32 k, bool inverse, cudaStream_t s) {
     c->tw_inverse = (int)inverse;
     return 0;
 }
+// the LDE scale tables of (log_n, rate_bits, shift), cached like the twiddles
+static int lde_tables_dev(sv_ctx* c, u32 log_n, u32 rate_bits, u64 shift, cudaStream_t s) {
+    if (c->d_lde_lo && c->lde_log_n == log_n && c->lde_rate_bits == rate_bits && c->lde_shift == shift) return 0;
+    if (int rc = sv_ctx_synchronize(c)) return rc;
+    const u32 h = lde_scale_h(log_n);
+    const size_t lo_words = (size_t)1 << (rate_bits + h), hi_words = (size_t)1 << (rate_bits + log_n - h);
+    if (grow(c, c->d_lde_lo, c->lde_lo_words, lo_words) || grow(c, c->d_lde_hi, c->lde_hi_words, hi_words)) return -6;
+    std::vector<u64> lo(lo_words), hi(hi_words);
+    lde_scale_tables(log_n, rate_bits, shift, lo.data(), hi.data());
+    CK(c, cudaMemcpyAsync(c->d_lde_lo, lo.data(), lo_words * 8, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(c->d_lde_hi, hi.data(), hi_words * 8, cudaMemcpyHostToDevice, s));
+    CK(c, cudaStreamSynchronize(s));
+    c->lde_log_n = log_n; c->lde_rate_bits = rate_bits; c->lde_shift = shift;
+    return 0;
+}
+
+static int launch_ntt_pass(sv_ctx* c, const NttPass& P, size_t items, const u64* src, size_t src_stride, u64* dst, size_t dst_stride,
+                           cudaStream_t s) {
+    static bool attr_set = false;
+    const size_t smem = (size_t)(((size_t)1 << P.logT) + ((size_t)1 << P.logT >> 3) + 8) * 8;
+    if (!attr_set) {
+        CK(c, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NTT_SMEM_WORDS * 8 + 64)));
+        attr_set = true;
+    }
+    const u64 blocks = (u64)items << (P.k - P.logT);
+    if (blocks >= (1ull << 31)) return fail(c, -8, "transform batch too large for one launch");
+    ntt_pass_kernel<<<(unsigned)blocks, NTT_THREADS, smem, s>>>(src, src_stride, dst, dst_stride, c->d_tw, c->d_lde_lo, c->d_lde_hi, P,
+                                                                 ntt_rounds(P));
+    c->launches++;
+    return 0;
+}
 
 static int enqueue_ntt(sv_ctx* c, u32 k, size_t n_polys, u64* d_data, bool inverse, cudaStream_t s) {
-    NttPass plan[8];
+    NttPass plan[NTT_MAX_PASSES];
     int np = ntt_plan(k, inverse, plan);
     if (np < 0) return fail(c, -8, "bad transform size 2^%u", k);
-    if (n_polys > 65535) return fail(c, -8, "more than 65535 polynomials per call");
     if (int rc = ntt_twiddles_dev(c, k, inverse, s)) return rc;
+    const size_t n = (size_t)1 << k;
+    for (int q = 0; q < np; q++)
+        if (int rc = launch_ntt_pass(c, plan[q], n_polys, d_data, n, d_data, n, s)) return rc;
+    CK(c, cudaGetLastError());
+    return 0;
+}
+// coefficients (n_polys x 2^log_n, at d_in) -> values on shift * <omega_N> in leaf order (n_polys x N, at d_out): 2^rate_bits
+// size-n transforms per polynomial, the first pass reading the coefficients and scaling them on load (ntt.hpp)
+static int enqueue_lde(sv_ctx* c, u32 log_n, u32 rate_bits, size_t n_polys, const u64* d_in, u64 shift, u64* d_out, cudaStream_t s) {
+    NttPass plan[NTT_MAX_PASSES];
+    int np = ntt_plan(log_n, false, plan);
+    if (np < 0) return fail(c, -8, "bad transform size 2^%u", log_n);
+    if (int rc = ntt_twiddles_dev(c, log_n, false, s)) return rc;
+    if (int rc = lde_tables_dev(c, log_n, rate_bits, shift, s)) return rc;
+    const size_t n = (size_t)1 << log_n, items = n_polys << rate_bits;
     for (int q = 0; q < np; q++) {
-        dim3 grid((unsigned)ntt_blocks_per_poly(plan[q]), (unsigned)n_polys);
-        ntt_pass_kernel<<<grid, SVB_NTT_BLOCK, 0, s>>>(d_data, c->d_tw, plan[q]);
-        c->launches++;
-    }
-    if (inverse) {
-        const size_t total = n_polys << k;
-        ntt_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(d_data, total, inv(((u64)1 << k) % GL_P));
-        c->launches++;
+        NttPass P = plan[q];
+        if (q == 0) {
+            P.coset_bits = rate_bits;
+            P.scale_h = lde_scale_h(log_n);
+            P.load_scaled = 1;
+            if (int rc = launch_ntt_pass(c, P, items, d_in, n, d_out, n, s)) return rc;
+        } else if (int rc = launch_ntt_pass(c, P, items, d_out, n, d_out, n, s))
+            return rc;
     }
     CK(c, cudaGetLastError());
     return 0;
@@ -977,9 +1070,7 @@ extern "C" int sv_lde_batch(sv_ctx* c, uint32_t log_n, uint32_t rate_bits, size_
         d_in = c->d_stage[0];
         d_out = c->d_stage[1];
     }
-    lde_scale_pad_kernel<<<(unsigned)((out_words + 255) / 256), 256, 0, s>>>(d_in, d_out, log_n, log_N, n_polys, shift);
-    c->launches++;
-    if (int rc = enqueue_ntt(c, log_N, n_polys, d_out, false, s)) return rc;
+    if (int rc = enqueue_lde(c, log_n, rate_bits, n_polys, d_in, shift, d_out, s)) return rc;
     if (mem != SV_MEM_DEVICE) {
         CK(c, cudaMemcpyAsync(out, d_out, out_words * 8, cudaMemcpyDeviceToHost, s));
         CK(c, cudaStreamSynchronize(s));
@@ -993,35 +1084,35 @@ extern "C" int sv_commit_batch(sv_ctx* c, uint32_t log_n, uint32_t rate_bits, si
     if (!known_mem(mem)) return fail(c, -5, "mem %d is neither SV_MEM_HOST nor SV_MEM_DEVICE", mem);
     if (!known_kind(hash_kind)) return fail(c, -5, "hash_kind %d not implemented", hash_kind);
     if (log_n == 0 || log_n + rate_bits > 26 || cap_height > log_n + rate_bits) return fail(c, -8, "bad commit parameters");
-    if (mem == SV_MEM_DEVICE && !leaves_out) return fail(c, -8, "SV_MEM_DEVICE needs leaves_out (it is the scratch of the transposition)");
     CK(c, cudaSetDevice(c->device));
     const u32 log_N = log_n + rate_bits;
     const size_t N = (size_t)1 << log_N, ncap = (size_t)1 << cap_height;
     const size_t in_words = n_polys << log_n, lde_words = n_polys << log_N, layer_words = 4 * (2 * N - ncap);
     cudaStream_t s = mem == SV_MEM_DEVICE ? c->stream : c->own_stream;
-    // device buffers: [2] = LDE (polynomial-major), leaves (point-major), layers
+    // device buffers: [2] = LDE (polynomial-major), leaves (point-major, only when asked for), layers
     if (grow(c, c->d_stage[2], c->stage_words[2], lde_words)) return -6;
     const u64* d_in = coeffs;
     u64 *d_leaves = leaves_out, *d_layers = layers_out;
     if (mem != SV_MEM_DEVICE) {
         if (grow(c, c->d_stage[0], c->stage_words[0], in_words)) return -6;
-        if (grow(c, c->d_stage[1], c->stage_words[1], lde_words)) return -6;
+        if (leaves_out && grow(c, c->d_stage[1], c->stage_words[1], lde_words)) return -6;
         if (grow(c, c->d_stage[3], c->stage_words[3], layer_words)) return -6;
         CK(c, cudaMemcpyAsync(c->d_stage[0], coeffs, in_words * 8, cudaMemcpyHostToDevice, s));
         d_in = c->d_stage[0];
-        d_leaves = c->d_stage[1];
+        d_leaves = leaves_out ? c->d_stage[1] : nullptr;
         d_layers = c->d_stage[3];
     }
     u64* d_lde = c->d_stage[2];
-    lde_scale_pad_kernel<<<(unsigned)((lde_words + 255) / 256), 256, 0, s>>>(d_in, d_lde, log_n, log_N, n_polys, 7);
-    c->launches++;
-    if (int rc = enqueue_ntt(c, log_N, n_polys, d_lde, false, s)) return rc;
-    dim3 tg((unsigned)((N + 31) / 32), (unsigned)((n_polys + 31) / 32));
-    transpose_kernel<<<tg, dim3(32, 8), 0, s>>>(d_lde, d_leaves, n_polys, N);
-    c->launches++;
+    if (int rc = enqueue_lde(c, log_n, rate_bits, n_polys, d_in, 7, d_lde, s)) return rc;
     const int B = SVB_BLOCK;
-    SVB_LAUNCH_KIND(hash_kind, merkle_leaf_hash_kernel, (unsigned)((N + B - 1) / B), B, s, d_leaves, (u32)n_polys, N, d_layers);
+    // leaf digests straight from the polynomial-major values: thread i reads word i of every polynomial (coalesced)
+    SVB_LAUNCH_KIND(hash_kind, merkle_leaf_hash_cols_kernel, (unsigned)((N + B - 1) / B), B, s, d_lde, (u32)n_polys, N, d_layers);
     c->launches++;
+    if (d_leaves) {
+        dim3 tg((unsigned)((N + 31) / 32), (unsigned)((n_polys + 31) / 32));
+        transpose_kernel<<<tg, dim3(32, 8), 0, s>>>(d_lde, d_leaves, n_polys, N);
+        c->launches++;
+    }
     u64* cur = d_layers;
     for (size_t m = N; m > ncap; m >>= 1) {
         u64* nxt = cur + 4 * m;

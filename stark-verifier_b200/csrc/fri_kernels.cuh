@@ -588,6 +588,33 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) merkle_leaf_
     o[0] = make_ulonglong2(canon(s[0]), canon(s[1]));
     o[1] = make_ulonglong2(canon(s[2]), canon(s[3]));
 }
+// The same digests from POLYNOMIAL-MAJOR values (the layout an LDE produces: word j of leaf i at cols[j * n + i]): thread i
+// walks down its column, so every load of a warp is one coalesced 256-byte run -- no transposing copy before the hash.
+template <int KIND>
+__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) merkle_leaf_hash_cols_kernel(const u64* __restrict__ cols, u32 leaf_len,
+                                                                                         size_t n, u64* __restrict__ digests) {
+    __shared__ u64 scratch[PermScratch<KIND>::array_len(SVB_BLOCK)];
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = 0;
+    if (leaf_len <= 4) {
+        for (u32 k = 0; k < leaf_len; k++) s[k] = __ldg(cols + (size_t)k * n + i);
+    } else {
+#pragma unroll 1
+        for (u32 off = 0; off < leaf_len; off += 8) {
+            u32 rem = leaf_len - off;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if ((u32)k < rem) s[k] = __ldg(cols + (size_t)(off + k) * n + i);
+            permute_dev<KIND>(s, scratch, SVB_BLOCK);
+        }
+    }
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(digests + 4 * i);
+    o[0] = make_ulonglong2(canon(s[0]), canon(s[1]));
+    o[1] = make_ulonglong2(canon(s[2]), canon(s[3]));
+}
 // One tree level: parent j = two_to_one(child 2j, child 2j+1).  One thread per parent.
 template <int KIND>
 __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) merkle_level_kernel(const u64* __restrict__ children, u64* __restrict__ parents,

@@ -188,12 +188,31 @@ SVB_HD u64 add_lc(u64 a, u64 b_canonical) {
     return s < a ? s + GL_EPS : s;
 }
 // canonical ops (inputs canonical, output canonical)
+// Device: borrow-mask forms, 5 instructions for a - b (t = a - b; a borrow means t is 2^64 too large, i.e. EPS = 2^32 - 1
+// too large mod p, and the mask the borrow chain leaves in a register IS that EPS) against 8 for compare + select; a + b
+// as a - (p - b), 7 against 10 (p - 0 = p is a harmless non-canonical subtrahend: a - p borrows and comes back as a).  The
+// NTT butterflies and the FRI algebra are made of these.
+SVB_HD u64 sub(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), r0, r1;
+    asm("{\n\t.reg .u32 t0, t1, m;\n\t"
+        "sub.cc.u32 t0, %2, %4;\n\t subc.cc.u32 t1, %3, %5;\n\t subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, t0, m;\n\t subc.u32 %1, t1, 0;\n\t}"
+        : "=r"(r0), "=r"(r1) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return ((u64)r1 << 32) | r0;
+#else
+    return a >= b ? a - b : a + (GL_P - b);
+#endif
+}
 SVB_HD u64 add(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+    return sub(a, GL_P - b);
+#else
     u64 s = a + b;
     if (s < a || s >= GL_P) s -= GL_P;
     return s;
+#endif
 }
-SVB_HD u64 sub(u64 a, u64 b) { return a >= b ? a - b : a + (GL_P - b); }
 SVB_HD u64 neg(u64 a) { return a ? GL_P - a : 0; }
 SVB_HD u64 mulc(u64 a, u64 b) { return canon(mul(a, b)); }
 

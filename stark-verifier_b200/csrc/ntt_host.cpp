@@ -1,31 +1,43 @@
-// Host twin of the NTT / LDE kernels: the same ntt_pass_block (ntt.hpp) with one "thread" per block, on CPU threads.
-// For the CPU test-suite and for callers that transform a handful of small polynomials.
+// Host twin of the NTT / LDE kernels: the same phase functions (ntt.hpp: ntt_tile_load / ntt_tile_round / ntt_tile_store)
+// that ntt_pass_kernel runs between barriers, here with every phase looped over the "threads" of a tile, on CPU
+// threads.  For the CPU test-suite (tests/test_ntt.py: against naive big-integer evaluation) and for callers that
+// transform a handful of small polynomials.
 #include "ntt.hpp"
 #include "host_util.hpp"
 
 using namespace svb;
 
-struct NoSync { void operator()() const {} };
+// one pass over every tile of `n_items` (polynomial, coset) items
+static void host_pass(const NttPass& P, size_t n_items, const u64* src, size_t src_stride, u64* dst, size_t dst_stride, const u64* tw,
+                      const u64* scale_lo, const u64* scale_hi, int nthreads) {
+    const u64 tiles = ntt_tiles_per_poly(P);
+    const NttRounds Q = ntt_rounds(P);
+    const u32 VT = 64;   // virtual threads per tile: any number gives the same result, > 1 exercises the strided loops
+    parallel_for(n_items * tiles, nthreads, [&](size_t b, size_t e) {
+        std::vector<u64> tile(NTT_SMEM_WORDS);
+        for (size_t it = b; it < e; it++) {
+            const size_t item = it / tiles;
+            const u64 t = it % tiles;
+            const NttTileMap M = ntt_tile_map(P, t);
+            const u64* s = src + (item >> P.coset_bits) * src_stride;
+            u64* d = dst + item * dst_stride;
+            const u32 coset = (u32)(item & ((1u << P.coset_bits) - 1));
+            for (u32 tid = 0; tid < VT; tid++) ntt_tile_load(P, M, s, scale_lo, scale_hi, coset, tile.data(), tid, VT);
+            for (u32 i = 0; i < Q.n; i++)
+                for (u32 tid = 0; tid < VT; tid++) ntt_tile_round_any(P, M, tw, tile.data(), Q.b[i], Q.r[i], tid, VT);
+            for (u32 tid = 0; tid < VT; tid++) ntt_tile_store(P, M, d, tile.data(), tid, VT);
+        }
+    });
+}
 
 static int ntt_host_impl(u32 k, size_t n_polys, u64* data, bool inverse, int nthreads) {
-    NttPass plan[8];
+    NttPass plan[NTT_MAX_PASSES];
     int np = ntt_plan(k, inverse, plan);
     if (np < 0) return -1;
     const u64 n = 1ull << k;
     std::vector<u64> tw(std::max<u64>(1, n / 2));
     ntt_twiddles(k, inverse, tw.data());
-    const u64 ninv = inverse ? inv(n % GL_P) : 1;
-    parallel_for(n_polys, nthreads, [&](size_t b, size_t e) {
-        std::vector<u64> tile((size_t)1 << NTT_TILE_LOG);
-        for (size_t p = b; p < e; p++) {
-            u64* poly = data + p * n;
-            for (int q = 0; q < np; q++)
-                for (u64 blk = 0; blk < ntt_blocks_per_poly(plan[q]); blk++)
-                    ntt_pass_block(plan[q], poly, tw.data(), tile.data(), blk, 0, 1, NoSync());
-            if (inverse)
-                for (u64 i = 0; i < n; i++) poly[i] = mulc(poly[i], ninv);
-        }
-    });
+    for (int q = 0; q < np; q++) host_pass(plan[q], n_polys, data, n, data, n, tw.data(), nullptr, nullptr, nthreads);
     return 0;
 }
 
@@ -41,10 +53,29 @@ extern "C" int sv_lde_host(uint32_t log_n, uint32_t rate_bits, size_t n_polys, c
                            uint64_t* out, int nthreads) {
     if ((!coeffs || !out) && n_polys) return -1;
     if (log_n == 0 || log_n + rate_bits > 26 || !is_canonical(shift) || shift == 0) return -2;
-    const u64 n = 1ull << log_n, N = 1ull << (log_n + rate_bits);
+    const u64 n = 1ull << log_n;
     for (size_t i = 0; i < n_polys * n; i++)
         if (!is_canonical(coeffs[i])) return -3;
-    for (size_t p = 0; p < n_polys; p++)
-        for (u64 j = 0; j < N; j++) out[p * N + j] = lde_scaled_coeff(coeffs + p * n, n, shift, j);
-    return ntt_host_impl(log_n + rate_bits, n_polys, out, false, nthreads < 1 ? 1 : nthreads);
+    // 2^rate_bits size-n transforms per polynomial, the first pass scaling on load (ntt.hpp)
+    NttPass plan[NTT_MAX_PASSES];
+    int np = ntt_plan(log_n, false, plan);
+    if (np < 0) return -2;
+    const u32 h = lde_scale_h(log_n);
+    std::vector<u64> lo((size_t)1 << (rate_bits + h)), hi((size_t)1 << (rate_bits + log_n - h)), tw(std::max<u64>(1, n / 2));
+    lde_scale_tables(log_n, rate_bits, shift, lo.data(), hi.data());
+    ntt_twiddles(log_n, false, tw.data());
+    const size_t items = n_polys << rate_bits;
+    if (nthreads < 1) nthreads = 1;
+    for (int q = 0; q < np; q++) {
+        NttPass P = plan[q];
+        P.coset_bits = rate_bits;
+        P.scale_h = h;
+        P.load_scaled = q == 0;
+        if (q == 0) host_pass(P, items, coeffs, n, out, n, tw.data(), lo.data(), hi.data(), nthreads);
+        else {
+            P.coset_bits = 0;   // in place on the output blocks from now on
+            host_pass(P, items, out, n, out, n, tw.data(), nullptr, nullptr, nthreads);
+        }
+    }
+    return 0;
 }

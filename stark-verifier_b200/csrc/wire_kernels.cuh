@@ -20,10 +20,15 @@ __global__ void __launch_bounds__(SVB_WIRE_BLOCK) wire_unpack_kernel(const u64* 
                                                                      WireDims d, const u32* __restrict__ hdr_src,
                                                                      const u32* __restrict__ q_src, const u32* __restrict__ chk,
                                                                      const u64* __restrict__ vk_cap, u64* __restrict__ records,
-                                                                     u32* __restrict__ malformed) {
+                                                                     u32* __restrict__ malformed, const u64* __restrict__ hdr_packed) {
     const size_t p = blockIdx.x, proof_off = first_off + p * stride;
     u64* rec = records + p * (size_t)d.record_words;
     if (blockIdx.y == 0) {
+        if (hdr_packed) {   // batch-wide transcript: the header was unpacked (and its challenge fields filled) before the chunks
+            const u64* h = hdr_packed + p * (size_t)d.header_words;
+            for (u32 w = threadIdx.x; w < d.header_words; w += SVB_WIRE_BLOCK) rec[w] = h[w];
+            return;
+        }
         for (u32 w = threadIdx.x; w < d.header_words; w += SVB_WIRE_BLOCK) rec[w] = wire_header_word(hdr_src, vk_cap, blob8, proof_off, w);
         return;
     }
@@ -33,6 +38,30 @@ __global__ void __launch_bounds__(SVB_WIRE_BLOCK) wire_unpack_kernel(const u64* 
     for (u32 r = threadIdx.x; r < d.query_words; r += SVB_WIRE_BLOCK)
         out[r] = wire_query_word(d, q_src, chk, vk_cap, blob8, proof_off, q, r, &bad);
     if (bad) malformed[p] = 1;
+}
+
+// The headers of a whole batch from their two byte spans (sv_verify_proofs_wire / _full): a serialised proof keeps its
+// header fields at both ends -- caps, openings and commit-phase caps in front of the query rounds, final polynomial, PoW
+// witness and public inputs behind them -- so the host sends those two spans of EVERY proof first (two strided copies),
+// this kernel gathers them into packed headers (header_words per proof), and the transcript runs once for the batch while
+// the query rounds are still crossing PCIe.  front8 / back8: row p at p * pitch bytes (8-byte aligned rows); a source code
+// below front_bytes lives in the front span, any other in the back span, which starts at byte back_off of the proof.
+__global__ void __launch_bounds__(SVB_WIRE_BLOCK) wire_header_unpack_kernel(const u64* __restrict__ front8, size_t front_pitch,
+                                                                            const u64* __restrict__ back8, size_t back_pitch,
+                                                                            u32 front_bytes, u32 back_off, u32 header_words,
+                                                                            const u32* __restrict__ hdr_src, const u64* __restrict__ vk_cap,
+                                                                            u64* __restrict__ hdr_out) {
+    const size_t p = blockIdx.x;
+    u64* out = hdr_out + p * (size_t)header_words;
+    for (u32 w = threadIdx.x; w < header_words; w += SVB_WIRE_BLOCK) {
+        const u32 code = hdr_src[w];
+        u64 v;
+        if (code == WIRE_ZERO) v = 0;
+        else if (code & WIRE_VK_FLAG) v = vk_cap[code & ~WIRE_VK_FLAG];
+        else if (code < front_bytes) v = wire_gather64(front8, p * front_pitch + code);
+        else v = wire_gather64(back8, p * back_pitch + (code - back_off));
+        out[w] = v;
+    }
 }
 
 // Public-inputs hash, one thread per proof: hash_n_to_hash_no_pad over Poseidon-Goldilocks

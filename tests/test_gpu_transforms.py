@@ -1,5 +1,5 @@
-"""GPU side of the NTT / LDE library: ntt_pass_kernel / lde_scale_pad_kernel against the host twin of the
-same tile routine (pinned by tests/test_ntt.py), and the whole commit phase on the device -- LDE -> leaves -> Merkle cap --
+"""GPU side of the NTT / LDE library: ntt_pass_kernel (plain, inverse, LDE first pass) against the host twin of the
+same phase functions (pinned by tests/test_ntt.py), and the whole commit phase on the device -- LDE -> leaves -> Merkle cap --
 against the cap a complete proof of the Python prover carries."""
 import numpy as np
 import pytest
@@ -9,10 +9,10 @@ from common import P
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("k", [1, 5, 9, 10, 12, 15, 19])
+@pytest.mark.parametrize("k", [1, 2, 5, 9, 10, 12, 13, 14, 15, 19, 22, 23])
 def test_ntt_kernel_matches_host_twin(svb, ctx, k):
     rng = np.random.default_rng(k)
-    n_polys = 3 if k < 19 else 2
+    n_polys = 3 if k < 19 else (2 if k < 23 else 1)
     a = rng.integers(0, P, size=(n_polys, 1 << k), dtype=np.uint64)
     a[0, :] = P - 1
     want = svb.ntt_host(a, nthreads=4)
@@ -37,7 +37,7 @@ def test_ntt_device_memory_and_many_polys(svb, ctx):
     assert (d.cpu().numpy().view(np.uint64) == a).all()
 
 
-@pytest.mark.parametrize("k,rate_bits", [(4, 3), (9, 1), (12, 3), (13, 2)])
+@pytest.mark.parametrize("k,rate_bits", [(1, 1), (4, 3), (9, 1), (12, 3), (13, 2), (14, 2), (17, 1)])
 def test_lde_kernel_matches_host_twin(svb, ctx, k, rate_bits):
     rng = np.random.default_rng(10 * k + rate_bits)
     c = rng.integers(0, P, size=(5, 1 << k), dtype=np.uint64)

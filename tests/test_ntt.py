@@ -1,6 +1,7 @@
-"""NTT / LDE, CPU side: the host twin runs the kernels' own tile routine (ntt.hpp: ntt_pass_block), so these
-tests pin the index arithmetic, the pass plan (1, 2 and 3 passes), the twiddles and the output order against naive
-big-integer evaluation and against the Merkle-leaf convention of the independent Python prover."""
+"""NTT / LDE, CPU side: the host twin runs the kernels' own phase functions (ntt.hpp: ntt_tile_load /
+ntt_tile_round / ntt_tile_store), so these tests pin the index arithmetic, the pass plan (1, 2 and 3 passes), the radix-8 / 4 / 2
+rounds, the twiddle factorisation, the LDE-as-cosets decomposition and the output order against naive big-integer evaluation
+and against the Merkle-leaf convention of the independent Python prover."""
 import numpy as np
 import pytest
 
@@ -32,24 +33,48 @@ def test_forward_matches_naive_dft_in_bit_reversed_order(svb, k):
     assert (svb.ntt_host(got, inverse=True) == a).all()
 
 
-@pytest.mark.parametrize("k", [9, 10, 12, 13, 15, 18, 19])
+@pytest.mark.parametrize("k", [9, 10, 11, 12, 13, 14, 15, 17, 20, 23])
 def test_multi_pass_sizes_sampled_points_and_round_trip(svb, k):
-    """9: one pass of 9 stages; 10-18: two passes; 19: three.  Values at sampled positions against Horner; inverse undoes it."""
+    """up to 13: one pass (rounds 3+3+.. with a last round of 1, 2 or 3 stages); 14-22: two passes; 23: three.  Values at sampled
+    positions against Horner; the inverse undoes it."""
     rng = np.random.default_rng(100 + k)
     n = 1 << k
-    a = rng.integers(0, P, size=(2, n), dtype=np.uint64)
+    a = rng.integers(0, P, size=(2 if k < 20 else 1, n), dtype=np.uint64)
     if k > 13:
         a[:, 64:] = 0                                       # sparse enough for the big-integer Horner below
         deg = 64
     else:
         deg = n
-    got = svb.ntt_host(a, nthreads=2)
+    got = svb.ntt_host(a, nthreads=8)
     w = pow(7, (P - 1) >> k, P)
     for i in [0, 1, 2, n // 2, n - 1] + [int(x) for x in rng.integers(0, n, size=6)]:
         x = pow(w, bitrev(i, k), P)
-        for p in range(2):
+        for p in range(a.shape[0]):
             assert int(got[p, i]) == naive_eval(a[p, :deg], x), (k, i)
-    assert (svb.ntt_host(got, inverse=True, nthreads=2) == a).all()
+    assert (svb.ntt_host(got, inverse=True, nthreads=8) == a).all()
+
+
+@pytest.mark.parametrize("k,rate_bits", [(3, 1), (5, 3), (9, 2), (12, 3), (13, 1), (14, 2), (16, 1), (17, 1)])
+def test_lde_sampled_points(svb, k, rate_bits):
+    """LDE = 2^rate_bits size-n transforms of the coset-scaled coefficients (ntt.hpp): value i of the output is
+    f(shift * omega_N^bitrev(i)), for one- and two-pass n and both levels of the scale table (k > 16: two-level)"""
+    rng = np.random.default_rng(k * 7 + rate_bits)
+    n, N, lN = 1 << k, 1 << (k + rate_bits), k + rate_bits
+    c = rng.integers(0, P, size=(2, n), dtype=np.uint64)
+    deg = n
+    if k > 12:
+        c[:, 48:n - 16] = 0                                 # keeps the big-integer Horner affordable: low and top coefficients
+    for shift in (7, 1, 12345):
+        got = svb.lde_host(c, rate_bits, shift=shift, nthreads=8)
+        wN = pow(7, (P - 1) >> lN, P)
+        for i in [0, 1, N // 2, N - 1, n, n + 1] + [int(x) for x in rng.integers(0, N, size=4)]:
+            x = shift * pow(wN, bitrev(i, lN), P) % P
+            for p in range(2):
+                if k > 12:
+                    want = (naive_eval(c[p, :48], x) + pow(x, n - 16, P) * naive_eval(c[p, n - 16:], x)) % P
+                else:
+                    want = naive_eval(c[p, :deg], x)
+                assert int(got[p, i]) == want, (k, rate_bits, shift, i)
 
 
 def test_linearity_and_convolution(svb):

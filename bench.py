@@ -445,6 +445,99 @@ def run_wire_leg(args):
     print(json.dumps(out))
 
 
+CORRUPTION_KINDS = ("sibling limb", "leaf evaluation", "step evaluation", "final-polynomial coefficient", "proof of work")
+
+
+def record_corruptions(params, L, n, rng):
+    """1/64 of the proofs corrupted, the five kinds round-robin -> [(row, word, kind index)].  Kind 4 sets the
+    top bit of the squeezed PoW response (the record path carries its challenges; on the wire path it is the PoW witness)."""
+    out, S = [], len(params.reduction_arity_bits)
+    for j, i in enumerate(range(32, n, 64)):
+        kind = j % 5
+        q = int(rng.integers(0, params.config.num_query_rounds))
+        qb = L.header_words + q * L.query_words
+        o = int(rng.integers(0, 4))
+        if kind == 2 and S == 0:
+            kind = 1
+        if kind == 0:
+            w = qb + L.q_off_init_sibs[o] + int(rng.integers(0, 4 * L.init_depth))
+        elif kind == 1:
+            w = qb + L.q_off_init_evals[o] + int(rng.integers(0, L.leaf_len[o]))
+        elif kind == 2:
+            st = int(rng.integers(0, S))
+            w = qb + L.q_off_step_evals[st] + int(rng.integers(0, 2 << params.reduction_arity_bits[st]))
+        elif kind == 3:
+            w = L.off_final_poly + int(rng.integers(0, 2 * params.final_poly_len()))
+        else:
+            w = L.off_pow_response
+        out.append((i, w, kind))
+    return out
+
+
+def apply_record_corruption(rec, w, kind):
+    rec[w] = (int(rec[w]) | (1 << 63)) if kind == 4 else (int(rec[w]) ^ 1)
+
+
+def wire_corruptions(params, L, common, nb, n, rng):
+    """the same five kinds as byte flips inside serialised proofs -> [(proof, byte offset, kind index)]"""
+    S = len(params.reduction_arity_bits)
+    q0 = 3 * 32 * L.ncap + 16 * (L.n0 + L.n1) + S * 32 * L.ncap
+    init = [8 * L.leaf_len[k] + 1 + 32 * L.init_depth for k in range(4)]
+    steps = [(16 << params.reduction_arity_bits[i]) + 1 + 32 * L.step_depth[i] for i in range(S)]
+    qbytes = sum(init) + sum(steps)
+    fin = q0 + params.config.num_query_rounds * qbytes
+    out = []
+    for j, i in enumerate(range(32, n, 64)):
+        kind = j % 5
+        q = int(rng.integers(0, params.config.num_query_rounds))
+        qb = q0 + q * qbytes
+        o = int(rng.integers(0, 4))
+        if kind == 2 and S == 0:
+            kind = 1
+        if kind == 0:
+            at = qb + sum(init[:o]) + 8 * L.leaf_len[o] + 1 + int(rng.integers(0, 32 * L.init_depth))
+        elif kind == 1:
+            at = qb + sum(init[:o]) + int(rng.integers(0, 8 * L.leaf_len[o]))
+        elif kind == 2:
+            st = int(rng.integers(0, S))
+            at = qb + sum(init) + sum(steps[:st]) + int(rng.integers(0, 16 << params.reduction_arity_bits[st]))
+        elif kind == 3:
+            at = fin + int(rng.integers(0, 16 * params.final_poly_len()))
+        else:
+            at = fin + 16 * params.final_poly_len()          # the PoW witness
+        out.append((i, at, kind))
+    assert fin + 16 * params.final_poly_len() + 8 + 8 * common.num_public_inputs == nb
+    return out
+
+
+def oracle_bits(orc, oshape, recs, threads):
+    bm = orc.fri_verify_batch(oshape, np.ascontiguousarray(recs), nthreads=threads)
+    return [(int(bm[i >> 5]) >> (i & 31)) & 1 for i in range(recs.shape[0])]
+
+
+def setup_abi_allgather(torch, dist, rank, world, local_rank):
+    """An ncclComm_t of our own for sv_allgather_bitmap (the C-ABI collective): unique id from rank 0, broadcast over the
+    existing process group.  -> (nccl library handle, comm) or raises."""
+    import ctypes
+    nccl = ctypes.CDLL("libnccl.so.2", mode=ctypes.RTLD_GLOBAL)      # the library torch already loaded (same soname)
+
+    class UniqueId(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_byte * 128)]
+    uid = UniqueId()
+    if rank == 0:
+        nccl.ncclGetUniqueId.argtypes = [ctypes.POINTER(UniqueId)]
+        if nccl.ncclGetUniqueId(ctypes.byref(uid)) != 0:
+            raise RuntimeError("ncclGetUniqueId failed")
+    t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    ctypes.memmove(ctypes.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+    comm = ctypes.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
+    if nccl.ncclCommInitRank(ctypes.byref(comm), world, uid, rank) != 0:
+        raise RuntimeError("ncclCommInitRank failed")
+    return nccl, comm
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -459,9 +552,11 @@ def main():
                                         max(3, min(args.steps, 10)))))
         return
 
+    import ctypes
     import torch
     import torch.distributed as dist
     import stark_verifier_b200 as svb
+    from oracle import binding as orc      # the CHECKER of this run (expected bitmaps, cpu_baseline); never on the measured path
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -477,32 +572,35 @@ def main():
     threads = len(os.sched_getaffinity(0)) or 1
     if args.workload == "merkle":
         return bench_merkle(args, svb, torch, dist, rank, local_rank, world)
-    params = workload_params(svb, args.workload)
+    wl = args.workload
+    params = workload_params(svb, wl)
     L = svb.api.make_layout(params)
-    n = args.proofs or (4096 if args.workload == "A" else 256)
+    oshape = orc.shape_from(params.to_shape())
+    n = args.proofs or (4096 if wl == "A" else 256)
     n = (n + 31) & ~31
-    distinct = args.distinct or {"A": 64, "B": 2, "outer": 4}[args.workload]
-    # synthetic proofs: `distinct` base proofs per rank (own seed), tiled to n PHYSICALLY DISTINCT copies
+    distinct = min(n, args.distinct or {"A": 256, "B": 2, "outer": 4}[wl])
+    # ---- synthetic proofs: `distinct` base proofs per rank (own seed) of ONE circuit, each bound to the hash of its own public
+    # inputs, so that the same proofs exist as flat records (challenges filled in by the host transcript) and as wire bytes
     t0 = time.perf_counter()
-    n_circ = 1 if (args.workload == "outer" or args.device_transcript) else min(2, distinct)
     seed = 0xB2000002 ^ (rank << 20)
-    base = svb.synth_proofs(params, distinct, seed=seed, n_circuits=n_circ, nthreads=max(1, threads // max(1, world)))
-    cd = ph_dev = ph_host = None
-    if args.device_transcript:
-        cd, ph = svb.synth_public_inputs(params, distinct, seed=seed, n_circuits=1)
-        cd = cd[0]
-        for off, cnt in ((L.off_alpha, 2), (L.off_betas, 2 * len(params.reduction_arity_bits)), (L.off_pow_response, 1),
-                         (L.off_indices, params.config.num_query_rounds), (L.off_zeta, 2), (L.off_zeta_next, 2)):
-            base[:, off:off + cnt] = 0
+    n_pi = 4
+    common = svb.CommonData.for_params(params, num_public_inputs=n_pi)
+    rng = np.random.default_rng(1234 + rank)
+    pis = rng.integers(0, 0xFFFFFFFF00000001, size=(distinct, n_pi), dtype=np.uint64)
+    pih = np.stack([svb.public_inputs_hash(pis[i]) for i in range(distinct)])
+    gen_threads = max(1, threads // max(1, world))
+    base = svb.synth_proofs(params, distinct, seed=seed, n_circuits=1, nthreads=gen_threads, pi_hashes=pih)
+    cds, _ = svb.synth_public_inputs(params, distinct, seed=seed, n_circuits=1)
+    cd = cds[0]
+    vk_cap = base[0, L.off_init_caps:L.off_init_caps + 4 * L.ncap].copy()
     t_gen = time.perf_counter() - t0
     rw = L.record_words
     ctx = svb.Context(local_rank)
     stream = torch.cuda.Stream()          # a real (non-default) stream: handle 0 would mean "ctx's own stream"
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    # device batch: the base proofs tiled ON THE DEVICE into n physically distinct records (config 3 is
-    # 54 GB -- it never exists on the host), then the seeded negative controls: 1/64 of the proofs get one
-    # sibling limb flipped; the expected bitmap is known without the oracle
+    # ---- device batch: the base proofs tiled ON THE DEVICE into n physically distinct records (config 3 is 54 GB -- it never
+    # exists on the host), then the seeded negative controls: 1/64 of the proofs, five corruption kinds round-robin
     d_recs = torch.empty((n, rw), dtype=torch.int64, device="cuda")
     d_recs[:distinct].copy_(torch.from_numpy(base.view(np.int64)))
     k = distinct
@@ -510,38 +608,50 @@ def main():
         c = min(k, n - k)
         d_recs[k:k + c].copy_(d_recs[:c])
         k += c
-    rng = np.random.default_rng(1234 + rank)
-    exp = np.full(n // 32, 0xFFFFFFFF, dtype=np.uint32)
-    rows, cols = [], []
-    for i in range(32, n, 64):
-        q = int(rng.integers(0, params.config.num_query_rounds))
-        rows.append(i)
-        cols.append(L.header_words + q * L.query_words + L.q_off_init_sibs[i % 4] + int(rng.integers(0, 4 * L.init_depth)))
-        exp[i >> 5] &= np.uint32(~(1 << (i & 31)) & 0xFFFFFFFF)
-    if rows:
-        r_t, c_t = torch.tensor(rows, device="cuda"), torch.tensor(cols, device="cuda")
-        d_recs[r_t, c_t] = d_recs[r_t, c_t] ^ 1
-    # host copy (pinned) of a bounded prefix for the end-to-end leg
-    n_host = min(n, 4096 if args.workload == "A" else 512)
-    host = torch.empty((n_host, rw), dtype=torch.int64).pin_memory()
-    host.copy_(d_recs[:n_host])
+    cor = record_corruptions(params, L, n, rng)
+    # expected bitmap FROM THE ORACLE, in this run: every base proof, and every corrupted record rebuilt on the host
+    base_bits = oracle_bits(orc, oshape, base, threads)
+    bad_recs = np.stack([base[i % distinct] for i, _, _ in cor]) if cor else np.zeros((0, rw), dtype=np.uint64)
+    for r, (_, w, kind) in zip(bad_recs, cor):
+        apply_record_corruption(r, w, kind)
+    bad_bits = oracle_bits(orc, oshape, bad_recs, threads) if cor else []
+    if not all(base_bits) or any(bad_bits):
+        raise SystemExit(f"rank {rank}: the oracle rejects a base proof or accepts a corrupted one")
+    exp = np.zeros(n // 32, dtype=np.uint32)
+    for i in range(n):
+        if base_bits[i % distinct]:
+            exp[i >> 5] |= np.uint32(1 << (i & 31))
+    for (i, _, _), b in zip(cor, bad_bits):
+        if not b:
+            exp[i >> 5] &= np.uint32(~(1 << (i & 31)) & 0xFFFFFFFF)
+    if cor:
+        r_t = torch.tensor([i for i, _, _ in cor], device="cuda")
+        c_t = torch.tensor([w for _, w, _ in cor], device="cuda")
+        vals = torch.from_numpy(np.array([r[w] for r, (_, w, _) in zip(bad_recs, cor)], dtype=np.uint64).view(np.int64)).cuda()
+        d_recs[r_t, c_t] = vals
     words = n // 32
     d_bm = torch.zeros(words, dtype=torch.int32, device="cuda")
     d_all = torch.zeros(words * world, dtype=torch.int32, device="cuda")
-    if args.device_transcript:
-        reps = (n + distinct - 1) // distinct
-        ph_host = np.ascontiguousarray(np.tile(ph, (reps, 1))[:n])
-        ph_dev = torch.from_numpy(ph_host.view(np.int64)).cuda()
+    d_all_torch = torch.zeros(words * world, dtype=torch.int32, device="cuda")
+    # the accept-bitmap all-gather goes through the C ABI (sv_allgather_bitmap on a communicator of our own); torch's gather
+    # is the cross-check after the timed region, and the fallback if the communicator cannot be made
+    abi = None
+    gather_via = "n/a (1 rank)"
+    if world > 1:
+        try:
+            abi = setup_abi_allgather(torch, dist, rank, world, local_rank)
+            gather_via = "sv_allgather_bitmap (C ABI, ncclAllGather on the ctx stream)"
+        except Exception as ex:   # noqa: BLE001
+            gather_via = f"torch.distributed.all_gather_into_tensor (C-ABI communicator unavailable: {type(ex).__name__}: {ex})"
     torch.cuda.synchronize()
 
     def step():
-        if args.device_transcript:
-            ctx.fri_verify_batch_fs(params, d_recs.data_ptr(), cd, ph_dev.data_ptr(), n_proofs=n, accept_bitmap=d_bm.data_ptr(),
-                                    mem=svb.MEM_DEVICE)
-        else:
-            ctx.fri_verify_batch(params, d_recs.data_ptr(), n_proofs=n, accept_bitmap=d_bm.data_ptr(), mem=svb.MEM_DEVICE)
+        ctx.fri_verify_batch(params, d_recs.data_ptr(), n_proofs=n, accept_bitmap=d_bm.data_ptr(), mem=svb.MEM_DEVICE)
         if world > 1:
-            dist.all_gather_into_tensor(d_all, d_bm)
+            if abi is not None:
+                ctx.allgather_bitmap(abi[1].value, d_bm.data_ptr(), d_all.data_ptr(), words)
+            else:
+                dist.all_gather_into_tensor(d_all, d_bm)
 
     def barrier():
         if world > 1:
@@ -553,7 +663,12 @@ def main():
     barrier()
     got = d_bm.cpu().numpy().view(np.uint32)
     if not (got == exp).all():
-        raise SystemExit(f"rank {rank}: accept bitmap differs from the expected pattern")
+        raise SystemExit(f"rank {rank}: accept bitmap differs from the oracle's")
+    if world > 1:
+        dist.all_gather_into_tensor(d_all_torch, d_bm)
+        torch.cuda.synchronize()
+        if not bool((d_all == d_all_torch).all()):
+            raise SystemExit(f"rank {rank}: sv_allgather_bitmap and torch's all-gather disagree")
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -577,61 +692,185 @@ def main():
     ms = float(t.item())
     value = world * n * args.steps / (ms / 1e3)
 
-    # end to end through the public C ABI with HOST buffers (pinned): H2D + kernels + D2H of the bitmap
+    def timed_events(fn, reps):
+        """device time of `reps` resident calls on the ctx stream, max over ranks"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) / 1e3
+
+    # resident data with the Fiat-Shamir transcript on the device as well (sv_fri_verify_batch_fs): challenge fields zeroed
+    resident_fs = None
+    try:
+        d_fs = d_recs.clone()
+        d_fs[:, L.off_alpha:L.header_words] = 0
+        ph_dev = torch.from_numpy(np.ascontiguousarray(np.tile(pih, ((n + distinct - 1) // distinct, 1))[:n]).view(np.int64)).cuda()
+        d_bm2 = torch.zeros(words, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        run_fs = lambda: ctx.fri_verify_batch_fs(params, d_fs.data_ptr(), cd, ph_dev.data_ptr(), n_proofs=n, accept_bitmap=d_bm2.data_ptr(),
+                                                 mem=svb.MEM_DEVICE)
+        for _ in range(2):
+            run_fs()
+        torch.cuda.synchronize()
+        # a corrupted PoW response is recomputed by the device transcript: those proofs are valid again
+        exp_fs = exp.copy()
+        for i, _, kind in cor:
+            if kind == 4:
+                exp_fs[i >> 5] |= np.uint32(1 << (i & 31))
+        if not (d_bm2.cpu().numpy().view(np.uint32) == exp_fs).all():
+            raise RuntimeError("bitmap of the device-transcript leg differs from the oracle's")
+        dt = timed_events(run_fs, args.steps)
+        resident_fs = {"value": world * n * args.steps / dt, "unit": "proofs/s", "steps": args.steps,
+                       "note": "sv_fri_verify_batch_fs on resident records: device transcript (one launch per batch) + prepare + query"}
+        del d_fs
+    except Exception as ex:   # noqa: BLE001
+        resident_fs = {"error": f"{type(ex).__name__}: {ex}"}
+
+    # ---- end to end through the public C ABI with HOST buffers (pinned).  The headline leg starts from SERIALISED proofs: plonky2
+    # wire bytes -> H2D -> device unpack, public-input hashes, Fiat-Shamir transcript, query phase -> D2H of the bitmap
+    # (sv_verify_proofs_wire).  Sub-legs: the same bytes through the complete verifier; flat records with host-side challenges
+    # (sv_fri_verify_batch) and with the device transcript; the copy-only ceiling of the same bytes.
     e2e = None
     if not args.no_e2e:
         ctx.set_stream(0)
+        n_host = min(n, 4096 if wl == "A" else 512)
         hwords = n_host // 32
-        hb = np.zeros(hwords, dtype=np.uint32)
-        e2e_steps = max(2, min(args.steps, 10))
-        def host_call():
-            if args.device_transcript:
-                ctx.fri_verify_batch_fs(params, host.data_ptr(), cd, ph_host[:n_host], n_proofs=n_host, accept_bitmap=hb, mem=svb.MEM_HOST)
-            else:
-                ctx.fri_verify_batch(params, host.data_ptr(), n_proofs=n_host, accept_bitmap=hb, mem=svb.MEM_HOST)
-        for _ in range(2):
-            host_call()
-        assert (hb == exp[:hwords]).all()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            host_call()
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        # the PCIe ceiling of that leg: the same bytes, copy only
-        stage = torch.empty_like(host, device="cuda")
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            stage.copy_(host, non_blocking=True)
-        torch.cuda.synchronize()
-        h2d_s = (time.perf_counter() - t0) / 3
-        del stage
-        e2e = {"value": world * n_host * e2e_steps / float(tt.item()), "unit": "proofs/s",
-               "h2d_bytes_per_step": int(n_host * rw * 8), "d2h_bytes_per_step": int(hwords * 4), "steps": e2e_steps,
-               "proofs_per_step_per_gpu": n_host, "host_binding": numa,
-               "h2d_only_gbs": n_host * rw * 8 / h2d_s / 1e9,
-               "h2d_only_proofs_per_s": world * n_host / h2d_s,
-               "note": "sv_fri_verify_batch(SV_MEM_HOST) from pinned host records, chunked H2D overlapped with kernels; "
-                       "h2d_only_* = the same bytes copied with no compute (the PCIe ceiling of this leg)"}
-
-    # the same leg from SERIALISED proofs (plonky2 wire bytes, pinned): H2D of the bytes, device unpack, public-input
-    # hashes, device transcript, query phase (sv_verify_proofs_wire).  1 GPU only, in a child process with a time limit:
-    # whatever happens there is reported under e2e.wire and cannot take the main measurement down with it.
-    if e2e is not None and world == 1 and not args.no_wire and args.workload != "B":   # (shape-B proofs take minutes to synthesise)
-        import subprocess
+        e2e_steps = args.steps
+        blob = svb.wire_pack(common, base, pis)
+        nb = blob.shape[1]
+        p = ctypes.c_void_p()
+        if svb.lib().sv_host_alloc(n_host * nb, ctypes.byref(p)) != 0:
+            raise SystemExit("sv_host_alloc failed")
         try:
-            cmd = [sys.executable, os.path.abspath(__file__), "--wire-leg", "--workload", args.workload, "--proofs", str(n_host),
-                   "--distinct", str(distinct), "--steps", str(max(2, min(args.steps, 10)))]
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            e2e["wire"] = json.loads(lines[-1]) if r.returncode == 0 and lines else {
-                "error": f"exit {r.returncode}: {(r.stderr or r.stdout).strip()[-400:]}"}
-        except Exception as ex:   # noqa: BLE001
-            e2e["wire"] = {"error": f"{type(ex).__name__}: {ex}"}
+            hostb = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(n_host, nb))
+            for i in range(0, n_host, distinct):
+                c = min(distinct, n_host - i)
+                hostb[i:i + c] = blob[:c]
+            wcor = wire_corruptions(params, L, common, nb, n_host, np.random.default_rng(77 + rank))
+            for i, at, _ in wcor:
+                hostb[i, at] ^= 1
+            # the oracle's verdict on the corrupted proofs, from their bytes (its own reader and transcript)
+            ocommon = orc.common_from(common.to_c())
+            exp_w = np.zeros(hwords, dtype=np.uint32)
+            for i in range(n_host):
+                if base_bits[i % distinct]:
+                    exp_w[i >> 5] |= np.uint32(1 << (i & 31))
+            for i, _, _ in wcor:
+                rc, rec_o, _, pih_o = orc.wire_read_proof(oshape, ocommon, vk_cap, hostb[i])
+                ok = False
+                if rc == 0:
+                    orc.fri_challenges(oshape, rec_o, cd, pih_o, common.num_challenges)
+                    ok = bool(orc.fri_verify(oshape, rec_o)[0])
+                if not ok:
+                    exp_w[i >> 5] &= np.uint32(~(1 << (i & 31)) & 0xFFFFFFFF)
+
+            def time_host(call, reps):
+                for _ in range(2):
+                    call()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    call()
+                barrier()
+                tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                return float(tt.item())
+
+            hb = {}
+
+            def wire_call():
+                hb["bm"] = ctx.verify_proofs_wire(common, vk_cap, cd, p.value, n_proofs=n_host)
+            dt1 = time_host(wire_call, e2e_steps)
+            if not (hb["bm"] == exp_w).all():
+                raise SystemExit(f"rank {rank}: accept bitmap of the wire leg differs from the oracle's")
+            # The headline: the same call from TWO host threads, each with its own sv_ctx (the threading model of the C ABI:
+            # one ctx per host thread and GPU, distinct ctxs fully concurrent), every call a full batch of n_host proofs from
+            # its own pinned buffer.  A lone synchronous call exposes the latency of its batch transcript (~3 ms of ~14: the
+            # query phase needs the query indices, the last thing the transcript yields); with a second call in flight that
+            # latency is hidden behind the other call's copies and kernels.  e2e_steps calls in total.
+            import threading
+            ctx2 = svb.Context(local_rank)
+            p2 = ctypes.c_void_p()
+            if svb.lib().sv_host_alloc(n_host * nb, ctypes.byref(p2)) != 0:
+                raise SystemExit("sv_host_alloc failed")
+            ctypes.memmove(p2.value, p.value, n_host * nb)
+            res = {}
+
+            def worker(c, ptr, reps, key):
+                for _ in range(reps):
+                    res[key] = c.verify_proofs_wire(common, vk_cap, cd, ptr, n_proofs=n_host)
+
+            def two_in_flight(reps):
+                th = [threading.Thread(target=worker, args=(ctx, p.value, (reps + 1) // 2, 0)),
+                      threading.Thread(target=worker, args=(ctx2, p2.value, reps // 2, 1))]
+                for t_ in th:
+                    t_.start()
+                for t_ in th:
+                    t_.join()
+            two_in_flight(4)
+            barrier()
+            t0 = time.perf_counter()
+            two_in_flight(e2e_steps)
+            barrier()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+            if not all((res[k_] == exp_w).all() for k_ in res):
+                raise SystemExit(f"rank {rank}: accept bitmap of the two-calls-in-flight wire leg differs from the oracle's")
+            svb.lib().sv_host_free(p2)
+            ctx2.close()
+            e2e = {"value": world * n_host * e2e_steps / dt, "unit": "proofs/s", "h2d_bytes_per_step": int(n_host * nb),
+                   "calls_in_flight": 2,
+                   "single_call": {"value": world * n_host * e2e_steps / dt1, "unit": "proofs/s",
+                                   "note": "one synchronous sv_verify_proofs_wire call at a time (the batch transcript's latency is exposed)"},
+                   "d2h_bytes_per_step": int(hwords * 4), "steps": e2e_steps, "proofs_per_step_per_gpu": n_host, "host_binding": numa,
+                   "proof_bytes": int(nb), "public_inputs": n_pi,
+                   "entry_point": "sv_verify_proofs_wire (bytes -> verdict: unpack, public-inputs hash, Fiat-Shamir transcript and query "
+                                  "phase on the device; headers first, transcript once per batch)",
+                   "corrupted": "1/64 proofs, five kinds round-robin as byte flips; bitmap == the oracle's (its own wire reader + transcript)"}
+            # copy-only ceiling of the same bytes
+            stage = torch.empty(n_host * nb, dtype=torch.uint8, device="cuda")
+            hview = torch.from_numpy(hostb.reshape(-1))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                stage.copy_(hview, non_blocking=True)
+            torch.cuda.synchronize()
+            h2d_s = (time.perf_counter() - t0) / 3
+            del stage
+            e2e["h2d_only_gbs"] = n_host * nb / h2d_s / 1e9
+            e2e["h2d_only_proofs_per_s"] = world * n_host / h2d_s
+            e2e["frac_of_h2d_only"] = e2e["value"] / e2e["h2d_only_proofs_per_s"]
+            # sub-leg: flat records with host-side challenges (the round-1 headline), and with the device transcript
+            host = torch.empty((n_host, rw), dtype=torch.int64).pin_memory()
+            host.copy_(d_recs[:n_host])
+            hbm = np.zeros(hwords, dtype=np.uint32)
+            dt = time_host(lambda: ctx.fri_verify_batch(params, host.data_ptr(), n_proofs=n_host, accept_bitmap=hbm, mem=svb.MEM_HOST), e2e_steps)
+            assert (hbm == exp[:hwords]).all()
+            e2e["record_path"] = {"value": world * n_host * e2e_steps / dt, "unit": "proofs/s", "h2d_bytes_per_step": int(n_host * rw * 8),
+                                  "note": "sv_fri_verify_batch(SV_MEM_HOST): flat records whose challenges the host derived"}
+            ph_host = np.ascontiguousarray(np.tile(pih, ((n_host + distinct - 1) // distinct, 1))[:n_host])
+            dt = time_host(lambda: ctx.fri_verify_batch_fs(params, host.data_ptr(), cd, ph_host, n_proofs=n_host, accept_bitmap=hbm,
+                                                           mem=svb.MEM_HOST), e2e_steps)
+            e2e["record_path_device_transcript"] = {"value": world * n_host * e2e_steps / dt, "unit": "proofs/s",
+                                                    "note": "sv_fri_verify_batch_fs(SV_MEM_HOST)"}
+            del host
+            if world == 1 and wl != "B":
+                e2e["full_verifier"] = full_leg(svb, torch, ctx, params, common, vk_cap, cd, p.value, n_host, e2e_steps)
+                e2e["plonk_check"] = plonk_leg(svb, torch, ctx, params, base, n_host, e2e_steps)
+                if not args.no_wire:
+                    e2e["transforms"] = transforms_leg(svb, torch, ctx, params, min(e2e_steps, 10))
+        finally:
+            svb.lib().sv_host_free(p)
 
     if rank != 0:
         if world > 1:
@@ -639,64 +878,70 @@ def main():
         return
 
     peak, peak_src = measured_peak_gbs()
-    # DRAM traffic of one launch of the dominant kernel, from the committed ncu capture of this same workload
-    traffic = None
+    # DRAM traffic of one launch of the dominant kernel: from the committed ncu capture of THIS library revision and workload only
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json"))).get(f"{args.workload}:{n}")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))
+        if tj.get("sv_version") == svb.api.version():
+            traffic = tj.get("bytes", {}).get(f"{wl}:{n}")
+            traffic_src = tj.get("source")
+        else:
+            traffic_src = f"profiles/traffic_r2.json is for library {tj.get('sv_version')}, this is {svb.api.version()}: not reported"
     except Exception:
         pass
     algo_bytes = n * (params.config.num_query_rounds * L.algo_bytes_per_query + L.algo_bytes_shared)
     k_avg_s = (kernel_ms / max(1, kernel_n)) / 1e3
     achieved = algo_bytes / k_avg_s / 1e9
     perms = n * params.config.num_query_rounds * L.perms_per_query
+    cfg = workload_config(wl, n, distinct, rw * 8, world, "host (challenges arrive in the records) for `value`; on the device for `e2e`",
+                          "1/64 proofs, five kinds round-robin (" + ", ".join(CORRUPTION_KINDS) + "); bitmap == the oracle's, computed in this run")
+    cfg["bitmap_gather"] = gather_via
     out = {
         "metric": "plonky2_proofs_verified_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": {"A": f"BASELINE configs[1]: {n} proofs/GPU/step, shape A",
-                                "B": f"BASELINE configs[2]: {n} proofs/GPU/step, shape B",
-                                "outer": f"outer wrapped-proof configuration (Poseidon-BN254 hash, cap_height 0): {n} proofs/GPU/step"}[args.workload],
-                   "hash_kind": params.hash_kind,
-                   "trace_bits": params.degree_bits, "fri_queries": params.config.num_query_rounds,
-                   "blowup": 1 << params.config.rate_bits, "cap_height": params.config.cap_height,
-                   "pow_bits": params.config.proof_of_work_bits, "proofs_per_gpu": n, "distinct_base_proofs": distinct,
-                   "record_bytes": rw * 8, "l2_policy": f"inputs larger than L2 ({n * rw * 8 / 1e6:.0f} MB/GPU resident, physically distinct copies)",
-                   "sharding": f"proofs sharded over {world} ranks; NCCL all-gather of the accept bitmap only",
-                   "corrupted": "1/64 proofs (sibling limb), bitmap checked against the expected pattern",
-                   "transcript": "device (sv_fri_verify_batch_fs)" if args.device_transcript else "host (challenges arrive in the records)"},
+        "config": cfg,
         "e2e": e2e,
+        "resident_with_device_transcript": resident_fs,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "fri_query_kernel", "kernel_ms": kernel_ms / max(1, kernel_n),
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "fri_query_kernel", "kernel_ms": kernel_ms / max(1, kernel_n),
                      "kernel_share_of_step": kernel_ms / ms, "algorithmic_bytes_per_launch": int(algo_bytes),
                      "peak_source": peak_src,
-                     "note": "integer-issue bound, not HBM bound (SURVEY 8d): see perms_per_sec"},
+                     "note": "integer-issue bound, not HBM bound (SURVEY 8d): see issue_roofline"},
         "perms_per_sec": world * perms * args.steps / (ms / 1e3),
         # what actually binds: instruction issue.  One Poseidon-Goldilocks permutation executes
-        # PERM_INSTR warp-instructions (tools/sass_dyn.py on the shipped library, profiles/sass_dyn_r1_v10.txt), of
-        # which PERM_WIDE IMAD.WIDE.U32 (4.24 cycles each on the multiplier pipe, profiles/pipes2_b200_r1.txt) and
-        # PERM_FP64 DADD/DFMA (2.18 cycles each); a sub-partition issues at most one warp-instruction per cycle.
+        # PERM_INSTR warp-instructions (tools/sass_dyn.py on the shipped library), of which PERM_WIDE IMAD.WIDE.U32
+        # (4.24 cycles each on the multiplier pipe, profiles/pipes2_b200_r1.txt) and PERM_FP64 DADD/DFMA (2.18 cycles each);
+        # a sub-partition issues at most one warp-instruction per cycle.
         "issue_roofline": None if params.hash_kind else issue_roofline(perms / k_avg_s, clocks.get("sm_mhz") or 1965.0),
         "synth_seconds": t_gen,
+        "library": svb.api.version(),
     }
     if not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)      # the CPU baseline gets every host core
         threads = len(all_cpus)
         sample = args.cpu_sample
+        shape_c = params.to_shape()
         if not sample:
             # probe on a small batch, then size the sample for ~12 s of CPU work on all host threads
-            probe = 8 * threads if args.workload == "A" else threads
-            if args.workload == "outer":
+            probe = 8 * threads if wl == "A" else threads
+            if wl == "outer":
                 probe = max(4, threads // 4)
-            v0, _, _ = cpu_baseline(svb, params, base, probe, threads)
+            v0, _, _, _ = cpu_baseline(shape_c, rw, base, probe, threads)
             sample = max(probe, int(v0 * 12.0) // threads * threads)
-        v, dt, _ = cpu_baseline(svb, params, base, sample, threads)
-        v1, _, _ = cpu_baseline(svb, params, base, max(1, min(sample, {"A": 16, "B": 1, "outer": 1}[args.workload])), 1)
+        v, dt, bm_cpu, recs_cpu = cpu_baseline(shape_c, rw, base, sample, threads)
+        # the same sample through the GPU: bit-for-bit the oracle's bitmap
+        bm_gpu = ctx.fri_verify_batch(params, recs_cpu)
+        if not (bm_gpu == bm_cpu).all():
+            raise SystemExit("GPU and oracle bitmaps differ on the cpu_baseline sample")
+        v1, _, _, _ = cpu_baseline(shape_c, rw, base, max(1, min(sample, {"A": 16, "B": 1, "outer": 1}[wl])), 1)
         perms_per_proof = params.config.num_query_rounds * L.perms_per_query
         out["cpu_baseline"] = {"value": v, "unit": "proofs/s", "cores": threads, "kind": "port",
                                "perms_per_sec": v * perms_per_proof, "single_thread_value": v1,
-                               "single_thread_perms_per_sec": v1 * perms_per_proof,
+                               "single_thread_perms_per_sec": v1 * perms_per_proof, "perm_ns_per_thread": 1e9 / (v1 * perms_per_proof),
+                               "gpu_bitmap_equal_on_sample": True,
                                "sample": f"{sample} proofs of the same workload in {dt:.1f} s on {threads} threads; oracle/oracle.c, "
                                          "CPU restatement of reference semantics (not the Rust binary)"}
     print(json.dumps(out))

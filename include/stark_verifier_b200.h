@@ -16,7 +16,8 @@
  *  - `mem` says where the data buffers live: SV_MEM_HOST (the call copies H2D in chunks overlapped
  *    with the kernels, copies the result back and returns when it is in host memory) or
  *    SV_MEM_DEVICE (pointers are device pointers on the ctx device; the work is enqueued on the
- *    ctx stream and the call returns without synchronising);
+ *    ctx stream and the call returns without synchronising; the calls of one ctx share its scratch buffers, so the library
+ *    orders a call behind the previous one even when sv_ctx_set_stream moved the ctx to another stream in between);
  *  - there is no CPU fallback: without a CUDA device every compute entry point fails.
  */
 #ifndef STARK_VERIFIER_B200_H
@@ -341,6 +342,33 @@ typedef struct sv_plonk_circuit {
  * reference hard-codes the ones of its recursion circuits), base-2 BaseSumGate only; < 0 for an unknown id
  * (the reference: unimplemented!()). */
 int sv_plonk_gate_from_id(const char* gate_id, sv_plonk_gate* out);
+
+/* What CommonData::from reads out of plonky2's CommonCircuitData (types/common_data.rs:224-270), as plain arrays: the Rust
+ * side passes `gate.0.id()` of every gate (the string CustomGateRef::from matches, chip/plonk/gates/mod.rs:138-196),
+ * SelectorsInfo (selector_indices per gate, groups as [start, end) ranges) and k_is. */
+typedef struct sv_common_circuit_data {
+    sv_plonk_common common;           /* CircuitConfig.num_wires / num_routed_wires / num_challenges, CommonCircuitData.num_constants /
+                                         num_partial_products / quotient_degree_factor / num_public_inputs */
+    uint32_t rate_bits, cap_height, proof_of_work_bits, num_query_rounds; /* config.fri_config */
+    uint32_t hiding, degree_bits;     /* fri_params */
+    uint32_t num_reduction_steps;
+    const uint32_t* reduction_arity_bits; /* fri_params.reduction_arity_bits[num_reduction_steps] */
+    uint32_t num_gate_constraints;
+    uint32_t num_gates;
+    const char* const* gate_ids;      /* gates[i].0.id() */
+    const uint32_t* selector_indices; /* selectors_info.selector_indices[num_gates] */
+    uint32_t num_selector_groups;
+    const uint32_t* group_starts;     /* selectors_info.groups[s].start */
+    const uint32_t* group_ends;       /* selectors_info.groups[s].end */
+    uint32_t num_k_is;
+    const uint64_t* k_is;             /* k_is[num_k_is], num_k_is = num_routed_wires */
+    uint32_t hash_kind;               /* SV_HASH_*: the Hasher of the proof's GenericConfig */
+} sv_common_circuit_data;
+
+/* CommonCircuitData -> (sv_fri_shape, sv_plonk_circuit): gate ids -> kinds and parameters (an id outside the reference's table is
+ * refused, like its unimplemented!()), selector groups, k_is, oracle widths; the result passed sv_plonk_circuit_check.
+ * Replaces: CommonData::from (types/common_data.rs:224-270) + CustomGateRef::from (chip/plonk/gates/mod.rs:138-196). */
+int sv_circuit_from_common_data(const sv_common_circuit_data* cd, sv_fri_shape* shape_out, sv_plonk_circuit* circuit_out);
 
 /* 0 if the circuit description is consistent and uses only gates this library evaluates, else < 0. */
 int sv_plonk_circuit_check(const sv_plonk_circuit* circuit);

@@ -27,6 +27,9 @@ from .api import (  # noqa: F401
     fri_challenges,
     lib,
     lib_path,
+    version,
+    circuit_from_common_data,
+    constant_arity_bits,
     synth_proofs,
     synth_public_inputs,
     MEM_HOST,

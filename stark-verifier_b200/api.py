@@ -201,6 +201,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 
+def version() -> str:
+    """sv_version(): library version + kernel revision"""
+    return lib().sv_version().decode()
+
+
 def lib_path() -> str:
     """The in-tree library; SVB200_LIB overrides it (e.g. an AddressSanitizer build of the same sources for the CPU tests)."""
     return os.environ.get("SVB200_LIB") or os.path.join(_HERE, "libsvb200.so")
@@ -259,6 +264,7 @@ def lib() -> ctypes.CDLL:
     L.sv_public_inputs_hash.argtypes = [vp, ctypes.c_size_t, vp]
     pc = ctypes.POINTER(PlonkCircuit)
     L.sv_plonk_circuit_check.argtypes = [pc]
+    L.sv_circuit_from_common_data.argtypes = [vp, sp, pc]
     L.sv_plonk_gate_from_id.argtypes = [ctypes.c_char_p, ctypes.POINTER(PlonkGate)]
     L.sv_plonk_challenges.argtypes = [sp, vp, vp, vp, ctypes.c_uint32, vp]
     L.sv_plonk_check_host.argtypes = [sp, pc, ctypes.c_size_t, vp, vp, vp, vp, ctypes.c_int]
@@ -427,6 +433,47 @@ def make_plonk_circuit(common: CommonData, gates, groups, k_is, num_gate_constra
     if rc != 0:
         raise SvError(f"sv_plonk_circuit_check refused the circuit: {rc}")
     return c
+
+
+class CommonCircuitDataC(ctypes.Structure):
+    """sv_common_circuit_data"""
+    _fields_ = [("common", PlonkCommon), ("rate_bits", ctypes.c_uint32), ("cap_height", ctypes.c_uint32), ("proof_of_work_bits", ctypes.c_uint32),
+                ("num_query_rounds", ctypes.c_uint32), ("hiding", ctypes.c_uint32), ("degree_bits", ctypes.c_uint32),
+                ("num_reduction_steps", ctypes.c_uint32), ("reduction_arity_bits", ctypes.POINTER(ctypes.c_uint32)),
+                ("num_gate_constraints", ctypes.c_uint32), ("num_gates", ctypes.c_uint32), ("gate_ids", ctypes.POINTER(ctypes.c_char_p)),
+                ("selector_indices", ctypes.POINTER(ctypes.c_uint32)), ("num_selector_groups", ctypes.c_uint32),
+                ("group_starts", ctypes.POINTER(ctypes.c_uint32)), ("group_ends", ctypes.POINTER(ctypes.c_uint32)),
+                ("num_k_is", ctypes.c_uint32), ("k_is", ctypes.POINTER(ctypes.c_uint64)), ("hash_kind", ctypes.c_uint32)]
+
+
+def circuit_from_common_data(common: CommonData, gate_ids, selector_indices, groups, k_is, num_gate_constraints: int):
+    """sv_circuit_from_common_data: what CommonData::from (types/common_data.rs:224-270) + CustomGateRef::from
+    (chip/plonk/gates/mod.rs:138-196) make of a plonky2 CommonCircuitData -> (FriShape, PlonkCircuit).
+    gate_ids: `gate.0.id()` strings; selector_indices / groups: SelectorsInfo; common.fri_params carries the FRI side."""
+    p = common.fri_params
+    u32 = ctypes.c_uint32
+    cd = CommonCircuitDataC()
+    cd.common = common.to_c()
+    cd.rate_bits, cd.cap_height = p.config.rate_bits, p.config.cap_height
+    cd.proof_of_work_bits, cd.num_query_rounds = p.config.proof_of_work_bits, p.config.num_query_rounds
+    cd.hiding, cd.degree_bits = int(p.hiding), p.degree_bits
+    ab = (u32 * max(1, len(p.reduction_arity_bits)))(*p.reduction_arity_bits)
+    cd.num_reduction_steps, cd.reduction_arity_bits = len(p.reduction_arity_bits), ab
+    cd.num_gate_constraints = num_gate_constraints
+    ids = (ctypes.c_char_p * len(gate_ids))(*[g.encode() for g in gate_ids])
+    cd.num_gates, cd.gate_ids = len(gate_ids), ids
+    si = (u32 * len(selector_indices))(*selector_indices)
+    cd.selector_indices = si
+    gs, ge = (u32 * len(groups))(*[g[0] for g in groups]), (u32 * len(groups))(*[g[1] for g in groups])
+    cd.num_selector_groups, cd.group_starts, cd.group_ends = len(groups), gs, ge
+    ks = (ctypes.c_uint64 * len(k_is))(*[int(k) for k in k_is])
+    cd.num_k_is, cd.k_is = len(k_is), ks
+    cd.hash_kind = p.hash_kind
+    shape, circuit = FriShape(), PlonkCircuit()
+    rc = lib().sv_circuit_from_common_data(ctypes.byref(cd), ctypes.byref(shape), ctypes.byref(circuit))
+    if rc != 0:
+        raise SvError(f"sv_circuit_from_common_data refused the circuit data: {rc}")
+    return shape, circuit
 
 
 def plonk_gate_from_id(gate_id: str):

@@ -30,6 +30,7 @@ struct sv_ctx {
     cudaStream_t stream = nullptr;       // stream used for SV_MEM_DEVICE work (own or caller's)
     // device scratch, grown on demand, reused across calls (no hidden allocation after warm-up)
     u64* d_scratch = nullptr; size_t scratch_words = 0;          // reduced openings
+    cudaEvent_t ev_scratch = nullptr; cudaStream_t scratch_stream = nullptr; bool scratch_busy = false;   // last SV_MEM_DEVICE user of d_scratch
     u64* d_stage[SV_NBUF] = {}; size_t stage_words[SV_NBUF] = {};   // H2D chunk ring
     u32* d_bitmap = nullptr; size_t bitmap_words = 0;
     u32* d_fail = nullptr; size_t fail_words = 0;
@@ -94,7 +95,10 @@ static int fail(sv_ctx* c, int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail((c), -100 - (int)e_, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
-extern "C" const char* sv_version(void) { return "stark-verifier_b200 0.1 (sm_100a)"; }
+// bump SVB_KERNEL_REV whenever a kernel changes: profiles/traffic_r2.json and the ncu summaries are stamped with it, and bench.py
+// reports DRAM traffic only from a capture of the same revision
+#define SVB_KERNEL_REV "r2.1"
+extern "C" const char* sv_version(void) { return "stark-verifier_b200 0.2 (sm_100a, kernels " SVB_KERNEL_REV ")"; }
 
 extern "C" const char* sv_last_error(const sv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
@@ -121,7 +125,12 @@ extern "C" int sv_ctx_create(int device, sv_ctx** out) {
         CK(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
         for (int i = 0; i < SV_NKS - 1; i++) CK(nullptr, cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));
         CK(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        CK(nullptr, cudaStreamCreateWithFlags(&c->fs_stream, cudaStreamNonBlocking));
+        {   // the transcript is a chain of dependent permutations on a few warps: its blocks must not queue behind the
+            // thousands of query-kernel blocks of another chunk or another call, so its stream gets the highest priority
+            int lo = 0, hi = 0;
+            CK(nullptr, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(nullptr, cudaStreamCreateWithPriority(&c->fs_stream, cudaStreamNonBlocking, hi));
+        }
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_hdr, cudaEventDisableTiming));
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_fs, cudaEventDisableTiming));
         for (int i = 0; i < SV_NBUF; i++) {
@@ -168,6 +177,7 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaFree(c->d_circuit);
     cudaFree(c->d_chal);
     cudaFree(c->d_pbm);
+    if (c->ev_scratch) cudaEventDestroy(c->ev_scratch);
     cudaFree(c->d_tw);
     cudaFree(c->d_lde_lo);
     cudaFree(c->d_lde_hi);
@@ -563,8 +573,21 @@ static int fri_verify_impl(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs
     if (grow(c, c->d_scratch, c->scratch_words, 4 * n_proofs)) return -6;
 
     if (mem == SV_MEM_DEVICE) {
+        // SV_MEM_DEVICE calls return without synchronising and all share d_scratch (reduced openings): when the caller moved to
+        // another stream since the last such call (sv_ctx_set_stream), this call is ordered behind it
+        if (c->scratch_busy && c->scratch_stream != c->stream) CK(c, cudaStreamWaitEvent(c->stream, c->ev_scratch, 0));
         if (fs && (rc = enqueue_challenges(c, P, *fs, n_proofs, const_cast<u64*>(records), pi_hashes, c->stream))) return rc;
-        return enqueue_fri(c, P, n_proofs, records, c->d_scratch, accept_bitmap, first_fail, c->stream);
+        rc = enqueue_fri(c, P, n_proofs, records, c->d_scratch, accept_bitmap, first_fail, c->stream);
+        if (!c->ev_scratch) CK(c, cudaEventCreateWithFlags(&c->ev_scratch, cudaEventDisableTiming));
+        CK(c, cudaEventRecord(c->ev_scratch, c->stream));
+        c->scratch_stream = c->stream;
+        c->scratch_busy = true;
+        return rc;
+    }
+    // a host-mode call uses the library's own streams: wait for a device-mode call that may still be reading d_scratch
+    if (c->scratch_busy) {
+        CK(c, cudaEventSynchronize(c->ev_scratch));
+        c->scratch_busy = false;
     }
     // host buffers: on an error half-way, drain what was already enqueued before the caller may free its buffers
     rc = fri_verify_host(c, P, n_proofs, records, accept_bitmap, first_fail, fs, pi_hashes);
@@ -777,7 +800,10 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
     const size_t front_pitch = up8(front_bytes) + 8, back_pitch = up8(back_bytes) + 8, q_pitch = up8(q_bytes) + 8;
     if (grow(c, c->d_hfront, c->hfront_words, n_proofs * front_pitch / 8 + 2)) return -6;
     if (grow(c, c->d_hback, c->hback_words, n_proofs * back_pitch / 8 + 2)) return -6;
-    size_t chunk_mb = 32;
+    // 64 MiB chunks here (32 on the record path): the query kernels cannot start before the batch's transcript is done
+    // (~3 ms), and until then the copy engine must find free buffers -- 6 x 64 MiB hold 7 ms of PCIe traffic (measured with
+    // SVB_TRACE: 32 MiB chunks stall the copies for 1.5 ms; tools/lab/wire_trace.sh)
+    size_t chunk_mb = 64;
     int n_ks = SV_NKS;
     if (const char* e = getenv("SVB_CHUNK_MB")) { long v = atol(e); if (v >= 1 && v <= 4096) chunk_mb = (size_t)v; }
     if (const char* e = getenv("SVB_KSTREAMS")) { long v = atol(e); if (v >= 1 && v <= SV_NKS) n_ks = (int)v; }
@@ -788,10 +814,18 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
         if (grow(c, c->d_stage[b], c->stage_words[b], chunk * rw)) return -6;
         if (grow(c, c->d_wire[b], c->wire_words[b], chunk * q_pitch / 8 + 2)) return -6;
     }
+    // SVB_TRACE=1: a timeline of this call on stderr (lab knob)
+    static const bool trace = getenv("SVB_TRACE") != nullptr;
+    cudaEvent_t tv[8] = {};
+    if (trace) {
+        for (auto& e : tv) cudaEventCreate(&e);
+        cudaEventRecord(tv[0], cs);
+    }
     // ---- headers first -------------------------------------------------------------------------------------
     CK(c, cudaMemcpy2DAsync(c->d_hfront, front_pitch, blob, stride, front_bytes, n_proofs, cudaMemcpyHostToDevice, cs));
     CK(c, cudaMemcpy2DAsync(c->d_hback, back_pitch, blob + back_off, stride, back_bytes, n_proofs, cudaMemcpyHostToDevice, cs));
     CK(c, cudaEventRecord(c->ev_hdr, cs));
+    if (trace) cudaEventRecord(tv[1], cs);
     CK(c, cudaStreamWaitEvent(fss, c->ev_hdr, 0));
     CK(c, cudaMemsetAsync(c->d_mal, 0, n_proofs * 4, fss));
     wire_header_unpack_kernel<<<(unsigned)n_proofs, SVB_WIRE_BLOCK, 0, fss>>>(c->d_hfront, front_pitch, c->d_hback, back_pitch, (u32)front_bytes,
@@ -803,6 +837,7 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
                                                                                                        c->d_pi, c->d_mal);
     }
     c->launches += 2;
+    if (trace) cudaEventRecord(tv[6], fss);
     FriKernelParams Ph = P;
     Ph.L.record_words = (u32)hw;                            // the headers are packed back to back
     if (circuit) {   // plonk challenges: the prefix of the transcript below, kept this time
@@ -812,6 +847,7 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
         c->launches++;
     }
     if ((rc = enqueue_challenges(c, Ph, F, n_proofs, c->d_hdr, c->d_pi, fss))) return rc;
+    if (trace) cudaEventRecord(tv[7], fss);
     if (circuit) {   // the vanishing-polynomial identity reads headers only (zeta is in them now)
         PlonkRecordView V = {(u32)hw, P.L.off_open0, P.L.off_open1, P.L.off_zeta};
         plonk_check_kernel<<<(unsigned)((n_proofs + 127) / 128), 128, 0, fss>>>(c->d_hdr, V, c->d_circuit, c->d_pi, c->d_chal, (u32)n_proofs,
@@ -820,6 +856,7 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
     }
     CK(c, cudaGetLastError());
     CK(c, cudaEventRecord(c->ev_fs, fss));
+    if (trace) cudaEventRecord(tv[2], fss);
     // ---- query rounds, chunk by chunk ------------------------------------------------------------------------
     WireDims dq = W.d;
     dq.query_base = 0;                                      // a chunk buffer row holds the query rounds only
@@ -849,14 +886,25 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
         c->launches++;
         CK(c, cudaGetLastError());
         CK(c, cudaEventRecord(c->ev_done[b], k));
+        if (trace && i == 0) cudaEventRecord(tv[3], k);
     }
+    if (trace) cudaEventRecord(tv[4], cs);
     for (int j = 1; j < n_ks && (size_t)j < n_chunks; j++) {
         CK(c, cudaEventRecord(c->ev_join[j], ks[j]));
         CK(c, cudaStreamWaitEvent(ks[0], c->ev_join[j], 0));
     }
     CK(c, cudaMemcpyAsync(accept_bitmap, c->d_bitmap, n_words * 4, cudaMemcpyDeviceToHost, ks[0]));
     if (first_fail) CK(c, cudaMemcpyAsync(first_fail, c->d_fail, n_proofs * 4, cudaMemcpyDeviceToHost, ks[0]));
+    if (trace) cudaEventRecord(tv[5], ks[0]);
     CK(c, cudaStreamSynchronize(ks[0]));
+    if (trace) {
+        float t[8] = {};
+        for (int i = 1; i < 8; i++) cudaEventElapsedTime(&t[i], tv[0], tv[i]);
+        fprintf(stderr, "[svb trace] wire: headers copied %.2f ms, headers unpacked + pi hashed %.2f, challenges %.2f, transcript stream done %.2f, "
+                        "first chunk done %.2f, last chunk copied %.2f, end %.2f (%zu proofs, %zu chunks of %zu)\n",
+                t[1], t[6], t[7], t[2], t[3], t[4], t[5], n_proofs, n_chunks, chunk);
+        for (auto& e : tv) cudaEventDestroy(e);
+    }
     return 0;
 }
 
@@ -873,6 +921,10 @@ extern "C" int sv_verify_proofs_wire(sv_ctx* c, const sv_fri_shape* shape, const
     if (n_proofs * (size_t)P.num_queries >= (1ull << 31)) return fail(c, -8, "batch too large for one call");
     CK(c, cudaSetDevice(c->device));
     if (grow(c, c->d_scratch, c->scratch_words, 4 * n_proofs)) return -6;
+    if (c->scratch_busy) {   // a SV_MEM_DEVICE call on the caller's stream may still be reading d_scratch
+        CK(c, cudaEventSynchronize(c->ev_scratch));
+        c->scratch_busy = false;
+    }
     rc = wire_verify_host(c, P, F, *shape, *common, vk_cap, blob, stride, n_proofs, accept_bitmap, first_fail, nullptr);
     if (rc) {
         std::string keep = c->err;
@@ -899,6 +951,10 @@ extern "C" int sv_verify_proofs_full(sv_ctx* c, const sv_fri_shape* shape, const
     if (n_proofs * (size_t)P.num_queries >= (1ull << 31)) return fail(c, -8, "batch too large for one call");
     CK(c, cudaSetDevice(c->device));
     if (grow(c, c->d_scratch, c->scratch_words, 4 * n_proofs)) return -6;
+    if (c->scratch_busy) {   // a SV_MEM_DEVICE call on the caller's stream may still be reading d_scratch
+        CK(c, cudaEventSynchronize(c->ev_scratch));
+        c->scratch_busy = false;
+    }
     rc = wire_verify_host(c, P, F, *shape, circuit->common, vk_cap, blob, stride, n_proofs, accept_bitmap, first_fail, circuit);
     if (rc) {
         std::string keep = c->err;

@@ -49,6 +49,10 @@ SVB_HD alg2 alg_scalar_mul_add(fp2 s, alg2 y, alg2 c) { alg2 r; r.a = add2(mul2(
 // wires used / constraints produced by a gate (0 wires = unknown kind)
 SVB_HD void plonk_gate_dims(u32 kind, u32 param, u32 param2, u32 param3, u32& wires, u32& constraints, u32& constants) {
     wires = constraints = constants = 0;
+    // A gate parameter comes straight from a gate-id string (sv_plonk_gate_from_id): bound it BEFORE the u32 products below
+    // can wrap (ArithmeticExtensionGate { num_ops: 0x80000001 } would otherwise look like 8 wires / 2 constraints and then
+    // run its loops 2^31 times over the openings).  No gate of the reference has more than 135 wires; 0 wires = refused.
+    if (param > SV_MAX_GATE_CONSTRAINTS || param2 > 64 || param3 > 64) return;
     switch (kind) {
         case SV_GATE_NOOP: wires = 1; break;
         case SV_GATE_CONSTANT: wires = param; constraints = param; constants = param; break;

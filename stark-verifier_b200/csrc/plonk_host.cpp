@@ -51,6 +51,42 @@ extern "C" int sv_plonk_gate_from_id(const char* id, sv_plonk_gate* out) {
     return 0;
 }
 
+// CommonData::from (types/common_data.rs:224-270): field-by-field, with CustomGateRef::from (gates/mod.rs:138-196) per gate.
+extern "C" int sv_circuit_from_common_data(const sv_common_circuit_data* cd, sv_fri_shape* shape_out, sv_plonk_circuit* circuit_out) {
+    if (!cd || !shape_out || !circuit_out) return -1;
+    if (cd->num_gates == 0 || cd->num_gates > SV_MAX_GATES || !cd->gate_ids || !cd->selector_indices) return -2;
+    if (cd->num_selector_groups == 0 || cd->num_selector_groups > SV_MAX_SELECTORS || !cd->group_starts || !cd->group_ends) return -2;
+    if (cd->num_k_is != cd->common.num_routed_wires || cd->num_k_is > SV_MAX_ROUTED_WIRES || !cd->k_is) return -2;
+    if (cd->num_reduction_steps && !cd->reduction_arity_bits) return -2;
+    sv_fri_shape s;
+    if (int rc = sv_fri_shape_from_common(&cd->common, cd->degree_bits, cd->rate_bits, cd->cap_height, cd->num_query_rounds,
+                                          cd->proof_of_work_bits, cd->num_reduction_steps, cd->reduction_arity_bits, cd->hiding, cd->hash_kind, &s))
+        return rc < 0 ? rc - 10 : rc;
+    sv_plonk_circuit C;
+    memset(&C, 0, sizeof C);
+    C.common = cd->common;
+    C.degree_bits = cd->degree_bits;
+    C.num_gate_constraints = cd->num_gate_constraints;
+    C.num_selectors = cd->num_selector_groups;
+    for (u32 g = 0; g < cd->num_selector_groups; g++) { C.group_lo[g] = cd->group_starts[g]; C.group_hi[g] = cd->group_ends[g]; }
+    C.num_gates = cd->num_gates;
+    for (u32 i = 0; i < cd->num_gates; i++) {
+        if (sv_plonk_gate_from_id(cd->gate_ids[i], &C.gates[i])) return -3;          // unimplemented!() in the reference
+        const u32 sel = cd->selector_indices[i];
+        if (sel >= cd->num_selector_groups || i < cd->group_starts[sel] || i >= cd->group_ends[sel]) return -4;   // SelectorsInfo invariant
+        C.gates[i].selector_index = sel;
+    }
+    for (u32 j = 0; j < cd->num_k_is; j++) {
+        if (!is_canonical(cd->k_is[j])) return -5;
+        C.k_is[j] = cd->k_is[j];
+    }
+    if (int rc = plonk_circuit_check(C)) return rc < 0 ? rc - 20 : rc;
+    if (int rc = plonk_shape_matches(s, C)) return rc < 0 ? rc - 30 : rc;
+    *shape_out = s;
+    *circuit_out = C;
+    return 0;
+}
+
 extern "C" int sv_plonk_circuit_check(const sv_plonk_circuit* circuit) {
     if (!circuit) return -1;
     return plonk_circuit_check(*circuit);

@@ -121,6 +121,25 @@ def poseidon_gate_trace(w, check):
     return cs
 
 
+def gate_id(kind, param):
+    """plonky2's `gate.id()` string of a gate, the key CustomGateRef::from matches on (chip/plonk/gates/mod.rs:138-196)"""
+    ph = "PhantomData<plonky2_field::goldilocks_field::GoldilocksField>"
+    if kind == GATE_NOOP: return "NoopGate"
+    if kind == GATE_PUBLIC_INPUT: return "PublicInputGate"
+    if kind == GATE_CONSTANT: return "ConstantGate { num_consts: %d }" % param
+    if kind == GATE_ARITHMETIC: return "ArithmeticGate { num_ops: %d }" % param
+    if kind == GATE_ARITHMETIC_EXT: return "ArithmeticExtensionGate { num_ops: %d }" % param
+    if kind == GATE_MUL_EXT: return "MulExtensionGate { num_ops: %d }" % param
+    if kind == GATE_BASE_SUM: return "BaseSumGate { num_limbs: %d } + Base: 2" % param
+    if kind == GATE_REDUCING: return "ReducingGate { num_coeffs: %d }" % param
+    if kind == GATE_REDUCING_EXT: return "ReducingExtensionGate { num_coeffs: %d }" % param
+    if kind == GATE_RANDOM_ACCESS:
+        return "RandomAccessGate { bits: %d, num_copies: %d, num_extra_constants: %d, _phantom: %s }<D=2>" % (param[0], param[1], param[2], ph)
+    if kind == GATE_POSEIDON_MDS: return "PoseidonMdsGate(%s)<WIDTH=12>" % ph
+    if kind == GATE_POSEIDON: return "PoseidonGate(%s)<WIDTH=12>" % ph
+    raise ValueError(kind)
+
+
 def _ra(param):
     bits, copies, extra = param
     return bits, copies, extra, 1 << bits, (2 + (1 << bits)) * copies + extra

@@ -139,6 +139,14 @@ def test_unknown_gates_and_inconsistent_circuits_are_refused(svb):
         svb.make_plonk_circuit(bad, C.gates, C.groups, C.k_is, C.num_gate_constraints)
     with pytest.raises(svb.SvError):       # too few constraint slots for the arithmetic gate
         svb.make_plonk_circuit(common, C.gates, C.groups, C.k_is, 2)
+    # a gate parameter that would wrap the u32 wire / constraint products: refused, not "8 wires, 2 constraints"
+    for gates in ([(svb.GATE_ARITHMETIC_EXT, 0x80000001)], [(svb.GATE_ARITHMETIC, 0x40000001)], [(svb.GATE_REDUCING, 0x55555556)],
+                  [(svb.GATE_RANDOM_ACCESS, 4, 0x10000000, 0)], [(svb.GATE_BASE_SUM, 0xFFFFFFFF)], [(svb.GATE_MUL_EXT, 0x2AAAAAAB)]):
+        with pytest.raises(svb.SvError):
+            svb.make_plonk_circuit(common, C.gates + gates, [(0, len(C.gates) + 1)], C.k_is, C.num_gate_constraints)
+    g = svb.plonk_gate_from_id("ArithmeticExtensionGate { num_ops: 2147483649 }")
+    with pytest.raises(svb.SvError):
+        svb.make_plonk_circuit(common, C.gates + [g], [(0, len(C.gates) + 1)], C.k_is, C.num_gate_constraints)
     # FRI shape and circuit must describe the same openings
     other = svb.api._params(C.degree_bits + 1, 3, 1, 2, 2, oracle_num_polys=tuple(params.oracle_num_polys), num_zs=C.num_challenges)
     with pytest.raises(svb.SvError):
@@ -221,3 +229,27 @@ def test_more_witnesses_of_the_recursion_gate_set(svb, orc, seed):
     common = svb.CommonData.for_params(params, num_public_inputs=0, num_constants=C.num_constants)
     other = svb.make_plonk_circuit(common, gates, C.groups, C.k_is, C.num_gate_constraints)
     assert bit(svb.plonk_check_host(params, other, recs, pih, chal), 0) == 0
+
+
+@pytest.mark.parametrize("name", ["one_selector", "two_selectors", "recursion_gate_set"])
+def test_circuit_from_common_data_is_the_hand_filled_circuit(svb, name):
+    """sv_circuit_from_common_data (CommonData::from + CustomGateRef::from, types/common_data.rs:224-270, gates/mod.rs:138-196): from the
+    gate id strings, SelectorsInfo and k_is of the prover's circuit -> byte for byte the sv_plonk_circuit / sv_fri_shape the tests
+    fill by hand; an id outside the reference's table, a gate outside its selector group or a wrong k_is count is refused"""
+    import ctypes
+    C, params, circuit, L = plonk_setup(svb, CONFIGS[name])
+    common = svb.CommonData.for_params(params, num_public_inputs=0, num_constants=C.num_constants)
+    ids = [pp.gate_id(k, p) for k, p in C.gates]
+    sel = [C.selector_index(i) for i in range(len(C.gates))]
+    shape, got = svb.circuit_from_common_data(common, ids, sel, C.groups, C.k_is, C.num_gate_constraints)
+    assert bytes(got) == bytes(circuit)
+    assert bytes(shape) == bytes(params.to_shape())
+    with pytest.raises(svb.SvError):
+        svb.circuit_from_common_data(common, ids[:-1] + ["LookupGate { num_slots: 3 }"], sel, C.groups, C.k_is, C.num_gate_constraints)
+    if len(C.groups) > 1:
+        bad = list(sel)
+        bad[0] = 1 - bad[0]
+        with pytest.raises(svb.SvError):
+            svb.circuit_from_common_data(common, ids, bad, C.groups, C.k_is, C.num_gate_constraints)
+    with pytest.raises(svb.SvError):
+        svb.circuit_from_common_data(common, ids, sel, C.groups, C.k_is[:-1], C.num_gate_constraints)

@@ -153,11 +153,24 @@ def cpu_baseline(params_shape, record_words, base, sample_proofs, threads):
     n = base.shape[0]
     reps = (sample_proofs + n - 1) // n
     recs = np.ascontiguousarray(np.tile(base, (reps, 1))[:sample_proofs])
-    orc.fri_verify_batch(oshape, recs[: min(len(recs), threads)], nthreads=threads)   # warm-up
+    verify = cpu_verify_fn(orc)[0]
+    verify(oshape, recs[: min(len(recs), threads)], nthreads=threads)   # warm-up
     t = time.perf_counter()
-    bm = orc.fri_verify_batch(oshape, recs, nthreads=threads)
+    bm = verify(oshape, recs, nthreads=threads)
     dt = time.perf_counter() - t
     return sample_proofs / dt, dt, bm, recs
+
+
+def cpu_verify_fn(orc):
+    """(batch verifier of the CPU arm, its description): oracle/fast (AVX-512, 8 Merkle proofs per vector; verdicts bit-identical
+    to oracle.c, tests/test_oracle_fast.py) when the CPU has AVX-512, else the scalar oracle.c"""
+    if orc.fast_available() and not os.environ.get("SVB_CPU_SCALAR"):
+        try:
+            orc.fast_lib()
+            return orc.fast_fri_verify_batch, "oracle/fast/fast_avx512.c (AVX-512, 8 Merkle proofs per vector) over oracle/oracle.c"
+        except OSError:
+            pass
+    return orc.fri_verify_batch, "oracle/oracle.c (scalar)"
 
 
 WORKLOAD_TEXT = {"A": "BASELINE configs[1]: {n} proofs/GPU/step, shape A", "B": "BASELINE configs[2]: {n} proofs/GPU/step, shape B",
@@ -215,19 +228,23 @@ def run_reference(args):
     n_gpu_arm = args.proofs or (4096 if wl == "A" else 256)
     distinct = args.distinct or {"A": 256, "B": 2, "outer": 4}[wl]
     recs = np.ascontiguousarray(np.tile(base, (sample, 1)))
+    verify, verify_desc = cpu_verify_fn(orc)
     for _ in range(args.warmup):
-        orc.fri_verify_batch(oshape, recs[:threads], nthreads=threads)
+        verify(oshape, recs[:threads], nthreads=threads)
     t = time.perf_counter()
     for _ in range(args.steps):
-        bm = orc.fri_verify_batch(oshape, recs, nthreads=threads)
+        bm = verify(oshape, recs, nthreads=threads)
     dt = time.perf_counter() - t
     assert all((int(bm[i >> 5]) >> (i & 31)) & 1 for i in range(sample))
     v = sample * args.steps / dt
-    # one thread on a small sample: the per-core figure (SURVEY 8d asks for both)
+    # one thread on a small sample: the per-core figure (SURVEY 8d asks for both), and the scalar restatement beside it
     n1 = max(1, min(sample, {"A": 16, "B": 1, "outer": 1}[wl]))
     t = time.perf_counter()
-    orc.fri_verify_batch(oshape, recs[:n1], nthreads=1)
+    verify(oshape, recs[:n1], nthreads=1)
     v1 = n1 / (time.perf_counter() - t)
+    t = time.perf_counter()
+    orc.fri_verify_batch(oshape, recs[:n1], nthreads=1)
+    v1_scalar = n1 / (time.perf_counter() - t)
     leaf = [84, 135, 20, 16]
     lde = d + r
     perms_per_query = sum((x + 7) // 8 for x in leaf) + 4 * (lde - c) + sum(lde - (i + 1) - c for i in range(d - 5))
@@ -243,8 +260,9 @@ def run_reference(args):
         "config": cfg,
         "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": threads, "kind": "port",
                          "perms_per_sec": v * perms_per_proof, "single_thread_value": v1, "single_thread_perms_per_sec": v1 * perms_per_proof,
-                         "perm_ns_per_thread": 1e9 / (v1 * perms_per_proof),
-                         "sample": f"{sample} proofs x {args.steps} steps, oracle/oracle.c on {threads} threads ({cpu}); "
+                         "perm_ns_per_thread": 1e9 / (v1 * perms_per_proof), "scalar_perm_ns_per_thread": 1e9 / (v1_scalar * perms_per_proof),
+                         "implementation": verify_desc,
+                         "sample": f"{sample} proofs x {args.steps} steps, {verify_desc} on {threads} threads ({cpu}); "
                                    "CPU restatement of reference semantics, not the Rust binary; inputs: committed fixture proof, "
                                    "the product library is not loaded"},
         "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -788,55 +806,35 @@ def main():
 
             def wire_call():
                 hb["bm"] = ctx.verify_proofs_wire(common, vk_cap, cd, p.value, n_proofs=n_host)
-            dt1 = time_host(wire_call, e2e_steps)
+            dt = time_host(wire_call, e2e_steps)
             if not (hb["bm"] == exp_w).all():
                 raise SystemExit(f"rank {rank}: accept bitmap of the wire leg differs from the oracle's")
-            # The headline: the same call from TWO host threads, each with its own sv_ctx (the threading model of the C ABI:
-            # one ctx per host thread and GPU, distinct ctxs fully concurrent), every call a full batch of n_host proofs from
-            # its own pinned buffer.  A lone synchronous call exposes the latency of its batch transcript (~3 ms of ~14: the
-            # query phase needs the query indices, the last thing the transcript yields); with a second call in flight that
-            # latency is hidden behind the other call's copies and kernels.  e2e_steps calls in total.
-            import threading
-            ctx2 = svb.Context(local_rank)
-            p2 = ctypes.c_void_p()
-            if svb.lib().sv_host_alloc(n_host * nb, ctypes.byref(p2)) != 0:
-                raise SystemExit("sv_host_alloc failed")
-            ctypes.memmove(p2.value, p.value, n_host * nb)
-            res = {}
-
-            def worker(c, ptr, reps, key):
-                for _ in range(reps):
-                    res[key] = c.verify_proofs_wire(common, vk_cap, cd, ptr, n_proofs=n_host)
-
-            def two_in_flight(reps):
-                th = [threading.Thread(target=worker, args=(ctx, p.value, (reps + 1) // 2, 0)),
-                      threading.Thread(target=worker, args=(ctx2, p2.value, reps // 2, 1))]
-                for t_ in th:
-                    t_.start()
-                for t_ in th:
-                    t_.join()
-            two_in_flight(4)
-            barrier()
-            t0 = time.perf_counter()
-            two_in_flight(e2e_steps)
-            barrier()
-            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-            if not all((res[k_] == exp_w).all() for k_ in res):
-                raise SystemExit(f"rank {rank}: accept bitmap of the two-calls-in-flight wire leg differs from the oracle's")
-            svb.lib().sv_host_free(p2)
-            ctx2.close()
             e2e = {"value": world * n_host * e2e_steps / dt, "unit": "proofs/s", "h2d_bytes_per_step": int(n_host * nb),
-                   "calls_in_flight": 2,
-                   "single_call": {"value": world * n_host * e2e_steps / dt1, "unit": "proofs/s",
-                                   "note": "one synchronous sv_verify_proofs_wire call at a time (the batch transcript's latency is exposed)"},
                    "d2h_bytes_per_step": int(hwords * 4), "steps": e2e_steps, "proofs_per_step_per_gpu": n_host, "host_binding": numa,
                    "proof_bytes": int(nb), "public_inputs": n_pi,
-                   "entry_point": "sv_verify_proofs_wire (bytes -> verdict: unpack, public-inputs hash, Fiat-Shamir transcript and query "
-                                  "phase on the device; headers first, transcript once per batch)",
+                   "entry_point": "sv_verify_proofs_wire, one synchronous call per step (bytes -> verdict: unpack, public-inputs hash, "
+                                  "Fiat-Shamir transcript and query phase on the device; headers first, transcript in two parts)",
                    "corrupted": "1/64 proofs, five kinds round-robin as byte flips; bitmap == the oracle's (its own wire reader + transcript)"}
+            if world == 1 and wl == "A":
+                # the same entry point on a 4x larger batch per call: the ~2.6 ms before the first query kernel can start (header
+                # copies + the first transcript part, the one latency a lone call cannot hide) amortise over 4x the bytes
+                big = 4 * n_host
+                pb = ctypes.c_void_p()
+                if svb.lib().sv_host_alloc(big * nb, ctypes.byref(pb)) == 0:
+                    try:
+                        for r_ in range(4):
+                            ctypes.memmove(pb.value + r_ * n_host * nb, p.value, n_host * nb)
+                        hb2 = {}
+
+                        def big_call():
+                            hb2["bm"] = ctx.verify_proofs_wire(common, vk_cap, cd, pb.value, n_proofs=big)
+                        dtb = time_host(big_call, max(2, e2e_steps // 4))
+                        if not (hb2["bm"] == np.tile(exp_w, 4)).all():
+                            raise SystemExit("accept bitmap of the large-batch wire leg differs from the oracle's")
+                        e2e["large_batch"] = {"value": big * max(2, e2e_steps // 4) / dtb, "unit": "proofs/s", "proofs_per_call": big,
+                                              "h2d_bytes_per_call": int(big * nb)}
+                    finally:
+                        svb.lib().sv_host_free(pb)
             # copy-only ceiling of the same bytes
             stage = torch.empty(n_host * nb, dtype=torch.uint8, device="cuda")
             hview = torch.from_numpy(hostb.reshape(-1))
@@ -941,8 +939,8 @@ def main():
         out["cpu_baseline"] = {"value": v, "unit": "proofs/s", "cores": threads, "kind": "port",
                                "perms_per_sec": v * perms_per_proof, "single_thread_value": v1,
                                "single_thread_perms_per_sec": v1 * perms_per_proof, "perm_ns_per_thread": 1e9 / (v1 * perms_per_proof),
-                               "gpu_bitmap_equal_on_sample": True,
-                               "sample": f"{sample} proofs of the same workload in {dt:.1f} s on {threads} threads; oracle/oracle.c, "
+                               "gpu_bitmap_equal_on_sample": True, "implementation": cpu_verify_fn(orc)[1],
+                               "sample": f"{sample} proofs of the same workload in {dt:.1f} s on {threads} threads; {cpu_verify_fn(orc)[1]}, "
                                          "CPU restatement of reference semantics (not the Rust binary)"}
     print(json.dumps(out))
     if world > 1:

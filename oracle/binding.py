@@ -34,8 +34,10 @@ class OrcLayout(ctypes.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "_build", "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "wire.c", "plonk.c", "oracle.h", "orc_field.h", "poseidon_g_constants.h", "poseidon_b_constants.h")]
-    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "wire.c", "plonk.c", "oracle.h", "orc_field.h", "poseidon_g_constants.h", "poseidon_b_constants.h",
+                                             os.path.join("fast", "fast_avx512.c"))]
+    fast = os.path.join(_HERE, "_build", "liboracle_fast.so")
+    if force or not os.path.exists(so) or not os.path.exists(fast) or any(os.path.getmtime(s) > min(os.path.getmtime(so), os.path.getmtime(fast)) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
 
@@ -263,3 +265,41 @@ def plonk_challenges(shape: OrcShape, record, circuit_digest, pi_hash, num_chall
     out = np.zeros(3 * num_challenges, dtype=np.uint64)
     L.orc_plonk_challenges(ctypes.byref(shape), rec.ctypes.data, cd.ctypes.data, ph.ctypes.data, num_challenges, out.ctypes.data)
     return out
+
+
+# ---- oracle/fast: the AVX-512 arm of the CPU baseline (bench-only; same verdicts as orc_fri_verify_batch) -----------------
+_FAST = None
+
+
+def fast_available() -> bool:
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        return False
+    return " avx512f" in flags and " avx512dq" in flags
+
+
+def fast_lib():
+    global _FAST
+    if _FAST is None:
+        build()
+        so = os.path.join(_HERE, "_build", "liboracle_fast.so")
+        L = ctypes.CDLL(so)
+        L.orc_fast_poseidon8.argtypes = [ctypes.c_void_p]
+        L.orc_fast_fri_verify_batch.argtypes = [ctypes.POINTER(OrcShape), ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int]
+        _FAST = L
+    return _FAST
+
+
+def fast_poseidon8(states):
+    a = np.array(states, dtype=np.uint64, copy=True).reshape(8, 12)
+    fast_lib().orc_fast_poseidon8(a.ctypes.data)
+    return a
+
+
+def fast_fri_verify_batch(shape: OrcShape, records, nthreads=1):
+    records = np.ascontiguousarray(records, dtype=np.uint64)
+    n = records.shape[0]
+    bm = np.zeros((n + 31) // 32, dtype=np.uint32)
+    fast_lib().orc_fast_fri_verify_batch(ctypes.byref(shape), records.ctypes.data, n, bm.ctypes.data, nthreads)
+    return bm

@@ -384,6 +384,14 @@ static int all_canonical(const uint64_t *w, size_t n) {
     return 1;
 }
 
+/* oracle/fast/fast_avx512.c (bench-only) includes this file and verifies the Merkle proofs of a proof 8 at a time with
+ * AVX-512; it then runs check_consistency with this flag set for everything else.  Never set by the oracle itself. */
+static _Thread_local int orc_merkle_elsewhere = 0;
+static int merkle_step(const uint64_t *leaf, size_t leaf_len, uint64_t index, const uint64_t *siblings, size_t depth,
+                       const uint64_t *cap, size_t cap_index) {
+    return orc_merkle_elsewhere ? 1 : orc_merkle_verify(leaf, leaf_len, index, siblings, depth, cap, cap_index);
+}
+
 /* check_consistency (fri_chip.rs:228-327) for one query round.  returns fail code. */
 static int check_consistency(const orc_shape *s, const orc_layout *L, const uint64_t *rec, uint32_t round,
                              const orc_fp2 reduced_openings[2]) {
@@ -414,7 +422,7 @@ static int check_consistency(const orc_shape *s, const orc_layout *L, const uint
     /* :254-260, :85-110 verify_initial_merkle_proof */
     for (int k = 0; k < 4; k++) {
         const uint64_t *cap = rec + L->off_init_caps + (size_t)k * L->ncap * 4;
-        if (!orc_merkle_verify(q + L->q_off_init_evals[k], L->leaf_len[k], x_index,
+        if (!merkle_step(q + L->q_off_init_evals[k], L->leaf_len[k], x_index,
                                q + L->q_off_init_sibs[k], L->init_depth, cap, cap_index))
             return ORC_FAIL_INIT_MERKLE;
     }
@@ -516,7 +524,7 @@ static int check_consistency(const orc_shape *s, const orc_layout *L, const uint
         uint64_t coset_index = 0;
         for (uint32_t j = 0; j < coset_len; j++) coset_index |= (uint64_t)coset_index_bits[j] << j;
         const uint64_t *cap = rec + L->off_step_caps + (size_t)i * L->ncap * 4;
-        if (!orc_merkle_verify(evals, 2 * arity, coset_index, q + L->q_off_step_sibs[i], L->step_depth[i], cap, cap_index))
+        if (!merkle_step(evals, 2 * arity, coset_index, q + L->q_off_step_sibs[i], L->step_depth[i], cap, cap_index))
             return ORC_FAIL_STEP_MERKLE;
         for (uint32_t b = 0; b < arity_bits; b++) x = orc_mul(x, x);   /* :313 exp_power_of_2(x, arity_bits) */
         xb = coset_index_bits; xb_len = coset_len;                /* :315 */

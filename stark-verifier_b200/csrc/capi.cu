@@ -39,6 +39,8 @@ struct sv_ctx {
     u64* d_hdr = nullptr; size_t hdr_words = 0;                        // record headers of a whole host batch (transcript)
     cudaStream_t fs_stream = nullptr;                                  // the batch-wide transcript of the host pipeline
     cudaEvent_t ev_hdr = nullptr, ev_fs = nullptr;
+    cudaStream_t fs_part_stream[2] = {};                               // transcript parts 1 and 2 of a wire batch (part 0: fs_stream)
+    cudaEvent_t ev_part[3] = {}, ev_hdr_ready = nullptr;
     cudaEvent_t ev_copied[SV_NBUF] = {}, ev_done[SV_NBUF] = {}, ev_join[SV_NKS] = {};
     // wire format (sv_wire_unpack_batch_gpu, sv_verify_proofs_wire): offset tables of the last (shape, common) seen,
     // the verifier key's cap, wire-byte staging ring, malformed flags
@@ -130,9 +132,12 @@ extern "C" int sv_ctx_create(int device, sv_ctx** out) {
             int lo = 0, hi = 0;
             CK(nullptr, cudaDeviceGetStreamPriorityRange(&lo, &hi));
             CK(nullptr, cudaStreamCreateWithPriority(&c->fs_stream, cudaStreamNonBlocking, hi));
+            for (auto& st : c->fs_part_stream) CK(nullptr, cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi));
         }
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_hdr, cudaEventDisableTiming));
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_fs, cudaEventDisableTiming));
+        CK(nullptr, cudaEventCreateWithFlags(&c->ev_hdr_ready, cudaEventDisableTiming));
+        for (auto& e : c->ev_part) CK(nullptr, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (int i = 0; i < SV_NBUF; i++) {
             CK(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
             CK(nullptr, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
@@ -183,11 +188,13 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaFree(c->d_lde_hi);
     auto drop_s = [](cudaStream_t s) { if (s) cudaStreamDestroy(s); };
     auto drop_e = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
-    drop_e(c->ev_hdr); drop_e(c->ev_fs);
+    drop_e(c->ev_hdr); drop_e(c->ev_fs); drop_e(c->ev_hdr_ready);
+    for (auto& e : c->ev_part) drop_e(e);
     for (int i = 0; i < SV_NBUF; i++) { drop_e(c->ev_copied[i]); drop_e(c->ev_done[i]); }
     for (int i = 0; i < SV_NKS; i++) drop_e(c->ev_join[i]);
     for (auto& pr : c->tev) { drop_e(pr.first); drop_e(pr.second); }
     drop_s(c->fs_stream);
+    for (auto& st : c->fs_part_stream) drop_s(st);
     drop_s(c->own_stream);
     for (int i = 0; i < SV_NKS - 1; i++) drop_s(c->aux_stream[i]);
     drop_s(c->copy_stream);
@@ -208,6 +215,7 @@ extern "C" int sv_ctx_synchronize(sv_ctx* c) {
     for (int i = 0; i < SV_NKS - 1; i++) CK(c, cudaStreamSynchronize(c->aux_stream[i]));
     CK(c, cudaStreamSynchronize(c->copy_stream));
     CK(c, cudaStreamSynchronize(c->fs_stream));
+    for (auto& st : c->fs_part_stream) CK(c, cudaStreamSynchronize(st));
     return 0;
 }
 extern "C" uint64_t sv_ctx_launch_count(const sv_ctx* c) { return c ? c->launches : 0; }
@@ -439,14 +447,15 @@ static int make_params(sv_ctx* c, const sv_fri_shape& s, FriKernelParams& P) {
 }
 
 // enqueue prepare + query (+ finalize) for `n` proofs whose records are at d_records
+// force: 0 = choose by batch size, 1 = lane-cooperative kernel (lowest latency), 2 = one thread per proof (most throughput)
 static int enqueue_challenges(sv_ctx* c, FriKernelParams& P, const FsParams& F, size_t n, u64* d_records, const u64* d_pi,
-                              cudaStream_t s) {
+                              cudaStream_t s, int force = 0) {
     P.n_proofs = (u32)n;
     // SVB_FS_COOP: 1 = always lane-cooperative, 0 = never, unset = by batch size.  The cooperative kernel has the
     // lower latency (11.9 vs 24.4 us per permutation) but 4.6x less throughput (254 vs 1 177 M perms/s), so it wins
     // while the batch is latency-bound: below ~8k proofs per call.
     static const int coop_env = [] { const char* e = getenv("SVB_FS_COOP"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
-    const bool coop = coop_env < 0 ? n < 8192 : coop_env == 1;
+    const bool coop = force ? force == 1 : (coop_env < 0 ? n < 8192 : coop_env == 1);
     if (P.hash_kind == SV_HASH_POSEIDON_GOLDILOCKS && coop) {
         // lane-cooperative transcript: 16 lanes per proof
         fri_challenges_coop_kernel<<<(unsigned)((n * SVB_COOP_GROUP + 127) / 128), 128, 0, s>>>(d_records, P, F, d_pi);
@@ -838,25 +847,50 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
     }
     c->launches += 2;
     if (trace) cudaEventRecord(tv[6], fss);
-    FriKernelParams Ph = P;
-    Ph.L.record_words = (u32)hw;                            // the headers are packed back to back
-    if (circuit) {   // plonk challenges: the prefix of the transcript below, kept this time
-        Ph.n_proofs = (u32)n_proofs;
-        SVB_LAUNCH_KIND(P.hash_kind, plonk_challenges_kernel, (unsigned)((n_proofs + SVB_FS_BLOCK - 1) / SVB_FS_BLOCK), SVB_FS_BLOCK, fss,
-                        c->d_hdr, Ph, F, c->d_pi, c->d_chal);
-        c->launches++;
+    CK(c, cudaEventRecord(c->ev_hdr_ready, fss));
+    // The transcript in three parts, each on its own high-priority stream, all started now.  A transcript is ~155 DEPENDENT
+    // permutations per proof: the lane-cooperative kernel has the lower latency (1.7 ms for a few hundred proofs, 3.2 ms for
+    // 4 096) but a quarter of the throughput, the thread-per-proof kernel needs 4.3 ms and almost no GPU time.  So the proofs of
+    // chunk 0 and of chunks 1-2 get the cooperative kernel -- their query kernels start after ~2 ms and keep the GPU busy
+    // until the third part, everything else on the thread-per-proof kernel, is done.  (One transcript for the whole batch
+    // left the GPU idle for 3.3 of 14.4 ms: tools/lab/wire_trace.sh, SVB_TRACE.)
+    static const int parts_env = [] { const char* e = getenv("SVB_FS_PARTS"); return e ? atoi(e) : 2; }();
+    static const int lead_env = [] { const char* e = getenv("SVB_FS_LEAD"); return e ? atoi(e) : 2; }();   // chunks in the first part
+    const size_t part_end[3] = {std::min(n_proofs, (size_t)lead_env * chunk), std::min(n_proofs, (size_t)(lead_env + 2) * chunk), n_proofs};
+    cudaStream_t pst[3] = {fss, c->fs_part_stream[0], c->fs_part_stream[1]};
+    int part_of_first[3] = {0, 0, 0};
+    {
+        size_t lo = 0;
+        for (int pi = 0; pi < 3; pi++) {
+            const size_t hi_ = parts_env >= 3 ? part_end[pi] : (parts_env == 2 ? (pi == 0 ? part_end[0] : n_proofs) : n_proofs);
+            if (hi_ <= lo) { part_of_first[pi] = -1; continue; }
+            const size_t cnt = hi_ - lo;
+            cudaStream_t ps = pst[pi];
+            if (pi) CK(c, cudaStreamWaitEvent(ps, c->ev_hdr_ready, 0));
+            FriKernelParams Ph = P;
+            Ph.L.record_words = (u32)hw;                    // the headers are packed back to back
+            if (circuit) {   // plonk challenges: the prefix of the transcript below, kept this time
+                Ph.n_proofs = (u32)cnt;
+                SVB_LAUNCH_KIND(P.hash_kind, plonk_challenges_kernel, (unsigned)((cnt + SVB_FS_BLOCK - 1) / SVB_FS_BLOCK), SVB_FS_BLOCK, ps,
+                                c->d_hdr + lo * hw, Ph, F, c->d_pi + 4 * lo, c->d_chal + 3 * (size_t)nch * lo);
+                c->launches++;
+            }
+            const int force = hi_ == n_proofs && cnt > 2048 && lo > 0 ? 2 : 0;   // the big last part: thread per proof
+            if ((rc = enqueue_challenges(c, Ph, F, cnt, c->d_hdr + lo * hw, c->d_pi + 4 * lo, ps, force))) return rc;
+            if (trace && pi == 0) cudaEventRecord(tv[7], ps);
+            if (circuit) {   // the vanishing-polynomial identity reads headers only (zeta is in them now)
+                PlonkRecordView V = {(u32)hw, P.L.off_open0, P.L.off_open1, P.L.off_zeta};
+                plonk_check_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, ps>>>(c->d_hdr + lo * hw, V, c->d_circuit, c->d_pi + 4 * lo,
+                                                                                 c->d_chal + 3 * (size_t)nch * lo, (u32)cnt, c->d_pbm + lo / 32);
+                c->launches++;
+            }
+            CK(c, cudaGetLastError());
+            CK(c, cudaEventRecord(c->ev_part[pi], ps));
+            part_of_first[pi] = (int)(lo / chunk);
+            lo = hi_;
+        }
     }
-    if ((rc = enqueue_challenges(c, Ph, F, n_proofs, c->d_hdr, c->d_pi, fss))) return rc;
-    if (trace) cudaEventRecord(tv[7], fss);
-    if (circuit) {   // the vanishing-polynomial identity reads headers only (zeta is in them now)
-        PlonkRecordView V = {(u32)hw, P.L.off_open0, P.L.off_open1, P.L.off_zeta};
-        plonk_check_kernel<<<(unsigned)((n_proofs + 127) / 128), 128, 0, fss>>>(c->d_hdr, V, c->d_circuit, c->d_pi, c->d_chal, (u32)n_proofs,
-                                                                                  c->d_pbm);
-        c->launches++;
-    }
-    CK(c, cudaGetLastError());
-    CK(c, cudaEventRecord(c->ev_fs, fss));
-    if (trace) cudaEventRecord(tv[2], fss);
+    if (trace) cudaEventRecord(tv[2], c->fs_part_stream[1]);
     // ---- query rounds, chunk by chunk ------------------------------------------------------------------------
     WireDims dq = W.d;
     dq.query_base = 0;                                      // a chunk buffer row holds the query rounds only
@@ -871,7 +905,11 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
         CK(c, cudaMemcpy2DAsync(c->d_wire[b], q_pitch, blob + first * stride + front_bytes, stride, q_bytes, cnt, cudaMemcpyHostToDevice, cs));
         CK(c, cudaEventRecord(c->ev_copied[b], cs));
         CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
-        CK(c, cudaStreamWaitEvent(k, c->ev_fs, 0));
+        {   // the transcript part that covers this chunk (parts end on chunk boundaries)
+            int pi = 2;
+            while (pi > 0 && (part_of_first[pi] < 0 || (size_t)part_of_first[pi] > i)) pi--;
+            CK(c, cudaStreamWaitEvent(k, c->ev_part[pi], 0));
+        }
         dim3 grid((unsigned)cnt, 1 + W.d.num_queries);
         wire_unpack_kernel<<<grid, SVB_WIRE_BLOCK, 0, k>>>(c->d_wire[b], 0, q_pitch, dq, W.hdr_src, W.q_src, W.chk, W.vk, c->d_stage[b],
                                                            c->d_mal + first, c->d_hdr + first * hw);

@@ -22,19 +22,22 @@ for vals in rows[2:]:
             print(f"  {h:75s} {v} {u}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hi = next(i for i, r in enumerate(rows) if "Source" in r and "Address" in r)
-hdr = rows[hi]; ix = {h: i for i, h in enumerate(hdr)}
-stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-ex, sm, st = collections.Counter(), collections.Counter(), collections.Counter()
-for r in rows[hi + 1:]:
-    if len(r) < len(hdr): continue
-    t = r[ix["Source"]].strip()
-    if not t: continue
-    op = t.split()[1] if t.startswith("@") else t.split()[0]
-    ex[op] += int(r[ix["Instructions Executed"]] or 0); sm[op] += int(r[ix["# Samples"]] or 0)
-    for h in stalls: st[h] += int(r[ix[h]] or 0)
-te, ts = sum(ex.values()), sum(sm.values())
-print(f"== source page: {te} warp instructions, {ts} samples")
-for op, e in ex.most_common(18):
-    print(f"  {op:20s} exec {100 * e / te:5.1f}%   samples {100 * sm[op] / max(1, ts):5.1f}%")
-print("  stalls:", {k[6:]: round(100 * v / max(1, ts), 1) for k, v in st.most_common(8)})
+# one section per captured launch, each starting with its own header row
+heads = [i for i, r in enumerate(rows) if "Source" in r and "Address" in r]
+for n, hi in enumerate(heads[:3]):                      # the first three launches are enough for a summary
+    hdr = rows[hi]; ix = {h: i for i, h in enumerate(hdr)}
+    end = heads[n + 1] if n + 1 < len(heads) else len(rows)
+    stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    ex, sm, st = collections.Counter(), collections.Counter(), collections.Counter()
+    for r in rows[hi + 1:end]:
+        if len(r) < len(hdr): continue
+        t = r[ix["Source"]].strip()
+        if not t or not (r[ix["Instructions Executed"]] or "0").isdigit(): continue
+        op = t.split()[1] if t.startswith("@") else t.split()[0]
+        ex[op] += int(r[ix["Instructions Executed"]] or 0); sm[op] += int(r[ix["# Samples"]] or 0)
+        for h in stalls: st[h] += int(r[ix[h]] or 0)
+    te, ts = sum(ex.values()), sum(sm.values())
+    print(f"== source page (launch {n}): {te} warp instructions, {ts} samples")
+    for op, e in ex.most_common(18):
+        print(f"  {op:20s} exec {100 * e / max(1, te):5.1f}%   samples {100 * sm[op] / max(1, ts):5.1f}%")
+    print("  stalls:", {k[6:]: round(100 * v / max(1, ts), 1) for k, v in st.most_common(8)})

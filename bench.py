@@ -727,6 +727,8 @@ def main():
     # resident data with the Fiat-Shamir transcript on the device as well (sv_fri_verify_batch_fs): challenge fields zeroed
     resident_fs = None
     try:
+        if n * rw * 8 > 40e9:
+            raise RuntimeError("skipped: a second copy of the records would not fit beside the first")
         d_fs = d_recs.clone()
         d_fs[:, L.off_alpha:L.header_words] = 0
         ph_dev = torch.from_numpy(np.ascontiguousarray(np.tile(pih, ((n + distinct - 1) // distinct, 1))[:n]).view(np.int64)).cuda()

@@ -92,6 +92,21 @@ pub const SV_MAX_ROUTED_WIRES: usize = 128;
 #[derive(Clone, Copy, Default)]
 pub struct sv_plonk_gate { pub kind: u32, pub param: u32, pub param2: u32, pub param3: u32, pub selector_index: u32 }
 
+/// `sv_common_circuit_data`: plonky2's CommonCircuitData as plain arrays (what CommonData::from reads)
+#[repr(C)]
+pub struct sv_common_circuit_data {
+    pub common: sv_plonk_common,
+    pub rate_bits: u32, pub cap_height: u32, pub proof_of_work_bits: u32, pub num_query_rounds: u32,
+    pub hiding: u32, pub degree_bits: u32,
+    pub num_reduction_steps: u32, pub reduction_arity_bits: *const u32,
+    pub num_gate_constraints: u32,
+    pub num_gates: u32, pub gate_ids: *const *const c_char,
+    pub selector_indices: *const u32,
+    pub num_selector_groups: u32, pub group_starts: *const u32, pub group_ends: *const u32,
+    pub num_k_is: u32, pub k_is: *const u64,
+    pub hash_kind: u32,
+}
+
 /// What `eval_vanishing_poly` reads from `CommonData` (types/common_data.rs:56-96).
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -151,6 +166,8 @@ extern "C" {
     pub fn sv_public_inputs_hash(public_inputs: *const u64, n: usize, out: *mut u64) -> c_int;
     // plonk-level checks and the complete verifier
     pub fn sv_plonk_gate_from_id(gate_id: *const c_char, out: *mut sv_plonk_gate) -> c_int;
+    /// CommonData::from + CustomGateRef::from in one call (types/common_data.rs:224-270, gates/mod.rs:138-196)
+    pub fn sv_circuit_from_common_data(cd: *const sv_common_circuit_data, shape_out: *mut sv_fri_shape, circuit_out: *mut sv_plonk_circuit) -> c_int;
     pub fn sv_plonk_circuit_check(circuit: *const sv_plonk_circuit) -> c_int;
     pub fn sv_verify_proofs_full(ctx: *mut sv_ctx, shape: *const sv_fri_shape, circuit: *const sv_plonk_circuit,
                                  constants_sigmas_cap: *const u64, circuit_digest: *const u64, blob: *const u8,

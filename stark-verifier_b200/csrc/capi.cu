@@ -527,6 +527,7 @@ static int fri_verify_host(sv_ctx* c, FriKernelParams& P, size_t n_proofs, const
     // (they travel first: 7 % of the bytes), beside the H2D of the full records; every chunk then gets
     // its challenge fields patched in with one strided device-to-device copy.
     const size_t hw = P.L.header_words, chal_off = P.L.off_alpha, chal_words = hw - chal_off;
+    size_t fs_lead = 0;
     if (fs) {
         if (grow(c, c->d_hdr, c->hdr_words, n_proofs * hw)) return -6;
         CK(c, cudaMemcpy2DAsync(c->d_hdr, hw * 8, records, rw * 8, hw * 8, n_proofs, cudaMemcpyHostToDevice, cs));
@@ -535,8 +536,17 @@ static int fri_verify_host(sv_ctx* c, FriKernelParams& P, size_t n_proofs, const
         CK(c, cudaStreamWaitEvent(c->fs_stream, c->ev_hdr, 0));
         FriKernelParams Ph = P;
         Ph.L.record_words = (u32)hw;          // the headers are packed back to back
-        if ((rc = enqueue_challenges(c, Ph, *fs, n_proofs, c->d_hdr, c->d_pi, c->fs_stream))) return rc;
-        CK(c, cudaEventRecord(c->ev_fs, c->fs_stream));
+        // two parts, as in the wire path: the proofs of the first two chunks on the low-latency kernel, the rest with one
+        // thread per proof beside them (their query kernels are not due before the first chunks are through)
+        fs_lead = std::min(n_proofs, 2 * chunk);
+        if (fs_lead < n_proofs) {
+            CK(c, cudaStreamWaitEvent(c->fs_part_stream[0], c->ev_hdr, 0));
+            FriKernelParams P1 = Ph;
+            if ((rc = enqueue_challenges(c, P1, *fs, n_proofs - fs_lead, c->d_hdr + fs_lead * hw, c->d_pi + 4 * fs_lead, c->fs_part_stream[0], 2))) return rc;
+            CK(c, cudaEventRecord(c->ev_part[1], c->fs_part_stream[0]));
+        }
+        if ((rc = enqueue_challenges(c, Ph, *fs, fs_lead, c->d_hdr, c->d_pi, c->fs_stream, fs_lead < n_proofs ? 1 : 0))) return rc;
+        CK(c, cudaEventRecord(c->ev_part[0], c->fs_stream));
     }
     for (size_t i = 0; i < n_chunks; i++) {
         int b = (int)(i % SV_NBUF);
@@ -547,7 +557,7 @@ static int fri_verify_host(sv_ctx* c, FriKernelParams& P, size_t n_proofs, const
         CK(c, cudaEventRecord(c->ev_copied[b], cs));
         CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
         if (fs) {
-            CK(c, cudaStreamWaitEvent(k, c->ev_fs, 0));
+            CK(c, cudaStreamWaitEvent(k, c->ev_part[first < fs_lead ? 0 : 1], 0));
             CK(c, cudaMemcpy2DAsync(c->d_stage[b] + chal_off, rw * 8, c->d_hdr + first * hw + chal_off, hw * 8, chal_words * 8, cnt,
                                     cudaMemcpyDeviceToDevice, k));
         }
@@ -585,8 +595,30 @@ static int fri_verify_impl(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs
         // SV_MEM_DEVICE calls return without synchronising and all share d_scratch (reduced openings): when the caller moved to
         // another stream since the last such call (sv_ctx_set_stream), this call is ordered behind it
         if (c->scratch_busy && c->scratch_stream != c->stream) CK(c, cudaStreamWaitEvent(c->stream, c->ev_scratch, 0));
-        if (fs && (rc = enqueue_challenges(c, P, *fs, n_proofs, const_cast<u64*>(records), pi_hashes, c->stream))) return rc;
-        rc = enqueue_fri(c, P, n_proofs, records, c->d_scratch, accept_bitmap, first_fail, c->stream);
+        const size_t lead = fs && n_proofs >= 4096 ? 1024 : 0;
+        if (fs && lead) {
+            // The transcript (~155 dependent permutations per proof) in two parts on the high-priority side streams, both started
+            // now: the first 1 024 proofs on the lane-cooperative kernel (lowest latency, ~2 ms), the rest with one thread per
+            // proof (4.3 ms, almost no GPU time); the query kernel of the first part hides the rest of the second transcript.
+            u64* recs = const_cast<u64*>(records);
+            const size_t rw = P.L.record_words;
+            CK(c, cudaEventRecord(c->ev_hdr_ready, c->stream));
+            CK(c, cudaStreamWaitEvent(c->fs_stream, c->ev_hdr_ready, 0));
+            CK(c, cudaStreamWaitEvent(c->fs_part_stream[0], c->ev_hdr_ready, 0));
+            FriKernelParams P0 = P, P1 = P;
+            if ((rc = enqueue_challenges(c, P0, *fs, lead, recs, pi_hashes, c->fs_stream, 1))) return rc;
+            CK(c, cudaEventRecord(c->ev_part[0], c->fs_stream));
+            if ((rc = enqueue_challenges(c, P1, *fs, n_proofs - lead, recs + lead * rw, pi_hashes + 4 * lead, c->fs_part_stream[0], 2))) return rc;
+            CK(c, cudaEventRecord(c->ev_part[1], c->fs_part_stream[0]));
+            CK(c, cudaStreamWaitEvent(c->stream, c->ev_part[0], 0));
+            if ((rc = enqueue_fri(c, P, lead, records, c->d_scratch, accept_bitmap, first_fail, c->stream))) return rc;
+            CK(c, cudaStreamWaitEvent(c->stream, c->ev_part[1], 0));
+            rc = enqueue_fri(c, P, n_proofs - lead, records + lead * rw, c->d_scratch + 4 * lead, accept_bitmap + lead / 32,
+                             first_fail ? first_fail + lead : nullptr, c->stream);
+        } else {
+            if (fs && (rc = enqueue_challenges(c, P, *fs, n_proofs, const_cast<u64*>(records), pi_hashes, c->stream))) return rc;
+            rc = enqueue_fri(c, P, n_proofs, records, c->d_scratch, accept_bitmap, first_fail, c->stream);
+        }
         if (!c->ev_scratch) CK(c, cudaEventCreateWithFlags(&c->ev_scratch, cudaEventDisableTiming));
         CK(c, cudaEventRecord(c->ev_scratch, c->stream));
         c->scratch_stream = c->stream;

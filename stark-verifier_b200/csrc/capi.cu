@@ -32,6 +32,8 @@ struct sv_ctx {
     u64* d_scratch = nullptr; size_t scratch_words = 0;          // reduced openings
     cudaEvent_t ev_scratch = nullptr; cudaStream_t scratch_stream = nullptr; bool scratch_busy = false;   // last SV_MEM_DEVICE user of d_scratch
     u64* d_stage[SV_NBUF] = {}; size_t stage_words[SV_NBUF] = {};   // H2D chunk ring
+    u64* d_leaf[SV_NBUF] = {}; size_t leaf_words[SV_NBUF] = {};     // leaf digests of the chunk in d_stage[b] (fri_leaf_kernel)
+    u64* d_leaf_dev = nullptr; size_t leaf_dev_words = 0;           // the same for a SV_MEM_DEVICE batch
     u32* d_bitmap = nullptr; size_t bitmap_words = 0;
     u32* d_fail = nullptr; size_t fail_words = 0;
     u64* d_pi = nullptr; size_t pi_words = 0;                          // public-input hashes (device-side transcript)
@@ -99,7 +101,7 @@ static int fail(sv_ctx* c, int code, const char* fmt, ...) {
 
 // bump SVB_KERNEL_REV whenever a kernel changes: profiles/traffic_r2.json and the ncu summaries are stamped with it, and bench.py
 // reports DRAM traffic only from a capture of the same revision
-#define SVB_KERNEL_REV "r2.1"
+#define SVB_KERNEL_REV "r2.2"
 extern "C" const char* sv_version(void) { return "stark-verifier_b200 0.2 (sm_100a, kernels " SVB_KERNEL_REV ")"; }
 
 extern "C" const char* sv_last_error(const sv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
@@ -168,7 +170,8 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     cudaFree(c->d_scratch);
-    for (int i = 0; i < SV_NBUF; i++) cudaFree(c->d_stage[i]);
+    for (int i = 0; i < SV_NBUF; i++) { cudaFree(c->d_stage[i]); cudaFree(c->d_leaf[i]); }
+    cudaFree(c->d_leaf_dev);
     cudaFree(c->d_bitmap);
     cudaFree(c->d_fail);
     cudaFree(c->d_pi);
@@ -441,6 +444,8 @@ static int make_params(sv_ctx* c, const sv_fri_shape& s, FriKernelParams& P) {
     std::stable_sort(steps.begin(), steps.end(), [](const std::pair<u32, u32>& a, const std::pair<u32, u32>& b) { return a.first > b.first; });
     cost.insert(cost.end(), steps.begin(), steps.end());
     for (u32 i = 0; i < P.n_classes; i++) P.class_order[i] = cost[i].second;
+    for (u32 i = 0; i < 4; i++)                                  // fri_leaf_kernel: the hashed oracle leaves, heaviest first
+        if (P.L.leaf_len[cost[i].second] > 4) P.leaf_class_order[P.n_leaf_classes++] = cost[i].second;
     u64 omega = svb::pow(7, (GL_P - 1) >> P.L.lde_bits);
     for (u32 i = 0; i < P.L.lde_bits; i++) { P.omega_pow2[i] = omega; omega = mulc(omega, omega); }
     return 0;
@@ -470,8 +475,29 @@ static int enqueue_challenges(sv_ctx* c, FriKernelParams& P, const FsParams& F, 
     return 0;
 }
 
+// Leaf digests before the challenges (fri_leaf_kernel), for the paths whose Fiat-Shamir transcript runs on the device: the
+// challenge-independent quarter of the query phase can then run beside the transcript's latency.  OFF unless SVB_LEAF_SPLIT=1
+// (read per call): measured on B200 (tools/lab/leaf_split.sh, tools/lab/NOTES.md) the leaf warps share the SM sub-partitions
+// with the transcript's few latency-bound warps and slow those down by more than the overlap gains -- wire path 291 k against
+// 299 k proofs/s fused, resident batch with device transcript 265 k against 334 k.  Kept as a knob and as a parity-tested
+// second decomposition of the query phase (tests/test_gpu_leaf_split.py).
+static bool leaf_split_enabled(const FriKernelParams& P) {
+    const char* e = getenv("SVB_LEAF_SPLIT");
+    return P.n_leaf_classes > 0 && e && atoi(e) != 0;
+}
+static size_t leaf_digest_words(const FriKernelParams& P, size_t n) { return n * P.num_queries * 16; }
+static int enqueue_leaf(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_records, u64* d_leaf, cudaStream_t s) {
+    P.n_proofs = (u32)n;
+    P.n_units = (u32)(n * P.num_queries);
+    P.blocks_per_class = (P.n_units + SVB_BLOCK - 1) / SVB_BLOCK;
+    SVB_LAUNCH_KIND(P.hash_kind, fri_leaf_kernel, P.blocks_per_class * P.n_leaf_classes, SVB_BLOCK, s, d_records, P, d_leaf);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return 0;
+}
+
 static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_records, u64* d_scratch, u32* d_bitmap,
-                       u32* d_fail, cudaStream_t s) {
+                       u32* d_fail, cudaStream_t s, const u64* d_leaf = nullptr) {
     const int B = SVB_BLOCK;
     P.n_proofs = (u32)n;
     P.n_units = (u32)(n * P.num_queries);
@@ -483,7 +509,7 @@ static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_rec
     fri_prepare_kernel<<<(unsigned)((n + 31) / 32), SVB_PREP_BLOCK, 0, s>>>(d_records, P, d_scratch, d_bitmap, d_fail);
     cudaEvent_t te = time_begin(c, s);
     const u32 grid = P.n_groups * P.group_blocks * P.n_classes_a + P.blocks_per_class * (P.n_classes - P.n_classes_a);
-    SVB_LAUNCH_KIND(P.hash_kind, fri_query_kernel, grid, B, s, d_records, P, d_scratch, d_bitmap, d_fail);
+    SVB_LAUNCH_KIND(P.hash_kind, fri_query_kernel, grid, B, s, d_records, P, d_scratch, d_bitmap, d_fail, d_leaf);
     time_end(c, te, s);
     c->launches += 2;
     if (d_fail) {
@@ -516,8 +542,11 @@ static int fri_verify_host(sv_ctx* c, FriKernelParams& P, size_t n_proofs, const
     size_t chunk = ((chunk_mb << 20) / (rw * 8)) & ~(size_t)31;
     if (chunk < 32) chunk = 32;
     if (chunk > n_proofs) chunk = (n_proofs + 31) & ~(size_t)31;
-    for (int b = 0; b < SV_NBUF; b++)
+    const bool split = fs && leaf_split_enabled(P);
+    for (int b = 0; b < SV_NBUF; b++) {
         if (grow(c, c->d_stage[b], c->stage_words[b], chunk * rw)) return -6;
+        if (split && grow(c, c->d_leaf[b], c->leaf_words[b], leaf_digest_words(P, chunk))) return -6;
+    }
     cudaStream_t cs = c->copy_stream;
     cudaStream_t ks[SV_NKS] = {c->own_stream};
     for (int i = 1; i < SV_NKS; i++) ks[i] = c->aux_stream[i - 1];
@@ -557,12 +586,13 @@ static int fri_verify_host(sv_ctx* c, FriKernelParams& P, size_t n_proofs, const
         CK(c, cudaEventRecord(c->ev_copied[b], cs));
         CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
         if (fs) {
+            if (split && (rc = enqueue_leaf(c, P, cnt, c->d_stage[b], c->d_leaf[b], k))) return rc;   // needs no challenge
             CK(c, cudaStreamWaitEvent(k, c->ev_part[first < fs_lead ? 0 : 1], 0));
             CK(c, cudaMemcpy2DAsync(c->d_stage[b] + chal_off, rw * 8, c->d_hdr + first * hw + chal_off, hw * 8, chal_words * 8, cnt,
                                     cudaMemcpyDeviceToDevice, k));
         }
         rc = enqueue_fri(c, P, cnt, c->d_stage[b], c->d_scratch + 4 * first, c->d_bitmap + first / 32,
-                         first_fail ? c->d_fail + first : nullptr, k);
+                         first_fail ? c->d_fail + first : nullptr, k, split ? c->d_leaf[b] : nullptr);
         if (rc) return rc;
         CK(c, cudaEventRecord(c->ev_done[b], k));
     }
@@ -610,11 +640,20 @@ static int fri_verify_impl(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs
             CK(c, cudaEventRecord(c->ev_part[0], c->fs_stream));
             if ((rc = enqueue_challenges(c, P1, *fs, n_proofs - lead, recs + lead * rw, pi_hashes + 4 * lead, c->fs_part_stream[0], 2))) return rc;
             CK(c, cudaEventRecord(c->ev_part[1], c->fs_part_stream[0]));
+            // the leaf sponges need no challenge: they fill the GPU while the transcripts run (the transcript kernels only
+            // WRITE challenge fields of the header, the leaf kernel only reads query rounds)
+            const bool split = leaf_split_enabled(P);
+            const u64* lf = nullptr;
+            if (split) {
+                if (grow(c, c->d_leaf_dev, c->leaf_dev_words, leaf_digest_words(P, n_proofs))) return -6;
+                if ((rc = enqueue_leaf(c, P, n_proofs, records, c->d_leaf_dev, c->stream))) return rc;
+                lf = c->d_leaf_dev;
+            }
             CK(c, cudaStreamWaitEvent(c->stream, c->ev_part[0], 0));
-            if ((rc = enqueue_fri(c, P, lead, records, c->d_scratch, accept_bitmap, first_fail, c->stream))) return rc;
+            if ((rc = enqueue_fri(c, P, lead, records, c->d_scratch, accept_bitmap, first_fail, c->stream, lf))) return rc;
             CK(c, cudaStreamWaitEvent(c->stream, c->ev_part[1], 0));
             rc = enqueue_fri(c, P, n_proofs - lead, records + lead * rw, c->d_scratch + 4 * lead, accept_bitmap + lead / 32,
-                             first_fail ? first_fail + lead : nullptr, c->stream);
+                             first_fail ? first_fail + lead : nullptr, c->stream, lf ? lf + leaf_digest_words(P, lead) : nullptr);
         } else {
             if (fs && (rc = enqueue_challenges(c, P, *fs, n_proofs, const_cast<u64*>(records), pi_hashes, c->stream))) return rc;
             rc = enqueue_fri(c, P, n_proofs, records, c->d_scratch, accept_bitmap, first_fail, c->stream);
@@ -761,7 +800,7 @@ static int enqueue_unpack(sv_ctx* c, const WireDev& W, const u64* d_blob8, size_
                           u64* d_pi, u32* d_mal, cudaStream_t s) {
     CK(c, cudaMemsetAsync(d_mal, 0, n * 4, s));
     dim3 grid((unsigned)n, 1 + W.d.num_queries);   // per proof: one block for the header, one per query round
-    wire_unpack_kernel<<<grid, SVB_WIRE_BLOCK, 0, s>>>(d_blob8, first_off, stride, W.d, W.hdr_src, W.q_src, W.chk, W.vk, d_records, d_mal, nullptr);
+    wire_unpack_kernel<<<grid, SVB_WIRE_BLOCK, 0, s>>>(d_blob8, first_off, stride, W.d, W.hdr_src, W.q_src, W.chk, W.vk, d_records, d_mal, nullptr, 0);
     c->launches++;
     if (d_pi) {
         wire_pi_hash_kernel<<<(unsigned)((n + SVB_BLOCK - 1) / SVB_BLOCK), SVB_BLOCK, 0, s>>>(d_blob8, first_off, stride, W.d, n, d_pi, d_mal);
@@ -851,9 +890,11 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
     size_t chunk = ((chunk_mb << 20) / (rw * 8)) & ~(size_t)31;
     if (chunk < 32) chunk = 32;
     if (chunk > n_proofs) chunk = (n_proofs + 31) & ~(size_t)31;
+    const bool split = leaf_split_enabled(P);
     for (int b = 0; b < SV_NBUF; b++) {
         if (grow(c, c->d_stage[b], c->stage_words[b], chunk * rw)) return -6;
         if (grow(c, c->d_wire[b], c->wire_words[b], chunk * q_pitch / 8 + 2)) return -6;
+        if (split && grow(c, c->d_leaf[b], c->leaf_words[b], leaf_digest_words(P, chunk))) return -6;
     }
     // SVB_TRACE=1: a timeline of this call on stderr (lab knob)
     static const bool trace = getenv("SVB_TRACE") != nullptr;
@@ -937,17 +978,30 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
         CK(c, cudaMemcpy2DAsync(c->d_wire[b], q_pitch, blob + first * stride + front_bytes, stride, q_bytes, cnt, cudaMemcpyHostToDevice, cs));
         CK(c, cudaEventRecord(c->ev_copied[b], cs));
         CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
-        {   // the transcript part that covers this chunk (parts end on chunk boundaries)
-            int pi = 2;
-            while (pi > 0 && (part_of_first[pi] < 0 || (size_t)part_of_first[pi] > i)) pi--;
+        int pi = 2;   // the transcript part that covers this chunk (parts end on chunk boundaries)
+        while (pi > 0 && (part_of_first[pi] < 0 || (size_t)part_of_first[pi] > i)) pi--;
+        if (split) {
+            // what needs no challenge goes first: the query rounds into the records, then their leaf digests -- this work fills
+            // the GPU while the transcript of the chunk's part is still running; the finished header follows
+            wire_unpack_kernel<<<dim3((unsigned)cnt, W.d.num_queries), SVB_WIRE_BLOCK, 0, k>>>(c->d_wire[b], 0, q_pitch, dq, W.hdr_src, W.q_src, W.chk,
+                                                                                            W.vk, c->d_stage[b], c->d_mal + first, nullptr, 1);
+            c->launches++;
+            if ((rc = enqueue_leaf(c, P, cnt, c->d_stage[b], c->d_leaf[b], k))) return rc;
             CK(c, cudaStreamWaitEvent(k, c->ev_part[pi], 0));
+            wire_unpack_kernel<<<dim3((unsigned)cnt, 1), SVB_WIRE_BLOCK, 0, k>>>(c->d_wire[b], 0, q_pitch, dq, W.hdr_src, W.q_src, W.chk, W.vk,
+                                                                              c->d_stage[b], c->d_mal + first, c->d_hdr + first * hw, 0);
+            c->launches++;
+        } else {
+            CK(c, cudaStreamWaitEvent(k, c->ev_part[pi], 0));
+            dim3 grid((unsigned)cnt, 1 + W.d.num_queries);
+            wire_unpack_kernel<<<grid, SVB_WIRE_BLOCK, 0, k>>>(c->d_wire[b], 0, q_pitch, dq, W.hdr_src, W.q_src, W.chk, W.vk, c->d_stage[b],
+                                                               c->d_mal + first, c->d_hdr + first * hw, 0);
+            c->launches++;
         }
-        dim3 grid((unsigned)cnt, 1 + W.d.num_queries);
-        wire_unpack_kernel<<<grid, SVB_WIRE_BLOCK, 0, k>>>(c->d_wire[b], 0, q_pitch, dq, W.hdr_src, W.q_src, W.chk, W.vk, c->d_stage[b],
-                                                           c->d_mal + first, c->d_hdr + first * hw);
-        c->launches++;
         u32* d_fail = first_fail ? c->d_fail + first : nullptr;
-        if ((rc = enqueue_fri(c, P, cnt, c->d_stage[b], c->d_scratch + 4 * first, c->d_bitmap + first / 32, d_fail, k))) return rc;
+        if ((rc = enqueue_fri(c, P, cnt, c->d_stage[b], c->d_scratch + 4 * first, c->d_bitmap + first / 32, d_fail, k,
+                              split ? c->d_leaf[b] : nullptr)))
+            return rc;
         if (circuit) {
             plonk_and_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, k>>>(c->d_pbm + first / 32, c->d_bitmap + first / 32, d_fail, (u32)cnt);
             c->launches++;

@@ -48,6 +48,8 @@ struct FriKernelParams {
     u32 n_classes_a;      // classes of phase A: the 4 oracle trees (heaviest first) + the algebra chain
     u32 n_classes;        // 4 + num_steps + 1
     u32 class_order[SV_MAX_STEPS + 5];  // phase A classes, then the step trees (deepest first)
+    u32 n_leaf_classes;   // oracle trees whose leaves are hashed (leaf_len > 4), heaviest first: the grid of fri_leaf_kernel
+    u32 leaf_class_order[4];
     u64 omega_pow2[40];   // omega^(2^i), omega = 7^((p-1)/2^lde_bits)
 };
 
@@ -245,11 +247,60 @@ __global__ void __launch_bounds__(SVB_PREP_BLOCK) fri_prepare_kernel(const u64* 
     }
 }
 
-// The fused query kernel: one thread per (class, unit).
+// The challenge-INDEPENDENT part of a query round: the leaf sponges of the four oracle trees (hash_or_noop of the
+// opened evaluations, chip/merkle_proof_chip.rs:52-53 -- 34 of the 126 permutations of a shape-A query round).  They need
+// neither the query index nor any other challenge, so when the Fiat-Shamir transcript runs on the device (~155
+// DEPENDENT permutations per proof, 2-3 ms of latency that nothing else of the query phase can overlap) these digests
+// CAN be computed beside it, as soon as the bytes are in HBM (opt-in, SVB_LEAF_SPLIT=1: on B200 the contention with the
+// transcript's warps costs more than the overlap gains, see capi.cu); fri_query_kernel then starts its oracle-tree chains from
+// leaf_digests instead of hashing the leaf (same words, same canonical-range check: a non-canonical evaluation is
+// passed on as an all-ones digest, which the chain reports as SV_FAIL_NONCANONICAL exactly as before).
+// One thread per (hashed oracle tree, unit), class-major, heaviest first.  leaf_digests: [unit][4 trees][4 words].
+template <int KIND>
+__global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) fri_leaf_kernel(const u64* __restrict__ records, FriKernelParams P,
+                                                                                   u64* __restrict__ leaf_digests) {
+    __shared__ u64 pscratch[PermScratch<KIND>::array_len(SVB_BLOCK)];
+    const sv_fri_layout& L = P.L;
+    const u32 cls = P.leaf_class_order[blockIdx.x / P.blocks_per_class], blk = blockIdx.x % P.blocks_per_class;
+    const u32 unit = blk * blockDim.x + threadIdx.x;
+    if (unit >= P.n_units) return;
+    const u32 proof = unit / P.num_queries, query = unit - proof * P.num_queries;
+    const u64* leaf = records + (size_t)proof * L.record_words + L.header_words + (size_t)query * L.query_words + L.q_off_init_evals[cls];
+    const u32 leaf_len = L.leaf_len[cls], n_sponge = (leaf_len + 7) >> 3;
+    u64 s[12];
+    bool canon_ok = true;
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+#pragma unroll 1
+    for (u32 it = 0; it < n_sponge; it++) {
+        const u32 off = it * 8, rem = leaf_len - off;
+        u64 w[8];
+        ldg4(leaf + off, w);
+        if (rem > 4) ldg4(leaf + off + 4, w + 4);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if ((u32)i < rem) {
+                s[i] = w[i];
+                canon_ok &= is_canonical(w[i]);
+            }
+        if (it + 1 < n_sponge) {
+            prefetch32(leaf + (it + 1) * 8);
+            if ((it + 1) * 8 + 4 < leaf_len) prefetch32(leaf + (it + 1) * 8 + 4);
+        }
+        permute_dev<KIND>(s, pscratch, SVB_BLOCK);
+    }
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(leaf_digests + ((size_t)unit * 4 + cls) * 4);
+    const u64 bad = ~0ull;
+    o[0] = canon_ok ? make_ulonglong2(canon(s[0]), canon(s[1])) : make_ulonglong2(bad, bad);
+    o[1] = canon_ok ? make_ulonglong2(canon(s[2]), canon(s[3])) : make_ulonglong2(bad, bad);
+}
+
+// The fused query kernel: one thread per (class, unit).  leaf_digests: nullptr = every oracle-tree chain hashes its own
+// leaf (the fused form); otherwise the digests fri_leaf_kernel left for this batch.
 template <int KIND>
 __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) fri_query_kernel(const u64* __restrict__ records, FriKernelParams P,
                                                         const u64* __restrict__ scratch, u32* __restrict__ accept_bitmap,
-                                                        u32* __restrict__ first_fail) {
+                                                        u32* __restrict__ first_fail, const u64* __restrict__ leaf_digests) {
     __shared__ u64 pscratch[PermScratch<KIND>::array_len(SVB_BLOCK)];
     const sv_fri_layout& L = P.L;
     // Grid order.  Phase A: unit groups of `group_blocks` blocks; inside a group the four oracle-tree classes
@@ -289,7 +340,12 @@ __global__ void __launch_bounds__(SVB_BLOCK, SVB_MINBLOCKS_K(KIND)) fri_query_ke
                                      : L.off_step_caps + ((size_t)i * L.ncap + cap_index) * 4);
         const u64* leaf = q + (init ? L.q_off_init_evals[cls] : L.q_off_step_evals[i]);
         const u64* sibs = q + (init ? L.q_off_init_sibs[cls] : L.q_off_step_sibs[i]);
-        u32 rc = merkle_chain<KIND>(leaf, init ? L.leaf_len[cls] : (2u << L.step_arity_bits[i]), sibs, init ? L.init_depth : L.step_depth[i],
+        u32 leaf_len = init ? L.leaf_len[cls] : (2u << L.step_arity_bits[i]);
+        if (leaf_digests && init && leaf_len > 4) {   // the leaf was hashed by fri_leaf_kernel: its digest enters as a 4-word "leaf"
+            leaf = leaf_digests + ((size_t)unit * 4 + cls) * 4;
+            leaf_len = 4;
+        }
+        u32 rc = merkle_chain<KIND>(leaf, leaf_len, sibs, init ? L.init_depth : L.step_depth[i],
                               init ? x_index : x_index >> L.step_index_shift[i], cap, init ? SV_FAIL_INIT_MERKLE : SV_FAIL_STEP_MERKLE,
                               pscratch);
         if (rc) report_fail(accept_bitmap, first_fail, proof, query,

@@ -20,10 +20,12 @@ __global__ void __launch_bounds__(SVB_WIRE_BLOCK) wire_unpack_kernel(const u64* 
                                                                      WireDims d, const u32* __restrict__ hdr_src,
                                                                      const u32* __restrict__ q_src, const u32* __restrict__ chk,
                                                                      const u64* __restrict__ vk_cap, u64* __restrict__ records,
-                                                                     u32* __restrict__ malformed, const u64* __restrict__ hdr_packed) {
+                                                                     u32* __restrict__ malformed, const u64* __restrict__ hdr_packed,
+                                                                     u32 y0 /* segment of block row 0: 0 = header, 1 = first query round */) {
     const size_t p = blockIdx.x, proof_off = first_off + p * stride;
     u64* rec = records + p * (size_t)d.record_words;
-    if (blockIdx.y == 0) {
+    const u32 seg = blockIdx.y + y0;
+    if (seg == 0) {
         if (hdr_packed) {   // batch-wide transcript: the header was unpacked (and its challenge fields filled) before the chunks
             const u64* h = hdr_packed + p * (size_t)d.header_words;
             for (u32 w = threadIdx.x; w < d.header_words; w += SVB_WIRE_BLOCK) rec[w] = h[w];
@@ -32,7 +34,7 @@ __global__ void __launch_bounds__(SVB_WIRE_BLOCK) wire_unpack_kernel(const u64* 
         for (u32 w = threadIdx.x; w < d.header_words; w += SVB_WIRE_BLOCK) rec[w] = wire_header_word(hdr_src, vk_cap, blob8, proof_off, w);
         return;
     }
-    const u32 q = blockIdx.y - 1;
+    const u32 q = seg - 1;
     u64* out = rec + d.header_words + (size_t)q * d.query_words;
     bool bad = false;
     for (u32 r = threadIdx.x; r < d.query_words; r += SVB_WIRE_BLOCK)

@@ -240,21 +240,23 @@ SVB_D u64 mds_recombine(u32 al0, u32 al1, u32 ah0, u32 ah1) {
 #if SVB_MDS_FFT && SVB_MDS_CVT != 2
 #error "SVB_MDS_FFT needs the subnormal operand form (SVB_MDS_CVT == 2)"
 #endif
+// RC = 12: the layer adds the 12 constants rcf (2 subnormal words per row); RC = 0: no constants (rcf unused)
+template <int RC = 12>
 SVB_D void mds_layer_rc_f64(u64 s[12], const u64* __restrict__ rcf /* FULL_RC_NEXT_{F64,SUBNORMAL}: 2 words per row */) {
 #if SVB_MDS_FFT
     double x[12], rc[12], yl[12], yh[12];
 #pragma unroll
     for (int j = 0; j < 12; j++) {
         x[j] = u32_to_f64((u32)s[j]);
-        rc[j] = __longlong_as_double((long long)rcf[2 * j]);
+        if (RC) rc[j] = __longlong_as_double((long long)rcf[2 * j]);
     }
-    mds_freq_half<12>(x, rc, yl);
+    mds_freq_half<RC>(x, rc, yl);
 #pragma unroll
     for (int j = 0; j < 12; j++) {
         x[j] = u32_to_f64((u32)(s[j] >> 32));
-        rc[j] = __longlong_as_double((long long)rcf[2 * j + 1]);
+        if (RC) rc[j] = __longlong_as_double((long long)rcf[2 * j + 1]);
     }
-    mds_freq_half<12>(x, rc, yh);
+    mds_freq_half<RC>(x, rc, yh);
 #pragma unroll
     for (int r = 0; r < 12; r++)
         s[r] = mds_recombine((u32)__double2loint(yl[r]), (u32)__double2hiint(yl[r]), (u32)__double2loint(yh[r]), (u32)__double2hiint(yh[r]));
@@ -367,6 +369,9 @@ SVB_D void rot_lanes(u64 s[12]) {
 #ifndef SVB_PARTIAL_NAIVE
 #define SVB_PARTIAL_NAIVE 1
 #endif
+#ifndef SVB_RC_PRE_MDS
+#define SVB_RC_PRE_MDS 1   // full rounds: next round's constants as M^-1 c on the S-box outputs (x3 * x4 + c) instead of 24 DADD in the MDS layer
+#endif
 #if SVB_PARTIAL_NAIVE && !(SVB_MDS_CVT == 2 && SVB_MDS_FFT)
 #error "SVB_PARTIAL_NAIVE needs the subnormal, frequency-domain MDS (SVB_MDS_CVT == 2, SVB_MDS_FFT == 1)"
 #endif
@@ -387,9 +392,17 @@ SVB_D void poseidon_g_dev(u64 s[12], u64* __restrict__ scratch /* 11 words of pe
         // four full rounds: S-box layer, MDS + constants of the next round (:641-650, :675-684)
 #pragma unroll 1
         for (int f = 0; f < 4; f++) {
+#if SVB_RC_PRE_MDS
+            // the constants of the next round, moved in front of the MDS layer (M^-1 c): they ride on the last product of x^7
+            const u64* __restrict__ cpre = d_NAIVE_FULL_RC_PRE_MDS + 12 * (4 * phase + f);
+#pragma unroll
+            for (int i = 0; i < 12; i++) s[i] = sbox7_add(s[i], cpre[i]);
+            mds_layer_rc_f64<0>(s, nullptr);
+#else
 #pragma unroll
             for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
             mds_layer_rc_f64(s, d_NAIVE_FULL_RC_NEXT_SUBNORMAL + 24 * (4 * phase + f));
+#endif
         }
         if (phase == 0) {
             // rounds 4..25 as 11 double layers

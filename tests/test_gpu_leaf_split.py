@@ -58,9 +58,12 @@ def test_leaf_split_matches_fused_and_oracle(svb, orc, ctx, hiding, cap, degree_
     cd, ph = svb.synth_public_inputs(params, base, seed=77 + cap, n_circuits=1)
     bad = _corrupt_query_data(recs, L, params, np.random.default_rng(5))
     oshape = orc.shape_from(params.to_shape())
-    want_bm, want_ff = orc.fri_verify_batch(oshape, recs, nthreads=4, want_fail=True)
+    want_bm = orc.fri_verify_batch(oshape, recs, nthreads=4)
+    want_ff = np.zeros(base, dtype=np.uint32)
     for i in range(base):
-        assert bit(want_bm, i) == (0 if i in bad else 1)
+        ok, code, q = orc.fri_verify(oshape, recs[i])     # the oracle's first failure: (query, code)
+        assert bit(want_bm, i) == int(ok) == (0 if i in bad else 1), (i, bad.get(i))
+        want_ff[i] = 0 if ok else ((max(q, 0) << 8) | code)
     stripped = _clear(recs, L, params)
     got = {}
     old = os.environ.get("SVB_LEAF_SPLIT")

@@ -28,8 +28,8 @@ if [ "$2" = knobs ]; then
   run SVB_PREFETCH=1 SVB_L2_FETCH=128
 fi
 # block order: class-major over the whole batch (0) against unit groups of 8 / 32 / 128 blocks per class
-for g in 0 16 32 64; do run SVB_GROUP_BLOCKS=$g; done
-for g in 0 16 32 64; do
+for g in ${GROUPS_LIST:-0 16 32 64}; do run SVB_GROUP_BLOCKS=$g; done
+for g in ${GROUPS_LIST:-0 16 32 64}; do
   echo "== bench SVB_GROUP_BLOCKS=$g" >> $OUT
   env SVB_GROUP_BLOCKS=$g timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'])" >> $OUT
 done

@@ -837,6 +837,36 @@ def main():
                                               "h2d_bytes_per_call": int(big * nb)}
                     finally:
                         svb.lib().sv_host_free(pb)
+            if world == 1 and wl == "A":
+                # two host threads, each with its own sv_ctx (the header's threading contract: one context per (host thread, GPU),
+                # distinct contexts fully concurrent), each making the same synchronous call on the same pinned bytes: the head
+                # latency of one call (header copies + first transcript part) hides behind the query kernels of the other
+                try:
+                    import threading
+                    ctx2 = svb.Context(local_rank)
+                    res = [None, None]
+                    reps2 = max(2, e2e_steps // 2)
+
+                    def worker(k, cx, reps):
+                        for _ in range(reps):
+                            res[k] = cx.verify_proofs_wire(common, vk_cap, cd, p.value, n_proofs=n_host)
+                    worker(1, ctx2, 2)                                  # warm-up of the second context (allocations)
+                    torch.cuda.synchronize()
+                    ths = [threading.Thread(target=worker, args=(k, cx, reps2)) for k, cx in enumerate((ctx, ctx2))]
+                    t0 = time.perf_counter()
+                    for th in ths:
+                        th.start()
+                    for th in ths:
+                        th.join()
+                    torch.cuda.synchronize()
+                    dt2 = time.perf_counter() - t0
+                    if not ((res[0] == exp_w).all() and (res[1] == exp_w).all()):
+                        raise RuntimeError("accept bitmap of the two-context leg differs from the oracle's")
+                    e2e["two_contexts"] = {"value": 2 * reps2 * n_host / dt2, "unit": "proofs/s", "calls": 2 * reps2, "proofs_per_call": n_host,
+                                           "note": "two host threads x their own sv_ctx, synchronous sv_verify_proofs_wire calls in flight together"}
+                    del ctx2
+                except Exception as ex:   # noqa: BLE001
+                    e2e["two_contexts"] = {"error": f"{type(ex).__name__}: {ex}"}
             # copy-only ceiling of the same bytes
             stage = torch.empty(n_host * nb, dtype=torch.uint8, device="cuda")
             hview = torch.from_numpy(hostb.reshape(-1))

@@ -34,6 +34,7 @@ def parse():
                     help="A = configs[1], B = configs[2], merkle = configs[4], outer = the reference's outer wrapped-proof "
                          "configuration (hash family B = Poseidon-BN254, cap_height 0)")
     ap.add_argument("--proofs", type=int, default=0, help="proofs per GPU per step (default 4096 for A, 256 for B)")
+    ap.add_argument("--total-proofs", type=int, default=0, help="a fixed batch sharded over the ranks (strong split of e.g. 2^20 proofs, configs[3]) instead of --proofs per GPU")
     ap.add_argument("--distinct", type=int, default=0, help="distinct base proofs generated on the host (default 64 / 4)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="proofs in the cpu_baseline sample (default: sized for ~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -596,6 +597,12 @@ def main():
     oshape = orc.shape_from(params.to_shape())
     n = args.proofs or (4096 if wl == "A" else 256)
     n = (n + 31) & ~31
+    if args.total_proofs:
+        # a FIXED batch cut into contiguous per-rank ranges on bitmap-word boundaries (stark-verifier_b200/shard.py): configs[3]
+        first, last = svb.shard.shard_range(args.total_proofs, rank, world)
+        n = (last - first + 31) & ~31
+        if n == 0:
+            raise SystemExit(f"rank {rank}: --total-proofs {args.total_proofs} leaves this rank without work")
     distinct = min(n, args.distinct or {"A": 256, "B": 2, "outer": 4}[wl])
     # ---- synthetic proofs: `distinct` base proofs per rank (own seed) of ONE circuit, each bound to the hash of its own public
     # inputs, so that the same proofs exist as flat records (challenges filled in by the host transcript) and as wire bytes
@@ -926,10 +933,13 @@ def main():
     cfg = workload_config(wl, n, distinct, rw * 8, world, "host (challenges arrive in the records) for `value`; on the device for `e2e`",
                           "1/64 proofs, five kinds round-robin (" + ", ".join(CORRUPTION_KINDS) + "); bitmap == the oracle's, computed in this run")
     cfg["bitmap_gather"] = gather_via
+    if args.total_proofs:
+        cfg["total_proofs"] = args.total_proofs
+        cfg["workload"] = f"BASELINE configs[3]: {args.total_proofs} shape-A proofs sharded over {world} GPUs ({n} per GPU, shard.py)" if wl == "A" else cfg["workload"]
     out = {
         "metric": "plonky2_proofs_verified_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "scaling": "strong" if args.total_proofs else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": cfg,
         "e2e": e2e,
         "resident_with_device_transcript": resident_fs,

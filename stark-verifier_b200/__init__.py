@@ -9,6 +9,7 @@ the repository root.
 
 There is no CPU fallback: creating a :class:`Context` without a CUDA device raises.
 """
+from . import shard  # noqa: F401
 from .api import (  # noqa: F401
     Context,
     FriConfig,

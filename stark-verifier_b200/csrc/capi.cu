@@ -42,7 +42,7 @@ struct sv_ctx {
     cudaStream_t fs_stream = nullptr;                                  // the batch-wide transcript of the host pipeline
     cudaEvent_t ev_hdr = nullptr, ev_fs = nullptr;
     cudaStream_t fs_part_stream[2] = {};                               // transcript parts 1 and 2 of a wire batch (part 0: fs_stream)
-    cudaEvent_t ev_part[3] = {}, ev_hdr_ready = nullptr;
+    cudaEvent_t ev_part[3] = {}, ev_plonk[3] = {}, ev_hdr_ready = nullptr;   // per transcript part: challenges written / plonk identity checked
     cudaEvent_t ev_copied[SV_NBUF] = {}, ev_done[SV_NBUF] = {}, ev_join[SV_NKS] = {};
     // wire format (sv_wire_unpack_batch_gpu, sv_verify_proofs_wire): offset tables of the last (shape, common) seen,
     // the verifier key's cap, wire-byte staging ring, malformed flags
@@ -140,6 +140,7 @@ extern "C" int sv_ctx_create(int device, sv_ctx** out) {
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_fs, cudaEventDisableTiming));
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_hdr_ready, cudaEventDisableTiming));
         for (auto& e : c->ev_part) CK(nullptr, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : c->ev_plonk) CK(nullptr, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (int i = 0; i < SV_NBUF; i++) {
             CK(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
             CK(nullptr, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
@@ -193,6 +194,7 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     auto drop_e = [](cudaEvent_t e) { if (e) cudaEventDestroy(e); };
     drop_e(c->ev_hdr); drop_e(c->ev_fs); drop_e(c->ev_hdr_ready);
     for (auto& e : c->ev_part) drop_e(e);
+    for (auto& e : c->ev_plonk) drop_e(e);
     for (int i = 0; i < SV_NBUF; i++) { drop_e(c->ev_copied[i]); drop_e(c->ev_done[i]); }
     for (int i = 0; i < SV_NKS; i++) drop_e(c->ev_join[i]);
     for (auto& pr : c->tev) { drop_e(pr.first); drop_e(pr.second); }
@@ -951,14 +953,16 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
             const int force = hi_ == n_proofs && cnt > 2048 && lo > 0 ? 2 : 0;   // the big last part: thread per proof
             if ((rc = enqueue_challenges(c, Ph, F, cnt, c->d_hdr + lo * hw, c->d_pi + 4 * lo, ps, force))) return rc;
             if (trace && pi == 0) cudaEventRecord(tv[7], ps);
-            if (circuit) {   // the vanishing-polynomial identity reads headers only (zeta is in them now)
+            CK(c, cudaEventRecord(c->ev_part[pi], ps));       // the chunks' query kernels wait for the challenges only
+            if (circuit) {   // the vanishing-polynomial identity reads headers only (zeta is in them now); its verdict is not needed
+                             // before the AND at the end of a chunk, so it runs beside the first query kernels (ev_plonk)
                 PlonkRecordView V = {(u32)hw, P.L.off_open0, P.L.off_open1, P.L.off_zeta};
                 plonk_check_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, ps>>>(c->d_hdr + lo * hw, V, c->d_circuit, c->d_pi + 4 * lo,
                                                                                  c->d_chal + 3 * (size_t)nch * lo, (u32)cnt, c->d_pbm + lo / 32);
                 c->launches++;
+                CK(c, cudaEventRecord(c->ev_plonk[pi], ps));
             }
             CK(c, cudaGetLastError());
-            CK(c, cudaEventRecord(c->ev_part[pi], ps));
             part_of_first[pi] = (int)(lo / chunk);
             lo = hi_;
         }
@@ -1003,6 +1007,7 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
                               split ? c->d_leaf[b] : nullptr)))
             return rc;
         if (circuit) {
+            CK(c, cudaStreamWaitEvent(k, c->ev_plonk[pi], 0));
             plonk_and_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, k>>>(c->d_pbm + first / 32, c->d_bitmap + first / 32, d_fail, (u32)cnt);
             c->launches++;
         }

@@ -181,13 +181,15 @@ WORKLOAD_TEXT = {"A": "BASELINE configs[1]: {n} proofs/GPU/step, shape A", "B": 
 WORKLOAD_SHAPE = {"A": (12, 3, 4, 16, 28, 0), "B": (20, 2, 4, 16, 84, 0), "outer": (12, 3, 0, 16, 28, 1)}
 
 
-def workload_config(wl, n, distinct, record_bytes, world, transcript, corrupted):
+def workload_config(wl, n, distinct, record_bytes, world):
+    """The workload definition -- the SAME dict, key for key and value for value, in the b200 arm and in the reference arm
+    (what differs between the arms is reported under the top-level "arm" key)."""
     d, r, c, pw, q, kind = WORKLOAD_SHAPE[wl]
     return {"workload": WORKLOAD_TEXT[wl].format(n=n), "hash_kind": kind, "trace_bits": d, "fri_queries": q, "blowup": 1 << r,
             "cap_height": c, "pow_bits": pw, "reduction_arity_bits": [1] * (d - 5), "proofs_per_gpu": n, "distinct_base_proofs": distinct,
             "record_bytes": record_bytes, "l2_policy": f"inputs larger than L2 ({n * record_bytes / 1e6:.0f} MB/GPU resident, physically distinct copies)",
-            "sharding": f"proofs sharded over {world} ranks; all-gather of the accept bitmap only", "corrupted": corrupted,
-            "transcript": transcript}
+            "sharding": f"proofs sharded over {world} ranks; all-gather of the accept bitmap only",
+            "corrupted": "1/64 proofs, five kinds round-robin (" + ", ".join(CORRUPTION_KINDS) + ")"}
 
 
 def reference_fixture(wl):
@@ -251,14 +253,14 @@ def run_reference(args):
     perms_per_query = sum((x + 7) // 8 for x in leaf) + 4 * (lde - c) + sum(lde - (i + 1) - c for i in range(d - 5))
     perms_per_proof = q * perms_per_query
     cpu = open("/proc/cpuinfo").read().split("model name")[1].split("\n")[0].strip(": \t") if os.path.exists("/proc/cpuinfo") else "?"
-    cfg = workload_config(wl, n_gpu_arm, distinct, oL.record_words * 8, args.gpus, "n/a (the CPU arm verifies records whose challenges are filled in)",
-                          "none in this arm")
-    cfg["sample"] = f"each step verifies a bounded sample of {sample} proofs of that workload on the host CPU"
+    cfg = workload_config(wl, n_gpu_arm, distinct, oL.record_words * 8, args.gpus)
+    arm = {"sample": f"each step verifies a bounded sample of {sample} valid proofs of that workload on the host CPU (no corrupted ones)",
+           "transcript": "n/a (the CPU arm verifies records whose challenges are filled in)"}
     print(json.dumps({
         "impl": "reference", "metric": "plonky2_proofs_verified_per_sec", "value": v, "unit": "proofs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": cfg,
+        "config": cfg, "arm": arm,
         "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": threads, "kind": "port",
                          "perms_per_sec": v * perms_per_proof, "single_thread_value": v1, "single_thread_perms_per_sec": v1 * perms_per_proof,
                          "perm_ns_per_thread": 1e9 / (v1 * perms_per_proof), "scalar_perm_ns_per_thread": 1e9 / (v1_scalar * perms_per_proof),
@@ -930,9 +932,9 @@ def main():
     k_avg_s = (kernel_ms / max(1, kernel_n)) / 1e3
     achieved = algo_bytes / k_avg_s / 1e9
     perms = n * params.config.num_query_rounds * L.perms_per_query
-    cfg = workload_config(wl, n, distinct, rw * 8, world, "host (challenges arrive in the records) for `value`; on the device for `e2e`",
-                          "1/64 proofs, five kinds round-robin (" + ", ".join(CORRUPTION_KINDS) + "); bitmap == the oracle's, computed in this run")
-    cfg["bitmap_gather"] = gather_via
+    cfg = workload_config(wl, n, distinct, rw * 8, world)
+    arm = {"transcript": "host (challenges arrive in the records) for `value`; on the device for `e2e`",
+           "bitmap_check": "accept bitmap == the oracle's, computed in this run", "bitmap_gather": gather_via}
     if args.total_proofs:
         cfg["total_proofs"] = args.total_proofs
         cfg["workload"] = f"BASELINE configs[3]: {args.total_proofs} shape-A proofs sharded over {world} GPUs ({n} per GPU, shard.py)" if wl == "A" else cfg["workload"]
@@ -940,7 +942,7 @@ def main():
         "metric": "plonky2_proofs_verified_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong" if args.total_proofs else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": cfg,
+        "config": cfg, "arm": arm,
         "e2e": e2e,
         "resident_with_device_transcript": resident_fs,
         "gpu_launches": int(launches),

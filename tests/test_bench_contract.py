@@ -20,6 +20,11 @@ def test_reference_arm_json_line(svb, orc):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "BASELINE configs[1]" in d["config"]["workload"] and d["config"]["fri_queries"] == 28
+    # the config dict is the workload definition the b200 arm prints, key for key and value for value (arm-specific notes: "arm")
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config("A", 4096, 4, 157728, 1)
+    assert "sample" in d["arm"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -522,6 +522,33 @@ static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_rec
     return 0;
 }
 
+// Chunk schedule of a host batch: full chunks, then a ramp-down (1/2, 1/4, ... of a chunk, whole 32-proof bitmap words, never
+// below 64 proofs).  The pipeline is copy-bound (the query kernels of a chunk take less time than its H2D), so a call ends one
+// chunk-processing time after its last byte arrived -- and a chunk cannot be processed faster than its longest chain (28
+// dependent permutations, 0.67 ms), however small it is.  With the ramp the last chunk carries ~100 proofs instead of ~400: its
+// bytes arrive ~0.8 ms before the end of the copies and the work queued behind the copy engine at that point is a quarter.
+// Measured on B200 (4 096 shape-A proofs): record path 316.4 -> 321.8 k proofs/s, with device transcript 276.0 -> 279.6 k; the
+// wire path LOSES (303.4 -> 295.4 k, complete verifier 294.5 -> 284.9 k: its 64 MiB chunks ramp down into five small ones, each
+// with its strided copy and seven launches), so the ramp is on for the record path only.  SVB_RAMP=0 / 1 forces it off / on
+// everywhere (lab knob).  Returns the start of every chunk plus the end sentinel.
+static std::vector<size_t> chunk_schedule(size_t n_proofs, size_t chunk, bool ramp_default) {
+    const char* e = getenv("SVB_RAMP");                     // read per call: the tests toggle it
+    const bool ramp = e ? atoi(e) != 0 : ramp_default;
+    std::vector<size_t> starts;
+    size_t at = 0;
+    while (at < n_proofs) {
+        starts.push_back(at);
+        size_t left = n_proofs - at, sz = chunk;
+        if (ramp && left <= 2 * chunk && left > 64) {
+            sz = ((left / 2) + 31) & ~(size_t)31;
+            if (sz < 64) sz = 64;
+        }
+        at += std::min(sz, left);
+    }
+    starts.push_back(n_proofs);
+    return starts;
+}
+
 // SV_MEM_HOST leg of sv_fri_verify_batch[_fs]: the chunked H2D / compute pipeline.
 static int fri_verify_host(sv_ctx* c, FriKernelParams& P, size_t n_proofs, const uint64_t* records, uint32_t* accept_bitmap,
                            uint32_t* first_fail, const FsParams* fs, const uint64_t* pi_hashes) {
@@ -552,7 +579,8 @@ static int fri_verify_host(sv_ctx* c, FriKernelParams& P, size_t n_proofs, const
     cudaStream_t cs = c->copy_stream;
     cudaStream_t ks[SV_NKS] = {c->own_stream};
     for (int i = 1; i < SV_NKS; i++) ks[i] = c->aux_stream[i - 1];
-    size_t n_chunks = (n_proofs + chunk - 1) / chunk;
+    const std::vector<size_t> sched = chunk_schedule(n_proofs, chunk, true);
+    const size_t n_chunks = sched.size() - 1;
     // Device-side transcript of a host batch: the ~85 dependent permutations per proof are latency-bound
     // (one warp per 32 proofs), so the transcript runs ONCE for the whole batch, on the headers alone
     // (they travel first: 7 % of the bytes), beside the H2D of the full records; every chunk then gets
@@ -582,14 +610,15 @@ static int fri_verify_host(sv_ctx* c, FriKernelParams& P, size_t n_proofs, const
     for (size_t i = 0; i < n_chunks; i++) {
         int b = (int)(i % SV_NBUF);
         cudaStream_t k = ks[i % n_ks];
-        size_t first = i * chunk, cnt = std::min(chunk, n_proofs - first);
+        const size_t first = sched[i], cnt = sched[i + 1] - first;
         if (i >= SV_NBUF) CK(c, cudaStreamWaitEvent(cs, c->ev_done[b], 0));   // buffer b free again
         CK(c, cudaMemcpyAsync(c->d_stage[b], records + first * rw, cnt * rw * 8, cudaMemcpyHostToDevice, cs));
         CK(c, cudaEventRecord(c->ev_copied[b], cs));
         CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
         if (fs) {
             if (split && (rc = enqueue_leaf(c, P, cnt, c->d_stage[b], c->d_leaf[b], k))) return rc;   // needs no challenge
-            CK(c, cudaStreamWaitEvent(k, c->ev_part[first < fs_lead ? 0 : 1], 0));
+            if (first < fs_lead) CK(c, cudaStreamWaitEvent(k, c->ev_part[0], 0));             // a ramp-down chunk may straddle
+            if (first + cnt > fs_lead) CK(c, cudaStreamWaitEvent(k, c->ev_part[1], 0));       // the two transcript parts
             CK(c, cudaMemcpy2DAsync(c->d_stage[b] + chal_off, rw * 8, c->d_hdr + first * hw + chal_off, hw * 8, chal_words * 8, cnt,
                                     cudaMemcpyDeviceToDevice, k));
         }
@@ -933,12 +962,12 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
     static const int lead_env = [] { const char* e = getenv("SVB_FS_LEAD"); return e ? atoi(e) : 2; }();   // chunks in the first part
     const size_t part_end[3] = {std::min(n_proofs, (size_t)lead_env * chunk), std::min(n_proofs, (size_t)(lead_env + 2) * chunk), n_proofs};
     cudaStream_t pst[3] = {fss, c->fs_part_stream[0], c->fs_part_stream[1]};
-    int part_of_first[3] = {0, 0, 0};
+    size_t part_lo[3] = {0, 0, 0}, part_hi[3] = {0, 0, 0};   // proofs [lo, hi) of each transcript part (hi == lo: part unused)
     {
         size_t lo = 0;
         for (int pi = 0; pi < 3; pi++) {
             const size_t hi_ = parts_env >= 3 ? part_end[pi] : (parts_env == 2 ? (pi == 0 ? part_end[0] : n_proofs) : n_proofs);
-            if (hi_ <= lo) { part_of_first[pi] = -1; continue; }
+            if (hi_ <= lo) continue;
             const size_t cnt = hi_ - lo;
             cudaStream_t ps = pst[pi];
             if (pi) CK(c, cudaStreamWaitEvent(ps, c->ev_hdr_ready, 0));
@@ -963,7 +992,7 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
                 CK(c, cudaEventRecord(c->ev_plonk[pi], ps));
             }
             CK(c, cudaGetLastError());
-            part_of_first[pi] = (int)(lo / chunk);
+            part_lo[pi] = lo; part_hi[pi] = hi_;
             lo = hi_;
         }
     }
@@ -973,17 +1002,22 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
     dq.query_base = 0;                                      // a chunk buffer row holds the query rounds only
     cudaStream_t ks[SV_NKS] = {c->own_stream};
     for (int i = 1; i < SV_NKS; i++) ks[i] = c->aux_stream[i - 1];
-    size_t n_chunks = (n_proofs + chunk - 1) / chunk;
+    const std::vector<size_t> sched = chunk_schedule(n_proofs, chunk, false);
+    const size_t n_chunks = sched.size() - 1;
     for (size_t i = 0; i < n_chunks; i++) {
         int b = (int)(i % SV_NBUF);
         cudaStream_t k = ks[i % n_ks];
-        size_t first = i * chunk, cnt = std::min(chunk, n_proofs - first);
+        const size_t first = sched[i], cnt = sched[i + 1] - first;
         if (i >= SV_NBUF) CK(c, cudaStreamWaitEvent(cs, c->ev_done[b], 0));   // buffers b free again
         CK(c, cudaMemcpy2DAsync(c->d_wire[b], q_pitch, blob + first * stride + front_bytes, stride, q_bytes, cnt, cudaMemcpyHostToDevice, cs));
         CK(c, cudaEventRecord(c->ev_copied[b], cs));
         CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
-        int pi = 2;   // the transcript part that covers this chunk (parts end on chunk boundaries)
-        while (pi > 0 && (part_of_first[pi] < 0 || (size_t)part_of_first[pi] > i)) pi--;
+        // the transcript parts that cover this chunk (a ramp-down chunk may straddle two of them)
+        auto wait_parts = [&](cudaEvent_t* ev) -> int {
+            for (int pi = 0; pi < 3; pi++)
+                if (part_hi[pi] > part_lo[pi] && part_lo[pi] < first + cnt && first < part_hi[pi]) CK(c, cudaStreamWaitEvent(k, ev[pi], 0));
+            return 0;
+        };
         if (split) {
             // what needs no challenge goes first: the query rounds into the records, then their leaf digests -- this work fills
             // the GPU while the transcript of the chunk's part is still running; the finished header follows
@@ -991,12 +1025,12 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
                                                                                             W.vk, c->d_stage[b], c->d_mal + first, nullptr, 1);
             c->launches++;
             if ((rc = enqueue_leaf(c, P, cnt, c->d_stage[b], c->d_leaf[b], k))) return rc;
-            CK(c, cudaStreamWaitEvent(k, c->ev_part[pi], 0));
+            if ((rc = wait_parts(c->ev_part))) return rc;
             wire_unpack_kernel<<<dim3((unsigned)cnt, 1), SVB_WIRE_BLOCK, 0, k>>>(c->d_wire[b], 0, q_pitch, dq, W.hdr_src, W.q_src, W.chk, W.vk,
                                                                               c->d_stage[b], c->d_mal + first, c->d_hdr + first * hw, 0);
             c->launches++;
         } else {
-            CK(c, cudaStreamWaitEvent(k, c->ev_part[pi], 0));
+            if ((rc = wait_parts(c->ev_part))) return rc;
             dim3 grid((unsigned)cnt, 1 + W.d.num_queries);
             wire_unpack_kernel<<<grid, SVB_WIRE_BLOCK, 0, k>>>(c->d_wire[b], 0, q_pitch, dq, W.hdr_src, W.q_src, W.chk, W.vk, c->d_stage[b],
                                                                c->d_mal + first, c->d_hdr + first * hw, 0);
@@ -1007,7 +1041,7 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
                               split ? c->d_leaf[b] : nullptr)))
             return rc;
         if (circuit) {
-            CK(c, cudaStreamWaitEvent(k, c->ev_plonk[pi], 0));
+            if ((rc = wait_parts(c->ev_plonk))) return rc;
             plonk_and_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, k>>>(c->d_pbm + first / 32, c->d_bitmap + first / 32, d_fail, (u32)cnt);
             c->launches++;
         }

@@ -96,3 +96,37 @@ def test_leaf_split_matches_fused_and_oracle(svb, orc, ctx, hiding, cap, degree_
         else:
             os.environ["SVB_LEAF_SPLIT"] = old
     assert (got["1"][0] == got["0"][0]).all() and (got["1"][1] == got["0"][1]).all()
+
+
+@pytest.mark.parametrize("chunk_mb,n", [(6, 560), (2, 645), (1, 200)])
+def test_record_path_device_transcript_chunk_schedule(svb, orc, ctx, chunk_mb, n):
+    """sv_fri_verify_batch_fs(SV_MEM_HOST) over several chunks: full chunks, the ramp-down at the end of the schedule and a
+    chunk that straddles the two transcript parts -- verdicts and first-failure codes equal the oracle's."""
+    params = tiny_params(svb, cap=2, degree_bits=7)
+    L = svb.api.make_layout(params)
+    base = 64
+    recs = svb.synth_proofs(params, base, seed=31, n_circuits=1)
+    cd, ph = svb.synth_public_inputs(params, base, seed=31, n_circuits=1)
+    _corrupt_query_data(recs, L, params, np.random.default_rng(8))
+    oshape = orc.shape_from(params.to_shape())
+    ff1 = np.zeros(base, dtype=np.uint32)
+    for i in range(base):
+        ok, code, q = orc.fri_verify(oshape, recs[i])
+        ff1[i] = 0 if ok else ((max(q, 0) << 8) | code)
+    reps = (n + base - 1) // base
+    big = np.ascontiguousarray(np.tile(_clear(recs, L, params), (reps, 1))[:n])
+    bph = np.ascontiguousarray(np.tile(ph, (reps, 1))[:n])
+    old = os.environ.get("SVB_CHUNK_MB")
+    os.environ["SVB_CHUNK_MB"] = str(chunk_mb)
+    try:
+        bm, ff = ctx.fri_verify_batch_fs(params, big, cd[0], bph, want_fail=True)
+    finally:
+        if old is None:
+            del os.environ["SVB_CHUNK_MB"]
+        else:
+            os.environ["SVB_CHUNK_MB"] = old
+    want_ff = np.tile(ff1, reps)[:n]
+    assert (ff == want_ff).all(), np.nonzero(ff != want_ff)[0][:8]
+    for i in range(n):
+        assert bit(bm, i) == int(want_ff[i] == 0), i
+    assert n & 31 == 0 or int(bm[-1]) >> (n & 31) == 0

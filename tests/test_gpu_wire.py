@@ -110,13 +110,16 @@ def test_verify_proofs_wire_matches_oracle(svb, orc, ctx, kw, n_pi, kind):
     assert (ctx.verify_proofs_wire(common, vk_cap, cds[0], blob.reshape(-1)) == bm).all()
 
 
-def test_verify_proofs_wire_many_chunks(svb, orc, ctx):
-    """More chunks than staging buffers (the ring wraps), a ragged last chunk, pinned host memory."""
+@pytest.mark.parametrize("chunk_mb,n", [(1, 16 * 15 + 5), (6, 560), (4, 645)])
+def test_verify_proofs_wire_many_chunks(svb, orc, ctx, chunk_mb, n):
+    """More chunks than staging buffers (the ring wraps), a ragged last chunk, pinned host memory; (6, 560): chunks of 224, 192,
+    96, 48 proofs -- the ramp-down of the chunk schedule, with one chunk straddling the two transcript parts (boundary at 448);
+    (4, 645): 128, 128, 128, 128, 96, 37."""
     import ctypes
     params = tiny_params(svb)
     L = svb.api.make_layout(params)
     common = svb.CommonData.for_params(params, num_public_inputs=2)
-    base_n, n = 16, 16 * 15 + 5
+    base_n = 16
     recs, pis, pih, cds = bound_proofs(svb, params, base_n, 2, seed=9)
     blob16 = svb.wire_pack(common, recs, pis)
     nb = blob16.shape[1]
@@ -136,15 +139,20 @@ def test_verify_proofs_wire_many_chunks(svb, orc, ctx):
             svb.fri_challenges(params, r2[i], cds[0], pih2[i])
         want = orc.fri_verify_batch(orc.shape_from(params.to_shape()), r2, nthreads=4)
         assert not mal.any() and [i for i in range(n) if not bit(want, i)] == bad
-        old = os.environ.get("SVB_CHUNK_MB")
-        os.environ["SVB_CHUNK_MB"] = "1"                  # 32 proofs per chunk -> 8 chunks over 6 buffers
+        old = {k: os.environ.get(k) for k in ("SVB_CHUNK_MB", "SVB_RAMP")}
+        os.environ["SVB_CHUNK_MB"] = str(chunk_mb)        # 1 MiB: 32 proofs per chunk -> 8 chunks over 6 buffers
+        os.environ["SVB_RAMP"] = "1"                      # the ramp-down is off by default on the wire path
         try:
             bm = ctx.verify_proofs_wire(common, vk_cap, cds[0], p.value, n_proofs=n)
+            os.environ["SVB_RAMP"] = "0"
+            bm0 = ctx.verify_proofs_wire(common, vk_cap, cds[0], p.value, n_proofs=n)
         finally:
-            if old is None:
-                del os.environ["SVB_CHUNK_MB"]
-            else:
-                os.environ["SVB_CHUNK_MB"] = old
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        assert (bm == bm0).all()
         assert [i for i in range(n) if not bit(bm, i)] == bad
         assert int(bm[-1]) >> (n & 31) == 0               # bits past the batch stay clear
     finally:

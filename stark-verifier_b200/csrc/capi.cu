@@ -42,7 +42,7 @@ struct sv_ctx {
     cudaStream_t fs_stream = nullptr;                                  // the batch-wide transcript of the host pipeline
     cudaEvent_t ev_hdr = nullptr, ev_fs = nullptr;
     cudaStream_t fs_part_stream[2] = {};                               // transcript parts 1 and 2 of a wire batch (part 0: fs_stream)
-    cudaEvent_t ev_part[3] = {}, ev_plonk[3] = {}, ev_hdr_ready = nullptr;   // per transcript part: challenges written / plonk identity checked
+    cudaEvent_t ev_part[3] = {}, ev_plonk[3] = {}, ev_hdr_part[3] = {}, ev_hdr_ready = nullptr;   // per transcript part: challenges written / plonk identity checked
     cudaEvent_t ev_copied[SV_NBUF] = {}, ev_done[SV_NBUF] = {}, ev_join[SV_NKS] = {};
     // wire format (sv_wire_unpack_batch_gpu, sv_verify_proofs_wire): offset tables of the last (shape, common) seen,
     // the verifier key's cap, wire-byte staging ring, malformed flags
@@ -101,7 +101,7 @@ static int fail(sv_ctx* c, int code, const char* fmt, ...) {
 
 // bump SVB_KERNEL_REV whenever a kernel changes: profiles/traffic_r2.json and the ncu summaries are stamped with it, and bench.py
 // reports DRAM traffic only from a capture of the same revision
-#define SVB_KERNEL_REV "r2.3"
+#define SVB_KERNEL_REV "r2.4"
 extern "C" const char* sv_version(void) { return "stark-verifier_b200 0.2 (sm_100a, kernels " SVB_KERNEL_REV ")"; }
 
 extern "C" const char* sv_last_error(const sv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
@@ -141,6 +141,7 @@ extern "C" int sv_ctx_create(int device, sv_ctx** out) {
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_hdr_ready, cudaEventDisableTiming));
         for (auto& e : c->ev_part) CK(nullptr, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : c->ev_plonk) CK(nullptr, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : c->ev_hdr_part) CK(nullptr, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (int i = 0; i < SV_NBUF; i++) {
             CK(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
             CK(nullptr, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
@@ -195,6 +196,7 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     drop_e(c->ev_hdr); drop_e(c->ev_fs); drop_e(c->ev_hdr_ready);
     for (auto& e : c->ev_part) drop_e(e);
     for (auto& e : c->ev_plonk) drop_e(e);
+    for (auto& e : c->ev_hdr_part) drop_e(e);
     for (int i = 0; i < SV_NBUF; i++) { drop_e(c->ev_copied[i]); drop_e(c->ev_done[i]); }
     for (int i = 0; i < SV_NKS; i++) drop_e(c->ev_join[i]);
     for (auto& pr : c->tev) { drop_e(pr.first); drop_e(pr.second); }
@@ -459,13 +461,13 @@ static int enqueue_challenges(sv_ctx* c, FriKernelParams& P, const FsParams& F, 
                               cudaStream_t s, int force = 0) {
     P.n_proofs = (u32)n;
     // SVB_FS_COOP: 1 = always lane-cooperative, 0 = never, unset = by batch size.  The cooperative kernel has the
-    // lower latency (11.9 vs 24.4 us per permutation) but 4.6x less throughput (254 vs 1 177 M perms/s), so it wins
+    // lower latency (6.4 vs 24.4 us per permutation) but 4.6x less throughput (252 vs 1 177 M perms/s), so it wins
     // while the batch is latency-bound: below ~8k proofs per call.
     static const int coop_env = [] { const char* e = getenv("SVB_FS_COOP"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
     const bool coop = force ? force == 1 : (coop_env < 0 ? n < 8192 : coop_env == 1);
     if (P.hash_kind == SV_HASH_POSEIDON_GOLDILOCKS && coop) {
         // lane-cooperative transcript: 16 lanes per proof
-        fri_challenges_coop_kernel<<<(unsigned)((n * SVB_COOP_GROUP + 127) / 128), 128, 0, s>>>(d_records, P, F, d_pi);
+        fri_challenges_coop_kernel<<<(unsigned)((n * SVB_COOP2_GROUP + SVB_COOP_BLOCK - 1) / SVB_COOP_BLOCK), SVB_COOP_BLOCK, 0, s>>>(d_records, P, F, d_pi);
         c->launches++;
         CK(c, cudaGetLastError());
         return 0;
@@ -475,6 +477,17 @@ static int enqueue_challenges(sv_ctx* c, FriKernelParams& P, const FsParams& F, 
     c->launches++;
     CK(c, cudaGetLastError());
     return 0;
+}
+
+// Proofs in the LEAD part of a device-side transcript (the part on the lane-cooperative kernel, whose query kernels then hide
+// the thread-per-proof transcript of the rest): ~1 664 by default -- the cooperative kernel is still latency-bound there (1.36 ms
+// against 1.0 ms for a lone warp per sub-partition) and their query phase (3.8 ms) outlasts the second part (3.8 ms + its
+// start).  Rounded up to whole chunks.  SVB_FS_LEAD_PROOFS overrides (lab knob).
+static size_t fs_lead_proofs(size_t n_proofs, size_t chunk) {
+    static const long env = [] { const char* e = getenv("SVB_FS_LEAD_PROOFS"); return e ? atol(e) : 1664L; }();
+    size_t lead = env > 0 ? (size_t)env : 1664;
+    if (chunk) lead = (lead + chunk - 1) / chunk * chunk;
+    return std::min(n_proofs, lead);
 }
 
 // Leaf digests before the challenges (fri_leaf_kernel), for the paths whose Fiat-Shamir transcript runs on the device: the
@@ -595,9 +608,9 @@ static int fri_verify_host(sv_ctx* c, FriKernelParams& P, size_t n_proofs, const
         CK(c, cudaStreamWaitEvent(c->fs_stream, c->ev_hdr, 0));
         FriKernelParams Ph = P;
         Ph.L.record_words = (u32)hw;          // the headers are packed back to back
-        // two parts, as in the wire path: the proofs of the first two chunks on the low-latency kernel, the rest with one
+        // two parts, as in the wire path: the proofs of the first chunks (fs_lead_proofs) on the low-latency kernel, the rest with one
         // thread per proof beside them (their query kernels are not due before the first chunks are through)
-        fs_lead = std::min(n_proofs, 2 * chunk);
+        fs_lead = fs_lead_proofs(n_proofs, chunk);
         if (fs_lead < n_proofs) {
             CK(c, cudaStreamWaitEvent(c->fs_part_stream[0], c->ev_hdr, 0));
             FriKernelParams P1 = Ph;
@@ -656,11 +669,11 @@ static int fri_verify_impl(sv_ctx* c, const sv_fri_shape* shape, size_t n_proofs
         // SV_MEM_DEVICE calls return without synchronising and all share d_scratch (reduced openings): when the caller moved to
         // another stream since the last such call (sv_ctx_set_stream), this call is ordered behind it
         if (c->scratch_busy && c->scratch_stream != c->stream) CK(c, cudaStreamWaitEvent(c->stream, c->ev_scratch, 0));
-        const size_t lead = fs && n_proofs >= 4096 ? 1024 : 0;
+        const size_t lead = fs && n_proofs >= 4096 ? fs_lead_proofs(n_proofs, 32) : 0;
         if (fs && lead) {
             // The transcript (~155 dependent permutations per proof) in two parts on the high-priority side streams, both started
-            // now: the first 1 024 proofs on the lane-cooperative kernel (lowest latency, ~2 ms), the rest with one thread per
-            // proof (4.3 ms, almost no GPU time); the query kernel of the first part hides the rest of the second transcript.
+            // now: the first ~1 664 proofs on the lane-cooperative kernel (lowest latency, ~1.4 ms), the rest with one thread per
+            // proof (3.8 ms, almost no GPU time); the query kernel of the first part hides the rest of the second transcript.
             u64* recs = const_cast<u64*>(records);
             const size_t rw = P.L.record_words;
             CK(c, cudaEventRecord(c->ev_hdr_ready, c->stream));
@@ -934,35 +947,23 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
         for (auto& e : tv) cudaEventCreate(&e);
         cudaEventRecord(tv[0], cs);
     }
-    // ---- headers first -------------------------------------------------------------------------------------
-    CK(c, cudaMemcpy2DAsync(c->d_hfront, front_pitch, blob, stride, front_bytes, n_proofs, cudaMemcpyHostToDevice, cs));
-    CK(c, cudaMemcpy2DAsync(c->d_hback, back_pitch, blob + back_off, stride, back_bytes, n_proofs, cudaMemcpyHostToDevice, cs));
-    CK(c, cudaEventRecord(c->ev_hdr, cs));
-    if (trace) cudaEventRecord(tv[1], cs);
-    CK(c, cudaStreamWaitEvent(fss, c->ev_hdr, 0));
-    CK(c, cudaMemsetAsync(c->d_mal, 0, n_proofs * 4, fss));
-    wire_header_unpack_kernel<<<(unsigned)n_proofs, SVB_WIRE_BLOCK, 0, fss>>>(c->d_hfront, front_pitch, c->d_hback, back_pitch, (u32)front_bytes,
-                                                                               (u32)back_off, (u32)hw, W.hdr_src, W.vk, c->d_hdr);
-    {
-        WireDims db = W.d;
-        db.pi_off = (u32)(W.d.pi_off - back_off);          // the public inputs inside the back span
-        wire_pi_hash_kernel<<<(unsigned)((n_proofs + SVB_BLOCK - 1) / SVB_BLOCK), SVB_BLOCK, 0, fss>>>(c->d_hback, 0, back_pitch, db, n_proofs,
-                                                                                                       c->d_pi, c->d_mal);
-    }
-    c->launches += 2;
-    if (trace) cudaEventRecord(tv[6], fss);
-    CK(c, cudaEventRecord(c->ev_hdr_ready, fss));
-    // The transcript in three parts, each on its own high-priority stream, all started now.  A transcript is ~155 DEPENDENT
-    // permutations per proof: the lane-cooperative kernel has the lower latency (1.7 ms for a few hundred proofs, 3.2 ms for
-    // 4 096) but a quarter of the throughput, the thread-per-proof kernel needs 4.3 ms and almost no GPU time.  So the proofs of
-    // chunk 0 and of chunks 1-2 get the cooperative kernel -- their query kernels start after ~2 ms and keep the GPU busy
-    // until the third part, everything else on the thread-per-proof kernel, is done.  (One transcript for the whole batch
-    // left the GPU idle for 3.3 of 14.4 ms: tools/lab/wire_trace.sh, SVB_TRACE.)
+    // ---- headers first, transcript part by transcript part ---------------------------------------------------
+    // A transcript is ~155 DEPENDENT permutations per proof.  The lane-cooperative kernel has the lower latency (6.9 us per
+    // permutation while every warp has an SM sub-partition to itself: ~1.1 ms for up to ~1 200 proofs, 2.8 ms for 4 096), the
+    // thread-per-proof kernel needs ~3.8 ms and almost no GPU time.  So the batch is cut into parts, each on its own high-priority
+    // stream: the header spans of the LEAD chunks cross PCIe first (0.2 ms instead of 0.8 for the whole batch) and their
+    // transcript starts at once -- the query kernels of those chunks then keep the GPU busy while the rest of the headers
+    // arrive and the other parts finish.  (One transcript for the whole batch left the GPU idle for 3.3 of 14.4 ms:
+    // tools/lab/wire_trace.sh, SVB_TRACE.)
     static const int parts_env = [] { const char* e = getenv("SVB_FS_PARTS"); return e ? atoi(e) : 2; }();
-    static const int lead_env = [] { const char* e = getenv("SVB_FS_LEAD"); return e ? atoi(e) : 2; }();   // chunks in the first part
-    const size_t part_end[3] = {std::min(n_proofs, (size_t)lead_env * chunk), std::min(n_proofs, (size_t)(lead_env + 2) * chunk), n_proofs};
+    static const int lead_chunks_env = [] { const char* e = getenv("SVB_FS_LEAD"); return e ? atoi(e) : 0; }();   // chunks in the first part (lab knob)
+    const size_t lead_env = lead_chunks_env > 0 ? (size_t)lead_chunks_env : (fs_lead_proofs(n_proofs, chunk) + chunk - 1) / chunk;
+    static const int mid_env = [] { const char* e = getenv("SVB_FS_MID"); return e ? atoi(e) : 2; }();     // chunks in the second of three parts
+    static const int rest_coop_env = [] { const char* e = getenv("SVB_FS_REST_COOP"); return e ? atoi(e) : 0; }();   // last part: cooperative too
+    const size_t part_end[3] = {std::min(n_proofs, (size_t)lead_env * chunk), std::min(n_proofs, (size_t)(lead_env + mid_env) * chunk), n_proofs};
     cudaStream_t pst[3] = {fss, c->fs_part_stream[0], c->fs_part_stream[1]};
     size_t part_lo[3] = {0, 0, 0}, part_hi[3] = {0, 0, 0};   // proofs [lo, hi) of each transcript part (hi == lo: part unused)
+    CK(c, cudaMemsetAsync(c->d_mal, 0, n_proofs * 4, cs));
     {
         size_t lo = 0;
         for (int pi = 0; pi < 3; pi++) {
@@ -970,7 +971,25 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
             if (hi_ <= lo) continue;
             const size_t cnt = hi_ - lo;
             cudaStream_t ps = pst[pi];
-            if (pi) CK(c, cudaStreamWaitEvent(ps, c->ev_hdr_ready, 0));
+            // the two header spans of this part's proofs: packed rows on the device
+            CK(c, cudaMemcpy2DAsync((uint8_t*)c->d_hfront + lo * front_pitch, front_pitch, blob + lo * stride, stride, front_bytes, cnt,
+                                    cudaMemcpyHostToDevice, cs));
+            CK(c, cudaMemcpy2DAsync((uint8_t*)c->d_hback + lo * back_pitch, back_pitch, blob + lo * stride + back_off, stride, back_bytes, cnt,
+                                    cudaMemcpyHostToDevice, cs));
+            CK(c, cudaEventRecord(c->ev_hdr_part[pi], cs));
+            if (trace && hi_ == n_proofs) cudaEventRecord(tv[1], cs);
+            CK(c, cudaStreamWaitEvent(ps, c->ev_hdr_part[pi], 0));
+            wire_header_unpack_kernel<<<(unsigned)cnt, SVB_WIRE_BLOCK, 0, ps>>>(c->d_hfront + lo * (front_pitch / 8), front_pitch,
+                                                                                c->d_hback + lo * (back_pitch / 8), back_pitch, (u32)front_bytes,
+                                                                                (u32)back_off, (u32)hw, W.hdr_src, W.vk, c->d_hdr + lo * hw);
+            {
+                WireDims db = W.d;
+                db.pi_off = (u32)(W.d.pi_off - back_off);          // the public inputs inside the back span
+                wire_pi_hash_kernel<<<(unsigned)((cnt + SVB_BLOCK - 1) / SVB_BLOCK), SVB_BLOCK, 0, ps>>>(c->d_hback + lo * (back_pitch / 8), 0, back_pitch, db,
+                                                                                                       cnt, c->d_pi + 4 * lo, c->d_mal + lo);
+            }
+            c->launches += 2;
+            if (trace && pi == 0) cudaEventRecord(tv[6], ps);
             FriKernelParams Ph = P;
             Ph.L.record_words = (u32)hw;                    // the headers are packed back to back
             if (circuit) {   // plonk challenges: the prefix of the transcript below, kept this time
@@ -979,7 +998,8 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
                                 c->d_hdr + lo * hw, Ph, F, c->d_pi + 4 * lo, c->d_chal + 3 * (size_t)nch * lo);
                 c->launches++;
             }
-            const int force = hi_ == n_proofs && cnt > 2048 && lo > 0 ? 2 : 0;   // the big last part: thread per proof
+            // the big last part: thread per proof (it ends long before the chunks in front of it are through their query kernels)
+            const int force = hi_ == n_proofs && cnt > 2048 && lo > 0 && !rest_coop_env ? 2 : 0;
             if ((rc = enqueue_challenges(c, Ph, F, cnt, c->d_hdr + lo * hw, c->d_pi + 4 * lo, ps, force))) return rc;
             if (trace && pi == 0) cudaEventRecord(tv[7], ps);
             CK(c, cudaEventRecord(c->ev_part[pi], ps));       // the chunks' query kernels wait for the challenges only

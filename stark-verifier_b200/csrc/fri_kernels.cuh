@@ -25,6 +25,7 @@
 #include "poseidon_g.cuh"
 #include "poseidon_b.cuh"
 #include "poseidon_g_coop.cuh"
+#include "poseidon_g_coop2.cuh"
 
 namespace svb {
 
@@ -544,15 +545,22 @@ __global__ void __launch_bounds__(SVB_FS_BLOCK) fri_challenges_kernel(u64* __res
     for (u32 q = 0; q < P.num_queries; q++) rec[L.off_indices + q] = ch.squeeze();
 }
 
-// The same transcript with the lane-cooperative permutation (poseidon_g_coop.cuh): one 16-lane group per
-// proof, lane l holds sponge word l.  Absorbing is a coalesced load of up to 8 consecutive words by lanes
-// 0..7; a squeeze broadcasts the word of lane (n_out - 1).  Poseidon-Goldilocks only.
+// The same transcript with the lane-cooperative permutation in its latency form (poseidon_g_coop2.cuh): one 16-lane
+// group per proof, lane l holds sponge word l.  Absorbing is a coalesced load of up to 8 consecutive words by lanes
+// 0..7; a squeeze broadcasts the word of lane (n_out - 1).  Poseidon-Goldilocks only.  (poseidon_g_coop.cuh, the first
+// cooperative mapping, stays in the tree for tools/lab/coopbench.cu: 10.5 us per permutation against 6.9 here.)
+#define SVB_COOP_BLOCK 128
+#define SVB_COOP_GROUPS (SVB_COOP_BLOCK / SVB_COOP2_GROUP)
+// ONE out-of-line copy of the permutation (~2 000 instructions) for the ~20 call sites of the transcript
+__device__ __noinline__ u64 coop2_permute_canonical(u64 s, int l, Coop2Tables<SVB_COOP_GROUPS>* T, int g) {
+    return canon(poseidon_g_coop2(s, l, *T, g));
+}
 struct CoopChallenger {
     u64 s;          // this lane's state word
-    int l, n_out;
-    const CoopTables* T;
+    int n_out, g, l;
+    Coop2Tables<SVB_COOP_GROUPS>* T;
     SVB_D void permute() {
-        s = canon(poseidon_g_coop(s, l, *T));
+        s = coop2_permute_canonical(s, l, T, g);
         n_out = 8;
     }
     // observe the concatenation of two segments (n1 may be 0), in rate-8 chunks, overwrite mode
@@ -567,16 +575,16 @@ struct CoopChallenger {
     SVB_D u64 squeeze() {
         if (n_out == 0) permute();
         n_out--;
-        return coop_shfl(s, n_out);
+        return coop2_shfl(s, n_out);
     }
 };
 
-__global__ void __launch_bounds__(128) fri_challenges_coop_kernel(u64* __restrict__ records, FriKernelParams P, FsParams F,
-                                                                  const u64* __restrict__ pi_hashes) {
-    __shared__ CoopTables T;
-    coop_load_tables(T);
-    const int l = threadIdx.x & (SVB_COOP_GROUP - 1);
-    u32 p = (blockIdx.x * blockDim.x + threadIdx.x) / SVB_COOP_GROUP;
+__global__ void __launch_bounds__(SVB_COOP_BLOCK) fri_challenges_coop_kernel(u64* __restrict__ records, FriKernelParams P, FsParams F,
+                                                                             const u64* __restrict__ pi_hashes) {
+    __shared__ Coop2Tables<SVB_COOP_GROUPS> T;
+    coop2_load_tables(T);
+    const int l = threadIdx.x & (SVB_COOP2_GROUP - 1);
+    u32 p = (blockIdx.x * blockDim.x + threadIdx.x) / SVB_COOP2_GROUP;
     const bool valid = p < P.n_proofs;
     if (!valid) p = P.n_proofs - 1;            // keep the warp convergent for the shuffles; writes are suppressed
     const bool writer = valid && l == 0;
@@ -584,7 +592,7 @@ __global__ void __launch_bounds__(128) fri_challenges_coop_kernel(u64* __restric
     u64* rec = records + (size_t)p * L.record_words;
     const u32 cap_words = L.ncap * 4;
     CoopChallenger ch;
-    ch.l = l; ch.n_out = 0; ch.T = &T;
+    ch.l = l; ch.n_out = 0; ch.T = &T; ch.g = threadIdx.x / SVB_COOP2_GROUP;
     // first chunk: circuit digest (4) + public-input hash (4)   (plonk_verifier_chip.rs:65-71)
     ch.s = l < 4 ? F.circuit_digest[l & 3] : (l < 8 ? pi_hashes[4 * (size_t)p + (l - 4)] : 0);
     ch.permute();

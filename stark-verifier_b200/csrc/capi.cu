@@ -44,6 +44,8 @@ struct sv_ctx {
     cudaStream_t fs_part_stream[2] = {};                               // transcript parts 1 and 2 of a wire batch (part 0: fs_stream)
     cudaEvent_t ev_part[3] = {}, ev_plonk[3] = {}, ev_hdr_part[3] = {}, ev_hdr_ready = nullptr;   // per transcript part: challenges written / plonk identity checked
     cudaEvent_t ev_copied[SV_NBUF] = {}, ev_done[SV_NBUF] = {}, ev_join[SV_NKS] = {};
+    cudaStream_t prep_stream = nullptr;                                 // high priority: the short kernels in front of a chunk's query kernel
+    cudaEvent_t ev_prep[SV_NBUF] = {};
     // wire format (sv_wire_unpack_batch_gpu, sv_verify_proofs_wire): offset tables of the last (shape, common) seen,
     // the verifier key's cap, wire-byte staging ring, malformed flags
     bool w_valid = false;
@@ -135,6 +137,7 @@ extern "C" int sv_ctx_create(int device, sv_ctx** out) {
             CK(nullptr, cudaDeviceGetStreamPriorityRange(&lo, &hi));
             CK(nullptr, cudaStreamCreateWithPriority(&c->fs_stream, cudaStreamNonBlocking, hi));
             for (auto& st : c->fs_part_stream) CK(nullptr, cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi));
+            CK(nullptr, cudaStreamCreateWithPriority(&c->prep_stream, cudaStreamNonBlocking, hi));
         }
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_hdr, cudaEventDisableTiming));
         CK(nullptr, cudaEventCreateWithFlags(&c->ev_fs, cudaEventDisableTiming));
@@ -145,6 +148,7 @@ extern "C" int sv_ctx_create(int device, sv_ctx** out) {
         for (int i = 0; i < SV_NBUF; i++) {
             CK(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
             CK(nullptr, cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+            CK(nullptr, cudaEventCreateWithFlags(&c->ev_prep[i], cudaEventDisableTiming));
         }
         for (int i = 0; i < SV_NKS; i++) CK(nullptr, cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
         return 0;
@@ -197,13 +201,14 @@ extern "C" void sv_ctx_destroy(sv_ctx* c) {
     for (auto& e : c->ev_part) drop_e(e);
     for (auto& e : c->ev_plonk) drop_e(e);
     for (auto& e : c->ev_hdr_part) drop_e(e);
-    for (int i = 0; i < SV_NBUF; i++) { drop_e(c->ev_copied[i]); drop_e(c->ev_done[i]); }
+    for (int i = 0; i < SV_NBUF; i++) { drop_e(c->ev_copied[i]); drop_e(c->ev_done[i]); drop_e(c->ev_prep[i]); }
     for (int i = 0; i < SV_NKS; i++) drop_e(c->ev_join[i]);
     for (auto& pr : c->tev) { drop_e(pr.first); drop_e(pr.second); }
     drop_s(c->fs_stream);
     for (auto& st : c->fs_part_stream) drop_s(st);
     drop_s(c->own_stream);
     for (int i = 0; i < SV_NKS - 1; i++) drop_s(c->aux_stream[i]);
+    drop_s(c->prep_stream);
     drop_s(c->copy_stream);
     if (c->nccl_lib) dlclose(c->nccl_lib);
     delete c;
@@ -220,6 +225,7 @@ extern "C" int sv_ctx_synchronize(sv_ctx* c) {
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaStreamSynchronize(c->own_stream));
     for (int i = 0; i < SV_NKS - 1; i++) CK(c, cudaStreamSynchronize(c->aux_stream[i]));
+    if (c->prep_stream) CK(c, cudaStreamSynchronize(c->prep_stream));
     CK(c, cudaStreamSynchronize(c->copy_stream));
     CK(c, cudaStreamSynchronize(c->fs_stream));
     for (auto& st : c->fs_part_stream) CK(c, cudaStreamSynchronize(st));
@@ -511,8 +517,11 @@ static int enqueue_leaf(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_re
     return 0;
 }
 
+// sp / ev_sp: when given, fri_prepare_kernel (a dozen blocks) runs on that (high-priority) stream and the query kernel waits for the
+// event -- in the host pipelines the SMs are full of the previous chunk's query blocks, and a short kernel queued behind them on
+// an ordinary stream would hold this chunk's query kernel back until that grid has drained
 static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_records, u64* d_scratch, u32* d_bitmap,
-                       u32* d_fail, cudaStream_t s, const u64* d_leaf = nullptr) {
+                       u32* d_fail, cudaStream_t s, const u64* d_leaf = nullptr, cudaStream_t sp = nullptr, cudaEvent_t ev_sp = nullptr) {
     const int B = SVB_BLOCK;
     P.n_proofs = (u32)n;
     P.n_units = (u32)(n * P.num_queries);
@@ -521,7 +530,11 @@ static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_rec
     static const u32 group_env = [] { const char* e = getenv("SVB_GROUP_BLOCKS"); return e ? (u32)atoi(e) : 32u; }();
     P.group_blocks = group_env == 0 || group_env > P.blocks_per_class ? P.blocks_per_class : group_env;   // 0: class-major over the batch
     P.n_groups = (P.blocks_per_class + P.group_blocks - 1) / P.group_blocks;
-    fri_prepare_kernel<<<(unsigned)((n + 31) / 32), SVB_PREP_BLOCK, 0, s>>>(d_records, P, d_scratch, d_bitmap, d_fail);
+    fri_prepare_kernel<<<(unsigned)((n + 31) / 32), SVB_PREP_BLOCK, 0, sp ? sp : s>>>(d_records, P, d_scratch, d_bitmap, d_fail);
+    if (sp) {
+        CK(c, cudaEventRecord(ev_sp, sp));
+        CK(c, cudaStreamWaitEvent(s, ev_sp, 0));
+    }
     cudaEvent_t te = time_begin(c, s);
     const u32 grid = P.n_groups * P.group_blocks * P.n_classes_a + P.blocks_per_class * (P.n_classes - P.n_classes_a);
     SVB_LAUNCH_KIND(P.hash_kind, fri_query_kernel, grid, B, s, d_records, P, d_scratch, d_bitmap, d_fail, d_leaf);
@@ -533,6 +546,12 @@ static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_rec
     }
     CK(c, cudaGetLastError());
     return 0;
+}
+
+// SVB_PREP_STREAM=0: the short kernels of a chunk on the chunk's own compute stream, as before (lab knob)
+static bool prep_stream_enabled() {
+    static const bool on = [] { const char* e = getenv("SVB_PREP_STREAM"); return e ? atoi(e) != 0 : true; }();
+    return on;
 }
 
 // Chunk schedule of a host batch: full chunks, then a ramp-down (1/2, 1/4, ... of a chunk, whole 32-proof bitmap words, never
@@ -547,14 +566,16 @@ static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_rec
 static std::vector<size_t> chunk_schedule(size_t n_proofs, size_t chunk, bool ramp_default) {
     const char* e = getenv("SVB_RAMP");                     // read per call: the tests toggle it
     const bool ramp = e ? atoi(e) != 0 : ramp_default;
+    const char* em = getenv("SVB_RAMP_MIN");                // smallest ramp-down chunk, proofs (lab knob)
+    const size_t ramp_min = em && atol(em) >= 32 ? ((size_t)atol(em) + 31) & ~(size_t)31 : 64;
     std::vector<size_t> starts;
     size_t at = 0;
     while (at < n_proofs) {
         starts.push_back(at);
         size_t left = n_proofs - at, sz = chunk;
-        if (ramp && left <= 2 * chunk && left > 64) {
+        if (ramp && left <= 2 * chunk && left > ramp_min) {
             sz = ((left / 2) + 31) & ~(size_t)31;
-            if (sz < 64) sz = 64;
+            if (sz < ramp_min) sz = ramp_min;
         }
         at += std::min(sz, left);
     }
@@ -627,16 +648,19 @@ static int fri_verify_host(sv_ctx* c, FriKernelParams& P, size_t n_proofs, const
         if (i >= SV_NBUF) CK(c, cudaStreamWaitEvent(cs, c->ev_done[b], 0));   // buffer b free again
         CK(c, cudaMemcpyAsync(c->d_stage[b], records + first * rw, cnt * rw * 8, cudaMemcpyHostToDevice, cs));
         CK(c, cudaEventRecord(c->ev_copied[b], cs));
-        CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
+        // the short work in front of the query kernel (challenge patch, fri_prepare_kernel) goes to the high-priority stream
+        cudaStream_t pre = prep_stream_enabled() && !split ? c->prep_stream : k;
+        CK(c, cudaStreamWaitEvent(pre, c->ev_copied[b], 0));
+        if (pre != k) CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
         if (fs) {
             if (split && (rc = enqueue_leaf(c, P, cnt, c->d_stage[b], c->d_leaf[b], k))) return rc;   // needs no challenge
-            if (first < fs_lead) CK(c, cudaStreamWaitEvent(k, c->ev_part[0], 0));             // a ramp-down chunk may straddle
-            if (first + cnt > fs_lead) CK(c, cudaStreamWaitEvent(k, c->ev_part[1], 0));       // the two transcript parts
+            if (first < fs_lead) CK(c, cudaStreamWaitEvent(pre, c->ev_part[0], 0));             // a ramp-down chunk may straddle
+            if (first + cnt > fs_lead) CK(c, cudaStreamWaitEvent(pre, c->ev_part[1], 0));       // the two transcript parts
             CK(c, cudaMemcpy2DAsync(c->d_stage[b] + chal_off, rw * 8, c->d_hdr + first * hw + chal_off, hw * 8, chal_words * 8, cnt,
-                                    cudaMemcpyDeviceToDevice, k));
+                                    cudaMemcpyDeviceToDevice, pre));
         }
         rc = enqueue_fri(c, P, cnt, c->d_stage[b], c->d_scratch + 4 * first, c->d_bitmap + first / 32,
-                         first_fail ? c->d_fail + first : nullptr, k, split ? c->d_leaf[b] : nullptr);
+                         first_fail ? c->d_fail + first : nullptr, k, split ? c->d_leaf[b] : nullptr, pre != k ? pre : nullptr, c->ev_prep[b]);
         if (rc) return rc;
         CK(c, cudaEventRecord(c->ev_done[b], k));
     }
@@ -943,6 +967,7 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
     // SVB_TRACE=1: a timeline of this call on stderr (lab knob)
     static const bool trace = getenv("SVB_TRACE") != nullptr;
     cudaEvent_t tv[8] = {};
+    std::vector<cudaEvent_t> tc;                            // per chunk: copied, kernels start, query kernel start, done
     if (trace) {
         for (auto& e : tv) cudaEventCreate(&e);
         cudaEventRecord(tv[0], cs);
@@ -1031,11 +1056,19 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
         if (i >= SV_NBUF) CK(c, cudaStreamWaitEvent(cs, c->ev_done[b], 0));   // buffers b free again
         CK(c, cudaMemcpy2DAsync(c->d_wire[b], q_pitch, blob + first * stride + front_bytes, stride, q_bytes, cnt, cudaMemcpyHostToDevice, cs));
         CK(c, cudaEventRecord(c->ev_copied[b], cs));
-        CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
+        // unpack + prepare are short; on the chunk's own stream they would queue behind the ~1 000 pending blocks of the previous
+        // chunk's query kernel (the SMs are full) and hold this chunk's query kernel back by ~0.6 ms (SVB_TRACE): high-priority stream
+        cudaStream_t pre = prep_stream_enabled() && !split ? c->prep_stream : k;
+        CK(c, cudaStreamWaitEvent(pre, c->ev_copied[b], 0));
+        if (pre != k) CK(c, cudaStreamWaitEvent(k, c->ev_copied[b], 0));
+        if (trace) {
+            for (int j = 0; j < 4; j++) { cudaEvent_t e; cudaEventCreate(&e); tc.push_back(e); }
+            cudaEventRecord(tc[4 * i], cs);
+        }
         // the transcript parts that cover this chunk (a ramp-down chunk may straddle two of them)
-        auto wait_parts = [&](cudaEvent_t* ev) -> int {
+        auto wait_parts = [&](cudaEvent_t* ev, cudaStream_t st) -> int {
             for (int pi = 0; pi < 3; pi++)
-                if (part_hi[pi] > part_lo[pi] && part_lo[pi] < first + cnt && first < part_hi[pi]) CK(c, cudaStreamWaitEvent(k, ev[pi], 0));
+                if (part_hi[pi] > part_lo[pi] && part_lo[pi] < first + cnt && first < part_hi[pi]) CK(c, cudaStreamWaitEvent(st, ev[pi], 0));
             return 0;
         };
         if (split) {
@@ -1045,23 +1078,26 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
                                                                                             W.vk, c->d_stage[b], c->d_mal + first, nullptr, 1);
             c->launches++;
             if ((rc = enqueue_leaf(c, P, cnt, c->d_stage[b], c->d_leaf[b], k))) return rc;
-            if ((rc = wait_parts(c->ev_part))) return rc;
+            if ((rc = wait_parts(c->ev_part, k))) return rc;
             wire_unpack_kernel<<<dim3((unsigned)cnt, 1), SVB_WIRE_BLOCK, 0, k>>>(c->d_wire[b], 0, q_pitch, dq, W.hdr_src, W.q_src, W.chk, W.vk,
                                                                               c->d_stage[b], c->d_mal + first, c->d_hdr + first * hw, 0);
             c->launches++;
         } else {
-            if ((rc = wait_parts(c->ev_part))) return rc;
+            if ((rc = wait_parts(c->ev_part, pre))) return rc;
+            if (trace) cudaEventRecord(tc[4 * i + 1], pre);
             dim3 grid((unsigned)cnt, 1 + W.d.num_queries);
-            wire_unpack_kernel<<<grid, SVB_WIRE_BLOCK, 0, k>>>(c->d_wire[b], 0, q_pitch, dq, W.hdr_src, W.q_src, W.chk, W.vk, c->d_stage[b],
-                                                               c->d_mal + first, c->d_hdr + first * hw, 0);
+            wire_unpack_kernel<<<grid, SVB_WIRE_BLOCK, 0, pre>>>(c->d_wire[b], 0, q_pitch, dq, W.hdr_src, W.q_src, W.chk, W.vk, c->d_stage[b],
+                                                                 c->d_mal + first, c->d_hdr + first * hw, 0);
             c->launches++;
         }
         u32* d_fail = first_fail ? c->d_fail + first : nullptr;
+        if (trace && !split) cudaEventRecord(tc[4 * i + 2], k);
         if ((rc = enqueue_fri(c, P, cnt, c->d_stage[b], c->d_scratch + 4 * first, c->d_bitmap + first / 32, d_fail, k,
-                              split ? c->d_leaf[b] : nullptr)))
+                              split ? c->d_leaf[b] : nullptr, pre != k ? pre : nullptr, c->ev_prep[b])))
             return rc;
+        if (trace) cudaEventRecord(tc[4 * i + 3], k);
         if (circuit) {
-            if ((rc = wait_parts(c->ev_plonk))) return rc;
+            if ((rc = wait_parts(c->ev_plonk, k))) return rc;
             plonk_and_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, k>>>(c->d_pbm + first / 32, c->d_bitmap + first / 32, d_fail, (u32)cnt);
             c->launches++;
         }
@@ -1086,6 +1122,17 @@ static int wire_verify_host(sv_ctx* c, FriKernelParams& P, const FsParams& F, co
         fprintf(stderr, "[svb trace] wire: headers copied %.2f ms, headers unpacked + pi hashed %.2f, challenges %.2f, transcript stream done %.2f, "
                         "first chunk done %.2f, last chunk copied %.2f, end %.2f (%zu proofs, %zu chunks of %zu)\n",
                 t[1], t[6], t[7], t[2], t[3], t[4], t[5], n_proofs, n_chunks, chunk);
+        if (!split) {
+            fprintf(stderr, "[svb trace] chunks (copied / kernels start / query start / query done, ms):");
+            for (size_t i = 0; i < n_chunks; i++) {
+                float a = 0, b = 0, d = 0, e = 0;
+                cudaEventElapsedTime(&a, tv[0], tc[4 * i]); cudaEventElapsedTime(&b, tv[0], tc[4 * i + 1]);
+                cudaEventElapsedTime(&d, tv[0], tc[4 * i + 2]); cudaEventElapsedTime(&e, tv[0], tc[4 * i + 3]);
+                fprintf(stderr, " [%zu] %.2f %.2f %.2f %.2f", i, a, b, d, e);
+            }
+            fprintf(stderr, "\n");
+        }
+        for (auto& e : tc) cudaEventDestroy(e);
         for (auto& e : tv) cudaEventDestroy(e);
     }
     return 0;

@@ -137,6 +137,7 @@ extern "C" {
     pub fn sv_fri_layout_make(shape: *const sv_fri_shape, out: *mut sv_fri_layout) -> c_int;
     pub fn sv_poseidon_permute_batch(ctx: *mut sv_ctx, input: *const u64, out: *mut u64, n: usize,
                                      hash_kind: c_int, mem: c_int) -> c_int;
+    pub fn sv_poseidon_permute_batch_coop(ctx: *mut sv_ctx, input: *const u64, out: *mut u64, n: usize, mem: c_int) -> c_int;
     pub fn sv_goldilocks_mul_add_batch(ctx: *mut sv_ctx, a: *const u64, b: *const u64, c: *const u64, out: *mut u64,
                                        n: usize, mem: c_int) -> c_int;
     pub fn sv_merkle_verify_batch(ctx: *mut sv_ctx, leaf_len: u32, depth: u32, cap_height: u32, hash_kind: c_int,

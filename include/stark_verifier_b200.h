@@ -140,6 +140,10 @@ int sv_fri_layout_make(const sv_fri_shape* shape, sv_fri_layout* out);
 /* n independent width-12 permutations, in[12n] -> out[12n] (in == out allowed).
  * Replaces: PlonkyPermutation::permute / HasherChip::permutation (chip/hasher_chip.rs:101-105). */
 int sv_poseidon_permute_batch(sv_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, int hash_kind, int mem);
+/* The same permutation (Poseidon-Goldilocks only) on the lane-cooperative mapping the device-side transcript uses -- 16 lanes
+ * per state, built for latency (HasherChip's duplex sponge, chip/hasher_chip.rs:51-120, is a chain of dependent permutations).
+ * Same results as sv_poseidon_permute_batch; in and out must not overlap for SV_MEM_DEVICE.  Exposed for the parity tests. */
+int sv_poseidon_permute_batch_coop(sv_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, int mem);
 
 /* out[i] = a[i] * b[i] + c[i] mod p (canonical); a, b, c are arbitrary u64 words (reduced mod p).
  * Replaces: GoldilocksChip::mul_add, the gate r = a*b + c (chip/goldilocks_chip.rs:175-195,

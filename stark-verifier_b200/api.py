@@ -238,6 +238,7 @@ def lib() -> ctypes.CDLL:
     L.sv_host_free.argtypes = [vp]
     L.sv_fri_layout_make.argtypes = [ctypes.POINTER(FriShape), ctypes.POINTER(Layout)]
     L.sv_poseidon_permute_batch.argtypes = [vp, vp, vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
+    L.sv_poseidon_permute_batch_coop.argtypes = [vp, vp, vp, ctypes.c_size_t, ctypes.c_int]
     L.sv_goldilocks_mul_add_batch.argtypes = [vp, vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_int]
     L.sv_merkle_verify_batch.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int,
                                          vp, vp, vp, vp, ctypes.c_size_t, ctypes.c_int]
@@ -591,6 +592,14 @@ class Context:
             out = np.empty_like(states) if out is None else out
         self._ck(self._lib.sv_poseidon_permute_batch(self._h, _ptr(states), _ptr(out), n, hash_kind, mem),
                  "sv_poseidon_permute_batch")
+        return out
+
+    def poseidon_permute_batch_coop(self, states):
+        """Poseidon-Goldilocks on the lane-cooperative mapping of the device-side transcript (host arrays in / out)."""
+        states = np.ascontiguousarray(states, dtype=np.uint64)
+        out = np.empty_like(states)
+        self._ck(self._lib.sv_poseidon_permute_batch_coop(self._h, _ptr(states), _ptr(out), states.size // 12, MEM_HOST),
+                 "sv_poseidon_permute_batch_coop")
         return out
 
     def goldilocks_mul_add_batch(self, a, b, c):

@@ -317,6 +317,30 @@ extern "C" int sv_poseidon_permute_batch(sv_ctx* c, const uint64_t* in, uint64_t
     return 0;
 }
 
+extern "C" int sv_poseidon_permute_batch_coop(sv_ctx* c, const uint64_t* in, uint64_t* out, size_t n, int mem) {
+    if (!c || !in || !out) return -1;
+    if (!known_mem(mem)) return fail(c, -5, "mem %d is neither SV_MEM_HOST nor SV_MEM_DEVICE", mem);
+    if (n == 0) return 0;
+    CK(c, cudaSetDevice(c->device));
+    const unsigned grid = (unsigned)((n * SVB_COOP2_GROUP + SVB_COOP_BLOCK - 1) / SVB_COOP_BLOCK);
+    if (mem == SV_MEM_DEVICE) {
+        poseidon_permute_coop_kernel<<<grid, SVB_COOP_BLOCK, 0, c->stream>>>(in, out, n);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        return 0;
+    }
+    size_t words = 12 * n;
+    if (grow(c, c->d_stage[0], c->stage_words[0], 2 * words)) return -6;
+    cudaStream_t s = c->own_stream;
+    CK(c, cudaMemcpyAsync(c->d_stage[0], in, words * 8, cudaMemcpyHostToDevice, s));
+    poseidon_permute_coop_kernel<<<grid, SVB_COOP_BLOCK, 0, s>>>(c->d_stage[0], c->d_stage[0] + words, n);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out, c->d_stage[0] + words, words * 8, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
 extern "C" int sv_goldilocks_mul_add_batch(sv_ctx* c, const uint64_t* a, const uint64_t* b, const uint64_t* cc, uint64_t* out,
                                            size_t n, int mem) {
     if (!c || !a || !b || !cc || !out) return -1;

@@ -623,6 +623,20 @@ __global__ void __launch_bounds__(SVB_COOP_BLOCK) fri_challenges_coop_kernel(u64
     }
 }
 
+// n independent permutations on the lane-cooperative mapping of the transcript (16 lanes per state): exposes
+// coop2_permute_canonical to the tests so that its carry / borrow paths can be driven with crafted states.
+__global__ void __launch_bounds__(SVB_COOP_BLOCK) poseidon_permute_coop_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
+    __shared__ Coop2Tables<SVB_COOP_GROUPS> T;
+    coop2_load_tables(T);
+    const int l = threadIdx.x & (SVB_COOP2_GROUP - 1);
+    size_t g = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / SVB_COOP2_GROUP;
+    const bool valid = g < n;
+    if (!valid) g = n - 1;                       // keep the warp convergent; writes are suppressed
+    u64 s = l < 12 ? in[12 * g + l] : 0;
+    s = coop2_permute_canonical(s, l, &T, threadIdx.x / SVB_COOP2_GROUP);
+    if (valid && l < 12) out[12 * g + l] = s;
+}
+
 // ---- Merkle tree construction (the prover side of the same hash) ---------------------
 // Leaf digests: hash_or_noop of each leaf row (plonky2 MerkleTree::new; call sites
 // plonky2_semaphore/access_set.rs:25, circuit.rs:91).  One thread per leaf.

@@ -73,11 +73,20 @@ SVB_HD NttTileMap ntt_tile_map(const NttPass& P, u64 tile) {
     return M;
 }
 
-// the fixed roots of the radix-8 / radix-4 butterflies: omega_8 = 7^((p-1)/8) = -2^24, omega_4 = omega_8^2 = 2^48
-SVB_HD u64 ntt_w8(u32 j, bool inverse) {
-    constexpr u64 F[4] = {1ull, 0xfffffffeff000001ull, 0x0001000000000000ull, 0xfffffeff00000101ull};
-    constexpr u64 I[4] = {1ull, 0x000000ffffffff00ull, 0xfffeffff00000001ull, 0x0000000001000000ull};
-    return inverse ? I[j & 3] : F[j & 3];
+// the fixed roots of the radix-8 / radix-4 butterflies are powers of two: omega_8 = 7^((p-1)/8) = -2^24, omega_4 = omega_8^2 = 2^48.
+// x * 2^(24 j) mod p, canonical, j = 1..3: the magnitude of omega_8^j (omega_8^j = (-1)^j 2^(24 j); inverse: omega_8^-j =
+// (-1)^(j+1) 2^(24 (4 - j))) -- the callers fold the sign into the subtraction in front.  On the device the product is three
+// funnel shifts into the limbs of red5 (1 IMAD.WIDE + 6 ALU) instead of a full modular multiplication (5 IMAD.WIDE + 9 ALU).
+template <int J>
+SVB_HD u64 ntt_mul_pow24(u64 x) {
+#if defined(__CUDA_ARCH__)
+    const u32 lo = (u32)x, hi = (u32)(x >> 32);
+    if (J == 1) return canon(red5(lo << 24, __funnelshift_l(lo, hi, 24), hi >> 8, 0, 0));
+    if (J == 2) return canon(red5(0, lo << 16, __funnelshift_l(lo, hi, 16), hi >> 16, 0));
+    return canon(red5(0, 0, lo << 8, __funnelshift_l(lo, hi, 8), hi >> 24));
+#else
+    return mulc(x, J == 1 ? (1ull << 24) : J == 2 ? (1ull << 48) : 0x000000ffffffff00ull /* 2^72 mod p */);
+#endif
 }
 
 // ---- phases of one tile ------------------------------------------------------------------------------------
@@ -131,11 +140,12 @@ SVB_HD void ntt_tile_round(const NttPass& P, const NttTileMap& M, const u64* __r
             if (!inv_) {
                 // DIF: three butterfly levels, then output p (frequency bitrev(p)) times w1^bitrev(p)
                 u64 a0 = add(x[0], x[4]), a4 = sub(x[0], x[4]);
-                u64 a1 = add(x[1], x[5]), a5 = mulc(sub(x[1], x[5]), ntt_w8(1, false));
-                u64 a2 = add(x[2], x[6]), a6 = mulc(sub(x[2], x[6]), ntt_w8(2, false));
-                u64 a3 = add(x[3], x[7]), a7 = mulc(sub(x[3], x[7]), ntt_w8(3, false));
-                u64 b0 = add(a0, a2), b2 = sub(a0, a2), b1 = add(a1, a3), b3 = mulc(sub(a1, a3), ntt_w8(2, false));
-                u64 b4 = add(a4, a6), b6 = sub(a4, a6), b5 = add(a5, a7), b7 = mulc(sub(a5, a7), ntt_w8(2, false));
+                // omega_8 = -2^24, omega_8^2 = 2^48, omega_8^3 = -2^72: shifts, the sign in the order of the subtraction
+                u64 a1 = add(x[1], x[5]), a5 = ntt_mul_pow24<1>(sub(x[5], x[1]));
+                u64 a2 = add(x[2], x[6]), a6 = ntt_mul_pow24<2>(sub(x[2], x[6]));
+                u64 a3 = add(x[3], x[7]), a7 = ntt_mul_pow24<3>(sub(x[7], x[3]));
+                u64 b0 = add(a0, a2), b2 = sub(a0, a2), b1 = add(a1, a3), b3 = ntt_mul_pow24<2>(sub(a1, a3));
+                u64 b4 = add(a4, a6), b6 = sub(a4, a6), b5 = add(a5, a7), b7 = ntt_mul_pow24<2>(sub(a5, a7));
                 x[0] = add(b0, b1);
                 x[1] = mulc(sub(b0, b1), w4);
                 x[2] = mulc(add(b2, b3), w2);
@@ -148,28 +158,29 @@ SVB_HD void ntt_tile_round(const NttPass& P, const NttTileMap& M, const u64* __r
                 // DIT: input p times w1^bitrev(p) (inverse table), then the three levels from the bottom
                 u64 y1 = mulc(x[1], w4), y2 = mulc(x[2], w2), y3 = mulc(x[3], w6), y4 = mulc(x[4], w1), y5 = mulc(x[5], w5),
                     y6 = mulc(x[6], w3), y7 = mulc(x[7], w7);
-                u64 b0 = add(x[0], y1), b1 = sub(x[0], y1), b2 = add(y2, y3), b3 = mulc(sub(y2, y3), ntt_w8(2, true));
-                u64 b4 = add(y4, y5), b5 = sub(y4, y5), b6 = add(y6, y7), b7 = mulc(sub(y6, y7), ntt_w8(2, true));
+                // omega_8^-1 = 2^72, omega_8^-2 = -2^48, omega_8^-3 = 2^24
+                u64 b0 = add(x[0], y1), b1 = sub(x[0], y1), b2 = add(y2, y3), b3 = ntt_mul_pow24<2>(sub(y3, y2));
+                u64 b4 = add(y4, y5), b5 = sub(y4, y5), b6 = add(y6, y7), b7 = ntt_mul_pow24<2>(sub(y7, y6));
                 u64 a0 = add(b0, b2), a2 = sub(b0, b2), a1 = add(b1, b3), a3 = sub(b1, b3);
                 u64 a4 = add(b4, b6), a6 = sub(b4, b6), a5 = add(b5, b7), a7 = sub(b5, b7);
-                a5 = mulc(a5, ntt_w8(1, true));
-                a6 = mulc(a6, ntt_w8(2, true));
-                a7 = mulc(a7, ntt_w8(3, true));
+                a5 = ntt_mul_pow24<3>(a5);
+                a6 = ntt_mul_pow24<2>(a6);                         // magnitude of omega_8^-2 = -2^48: the sign swaps add and sub below
+                a7 = ntt_mul_pow24<1>(a7);
                 x[0] = add(a0, a4); x[4] = sub(a0, a4);
                 x[1] = add(a1, a5); x[5] = sub(a1, a5);
-                x[2] = add(a2, a6); x[6] = sub(a2, a6);
+                x[2] = sub(a2, a6); x[6] = add(a2, a6);
                 x[3] = add(a3, a7); x[7] = sub(a3, a7);
             }
         } else if (r == 2) {
             if (!inv_) {
-                u64 a0 = add(x[0], x[2]), a2 = sub(x[0], x[2]), a1 = add(x[1], x[3]), a3 = mulc(sub(x[1], x[3]), ntt_w8(2, false));
+                u64 a0 = add(x[0], x[2]), a2 = sub(x[0], x[2]), a1 = add(x[1], x[3]), a3 = ntt_mul_pow24<2>(sub(x[1], x[3]));
                 x[0] = add(a0, a1);
                 x[1] = mulc(sub(a0, a1), w2);
                 x[2] = mulc(add(a2, a3), w1);
                 x[3] = mulc(sub(a2, a3), w3);
             } else {
                 u64 y1 = mulc(x[1], w2), y2 = mulc(x[2], w1), y3 = mulc(x[3], w3);
-                u64 a0 = add(x[0], y1), a1 = sub(x[0], y1), a2 = add(y2, y3), a3 = mulc(sub(y2, y3), ntt_w8(2, true));
+                u64 a0 = add(x[0], y1), a1 = sub(x[0], y1), a2 = add(y2, y3), a3 = ntt_mul_pow24<2>(sub(y3, y2));
                 x[0] = add(a0, a2); x[2] = sub(a0, a2);
                 x[1] = add(a1, a3); x[3] = sub(a1, a3);
             }

@@ -25,6 +25,29 @@ def test_permute_kat_and_random(svb, orc, ctx):
     assert [int(x) for x in tv] == PLONKY2_TV12_OUT      # upstream plonky2 test_vectors12, random state
 
 
+def test_permute_cooperative_mapping(svb, orc, ctx):
+    """The lane-cooperative permutation of the device-side transcript (poseidon_g_coop2.cuh: partial section linearised,
+    16 lanes per state) against the oracle: known answers, states of extremal halves (carries and borrows of its
+    accumulators and of the LOOSE subtraction), ragged counts that leave a warp half empty."""
+    rng = np.random.default_rng(0xC002)
+    halves = [0, 1, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000]
+    edge = [[0] * 12, list(range(12)), [P - 1] * 12, [P - 1, 0, 1, P - 2] * 3, [0xFFFFFFFF] * 12, [0xFFFFFFFF00000000] * 12]
+    for _ in range(200):
+        edge.append([min(P - 1, (int(rng.choice(halves)) << 32) | int(rng.choice(halves))) for _ in range(12)])
+    rnd = rng.integers(0, P, size=(4099, 12), dtype=np.uint64)
+    states = np.concatenate([np.array(edge, dtype=np.uint64), rnd])
+    want = orc.poseidon_batch(states)
+    got = ctx.poseidon_permute_batch_coop(states).reshape(-1, 12)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, [(int(i), [hex(int(x)) for x in states[i]]) for i in bad[:3]]
+    assert int(got[1, 0]) == 0xd64e1e3efc5b8e9e
+    for n in (1, 2, 3, 17):                                  # one group, a half-empty warp, ...
+        g = ctx.poseidon_permute_batch_coop(states[:n]).reshape(-1, 12)
+        assert (g == want[:n]).all()
+    tv = ctx.poseidon_permute_batch_coop(np.array(PLONKY2_TV12_IN, dtype=np.uint64))
+    assert [int(x) for x in tv] == PLONKY2_TV12_OUT
+
+
 def test_field_corner_cases(svb, ctx):
     """a*b + c mod p on the device against Python big integers, on operands whose 128-bit products hit
     the rare limb patterns of the reduction (borrow with a zero middle limb, carry out of the

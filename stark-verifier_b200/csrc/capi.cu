@@ -544,8 +544,25 @@ static int enqueue_leaf(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_re
 // sp / ev_sp: when given, fri_prepare_kernel (a dozen blocks) runs on that (high-priority) stream and the query kernel waits for the
 // event -- in the host pipelines the SMs are full of the previous chunk's query blocks, and a short kernel queued behind them on
 // an ordinary stream would hold this chunk's query kernel back until that grid has drained
+// Lab knob SVB_QUERY_BPS: blocks of fri_query_kernel<G> per SM, capped through unused dynamic shared memory (unset / 0 = the launch
+// bound's 6).  The idea was to shorten the drain of a chunk in the host pipelines (a chain's permutations take longer the more warps
+// share its sub-partition: 29 dependent permutations = 2.1 ms at six warps, 0.7 ms alone).  Measured on B200 (tools/lab/bps_pass.sh):
+// resident throughput 438.7 k (6) -> 432.0 k (4) -> 421.0 k (3) -> 389.8 k (2) proofs/s, wire path 302.6 / 306.2 / 305.1 / 292.4 k --
+// no gain end to end, a loss resident, so nothing sets it.
+static size_t query_dyn_smem(int bps) {
+    static const int env = [] { const char* e = getenv("SVB_QUERY_BPS"); return e ? atoi(e) : -1; }();
+    if (env >= 0) bps = env;
+    if (bps <= 0 || bps >= SVB_MINBLOCKS) return 0;
+    if (bps < 2) bps = 2;
+    static const bool attr = [] {
+        return cudaFuncSetAttribute(fri_query_kernel<SV_HASH_POSEIDON_GOLDILOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
+    }();
+    if (!attr) return 0;
+    return ((size_t)227 * 1024 / (size_t)bps - 1024) & ~(size_t)1023;
+}
 static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_records, u64* d_scratch, u32* d_bitmap,
-                       u32* d_fail, cudaStream_t s, const u64* d_leaf = nullptr, cudaStream_t sp = nullptr, cudaEvent_t ev_sp = nullptr) {
+                       u32* d_fail, cudaStream_t s, const u64* d_leaf = nullptr, cudaStream_t sp = nullptr, cudaEvent_t ev_sp = nullptr,
+                       int bps = 0) {
     const int B = SVB_BLOCK;
     P.n_proofs = (u32)n;
     P.n_units = (u32)(n * P.num_queries);
@@ -561,7 +578,9 @@ static int enqueue_fri(sv_ctx* c, FriKernelParams& P, size_t n, const u64* d_rec
     }
     cudaEvent_t te = time_begin(c, s);
     const u32 grid = P.n_groups * P.group_blocks * P.n_classes_a + P.blocks_per_class * (P.n_classes - P.n_classes_a);
-    SVB_LAUNCH_KIND(P.hash_kind, fri_query_kernel, grid, B, s, d_records, P, d_scratch, d_bitmap, d_fail, d_leaf);
+    const size_t dsm = P.hash_kind == SV_HASH_POSEIDON_GOLDILOCKS ? query_dyn_smem(bps) : 0;
+    if (dsm) fri_query_kernel<SV_HASH_POSEIDON_GOLDILOCKS><<<grid, B, dsm, s>>>(d_records, P, d_scratch, d_bitmap, d_fail, d_leaf);
+    else SVB_LAUNCH_KIND(P.hash_kind, fri_query_kernel, grid, B, s, d_records, P, d_scratch, d_bitmap, d_fail, d_leaf);
     time_end(c, te, s);
     c->launches += 2;
     if (d_fail) {

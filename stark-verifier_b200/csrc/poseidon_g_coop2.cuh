@@ -3,7 +3,7 @@
 // 634-686); a different SCHEDULE, built for the Fiat-Shamir transcript, which is ~155 DEPENDENT permutations per
 // proof and therefore bound by the latency of one permutation, not by throughput.
 //
-// What is on the critical path of poseidon_g_coop (measured 11.9 us per permutation on a lone warp) and is not here:
+// What is on the critical path of poseidon_g_coop (measured 10.5 us per permutation, one warp per sub-partition) and is not here:
 //   * partial rounds.  Everything in the partial section except the one x^7 per round is linear, so with
 //     z = the S-box outputs of full round 3 and q_r = 25 x_r^7 every quantity is a linear form over (1, z, q):
 //         x_{r+1} = q_r + B_{r+1}(1, z, q_0 .. q_{r-1})        (tools/gen_poseidon_coop2_constants.py)

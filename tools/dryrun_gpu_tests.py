@@ -190,6 +190,11 @@ def main():
     ctx = MockCtx()
     fx = dict(svb=svb, orc=orc, ctx=ctx)
     skip = {"test_unpack_kernel_device_memory", "test_plonk_kernel_device_memory", "test_ntt_device_memory_and_many_polys"}  # need torch.cuda
+    if "--quick" in sys.argv:
+        # the CPU suite's budget: the four slowest dry runs (~110 s of mock verification) only run without --quick; every one of
+        # these test functions has been green on real B200s since round 2 (profiles/, GPUTEST records)
+        skip |= {"test_full_verifier_matches_cpu_side", "test_verify_proofs_wire_matches_oracle",
+                 "test_fri_kernel_accepts_python_prover_proofs", "test_fri_arity_small_shapes"}
     total = 0
     for mod in (t_gold, t_ar, t_pp, t_plonk, t_tr, t_full, t_wire):
         for name in sorted(n for n in dir(mod) if n.startswith("test_") and n not in skip):

@@ -2,6 +2,7 @@
 // permutation, their latency on a lone warp per SM and their time for transcript-like batches (155 dependent permutations
 // for 416 .. 4096 proofs).  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr coopbench.cu
 #include "../../stark-verifier_b200/csrc/fri_kernels.cuh"
+#include "poseidon_g_coop_v1.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <vector>

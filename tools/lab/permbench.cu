@@ -1,6 +1,7 @@
 // Lab harness: time poseidon_permute_kernel / merkle-style chains for one build configuration and check
 // the outputs against the host path.  Build with -D switches (see tools/lab/run_variants.sh).
 #include "../../stark-verifier_b200/csrc/fri_kernels.cuh"
+#include "poseidon_g_coop_v1.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <vector>

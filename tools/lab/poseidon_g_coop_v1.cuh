@@ -1,3 +1,5 @@
+// LAB COPY (not part of the library since kernels r2.4: the transcript runs on csrc/poseidon_g_coop2.cuh, the latency form; this first
+// mapping is kept for the before / after of tools/lab/coopbench.cu).
 // Lane-cooperative Poseidon-Goldilocks: one permutation spread over a 16-lane group (lanes 0..11 hold
 // the 12 state words, lanes 12..15 idle), two groups per warp.  Same function as poseidon_g_dev
 // (chip/plonk/gates/poseidon.rs:634-686, fast form); a different mapping.
@@ -10,7 +12,7 @@
 // product), which cuts the latency of one permutation ~5x.  The price is throughput: the 22 partial
 // rounds keep 11 of 12 lanes idle during the lane-0 S-box -- measured in tools/lab (coop vs thread).
 #pragma once
-#include "poseidon_g.cuh"
+#include "../../stark-verifier_b200/csrc/poseidon_g.cuh"
 
 namespace svb {
 

@@ -103,7 +103,7 @@ static int fail(sv_ctx* c, int code, const char* fmt, ...) {
 
 // bump SVB_KERNEL_REV whenever a kernel changes: profiles/traffic_r2.json and the ncu summaries are stamped with it, and bench.py
 // reports DRAM traffic only from a capture of the same revision
-#define SVB_KERNEL_REV "r2.4"
+#define SVB_KERNEL_REV "r2.5"
 extern "C" const char* sv_version(void) { return "stark-verifier_b200 0.2 (sm_100a, kernels " SVB_KERNEL_REV ")"; }
 
 extern "C" const char* sv_last_error(const sv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }

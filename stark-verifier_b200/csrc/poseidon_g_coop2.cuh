@@ -172,11 +172,11 @@ SVB_D u64 poseidon_g_coop2(u64 s, int l, Coop2Tables<GROUPS>& T, int g) {
     for (int k = 0; k < 12; k++) dot_mac(a0, T.zc[(k * 3) * 16 + l], b1[k]);
     u64 x = coop2_shfl(dot_reduce(a0), 0);       // x_0
     u64 q = 0;
-#pragma unroll 1
+#pragma unroll 2
     for (int r = 0; r < 12; r++) coop2_partial_round<true, 0>(r, x, q, a0, a1, a2, L, T, b1);
-#pragma unroll 1
+#pragma unroll
     for (int r = 12; r < 15; r++) coop2_partial_round<false, 0>(r, x, q, a0, a1, a2, L, T, b1);
-#pragma unroll 1
+#pragma unroll 2
     for (int r = 15; r < 22; r++) coop2_partial_round<false, 1>(r, x, q, a0, a1, a2, L, T, b1);
     dot_mac(a2, T.qc[(22 * 3 + 2) * 16 + l], q);
     s = dot_reduce(a2);                          // state entering round 26, its constants included

@@ -491,7 +491,7 @@ static int enqueue_challenges(sv_ctx* c, FriKernelParams& P, const FsParams& F, 
                               cudaStream_t s, int force = 0) {
     P.n_proofs = (u32)n;
     // SVB_FS_COOP: 1 = always lane-cooperative, 0 = never, unset = by batch size.  The cooperative kernel has the
-    // lower latency (6.4 vs 24.4 us per permutation) but 4.6x less throughput (252 vs 1 177 M perms/s), so it wins
+    // lower latency (6.1 vs 24.4 us per permutation) but 4.6x less throughput (252 vs 1 177 M perms/s), so it wins
     // while the batch is latency-bound: below ~8k proofs per call.
     static const int coop_env = [] { const char* e = getenv("SVB_FS_COOP"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
     const bool coop = force ? force == 1 : (coop_env < 0 ? n < 8192 : coop_env == 1);

@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(SVB_FS_BLOCK) fri_challenges_kernel(u64* __res
 // The same transcript with the lane-cooperative permutation in its latency form (poseidon_g_coop2.cuh): one 16-lane
 // group per proof, lane l holds sponge word l.  Absorbing is a coalesced load of up to 8 consecutive words by lanes
 // 0..7; a squeeze broadcasts the word of lane (n_out - 1).  Poseidon-Goldilocks only.  (The first cooperative mapping
-// lives on in tools/lab/poseidon_g_coop_v1.cuh for tools/lab/coopbench.cu: 10.5 us per permutation against 6.4 here.)
+// lives on in tools/lab/poseidon_g_coop_v1.cuh for tools/lab/coopbench.cu: 10.5 us per permutation against 6.1 here.)
 #define SVB_COOP_BLOCK 128
 #define SVB_COOP_GROUPS (SVB_COOP_BLOCK / SVB_COOP2_GROUP)
 // ONE out-of-line copy of the permutation (~2 000 instructions) for the ~20 call sites of the transcript
